@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Throughput bench for the stain-normalization hot path (BASELINE.json metric: megapixels/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--method hm|reinhard|macenko]
+
+Headline workload (N GPUs, weak scaling, 64 images per GPU): BASELINE.json configs[1] --
+HistogramMatching, uint8, 64x3x1024x1024 per GPU, reference mode.  One step = one transform of the
+batch: per-channel histogram of the (sharded) batch, [N>1: NCCL all-reduce of the 3x256 counts],
+LUT build, LUT remap.  The batch (201 MB per GPU) is larger than the 126 MB L2, so every step
+streams it from HBM; no L2 flush is needed between steps.
+
+Rank 0 prints ONE JSON line (see the keys in `main`).  `--impl reference` times the CPU oracle
+port (oracle/stainx_oracle.c, OpenMP, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+IMAGES_PER_GPU = 64
+H = W = 1024
+ALGO_BYTES_PER_PX = {"hm": 9.0, "reinhard": 36.0, "macenko": 24.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--method", default="hm", choices=["hm", "reinhard", "macenko"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-method side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.path = Path(tempfile.mkstemp(prefix="clocks_", suffix=".csv")[1])
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except (FileNotFoundError, OSError):
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, reasons, sm_max = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in self.path.read_text().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    sm_max = float(f[1])
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        finally:
+            self.path.unlink(missing_ok=True)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=sm_max, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_hm_sample(n_img: int, seconds: float) -> dict:
+    """Time the oracle's HistogramMatching transform on `n_img` uint8 1024x1024 images, repeated
+    for about `seconds`; returns MP/s (best repetition) and what was run."""
+    import numpy as np
+
+    from oracle import oracle as ox
+
+    rng = np.random.default_rng(43)
+    ref = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
+    src = rng.integers(0, 256, size=(n_img, 3, H, W), dtype=np.uint8)
+    ref_hist = ox.hm_fit(ref)
+    ox.hm_transform(src[:1], ref_hist)  # warm-up (page in, thread pool)
+    best, reps, t_end = None, 0, time.perf_counter() + seconds
+    while reps < 3 or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        ox.hm_transform(src, ref_hist)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        reps += 1
+        if reps >= 200:
+            break
+    mp = n_img * H * W / 1e6
+    return {"value": mp / best, "unit": "MP/s", "cores": ox.num_threads(), "kind": "port", "sample": f"oracle/stainx_oracle.c hm_transform on {n_img}x3x{H}x{W} uint8 (of the {IMAGES_PER_GPU}-image batch), best of {reps} reps"}
+
+
+def run_reference(args) -> None:
+    """`--impl reference`: the reference's CPU path (oracle port), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import oracle as ox
+
+    ox.build()
+    n_img = 8  # bounded sample of the 64-image batch; cost is linear in pixels
+    rng = np.random.default_rng(43)
+    ref = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
+    src = rng.integers(0, 256, size=(n_img, 3, H, W), dtype=np.uint8)
+    ref_hist = ox.hm_fit(ref)
+    for _ in range(max(args.warmup, 1)):
+        ox.hm_transform(src, ref_hist)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ox.hm_transform(src, ref_hist)
+    dt = time.perf_counter() - t0
+    mp_per_step = n_img * H * W / 1e6
+    value = mp_per_step * args.steps / dt
+    sample = f"{n_img}x3x{H}x{W} uint8 per step (bounded sample of the {IMAGES_PER_GPU}-image batch), oracle port with OpenMP"
+    line = {
+        "impl": "reference", "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "HistogramMatching uint8 64x3x1024x1024 per GPU, reference mode (BASELINE configs[1])", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": ox.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main() -> None:
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from stainx_b200 import HistogramMatching, Macenko, Reinhard, _native, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pg = "world" if distributed else None
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak_gbs, peak_src = peaks()
+    n_img = IMAGES_PER_GPU
+    mp_per_gpu = n_img * H * W / 1e6
+
+    # ---- inputs (synthetic, BASELINE convention: ref seed 42, src seed 43 + rank) ------------
+    g = torch.Generator(device=dev).manual_seed(42)
+    ref = (torch.rand((1, 3, H, W), device=dev, generator=g) * 255).round().to(torch.uint8)
+    g.manual_seed(43 + rank)
+    src = (torch.rand((n_img, 3, H, W), device=dev, generator=g) * 255).round().to(torch.uint8)
+
+    hm = HistogramMatching(device=dev, backend="torch_cuda", channel_axis=1, process_group=pg)
+    hm.fit_broadcast(ref, src=0) if distributed else hm.fit(ref)
+    ref_hist = torch.stack(hm._ref_histograms_256).contiguous()
+    reducer = hm._make_reducer()
+
+    # One step, written with the phase-level calls so that each kernel can be bracketed by events.
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks: list[tuple] = []
+
+    def step(record: bool):
+        e = [ev() for _ in range(4)] if record else None
+        if record:
+            e[0].record()
+        counts = ops.hm_hist(src)
+        if record:
+            e[1].record()
+        reducer.sum_(counts)
+        lut = ops.hm_build_lut(counts, -1 if distributed else src.numel() // 3, ops.hm_ref_cdf(ref_hist))
+        if record:
+            e[2].record()
+        out = ops.hm_apply(src, lut)
+        if record:
+            e[3].record()
+            marks.append(tuple(e))
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _native.kernel_launches()
+    t_start, t_stop = ev(), ev()
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        step(True)
+    t_stop.record()
+    barrier()
+    elapsed_ms = max_over_ranks(t_start.elapsed_time(t_stop))
+    launches = _native.kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    hist_ms = sum(m[0].elapsed_time(m[1]) for m in marks) / len(marks)
+    lut_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks)
+    apply_ms = sum(m[2].elapsed_time(m[3]) for m in marks) / len(marks)
+    ms_per_step = elapsed_ms / args.steps
+    value = mp_per_gpu * world / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes / live CUDA-event time) ----------
+    px = n_img * H * W
+    kernels = {
+        "hm::hist_u8_planar_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
+        "hm::apply_u8_planar_kernel": {"algo_bytes": 6.0 * px, "ms": apply_ms},
+    }
+    for k in kernels.values():
+        k["gbs"] = k["algo_bytes"] / (k["ms"] / 1e3) / 1e9
+        k["frac"] = k["gbs"] / peak_gbs
+    dom_name = max(kernels, key=lambda k: kernels[k]["ms"])
+    dom = kernels[dom_name]
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "step": {"algo_bytes": ALGO_BYTES_PER_PX["hm"] * px, "gbs": ALGO_BYTES_PER_PX["hm"] * px / (ms_per_step / 1e3) / 1e9, "frac": ALGO_BYTES_PER_PX["hm"] * px / (ms_per_step / 1e3) / 1e9 / peak_gbs},
+                "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "frac": round(v["frac"], 4)} for k, v in kernels.items()}, "lut_and_allreduce_ms": round(lut_ms, 4)}
+    traffic_file = ROOT / "profiles" / "traffic.json"  # per-launch dram bytes from the last ncu --set full capture
+    if traffic_file.exists():
+        try:
+            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name)
+        except Exception:
+            pass
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ---------------------
+    host_in = torch.empty((n_img, 3, H, W), dtype=torch.uint8).pin_memory()
+    host_in.copy_(src)
+    host_out = torch.empty((n_img, 3, H, W), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        out = hm.transform(host_in)          # the call a user makes: H2D inside, kernels, result on device
+        host_out.copy_(out, non_blocking=True)  # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+    e2e = {"value": mp_per_gpu * world / (e2e_ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": host_in.numel(), "d2h_bytes_per_step": host_out.numel(), "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "HistogramMatching(backend='torch_cuda').transform(pinned host uint8) + D2H copy of the result"}
+
+    # ---- side measurements: the other two methods (informative; N=1 only) ---------------------
+    methods = {"hm_u8_64x1024": {"mp_per_s": value / world, "algo_gbs": roofline["step"]["gbs"], "frac_of_peak": roofline["step"]["frac"]}}
+    if not args.no_extras and not distributed:
+        def timeit(fn, steps, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / steps
+
+        del host_in, host_out
+        g.manual_seed(43)
+        srcf = torch.rand((n_img, 3, H, W), device=dev, generator=g)
+        g.manual_seed(42)
+        reff = torch.rand((1, 3, H, W), device=dev, generator=g)
+        rh = Reinhard(device=dev, backend="torch_cuda").fit(reff)
+        ms = timeit(lambda: rh.transform(srcf), 5)
+        gbs = ALGO_BYTES_PER_PX["reinhard"] * px / (ms / 1e3) / 1e9
+        methods["reinhard_f32_64x1024"] = {"mp_per_s": mp_per_gpu / (ms / 1e3), "algo_gbs": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms}
+        ref10 = torch.rand((1, 3, 512, 512), device=dev, generator=g)
+        src10 = torch.rand((10, 3, 512, 512), device=dev, generator=g)
+        ms = timeit(lambda: Reinhard(device=dev, backend="torch_cuda").fit(ref10).transform(src10), 20)
+        methods["reinhard_f32_C1_fit1x512_transform10x512"] = {"mp_per_s": 10 * 512 * 512 / 1e6 / (ms / 1e3), "ms": ms, "note": "README quick-start (BASELINE configs[0]); fits in L2, launch-latency bound"}
+        mk = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True).fit(reff)
+        ms = timeit(lambda: mk.transform(srcf), 5)
+        gbs = ALGO_BYTES_PER_PX["macenko"] * px / (ms / 1e3) / 1e9
+        methods["macenko_f32_64x1024"] = {"mp_per_s": mp_per_gpu / (ms / 1e3), "algo_gbs": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms}
+        del srcf
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
+    cpu = None
+    if rank == 0 and not distributed and not args.no_cpu_baseline:
+        cpu = cpu_hm_sample(8, 10.0)
+
+    if rank == 0:
+        line = {
+            "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"HistogramMatching uint8 {n_img}x3x{H}x{W} per GPU, reference mode (BASELINE configs[1])", "images_per_gpu": n_img, "global_images": n_img * world,
+                       "parallelism": f"image-sharded x{world}" + (", NCCL all-reduce of 3x256 int64 counts per step" if distributed else ""),
+                       "l2": "input per GPU (201 MB) exceeds L2 (126 MB); no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "methods": methods,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/*
+ * stainx_b200.h -- C ABI of libstainx_b200.so, the B200 (sm_100a) implementation of StainX's
+ * per-pixel stain-normalization hot path.
+ *
+ * This is the drop-in boundary.  It replaces the reference's pybind11
+ * module `stainx_cuda_torch.stainx_cuda_torch` (rendeirolab/stainx v0.1.4,
+ * src/stainx_cuda_torch/csrc/bindings.cpp:L19-35), whose four entry points
+ *     histogram_matching(images, ref_hist)            src/stainx_cuda_torch/csrc/histogram_matching.cu:L25-169
+ *     reinhard(images, target_mean, target_std)        src/stainx_cuda_torch/csrc/reinhard.cu:L25-121
+ *     macenko / macenko_fast(images, HE, maxC)         src/stainx_cuda_torch/csrc/macenko.cu:L67-274
+ * take and return torch tensors, and the torch-only fit path
+ *     HistogramMatchingTorch.compute_reference_histograms_torch   src/stainx/backends/torch_backend.py:L143-179
+ *     ReinhardTorch.compute_reference_mean_std_torch               src/stainx/backends/torch_backend.py:L308-323
+ *     MacenkoTorch.compute_reference_stain_matrix_torch            src/stainx/backends/torch_backend.py:L463-519
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, int64 sizes, enums as int, the CUDA stream as void*.
+ *   - every function returns an int status (SX_OK = 0); sx_last_error() gives the thread-local
+ *     message of the last failure.  (Reference behaviour: TORCH_CHECK -> RuntimeError.)
+ *   - the library owns no memory: the caller allocates inputs, outputs and the workspace
+ *     (sx_*_workspace_bytes) and keeps them alive until the stream has drained.
+ *   - asynchronous: work is enqueued on `stream`; no call synchronises the host.
+ *   - images are contiguous, C = 3.  SX_NCHW everywhere; SX_NHWC additionally for histogram
+ *     matching (the reference accepts it there through a permute view,
+ *     src/stainx/backends/torch_cuda_backend.py:L46-49).
+ *   - uint8 images are [0,255]; float32 images are assumed [0,1] and never max-rescaled
+ *     (torch_backend.py:L103-113).
+ *   - phase-level functions are split exactly where a sharded (multi-GPU) run must all-reduce
+ *     statistics; the *_transform / *_fit conveniences chain the phases on one stream.
+ */
+#ifndef STAINX_B200_H
+#define STAINX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SX_ABI_VERSION 1
+
+enum sx_status { SX_OK = 0, SX_ERR_INVALID = 1, SX_ERR_CUDA = 2, SX_ERR_UNSUPPORTED = 3 };
+enum sx_dtype { SX_U8 = 0, SX_F32 = 1 };
+enum sx_layout { SX_NCHW = 0, SX_NHWC = 1 };
+
+typedef void *sx_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int sx_abi_version(void);
+const char *sx_last_error(void);
+/* SM count, compute capability and L2 size of the current device. */
+int sx_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *l2_bytes);
+/* Number of kernels this library has launched in the calling process (monotonic). */
+int64_t sx_kernel_launches(void);
+
+/* ---- histogram matching --------------------------------------------------------------------
+ * Reference: torch_backend.py:L194-301 (oracle), csrc/histogram_matching.cu:L49-226 (CUDA). */
+
+/* H3: per-channel 256-bin counts of the whole batch, ADDED into counts[3][256] (uint64; the caller
+ * zeroes it, or keeps accumulating over shards).  float32 input is quantised by truncating
+ * clamp(x*255, 0, 255) (torch_backend.py:L115-120). */
+int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
+               uint64_t *counts, sx_stream_t stream);
+/* H1 (fit): ref_hist[c][b] = float(counts) / (torch-order float32 sum + 1e-8)  (L139-141). */
+int sx_hm_ref_hist(const uint64_t *counts, float *ref_hist, sx_stream_t stream);
+/* H2a: reference CDF: h/(sum(h)+1e-8), cumsum with a double accumulator (L221-223). */
+int sx_hm_ref_cdf(const float *ref_hist, float *ref_cdf, sx_stream_t stream);
+/* H2b: source CDF from counts and npix = N*H*W, searchsorted + interpolation -> lut[3][256]
+ * float32 in [0,255] (L234-281).  npix < 0: use the sum of each channel's counts (sharded runs). */
+int sx_hm_build_lut(const uint64_t *counts, int64_t npix, const float *ref_cdf, float *lut,
+                    sx_stream_t stream);
+/* H4: out = lut[c][v]; uint8 -> uint8 (truncated), float32 -> float32 clamp(lut/255, 0, 1)
+ * (L285-298).  `out` has the dtype and layout of `images`. */
+int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
+                const float *lut, void *out, sx_stream_t stream);
+/* Workspace for the chained transform/fit below (bytes). */
+int64_t sx_hm_workspace_bytes(void);
+/* hist -> ref_cdf -> build_lut -> apply on one stream (single-device transform). */
+int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
+                    const float *ref_hist, void *out, void *workspace, int64_t workspace_bytes,
+                    sx_stream_t stream);
+/* hist -> ref_hist (single-device fit). */
+int sx_hm_fit(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
+              float *ref_hist, void *workspace, int64_t workspace_bytes, sx_stream_t stream);
+
+/* ---- Reinhard ------------------------------------------------------------------------------
+ * Reference: torch_backend.py:L16-101, L308-355 (oracle), csrc/reinhard.cu:L45-139 (CUDA). */
+
+/* R1+R2: fused RGB->LAB and whole-batch statistics.  ADDS into sums[7] (double):
+ *   [0..2] sum(lab_c - 128), [3..5] sum((lab_c - 128)^2), [6] pixel count.
+ * The caller zeroes sums (and, when sharded, all-reduces it with SUM before finalize). */
+int sx_reinhard_stats(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
+                      double *sums, sx_stream_t stream);
+/* mean[3], std[3] (unbiased, Bessel) float32 from sums (L320-321 / L345-346). */
+int sx_reinhard_finalize(const double *sums, float *mean, float *std, sx_stream_t stream);
+/* R1+R3+R4: RGB->LAB, ((lab-src_mean)/(src_std+1e-8))*ref_std+ref_mean, LAB->RGB, clamp.
+ * float32 -> float32 [0,1]; uint8 -> uint8 = trunc(clamp(rgb*255,0,255)) (L349-355). */
+int sx_reinhard_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
+                      const float *src_mean, const float *src_std, const float *ref_mean,
+                      const float *ref_std, void *out, sx_stream_t stream);
+int64_t sx_reinhard_workspace_bytes(void);
+/* stats -> finalize -> apply on one stream. */
+int sx_reinhard_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
+                          const float *ref_mean, const float *ref_std, void *out, void *workspace,
+                          int64_t workspace_bytes, sx_stream_t stream);
+/* stats -> finalize (single-device fit, L308-323). */
+int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *mean,
+                    float *std, void *workspace, int64_t workspace_bytes, sx_stream_t stream);
+
+/* ---- Macenko -------------------------------------------------------------------------------
+ * Reference: torch_backend.py:L362-560 (oracle), src/stainx_cuda_torch/csrc/macenko.cu:L67-266
+ * and csrc/macenko.cu:L145-262 (CUDA).
+ *
+ * Statistics live in "slots": transform uses one slot per image (every statistic is per image,
+ * torch_backend.py:L556-558); fit pools all images into slot 0 (L477-485).  The workspace holds,
+ * per slot, the OD moments, the order-statistic histograms and the fitted HE / maxC.
+ *
+ * Phase order (each `hist` is one streaming pass over the images, each `select` a tiny kernel):
+ *   begin -> moments -> basis -> [moments_fallback -> basis_fallback]          (M1-M4)
+ *         -> hist(ANGLE,0) -> select(ANGLE,0) -> hist(ANGLE,1) -> select(ANGLE,1)   (M5-M7)
+ *         -> hist(CONC,0)  -> select(CONC,0)  -> hist(CONC,1)  -> select(CONC,1)    (M8-M9)
+ *         -> apply (M10)   or   get_fit (M11)
+ * A sharded pooled fit all-reduces the region named by sx_macenko_region() after `moments` and
+ * after every `hist`. */
+enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
+enum sx_macenko_region_id {
+    SX_REGION_MOMENTS = 0,  /* double  [slots][12]   reduce: SUM */
+    SX_REGION_ODRANGE = 1,  /* float32 [slots][8]    reduce: MAX  (-min_c, max_c, pad) */
+    SX_REGION_HIST1 = 2,    /* int32   [slots][2][4096]  reduce: SUM (wraps mod 2^32) */
+    SX_REGION_HIST2 = 3,    /* int32   [slots][2][4096]  reduce: SUM */
+    SX_REGION_VMIN = 4,     /* float32 [slots][2][4096]  reduce: MIN */
+    SX_REGION_VMAX = 5,     /* float32 [slots][2][4096]  reduce: MAX */
+    SX_REGION_FIT = 6       /* float32 [slots][8]: HE row-major (6) + maxC (2); read-only result */
+};
+
+int64_t sx_macenko_workspace_bytes(int64_t slots);
+/* Byte offset and size of a region inside the workspace. */
+int sx_macenko_region(int64_t slots, int region, int64_t *offset, int64_t *bytes);
+/* Initialise the workspace (must precede moments). */
+int sx_macenko_begin(void *workspace, int64_t slots, sx_stream_t stream);
+/* M1-M3: OD = -ln((255x+1)/240); mask min_c OD >= 0.15; accumulates count and shifted first and
+ * second moments of the kept rows, and the per-channel OD range of all rows.
+ * pooled != 0: every image goes to slot 0, else image i goes to slot slot0 + i. */
+int sx_macenko_moments(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled,
+                       int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream);
+/* M3-M4: unbiased covariance -> symmetric 3x3 eigen-decomposition -> E = eigvecs[:, (1, 2)].
+ * allow_fallback != 0 (transform): slots with fewer than 3 kept rows are flagged to use all rows
+ * (torch_backend.py:L409-410); run moments_fallback + basis_fallback afterwards.
+ * basis / select act on the slot range [slot0, slot0 + count). */
+int sx_macenko_basis(void *workspace, int64_t slots, int64_t slot0, int64_t count,
+                     int allow_fallback, sx_stream_t stream);
+int sx_macenko_moments_fallback(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
+                                int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream);
+int sx_macenko_basis_fallback(void *workspace, int64_t slots, int64_t slot0, int64_t count,
+                              sx_stream_t stream);
+/* One order-statistic pass.  stage ANGLE: nearest-rank 1st/99th percentile of
+ * phi = atan2(OD.e_large, OD.e_mid) over the kept rows (M5-M6); stage CONC: 99th percentile of
+ * each least-squares concentration row over all rows (M8-M9).  level 0 histograms a 12-bit
+ * prefix of a monotone 24-bit key; level 1 resolves the remaining 12 bits inside the selected
+ * bin and records the exact min/max value of every sub-bin. */
+int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled,
+                    int64_t slot0, int stage, int level, void *workspace, int64_t slots,
+                    sx_stream_t stream);
+/* Rank search after a hist pass.  (ANGLE,1) also forms HE, its pseudo-inverse and the key range
+ * of the concentrations (M7); (CONC,1) stores maxC. */
+int sx_macenko_select(void *workspace, int64_t slots, int64_t slot0, int64_t count, int stage,
+                      int level, sx_stream_t stream);
+/* M10: C = pinv(HE_src).OD scaled by maxc_ref/maxC_src; OD' = he_ref.C; rgb = clamp(240 exp(-OD'),
+ * 0, 255) * out_scale.  out_dtype SX_U8 (only for uint8 input, truncated; out_scale ignored) or
+ * SX_F32.  out_scale = 1 keeps the reference's [0,255] float output, 1/255 folds the
+ * normalize_to_0_1 division (src/stainx/normalizers/_template.py:L111-112) into the store. */
+int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0,
+                     const float *he_ref, const float *maxc_ref, void *out, int out_dtype,
+                     float out_scale, void *workspace, int64_t slots, sx_stream_t stream);
+/* Whole per-image transform on one stream (slots = n). */
+int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
+                         const float *he_ref, const float *maxc_ref, void *out, int out_dtype,
+                         float out_scale, void *workspace, int64_t workspace_bytes,
+                         sx_stream_t stream);
+/* Whole pooled fit on one stream (slots = 1): he[3][2] row-major, maxc[2] (device pointers). */
+int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he,
+                   float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAINX_B200_H */

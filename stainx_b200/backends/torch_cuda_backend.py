@@ -1,0 +1,210 @@
+"""``backend="torch_cuda"`` implementations on top of ``libstainx_b200.so``.
+
+Mirrors the reference's ``src/stainx/backends/torch_cuda_backend.py`` (class names, constructor
+arguments, ``transform(images, *reference_params)`` signatures, error behaviour) and additionally
+provides the fit entry points, which the reference only has in its torch backend
+(``compute_reference_*_torch``, ``torch_backend.py:L143-179, L308-323, L463-519``): here fit runs on
+the GPU with the same kernels as transform.
+
+Sharded execution: every class takes an optional :class:`~stainx_b200.sharding.StatReducer`.  With
+one, the batch passed to ``fit`` / ``transform`` is this rank's shard and whole-batch statistics
+are all-reduced between kernel phases, so every rank sees the single-device result.
+"""
+from __future__ import annotations
+
+import torch
+
+from stainx_b200 import _native
+from stainx_b200.sharding import StatReducer
+
+CUDA_AVAILABLE = _native.FUNCTIONS_AVAILABLE
+
+_CHANNELS_LAST = (-1, 3)
+
+
+class TorchCUDABackendBase:
+    """Device / availability checks shared by the three backends
+    (reference: ``torch_cuda_backend.py:L17-33``)."""
+
+    def __init__(self, device: str | torch.device | None = None, reducer: StatReducer | None = None, ops=None):
+        # `ops` lets the CPU test-suite substitute the kernel layer to exercise the sharding logic;
+        # the product always uses stainx_b200.ops (the native library).
+        self._injected_ops = ops is not None
+        if ops is None:
+            if not _native.available():
+                raise ImportError("libstainx_b200 is not built. CUDA backend is not available (python -m stainx_b200.build); there is no fallback backend.")
+            from stainx_b200 import ops as native_ops
+
+            ops = native_ops
+        self._ops = ops
+        self._reducer = reducer if reducer is not None else StatReducer()
+
+        if device is None:
+            if torch.cuda.is_available():
+                self.device = torch.device("cuda")
+            elif self._injected_ops:
+                self.device = torch.device("cpu")
+            else:
+                raise RuntimeError("CUDA is not available on this system")
+        else:
+            self.device = torch.device(device)
+        if self.device.type != "cuda" and not self._injected_ops:
+            raise ValueError(f"CUDA backend requires CUDA device, got {self.device.type}")
+
+    def _to_native(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.dtype]:
+        """Move to the device and to a dtype the kernels take: uint8 stays, every other dtype is
+        read as float32 in [0, 1] (torch_backend.py:L103-113)."""
+        if not isinstance(images, torch.Tensor):
+            raise TypeError(f"images must be a torch.Tensor, got {type(images)}")
+        original = images.dtype
+        images = images.to(self.device)
+        if images.dtype != torch.uint8 and images.dtype != torch.float32:
+            images = images.float()
+        return images.contiguous(), original
+
+    @staticmethod
+    def _restore_dtype(result: torch.Tensor, original: torch.dtype) -> torch.Tensor:
+        # torch_backend.py:L131: the result is cast back to the caller's dtype.
+        if original in (torch.uint8, torch.float32) or result.dtype == original:
+            return result
+        return result.to(original)
+
+
+class HistogramMatchingCUDA(TorchCUDABackendBase):
+    def __init__(self, device: str | torch.device | None = None, channel_axis: int = 1, reducer: StatReducer | None = None, ops=None):
+        super().__init__(device, reducer, ops)
+        self.channel_axis = channel_axis
+
+    def _layout(self, images: torch.Tensor) -> int:
+        if self.channel_axis == -1 or (self.channel_axis == 3 and images.ndim == 4):
+            return _native.SX_NHWC
+        return _native.SX_NCHW
+
+    def _stack_reference(self, reference_histogram: torch.Tensor | list) -> torch.Tensor:
+        """(3, 256) float32 reference histograms from the list / single-tensor forms the reference
+        accepts (``torch_cuda_backend.py:L51-75``)."""
+        if isinstance(reference_histogram, (list, tuple)):
+            if len(reference_histogram) == 0:
+                raise ValueError("reference_histogram list cannot be empty")
+            for i, h in enumerate(reference_histogram):
+                if not isinstance(h, torch.Tensor):
+                    raise TypeError(f"reference_histogram[{i}] must be a torch.Tensor, got {type(h)}")
+                if h.dim() != 1 or h.size(0) != 256:
+                    raise ValueError(f"Each histogram in reference_histogram list must be 1D with 256 elements. Got histogram at index {i} with shape {h.shape}")
+            rows = [h.to(self.device) for h in reference_histogram[:3]]
+            while len(rows) < 3:
+                rows.append(rows[0])
+            return torch.stack(rows, dim=0).float().contiguous()
+        ref = reference_histogram.to(self.device)
+        if ref.dim() == 2 and tuple(ref.shape) == (3, 256):
+            return ref.float().contiguous()
+        if ref.dim() != 1 or ref.size(0) != 256:
+            raise ValueError(f"reference_histogram must be 1D with 256 elements. Got shape {ref.shape}")
+        return ref.float().unsqueeze(0).repeat(3, 1).contiguous()
+
+    def compute_reference_counts(self, images: torch.Tensor) -> torch.Tensor:
+        """Whole-reference-set per-channel counts, int64 (3, 256), summed over ranks."""
+        images, _ = self._to_native(images)
+        counts = self._ops.hm_hist(images, self._layout(images))
+        return self._reducer.sum_(counts)
+
+    def compute_reference_histograms(self, images: torch.Tensor) -> tuple[torch.Tensor, list[torch.Tensor]]:
+        """H1 (``compute_reference_histograms_torch``): -> counts (3, 256) int64 and the list of three
+        float32 (256,) histograms ``counts / (counts.sum() + 1e-8)``."""
+        counts = self.compute_reference_counts(images)
+        ref_hist = self._ops.hm_ref_hist(counts)
+        return counts, [ref_hist[c] for c in range(3)]
+
+    def transform(self, images: torch.Tensor, reference_histogram: torch.Tensor | list) -> torch.Tensor:
+        images, original = self._to_native(images)
+        layout = self._layout(images)
+        ref_hist = self._stack_reference(reference_histogram)
+        if self._reducer.enabled:
+            # H3 -> all-reduce -> H2 -> H4: the source histogram spans the whole sharded batch.
+            counts = self._reducer.sum_(self._ops.hm_hist(images, layout))
+            # npix = -1: the LUT kernel takes the global pixel count from the reduced counts
+            lut = self._ops.hm_build_lut(counts, -1, self._ops.hm_ref_cdf(ref_hist))
+            result = self._ops.hm_apply(images, lut, layout)
+        else:
+            result = self._ops.hm_transform(images, ref_hist, layout)
+        return self._restore_dtype(result, original)
+
+
+class ReinhardCUDA(TorchCUDABackendBase):
+    def compute_reference_mean_std(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """R5 (``compute_reference_mean_std_torch``): LAB mean / unbiased std over the whole set."""
+        images, _ = self._to_native(images)
+        if self._reducer.enabled:
+            return self._ops.reinhard_finalize(self._reducer.sum_(self._ops.reinhard_stats(images)))
+        return self._ops.reinhard_fit(images)
+
+    def transform(self, images: torch.Tensor, target_mean: torch.Tensor, target_std: torch.Tensor) -> torch.Tensor:
+        images, original = self._to_native(images)
+        if self._reducer.enabled:
+            src_mean, src_std = self._ops.reinhard_finalize(self._reducer.sum_(self._ops.reinhard_stats(images)))
+            result = self._ops.reinhard_apply(images, src_mean, src_std, target_mean, target_std)
+        else:
+            result = self._ops.reinhard_transform(images, target_mean, target_std)
+        return self._restore_dtype(result, original)
+
+
+class MacenkoCUDA(TorchCUDABackendBase):
+    """Macenko backend.
+
+    ``precision`` is accepted for API compatibility (reference: ``"stable"`` = fp64 covariance +
+    fp32 pixels, ``"fast"`` = fp16 pixel tensors).  This build has one path: fp32 pixels in
+    registers, fp64 moment accumulation and eigen-decomposition, no materialised pixel tensors, so
+    both values select the same kernels.
+    """
+
+    def __init__(self, device: str | torch.device | None = None, precision: str = "stable", reducer: StatReducer | None = None, ops=None):
+        if precision not in ("stable", "fast"):
+            raise ValueError(f"precision must be 'stable' or 'fast', got {precision!r}")
+        super().__init__(device, reducer, ops)
+        self._precision = precision
+
+    def compute_reference_stain_matrix(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """M11 (``compute_reference_stain_matrix_torch``): pooled fit -> HE (3, 2), maxC (2,)."""
+        images, _ = self._to_native(images)
+        if images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError(f"Macenko fit expects NCHW with C=3, got shape {tuple(images.shape)}")
+        if not self._reducer.enabled:
+            return self._ops.macenko_fit(images)
+        return self._pooled_fit_sharded(images)
+
+    def _pooled_fit_sharded(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        red = self._reducer
+        ws = self._ops.MacenkoWorkspace(1, images.device)
+        ws.begin()
+        if images.shape[0] > 0:
+            ws.moments(images, pooled=True)
+        red.sum_(ws.region("moments"))
+        red.max_(ws.region("odrange"))
+        ws.basis(0, 1, allow_fallback=False)
+        for stage in (_native.SX_STAGE_ANGLE, _native.SX_STAGE_CONC):
+            if images.shape[0] > 0:
+                ws.hist(images, True, stage, 0)
+            red.sum_(ws.region("hist1"))
+            ws.select(0, 1, stage, 0)
+            if images.shape[0] > 0:
+                ws.hist(images, True, stage, 1)
+            red.sum_(ws.region("hist2"))
+            red.min_(ws.region("vmin"))
+            red.max_(ws.region("vmax"))
+            ws.select(0, 1, stage, 1)
+        fit = ws.region("fit")[0]
+        return fit[:6].reshape(3, 2).clone(), fit[6:8].clone()
+
+    def transform(self, images: torch.Tensor, stain_matrix: torch.Tensor, target_max_conc: torch.Tensor, normalize_to_0_1: bool = False) -> torch.Tensor:
+        images, original = self._to_native(images)
+        if tuple(stain_matrix.shape) != (3, 2):
+            raise ValueError(f"stain_matrix must have shape (3, 2), got {stain_matrix.shape}")
+        if images.dim() != 4:
+            raise ValueError(f"Macenko expects NCHW images, got shape {tuple(images.shape)}")
+        if images.shape[1] != 3:
+            raise ValueError(f"Macenko expects 3 channels in dim 1 (NCHW), got C={images.shape[1]} with shape {tuple(images.shape)}")
+        # Per-image statistics: a sharded batch needs no exchange at transform time.
+        result = self._ops.macenko_transform(images, stain_matrix, target_max_conc.flatten(), unit=bool(normalize_to_0_1))
+        if normalize_to_0_1 and original == torch.uint8:
+            return result  # the reference's `uint8 / 255.0` is float32
+        return self._restore_dtype(result, original)

@@ -1,0 +1,111 @@
+// common.cuh -- shared host/device helpers for libstainx_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stainx_b200.h"
+
+namespace sx {
+
+// ---- host side ------------------------------------------------------------------------------
+int fail(int code, const char *fmt, ...);
+void note_launch(int n = 1);
+int sm_count();
+int64_t l2_bytes();
+
+#define SX_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return ::sx::fail(SX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// After a <<<>>> launch: count it and surface launch errors (reference: cudaGetLastError after
+// every launch, src/stainx_cuda_torch/csrc/reinhard.cu:L76-77).
+#define SX_LAUNCHED(name)                                                                          \
+    do {                                                                                           \
+        ::sx::note_launch();                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) return ::sx::fail(SX_ERR_CUDA, "launch of %s: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define SX_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                           \
+        if (!(cond)) return ::sx::fail(SX_ERR_INVALID, __VA_ARGS__);                               \
+    } while (0)
+
+inline int64_t max_i64(int64_t a, int64_t b) { return a > b ? a : b; }
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int check_images(const void *images, int dtype, int64_t n, int64_t h, int64_t w) {
+    SX_REQUIRE(images != nullptr, "images is NULL");
+    SX_REQUIRE(dtype == SX_U8 || dtype == SX_F32, "dtype must be SX_U8 or SX_F32, got %d", dtype);
+    SX_REQUIRE(n >= 0 && h >= 0 && w >= 0, "negative image extent (%lld, %lld, %lld)", (long long)n, (long long)h, (long long)w);
+    return SX_OK;
+}
+
+// Grid for a grid-stride streaming kernel: enough CTAs to fill every SM `per_sm` times, never
+// more than the work items.
+inline unsigned stream_grid(int64_t items, int per_sm) {
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    int64_t g = items < cap ? items : cap;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
+// ---- device side ----------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// 128-bit streaming loads/stores.  .nc + L1::no_allocate: every byte is used once per pass, so
+// keep it out of L1; L2 allocation stays default so that later passes over the same image can
+// hit the 126 MB L2.
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// float atomic max / min on plain float storage (works for mixed signs; NaN is ignored).
+__device__ __forceinline__ void atomic_max_f32(float *addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f32(float *addr, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// float32 -> grey level exactly as torch_backend.py:L115-120: trunc(clamp(x*255, 0, 255)).
+__device__ __forceinline__ unsigned quantize_u8(float x) {
+    float v = __fmul_rn(x, 255.0f);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    return (unsigned)__float2int_rz(v);
+}
+
+#endif  // __CUDACC__
+}  // namespace sx

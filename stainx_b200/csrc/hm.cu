@@ -1,0 +1,685 @@
+// hm.cu -- histogram matching on B200: 256-bin per-channel histogram of the whole batch (H3),
+// bit-exact LUT construction (H1/H2) and the streaming LUT remap (H4).
+//
+// Reference semantics: src/stainx/backends/torch_backend.py:L139-141, L194-301 (torch CPU oracle);
+// the kernels it replaces: csrc/histogram_matching.cu:L21-226 and the ATen glue in
+// src/stainx_cuda_torch/csrc/histogram_matching.cu:L25-169.
+//
+// Data path (uint8 NCHW, the BASELINE config): 3 B/px read for the histogram, 3 B/px read +
+// 3 B/px written for the remap = 9 algorithmic bytes per pixel, all 128-bit coalesced.
+#include "common.cuh"
+
+namespace sx {
+namespace hm {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kUnroll = 4;                            // 128-bit loads in flight per thread
+constexpr int kTileVecs = kThreads * kUnroll;         // uint4 / float4 vectors per tile
+constexpr int kFlushTiles = 3;                        // 3 tiles * 4 loads * 16 B = 192 <= 255 per counter
+
+// ------------------------------------------------------------------------------------------------
+// Histogram, planar uint8.  grid = (blocks, 3 channels); a CTA only ever sees one channel.
+//
+// Counting scheme: every THREAD owns a private 256-bin histogram of 8-bit counters in shared
+// memory, so counting is a plain byte load / add / store -- no atomics and no bank conflicts:
+// the counter of (bin, lane) lives in word (bin >> 2) * 32 + lane, byte (bin & 3), i.e. lane l only
+// ever touches bank l.  Byte counters overflow after 255 hits, so each warp folds its 8 KB region
+// into the CTA's 32-bit histogram every kFlushTiles tiles (<= 192 values per thread).
+// ------------------------------------------------------------------------------------------------
+struct ByteCounters {
+    // warp-private region: 64 rows (bin >> 2) x 32 lanes x 4 byte-counters
+    static constexpr int kBytesPerWarp = 64 * 32 * 4;
+
+    unsigned char *mine;   // &region[lane * 4]
+    unsigned int *region;  // warp region as words
+    unsigned int *hist32;  // CTA histogram (256 x u32)
+    int lane;
+
+    __device__ __forceinline__ void init(unsigned char *smem_counters, unsigned int *h32) {
+        int warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        region = reinterpret_cast<unsigned int *>(smem_counters + warp * kBytesPerWarp);
+        mine = reinterpret_cast<unsigned char *>(region) + lane * 4;
+        hist32 = h32;
+        for (int i = lane; i < 64 * 32; i += 32) region[i] = 0u;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void add(unsigned b) {  // b in [0,255]
+        unsigned off = ((b & 0xfcu) << 5) | (b & 3u);
+        mine[off] = (unsigned char)(mine[off] + 1);
+    }
+    __device__ __forceinline__ void add4(unsigned w) {
+        add(w & 0xffu);
+        add((w >> 8) & 0xffu);
+        add((w >> 16) & 0xffu);
+        add(w >> 24);
+    }
+    // Fold the warp's byte counters into hist32 and clear them.  Lane j sums rows j and j + 32,
+    // walking the 32 words of a row with a lane-dependent rotation (bank = (k + lane) & 31).
+    __device__ __forceinline__ void flush() {
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            int q = lane + 32 * rr;
+            unsigned lo = 0, hi = 0;  // two 16-bit partial sums each
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                int col = (k + lane) & 31;
+                unsigned w = region[q * 32 + col];
+                region[q * 32 + col] = 0u;
+                lo += w & 0x00ff00ffu;
+                hi += (w >> 8) & 0x00ff00ffu;
+            }
+            if (lo & 0xffffu) atomicAdd(&hist32[4 * q + 0], lo & 0xffffu);
+            if (hi & 0xffffu) atomicAdd(&hist32[4 * q + 1], hi & 0xffffu);
+            if (lo >> 16) atomicAdd(&hist32[4 * q + 2], lo >> 16);
+            if (hi >> 16) atomicAdd(&hist32[4 * q + 3], hi >> 16);
+        }
+        __syncwarp();
+    }
+};
+
+// Alternative counting scheme (selectable for A/B measurements): warp-private 32-bit histograms
+// updated with shared-memory atomics.
+struct WarpAtomics {
+    unsigned int *wh;  // warp histogram (256 x u32)
+    __device__ __forceinline__ void init(unsigned int *smem_hist) {
+        wh = smem_hist + (threadIdx.x >> 5) * 256;
+        for (int i = threadIdx.x & 31; i < 256; i += 32) wh[i] = 0u;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void add(unsigned b) { atomicAdd(&wh[b], 1u); }
+    __device__ __forceinline__ void add4(unsigned w) {
+        add(w & 0xffu);
+        add((w >> 8) & 0xffu);
+        add((w >> 16) & 0xffu);
+        add(w >> 24);
+    }
+};
+
+// Work decomposition shared by the planar kernels: a plane of `len` elements starting at `p` is
+// split into an unaligned head (< 16 B), a body of 16-byte vectors and a tail.
+struct PlaneSplit {
+    int64_t head;   // elements before the first aligned vector
+    int64_t nvec;   // aligned vectors
+    int64_t tail0;  // first element after the body
+};
+template <typename T>
+__device__ __forceinline__ PlaneSplit split_plane(const T *p, int64_t len) {
+    constexpr int kPerVec = 16 / sizeof(T);
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    int64_t head = (int64_t)(((16 - (a & 15)) & 15) / sizeof(T));
+    if (head > len) head = len;
+    PlaneSplit s;
+    s.head = head;
+    s.nvec = (len - head) / kPerVec;
+    s.tail0 = head + s.nvec * kPerVec;
+    return s;
+}
+
+template <bool BYTE_COUNTERS>
+__global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned int *hist32 = reinterpret_cast<unsigned int *>(smem);  // 256 words
+    unsigned char *scratch = smem + 256 * sizeof(unsigned int);
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < 256; i += kThreads) hist32[i] = 0u;
+
+    ByteCounters bc;
+    WarpAtomics wa;
+    if (BYTE_COUNTERS) bc.init(scratch, hist32);
+    else wa.init(reinterpret_cast<unsigned int *>(scratch));
+    __syncthreads();
+
+    const int64_t items = n_img * tiles_per_plane;
+    int since_flush = 0;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t n = item / tiles_per_plane;
+        const int64_t t = item - n * tiles_per_plane;
+        const uint8_t *plane = img + (n * 3 + c) * hw;
+        const PlaneSplit sp = split_plane(plane, hw);
+        const uint4 *body = reinterpret_cast<const uint4 *>(plane + sp.head);
+        const int64_t v0 = t * kTileVecs;
+        uint4 v[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            int64_t vi = v0 + u * kThreads + threadIdx.x;
+            ok[u] = vi < sp.nvec;
+            if (ok[u]) v[u] = ld_stream(body + vi);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (ok[u]) {
+                if (BYTE_COUNTERS) { bc.add4(v[u].x); bc.add4(v[u].y); bc.add4(v[u].z); bc.add4(v[u].w); }
+                else { wa.add4(v[u].x); wa.add4(v[u].y); wa.add4(v[u].z); wa.add4(v[u].w); }
+            }
+        }
+        if (t == 0) {  // ragged ends of the plane: < 32 bytes, one thread each
+            int64_t ragged = sp.head + (hw - sp.tail0);
+            if ((int64_t)threadIdx.x < ragged) {
+                int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
+                if (BYTE_COUNTERS) bc.add(plane[idx]);
+                else wa.add(plane[idx]);
+            }
+        }
+        if (BYTE_COUNTERS && ++since_flush == kFlushTiles) {
+            bc.flush();
+            since_flush = 0;
+        }
+    }
+    if (BYTE_COUNTERS) {
+        bc.flush();
+    } else {
+        __syncwarp();
+        for (int i = threadIdx.x & 31; i < 256; i += 32)
+            if (wa.wh[i]) atomicAdd(&hist32[i], wa.wh[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += kThreads)
+        if (hist32[i]) atomicAdd(&counts[c * 256 + i], (unsigned long long)hist32[i]);
+}
+
+// Histogram, planar float32: quantise, then warp-private shared atomics (12 B/px of traffic per
+// 3 values, so the atomic rate is 4x lower than in the uint8 kernel).
+__global__ void __launch_bounds__(kThreads) hist_f32_planar_kernel(const float *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    __shared__ unsigned int hist32[256];
+    __shared__ unsigned int whist[kWarps * 256];
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < 256; i += kThreads) hist32[i] = 0u;
+    WarpAtomics wa;
+    wa.init(whist);
+    __syncthreads();
+    const int64_t items = n_img * tiles_per_plane;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t n = item / tiles_per_plane;
+        const int64_t t = item - n * tiles_per_plane;
+        const float *plane = img + (n * 3 + c) * hw;
+        const PlaneSplit sp = split_plane(plane, hw);
+        const float4 *body = reinterpret_cast<const float4 *>(plane + sp.head);
+        const int64_t v0 = t * kTileVecs;
+        float4 v[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            int64_t vi = v0 + u * kThreads + threadIdx.x;
+            ok[u] = vi < sp.nvec;
+            if (ok[u]) v[u] = ld_stream(body + vi);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (ok[u]) {
+                wa.add(quantize_u8(v[u].x));
+                wa.add(quantize_u8(v[u].y));
+                wa.add(quantize_u8(v[u].z));
+                wa.add(quantize_u8(v[u].w));
+            }
+        }
+        if (t == 0) {
+            int64_t ragged = sp.head + (hw - sp.tail0);
+            if ((int64_t)threadIdx.x < ragged) {
+                int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
+                wa.add(quantize_u8(plane[idx]));
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = threadIdx.x & 31; i < 256; i += 32)
+        if (wa.wh[i]) atomicAdd(&hist32[i], wa.wh[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += kThreads)
+        if (hist32[i]) atomicAdd(&counts[c * 256 + i], (unsigned long long)hist32[i]);
+}
+
+// Histogram, interleaved (NHWC): the batch is one flat array of 3*npix elements, element i
+// belongs to channel i % 3.  A thread takes 3 consecutive vectors = 48 B (uint8: 16 px) or 12
+// floats (4 px), so the channel of every register lane is a compile-time constant.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) hist_nhwc_kernel(const T *__restrict__ img, int64_t total, unsigned long long *__restrict__ counts) {
+    constexpr int kPerVec = 16 / sizeof(T);
+    constexpr int kGroup = 3 * kPerVec;  // elements per thread-iteration, multiple of 3
+    __shared__ unsigned int whist[kWarps * 3 * 256];
+    unsigned int *wh = whist + (threadIdx.x >> 5) * 768;
+    for (int i = threadIdx.x & 31; i < 768; i += 32) wh[i] = 0u;
+    __syncwarp();
+
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(img) & 15) == 0;
+    const int64_t groups = vec_ok ? total / kGroup : 0;
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
+        if constexpr (sizeof(T) == 1) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(img + g * kGroup);
+            uint4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
+            unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 48; ++j) {
+                unsigned v = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                atomicAdd(&wh[(j % 3) * 256 + v], 1u);
+            }
+        } else {
+            const float4 *p = reinterpret_cast<const float4 *>(img + g * kGroup);
+            float4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
+            float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 12; ++j) atomicAdd(&wh[(j % 3) * 256 + quantize_u8(f[j])], 1u);
+        }
+    }
+    // scalar remainder (everything when the base pointer is not 16-byte aligned)
+    for (int64_t i = groups * kGroup + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        unsigned v;
+        if constexpr (sizeof(T) == 1) v = img[i];
+        else v = quantize_u8(img[i]);
+        atomicAdd(&wh[(int)(i % 3) * 256 + v], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 768; i += kThreads) {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int wgt = 0; wgt < kWarps; ++wgt) s += whist[wgt * 768 + i];
+        if (s) atomicAdd(&counts[i], s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LUT construction.  Tiny, single CTA per channel; every float32 operation is pinned with
+// round-to-nearest intrinsics so the result is bit-identical to the torch CPU oracle.
+// ------------------------------------------------------------------------------------------------
+
+// torch.sum of a 256-vector on CPU: 8 lanes x 4 interleaved accumulators (see oracle/ox_sum_f32).
+__device__ float torch_sum_256(const float *a) {
+    float acc[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc[k][l] = 0.0f;
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) acc[k][l] = __fadd_rn(acc[k][l], a[(i * 4 + k) * 8 + l]);
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], acc[k][l]);
+    float f = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) f = __fadd_rn(f, acc[0][l]);
+    return f;
+}
+
+// H1: torch_backend.py:L139-141.
+__global__ void ref_hist_kernel(const unsigned long long *__restrict__ counts, float *__restrict__ ref_hist) {
+    __shared__ float cf[256];
+    __shared__ float denom;
+    const int c = blockIdx.x, b = threadIdx.x;
+    cf[b] = __ull2float_rn(counts[c * 256 + b]);
+    __syncthreads();
+    if (b == 0) denom = __fadd_rn(torch_sum_256(cf), 1e-8f);
+    __syncthreads();
+    ref_hist[c * 256 + b] = __fdiv_rn(cf[b], denom);
+}
+
+// H2a: torch_backend.py:L221-223.
+__global__ void ref_cdf_kernel(const float *__restrict__ ref_hist, float *__restrict__ ref_cdf) {
+    __shared__ float h[256];
+    const int c = blockIdx.x, b = threadIdx.x;
+    h[b] = ref_hist[c * 256 + b];
+    __syncthreads();
+    if (b == 0) {
+        float denom = __fadd_rn(torch_sum_256(h), 1e-8f);
+        double acc = 0.0;
+        for (int i = 0; i < 256; ++i) {
+            acc = __dadd_rn(acc, (double)__fdiv_rn(h[i], denom));
+            ref_cdf[c * 256 + i] = __double2float_rn(acc);
+        }
+    }
+}
+
+// H2b: torch_backend.py:L234-281.  npix < 0: derive the pixel count from the counts themselves
+// (sum over the 256 bins of the channel), which keeps a sharded run free of host round trips.
+__global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref_cdf, float *__restrict__ lut) {
+    __shared__ float rq[256];
+    __shared__ float sq[256];
+    __shared__ float s_npix_f;
+    const int c = blockIdx.x, b = threadIdx.x;
+    rq[b] = ref_cdf[c * 256 + b];
+    if (b == 0) {
+        unsigned long long total = 0;
+        if (npix < 0) for (int i = 0; i < 256; ++i) total += counts[c * 256 + i];
+        else total = (unsigned long long)npix;
+        // L235: python float (num_pixels + 1e-8), cast to float32 for the division
+        s_npix_f = __double2float_rn(__dadd_rn((double)total, 1e-8));
+    }
+    __syncthreads();
+    sq[b] = __fdiv_rn(__ull2float_rn(counts[c * 256 + b]), s_npix_f);  // L234-235
+    __syncthreads();
+    if (b == 0) {  // L236: cumsum, double accumulator rounded per element
+        double acc = 0.0;
+        for (int i = 0; i < 256; ++i) {
+            acc = __dadd_rn(acc, (double)sq[i]);
+            sq[i] = __double2float_rn(acc);
+        }
+    }
+    __syncthreads();
+    const float q = sq[b];
+    int lo = 0, hi = 256;  // L260: searchsorted(right=False)
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (rq[mid] < q) lo = mid + 1;
+        else hi = mid;
+    }
+    const int idx = min(max(lo, 1), 255);                                   // L261
+    const float ql = rq[idx - 1], qr = rq[idx];                             // L264-265
+    const float d = __fsub_rn(qr, ql);                                      // L272
+    const float alpha = d > 1e-10f ? __fdiv_rn(__fsub_rn(q, ql), d) : 0.f;  // L273
+    float v = __fadd_rn((float)(idx - 1), alpha);                           // L276 (ref_values step is exactly 1)
+    if (q <= rq[0]) v = 0.0f;                                               // L268, L279
+    if (q >= rq[255]) v = 255.0f;                                           // L269, L280
+    lut[c * 256 + b] = fminf(fmaxf(v, 0.0f), 255.0f);                       // L281
+}
+
+// ------------------------------------------------------------------------------------------------
+// LUT remap (H4).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned remap4(const unsigned char *l, unsigned w) {
+    return (unsigned)l[w & 0xffu] | ((unsigned)l[(w >> 8) & 0xffu] << 8) | ((unsigned)l[(w >> 16) & 0xffu] << 16) | ((unsigned)l[w >> 24] << 24);
+}
+
+// uint8 planar.  Items are walked from the END of the batch: the histogram pass has just
+// streamed the batch front to back, so the tail is what is still resident in L2.
+__global__ void __launch_bounds__(kThreads) apply_u8_planar_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, int64_t hw, int64_t planes, int64_t tiles_per_plane, const float *__restrict__ lut) {
+    __shared__ unsigned char lut8[3 * 256];
+    for (int i = threadIdx.x; i < 768; i += kThreads) lut8[i] = (unsigned char)__float2int_rz(lut[i]);  // trunc, L296-298
+    __syncthreads();
+    const int64_t items = planes * tiles_per_plane;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t item = items - 1 - it;
+        const int64_t pl = item / tiles_per_plane;
+        const int64_t t = item - pl * tiles_per_plane;
+        const unsigned char *l = lut8 + (int)(pl % 3) * 256;
+        const uint8_t *src = img + pl * hw;
+        uint8_t *dst = out + pl * hw;
+        const PlaneSplit sp = split_plane(src, hw);
+        const bool dst_vec = ((reinterpret_cast<uintptr_t>(dst + sp.head)) & 15) == 0;
+        const uint4 *body = reinterpret_cast<const uint4 *>(src + sp.head);
+        const int64_t v0 = t * kTileVecs;
+        uint4 v[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            int64_t vi = v0 + u * kThreads + threadIdx.x;
+            ok[u] = vi < sp.nvec;
+            if (ok[u]) v[u] = ld_stream(body + vi);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!ok[u]) continue;
+            int64_t vi = v0 + u * kThreads + threadIdx.x;
+            uint4 r;
+            r.x = remap4(l, v[u].x); r.y = remap4(l, v[u].y); r.z = remap4(l, v[u].z); r.w = remap4(l, v[u].w);
+            if (dst_vec) {
+                st_stream(reinterpret_cast<uint4 *>(dst + sp.head) + vi, r);
+            } else {
+                unsigned w[4] = {r.x, r.y, r.z, r.w};
+                uint8_t *d = dst + sp.head + vi * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) d[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+        if (t == 0) {
+            int64_t ragged = sp.head + (hw - sp.tail0);
+            if ((int64_t)threadIdx.x < ragged) {
+                int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
+                dst[idx] = l[src[idx]];
+            }
+        }
+    }
+}
+
+// float32 planar: out = clamp(lut[trunc(clamp(255 x))] / 255, 0, 1)   (L290-296).
+__global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const float *__restrict__ img, float *__restrict__ out, int64_t hw, int64_t planes, int64_t tiles_per_plane, const float *__restrict__ lut) {
+    __shared__ float lutf[3 * 256];
+    for (int i = threadIdx.x; i < 768; i += kThreads) lutf[i] = fminf(fmaxf(__fdiv_rn(lut[i], 255.0f), 0.0f), 1.0f);
+    __syncthreads();
+    const int64_t items = planes * tiles_per_plane;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t item = items - 1 - it;
+        const int64_t pl = item / tiles_per_plane;
+        const int64_t t = item - pl * tiles_per_plane;
+        const float *l = lutf + (int)(pl % 3) * 256;
+        const float *src = img + pl * hw;
+        float *dst = out + pl * hw;
+        const PlaneSplit sp = split_plane(src, hw);
+        const bool dst_vec = ((reinterpret_cast<uintptr_t>(dst + sp.head)) & 15) == 0;
+        const float4 *body = reinterpret_cast<const float4 *>(src + sp.head);
+        const int64_t v0 = t * kTileVecs;
+        float4 v[kUnroll];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            int64_t vi = v0 + u * kThreads + threadIdx.x;
+            ok[u] = vi < sp.nvec;
+            if (ok[u]) v[u] = ld_stream(body + vi);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!ok[u]) continue;
+            int64_t vi = v0 + u * kThreads + threadIdx.x;
+            float4 r = make_float4(l[quantize_u8(v[u].x)], l[quantize_u8(v[u].y)], l[quantize_u8(v[u].z)], l[quantize_u8(v[u].w)]);
+            if (dst_vec) {
+                st_stream(reinterpret_cast<float4 *>(dst + sp.head) + vi, r);
+            } else {
+                float *d = dst + sp.head + vi * 4;
+                d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w;
+            }
+        }
+        if (t == 0) {
+            int64_t ragged = sp.head + (hw - sp.tail0);
+            if ((int64_t)threadIdx.x < ragged) {
+                int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
+                dst[idx] = l[quantize_u8(src[idx])];
+            }
+        }
+    }
+}
+
+// Interleaved (NHWC) remap, uint8 or float32.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t total, const float *__restrict__ lut) {
+    constexpr int kPerVec = 16 / sizeof(T);
+    constexpr int kGroup = 3 * kPerVec;
+    __shared__ float lutf[3 * 256];
+    __shared__ unsigned char lut8[3 * 256];
+    for (int i = threadIdx.x; i < 768; i += kThreads) {
+        lut8[i] = (unsigned char)__float2int_rz(lut[i]);
+        lutf[i] = fminf(fmaxf(__fdiv_rn(lut[i], 255.0f), 0.0f), 1.0f);
+    }
+    __syncthreads();
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t groups = vec_ok ? total / kGroup : 0;
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
+        if constexpr (sizeof(T) == 1) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(img + g * kGroup);
+            uint4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
+            unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+            unsigned r[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) r[k] = 0u;
+#pragma unroll
+            for (int j = 0; j < 48; ++j) {
+                unsigned v = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                r[j >> 2] |= (unsigned)lut8[(j % 3) * 256 + v] << (8 * (j & 3));
+            }
+            uint4 *q = reinterpret_cast<uint4 *>(out + g * kGroup);
+            st_stream(q, make_uint4(r[0], r[1], r[2], r[3]));
+            st_stream(q + 1, make_uint4(r[4], r[5], r[6], r[7]));
+            st_stream(q + 2, make_uint4(r[8], r[9], r[10], r[11]));
+        } else {
+            const float4 *p = reinterpret_cast<const float4 *>(img + g * kGroup);
+            float4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
+            float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 12; ++j) f[j] = lutf[(j % 3) * 256 + quantize_u8(f[j])];
+            float4 *q = reinterpret_cast<float4 *>(out + g * kGroup);
+            st_stream(q, make_float4(f[0], f[1], f[2], f[3]));
+            st_stream(q + 1, make_float4(f[4], f[5], f[6], f[7]));
+            st_stream(q + 2, make_float4(f[8], f[9], f[10], f[11]));
+        }
+    }
+    for (int64_t i = groups * kGroup + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        if constexpr (sizeof(T) == 1) out[i] = lut8[(int)(i % 3) * 256 + img[i]];
+        else out[i] = lutf[(int)(i % 3) * 256 + quantize_u8(img[i])];
+    }
+}
+
+// ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
+static int g_hist_byte_counters = 1;
+static int g_hist_ctas_per_sm = 3;
+static int g_apply_ctas_per_sm = 8;
+
+}  // namespace hm
+}  // namespace sx
+
+using namespace sx;
+using namespace sx::hm;
+
+extern "C" {
+
+// Undocumented-in-header tuning hook used by bench/profiling scripts.
+int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm) {
+    if (hist_byte_counters >= 0) g_hist_byte_counters = hist_byte_counters;
+    if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
+    if (apply_ctas_per_sm > 0) g_apply_ctas_per_sm = apply_ctas_per_sm;
+    return SX_OK;
+}
+
+int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, uint64_t *counts, sx_stream_t stream_) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    SX_REQUIRE(counts != nullptr, "counts is NULL");
+    SX_REQUIRE(layout == SX_NCHW || layout == SX_NHWC, "layout must be SX_NCHW or SX_NHWC, got %d", layout);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t hw = h * w;
+    if (n == 0 || hw == 0) return SX_OK;
+    auto *cnt = reinterpret_cast<unsigned long long *>(counts);
+    if (layout == SX_NHWC) {
+        const int64_t total = n * hw * 3;
+        if (dtype == SX_U8) {
+            unsigned grid = stream_grid((total / 48 + kThreads - 1) / kThreads + 1, 8);
+            hist_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), total, cnt);
+        } else {
+            unsigned grid = stream_grid((total / 12 + kThreads - 1) / kThreads + 1, 8);
+            hist_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), total, cnt);
+        }
+        SX_LAUNCHED("hist_nhwc_kernel");
+        return SX_OK;
+    }
+    if (dtype == SX_U8) {
+        const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
+        const int64_t items = n * tiles;
+        if (g_hist_byte_counters) {
+            const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * ByteCounters::kBytesPerWarp;
+            static bool attr_set = false;
+            if (!attr_set) {
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
+            dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
+            grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
+            hist_u8_planar_kernel<true><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
+        } else {
+            const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * 256 * sizeof(unsigned);
+            dim3 grid(stream_grid(items, 8), 3);
+            grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
+            hist_u8_planar_kernel<false><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
+        }
+        SX_LAUNCHED("hist_u8_planar_kernel");
+    } else {
+        const int64_t tiles = max_i64(1, (hw / 4 + kTileVecs - 1) / kTileVecs);
+        dim3 grid(stream_grid(n * tiles, 6), 3);
+        grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
+        hist_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), hw, n, tiles, cnt);
+        SX_LAUNCHED("hist_f32_planar_kernel");
+    }
+    return SX_OK;
+}
+
+int sx_hm_ref_hist(const uint64_t *counts, float *ref_hist, sx_stream_t stream) {
+    SX_REQUIRE(counts && ref_hist, "NULL argument");
+    ref_hist_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), ref_hist);
+    SX_LAUNCHED("ref_hist_kernel");
+    return SX_OK;
+}
+
+int sx_hm_ref_cdf(const float *ref_hist, float *ref_cdf, sx_stream_t stream) {
+    SX_REQUIRE(ref_hist && ref_cdf, "NULL argument");
+    ref_cdf_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(ref_hist, ref_cdf);
+    SX_LAUNCHED("ref_cdf_kernel");
+    return SX_OK;
+}
+
+int sx_hm_build_lut(const uint64_t *counts, int64_t npix, const float *ref_cdf, float *lut, sx_stream_t stream) {
+    SX_REQUIRE(counts && ref_cdf && lut, "NULL argument");
+    build_lut_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)npix, ref_cdf, lut);
+    SX_LAUNCHED("build_lut_kernel");
+    return SX_OK;
+}
+
+int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const float *lut, void *out, sx_stream_t stream_) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    SX_REQUIRE(lut && out, "NULL argument");
+    SX_REQUIRE(layout == SX_NCHW || layout == SX_NHWC, "layout must be SX_NCHW or SX_NHWC, got %d", layout);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int64_t hw = h * w;
+    if (n == 0 || hw == 0) return SX_OK;
+    if (layout == SX_NHWC) {
+        const int64_t total = n * hw * 3;
+        if (dtype == SX_U8) {
+            unsigned grid = stream_grid((total / 48 + kThreads - 1) / kThreads + 1, 8);
+            apply_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), total, lut);
+        } else {
+            unsigned grid = stream_grid((total / 12 + kThreads - 1) / kThreads + 1, 8);
+            apply_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), total, lut);
+        }
+        SX_LAUNCHED("apply_nhwc_kernel");
+        return SX_OK;
+    }
+    const int64_t planes = n * 3;
+    if (dtype == SX_U8) {
+        const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
+        unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
+        apply_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, planes, tiles, lut);
+        SX_LAUNCHED("apply_u8_planar_kernel");
+    } else {
+        const int64_t tiles = max_i64(1, (hw / 4 + kTileVecs - 1) / kTileVecs);
+        unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
+        apply_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), hw, planes, tiles, lut);
+        SX_LAUNCHED("apply_f32_planar_kernel");
+    }
+    return SX_OK;
+}
+
+// workspace: counts u64[768] | ref_cdf f32[768] | lut f32[768]
+int64_t sx_hm_workspace_bytes(void) { return 768 * 8 + 768 * 4 + 768 * 4; }
+
+int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const float *ref_hist, void *out, void *workspace, int64_t workspace_bytes, sx_stream_t stream) {
+    SX_REQUIRE(workspace && workspace_bytes >= sx_hm_workspace_bytes(), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_hm_workspace_bytes());
+    SX_REQUIRE(ref_hist != nullptr, "ref_hist is NULL");
+    auto *counts = static_cast<uint64_t *>(workspace);
+    auto *ref_cdf = reinterpret_cast<float *>(counts + 768);
+    auto *lut = ref_cdf + 768;
+    SX_CUDA(cudaMemsetAsync(counts, 0, 768 * 8, static_cast<cudaStream_t>(stream)));
+    if (int rc = sx_hm_hist(images, dtype, layout, n, h, w, counts, stream)) return rc;
+    if (int rc = sx_hm_ref_cdf(ref_hist, ref_cdf, stream)) return rc;
+    if (int rc = sx_hm_build_lut(counts, n * h * w, ref_cdf, lut, stream)) return rc;
+    return sx_hm_apply(images, dtype, layout, n, h, w, lut, out, stream);
+}
+
+int sx_hm_fit(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, float *ref_hist, void *workspace, int64_t workspace_bytes, sx_stream_t stream) {
+    SX_REQUIRE(workspace && workspace_bytes >= sx_hm_workspace_bytes(), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_hm_workspace_bytes());
+    auto *counts = static_cast<uint64_t *>(workspace);
+    SX_CUDA(cudaMemsetAsync(counts, 0, 768 * 8, static_cast<cudaStream_t>(stream)));
+    if (int rc = sx_hm_hist(images, dtype, layout, n, h, w, counts, stream)) return rc;
+    return sx_hm_ref_hist(counts, ref_hist, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// lib.cu -- library-level entry points: error reporting, device info, launch counter.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace sx {
+
+static thread_local char g_error[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Per-device cached attributes (the only global mutable state besides the launch counter).
+struct DevCache {
+    int sms = 0;
+    int64_t l2 = 0;
+};
+static DevCache g_dev[64];
+
+static DevCache &dev() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) d = 0;
+    DevCache &c = g_dev[d];
+    if (c.sms == 0) {
+        int sms = 0, l2 = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d);
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, d);
+        c.l2 = l2;
+        c.sms = sms > 0 ? sms : 148;
+    }
+    return c;
+}
+
+int sm_count() { return dev().sms; }
+int64_t l2_bytes() { return dev().l2; }
+
+}  // namespace sx
+
+extern "C" {
+
+int sx_abi_version(void) { return SX_ABI_VERSION; }
+
+const char *sx_last_error(void) { return sx::g_error; }
+
+int64_t sx_kernel_launches(void) { return sx::g_launches.load(std::memory_order_relaxed); }
+
+int sx_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *l2_bytes) {
+    int d = 0;
+    SX_CUDA(cudaGetDevice(&d));
+    int sms = 0, maj = 0, min = 0, l2 = 0;
+    SX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
+    SX_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, d));
+    SX_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, d));
+    SX_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, d));
+    if (sm_count) *sm_count = sms;
+    if (cc_major) *cc_major = maj;
+    if (cc_minor) *cc_minor = min;
+    if (l2_bytes) *l2_bytes = l2;
+    return SX_OK;
+}
+
+}  // extern "C"

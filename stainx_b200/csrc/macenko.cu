@@ -1,0 +1,896 @@
+// macenko.cu -- Macenko stain normalisation on B200, without a sort and without materialising
+// OD / phi / concentration tensors.
+//
+// Reference semantics: src/stainx/backends/torch_backend.py:L362-560 (torch CPU oracle);
+// code replaced: csrc/macenko.cu:L145-262 (one-CTA-per-image covariance + analytic eigh) and the
+// ATen pipeline of src/stainx_cuda_torch/csrc/macenko.cu:L67-266 (OD copies, three full sorts).
+//
+// Every pixel pass reads the RGB planes with 128-bit loads and recomputes OD in registers:
+//   moments        OD, tissue mask, shifted first/second moments, per-channel OD range   (M1-M3)
+//   hist(ANGLE,0)  12-bit histogram of a monotone 24-bit key of phi over the kept rows     (M5-M6)
+//   hist(ANGLE,1)  the 12 low bits inside the two selected bins + exact min/max per sub-bin
+//   hist(CONC,0/1) the same two levels for the two concentration rows over all rows        (M8-M9)
+//   apply          concentrations -> rescale -> OD' -> RGB                                 (M10)
+// with one-CTA-per-slot kernels in between (eigen-decomposition, rank search, HE / pinv).
+//
+// Order statistics: phi = atan2(y, x) is never evaluated per pixel.  The selection runs on the
+// "diamond angle" p(y, x) in [-2, 2], a monotone function of atan2(y, x), quantised to 24 bits;
+// the selected pixel's (cos, sin) is recovered from p in closed form.  Concentration keys are a
+// linear 24-bit quantisation of [c_lo, c_hi], bounds derived from the OD range and pinv(HE).
+// Level 1 records the exact float min / max of every 24-bit cell, so the returned value is an
+// exact order statistic whenever the cell holds one distinct value (always, in practice) and is
+// otherwise within 2^-24 of the key range.
+#include "common.cuh"
+
+namespace sx {
+namespace macenko {
+
+constexpr int kThreads = 256;
+constexpr int kBins = 4096;      // per level
+constexpr int kKeyBits = 24;
+constexpr float kKeyMax = 16777215.0f;
+constexpr float kBeta = 0.15f;   // torch_backend.py:L542
+constexpr float kShift = 0.75f;  // moments are accumulated about this OD value
+
+constexpr float kLn2 = 0.693147180559945309f;
+constexpr float kLog2_240 = 7.906890595608519f;
+
+// ---- workspace layout (regions are contiguous over slots so that each can be all-reduced) ----
+struct SlotState {
+    float e[6];           // E (3x2) row-major: [i][0] = middle eigenvector, [i][1] = largest
+    int use_all;          // < 3 rows pass the mask: use every row (L409-410)
+    int pad0;
+    long long n_sel;      // rows entering the angle selection
+    long long n_all;      // rows in the slot
+    int bin1[2];          // selected level-0 bin per query
+    long long rank1[2];   // rank inside that bin
+    float val[2];         // selected values (angle: diamond angle p; conc: concentration)
+    float pinv[6];        // (HE^T HE)^-1 HE^T, 2x3 row-major
+    float c_lo[2];        // concentration key mapping: key = (C - c_lo) * c_scale
+    float c_scale[2];
+};
+
+struct Layout {
+    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, state, total;
+    __host__ __device__ explicit Layout(int64_t slots) {
+        int64_t o = 0;
+        moments = o; o += slots * 12 * 8;
+        odrange = o; o += slots * 8 * 4;
+        hist1 = o;   o += slots * 2 * kBins * 4;
+        hist2 = o;   o += slots * 2 * kBins * 4;
+        vmin = o;    o += slots * 2 * kBins * 4;
+        vmax = o;    o += slots * 2 * kBins * 4;
+        fit = o;     o += slots * 8 * 4;
+        state = o;   o += slots * (int64_t)sizeof(SlotState);
+        total = (o + 255) / 256 * 256;
+    }
+};
+
+struct Ws {
+    double *moments;
+    float *odrange;
+    unsigned *hist1, *hist2;
+    float *vmin, *vmax, *fit;
+    SlotState *state;
+    __host__ __device__ Ws(void *base, int64_t slots) {
+        Layout L(slots);
+        char *b = static_cast<char *>(base);
+        moments = reinterpret_cast<double *>(b + L.moments);
+        odrange = reinterpret_cast<float *>(b + L.odrange);
+        hist1 = reinterpret_cast<unsigned *>(b + L.hist1);
+        hist2 = reinterpret_cast<unsigned *>(b + L.hist2);
+        vmin = reinterpret_cast<float *>(b + L.vmin);
+        vmax = reinterpret_cast<float *>(b + L.vmax);
+        fit = reinterpret_cast<float *>(b + L.fit);
+        state = reinterpret_cast<SlotState *>(b + L.state);
+    }
+};
+
+// ---- pixel loading -----------------------------------------------------------------------------
+// A thread owns kPix consecutive pixels of one image: one 128-bit load per colour plane
+// (float32: 4 px, uint8: 16 px).  Planes that are not 16-byte aligned use kPix = 1.
+template <typename T, bool VEC>
+struct Pix {
+    static constexpr int kPix = VEC ? (int)(16 / sizeof(T)) : 1;
+};
+
+// uint8: table of 256 entries (OD or log2(255x+1)), built per CTA with the accurate functions in
+// the reference's operation order: x = v / 255; t = x * 255 + 1 (torch_backend.py:L112, L550).
+template <bool WANT_OD>
+__device__ __forceinline__ void build_u8_table(float *tab) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        float x = __fdiv_rn((float)i, 255.0f);
+        float t = __fadd_rn(__fmul_rn(x, 255.0f), 1.0f);
+        tab[i] = WANT_OD ? -logf(__fdiv_rn(t, 240.0f)) : log2f(t);
+    }
+}
+
+// float32: l = log2(255x + 1) on the SFU; OD = ln2 * (log2(240) - l).  Every op is pinned (no
+// contraction) so that all passes see bit-identical OD values for the same pixel.
+__device__ __forceinline__ float f32_l(float x) { return __log2f(__fmaf_rn(x, 255.0f, 1.0f)); }
+__device__ __forceinline__ float l_to_od(float l) { return __fmul_rn(kLn2, __fsub_rn(kLog2_240, l)); }
+
+// Loads kPix pixels; v[c][k] = OD (WANT_OD) or log2(255x+1) of channel c of pixel k.
+template <typename T, bool VEC, bool WANT_OD>
+__device__ __forceinline__ void load_pixels(const T *__restrict__ base, int64_t hw, const float *tab, float (&v)[3][Pix<T, VEC>::kPix]) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (VEC) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float4 q = ld_stream(reinterpret_cast<const float4 *>(base + c * hw));
+                v[c][0] = q.x; v[c][1] = q.y; v[c][2] = q.z; v[c][3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c][0] = base[c * hw];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < kPix; ++k) {
+                float l = f32_l(v[c][k]);
+                v[c][k] = WANT_OD ? l_to_od(l) : l;
+            }
+    } else {
+        if constexpr (VEC) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint4 q = ld_stream(reinterpret_cast<const uint4 *>(base + c * hw));
+                unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < kPix; ++k) v[c][k] = tab[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c][0] = tab[base[c * hw]];
+        }
+    }
+}
+
+// CTA -> (image, chunk) mapping shared by all pixel passes.
+struct PassGeom {
+    int64_t n_img, hw;
+    int cpi;  // CTAs per image
+};
+
+// ---- keys ------------------------------------------------------------------------------------
+// Diamond angle: monotone in atan2(y, x) over (-pi, pi], range [-2, 2].
+__device__ __forceinline__ float diamond_angle(float y, float x) {
+    float a = __fadd_rn(fabsf(x), fabsf(y));
+    float r = a > 0.0f ? __fdividef(y, a) : 0.0f;
+    return x >= 0.0f ? r : (y >= 0.0f ? __fsub_rn(2.0f, r) : __fsub_rn(-2.0f, r));
+}
+__device__ __forceinline__ unsigned angle_key(float p) {  // [-2,2] -> [0, 2^24)
+    float u = __fmul_rn(__fadd_rn(p, 2.0f), 4194304.0f);
+    return (unsigned)__float2int_rz(fminf(fmaxf(u, 0.0f), kKeyMax));
+}
+__device__ __forceinline__ unsigned conc_key(float c, float lo, float scale) {
+    float u = __fmul_rn(__fsub_rn(c, lo), scale);
+    return (unsigned)__float2int_rz(fminf(fmaxf(u, 0.0f), kKeyMax));
+}
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+
+// ---- moments (M1-M3) ---------------------------------------------------------------------------
+template <typename T, bool VEC, bool FALLBACK>
+__global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    __shared__ float tab[256];
+    __shared__ double red[kThreads / 32][10];
+    __shared__ float redf[kThreads / 32][6];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = pooled ? 0 : slot0 + n;
+    if (FALLBACK && !ws.state[slot].use_all) return;
+    if constexpr (sizeof(T) == 1) {
+        build_u8_table<true>(tab);
+        __syncthreads();
+    }
+    const T *image = img + n * 3 * g.hw;
+    const int64_t groups = g.hw / kPix;
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
+        float od[3][kPix];
+        load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
+        float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < kPix; ++k) {
+            const float r = od[0][k], gg = od[1][k], b = od[2][k];
+            if (!FALLBACK) {
+                lo[0] = fminf(lo[0], r); lo[1] = fminf(lo[1], gg); lo[2] = fminf(lo[2], b);
+                hi[0] = fmaxf(hi[0], r); hi[1] = fmaxf(hi[1], gg); hi[2] = fmaxf(hi[2], b);
+            }
+            const bool keep = FALLBACK || fminf(r, fminf(gg, b)) >= kBeta;  // L404-405
+            const float m = keep ? 1.0f : 0.0f;
+            const float x = (r - kShift) * m, y = (gg - kShift) * m, z = (b - kShift) * m;
+            s[0] += m;
+            s[1] += x; s[2] += y; s[3] += z;
+            s[4] = __fmaf_rn(x, x, s[4]); s[5] = __fmaf_rn(x, y, s[5]); s[6] = __fmaf_rn(x, z, s[6]);
+            s[7] = __fmaf_rn(y, y, s[7]); s[8] = __fmaf_rn(y, z, s[8]); s[9] = __fmaf_rn(z, z, s[9]);
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        double r = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = r;
+    }
+    if (!FALLBACK) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = warp_max(-lo[c]), b = warp_max(hi[c]);
+            if (lane == 0) { redf[warp][c] = a; redf[warp][3 + c] = b; }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double r = 0.0;
+        for (int k = 0; k < kThreads / 32; ++k) r += red[k][threadIdx.x];
+        if (r != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], r);
+    } else if (!FALLBACK && threadIdx.x >= 32 && threadIdx.x < 38) {
+        const int i = threadIdx.x - 32;
+        float r = -INFINITY;
+        for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i]);
+        atomic_max_f32(&ws.odrange[slot * 8 + i], r);
+    } else if (!FALLBACK && threadIdx.x == 64 && chunk == 0) {
+        atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);
+    }
+}
+
+// ---- symmetric 3x3 eigen-decomposition (M4) ----------------------------------------------------
+// Cyclic Jacobi in double.  Columns sorted by ascending eigenvalue; each column's component of
+// largest magnitude is made positive (LAPACK leaves the sign implementation-defined; the result of
+// the normaliser does not depend on it for well-posed stain planes, SURVEY.md section 7 H-a).
+__device__ void eigh3(const double C[3][3], double V[3][3], double w[3]) {
+    double A[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { A[i][j] = C[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+        if (off <= 1e-300 || off <= 1e-22 * diag) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) { double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
+                for (int k = 0; k < 3; ++k) { double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
+                for (int k = 0; k < 3; ++k) { double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
+            }
+    }
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2 - i; ++j)
+            if (w[ord[j]] > w[ord[j + 1]]) { int t = ord[j]; ord[j] = ord[j + 1]; ord[j + 1] = t; }
+    double Vs[3][3], ws_[3];
+    for (int j = 0; j < 3; ++j) {
+        ws_[j] = w[ord[j]];
+        int big = 0;
+        for (int i = 1; i < 3; ++i)
+            if (fabs(V[i][ord[j]]) > fabs(V[big][ord[j]])) big = i;
+        const double sg = V[big][ord[j]] < 0 ? -1.0 : 1.0;
+        for (int i = 0; i < 3; ++i) Vs[i][j] = sg * V[i][ord[j]];
+    }
+    for (int i = 0; i < 3; ++i) { w[i] = ws_[i]; for (int j = 0; j < 3; ++j) V[i][j] = Vs[i][j]; }
+}
+
+// One thread per slot.  mode 0: first pass (may flag the fallback); mode 1: after the fallback pass.
+__global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_t count, int allow_fallback, int mode) {
+    Ws ws(ws_base, slots);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int64_t slot = slot0 + idx;
+    SlotState &st = ws.state[slot];
+    double *m = ws.moments + slot * 12;
+    if (mode == 0) {
+        st.n_all = (long long)(m[10] + 0.5);
+        st.use_all = 0;
+        if (allow_fallback && m[0] < 3.0) {  // L409-410
+            st.use_all = 1;
+            for (int i = 0; i < 10; ++i) m[i] = 0.0;
+            return;
+        }
+    } else if (!st.use_all) {
+        return;
+    }
+    const double n = m[0];
+    st.n_sel = (long long)(n + 0.5);
+    double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    if (n > 1.0) {  // unbiased covariance about the mean (L393-397); n <= 1 -> zeros (L395-396)
+        const double sx = m[1], sy = m[2], sz = m[3], d = n - 1.0;
+        C[0][0] = (m[4] - sx * sx / n) / d; C[0][1] = (m[5] - sx * sy / n) / d; C[0][2] = (m[6] - sx * sz / n) / d;
+        C[1][1] = (m[7] - sy * sy / n) / d; C[1][2] = (m[8] - sy * sz / n) / d; C[2][2] = (m[9] - sz * sz / n) / d;
+        C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
+    }
+    double V[3][3], w[3];
+    eigh3(C, V, w);
+    for (int i = 0; i < 3; ++i) { st.e[i * 2] = (float)V[i][1]; st.e[i * 2 + 1] = (float)V[i][2]; }  // L415
+}
+
+// ---- order-statistic histogram passes ----------------------------------------------------------
+template <typename T, bool VEC, int STAGE, int LEVEL>
+__global__ void __launch_bounds__(kThreads) hist_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    constexpr int kQ = (STAGE == SX_STAGE_CONC) ? 2 : 1;  // level-0 histograms per CTA
+    __shared__ float tab[256];
+    __shared__ unsigned sh[LEVEL == 0 ? kQ * kBins : 1];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = pooled ? 0 : slot0 + n;
+    const SlotState st = ws.state[slot];
+    if constexpr (sizeof(T) == 1) build_u8_table<true>(tab);
+    if constexpr (LEVEL == 0)
+        for (int i = threadIdx.x; i < kQ * kBins; i += kThreads) sh[i] = 0u;
+    __syncthreads();
+    unsigned *h2 = ws.hist2 + slot * 2 * kBins;
+    float *vmin = ws.vmin + slot * 2 * kBins;
+    float *vmax = ws.vmax + slot * 2 * kBins;
+
+    const T *image = img + n * 3 * g.hw;
+    const int64_t groups = g.hw / kPix;
+    for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
+        float od[3][kPix];
+        load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
+#pragma unroll
+        for (int k = 0; k < kPix; ++k) {
+            const float r = od[0][k], gg = od[1][k], b = od[2][k];
+            if constexpr (STAGE == SX_STAGE_ANGLE) {
+                const bool keep = st.use_all || fminf(r, fminf(gg, b)) >= kBeta;
+                if (!keep) continue;
+                const float t0 = dot3(r, gg, b, st.e[0], st.e[2], st.e[4]);  // That[:,0] (L417)
+                const float t1 = dot3(r, gg, b, st.e[1], st.e[3], st.e[5]);  // That[:,1]
+                const float p = diamond_angle(t1, t0);                       // ~ atan2(t1, t0) (L418)
+                const unsigned key = angle_key(p);
+                if constexpr (LEVEL == 0) {
+                    atomicAdd(&sh[key >> 12], 1u);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if ((int)(key >> 12) == st.bin1[q]) {
+                            const int sub = q * kBins + (int)(key & 4095u);
+                            atomicAdd(&h2[sub], 1u);
+                            atomic_min_f32(&vmin[sub], p);
+                            atomic_max_f32(&vmax[sub], p);
+                        }
+                }
+            } else {
+                const float c0 = dot3(r, gg, b, st.pinv[0], st.pinv[1], st.pinv[2]);  // L444
+                const float c1 = dot3(r, gg, b, st.pinv[3], st.pinv[4], st.pinv[5]);
+                const unsigned k0 = conc_key(c0, st.c_lo[0], st.c_scale[0]);
+                const unsigned k1 = conc_key(c1, st.c_lo[1], st.c_scale[1]);
+                if constexpr (LEVEL == 0) {
+                    atomicAdd(&sh[k0 >> 12], 1u);
+                    atomicAdd(&sh[kBins + (k1 >> 12)], 1u);
+                } else {
+                    if ((int)(k0 >> 12) == st.bin1[0]) {
+                        const int sub = (int)(k0 & 4095u);
+                        atomicAdd(&h2[sub], 1u);
+                        atomic_min_f32(&vmin[sub], c0);
+                        atomic_max_f32(&vmax[sub], c0);
+                    }
+                    if ((int)(k1 >> 12) == st.bin1[1]) {
+                        const int sub = kBins + (int)(k1 & 4095u);
+                        atomicAdd(&h2[sub], 1u);
+                        atomic_min_f32(&vmin[sub], c1);
+                        atomic_max_f32(&vmax[sub], c1);
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (LEVEL == 0) {
+        __syncthreads();
+        unsigned *h1 = ws.hist1 + slot * 2 * kBins;
+        for (int i = threadIdx.x; i < kQ * kBins; i += kThreads)
+            if (sh[i]) atomicAdd(&h1[i], sh[i]);
+    }
+}
+
+// ---- rank search (one CTA per slot) --------------------------------------------------------------
+// Nearest-rank index (torch_backend.py:L362-365): round_half_even(0.01 * q * (n - 1)), in double.
+__device__ __forceinline__ long long rank_index(double q, long long n) { return (long long)rint(0.01 * q * (double)(n - 1)); }
+
+// Finds the bin of `hist` (kBins entries) holding 0-based rank k; returns bin, rank inside it and
+// its count through shared memory.  Called by all kThreads threads.
+__device__ void find_rank(const unsigned *hist, long long k, int *out_bin, long long *out_rank, unsigned *out_count) {
+    __shared__ unsigned long long part[kThreads];
+    constexpr int kPer = kBins / kThreads;
+    unsigned long long s = 0;
+    for (int i = 0; i < kPer; ++i) s += hist[threadIdx.x * kPer + i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long cum = 0;
+        int t = 0;
+        for (; t < kThreads - 1; ++t) {
+            if (cum + part[t] > (unsigned long long)k) break;
+            cum += part[t];
+        }
+        int b = t * kPer;
+        const int last = t * kPer + kPer - 1;
+        for (; b < last; ++b) {
+            if (cum + hist[b] > (unsigned long long)k) break;
+            cum += hist[b];
+        }
+        *out_bin = b;
+        *out_rank = k - (long long)cum;
+        *out_count = hist[b];
+    }
+    __syncthreads();
+}
+
+// Unit direction (cos, sin) of a diamond angle p in [-2, 2].
+__device__ __forceinline__ void diamond_to_unit(float p, double &c, double &s) {
+    double x, y;
+    const double pd = (double)p;
+    if (pd > 1.0) { x = -(pd - 1.0); y = 2.0 - pd; }
+    else if (pd < -1.0) { x = 1.0 + pd; y = -2.0 - pd; }
+    else { x = 1.0 - fabs(pd); y = pd; }
+    const double h = sqrt(x * x + y * y);
+    c = x / h; s = y / h;
+}
+
+__global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage, int level) {
+    Ws ws(ws_base, slots);
+    const int64_t slot = slot0 + blockIdx.x;
+    SlotState &st = ws.state[slot];
+    __shared__ int s_bin;
+    __shared__ long long s_rank;
+    __shared__ unsigned s_count;
+    for (int q = 0; q < 2; ++q) {
+        if (level == 0) {
+            const long long n = stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all;
+            const double pct = stage == SX_STAGE_ANGLE ? (q == 0 ? 1.0 : 99.0) : 99.0;  // L421-422, L447-448
+            long long k = rank_index(pct, n);
+            if (k < 0) k = 0;
+            if (k > n - 1) k = n - 1;
+            const unsigned *h = ws.hist1 + slot * 2 * kBins + (stage == SX_STAGE_ANGLE ? 0 : q * kBins);
+            find_rank(h, k, &s_bin, &s_rank, &s_count);
+            if (threadIdx.x == 0) { st.bin1[q] = s_bin; st.rank1[q] = s_rank; }
+        } else {
+            const unsigned *h = ws.hist2 + slot * 2 * kBins + q * kBins;
+            find_rank(h, st.rank1[q], &s_bin, &s_rank, &s_count);
+            if (threadIdx.x == 0) {
+                const float lo = ws.vmin[slot * 2 * kBins + q * kBins + s_bin];
+                const float hi = ws.vmax[slot * 2 * kBins + q * kBins + s_bin];
+                float v = lo;
+                if (s_count > 1u && hi > lo) v = lo + (hi - lo) * (float)((double)s_rank / (double)(s_count - 1u));
+                st.val[q] = v;
+            }
+        }
+        __syncthreads();
+    }
+    if (level != 1 || threadIdx.x != 0) return;
+    float *fit = ws.fit + slot * 8;
+    if (stage == SX_STAGE_ANGLE) {
+        // M7 (L425-439): v = E (cos phi, sin phi); HE columns ordered by first component.
+        double c0, s0, c1, s1;
+        diamond_to_unit(st.val[0], c0, s0);
+        diamond_to_unit(st.val[1], c1, s1);
+        float vmin[3], vmax[3];
+        for (int i = 0; i < 3; ++i) {
+            vmin[i] = (float)((double)st.e[i * 2] * c0 + (double)st.e[i * 2 + 1] * s0);
+            vmax[i] = (float)((double)st.e[i * 2] * c1 + (double)st.e[i * 2 + 1] * s1);
+        }
+        const bool min_first = vmin[0] > vmax[0];
+        float he[6];
+        for (int i = 0; i < 3; ++i) { he[i * 2] = min_first ? vmin[i] : vmax[i]; he[i * 2 + 1] = min_first ? vmax[i] : vmin[i]; }
+        for (int i = 0; i < 6; ++i) fit[i] = he[i];
+        // M8 (L444): least squares via the normal equations, in double.
+        double a00 = 0, a01 = 0, a11 = 0;
+        for (int i = 0; i < 3; ++i) { a00 += (double)he[i * 2] * he[i * 2]; a01 += (double)he[i * 2] * he[i * 2 + 1]; a11 += (double)he[i * 2 + 1] * he[i * 2 + 1]; }
+        const double det = a00 * a11 - a01 * a01;
+        for (int i = 0; i < 3; ++i) {
+            st.pinv[i] = (float)((a11 * he[i * 2] - a01 * he[i * 2 + 1]) / det);
+            st.pinv[3 + i] = (float)((-a01 * he[i * 2] + a00 * he[i * 2 + 1]) / det);
+        }
+        // Key range of each concentration row from the per-channel OD range (interval arithmetic).
+        const float *rg = ws.odrange + slot * 8;
+        for (int j = 0; j < 2; ++j) {
+            double lo = 0, hi = 0;
+            for (int c = 0; c < 3; ++c) {
+                const double pj = st.pinv[j * 3 + c], a = pj * (double)(-rg[c]), b = pj * (double)rg[3 + c];
+                lo += fmin(a, b); hi += fmax(a, b);
+            }
+            const double pad = 1e-6 * (fabs(lo) + fabs(hi)) + 1e-12;
+            lo -= pad; hi += pad;
+            st.c_lo[j] = (float)lo;
+            st.c_scale[j] = (float)(16777216.0 / (hi - lo));
+        }
+    } else {
+        fit[6] = st.val[0];  // maxC (L447-449)
+        fit[7] = st.val[1];
+    }
+}
+
+// ---- apply (M10) ---------------------------------------------------------------------------------
+// OD' = he_ref . diag(maxc_ref / maxC) . pinv . OD is a 3x3 map M3 of OD.  With l = log2(255x+1):
+//   240 exp(-OD'_c) = 2^( b_c + sum_k M3[c][k] l_k ),   b_c = log2(240) (1 - sum_k M3[c][k]).
+// OUT: 0 = uint8 (truncated), 1 = float32 in [0,255], 2 = float32 / 255 (normalize_to_0_1).
+template <typename T, bool VEC, int OUT>
+__global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ img, void *__restrict__ out_, PassGeom g, int64_t slot0, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    __shared__ float tab[256];
+    __shared__ float unit_tab[256];
+    __shared__ float coef[12];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = slot0 + n;
+    if constexpr (sizeof(T) == 1) build_u8_table<false>(tab);
+    if constexpr (OUT == 2 && sizeof(T) == 1)
+        for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
+    if (threadIdx.x < 3) {
+        const int c = threadIdx.x;
+        const SlotState &st = ws.state[slot];
+        const float *fit = ws.fit + slot * 8;
+        const float n0 = __fdiv_rn(maxc_ref[0], fit[6]), n1 = __fdiv_rn(maxc_ref[1], fit[7]);  // L452
+        float sum = 0.0f;
+        for (int k = 0; k < 3; ++k) {
+            const float m = he_ref[c * 2] * n0 * st.pinv[k] + he_ref[c * 2 + 1] * n1 * st.pinv[3 + k];
+            coef[c * 4 + k] = m;
+            sum += m;
+        }
+        float bias = kLog2_240 * (1.0f - sum);
+        if (OUT == 2 && sizeof(T) == 4) bias -= 7.994353436858858f;  // log2(255): fold the /255
+        coef[c * 4 + 3] = bias;
+    }
+    __syncthreads();
+    float A[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) A[c][k] = coef[c * 4 + k];
+    const float top = (OUT == 2 && sizeof(T) == 4) ? 1.0f : 255.0f;  // clamp(.., 0, 255) (L459)
+
+    const T *image = img + n * 3 * g.hw;
+    const int64_t groups = g.hw / kPix;
+    for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
+        float l[3][kPix];
+        load_pixels<T, VEC, false>(image + gi * kPix, g.hw, tab, l);
+        float o[3][kPix];
+#pragma unroll
+        for (int k = 0; k < kPix; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float e = __fmaf_rn(A[c][2], l[2][k], __fmaf_rn(A[c][1], l[1][k], __fmaf_rn(A[c][0], l[0][k], A[c][3])));
+                o[c][k] = fminf(exp2f(e), top);
+            }
+        const int64_t off = n * 3 * g.hw + gi * kPix;
+        if constexpr (OUT == 0) {
+            uint8_t *out = static_cast<uint8_t *>(out_) + off;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if constexpr (VEC) {
+                    unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int k = 0; k < kPix; ++k) w[k >> 2] |= (unsigned)__float2int_rz(o[c][k]) << (8 * (k & 3));
+                    st_stream(reinterpret_cast<uint4 *>(out + c * g.hw), make_uint4(w[0], w[1], w[2], w[3]));
+                } else {
+                    out[c * g.hw] = (uint8_t)__float2int_rz(o[c][0]);
+                }
+            }
+        } else {
+            float *out = static_cast<float *>(out_) + off;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if constexpr (sizeof(T) == 1) {
+                    // uint8 input: the reference truncates to uint8 first (L560), then casts / divides
+#pragma unroll
+                    for (int k = 0; k < kPix; ++k) {
+                        const int q = __float2int_rz(o[c][k]);
+                        o[c][k] = OUT == 2 ? unit_tab[q] : (float)q;
+                    }
+                }
+                if constexpr (VEC) {
+#pragma unroll
+                    for (int k = 0; k < kPix; k += 4) st_stream(reinterpret_cast<float4 *>(out + c * g.hw + k), make_float4(o[c][k], o[c][k + 1], o[c][k + 2], o[c][k + 3]));
+                } else {
+                    out[c * g.hw] = o[c][0];
+                }
+            }
+        }
+    }
+}
+
+__global__ void init_kernel(void *ws_base, int64_t slots) {
+    Ws ws(ws_base, slots);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = 2 * kBins;
+    if (i < slots * per) {
+        ws.hist1[i] = 0u;
+        ws.hist2[i] = 0u;
+        ws.vmin[i] = INFINITY;
+        ws.vmax[i] = -INFINITY;
+    }
+    if (i < slots * 12) ws.moments[i] = 0.0;
+    if (i < slots * 8) { ws.odrange[i] = -INFINITY; ws.fit[i] = 0.0f; }
+    if (i < slots) {
+        SlotState z = {};
+        ws.state[i] = z;
+    }
+}
+
+// Re-arm the level-1 arrays between the ANGLE and CONC stages.
+__global__ void rearm_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_t count) {
+    Ws ws(ws_base, slots);
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < count * 2 * kBins) {
+        const int64_t i = slot0 * 2 * kBins + j;
+        ws.hist1[i] = 0u;
+        ws.hist2[i] = 0u;
+        ws.vmin[i] = INFINITY;
+        ws.vmax[i] = -INFINITY;
+    }
+}
+
+static int g_ctas_per_sm = 4;
+static int64_t g_group_bytes = 64ll << 20;  // images per L2-resident group = g_group_bytes / image bytes
+
+static PassGeom make_geom(int64_t n, int64_t hw, int kpix) {
+    PassGeom g;
+    g.n_img = n;
+    g.hw = hw;
+    const int64_t groups = hw / kpix;
+    int64_t want = ((int64_t)sm_count() * g_ctas_per_sm + n - 1) / (n > 0 ? n : 1);
+    const int64_t most = (groups + kThreads - 1) / kThreads;
+    if (want > most) want = most;
+    if (want < 1) want = 1;
+    g.cpi = (int)want;
+    return g;
+}
+
+template <typename T>
+static bool vec_ok(const void *a, const void *b, int64_t hw) {
+    return hw % (16 / (int64_t)sizeof(T)) == 0 && aligned16(a) && (b == nullptr || aligned16(b));
+}
+
+}  // namespace macenko
+}  // namespace sx
+
+using namespace sx;
+using namespace sx::macenko;
+
+#define SX_DISPATCH_TV(dtype, vec, ...)                                        \
+    do {                                                                       \
+        if ((dtype) == SX_F32) {                                               \
+            using T = float;                                                   \
+            if (vec) { constexpr bool VEC = true; __VA_ARGS__; }               \
+            else { constexpr bool VEC = false; __VA_ARGS__; }                  \
+        } else {                                                               \
+            using T = uint8_t;                                                 \
+            if (vec) { constexpr bool VEC = true; __VA_ARGS__; }               \
+            else { constexpr bool VEC = false; __VA_ARGS__; }                  \
+        }                                                                      \
+    } while (0)
+
+static bool images_vec_ok(const void *images, const void *out, int dtype, int out_dtype, int64_t hw) {
+    bool in_ok = dtype == SX_F32 ? vec_ok<float>(images, nullptr, hw) : vec_ok<uint8_t>(images, nullptr, hw);
+    if (!in_ok) return false;
+    if (out == nullptr) return true;
+    // the output plane offsets are multiples of hw elements of the OUTPUT type
+    const int64_t in_pix = dtype == SX_F32 ? 4 : 16;
+    (void)out_dtype;
+    return aligned16(out) && hw % in_pix == 0;
+}
+
+extern "C" {
+
+int sx_macenko_set_tuning(int ctas_per_sm, int64_t group_bytes) {
+    if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
+    if (group_bytes >= 0) g_group_bytes = group_bytes;
+    return SX_OK;
+}
+
+int64_t sx_macenko_workspace_bytes(int64_t slots) { return slots > 0 ? Layout(slots).total : 0; }
+
+int sx_macenko_region(int64_t slots, int region, int64_t *offset, int64_t *bytes) {
+    SX_REQUIRE(slots > 0 && offset && bytes, "bad arguments");
+    Layout L(slots);
+    switch (region) {
+        case SX_REGION_MOMENTS: *offset = L.moments; *bytes = slots * 12 * 8; break;
+        case SX_REGION_ODRANGE: *offset = L.odrange; *bytes = slots * 8 * 4; break;
+        case SX_REGION_HIST1: *offset = L.hist1; *bytes = slots * 2 * kBins * 4; break;
+        case SX_REGION_HIST2: *offset = L.hist2; *bytes = slots * 2 * kBins * 4; break;
+        case SX_REGION_VMIN: *offset = L.vmin; *bytes = slots * 2 * kBins * 4; break;
+        case SX_REGION_VMAX: *offset = L.vmax; *bytes = slots * 2 * kBins * 4; break;
+        case SX_REGION_FIT: *offset = L.fit; *bytes = slots * 8 * 4; break;
+        default: return sx::fail(SX_ERR_INVALID, "unknown region %d", region);
+    }
+    return SX_OK;
+}
+
+int sx_macenko_begin(void *workspace, int64_t slots, sx_stream_t stream) {
+    SX_REQUIRE(workspace && slots > 0, "bad workspace");
+    const int64_t items = slots * 2 * kBins;
+    init_kernel<<<(unsigned)((items + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, slots);
+    SX_LAUNCHED("macenko::init_kernel");
+    return SX_OK;
+}
+
+static int check_slots(int64_t n, int pooled, int64_t slot0, int64_t slots) {
+    SX_REQUIRE(slots > 0, "slots must be > 0");
+    if (pooled) return SX_OK;
+    SX_REQUIRE(slot0 >= 0 && slot0 + n <= slots, "slot range [%lld, %lld) outside [0, %lld)", (long long)slot0, (long long)(slot0 + n), (long long)slots);
+    return SX_OK;
+}
+
+int sx_macenko_moments(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled, int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream_) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    if (int rc = check_slots(n, pooled, slot0, slots)) return rc;
+    SX_REQUIRE(workspace, "workspace is NULL");
+    const int64_t hw = h * w;
+    if (n == 0 || hw == 0) return SX_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool vec = images_vec_ok(images, nullptr, dtype, dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
+        moments_kernel<T, VEC, false><<<(unsigned)(n * g.cpi), kThreads, 0, stream>>>(static_cast<const T *>(images), g, pooled, slot0, workspace, slots);
+    });
+    SX_LAUNCHED("macenko::moments_kernel");
+    return SX_OK;
+}
+
+int sx_macenko_moments_fallback(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream_) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    if (int rc = check_slots(n, 0, slot0, slots)) return rc;
+    SX_REQUIRE(workspace, "workspace is NULL");
+    const int64_t hw = h * w;
+    if (n == 0 || hw == 0) return SX_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool vec = images_vec_ok(images, nullptr, dtype, dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
+        moments_kernel<T, VEC, true><<<(unsigned)(n * g.cpi), kThreads, 0, stream>>>(static_cast<const T *>(images), g, 0, slot0, workspace, slots);
+    });
+    SX_LAUNCHED("macenko::moments_kernel<fallback>");
+    return SX_OK;
+}
+
+static int check_range(int64_t slot0, int64_t count, int64_t slots) {
+    SX_REQUIRE(slots > 0 && slot0 >= 0 && count >= 0 && slot0 + count <= slots, "slot range [%lld, %lld) outside [0, %lld)", (long long)slot0, (long long)(slot0 + count), (long long)slots);
+    return SX_OK;
+}
+
+int sx_macenko_basis(void *workspace, int64_t slots, int64_t slot0, int64_t count, int allow_fallback, sx_stream_t stream) {
+    SX_REQUIRE(workspace, "workspace is NULL");
+    if (int rc = check_range(slot0, count, slots)) return rc;
+    if (count == 0) return SX_OK;
+    basis_kernel<<<(unsigned)((count + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(workspace, slots, slot0, count, allow_fallback, 0);
+    SX_LAUNCHED("macenko::basis_kernel");
+    return SX_OK;
+}
+
+int sx_macenko_basis_fallback(void *workspace, int64_t slots, int64_t slot0, int64_t count, sx_stream_t stream) {
+    SX_REQUIRE(workspace, "workspace is NULL");
+    if (int rc = check_range(slot0, count, slots)) return rc;
+    if (count == 0) return SX_OK;
+    basis_kernel<<<(unsigned)((count + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(workspace, slots, slot0, count, 1, 1);
+    SX_LAUNCHED("macenko::basis_kernel<fallback>");
+    return SX_OK;
+}
+
+int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled, int64_t slot0, int stage, int level, void *workspace, int64_t slots, sx_stream_t stream_) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    if (int rc = check_slots(n, pooled, slot0, slots)) return rc;
+    SX_REQUIRE(workspace, "workspace is NULL");
+    SX_REQUIRE((stage == SX_STAGE_ANGLE || stage == SX_STAGE_CONC) && (level == 0 || level == 1), "bad stage/level (%d, %d)", stage, level);
+    const int64_t hw = h * w;
+    if (n == 0 || hw == 0) return SX_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool vec = images_vec_ok(images, nullptr, dtype, dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
+        const unsigned grid = (unsigned)(n * g.cpi);
+        const T *p = static_cast<const T *>(images);
+        if (stage == SX_STAGE_ANGLE && level == 0) hist_kernel<T, VEC, SX_STAGE_ANGLE, 0><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+        else if (stage == SX_STAGE_ANGLE) hist_kernel<T, VEC, SX_STAGE_ANGLE, 1><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+        else if (level == 0) hist_kernel<T, VEC, SX_STAGE_CONC, 0><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+        else hist_kernel<T, VEC, SX_STAGE_CONC, 1><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+    });
+    SX_LAUNCHED("macenko::hist_kernel");
+    return SX_OK;
+}
+
+int sx_macenko_select(void *workspace, int64_t slots, int64_t slot0, int64_t count, int stage, int level, sx_stream_t stream_) {
+    SX_REQUIRE(workspace, "workspace is NULL");
+    if (int rc = check_range(slot0, count, slots)) return rc;
+    SX_REQUIRE((stage == SX_STAGE_ANGLE || stage == SX_STAGE_CONC) && (level == 0 || level == 1), "bad stage/level (%d, %d)", stage, level);
+    if (count == 0) return SX_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    select_kernel<<<(unsigned)count, kThreads, 0, stream>>>(workspace, slots, slot0, stage, level);
+    SX_LAUNCHED("macenko::select_kernel");
+    if (stage == SX_STAGE_ANGLE && level == 1) {  // re-arm the histograms for the CONC stage
+        const int64_t items = count * 2 * kBins;
+        rearm_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(workspace, slots, slot0, count);
+        SX_LAUNCHED("macenko::rearm_kernel");
+    }
+    return SX_OK;
+}
+
+int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, sx_stream_t stream_) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    if (int rc = check_slots(n, 0, slot0, slots)) return rc;
+    SX_REQUIRE(workspace && he_ref && maxc_ref && out, "NULL argument");
+    SX_REQUIRE(out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8), "uint8 output requires uint8 input");
+    const bool unit = out_scale != 1.0f;
+    SX_REQUIRE(!unit || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
+    const int64_t hw = h * w;
+    if (n == 0 || hw == 0) return SX_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool vec = images_vec_ok(images, out, dtype, out_dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
+        const unsigned grid = (unsigned)(n * g.cpi);
+        const T *p = static_cast<const T *>(images);
+        if (out_dtype == SX_U8) apply_kernel<T, VEC, 0><<<grid, kThreads, 0, stream>>>(p, out, g, slot0, he_ref, maxc_ref, workspace, slots);
+        else if (!unit) apply_kernel<T, VEC, 1><<<grid, kThreads, 0, stream>>>(p, out, g, slot0, he_ref, maxc_ref, workspace, slots);
+        else apply_kernel<T, VEC, 2><<<grid, kThreads, 0, stream>>>(p, out, g, slot0, he_ref, maxc_ref, workspace, slots);
+    });
+    SX_LAUNCHED("macenko::apply_kernel");
+    return SX_OK;
+}
+
+int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    if (n == 0 || h * w == 0) return SX_OK;
+    SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(n), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_macenko_workspace_bytes(n));
+    const int64_t in_bytes = (dtype == SX_F32 ? 4 : 1) * 3 * h * w;
+    const int64_t out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * h * w;
+    int rc;
+    if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
+    // Every statistic is per image, so the batch is walked in groups of images whose RGB planes
+    // fit in L2 together: the first pass of a group streams it from HBM, the five later passes
+    // of the same group are served from L2.
+    int64_t group = g_group_bytes > 0 ? g_group_bytes / in_bytes : n;
+    if (group < 1) group = 1;
+    if (group > n) group = n;
+    for (int64_t i0 = 0; i0 < n; i0 += group) {
+        const int64_t cnt = (n - i0) < group ? (n - i0) : group;
+        const char *img = static_cast<const char *>(images) + i0 * in_bytes;
+        char *o = static_cast<char *>(out) + i0 * out_bytes;
+        if ((rc = sx_macenko_moments(img, dtype, cnt, h, w, 0, i0, workspace, n, s))) return rc;
+        if ((rc = sx_macenko_basis(workspace, n, i0, cnt, 1, s))) return rc;
+        if ((rc = sx_macenko_moments_fallback(img, dtype, cnt, h, w, i0, workspace, n, s))) return rc;
+        if ((rc = sx_macenko_basis_fallback(workspace, n, i0, cnt, s))) return rc;
+        for (int stage = 0; stage < 2; ++stage)
+            for (int level = 0; level < 2; ++level) {
+                if ((rc = sx_macenko_hist(img, dtype, cnt, h, w, 0, i0, stage, level, workspace, n, s))) return rc;
+                if ((rc = sx_macenko_select(workspace, n, i0, cnt, stage, level, s))) return rc;
+            }
+        if ((rc = sx_macenko_apply(img, dtype, cnt, h, w, i0, he_ref, maxc_ref, o, out_dtype, out_scale, workspace, n, s))) return rc;
+    }
+    return SX_OK;
+}
+
+int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    SX_REQUIRE(n > 0 && h * w > 0, "empty reference batch");
+    SX_REQUIRE(he && maxc, "NULL output");
+    SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(1), "workspace too small");
+    int rc;
+    if ((rc = sx_macenko_begin(workspace, 1, s))) return rc;
+    if ((rc = sx_macenko_moments(images, dtype, n, h, w, 1, 0, workspace, 1, s))) return rc;
+    if ((rc = sx_macenko_basis(workspace, 1, 0, 1, 0, s))) return rc;  // no fallback in fit (L483-487)
+    for (int stage = 0; stage < 2; ++stage)
+        for (int level = 0; level < 2; ++level) {
+            if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, level, workspace, 1, s))) return rc;
+            if ((rc = sx_macenko_select(workspace, 1, 0, 1, stage, level, s))) return rc;
+        }
+    Ws ws(workspace, 1);
+    SX_CUDA(cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
+    SX_CUDA(cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
+    return SX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,426 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and against golden
+vectors produced by the reference itself.
+
+Bars: histogram matching bit-exact (uint8 and float32); Reinhard / Macenko
+float32 max-abs <= 1e-3 on [0, 1]; uint8 outputs within 1 grey level (truncation knife edge, the
+reference's own PARITY_ATOL, tests/torch_cuda_interface/test_cuda_backend_parity_against_torch.py
+L27-28); Macenko HE <= 1e-4, maxC rel <= 1e-3 on Beer-Lambert tiles; on near-isotropic noise the
+oracle is evaluated with both middle-eigenvector signs (SURVEY.md section 7 H-a).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import golden
+from tests.helpers import best_sign_diff, he_batch, he_tile, noise_f32, noise_u8
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-3  # on [0, 1] outputs (BASELINE.json north_star)
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+# ======================================================================== histogram matching
+@pytest.mark.parametrize("name", ["hm_u8", "hm_f32", "hm_u8_uniform", "hm_u8_self", "hm_u8_sparse"])
+def test_hm_golden_bit_exact(cuda, name):
+    from stainx_b200 import HistogramMatching
+
+    g = golden(name)
+    n = HistogramMatching(device=cuda, backend="torch_cuda", channel_axis=1).fit(torch.from_numpy(g["ref"]).to(cuda))
+    assert np.array_equal(_np(torch.stack(n._ref_histograms_256)), g["ref_hist"])
+    out = n.transform(torch.from_numpy(g["src"]).to(cuda))
+    assert out.dtype == torch.from_numpy(g["out"]).dtype
+    assert np.array_equal(_np(out), g["out"])
+
+
+def test_hm_golden_nhwc(cuda):
+    from stainx_b200 import HistogramMatching
+
+    g = golden("hm_u8_nhwc")
+    n = HistogramMatching(device=cuda, backend="torch_cuda", channel_axis=-1).fit(torch.from_numpy(g["ref"]).to(cuda))
+    assert np.array_equal(_np(torch.stack(n._ref_histograms_256)), g["ref_hist"])
+    out = n.transform(torch.from_numpy(g["src"]).to(cuda))
+    assert tuple(out.shape) == g["out"].shape
+    assert np.array_equal(_np(out), g["out"])
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+@pytest.mark.parametrize("shape", [(1, 3, 1, 1), (2, 3, 7, 5), (3, 3, 64, 64), (1, 3, 321, 199), (2, 3, 256, 512), (5, 3, 130, 131), (1, 3, 1024, 1024)])
+def test_hm_vs_oracle(cuda, ox, dtype, shape):
+    from stainx_b200 import HistogramMatching
+
+    make = noise_u8 if dtype == "u8" else noise_f32
+    ref = make((1, 3, shape[2], shape[3]), 42, 1.7)
+    src = make(shape, 43, 0.6)
+    n = HistogramMatching(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    ref_hist = ox.hm_fit(ref.numpy())
+    assert np.array_equal(_np(torch.stack(n._ref_histograms_256)), ref_hist)
+    out = n.transform(src.to(cuda))
+    assert np.array_equal(_np(out), ox.hm_transform(src.numpy(), ref_hist))
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_hm_nhwc_vs_oracle(cuda, ox, dtype):
+    from stainx_b200 import HistogramMatching
+
+    make = noise_u8 if dtype == "u8" else noise_f32
+    ref = make((1, 3, 50, 70), 1, 2.0)
+    src = make((3, 3, 61, 47), 2, 0.8)
+    n = HistogramMatching(device=cuda, backend="torch_cuda", channel_axis=-1).fit(ref.permute(0, 2, 3, 1).contiguous().to(cuda))
+    out = n.transform(src.permute(0, 2, 3, 1).contiguous().to(cuda))
+    want = ox.hm_transform(src.numpy(), ox.hm_fit(ref.numpy())).transpose(0, 2, 3, 1)
+    assert np.array_equal(_np(out), want)
+
+
+def test_hm_misaligned_view_and_noncontiguous(cuda, ox):
+    """Planes that do not start on 16-byte boundaries, and a non-contiguous input."""
+    from stainx_b200 import HistogramMatching
+
+    ref = noise_u8((1, 3, 33, 35), 5)
+    big = noise_u8((3, 3, 33, 37), 6)
+    src = big[:, :, :, 1:36]  # non-contiguous view
+    n = HistogramMatching(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    out = n.transform(src.to(cuda))
+    assert np.array_equal(_np(out), ox.hm_transform(np.ascontiguousarray(src.numpy()), ox.hm_fit(ref.numpy())))
+
+
+def test_hm_empty_batch(cuda):
+    from stainx_b200 import HistogramMatching
+
+    n = HistogramMatching(device=cuda, backend="torch_cuda").fit(noise_u8((1, 3, 16, 16), 0).to(cuda))
+    out = n.transform(torch.empty((0, 3, 16, 16), dtype=torch.uint8, device=cuda))
+    assert tuple(out.shape) == (0, 3, 16, 16)
+
+
+def test_hm_phases_equal_fused(cuda):
+    from stainx_b200 import ops
+
+    ref = noise_u8((1, 3, 96, 96), 3, 1.5).to(cuda)
+    src = noise_u8((4, 3, 96, 96), 4, 0.7).to(cuda)
+    ref_hist = ops.hm_fit(ref)
+    fused = ops.hm_transform(src, ref_hist)
+    counts = ops.hm_hist(src)
+    # two half-batches accumulate into the same counts (what a sharded run all-reduces)
+    halves = ops.hm_hist(src[:2].contiguous())
+    ops.hm_hist(src[2:].contiguous(), counts=halves)
+    assert torch.equal(counts, halves)
+    assert int(counts.sum()) == src.numel()
+    lut = ops.hm_build_lut(counts, src.numel() // 3, ops.hm_ref_cdf(ref_hist))
+    lut_auto = ops.hm_build_lut(counts, -1, ops.hm_ref_cdf(ref_hist))
+    assert torch.equal(lut, lut_auto)
+    assert torch.equal(ops.hm_apply(src, lut), fused)
+
+
+def test_hm_full_size_properties(cuda):
+    """BASELINE config C2 (uint8 64x3x1024x1024): size-independent checks."""
+    from stainx_b200 import ops
+
+    g = torch.Generator(device=cuda).manual_seed(43)
+    src = (torch.rand((64, 3, 1024, 1024), device=cuda, generator=g) * 255).round().to(torch.uint8)
+    ref = (torch.rand((1, 3, 1024, 1024), device=cuda, generator=g).pow(2.0) * 255).round().to(torch.uint8)
+    counts = ops.hm_hist(src)
+    for c in range(3):  # histogram == bincount, and it accounts for every pixel
+        want = torch.bincount(src[:, c].reshape(-1).long(), minlength=256)
+        assert torch.equal(counts[c], want)
+    ref_hist = ops.hm_fit(ref)
+    lut = ops.hm_build_lut(counts, 64 * 1024 * 1024, ops.hm_ref_cdf(ref_hist))
+    assert bool((lut[:, 1:] >= lut[:, :-1]).all()), "LUT must be monotone"
+    out = ops.hm_transform(src, ref_hist)
+    lut8 = lut.to(torch.uint8)
+    for c in range(3):  # remap == gather through the LUT
+        assert torch.equal(out[:, c], lut8[c][src[:, c].long()])
+    # matching pulls the source histogram onto the reference: CDF distance shrinks
+    oc = ops.hm_hist(out).double()
+    rc = ops.hm_hist(ref).double()
+    sc = counts.double()
+    cdf = lambda x: torch.cumsum(x / x.sum(dim=1, keepdim=True), dim=1)  # noqa: E731
+    assert (cdf(oc) - cdf(rc)).abs().max() < (cdf(sc) - cdf(rc)).abs().max()
+    assert (cdf(oc) - cdf(rc)).abs().max() < 0.01
+
+
+# ======================================================================== Reinhard
+@pytest.mark.parametrize("name", ["reinhard_u8", "reinhard_f32", "reinhard_he_u8"])
+def test_reinhard_golden(cuda, name):
+    from stainx_b200 import Reinhard
+
+    g = golden(name)
+    n = Reinhard(device=cuda, backend="torch_cuda").fit(torch.from_numpy(g["ref"]).to(cuda))
+    assert np.abs(_np(n._reference_mean) - g["mean"]).max() <= 1e-3
+    assert np.abs(_np(n._reference_std) - g["std"]).max() <= 1e-3
+    # transform with the reference's own fitted parameters (isolates the transform)
+    n._reference_mean = torch.from_numpy(g["mean"]).to(cuda)
+    n._reference_std = torch.from_numpy(g["std"]).to(cuda)
+    out = _np(n.transform(torch.from_numpy(g["src"]).to(cuda)))
+    assert out.dtype == g["out"].dtype
+    diff = np.abs(out.astype(np.float64) - g["out"].astype(np.float64))
+    if out.dtype == np.uint8:
+        assert diff.max() <= 1
+        assert (diff > 0).mean() < 0.01
+    else:
+        assert diff.max() <= F32_TOL
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+@pytest.mark.parametrize("shape", [(1, 3, 1, 2), (2, 3, 9, 7), (2, 3, 64, 64), (1, 3, 321, 199), (3, 3, 128, 256), (10, 3, 512, 512)])
+def test_reinhard_vs_oracle(cuda, ox, dtype, shape):
+    """Last shape = BASELINE config C1 (README quick-start): fit 1x3x512x512, transform 10x3x512x512."""
+    from stainx_b200 import Reinhard
+
+    make = noise_u8 if dtype == "u8" else noise_f32
+    ref = make((1, 3, shape[2], shape[3]), 42)
+    src = make(shape, 43, 1.4)
+    n = Reinhard(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    mean, std = ox.reinhard_fit(ref.numpy())
+    assert np.abs(_np(n._reference_mean) - mean).max() <= 1e-3
+    assert np.abs(_np(n._reference_std) - std).max() <= 1e-3
+    out = _np(n.transform(src.to(cuda)))
+    want = ox.reinhard_transform(src.numpy(), _np(n._reference_mean), _np(n._reference_std))
+    diff = np.abs(out.astype(np.float64) - want.astype(np.float64))
+    if dtype == "u8":
+        assert diff.max() <= 1
+        assert (diff > 0).mean() < 0.01
+    else:
+        assert diff.max() <= F32_TOL
+
+
+def test_reinhard_identity_property(cuda):
+    """fit_transform on the same batch maps LAB statistics onto themselves: output == input."""
+    from stainx_b200 import Reinhard
+
+    x = noise_f32((4, 3, 256, 256), 11).to(cuda)
+    out = Reinhard(device=cuda, backend="torch_cuda").fit_transform(x)
+    assert (out - x).abs().max().item() <= 2e-3
+
+
+def test_reinhard_phase_api_shards(cuda):
+    """Statistics accumulate over shards (what the multi-GPU path all-reduces)."""
+    from stainx_b200 import ops
+
+    x = noise_f32((4, 3, 64, 64), 12).to(cuda)
+    whole = ops.reinhard_stats(x)
+    parts = ops.reinhard_stats(x[:1].contiguous())
+    ops.reinhard_stats(x[1:].contiguous(), sums=parts)
+    assert torch.allclose(whole, parts, rtol=1e-12, atol=1e-9)
+    assert whole[6].item() == 4 * 64 * 64
+    m, s = ops.reinhard_finalize(whole)
+    m2, s2 = ops.reinhard_fit(x)
+    assert torch.allclose(m, m2, rtol=0, atol=1e-5) and torch.allclose(s, s2, rtol=0, atol=1e-5)
+
+
+# ======================================================================== Macenko
+@pytest.mark.parametrize("name", ["macenko_he_u8", "macenko_he_f32", "macenko_he_pooled_u8"])
+def test_macenko_golden(cuda, name):
+    from stainx_b200 import Macenko
+
+    g = golden(name)
+    n = Macenko(device=cuda, backend="torch_cuda").fit(torch.from_numpy(g["ref"]).to(cuda))
+    assert np.abs(_np(n._stain_matrix) - g["he"]).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / g["maxc"] - 1).max() <= 1e-3
+    n._stain_matrix = torch.from_numpy(g["he"]).to(cuda)
+    n._target_max_conc = torch.from_numpy(g["maxc"]).to(cuda)
+    out = _np(n.transform(torch.from_numpy(g["src"]).to(cuda)))
+    assert out.dtype == g["out"].dtype and out.shape == g["out"].shape
+    diff = np.abs(out.astype(np.float64) - g["out"].astype(np.float64))
+    if out.dtype == np.uint8:
+        assert diff.max() <= 1
+        assert (diff > 0).mean() < 0.01
+    else:
+        assert diff.max() <= F32_TOL * 255.0  # float output stays in [0, 255]
+    if "out01" in g.files:
+        n.normalize_to_0_1 = True
+        out01 = _np(n.transform(torch.from_numpy(g["src"]).to(cuda)))
+        assert out01.dtype == np.float32
+        assert np.abs(out01 - g["out01"]).max() <= F32_TOL
+
+
+def test_macenko_known_answer_512(cuda):
+    """SURVEY.md section 8c known-answer vector: reference fit on the 512x512 seed-42 tile."""
+    from stainx_b200 import Macenko
+
+    g = golden("macenko_kat_512")
+    tile = he_tile(512, 512, 42)
+    if int(tile.long().sum()) != int(g["tile_sum"]):  # torch interpolate changed: fall back to the stored tile
+        tile = torch.from_numpy(g["tile"])
+    n = Macenko(device=cuda, backend="torch_cuda").fit(tile.to(cuda))
+    he, maxc = _np(n._stain_matrix), _np(n._target_max_conc)
+    assert np.abs(he - np.array([[0.50870, 0.34880], [0.74012, 0.78338], [0.43983, 0.51445]])).max() <= 1e-4
+    assert np.abs(maxc - np.array([2.13133, 1.57859])).max() <= 2e-3
+    assert np.abs(he - g["he"]).max() <= 1e-4
+    assert np.abs(maxc / g["maxc"] - 1).max() <= 1e-3
+
+
+def test_macenko_noise_golden(cuda):
+    """uint8 noise fixture: the golden vectors hold the reference evaluated with the middle
+    eigenvector in canonical sign ('p', largest |component| positive -- the convention of this
+    build) and flipped ('m').  Fit must match one of them; transform is compared under 'p'."""
+    from stainx_b200 import Macenko
+
+    g = golden("macenko_noise_u8")
+    n = Macenko(device=cuda, backend="torch_cuda").fit(torch.from_numpy(g["ref"]).to(cuda))
+    he = _np(n._stain_matrix)
+    d = min(np.abs(he - g["he_p"]).max(), np.abs(he - g["he_m"]).max())
+    assert d <= 1e-4, f"fit HE matches neither sign of the oracle: {d}"
+    n._stain_matrix = torch.from_numpy(g["he_p"]).to(cuda)
+    n._target_max_conc = torch.from_numpy(g["maxc_p"]).to(cuda)
+    out = _np(n.transform(torch.from_numpy(g["src"]).to(cuda)))
+    diff = np.abs(out.astype(np.float64) - g["out_p"].astype(np.float64))
+    assert diff.max() <= 1
+    assert (diff > 0).mean() < 0.01
+
+
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+@pytest.mark.parametrize("hw", [(64, 64), (96, 80), (321, 199), (256, 512)])
+def test_macenko_vs_oracle_he_tiles(cuda, ox, dtype, hw):
+    from stainx_b200 import Macenko
+
+    h, w = hw
+    ref = he_tile(h, w, 42)
+    src = he_batch(3, h, w)
+    if dtype == "f32":
+        ref, src = ref.float() / 255.0, src.float() / 255.0
+    n = Macenko(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    he, maxc = ox.macenko_fit(ref.numpy())
+    assert np.abs(_np(n._stain_matrix) - he).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / maxc - 1).max() <= 1e-3
+    out = _np(n.transform(src.to(cuda)))
+    want = ox.macenko_transform(src.numpy(), _np(n._stain_matrix), _np(n._target_max_conc))
+    diff = np.abs(out.astype(np.float64) - want.astype(np.float64))
+    if dtype == "u8":
+        assert diff.max() <= 1
+        assert (diff > 0).mean() < 0.01
+    else:
+        assert diff.max() <= F32_TOL * 255.0
+
+
+def test_macenko_noise_vs_oracle_both_signs(cuda, ox):
+    """torch.rand-style input (the bench distribution): per image, the CUDA output must match the
+    oracle under one of the two middle-eigenvector signs."""
+    from stainx_b200 import Macenko
+
+    ref = noise_f32((1, 3, 128, 128), 42)
+    src = noise_f32((4, 3, 128, 128), 43)
+    n = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=True).fit(ref.to(cuda))
+    he_p, maxc_p = ox.macenko_fit(ref.numpy(), mid_sign=1)
+    he_m, maxc_m = ox.macenko_fit(ref.numpy(), mid_sign=-1)
+    he = _np(n._stain_matrix)
+    if np.abs(he - he_p).max() <= np.abs(he - he_m).max():
+        he_o, maxc_o = he_p, maxc_p
+    else:
+        he_o, maxc_o = he_m, maxc_m
+    assert np.abs(he - he_o).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / maxc_o - 1).max() <= 1e-3
+    out = _np(n.transform(src.to(cuda)))
+    cand_p = ox.macenko_transform(src.numpy(), he, _np(n._target_max_conc), mid_signs=[1] * 4) / 255.0
+    cand_m = ox.macenko_transform(src.numpy(), he, _np(n._target_max_conc), mid_signs=[-1] * 4) / 255.0
+    assert best_sign_diff(out, cand_p, cand_m).max() <= F32_TOL
+
+
+def test_macenko_fallback_when_mask_empty(cuda, ox):
+    """Bright image: no pixel has min OD >= 0.15, so all pixels are used (torch_backend.py L409-410)."""
+    from stainx_b200 import Macenko
+
+    ref = he_tile(64, 64, 42)
+    g = torch.Generator().manual_seed(5)
+    bright = (215 + 35 * torch.rand((2, 3, 48, 48), generator=g)).round().to(torch.uint8)
+    # mix: one bright image, one normal tile, in the same batch
+    src = torch.cat([bright[:1], he_tile(48, 48, 9, 1.0), bright[1:]])
+    n = Macenko(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    he, maxc = _np(n._stain_matrix), _np(n._target_max_conc)
+    out = _np(n.transform(src.to(cuda)))
+    cand_p = ox.macenko_transform(src.numpy(), he, maxc, mid_signs=[1, 1, 1])
+    cand_m = ox.macenko_transform(src.numpy(), he, maxc, mid_signs=[-1, -1, -1])
+    assert best_sign_diff(out, cand_p, cand_m).max() <= 1
+
+
+def test_macenko_per_image_independence(cuda):
+    """Every statistic is per image: transform(batch)[i] == transform(batch[i:i+1]) bit for bit."""
+    from stainx_b200 import Macenko
+
+    ref = he_tile(128, 128, 42)
+    src = he_batch(5, 128, 128).float() / 255.0
+    n = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=True).fit(ref.to(cuda))
+    whole = n.transform(src.to(cuda))
+    for i in range(5):
+        assert torch.equal(whole[i : i + 1], n.transform(src[i : i + 1].to(cuda)))
+
+
+def test_macenko_self_reference_reconstructs(cuda):
+    """With the image's own HE / maxC as target, the Beer-Lambert tile is reproduced (the stain
+    plane projection of OD is OD itself up to 8-bit rounding)."""
+    from stainx_b200 import Macenko
+
+    x = he_tile(256, 256, 77, 1.05).to(cuda)
+    n = Macenko(device=cuda, backend="torch_cuda")
+    out = n.fit_transform(x)
+    assert out.dtype == torch.uint8
+    assert (out.int() - x.int()).abs().max().item() <= 2
+
+
+def test_macenko_full_size_float(cuda, ox):
+    """BASELINE config C3 shape class (float32 1024x1024): a 6-image batch against the oracle, and
+    the full 64-image batch through batch-vs-single equality on sampled images."""
+    from stainx_b200 import Macenko
+
+    ref = he_tile(1024, 1024, 42).float() / 255.0
+    src = he_batch(6, 1024, 1024).float() / 255.0
+    n = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=True).fit(ref.to(cuda))
+    he, maxc = ox.macenko_fit(ref.numpy())
+    assert np.abs(_np(n._stain_matrix) - he).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / maxc - 1).max() <= 1e-3
+    out = _np(n.transform(src.to(cuda)))
+    want = ox.macenko_transform(src[:2].numpy(), _np(n._stain_matrix), _np(n._target_max_conc)) / 255.0
+    assert np.abs(out[:2] - want).max() <= F32_TOL
+    big = src.to(cuda).repeat(11, 1, 1, 1)[:64].contiguous()
+    whole = n.transform(big)
+    assert tuple(whole.shape) == (64, 3, 1024, 1024)
+    for i in (0, 17, 63):
+        assert torch.equal(whole[i], torch.from_numpy(out[i % 6]).to(cuda))
+
+
+def test_macenko_sharded_fit_emulation(cuda):
+    """Pooled fit over two 'ranks' emulated on one GPU: per-shard phases + the reductions a
+    process group would apply (SUM / MAX / MIN) give the single-device fit bit for bit."""
+    from stainx_b200 import _native as nv
+    from stainx_b200 import ops
+
+    imgs = torch.cat([he_tile(96, 96, 42), he_tile(96, 96, 7, 1.1), he_tile(96, 96, 8, 0.9)]).to(cuda)
+    he_ref, maxc_ref = ops.macenko_fit(imgs)
+    shards = [imgs[:1].contiguous(), imgs[1:].contiguous()]
+    wss = [ops.MacenkoWorkspace(1, cuda) for _ in shards]
+
+    def reduce(name, op):
+        stack = torch.stack([w.region(name) for w in wss])
+        red = {"sum": stack.sum(0), "max": stack.max(0).values, "min": stack.min(0).values}[op]
+        for w in wss:
+            w.region(name).copy_(red.to(w.region(name).dtype))
+
+    for w, s in zip(wss, shards):
+        w.begin()
+        w.moments(s, pooled=True)
+    reduce("moments", "sum")
+    reduce("odrange", "max")
+    for w in wss:
+        w.basis(0, 1, allow_fallback=False)
+    for stage in (nv.SX_STAGE_ANGLE, nv.SX_STAGE_CONC):
+        for w, s in zip(wss, shards):
+            w.hist(s, True, stage, 0)
+        reduce("hist1", "sum")
+        for w in wss:
+            w.select(0, 1, stage, 0)
+        for w, s in zip(wss, shards):
+            w.hist(s, True, stage, 1)
+        reduce("hist2", "sum")
+        reduce("vmin", "min")
+        reduce("vmax", "max")
+        for w in wss:
+            w.select(0, 1, stage, 1)
+    for w in wss:
+        fit = w.region("fit")[0]
+        assert torch.allclose(fit[:6].reshape(3, 2), he_ref, rtol=0, atol=1e-6)
+        assert torch.allclose(fit[6:8], maxc_ref, rtol=1e-6, atol=0)
+    assert torch.equal(wss[0].region("fit"), wss[1].region("fit"))
