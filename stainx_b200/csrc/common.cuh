@@ -37,7 +37,7 @@ inline int64_t max_i64(int64_t a, int64_t b) { return a > b ? a : b; }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int check_images(const void *images, int dtype, int64_t n, int64_t h, int64_t w) {
-    SX_REQUIRE(images != nullptr, "images is NULL");
+    SX_REQUIRE(images != nullptr || n == 0 || h == 0 || w == 0, "images is NULL");
     SX_REQUIRE(dtype == SX_U8 || dtype == SX_F32, "dtype must be SX_U8 or SX_F32, got %d", dtype);
     SX_REQUIRE(n >= 0 && h >= 0 && w >= 0, "negative image extent (%lld, %lld, %lld)", (long long)n, (long long)h, (long long)w);
     return SX_OK;

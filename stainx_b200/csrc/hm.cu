@@ -7,6 +7,8 @@
 //
 // Data path (uint8 NCHW, the BASELINE config): 3 B/px read for the histogram, 3 B/px read +
 // 3 B/px written for the remap = 9 algorithmic bytes per pixel, all 128-bit coalesced.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sx {
@@ -80,6 +82,58 @@ struct ByteCounters {
     }
 };
 
+// Counting scheme C: the same lane-private packed layout, but the update is a fire-and-forget
+// shared-memory reduction (RED.ADD of 1 << 8*(bin & 3)) instead of a byte load/add/store.  Lane l
+// only touches bank l, so the warp-wide RED is conflict-free, and nothing waits on its result.
+// A byte lane holds at most 255 hits between flushes, so a carry can never cross into its
+// neighbour.
+struct PackedRed {
+    static constexpr int kBytesPerWarp = 64 * 32 * 4;
+    unsigned int *mine;    // &region[lane]
+    unsigned int *region;
+    unsigned int *hist32;
+    int lane;
+    __device__ __forceinline__ void init(unsigned char *smem_counters, unsigned int *h32) {
+        int warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        region = reinterpret_cast<unsigned int *>(smem_counters + warp * kBytesPerWarp);
+        mine = region + lane;
+        hist32 = h32;
+        for (int i = lane; i < 64 * 32; i += 32) region[i] = 0u;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void add(unsigned b) {
+        atomicAdd(mine + ((b & 0xfcu) << 3), 1u << ((b & 3u) << 3));  // word (b>>2)*32 + lane
+    }
+    __device__ __forceinline__ void add4(unsigned w) {
+        add(w & 0xffu);
+        add((w >> 8) & 0xffu);
+        add((w >> 16) & 0xffu);
+        add(w >> 24);
+    }
+    __device__ __forceinline__ void flush() {
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            int q = lane + 32 * rr;
+            unsigned lo = 0, hi = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                int col = (k + lane) & 31;
+                unsigned w = region[q * 32 + col];
+                region[q * 32 + col] = 0u;
+                lo += w & 0x00ff00ffu;
+                hi += (w >> 8) & 0x00ff00ffu;
+            }
+            if (lo & 0xffffu) atomicAdd(&hist32[4 * q + 0], lo & 0xffffu);
+            if (hi & 0xffffu) atomicAdd(&hist32[4 * q + 1], hi & 0xffffu);
+            if (lo >> 16) atomicAdd(&hist32[4 * q + 2], lo >> 16);
+            if (hi >> 16) atomicAdd(&hist32[4 * q + 3], hi >> 16);
+        }
+        __syncwarp();
+    }
+};
+
 // Alternative counting scheme (selectable for A/B measurements): warp-private 32-bit histograms
 // updated with shared-memory atomics.
 struct WarpAtomics {
@@ -118,7 +172,7 @@ __device__ __forceinline__ PlaneSplit split_plane(const T *p, int64_t len) {
     return s;
 }
 
-template <bool BYTE_COUNTERS>
+template <int MODE>  // 0: warp-private shared atomics, 1: byte counters, 2: packed lane-private RED
 __global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned int *hist32 = reinterpret_cast<unsigned int *>(smem);  // 256 words
@@ -126,7 +180,9 @@ __global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t 
     const int c = blockIdx.y;
     for (int i = threadIdx.x; i < 256; i += kThreads) hist32[i] = 0u;
 
-    ByteCounters bc;
+    constexpr bool BYTE_COUNTERS = MODE != 0;  // modes 1 and 2 need the periodic flush
+    using Packed = typename std::conditional<MODE == 2, PackedRed, ByteCounters>::type;
+    Packed bc;
     WarpAtomics wa;
     if (BYTE_COUNTERS) bc.init(scratch, hist32);
     else wa.init(reinterpret_cast<unsigned int *>(scratch));
@@ -179,6 +235,115 @@ __global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t 
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += kThreads)
         if (hist32[i]) atomicAdd(&counts[c * 256 + i], (unsigned long long)hist32[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Histogram, planar uint8, scheme D ("lane32"): every LANE owns a full 256-bin histogram of 32-bit
+// counters, laid out [bin][lane] inside a 32 KB warp region, so counter (bin, lane) sits in bank
+// `lane`.  Counting one byte is SHF + LOP3 + a conflict-free fire-and-forget ATOMS.ADD; there is
+// no overflow, hence no periodic flush.  7 warps x 32 KB fill the SM's shared memory, so the CTA
+// is persistent (one per SM) and walks a CONTIGUOUS range of the (channel, image, tile) list,
+// folding its histogram into the global counts whenever the channel changes (at most twice).
+// Memory-level parallelism comes from 8 independent 128-bit loads per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int kL32Warps = 7;
+constexpr int kL32Threads = kL32Warps * 32;
+constexpr int kL32Unroll = 8;
+constexpr int kL32TileVecs = kL32Threads * kL32Unroll;
+constexpr int kL32SmemBytes = kL32Warps * 256 * 32 * 4 + 256 * 4;
+
+__device__ __forceinline__ void l32_count4(unsigned w, unsigned lane_off, uint32_t region_addr) {
+    // byte offset of counter (bin, lane) = bin * 128 + lane * 4
+    unsigned o0 = ((w << 7) & 0x7f80u) | lane_off;
+    unsigned o1 = ((w >> 1) & 0x7f80u) | lane_off;
+    unsigned o2 = ((w >> 9) & 0x7f80u) | lane_off;
+    unsigned o3 = ((w >> 17) & 0x7f80u) | lane_off;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o0) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o1) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o2) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o3) : "memory");
+}
+
+__global__ void __launch_bounds__(kL32Threads, 1) hist_u8_planar_lane32_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned int *regions = reinterpret_cast<unsigned int *>(smem);                                  // [warp][bin][lane]
+    unsigned int *hist32 = reinterpret_cast<unsigned int *>(smem + kL32Warps * 256 * 32 * 4);        // [bin]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int *region = regions + warp * 256 * 32;
+    const uint32_t region_addr = (uint32_t)__cvta_generic_to_shared(region);
+    const unsigned lane_off = (unsigned)lane * 4u;
+
+    for (int i = threadIdx.x; i < kL32Warps * 256 * 32; i += kL32Threads) regions[i] = 0u;
+    for (int i = threadIdx.x; i < 256; i += kL32Threads) hist32[i] = 0u;
+    __syncthreads();
+
+    // fold the lane-private counters of every warp into the global counts of channel c, re-zero
+    auto fold = [&](int c) {
+        __syncthreads();
+        for (int bin = lane; bin < 256; bin += 32) {  // lane j: bins j, j+32, ...; rotated walk = no conflicts
+            unsigned sum = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const int col = (k + lane) & 31;
+                sum += region[bin * 32 + col];
+                region[bin * 32 + col] = 0u;
+            }
+            if (sum) atomicAdd(&hist32[bin], sum);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 256; i += kL32Threads) {
+            const unsigned v = hist32[i];
+            if (v) atomicAdd(&counts[c * 256 + i], (unsigned long long)v);
+            hist32[i] = 0u;
+        }
+        __syncthreads();
+    };
+
+    const int64_t per_channel = n_img * tiles_per_plane;
+    const int64_t items = 3 * per_channel;
+    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const int64_t first = (int64_t)blockIdx.x * per_cta;
+    const int64_t last = first + per_cta < items ? first + per_cta : items;
+    int cur_c = -1;
+    for (int64_t item = first; item < last; ++item) {
+        const int c = (int)(item / per_channel);
+        const int64_t rem = item - (int64_t)c * per_channel;
+        const int64_t n = rem / tiles_per_plane;
+        const int64_t t = rem - n * tiles_per_plane;
+        if (c != cur_c) {
+            if (cur_c >= 0) fold(cur_c);
+            cur_c = c;
+        }
+        const uint8_t *plane = img + (n * 3 + c) * hw;
+        const PlaneSplit sp = split_plane(plane, hw);
+        const uint4 *body = reinterpret_cast<const uint4 *>(plane + sp.head);
+        const int64_t v0 = t * kL32TileVecs;
+        uint4 v[kL32Unroll];
+        bool ok[kL32Unroll];
+#pragma unroll
+        for (int u = 0; u < kL32Unroll; ++u) {
+            const int64_t vi = v0 + u * kL32Threads + threadIdx.x;
+            ok[u] = vi < sp.nvec;
+            if (ok[u]) v[u] = ld_stream(body + vi);
+        }
+#pragma unroll
+        for (int u = 0; u < kL32Unroll; ++u) {
+            if (ok[u]) {
+                l32_count4(v[u].x, lane_off, region_addr);
+                l32_count4(v[u].y, lane_off, region_addr);
+                l32_count4(v[u].z, lane_off, region_addr);
+                l32_count4(v[u].w, lane_off, region_addr);
+            }
+        }
+        if (t == 0) {  // ragged ends of the plane
+            const int64_t ragged = sp.head + (hw - sp.tail0);
+            if ((int64_t)threadIdx.x < ragged) {
+                const int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
+                atomicAdd(&region[(unsigned)plane[idx] * 32 + lane], 1u);
+            }
+        }
+    }
+    if (cur_c >= 0) fold(cur_c);
 }
 
 // Histogram, planar float32: quantise, then warp-private shared atomics (12 B/px of traffic per
@@ -282,10 +447,10 @@ __global__ void __launch_bounds__(kThreads) hist_nhwc_kernel(const T *__restrict
 
 // ------------------------------------------------------------------------------------------------
 // LUT construction.  Tiny, single CTA per channel; every float32 operation is pinned with
-// round-to-nearest intrinsics so the result is bit-identical to the torch CPU oracle.
+// round-to-nearest intrinsics so the result is bit-identical to the torch CPU backend of the reference.
 // ------------------------------------------------------------------------------------------------
 
-// torch.sum of a 256-vector on CPU: 8 lanes x 4 interleaved accumulators (see oracle/ox_sum_f32).
+// torch.sum of a 256-vector on CPU: 8 lanes x 4 interleaved accumulators (probed against torch; DESIGN.md section "bit-exact LUT").
 __device__ float torch_sum_256(const float *a) {
     float acc[4][8];
 #pragma unroll
@@ -319,30 +484,50 @@ __global__ void ref_hist_kernel(const unsigned long long *__restrict__ counts, f
     ref_hist[c * 256 + b] = __fdiv_rn(cf[b], denom);
 }
 
-// H2a: torch_backend.py:L221-223.
-__global__ void ref_cdf_kernel(const float *__restrict__ ref_hist, float *__restrict__ ref_cdf) {
-    __shared__ float h[256];
-    const int c = blockIdx.x, b = threadIdx.x;
-    h[b] = ref_hist[c * 256 + b];
+// Reference CDF of channel c into rq[256] (shared): H2a, torch_backend.py:L221-223.
+// The 256 divisions run in parallel; only the double-precision running sum is serial.
+__device__ __forceinline__ void ref_cdf_to_smem(const float *__restrict__ ref_hist_c, float *h, double *dacc, float *rq) {
+    __shared__ float s_denom;
+    const int b = threadIdx.x;
+    h[b] = ref_hist_c[b];
+    __syncthreads();
+    if (b == 0) s_denom = __fadd_rn(torch_sum_256(h), 1e-8f);
+    __syncthreads();
+    h[b] = __fdiv_rn(h[b], s_denom);
     __syncthreads();
     if (b == 0) {
-        float denom = __fadd_rn(torch_sum_256(h), 1e-8f);
         double acc = 0.0;
+#pragma unroll 8
         for (int i = 0; i < 256; ++i) {
-            acc = __dadd_rn(acc, (double)__fdiv_rn(h[i], denom));
-            ref_cdf[c * 256 + i] = __double2float_rn(acc);
+            acc = __dadd_rn(acc, (double)h[i]);
+            dacc[i] = acc;
         }
     }
+    __syncthreads();
+    rq[b] = __double2float_rn(dacc[b]);
+    __syncthreads();
+}
+
+__global__ void ref_cdf_kernel(const float *__restrict__ ref_hist, float *__restrict__ ref_cdf) {
+    __shared__ float h[256];
+    __shared__ double dacc[256];
+    __shared__ float rq[256];
+    ref_cdf_to_smem(ref_hist + blockIdx.x * 256, h, dacc, rq);
+    ref_cdf[blockIdx.x * 256 + threadIdx.x] = rq[threadIdx.x];
 }
 
 // H2b: torch_backend.py:L234-281.  npix < 0: derive the pixel count from the counts themselves
 // (sum over the 256 bins of the channel), which keeps a sharded run free of host round trips.
-__global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref_cdf, float *__restrict__ lut) {
+// FROM_HIST: the reference CDF is rebuilt from ref_hist inside the same kernel (fused transform).
+template <bool FROM_HIST>
+__global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
     __shared__ float rq[256];
     __shared__ float sq[256];
+    __shared__ double dacc[256];
     __shared__ float s_npix_f;
     const int c = blockIdx.x, b = threadIdx.x;
-    rq[b] = ref_cdf[c * 256 + b];
+    if (FROM_HIST) ref_cdf_to_smem(ref + c * 256, sq, dacc, rq);
+    else rq[b] = ref[c * 256 + b];
     if (b == 0) {
         unsigned long long total = 0;
         if (npix < 0) for (int i = 0; i < 256; ++i) total += counts[c * 256 + i];
@@ -355,11 +540,14 @@ __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, 
     __syncthreads();
     if (b == 0) {  // L236: cumsum, double accumulator rounded per element
         double acc = 0.0;
+#pragma unroll 8
         for (int i = 0; i < 256; ++i) {
             acc = __dadd_rn(acc, (double)sq[i]);
-            sq[i] = __double2float_rn(acc);
+            dacc[i] = acc;
         }
     }
+    __syncthreads();
+    sq[b] = __double2float_rn(dacc[b]);
     __syncthreads();
     const float q = sq[b];
     int lo = 0, hi = 256;  // L260: searchsorted(right=False)
@@ -533,8 +721,8 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
 }
 
 // ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
-static int g_hist_byte_counters = 1;
-static int g_hist_ctas_per_sm = 3;
+static int g_hist_byte_counters = 0;  // counting scheme: 0 warp atomics, 1 byte counters, 2 packed RED, 3 lane32
+static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 8;
 
 }  // namespace hm
@@ -576,21 +764,32 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
     if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         const int64_t items = n * tiles;
-        if (g_hist_byte_counters) {
+        if (g_hist_byte_counters == 3) {
+            static bool attr3_set = false;
+            if (!attr3_set) {
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL32SmemBytes));
+                attr3_set = true;
+            }
+            const int64_t tiles32 = max_i64(1, (hw / 16 + kL32TileVecs - 1) / kL32TileVecs);
+            const unsigned grid32 = stream_grid(3 * n * tiles32, 1);
+            hist_u8_planar_lane32_kernel<<<grid32, kL32Threads, kL32SmemBytes, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles32, cnt);
+        } else if (g_hist_byte_counters) {
             const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * ByteCounters::kBytesPerWarp;
             static bool attr_set = false;
             if (!attr_set) {
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 attr_set = true;
             }
             dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
             grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
-            hist_u8_planar_kernel<true><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
+            if (g_hist_byte_counters == 2) hist_u8_planar_kernel<2><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
+            else hist_u8_planar_kernel<1><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
         } else {
             const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * 256 * sizeof(unsigned);
-            dim3 grid(stream_grid(items, 8), 3);
+            dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
             grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
-            hist_u8_planar_kernel<false><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
+            hist_u8_planar_kernel<0><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
         }
         SX_LAUNCHED("hist_u8_planar_kernel");
     } else {
@@ -619,18 +818,18 @@ int sx_hm_ref_cdf(const float *ref_hist, float *ref_cdf, sx_stream_t stream) {
 
 int sx_hm_build_lut(const uint64_t *counts, int64_t npix, const float *ref_cdf, float *lut, sx_stream_t stream) {
     SX_REQUIRE(counts && ref_cdf && lut, "NULL argument");
-    build_lut_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)npix, ref_cdf, lut);
+    build_lut_kernel<false><<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)npix, ref_cdf, lut);
     SX_LAUNCHED("build_lut_kernel");
     return SX_OK;
 }
 
 int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const float *lut, void *out, sx_stream_t stream_) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
-    SX_REQUIRE(lut && out, "NULL argument");
     SX_REQUIRE(layout == SX_NCHW || layout == SX_NHWC, "layout must be SX_NCHW or SX_NHWC, got %d", layout);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
+    SX_REQUIRE(lut && out, "NULL argument");
     if (layout == SX_NHWC) {
         const int64_t total = n * hw * 3;
         if (dtype == SX_U8) {
@@ -669,8 +868,9 @@ int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_
     auto *lut = ref_cdf + 768;
     SX_CUDA(cudaMemsetAsync(counts, 0, 768 * 8, static_cast<cudaStream_t>(stream)));
     if (int rc = sx_hm_hist(images, dtype, layout, n, h, w, counts, stream)) return rc;
-    if (int rc = sx_hm_ref_cdf(ref_hist, ref_cdf, stream)) return rc;
-    if (int rc = sx_hm_build_lut(counts, n * h * w, ref_cdf, lut, stream)) return rc;
+    (void)ref_cdf;
+    build_lut_kernel<true><<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)(n * h * w), ref_hist, lut);
+    SX_LAUNCHED("build_lut_kernel<fused>");
     return sx_hm_apply(images, dtype, layout, n, h, w, lut, out, stream);
 }
 

@@ -821,6 +821,7 @@ int sx_macenko_select(void *workspace, int64_t slots, int64_t slot0, int64_t cou
 int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, sx_stream_t stream_) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     if (int rc = check_slots(n, 0, slot0, slots)) return rc;
+    if (n == 0 || h * w == 0) return SX_OK;
     SX_REQUIRE(workspace && he_ref && maxc_ref && out, "NULL argument");
     SX_REQUIRE(out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8), "uint8 output requires uint8 input");
     const bool unit = out_scale != 1.0f;

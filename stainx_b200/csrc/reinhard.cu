@@ -328,10 +328,10 @@ int sx_reinhard_finalize(const double *sums, float *mean, float *std, sx_stream_
 
 int sx_reinhard_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const float *src_mean, const float *src_std, const float *ref_mean, const float *ref_std, void *out, sx_stream_t stream_) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
-    SX_REQUIRE(src_mean && src_std && ref_mean && ref_std && out, "NULL argument");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
+    SX_REQUIRE(src_mean && src_std && ref_mean && ref_std && out, "NULL argument");
     if (dtype == SX_F32) {
         const float *p = static_cast<const float *>(images);
         float *o = static_cast<float *>(out);

@@ -1,0 +1,147 @@
+"""CPU: host-side API surface -- constructor validation, error texts and control flow that the
+reference's own tests pin (tests/test_normalizer_template_unit.py,
+tests/torch_interface/test_stain_normalizer_transform.py,
+tests/torch_interface/test_correctness_against_references.py L201-213).  No kernel runs here."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+import stainx_b200
+from stainx_b200 import HistogramMatching, Macenko, Reinhard, StainNormalizerBase, StainNormalizerTransform
+from stainx_b200.sharding import StatReducer, shard_range
+
+
+def test_public_names_match_the_reference():
+    assert set(stainx_b200.__all__) == {"HistogramMatching", "Macenko", "Reinhard", "StainNormalizerBase", "StainNormalizerTransform", "__version__"}
+    for cls in (HistogramMatching, Macenko, Reinhard):
+        assert issubclass(cls, StainNormalizerBase)
+        for method in ("fit", "transform", "fit_transform"):
+            assert callable(getattr(cls, method))
+    from stainx_b200.backends.torch_cuda_backend import CUDA_AVAILABLE, HistogramMatchingCUDA, MacenkoCUDA, ReinhardCUDA  # noqa: F401
+
+    assert CUDA_AVAILABLE is True
+
+
+@pytest.mark.parametrize("cls", [Reinhard, Macenko, HistogramMatching])
+def test_transform_before_fit_raises(cls):
+    with pytest.raises(ValueError, match=r"Must call fit\(\) before transform\(\)"):
+        cls(device="cuda", backend="torch_cuda").transform(torch.zeros(1, 3, 8, 8))
+
+
+def test_backend_validation():
+    with pytest.raises(ValueError, match="Unsupported backend"):
+        Reinhard(backend="torch")  # no pure-torch backend, no dispatch
+    with pytest.raises(ValueError, match="Unsupported backend"):
+        HistogramMatching(backend="numpy")
+    assert Reinhard(device="cuda").backend == "torch_cuda"
+    assert Macenko(device="cuda", backend="torch_cuda").backend == "torch_cuda"
+
+
+def test_macenko_precision_validation():
+    with pytest.raises(ValueError, match="precision='fast' requires backend='torch_cuda'"):
+        Macenko(backend="torch", precision="fast")
+    with pytest.raises(ValueError, match="precision must be"):
+        Macenko(precision="ultra")
+    assert Macenko(device="cuda", backend="torch_cuda", precision="fast")._precision == "fast"
+    assert Macenko(device="cuda")._precision == "stable"
+    assert Macenko(device="cuda").normalize_to_0_1 is False
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_backend_requires_cuda_device():
+    n = Reinhard(device="cpu")
+    with pytest.raises(ValueError, match="CUDA backend requires CUDA device"):
+        n.fit(torch.zeros(1, 3, 8, 8))
+    from stainx_b200.backends.torch_cuda_backend import ReinhardCUDA
+
+    with pytest.raises(RuntimeError, match="CUDA is not available"):
+        ReinhardCUDA(None)
+
+
+def test_hm_reference_histogram_validation():
+    from stainx_b200.backends.torch_cuda_backend import HistogramMatchingCUDA
+
+    b = HistogramMatchingCUDA("cpu", ops=object())  # injected ops: skips the device check only
+    with pytest.raises(ValueError, match="cannot be empty"):
+        b._stack_reference([])
+    with pytest.raises(TypeError, match="must be a torch.Tensor"):
+        b._stack_reference([1, 2, 3])
+    with pytest.raises(ValueError, match="1D with 256 elements"):
+        b._stack_reference([torch.zeros(255)])
+    with pytest.raises(ValueError, match="1D with 256 elements"):
+        b._stack_reference(torch.zeros(2, 100))
+    one = torch.rand(256)
+    assert torch.equal(b._stack_reference(one), one.unsqueeze(0).repeat(3, 1))
+    assert tuple(b._stack_reference([one, one * 2]).shape) == (3, 256)  # padded with channel 0
+
+
+class TestStainNormalizerTransformValidation:
+    def test_modes_and_methods(self):
+        with pytest.raises(ValueError, match="Unsupported mode"):
+            StainNormalizerTransform("reinhard", mode="online")
+        with pytest.raises(ValueError, match="Unknown method"):
+            StainNormalizerTransform("vahadane", mode="batch")
+        with pytest.raises(ValueError, match="requires a reference tensor"):
+            StainNormalizerTransform("reinhard", mode="reference")
+
+    def test_normalize_to_0_1_rules(self):
+        with pytest.raises(ValueError, match="only applies to Macenko"):
+            StainNormalizerTransform("reinhard", mode="batch", normalize_to_0_1=True)
+        assert StainNormalizerTransform("macenko", mode="batch").normalizer.normalize_to_0_1 is True
+        assert StainNormalizerTransform("macenko", mode="batch", normalize_to_0_1=False).normalizer.normalize_to_0_1 is False
+        pre = Macenko(device="cuda", normalize_to_0_1=False)
+        assert StainNormalizerTransform(mode="batch", normalizer=pre).normalizer.normalize_to_0_1 is False  # left alone
+        assert StainNormalizerTransform(mode="batch", normalizer=pre, normalize_to_0_1=True).normalizer.normalize_to_0_1 is True
+        with pytest.raises(ValueError, match="only applies to Macenko"):
+            StainNormalizerTransform(mode="batch", normalizer=Reinhard(device="cuda"), normalize_to_0_1=True)
+
+    def test_layout_rules(self):
+        with pytest.raises(ValueError, match="only supported for histogram_matching"):
+            StainNormalizerTransform("macenko", mode="batch", channel_axis=-1)
+        with pytest.raises(ValueError, match="only supported for histogram_matching"):
+            StainNormalizerTransform(mode="batch", normalizer=Reinhard(device="cuda"), channel_axis=3)
+        t = StainNormalizerTransform(mode="batch", normalizer=HistogramMatching(device="cuda", channel_axis=-1))
+        assert t.channel_axis == -1  # follows the prebuilt normalizer
+        with pytest.raises(ValueError, match="conflicts with prebuilt"):
+            StainNormalizerTransform(mode="batch", normalizer=HistogramMatching(device="cuda", channel_axis=-1), channel_axis=-3)
+        assert StainNormalizerTransform("histogram_matching", mode="batch", channel_axis=3).normalizer.channel_axis == 3
+
+    def test_device_rules(self):
+        with pytest.raises(ValueError, match="requires a CUDA device"):
+            StainNormalizerTransform("reinhard", mode="batch", device="cpu")
+        t = StainNormalizerTransform("reinhard", mode="batch")
+        with pytest.raises(ValueError, match="requires CUDA tensors when device=None"):
+            t(torch.rand(2, 3, 8, 8))
+
+    def test_shape_checks_run_before_any_device_work(self):
+        t = StainNormalizerTransform("macenko", mode="batch")
+        with pytest.raises(ValueError, match="Expected NCHW"):
+            t(torch.rand(2, 8, 8, 3))
+        with pytest.raises(ValueError, match="Expected CHW/NCHW"):
+            t(torch.rand(8, 8))
+        hm = StainNormalizerTransform("histogram_matching", mode="batch", channel_axis=-1)
+        with pytest.raises(ValueError, match="channels-last histogram matching expects"):
+            hm(torch.rand(2, 3, 8, 8))
+
+    def test_state_dict_carries_no_fitted_parameters(self):
+        t = StainNormalizerTransform("macenko", mode="batch")
+        assert t.state_dict() == {}
+        assert isinstance(t, torch.nn.Module)
+
+
+def test_shard_range_partitions_contiguously():
+    for n, world in ((64, 8), (10, 4), (3, 8), (0, 2), (512, 8)):
+        ranges = [shard_range(n, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_reducer_is_identity_without_a_group():
+    r = StatReducer()
+    assert not r.enabled and r.world_size == 1 and r.rank == 0
+    t = torch.arange(4)
+    assert r.sum_(t) is t and r.max_(t) is t and r.min_(t) is t
+    assert r.sum_int(7, torch.device("cpu")) == 7
