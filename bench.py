@@ -19,7 +19,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import time
 from pathlib import Path
 
@@ -35,13 +34,18 @@ ALGO_BYTES_PER_PX = {"hm": 9.0, "reinhard": 36.0, "macenko": 24.0}  # SURVEY.md 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 2000 for the GPU arm, 20 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default: 20 / 2)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="hm", choices=["hm", "reinhard", "macenko"])
     ap.add_argument("--no-extras", action="store_true", help="skip the per-method side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 2000 if args.impl == "b200" else 20
+    if args.warmup is None:
+        args.warmup = 20 if args.impl == "b200" else 2
+    return args
 
 
 def peaks() -> tuple[float, str]:
@@ -58,45 +62,67 @@ def peaks() -> tuple[float, str]:
 # clocks: sample nvidia-smi during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock and throttle reasons through NVML from a background thread (every ~2 ms)
+    while the timed region runs; falls back to one `nvidia-smi` query when NVML is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.path = Path(tempfile.mkstemp(prefix="clocks_", suffix=".csv")[1])
-        self.proc = None
+        import threading
+
+        self.samples: list[int] = []
+        self.reason_bits = 0
+        self.sm_max = None
+        self.power_w: list[float] = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except (FileNotFoundError, OSError):
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._nvml = None
+
+    def _run(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+                self.power_w.append(nv.nvmlDeviceGetPowerUsage(self._handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "source": "nvml"}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if self.samples:
+                s = sorted(self.samples)
+                out.update(sm_mhz=s[len(s) // 2], samples=len(s), reasons=sorted(n for bit, n in self.REASONS.items() if self.reason_bits & bit))
+                if self.power_w:
+                    out["power_w_max"] = max(self.power_w)
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, reasons, sm_max = [], set(), None
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in self.path.read_text().splitlines():
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 7:
-                    continue
-                try:
-                    sm.append(float(f[0]))
-                    sm_max = float(f[1])
-                except ValueError:
-                    continue
-                for name, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        finally:
-            self.path.unlink(missing_ok=True)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=sm_max, reasons=sorted(reasons), samples=len(sm))
+        try:  # fallback: a single nvidia-smi reading
+            txt = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            f = [x.strip() for x in txt.splitlines()[0].split(",")]
+            out.update(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), samples=1, source="nvidia-smi (single reading)")
+        except Exception:
+            out["source"] = "unavailable"
         return out
 
 
@@ -143,6 +169,14 @@ def run_reference(args) -> None:
     ref = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
     src = rng.integers(0, 256, size=(n_img, 3, H, W), dtype=np.uint8)
     ref_hist = ox.hm_fit(ref)
+    t0 = time.perf_counter()
+    ox.hm_transform(src, ref_hist)
+    one = time.perf_counter() - t0
+    budget = 120.0  # seconds for the whole run
+    while n_img > 1 and one * (args.steps + args.warmup) > budget:
+        n_img //= 2
+        src = src[:n_img]
+        one /= 2
     for _ in range(max(args.warmup, 1)):
         ox.hm_transform(src, ref_hist)
     t0 = time.perf_counter()
