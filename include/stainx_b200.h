@@ -115,22 +115,26 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
  * torch_backend.py:L556-558); fit pools all images into slot 0 (L477-485).  The workspace holds,
  * per slot, the OD moments, the order-statistic histograms and the fitted HE / maxC.
  *
- * Phase order (each `hist` is one streaming pass over the images, each `select` a tiny kernel):
- *   begin -> moments -> basis -> [moments_fallback -> basis_fallback]          (M1-M4)
+ * Phase order (`hist` level 0 is a ~3 % subsample pass, level 1 a full streaming pass; each `select`
+ * is a tiny one-CTA-per-slot kernel):
+ *   begin -> moments -> basis -> [moments_fallback]                            (M1-M4)
  *         -> hist(ANGLE,0) -> select(ANGLE,0) -> hist(ANGLE,1) -> select(ANGLE,1)   (M5-M7)
  *         -> hist(CONC,0)  -> select(CONC,0)  -> hist(CONC,1)  -> select(CONC,1)    (M8-M9)
- *         -> apply (M10)   or   get_fit (M11)
- * A sharded pooled fit all-reduces the region named by sx_macenko_region() after `moments` and
- * after every `hist`. */
+ *         -> apply (M10)   or   read the FIT region (M11)
+ * A sharded pooled fit all-reduces the regions named by sx_macenko_region() after `moments`
+ * (MOMENTS, ODRANGE) and after every `hist` (level 0: HIST1, COUNTERS; level 1: HIST2, COUNTERS,
+ * VMIN, VMAX). */
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
     SX_REGION_MOMENTS = 0,  /* double  [slots][12]   reduce: SUM */
     SX_REGION_ODRANGE = 1,  /* float32 [slots][8]    reduce: MAX  (-min_c, max_c, pad) */
-    SX_REGION_HIST1 = 2,    /* int32   [slots][2][4096]  reduce: SUM (wraps mod 2^32) */
-    SX_REGION_HIST2 = 3,    /* int32   [slots][2][4096]  reduce: SUM */
+    SX_REGION_HIST1 = 2,    /* int32   [slots][2][4096]  sample histogram; reduce: SUM (wraps mod 2^32) */
+    SX_REGION_HIST2 = 3,    /* int32   [slots][2][4096]  cells inside the bracket; reduce: SUM */
     SX_REGION_VMIN = 4,     /* float32 [slots][2][4096]  reduce: MIN */
     SX_REGION_VMAX = 5,     /* float32 [slots][2][4096]  reduce: MAX */
-    SX_REGION_FIT = 6       /* float32 [slots][8]: HE row-major (6) + maxC (2); read-only result */
+    SX_REGION_FIT = 6,      /* float32 [slots][8]: HE row-major (6) + maxC (2); read-only result */
+    SX_REGION_COUNTERS = 7, /* int64   [slots][8]: rows below the bracket (2), sampled rows (2), pad; reduce: SUM */
+    SX_REGION_STATUS = 8    /* int32   [slots][4]: [0] bit q set = rank q fell outside its bracket (never expected) */
 };
 
 int64_t sx_macenko_workspace_bytes(int64_t slots);
@@ -145,24 +149,27 @@ int sx_macenko_moments(const void *images, int dtype, int64_t n, int64_t h, int6
                        int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream);
 /* M3-M4: unbiased covariance -> symmetric 3x3 eigen-decomposition -> E = eigvecs[:, (1, 2)].
  * allow_fallback != 0 (transform): slots with fewer than 3 kept rows are flagged to use all rows
- * (torch_backend.py:L409-410); run moments_fallback + basis_fallback afterwards.
+ * (torch_backend.py:L409-410); run moments_fallback afterwards.
  * basis / select act on the slot range [slot0, slot0 + count). */
 int sx_macenko_basis(void *workspace, int64_t slots, int64_t slot0, int64_t count,
                      int allow_fallback, sx_stream_t stream);
+/* Transform only: slots flagged by `basis` re-accumulate every row and get their basis (one CTA per
+ * image; CTAs of unflagged slots exit at once). */
 int sx_macenko_moments_fallback(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
                                 int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream);
-int sx_macenko_basis_fallback(void *workspace, int64_t slots, int64_t slot0, int64_t count,
-                              sx_stream_t stream);
 /* One order-statistic pass.  stage ANGLE: nearest-rank 1st/99th percentile of
  * phi = atan2(OD.e_large, OD.e_mid) over the kept rows (M5-M6); stage CONC: 99th percentile of
  * each least-squares concentration row over all rows (M8-M9).  level 0 histograms a 12-bit
- * prefix of a monotone 24-bit key; level 1 resolves the remaining 12 bits inside the selected
- * bin and records the exact min/max value of every sub-bin. */
+ * prefix of a monotone key over a pseudo-random subsample (about 4096 pixel groups per image);
+ * level 1 is the full pass: it counts the rows below the bracket chosen by select(.,0), resolves
+ * the bracket into 4096 cells and records the exact min/max value of every cell. */
 int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled,
                     int64_t slot0, int stage, int level, void *workspace, int64_t slots,
                     sx_stream_t stream);
-/* Rank search after a hist pass.  (ANGLE,1) also forms HE, its pseudo-inverse and the key range
- * of the concentrations (M7); (CONC,1) stores maxC. */
+/* Per-slot step after a hist pass.  level 0: wanted ranks and their brackets (+-8 sigma of the
+ * sample rank, rounded out to 12-bit prefixes).  level 1: rank search inside the bracket;
+ * (ANGLE,1) also forms HE, its pseudo-inverse and the key range of the concentrations (M7) and
+ * re-arms the histograms; (CONC,1) stores maxC. */
 int sx_macenko_select(void *workspace, int64_t slots, int64_t slot0, int64_t count, int stage,
                       int level, sx_stream_t stream);
 /* M10: C = pinv(HE_src).OD scaled by maxc_ref/maxC_src; OD' = he_ref.C; rgb = clamp(240 exp(-OD'),

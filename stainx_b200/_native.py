@@ -47,7 +47,6 @@ PROTOTYPES: dict[str, list] = {
     "sx_macenko_moments": [_vp, _int, _i64, _i64, _i64, _int, _i64, _vp, _i64, _vp],
     "sx_macenko_basis": [_vp, _i64, _i64, _i64, _int, _vp],
     "sx_macenko_moments_fallback": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _i64, _vp],
-    "sx_macenko_basis_fallback": [_vp, _i64, _i64, _i64, _vp],
     "sx_macenko_hist": [_vp, _int, _i64, _i64, _i64, _int, _i64, _int, _int, _vp, _i64, _vp],
     "sx_macenko_select": [_vp, _i64, _i64, _i64, _int, _int, _vp],
     "sx_macenko_apply": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _vp, _i64, _vp],
@@ -69,7 +68,7 @@ _RESTYPES = {
 SX_U8, SX_F32 = 0, 1
 SX_NCHW, SX_NHWC = 0, 1
 SX_STAGE_ANGLE, SX_STAGE_CONC = 0, 1
-REGIONS = {"moments": 0, "odrange": 1, "hist1": 2, "hist2": 3, "vmin": 4, "vmax": 5, "fit": 6}
+REGIONS = {"moments": 0, "odrange": 1, "hist1": 2, "hist2": 3, "vmin": 4, "vmax": 5, "fit": 6, "counters": 7, "status": 8}
 
 _lib: ctypes.CDLL | None = None
 _load_error: str | None = None

@@ -183,12 +183,14 @@ class MacenkoCUDA(TorchCUDABackendBase):
         ws.basis(0, 1, allow_fallback=False)
         for stage in (_native.SX_STAGE_ANGLE, _native.SX_STAGE_CONC):
             if images.shape[0] > 0:
-                ws.hist(images, True, stage, 0)
+                ws.hist(images, True, stage, 0)   # subsample pass
             red.sum_(ws.region("hist1"))
-            ws.select(0, 1, stage, 0)
+            red.sum_(ws.region("counters"))
+            ws.select(0, 1, stage, 0)             # ranks + brackets, identical on every rank
             if images.shape[0] > 0:
-                ws.hist(images, True, stage, 1)
+                ws.hist(images, True, stage, 1)   # full pass
             red.sum_(ws.region("hist2"))
+            red.sum_(ws.region("counters"))
             red.min_(ws.region("vmin"))
             red.max_(ws.region("vmax"))
             ws.select(0, 1, stage, 1)

@@ -304,43 +304,71 @@ __global__ void __launch_bounds__(kL32Threads, 1) hist_u8_planar_lane32_kernel(c
     const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
     const int64_t first = (int64_t)blockIdx.x * per_cta;
     const int64_t last = first + per_cta < items ? first + per_cta : items;
-    int cur_c = -1;
-    for (int64_t item = first; item < last; ++item) {
+
+    // Two register buffers: the 8 loads of tile i+1 are in flight while tile i is counted.
+    uint4 va[kL32Unroll], vb[kL32Unroll];
+    unsigned oka = 0, okb = 0;
+    auto issue = [&](int64_t item, uint4(&v)[kL32Unroll], unsigned &okmask) {
         const int c = (int)(item / per_channel);
         const int64_t rem = item - (int64_t)c * per_channel;
         const int64_t n = rem / tiles_per_plane;
         const int64_t t = rem - n * tiles_per_plane;
-        if (c != cur_c) {
-            if (cur_c >= 0) fold(cur_c);
-            cur_c = c;
-        }
         const uint8_t *plane = img + (n * 3 + c) * hw;
         const PlaneSplit sp = split_plane(plane, hw);
         const uint4 *body = reinterpret_cast<const uint4 *>(plane + sp.head);
         const int64_t v0 = t * kL32TileVecs;
-        uint4 v[kL32Unroll];
-        bool ok[kL32Unroll];
+        okmask = 0;
 #pragma unroll
         for (int u = 0; u < kL32Unroll; ++u) {
             const int64_t vi = v0 + u * kL32Threads + threadIdx.x;
-            ok[u] = vi < sp.nvec;
-            if (ok[u]) v[u] = ld_stream(body + vi);
+            if (vi < sp.nvec) {
+                v[u] = ld_stream(body + vi);
+                okmask |= 1u << u;
+            }
         }
+    };
+    auto count = [&](int64_t item, const uint4(&v)[kL32Unroll], unsigned okmask) {
 #pragma unroll
         for (int u = 0; u < kL32Unroll; ++u) {
-            if (ok[u]) {
+            if (okmask & (1u << u)) {
                 l32_count4(v[u].x, lane_off, region_addr);
                 l32_count4(v[u].y, lane_off, region_addr);
                 l32_count4(v[u].z, lane_off, region_addr);
                 l32_count4(v[u].w, lane_off, region_addr);
             }
         }
-        if (t == 0) {  // ragged ends of the plane
+        const int c = (int)(item / per_channel);
+        const int64_t rem = item - (int64_t)c * per_channel;
+        const int64_t n = rem / tiles_per_plane;
+        if (rem - n * tiles_per_plane == 0) {  // ragged ends of the plane
+            const uint8_t *plane = img + (n * 3 + c) * hw;
+            const PlaneSplit sp = split_plane(plane, hw);
             const int64_t ragged = sp.head + (hw - sp.tail0);
             if ((int64_t)threadIdx.x < ragged) {
                 const int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
                 atomicAdd(&region[(unsigned)plane[idx] * 32 + lane], 1u);
             }
+        }
+    };
+
+    int cur_c = -1;
+    if (first < last) issue(first, va, oka);
+    for (int64_t item = first; item < last; item += 2) {
+        if (item + 1 < last) issue(item + 1, vb, okb);
+        int c = (int)(item / per_channel);
+        if (c != cur_c) {
+            if (cur_c >= 0) fold(cur_c);
+            cur_c = c;
+        }
+        count(item, va, oka);
+        if (item + 1 < last) {
+            if (item + 2 < last) issue(item + 2, va, oka);
+            c = (int)((item + 1) / per_channel);
+            if (c != cur_c) {
+                fold(cur_c);
+                cur_c = c;
+            }
+            count(item + 1, vb, okb);
         }
     }
     if (cur_c >= 0) fold(cur_c);
@@ -484,6 +512,23 @@ __global__ void ref_hist_kernel(const unsigned long long *__restrict__ counts, f
     ref_hist[c * 256 + b] = __fdiv_rn(cf[b], denom);
 }
 
+// torch.cumsum(float32) on CPU: one double accumulator, rounded to float32 per element.  The adds
+// are inherently serial; the 32 loads + conversions of a chunk are issued together so that only
+// the DADD chain is on the critical path.
+__device__ __forceinline__ void serial_cumsum_256(const float *__restrict__ in, double *__restrict__ out) {
+    double acc = 0.0;
+    for (int chunk = 0; chunk < 8; ++chunk) {
+        double v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (double)in[chunk * 32 + j];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            acc = __dadd_rn(acc, v[j]);
+            out[chunk * 32 + j] = acc;
+        }
+    }
+}
+
 // Reference CDF of channel c into rq[256] (shared): H2a, torch_backend.py:L221-223.
 // The 256 divisions run in parallel; only the double-precision running sum is serial.
 __device__ __forceinline__ void ref_cdf_to_smem(const float *__restrict__ ref_hist_c, float *h, double *dacc, float *rq) {
@@ -495,14 +540,7 @@ __device__ __forceinline__ void ref_cdf_to_smem(const float *__restrict__ ref_hi
     __syncthreads();
     h[b] = __fdiv_rn(h[b], s_denom);
     __syncthreads();
-    if (b == 0) {
-        double acc = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < 256; ++i) {
-            acc = __dadd_rn(acc, (double)h[i]);
-            dacc[i] = acc;
-        }
-    }
+    if (b == 0) serial_cumsum_256(h, dacc);
     __syncthreads();
     rq[b] = __double2float_rn(dacc[b]);
     __syncthreads();
@@ -538,14 +576,7 @@ __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, 
     __syncthreads();
     sq[b] = __fdiv_rn(__ull2float_rn(counts[c * 256 + b]), s_npix_f);  // L234-235
     __syncthreads();
-    if (b == 0) {  // L236: cumsum, double accumulator rounded per element
-        double acc = 0.0;
-#pragma unroll 8
-        for (int i = 0; i < 256; ++i) {
-            acc = __dadd_rn(acc, (double)sq[i]);
-            dacc[i] = acc;
-        }
-    }
+    if (b == 0) serial_cumsum_256(sq, dacc);  // L236: cumsum, double accumulator rounded per element
     __syncthreads();
     sq[b] = __double2float_rn(dacc[b]);
     __syncthreads();

@@ -5,32 +5,38 @@
 // code replaced: csrc/macenko.cu:L145-262 (one-CTA-per-image covariance + analytic eigh) and the
 // ATen pipeline of src/stainx_cuda_torch/csrc/macenko.cu:L67-266 (OD copies, three full sorts).
 //
-// Every pixel pass reads the RGB planes with 128-bit loads and recomputes OD in registers:
-//   moments        OD, tissue mask, shifted first/second moments, per-channel OD range   (M1-M3)
-//   hist(ANGLE,0)  12-bit histogram of a monotone 24-bit key of phi over the kept rows     (M5-M6)
-//   hist(ANGLE,1)  the 12 low bits inside the two selected bins + exact min/max per sub-bin
-//   hist(CONC,0/1) the same two levels for the two concentration rows over all rows        (M8-M9)
-//   apply          concentrations -> rescale -> OD' -> RGB                                 (M10)
-// with one-CTA-per-slot kernels in between (eigen-decomposition, rank search, HE / pinv).
+// FOUR streaming passes over the RGB planes (128-bit loads, OD recomputed in registers) plus two
+// ~3 % subsample passes:
+//   moments         OD, tissue mask, shifted first/second moments, per-channel OD range   (M1-M3)
+//   hist(ANGLE,0)   SAMPLE pass: 12-bit histogram of the angle key over a pseudo-random ~1/64
+//                   subsample -> bracket [lo, hi) that contains the wanted ranks (+-8 sigma)
+//   hist(ANGLE,1)   FULL pass: count keys below the bracket, 4096-cell histogram inside it with
+//                   the exact float min/max of every cell                                (M5-M6)
+//   hist(CONC,0/1)  the same pair for the two concentration rows over all rows           (M8-M9)
+//   apply           concentrations -> rescale -> OD' -> RGB                              (M10)
+// with one-CTA-per-slot kernels in between (eigen-decomposition, bracket, rank search, HE / pinv).
 //
 // Order statistics: phi = atan2(y, x) is never evaluated per pixel.  The selection runs on the
-// "diamond angle" p(y, x) in [-2, 2], a monotone function of atan2(y, x), quantised to 24 bits;
+// "diamond angle" p(y, x) in [-2, 2], a monotone function of atan2(y, x), scaled to [0, 2^24);
 // the selected pixel's (cos, sin) is recovered from p in closed form.  Concentration keys are a
-// linear 24-bit quantisation of [c_lo, c_hi], bounds derived from the OD range and pinv(HE).
-// Level 1 records the exact float min / max of every 24-bit cell, so the returned value is an
-// exact order statistic whenever the cell holds one distinct value (always, in practice) and is
-// otherwise within 2^-24 of the key range.
+// linear map of [c_lo, c_hi] (bounds from the OD range and pinv(HE)) onto the same key range.
+// The full pass resolves the bracket into 4096 cells and records each cell's exact float min and
+// max, so the returned value is the exact order statistic whenever the selected cell holds one
+// distinct value (the normal case: a bracket is ~1 % of the data), else it is interpolated inside
+// a cell of width <= bracket/4096.  The nearest-rank index is exact: ranks below the bracket are
+// counted, not estimated.
 #include "common.cuh"
 
 namespace sx {
 namespace macenko {
 
 constexpr int kThreads = 256;
-constexpr int kBins = 4096;      // per level
-constexpr int kKeyBits = 24;
+constexpr int kBins = 4096;      // coarse bins of the sample pass == cells of the full pass
 constexpr float kKeyMax = 16777215.0f;
 constexpr float kBeta = 0.15f;   // torch_backend.py:L542
 constexpr float kShift = 0.75f;  // moments are accumulated about this OD value
+constexpr int kSampleGroups = 4096;  // pixel groups sampled per image (float32: 16 K px, uint8: 64 K px)
+constexpr double kBracketZ = 8.0;    // half-width of the rank bracket in sample standard deviations
 
 constexpr float kLn2 = 0.693147180559945309f;
 constexpr float kLog2_240 = 7.906890595608519f;
@@ -42,8 +48,10 @@ struct SlotState {
     int pad0;
     long long n_sel;      // rows entering the angle selection
     long long n_all;      // rows in the slot
-    int bin1[2];          // selected level-0 bin per query
-    long long rank1[2];   // rank inside that bin
+    long long rank[2];    // wanted 0-based rank per query (nearest-rank index)
+    float lo_f[2];        // bracket [lo_f, hi_f) per query, in key units (multiples of 4096)
+    float hi_f[2];
+    float inv_nb[2];      // 1 / (coarse bins spanned by the bracket): key offset -> cell
     float val[2];         // selected values (angle: diamond angle p; conc: concentration)
     float pinv[6];        // (HE^T HE)^-1 HE^T, 2x3 row-major
     float c_lo[2];        // concentration key mapping: key = (C - c_lo) * c_scale
@@ -51,37 +59,43 @@ struct SlotState {
 };
 
 struct Layout {
-    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, state, total;
+    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, total;
     __host__ __device__ explicit Layout(int64_t slots) {
         int64_t o = 0;
-        moments = o; o += slots * 12 * 8;
-        odrange = o; o += slots * 8 * 4;
-        hist1 = o;   o += slots * 2 * kBins * 4;
-        hist2 = o;   o += slots * 2 * kBins * 4;
-        vmin = o;    o += slots * 2 * kBins * 4;
-        vmax = o;    o += slots * 2 * kBins * 4;
-        fit = o;     o += slots * 8 * 4;
-        state = o;   o += slots * (int64_t)sizeof(SlotState);
+        moments = o;  o += slots * 12 * 8;
+        counters = o; o += slots * 8 * 8;
+        odrange = o;  o += slots * 8 * 4;
+        hist1 = o;    o += slots * 2 * kBins * 4;
+        hist2 = o;    o += slots * 2 * kBins * 4;
+        vmin = o;     o += slots * 2 * kBins * 4;
+        vmax = o;     o += slots * 2 * kBins * 4;
+        fit = o;      o += slots * 8 * 4;
+        status = o;   o += slots * 4 * 4;
+        state = (o + 15) / 16 * 16; o = state + slots * (int64_t)sizeof(SlotState);
         total = (o + 255) / 256 * 256;
     }
 };
 
 struct Ws {
     double *moments;
+    unsigned long long *counters;  // [slot][8]: below[2], sample count[2], pad
     float *odrange;
     unsigned *hist1, *hist2;
     float *vmin, *vmax, *fit;
+    int *status;                   // [slot][4]: [0] bit q set = rank of query q fell outside its bracket
     SlotState *state;
     __host__ __device__ Ws(void *base, int64_t slots) {
         Layout L(slots);
         char *b = static_cast<char *>(base);
         moments = reinterpret_cast<double *>(b + L.moments);
+        counters = reinterpret_cast<unsigned long long *>(b + L.counters);
         odrange = reinterpret_cast<float *>(b + L.odrange);
         hist1 = reinterpret_cast<unsigned *>(b + L.hist1);
         hist2 = reinterpret_cast<unsigned *>(b + L.hist2);
         vmin = reinterpret_cast<float *>(b + L.vmin);
         vmax = reinterpret_cast<float *>(b + L.vmax);
         fit = reinterpret_cast<float *>(b + L.fit);
+        status = reinterpret_cast<int *>(b + L.status);
         state = reinterpret_cast<SlotState *>(b + L.state);
     }
 };
@@ -161,20 +175,58 @@ __device__ __forceinline__ float diamond_angle(float y, float x) {
     float r = a > 0.0f ? __fdividef(y, a) : 0.0f;
     return x >= 0.0f ? r : (y >= 0.0f ? __fsub_rn(2.0f, r) : __fsub_rn(-2.0f, r));
 }
-__device__ __forceinline__ unsigned angle_key(float p) {  // [-2,2] -> [0, 2^24)
-    float u = __fmul_rn(__fadd_rn(p, 2.0f), 4194304.0f);
-    return (unsigned)__float2int_rz(fminf(fmaxf(u, 0.0f), kKeyMax));
+// Keys are floats in [0, 2^24): monotone in the quantity being ranked.
+__device__ __forceinline__ float angle_key(float p) {  // p in [-2,2]
+    return fminf(fmaxf(__fmul_rn(__fadd_rn(p, 2.0f), 4194304.0f), 0.0f), kKeyMax);
 }
-__device__ __forceinline__ unsigned conc_key(float c, float lo, float scale) {
-    float u = __fmul_rn(__fsub_rn(c, lo), scale);
-    return (unsigned)__float2int_rz(fminf(fmaxf(u, 0.0f), kKeyMax));
+__device__ __forceinline__ float conc_key(float c, float lo, float scale) {
+    return fminf(fmaxf(__fmul_rn(__fsub_rn(c, lo), scale), 0.0f), kKeyMax);
 }
 __device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
     return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
 }
 
 // ---- moments (M1-M3) ---------------------------------------------------------------------------
-template <typename T, bool VEC, bool FALLBACK>
+// Per-thread accumulation of one pixel group; float32 partial sums over the group's <= 16 pixels.
+template <int kPix, bool MASKED>
+__device__ __forceinline__ void moments_group(const float (&od)[3][kPix], double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
+    float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+        const float r = od[0][k], gg = od[1][k], b = od[2][k];
+        if (MASKED) {
+            lo[0] = fminf(lo[0], r); lo[1] = fminf(lo[1], gg); lo[2] = fminf(lo[2], b);
+            hi[0] = fmaxf(hi[0], r); hi[1] = fmaxf(hi[1], gg); hi[2] = fmaxf(hi[2], b);
+        }
+        const bool keep = !MASKED || fminf(r, fminf(gg, b)) >= kBeta;  // L404-405
+        const float m = keep ? 1.0f : 0.0f;
+        const float x = (r - kShift) * m, y = (gg - kShift) * m, z = (b - kShift) * m;
+        s[0] += m;
+        s[1] += x; s[2] += y; s[3] += z;
+        s[4] = __fmaf_rn(x, x, s[4]); s[5] = __fmaf_rn(x, y, s[5]); s[6] = __fmaf_rn(x, z, s[6]);
+        s[7] = __fmaf_rn(y, y, s[7]); s[8] = __fmaf_rn(y, z, s[8]); s[9] = __fmaf_rn(z, z, s[9]);
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
+}
+
+// CTA-wide sum of acc[10] into shared red[0][*] (valid for threads < 10 after the call).
+__device__ __forceinline__ void block_sum10(double (&acc)[10], double (*red)[10]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const double r = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        double r = 0.0;
+        for (int k = 0; k < kThreads / 32; ++k) r += red[k][threadIdx.x];
+        acc[0] = r;  // thread i < 10 now holds total i in acc[0]
+    }
+}
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
@@ -184,7 +236,6 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
-    if (FALLBACK && !ws.state[slot].use_all) return;
     if constexpr (sizeof(T) == 1) {
         build_u8_table<true>(tab);
         __syncthreads();
@@ -196,49 +247,23 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
         float od[3][kPix];
         load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
-        float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < kPix; ++k) {
-            const float r = od[0][k], gg = od[1][k], b = od[2][k];
-            if (!FALLBACK) {
-                lo[0] = fminf(lo[0], r); lo[1] = fminf(lo[1], gg); lo[2] = fminf(lo[2], b);
-                hi[0] = fmaxf(hi[0], r); hi[1] = fmaxf(hi[1], gg); hi[2] = fmaxf(hi[2], b);
-            }
-            const bool keep = FALLBACK || fminf(r, fminf(gg, b)) >= kBeta;  // L404-405
-            const float m = keep ? 1.0f : 0.0f;
-            const float x = (r - kShift) * m, y = (gg - kShift) * m, z = (b - kShift) * m;
-            s[0] += m;
-            s[1] += x; s[2] += y; s[3] += z;
-            s[4] = __fmaf_rn(x, x, s[4]); s[5] = __fmaf_rn(x, y, s[5]); s[6] = __fmaf_rn(x, z, s[6]);
-            s[7] = __fmaf_rn(y, y, s[7]); s[8] = __fmaf_rn(y, z, s[8]); s[9] = __fmaf_rn(z, z, s[9]);
-        }
-#pragma unroll
-        for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
+        moments_group<kPix, true>(od, acc, lo, hi);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        double r = warp_sum(acc[i]);
-        if (lane == 0) red[warp][i] = r;
+    for (int c = 0; c < 3; ++c) {
+        const float a = warp_max(-lo[c]), b = warp_max(hi[c]);
+        if (lane == 0) { redf[warp][c] = a; redf[warp][3 + c] = b; }
     }
-    if (!FALLBACK) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = warp_max(-lo[c]), b = warp_max(hi[c]);
-            if (lane == 0) { redf[warp][c] = a; redf[warp][3 + c] = b; }
-        }
-    }
-    __syncthreads();
+    block_sum10(acc, red);
     if (threadIdx.x < 10) {
-        double r = 0.0;
-        for (int k = 0; k < kThreads / 32; ++k) r += red[k][threadIdx.x];
-        if (r != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], r);
-    } else if (!FALLBACK && threadIdx.x >= 32 && threadIdx.x < 38) {
+        if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
         const int i = threadIdx.x - 32;
         float r = -INFINITY;
         for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i]);
         atomic_max_f32(&ws.odrange[slot * 8 + i], r);
-    } else if (!FALLBACK && threadIdx.x == 64 && chunk == 0) {
+    } else if (threadIdx.x == 64 && chunk == 0) {
         atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);
     }
 }
@@ -283,25 +308,8 @@ __device__ void eigh3(const double C[3][3], double V[3][3], double w[3]) {
     for (int i = 0; i < 3; ++i) { w[i] = ws_[i]; for (int j = 0; j < 3; ++j) V[i][j] = Vs[i][j]; }
 }
 
-// One thread per slot.  mode 0: first pass (may flag the fallback); mode 1: after the fallback pass.
-__global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_t count, int allow_fallback, int mode) {
-    Ws ws(ws_base, slots);
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= count) return;
-    const int64_t slot = slot0 + idx;
-    SlotState &st = ws.state[slot];
-    double *m = ws.moments + slot * 12;
-    if (mode == 0) {
-        st.n_all = (long long)(m[10] + 0.5);
-        st.use_all = 0;
-        if (allow_fallback && m[0] < 3.0) {  // L409-410
-            st.use_all = 1;
-            for (int i = 0; i < 10; ++i) m[i] = 0.0;
-            return;
-        }
-    } else if (!st.use_all) {
-        return;
-    }
+// E = eigvecs[:, (1, 2)] of the unbiased covariance held (as shifted raw moments) in m[0..9].
+__device__ void basis_from_moments(const double *m, SlotState &st) {
     const double n = m[0];
     st.n_sel = (long long)(n + 0.5);
     double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
@@ -316,21 +324,145 @@ __global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_
     for (int i = 0; i < 3; ++i) { st.e[i * 2] = (float)V[i][1]; st.e[i * 2 + 1] = (float)V[i][2]; }  // L415
 }
 
-// ---- order-statistic histogram passes ----------------------------------------------------------
-template <typename T, bool VEC, int STAGE, int LEVEL>
-__global__ void __launch_bounds__(kThreads) hist_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+// One thread per slot.
+__global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_t count, int allow_fallback) {
+    Ws ws(ws_base, slots);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const int64_t slot = slot0 + idx;
+    SlotState &st = ws.state[slot];
+    const double *m = ws.moments + slot * 12;
+    st.n_all = (long long)(m[10] + 0.5);
+    st.use_all = 0;
+    if (allow_fallback && m[0] < 3.0) {  // L409-410: handled by fallback_kernel
+        st.use_all = 1;
+        return;
+    }
+    basis_from_moments(m, st);
+}
+
+// Fallback (transform only): slots with fewer than 3 masked rows use every row.  One CTA per image;
+// CTAs of unflagged slots exit at once, a flagged slot's CTA re-accumulates the whole image without
+// the mask and computes its basis (rare path, so it is not spread over several CTAs).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict__ img, int64_t hw, int64_t slot0, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    constexpr int kQ = (STAGE == SX_STAGE_CONC) ? 2 : 1;  // level-0 histograms per CTA
     __shared__ float tab[256];
-    __shared__ unsigned sh[LEVEL == 0 ? kQ * kBins : 1];
+    __shared__ double red[kThreads / 32][10];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x;
+    const int64_t slot = slot0 + n;
+    if (!ws.state[slot].use_all) return;
+    if constexpr (sizeof(T) == 1) {
+        build_u8_table<true>(tab);
+        __syncthreads();
+    }
+    const T *image = img + n * 3 * hw;
+    const int64_t groups = hw / kPix;
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float lo[3], hi[3];
+    for (int64_t gi = threadIdx.x; gi < groups; gi += kThreads) {
+        float od[3][kPix];
+        load_pixels<T, VEC, true>(image + gi * kPix, hw, tab, od);
+        moments_group<kPix, false>(od, acc, lo, hi);
+    }
+    block_sum10(acc, red);
+    __shared__ double tot[10];
+    if (threadIdx.x < 10) tot[threadIdx.x] = acc[0];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = tot[i];
+        basis_from_moments(tot, ws.state[slot]);
+    }
+}
+
+// ---- order-statistic passes ----------------------------------------------------------------------
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// Keys of one pixel.  ANGLE: one key (both queries), valid only for kept rows.  CONC: two keys.
+template <int STAGE>
+__device__ __forceinline__ bool pixel_keys(const SlotState &st, float r, float gg, float b, float (&key)[2], float (&val)[2]) {
+    if constexpr (STAGE == SX_STAGE_ANGLE) {
+        if (!(st.use_all || fminf(r, fminf(gg, b)) >= kBeta)) return false;
+        const float t0 = dot3(r, gg, b, st.e[0], st.e[2], st.e[4]);  // That[:,0] (L417)
+        const float t1 = dot3(r, gg, b, st.e[1], st.e[3], st.e[5]);  // That[:,1]
+        val[0] = val[1] = diamond_angle(t1, t0);                     // monotone in atan2(t1, t0) (L418)
+        key[0] = key[1] = angle_key(val[0]);
+    } else {
+        val[0] = dot3(r, gg, b, st.pinv[0], st.pinv[1], st.pinv[2]);  // L444
+        val[1] = dot3(r, gg, b, st.pinv[3], st.pinv[4], st.pinv[5]);
+        key[0] = conc_key(val[0], st.c_lo[0], st.c_scale[0]);
+        key[1] = conc_key(val[1], st.c_lo[1], st.c_scale[1]);
+    }
+    return true;
+}
+
+// LEVEL 0 -- sample pass: every image contributes ~kSampleGroups pixel groups, one per stride-sized
+// window at a hashed offset (so that periodic image structure cannot alias with the sampling).
+template <typename T, bool VEC, int STAGE>
+__global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    constexpr int kQ = (STAGE == SX_STAGE_CONC) ? 2 : 1;
+    __shared__ float tab[256];
+    __shared__ unsigned sh[kQ * kBins];
+    __shared__ unsigned s_cnt[kQ];
     Ws ws(ws_base, slots);
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
     const SlotState st = ws.state[slot];
     if constexpr (sizeof(T) == 1) build_u8_table<true>(tab);
-    if constexpr (LEVEL == 0)
-        for (int i = threadIdx.x; i < kQ * kBins; i += kThreads) sh[i] = 0u;
+    for (int i = threadIdx.x; i < kQ * kBins; i += kThreads) sh[i] = 0u;
+    if (threadIdx.x < kQ) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+
+    const T *image = img + n * 3 * g.hw;
+    const int64_t groups = g.hw / kPix;
+    const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
+    const int64_t nsamp = groups / stride;
+    unsigned cnt = 0;
+    for (int64_t i = (int64_t)chunk * kThreads + threadIdx.x; i < nsamp; i += (int64_t)g.cpi * kThreads) {
+        const unsigned off = stride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + (unsigned)n * 0x85ebca6bu), (unsigned)stride) : 0u;
+        const int64_t gi = i * stride + off;
+        float od[3][kPix];
+        load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
+#pragma unroll
+        for (int k = 0; k < kPix; ++k) {
+            float key[2], val[2];
+            if (!pixel_keys<STAGE>(st, od[0][k], od[1][k], od[2][k], key, val)) continue;
+            atomicAdd(&sh[__float2int_rz(key[0]) >> 12], 1u);
+            if (kQ == 2) atomicAdd(&sh[kBins + (__float2int_rz(key[1]) >> 12)], 1u);
+            ++cnt;
+        }
+    }
+    cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt[0], cnt);
+    __syncthreads();
+    unsigned *h1 = ws.hist1 + slot * 2 * kBins;
+    for (int i = threadIdx.x; i < kQ * kBins; i += kThreads)
+        if (sh[i]) atomicAdd(&h1[i], sh[i]);
+    if (threadIdx.x == 0 && s_cnt[0]) {
+        atomicAdd(&ws.counters[slot * 8 + 2], (unsigned long long)s_cnt[0]);
+        if (kQ == 2) atomicAdd(&ws.counters[slot * 8 + 3], (unsigned long long)s_cnt[0]);
+    }
+}
+
+// LEVEL 1 -- full pass: count keys below each bracket, resolve the bracket into kBins cells.
+template <typename T, bool VEC, int STAGE>
+__global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    __shared__ float tab[256];
+    __shared__ unsigned s_below[2];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = pooled ? 0 : slot0 + n;
+    const SlotState st = ws.state[slot];
+    if constexpr (sizeof(T) == 1) build_u8_table<true>(tab);
+    if (threadIdx.x < 2) s_below[threadIdx.x] = 0u;
     __syncthreads();
     unsigned *h2 = ws.hist2 + slot * 2 * kBins;
     float *vmin = ws.vmin + slot * 2 * kBins;
@@ -338,95 +470,72 @@ __global__ void __launch_bounds__(kThreads) hist_kernel(const T *__restrict__ im
 
     const T *image = img + n * 3 * g.hw;
     const int64_t groups = g.hw / kPix;
+    unsigned below[2] = {0u, 0u};
     for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
         float od[3][kPix];
         load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
 #pragma unroll
         for (int k = 0; k < kPix; ++k) {
-            const float r = od[0][k], gg = od[1][k], b = od[2][k];
-            if constexpr (STAGE == SX_STAGE_ANGLE) {
-                const bool keep = st.use_all || fminf(r, fminf(gg, b)) >= kBeta;
-                if (!keep) continue;
-                const float t0 = dot3(r, gg, b, st.e[0], st.e[2], st.e[4]);  // That[:,0] (L417)
-                const float t1 = dot3(r, gg, b, st.e[1], st.e[3], st.e[5]);  // That[:,1]
-                const float p = diamond_angle(t1, t0);                       // ~ atan2(t1, t0) (L418)
-                const unsigned key = angle_key(p);
-                if constexpr (LEVEL == 0) {
-                    atomicAdd(&sh[key >> 12], 1u);
-                } else {
+            float key[2], val[2];
+            if (!pixel_keys<STAGE>(st, od[0][k], od[1][k], od[2][k], key, val)) continue;
 #pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        if ((int)(key >> 12) == st.bin1[q]) {
-                            const int sub = q * kBins + (int)(key & 4095u);
-                            atomicAdd(&h2[sub], 1u);
-                            atomic_min_f32(&vmin[sub], p);
-                            atomic_max_f32(&vmax[sub], p);
-                        }
-                }
-            } else {
-                const float c0 = dot3(r, gg, b, st.pinv[0], st.pinv[1], st.pinv[2]);  // L444
-                const float c1 = dot3(r, gg, b, st.pinv[3], st.pinv[4], st.pinv[5]);
-                const unsigned k0 = conc_key(c0, st.c_lo[0], st.c_scale[0]);
-                const unsigned k1 = conc_key(c1, st.c_lo[1], st.c_scale[1]);
-                if constexpr (LEVEL == 0) {
-                    atomicAdd(&sh[k0 >> 12], 1u);
-                    atomicAdd(&sh[kBins + (k1 >> 12)], 1u);
-                } else {
-                    if ((int)(k0 >> 12) == st.bin1[0]) {
-                        const int sub = (int)(k0 & 4095u);
-                        atomicAdd(&h2[sub], 1u);
-                        atomic_min_f32(&vmin[sub], c0);
-                        atomic_max_f32(&vmax[sub], c0);
-                    }
-                    if ((int)(k1 >> 12) == st.bin1[1]) {
-                        const int sub = kBins + (int)(k1 & 4095u);
-                        atomicAdd(&h2[sub], 1u);
-                        atomic_min_f32(&vmin[sub], c1);
-                        atomic_max_f32(&vmax[sub], c1);
-                    }
+            for (int q = 0; q < 2; ++q) {
+                if (key[q] < st.lo_f[q]) {
+                    ++below[q];
+                } else if (key[q] < st.hi_f[q]) {
+                    const int cell = min(__float2int_rz(__fmul_rn(__fsub_rn(key[q], st.lo_f[q]), st.inv_nb[q])), kBins - 1);
+                    const int sub = q * kBins + cell;
+                    atomicAdd(&h2[sub], 1u);
+                    atomic_min_f32(&vmin[sub], val[q]);
+                    atomic_max_f32(&vmax[sub], val[q]);
                 }
             }
         }
     }
-    if constexpr (LEVEL == 0) {
-        __syncthreads();
-        unsigned *h1 = ws.hist1 + slot * 2 * kBins;
-        for (int i = threadIdx.x; i < kQ * kBins; i += kThreads)
-            if (sh[i]) atomicAdd(&h1[i], sh[i]);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const unsigned r = (unsigned)__reduce_add_sync(0xffffffffu, below[q]);
+        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_below[q], r);
     }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_below[threadIdx.x]) atomicAdd(&ws.counters[slot * 8 + threadIdx.x], (unsigned long long)s_below[threadIdx.x]);
 }
 
-// ---- rank search (one CTA per slot) --------------------------------------------------------------
+// ---- per-slot rank searches (one CTA per slot) --------------------------------------------------
 // Nearest-rank index (torch_backend.py:L362-365): round_half_even(0.01 * q * (n - 1)), in double.
 __device__ __forceinline__ long long rank_index(double q, long long n) { return (long long)rint(0.01 * q * (double)(n - 1)); }
 
-// Finds the bin of `hist` (kBins entries) holding 0-based rank k; returns bin, rank inside it and
-// its count through shared memory.  Called by all kThreads threads.
-__device__ void find_rank(const unsigned *hist, long long k, int *out_bin, long long *out_rank, unsigned *out_count) {
+// Inclusive prefix sums of a kBins histogram into shared `pre` (as unsigned long long).
+__device__ void block_prefix(const unsigned *__restrict__ hist, unsigned long long *pre) {
     __shared__ unsigned long long part[kThreads];
     constexpr int kPer = kBins / kThreads;
+    unsigned v[kPer];
     unsigned long long s = 0;
-    for (int i = 0; i < kPer; ++i) s += hist[threadIdx.x * kPer + i];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { v[i] = hist[threadIdx.x * kPer + i]; s += v[i]; }
     part[threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long cum = 0;
-        int t = 0;
-        for (; t < kThreads - 1; ++t) {
-            if (cum + part[t] > (unsigned long long)k) break;
-            cum += part[t];
-        }
-        int b = t * kPer;
-        const int last = t * kPer + kPer - 1;
-        for (; b < last; ++b) {
-            if (cum + hist[b] > (unsigned long long)k) break;
-            cum += hist[b];
-        }
-        *out_bin = b;
-        *out_rank = k - (long long)cum;
-        *out_count = hist[b];
+    // Hillis-Steele scan over the 256 partial sums
+    for (int o = 1; o < kThreads; o <<= 1) {
+        const unsigned long long add = threadIdx.x >= o ? part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        part[threadIdx.x] += add;
+        __syncthreads();
     }
+    unsigned long long run = part[threadIdx.x] - s;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { run += v[i]; pre[threadIdx.x * kPer + i] = run; }
     __syncthreads();
+}
+
+// Index of the bin holding 0-based rank k: first b with pre[b] > k (binary search; any thread).
+__device__ __forceinline__ int bin_of_rank(const unsigned long long *pre, long long k) {
+    int lo = 0, hi = kBins - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pre[mid] > (unsigned long long)k) hi = mid; else lo = mid + 1;
+    }
+    return lo;
 }
 
 // Unit direction (cos, sin) of a diamond angle p in [-2, 2].
@@ -440,76 +549,121 @@ __device__ __forceinline__ void diamond_to_unit(float p, double &c, double &s) {
     c = x / h; s = y / h;
 }
 
-__global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage, int level) {
+// After the sample pass: wanted ranks and their brackets.
+__global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
+    __shared__ unsigned long long pre[kBins];
     Ws ws(ws_base, slots);
     const int64_t slot = slot0 + blockIdx.x;
     SlotState &st = ws.state[slot];
-    __shared__ int s_bin;
-    __shared__ long long s_rank;
-    __shared__ unsigned s_count;
     for (int q = 0; q < 2; ++q) {
-        if (level == 0) {
+        const int hq = stage == SX_STAGE_ANGLE ? 0 : q;  // ANGLE: both queries read histogram 0
+        if (q == 0 || hq != 0) block_prefix(ws.hist1 + slot * 2 * kBins + hq * kBins, pre);
+        if (threadIdx.x == 0) {
             const long long n = stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all;
             const double pct = stage == SX_STAGE_ANGLE ? (q == 0 ? 1.0 : 99.0) : 99.0;  // L421-422, L447-448
             long long k = rank_index(pct, n);
-            if (k < 0) k = 0;
             if (k > n - 1) k = n - 1;
-            const unsigned *h = ws.hist1 + slot * 2 * kBins + (stage == SX_STAGE_ANGLE ? 0 : q * kBins);
-            find_rank(h, k, &s_bin, &s_rank, &s_count);
-            if (threadIdx.x == 0) { st.bin1[q] = s_bin; st.rank1[q] = s_rank; }
-        } else {
-            const unsigned *h = ws.hist2 + slot * 2 * kBins + q * kBins;
-            find_rank(h, st.rank1[q], &s_bin, &s_rank, &s_count);
-            if (threadIdx.x == 0) {
-                const float lo = ws.vmin[slot * 2 * kBins + q * kBins + s_bin];
-                const float hi = ws.vmax[slot * 2 * kBins + q * kBins + s_bin];
-                float v = lo;
-                if (s_count > 1u && hi > lo) v = lo + (hi - lo) * (float)((double)s_rank / (double)(s_count - 1u));
-                st.val[q] = v;
+            if (k < 0) k = 0;
+            st.rank[q] = k;
+            const long long m = (long long)ws.counters[slot * 8 + 2 + hq];
+            int b_lo = 0, b_hi = kBins - 1;
+            if (m > 0 && n > 0) {
+                long long r_lo, r_hi;
+                if (m >= n) {  // the "sample" is the whole slot: the coarse bin of rank k is certain
+                    r_lo = r_hi = k;
+                } else {
+                    const double ks = (double)k * (double)m / (double)n;
+                    const double sd = sqrt((double)m * (0.01 * pct) * (1.0 - 0.01 * pct));
+                    r_lo = (long long)floor(ks - kBracketZ * sd) - 2;
+                    r_hi = (long long)ceil(ks + kBracketZ * sd) + 2;
+                }
+                if (r_lo > 0) b_lo = bin_of_rank(pre, r_lo < m - 1 ? r_lo : m - 1);
+                if (r_hi < m - 1) b_hi = bin_of_rank(pre, r_hi);
             }
+            st.lo_f[q] = (float)(b_lo * 4096);
+            st.hi_f[q] = (float)((b_hi + 1) * 4096);
+            st.inv_nb[q] = (float)(1.0 / (double)(b_hi - b_lo + 1));
         }
         __syncthreads();
     }
-    if (level != 1 || threadIdx.x != 0) return;
-    float *fit = ws.fit + slot * 8;
-    if (stage == SX_STAGE_ANGLE) {
-        // M7 (L425-439): v = E (cos phi, sin phi); HE columns ordered by first component.
-        double c0, s0, c1, s1;
-        diamond_to_unit(st.val[0], c0, s0);
-        diamond_to_unit(st.val[1], c1, s1);
-        float vmin[3], vmax[3];
-        for (int i = 0; i < 3; ++i) {
-            vmin[i] = (float)((double)st.e[i * 2] * c0 + (double)st.e[i * 2 + 1] * s0);
-            vmax[i] = (float)((double)st.e[i * 2] * c1 + (double)st.e[i * 2 + 1] * s1);
-        }
-        const bool min_first = vmin[0] > vmax[0];
-        float he[6];
-        for (int i = 0; i < 3; ++i) { he[i * 2] = min_first ? vmin[i] : vmax[i]; he[i * 2 + 1] = min_first ? vmax[i] : vmin[i]; }
-        for (int i = 0; i < 6; ++i) fit[i] = he[i];
-        // M8 (L444): least squares via the normal equations, in double.
-        double a00 = 0, a01 = 0, a11 = 0;
-        for (int i = 0; i < 3; ++i) { a00 += (double)he[i * 2] * he[i * 2]; a01 += (double)he[i * 2] * he[i * 2 + 1]; a11 += (double)he[i * 2 + 1] * he[i * 2 + 1]; }
-        const double det = a00 * a11 - a01 * a01;
-        for (int i = 0; i < 3; ++i) {
-            st.pinv[i] = (float)((a11 * he[i * 2] - a01 * he[i * 2 + 1]) / det);
-            st.pinv[3 + i] = (float)((-a01 * he[i * 2] + a00 * he[i * 2 + 1]) / det);
-        }
-        // Key range of each concentration row from the per-channel OD range (interval arithmetic).
-        const float *rg = ws.odrange + slot * 8;
-        for (int j = 0; j < 2; ++j) {
-            double lo = 0, hi = 0;
-            for (int c = 0; c < 3; ++c) {
-                const double pj = st.pinv[j * 3 + c], a = pj * (double)(-rg[c]), b = pj * (double)rg[3 + c];
-                lo += fmin(a, b); hi += fmax(a, b);
+}
+
+// After the full pass: the order statistics; (ANGLE) HE, pinv, concentration key range; (CONC) maxC.
+__global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
+    __shared__ unsigned long long pre[kBins];
+    Ws ws(ws_base, slots);
+    const int64_t slot = slot0 + blockIdx.x;
+    SlotState &st = ws.state[slot];
+    const int64_t base = slot * 2 * kBins;
+    for (int q = 0; q < 2; ++q) {
+        block_prefix(ws.hist2 + base + q * kBins, pre);
+        if (threadIdx.x == 0) {
+            const long long inside = (long long)pre[kBins - 1];
+            long long k = st.rank[q] - (long long)ws.counters[slot * 8 + q];
+            if (k < 0 || k >= inside) {  // the rank fell outside the bracket (should not happen)
+                atomicOr(&ws.status[slot * 4], 1 << q);
+                k = k < 0 ? 0 : (inside > 0 ? inside - 1 : 0);
             }
-            const double pad = 1e-6 * (fabs(lo) + fabs(hi)) + 1e-12;
-            lo -= pad; hi += pad;
-            st.c_lo[j] = (float)lo;
-            st.c_scale[j] = (float)(16777216.0 / (hi - lo));
+            const int cell = bin_of_rank(pre, k);
+            const long long before = cell > 0 ? (long long)pre[cell - 1] : 0;
+            const long long cnt = (long long)pre[cell] - before;
+            const float lo = ws.vmin[base + q * kBins + cell], hi = ws.vmax[base + q * kBins + cell];
+            float v = lo;
+            if (cnt > 1 && hi > lo) v = lo + (hi - lo) * (float)((double)(k - before) / (double)(cnt - 1));
+            st.val[q] = v;
         }
-    } else {
-        fit[6] = st.val[0];  // maxC (L447-449)
-        fit[7] = st.val[1];
+        __syncthreads();
+    }
+    float *fit = ws.fit + slot * 8;
+    if (threadIdx.x == 0) {
+        if (stage == SX_STAGE_ANGLE) {
+            // M7 (L425-439): v = E (cos phi, sin phi); HE columns ordered by first component.
+            double c0, s0, c1, s1;
+            diamond_to_unit(st.val[0], c0, s0);
+            diamond_to_unit(st.val[1], c1, s1);
+            float vmin[3], vmax[3];
+            for (int i = 0; i < 3; ++i) {
+                vmin[i] = (float)((double)st.e[i * 2] * c0 + (double)st.e[i * 2 + 1] * s0);
+                vmax[i] = (float)((double)st.e[i * 2] * c1 + (double)st.e[i * 2 + 1] * s1);
+            }
+            const bool min_first = vmin[0] > vmax[0];
+            float he[6];
+            for (int i = 0; i < 3; ++i) { he[i * 2] = min_first ? vmin[i] : vmax[i]; he[i * 2 + 1] = min_first ? vmax[i] : vmin[i]; }
+            for (int i = 0; i < 6; ++i) fit[i] = he[i];
+            // M8 (L444): least squares via the normal equations, in double.
+            double a00 = 0, a01 = 0, a11 = 0;
+            for (int i = 0; i < 3; ++i) { a00 += (double)he[i * 2] * he[i * 2]; a01 += (double)he[i * 2] * he[i * 2 + 1]; a11 += (double)he[i * 2 + 1] * he[i * 2 + 1]; }
+            const double det = a00 * a11 - a01 * a01;
+            for (int i = 0; i < 3; ++i) {
+                st.pinv[i] = (float)((a11 * he[i * 2] - a01 * he[i * 2 + 1]) / det);
+                st.pinv[3 + i] = (float)((-a01 * he[i * 2] + a00 * he[i * 2 + 1]) / det);
+            }
+            // Key range of each concentration row from the per-channel OD range (interval arithmetic).
+            const float *rg = ws.odrange + slot * 8;
+            for (int j = 0; j < 2; ++j) {
+                double lo = 0, hi = 0;
+                for (int c = 0; c < 3; ++c) {
+                    const double pj = st.pinv[j * 3 + c], a = pj * (double)(-rg[c]), b = pj * (double)rg[3 + c];
+                    lo += fmin(a, b); hi += fmax(a, b);
+                }
+                const double pad = 1e-6 * (fabs(lo) + fabs(hi)) + 1e-12;
+                lo -= pad; hi += pad;
+                st.c_lo[j] = (float)lo;
+                st.c_scale[j] = (float)(16777216.0 / (hi - lo));
+            }
+        } else {
+            fit[6] = st.val[0];  // maxC (L447-449)
+            fit[7] = st.val[1];
+        }
+    }
+    if (stage == SX_STAGE_ANGLE) {  // re-arm the slot's histograms and counters for the CONC stage
+        for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+            ws.hist1[base + i] = 0u;
+            ws.hist2[base + i] = 0u;
+            ws.vmin[base + i] = INFINITY;
+            ws.vmax[base + i] = -INFINITY;
+        }
+        if (threadIdx.x < 8) ws.counters[slot * 8 + threadIdx.x] = 0ull;
     }
 }
 
@@ -614,34 +768,22 @@ __global__ void init_kernel(void *ws_base, int64_t slots) {
         ws.vmax[i] = -INFINITY;
     }
     if (i < slots * 12) ws.moments[i] = 0.0;
-    if (i < slots * 8) { ws.odrange[i] = -INFINITY; ws.fit[i] = 0.0f; }
+    if (i < slots * 8) { ws.odrange[i] = -INFINITY; ws.fit[i] = 0.0f; ws.counters[i] = 0ull; }
+    if (i < slots * 4) ws.status[i] = 0;
     if (i < slots) {
         SlotState z = {};
         ws.state[i] = z;
     }
 }
 
-// Re-arm the level-1 arrays between the ANGLE and CONC stages.
-__global__ void rearm_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_t count) {
-    Ws ws(ws_base, slots);
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < count * 2 * kBins) {
-        const int64_t i = slot0 * 2 * kBins + j;
-        ws.hist1[i] = 0u;
-        ws.hist2[i] = 0u;
-        ws.vmin[i] = INFINITY;
-        ws.vmax[i] = -INFINITY;
-    }
-}
-
 static int g_ctas_per_sm = 4;
-static int64_t g_group_bytes = 64ll << 20;  // images per L2-resident group = g_group_bytes / image bytes
+static int64_t g_group_bytes = 0;  // 0: one launch per phase over the whole batch; > 0: L2-sized image groups
 
-static PassGeom make_geom(int64_t n, int64_t hw, int kpix) {
+static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_override = -1) {
     PassGeom g;
     g.n_img = n;
     g.hw = hw;
-    const int64_t groups = hw / kpix;
+    const int64_t groups = groups_override >= 0 ? groups_override : hw / kpix;
     int64_t want = ((int64_t)sm_count() * g_ctas_per_sm + n - 1) / (n > 0 ? n : 1);
     const int64_t most = (groups + kThreads - 1) / kThreads;
     if (want > most) want = most;
@@ -674,14 +816,11 @@ using namespace sx::macenko;
         }                                                                      \
     } while (0)
 
-static bool images_vec_ok(const void *images, const void *out, int dtype, int out_dtype, int64_t hw) {
-    bool in_ok = dtype == SX_F32 ? vec_ok<float>(images, nullptr, hw) : vec_ok<uint8_t>(images, nullptr, hw);
-    if (!in_ok) return false;
-    if (out == nullptr) return true;
-    // the output plane offsets are multiples of hw elements of the OUTPUT type
-    const int64_t in_pix = dtype == SX_F32 ? 4 : 16;
-    (void)out_dtype;
-    return aligned16(out) && hw % in_pix == 0;
+static bool images_vec_ok(const void *images, const void *out, int dtype, int64_t hw) {
+    const bool in_ok = dtype == SX_F32 ? vec_ok<float>(images, nullptr, hw) : vec_ok<uint8_t>(images, nullptr, hw);
+    // output plane offsets are multiples of hw elements of the output type (>= 1 byte), so an
+    // aligned base and hw % kPix == 0 keep every 128-bit store aligned
+    return in_ok && (out == nullptr || aligned16(out));
 }
 
 extern "C" {
@@ -705,6 +844,8 @@ int sx_macenko_region(int64_t slots, int region, int64_t *offset, int64_t *bytes
         case SX_REGION_VMIN: *offset = L.vmin; *bytes = slots * 2 * kBins * 4; break;
         case SX_REGION_VMAX: *offset = L.vmax; *bytes = slots * 2 * kBins * 4; break;
         case SX_REGION_FIT: *offset = L.fit; *bytes = slots * 8 * 4; break;
+        case SX_REGION_COUNTERS: *offset = L.counters; *bytes = slots * 8 * 8; break;
+        case SX_REGION_STATUS: *offset = L.status; *bytes = slots * 4 * 4; break;
         default: return sx::fail(SX_ERR_INVALID, "unknown region %d", region);
     }
     return SX_OK;
@@ -725,6 +866,11 @@ static int check_slots(int64_t n, int pooled, int64_t slot0, int64_t slots) {
     return SX_OK;
 }
 
+static int check_range(int64_t slot0, int64_t count, int64_t slots) {
+    SX_REQUIRE(slots > 0 && slot0 >= 0 && count >= 0 && slot0 + count <= slots, "slot range [%lld, %lld) outside [0, %lld)", (long long)slot0, (long long)(slot0 + count), (long long)slots);
+    return SX_OK;
+}
+
 int sx_macenko_moments(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled, int64_t slot0, void *workspace, int64_t slots, sx_stream_t stream_) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     if (int rc = check_slots(n, pooled, slot0, slots)) return rc;
@@ -732,12 +878,21 @@ int sx_macenko_moments(const void *images, int dtype, int64_t n, int64_t h, int6
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const bool vec = images_vec_ok(images, nullptr, dtype, dtype, hw);
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
-        moments_kernel<T, VEC, false><<<(unsigned)(n * g.cpi), kThreads, 0, stream>>>(static_cast<const T *>(images), g, pooled, slot0, workspace, slots);
+        moments_kernel<T, VEC><<<(unsigned)(n * g.cpi), kThreads, 0, stream>>>(static_cast<const T *>(images), g, pooled, slot0, workspace, slots);
     });
     SX_LAUNCHED("macenko::moments_kernel");
+    return SX_OK;
+}
+
+int sx_macenko_basis(void *workspace, int64_t slots, int64_t slot0, int64_t count, int allow_fallback, sx_stream_t stream) {
+    SX_REQUIRE(workspace, "workspace is NULL");
+    if (int rc = check_range(slot0, count, slots)) return rc;
+    if (count == 0) return SX_OK;
+    basis_kernel<<<(unsigned)((count + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(workspace, slots, slot0, count, allow_fallback);
+    SX_LAUNCHED("macenko::basis_kernel");
     return SX_OK;
 }
 
@@ -748,35 +903,11 @@ int sx_macenko_moments_fallback(const void *images, int dtype, int64_t n, int64_
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const bool vec = images_vec_ok(images, nullptr, dtype, dtype, hw);
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
-        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
-        moments_kernel<T, VEC, true><<<(unsigned)(n * g.cpi), kThreads, 0, stream>>>(static_cast<const T *>(images), g, 0, slot0, workspace, slots);
+        fallback_kernel<T, VEC><<<(unsigned)n, kThreads, 0, stream>>>(static_cast<const T *>(images), hw, slot0, workspace, slots);
     });
-    SX_LAUNCHED("macenko::moments_kernel<fallback>");
-    return SX_OK;
-}
-
-static int check_range(int64_t slot0, int64_t count, int64_t slots) {
-    SX_REQUIRE(slots > 0 && slot0 >= 0 && count >= 0 && slot0 + count <= slots, "slot range [%lld, %lld) outside [0, %lld)", (long long)slot0, (long long)(slot0 + count), (long long)slots);
-    return SX_OK;
-}
-
-int sx_macenko_basis(void *workspace, int64_t slots, int64_t slot0, int64_t count, int allow_fallback, sx_stream_t stream) {
-    SX_REQUIRE(workspace, "workspace is NULL");
-    if (int rc = check_range(slot0, count, slots)) return rc;
-    if (count == 0) return SX_OK;
-    basis_kernel<<<(unsigned)((count + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(workspace, slots, slot0, count, allow_fallback, 0);
-    SX_LAUNCHED("macenko::basis_kernel");
-    return SX_OK;
-}
-
-int sx_macenko_basis_fallback(void *workspace, int64_t slots, int64_t slot0, int64_t count, sx_stream_t stream) {
-    SX_REQUIRE(workspace, "workspace is NULL");
-    if (int rc = check_range(slot0, count, slots)) return rc;
-    if (count == 0) return SX_OK;
-    basis_kernel<<<(unsigned)((count + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(workspace, slots, slot0, count, 1, 1);
-    SX_LAUNCHED("macenko::basis_kernel<fallback>");
+    SX_LAUNCHED("macenko::fallback_kernel");
     return SX_OK;
 }
 
@@ -788,17 +919,24 @@ int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const bool vec = images_vec_ok(images, nullptr, dtype, dtype, hw);
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
-        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
-        const unsigned grid = (unsigned)(n * g.cpi);
         const T *p = static_cast<const T *>(images);
-        if (stage == SX_STAGE_ANGLE && level == 0) hist_kernel<T, VEC, SX_STAGE_ANGLE, 0><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
-        else if (stage == SX_STAGE_ANGLE) hist_kernel<T, VEC, SX_STAGE_ANGLE, 1><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
-        else if (level == 0) hist_kernel<T, VEC, SX_STAGE_CONC, 0><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
-        else hist_kernel<T, VEC, SX_STAGE_CONC, 1><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+        if (level == 0) {
+            const int64_t groups = hw / Pix<T, VEC>::kPix;
+            const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
+            PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix, groups / stride);
+            const unsigned grid = (unsigned)(n * g.cpi);
+            if (stage == SX_STAGE_ANGLE) sample_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+            else sample_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+        } else {
+            PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
+            const unsigned grid = (unsigned)(n * g.cpi);
+            if (stage == SX_STAGE_ANGLE) resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+            else resolve_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+        }
     });
-    SX_LAUNCHED("macenko::hist_kernel");
+    SX_LAUNCHED("macenko::hist kernels");
     return SX_OK;
 }
 
@@ -808,13 +946,9 @@ int sx_macenko_select(void *workspace, int64_t slots, int64_t slot0, int64_t cou
     SX_REQUIRE((stage == SX_STAGE_ANGLE || stage == SX_STAGE_CONC) && (level == 0 || level == 1), "bad stage/level (%d, %d)", stage, level);
     if (count == 0) return SX_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    select_kernel<<<(unsigned)count, kThreads, 0, stream>>>(workspace, slots, slot0, stage, level);
-    SX_LAUNCHED("macenko::select_kernel");
-    if (stage == SX_STAGE_ANGLE && level == 1) {  // re-arm the histograms for the CONC stage
-        const int64_t items = count * 2 * kBins;
-        rearm_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(workspace, slots, slot0, count);
-        SX_LAUNCHED("macenko::rearm_kernel");
-    }
+    if (level == 0) bracket_kernel<<<(unsigned)count, kThreads, 0, stream>>>(workspace, slots, slot0, stage);
+    else select_kernel<<<(unsigned)count, kThreads, 0, stream>>>(workspace, slots, slot0, stage);
+    SX_LAUNCHED("macenko::select kernels");
     return SX_OK;
 }
 
@@ -827,9 +961,8 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
     const bool unit = out_scale != 1.0f;
     SX_REQUIRE(!unit || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
     const int64_t hw = h * w;
-    if (n == 0 || hw == 0) return SX_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const bool vec = images_vec_ok(images, out, dtype, out_dtype, hw);
+    const bool vec = images_vec_ok(images, out, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
         const unsigned grid = (unsigned)(n * g.cpi);
@@ -850,9 +983,8 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     const int64_t out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * h * w;
     int rc;
     if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
-    // Every statistic is per image, so the batch is walked in groups of images whose RGB planes
-    // fit in L2 together: the first pass of a group streams it from HBM, the five later passes
-    // of the same group are served from L2.
+    // Every statistic is per image, so the batch may be walked in groups of images (group_bytes > 0)
+    // whose planes fit in L2 together; by default each phase is one launch over the whole batch.
     int64_t group = g_group_bytes > 0 ? g_group_bytes / in_bytes : n;
     if (group < 1) group = 1;
     if (group > n) group = n;
@@ -863,7 +995,6 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
         if ((rc = sx_macenko_moments(img, dtype, cnt, h, w, 0, i0, workspace, n, s))) return rc;
         if ((rc = sx_macenko_basis(workspace, n, i0, cnt, 1, s))) return rc;
         if ((rc = sx_macenko_moments_fallback(img, dtype, cnt, h, w, i0, workspace, n, s))) return rc;
-        if ((rc = sx_macenko_basis_fallback(workspace, n, i0, cnt, s))) return rc;
         for (int stage = 0; stage < 2; ++stage)
             for (int level = 0; level < 2; ++level) {
                 if ((rc = sx_macenko_hist(img, dtype, cnt, h, w, 0, i0, stage, level, workspace, n, s))) return rc;

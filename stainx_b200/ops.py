@@ -197,8 +197,8 @@ def reinhard_fit(images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
 
 
 # ----------------------------------------------------------------------------- macenko
-_REGION_DTYPES = {"moments": torch.float64, "odrange": torch.float32, "hist1": torch.int32, "hist2": torch.int32, "vmin": torch.float32, "vmax": torch.float32, "fit": torch.float32}
-_REGION_SHAPES = {"moments": (12,), "odrange": (8,), "hist1": (2, 4096), "hist2": (2, 4096), "vmin": (2, 4096), "vmax": (2, 4096), "fit": (8,)}
+_REGION_DTYPES = {"moments": torch.float64, "odrange": torch.float32, "hist1": torch.int32, "hist2": torch.int32, "vmin": torch.float32, "vmax": torch.float32, "fit": torch.float32, "counters": torch.int64, "status": torch.int32}
+_REGION_SHAPES = {"moments": (12,), "odrange": (8,), "hist1": (2, 4096), "hist2": (2, 4096), "vmin": (2, 4096), "vmax": (2, 4096), "fit": (8,), "counters": (8,), "status": (4,)}
 
 
 class MacenkoWorkspace:
@@ -238,9 +238,6 @@ class MacenkoWorkspace:
     def moments_fallback(self, images: torch.Tensor, slot0: int = 0) -> None:
         n, h, w = _check_images(images)
         self._call("sx_macenko_moments_fallback", _ptr(images), _dtype_code(images), n, h, w, slot0, _ptr(self.buffer), self.slots)
-
-    def basis_fallback(self, slot0: int, count: int) -> None:
-        self._call("sx_macenko_basis_fallback", _ptr(self.buffer), self.slots, slot0, count)
 
     def hist(self, images: torch.Tensor, pooled: bool, stage: int, level: int, slot0: int = 0) -> None:
         n, h, w = _check_images(images)

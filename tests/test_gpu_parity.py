@@ -343,6 +343,36 @@ def test_macenko_fallback_when_mask_empty(cuda, ox):
     assert best_sign_diff(out, cand_p, cand_m).max() <= 1
 
 
+def test_macenko_brackets_always_hold_the_rank(cuda):
+    """The subsample bracket must contain every wanted rank (status region stays zero), on noise,
+    on stain-like tiles, on a periodic pattern that could alias with strided sampling, and on an
+    image with a tiny tissue fraction."""
+    from stainx_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    noise = torch.rand((2, 3, 512, 512), generator=g)
+    tiles = he_batch(2, 512, 512).float() / 255.0
+    yy, xx = torch.meshgrid(torch.arange(512), torch.arange(512), indexing="ij")
+    stripes = (0.25 + 0.5 * ((xx // 4 + yy // 64) % 2).float()).expand(1, 3, 512, 512).clone()
+    stripes[:, 0] *= 0.8
+    stripes += 0.05 * torch.rand((1, 3, 512, 512), generator=g)
+    sparse = torch.full((1, 3, 512, 512), 0.97)
+    sparse[:, :, 100:108, 200:232] = tiles[0, :, 100:108, 200:232]
+    batch = torch.cat([noise, tiles, stripes.clamp(0, 1), sparse]).contiguous().to(cuda)
+    he, maxc = ops.macenko_fit(tiles[:1].contiguous().to(cuda))
+    ws = ops.MacenkoWorkspace(batch.shape[0], cuda)
+    ws.begin()
+    ws.moments(batch, False)
+    ws.basis(0, batch.shape[0], True)
+    ws.moments_fallback(batch)
+    for stage in (0, 1):
+        for level in (0, 1):
+            ws.hist(batch, False, stage, level)
+            ws.select(0, batch.shape[0], stage, level)
+    assert int(ws.region("status").abs().sum()) == 0
+    assert bool(torch.isfinite(ws.region("fit")).all())
+
+
 def test_macenko_per_image_independence(cuda):
     """Every statistic is per image: transform(batch)[i] == transform(batch[i:i+1]) bit for bit."""
     from stainx_b200 import Macenko
@@ -416,11 +446,13 @@ def test_macenko_sharded_fit_emulation(cuda):
         for w, s in zip(wss, shards):
             w.hist(s, True, stage, 0)
         reduce("hist1", "sum")
+        reduce("counters", "sum")
         for w in wss:
             w.select(0, 1, stage, 0)
         for w, s in zip(wss, shards):
             w.hist(s, True, stage, 1)
         reduce("hist2", "sum")
+        reduce("counters", "sum")
         reduce("vmin", "min")
         reduce("vmax", "max")
         for w in wss:
@@ -430,3 +462,4 @@ def test_macenko_sharded_fit_emulation(cuda):
         assert torch.allclose(fit[:6].reshape(3, 2), he_ref, rtol=0, atol=1e-6)
         assert torch.allclose(fit[6:8], maxc_ref, rtol=1e-6, atol=0)
     assert torch.equal(wss[0].region("fit"), wss[1].region("fit"))
+    assert int(wss[0].region("status").abs().sum()) == 0

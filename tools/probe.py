@@ -139,7 +139,7 @@ def probe_macenko():
     report("macenko select", timeit(lambda: ws.select(0, n, 1, 1)), 0.001)
     full_phases()
     report("macenko apply f32 -> f32 unit", timeit(lambda: ws.apply(src, he, maxc, out, True)), 24 * px)
-    for group_mb in (0, 32, 64, 96):
+    for group_mb in (0, 64):
         lib.sx_macenko_set_tuning(-1, group_mb << 20)
         report(f"macenko transform f32 64x1024^2 group={group_mb}MB", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
     for ctas in (2, 8):
