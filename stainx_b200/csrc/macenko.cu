@@ -51,7 +51,9 @@ struct SlotState {
     long long rank[2];    // wanted 0-based rank per query (nearest-rank index)
     float lo_f[2];        // bracket [lo_f, hi_f) per query, in key units (multiples of 4096)
     float hi_f[2];
-    float inv_nb[2];      // 1 / (coarse bins spanned by the bracket): key offset -> cell
+    float inv_w[2];       // (kBins - 2) / (hi_f - lo_f): key offset -> inner cell 1 .. kBins-2
+    int open_lo[2];       // bracket reaches the smallest key: keys < lo_f go to catch-all cell 0
+    int open_hi[2];       // bracket reaches the largest key: keys >= hi_f go to catch-all cell kBins-1
     float val[2];         // selected values (angle: diamond angle p; conc: concentration)
     float pinv[6];        // (HE^T HE)^-1 HE^T, 2x3 row-major
     float c_lo[2];        // concentration key mapping: key = (C - c_lo) * c_scale
@@ -480,15 +482,20 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__
             if (!pixel_keys<STAGE>(st, od[0][k], od[1][k], od[2][k], key, val)) continue;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
+                int cell;
                 if (key[q] < st.lo_f[q]) {
-                    ++below[q];
+                    if (!st.open_lo[q]) { ++below[q]; continue; }
+                    cell = 0;
                 } else if (key[q] < st.hi_f[q]) {
-                    const int cell = min(__float2int_rz(__fmul_rn(__fsub_rn(key[q], st.lo_f[q]), st.inv_nb[q])), kBins - 1);
-                    const int sub = q * kBins + cell;
-                    atomicAdd(&h2[sub], 1u);
-                    atomic_min_f32(&vmin[sub], val[q]);
-                    atomic_max_f32(&vmax[sub], val[q]);
+                    cell = 1 + min(__float2int_rz(__fmul_rn(__fsub_rn(key[q], st.lo_f[q]), st.inv_w[q])), kBins - 3);
+                } else {
+                    if (!st.open_hi[q]) continue;
+                    cell = kBins - 1;
                 }
+                const int sub = q * kBins + cell;
+                atomicAdd(&h2[sub], 1u);
+                atomic_min_f32(&vmin[sub], val[q]);
+                atomic_max_f32(&vmax[sub], val[q]);
             }
         }
     }
@@ -566,23 +573,31 @@ __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_
             if (k < 0) k = 0;
             st.rank[q] = k;
             const long long m = (long long)ws.counters[slot * 8 + 2 + hq];
-            int b_lo = 0, b_hi = kBins - 1;
+            // Inner cells 1 .. kBins-2 tile [lo_f, hi_f).  When the rank bracket reaches an end of
+            // the sample, the true order statistic may lie beyond the sample's extreme value: that
+            // side is left open and its keys are collected in a catch-all cell (0 or kBins-1).
+            int b_lo = 0, b_hi = kBins - 1, open_lo = 1, open_hi = 1;
             if (m > 0 && n > 0) {
                 long long r_lo, r_hi;
                 if (m >= n) {  // the "sample" is the whole slot: the coarse bin of rank k is certain
                     r_lo = r_hi = k;
+                    open_lo = open_hi = 0;
                 } else {
                     const double ks = (double)k * (double)m / (double)n;
                     const double sd = sqrt((double)m * (0.01 * pct) * (1.0 - 0.01 * pct));
                     r_lo = (long long)floor(ks - kBracketZ * sd) - 2;
                     r_hi = (long long)ceil(ks + kBracketZ * sd) + 2;
+                    open_lo = r_lo <= 0;
+                    open_hi = r_hi >= m - 1;
                 }
-                if (r_lo > 0) b_lo = bin_of_rank(pre, r_lo < m - 1 ? r_lo : m - 1);
-                if (r_hi < m - 1) b_hi = bin_of_rank(pre, r_hi);
+                b_lo = bin_of_rank(pre, r_lo < 0 ? 0 : (r_lo < m - 1 ? r_lo : m - 1));
+                b_hi = bin_of_rank(pre, r_hi < 0 ? 0 : (r_hi < m - 1 ? r_hi : m - 1));
             }
             st.lo_f[q] = (float)(b_lo * 4096);
             st.hi_f[q] = (float)((b_hi + 1) * 4096);
-            st.inv_nb[q] = (float)(1.0 / (double)(b_hi - b_lo + 1));
+            st.inv_w[q] = (float)((double)(kBins - 2) / ((double)(b_hi - b_lo + 1) * 4096.0));
+            st.open_lo[q] = open_lo;
+            st.open_hi[q] = open_hi;
         }
         __syncthreads();
     }

@@ -227,13 +227,21 @@ class MacenkoWorkspace:
         st = self.state
         for q in range(2):
             key, val = keys[q]
-            cnt[q] += int((key < st["lo_f"][q]).sum())
-            sel = (key >= st["lo_f"][q]) & (key < st["hi_f"][q])
-            cell = np.minimum(((key[sel] - st["lo_f"][q]) * st["inv_nb"][q]).astype(np.int64), BINS - 1)
-            self._r["hist2"][0, q] += torch.from_numpy(np.bincount(cell, minlength=BINS).astype(np.int32))
+            lo, hi = st["lo_f"][q], st["hi_f"][q]
+            inner = (key >= lo) & (key < hi)
+            cell = np.full(key.shape, -1, dtype=np.int64)
+            cell[inner] = 1 + np.minimum(((key[inner] - lo) * st["inv_w"][q]).astype(np.int64), BINS - 3)
+            if st["open_lo"][q]:
+                cell[key < lo] = 0
+            else:
+                cnt[q] += int((key < lo).sum())
+            if st["open_hi"][q]:
+                cell[key >= hi] = BINS - 1
+            sel = cell >= 0
+            self._r["hist2"][0, q] += torch.from_numpy(np.bincount(cell[sel], minlength=BINS).astype(np.int32))
             vmin, vmax = self._r["vmin"][0, q].numpy(), self._r["vmax"][0, q].numpy()
-            np.minimum.at(vmin, cell, val[sel])
-            np.maximum.at(vmax, cell, val[sel])
+            np.minimum.at(vmin, cell[sel], val[sel])
+            np.maximum.at(vmax, cell[sel], val[sel])
 
     @staticmethod
     def _bin_of_rank(h, k):
@@ -244,7 +252,8 @@ class MacenkoWorkspace:
         st = self.state
         cnt = self._r["counters"][0]
         if level == 0:  # wanted ranks and brackets
-            st["rank"], st["lo_f"], st["hi_f"], st["inv_nb"] = [0, 0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]
+            st["rank"], st["lo_f"], st["hi_f"], st["inv_w"] = [0, 0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]
+            st["open_lo"], st["open_hi"] = [1, 1], [1, 1]
             for q in range(2):
                 hq = 0 if stage == 0 else q
                 n = st["n_sel"] if stage == 0 else st["n_all"]
@@ -257,17 +266,17 @@ class MacenkoWorkspace:
                 if m > 0 and n > 0:
                     if m >= n:
                         r_lo = r_hi = k
+                        st["open_lo"][q] = st["open_hi"][q] = 0
                     else:
                         ks = k * m / n
                         sd = np.sqrt(m * (0.01 * pct) * (1 - 0.01 * pct))
                         r_lo, r_hi = int(np.floor(ks - 8 * sd)) - 2, int(np.ceil(ks + 8 * sd)) + 2
-                    if r_lo > 0:
-                        b_lo = self._bin_of_rank(h, min(r_lo, m - 1))
-                    if r_hi < m - 1:
-                        b_hi = self._bin_of_rank(h, r_hi)
+                        st["open_lo"][q], st["open_hi"][q] = int(r_lo <= 0), int(r_hi >= m - 1)
+                    b_lo = self._bin_of_rank(h, min(max(r_lo, 0), m - 1))
+                    b_hi = self._bin_of_rank(h, min(max(r_hi, 0), m - 1))
                 st["lo_f"][q] = np.float32(b_lo * 4096)
                 st["hi_f"][q] = np.float32((b_hi + 1) * 4096)
-                st["inv_nb"][q] = np.float32(1.0 / (b_hi - b_lo + 1))
+                st["inv_w"][q] = np.float32((BINS - 2) / ((b_hi - b_lo + 1) * 4096.0))
             return
         val = [0.0, 0.0]
         for q in range(2):

@@ -117,27 +117,32 @@ def probe_macenko():
     ws = ops.MacenkoWorkspace(n, dev)
     out = torch.empty_like(src)
 
-    def full_phases():
+    def phases_until(stop_stage, stop_level):
+        """Run the pipeline up to (not including) hist(stop_stage, stop_level)."""
         ws.begin()
         ws.moments(src, False)
         ws.basis(0, n, True)
+        ws.moments_fallback(src)
         for stage in (0, 1):
             for level in (0, 1):
+                if (stage, level) == (stop_stage, stop_level):
+                    return
                 ws.hist(src, False, stage, level)
                 ws.select(0, n, stage, level)
 
-    full_phases()
     report("macenko begin (init workspace)", timeit(ws.begin), 0.001)
     report("macenko moments f32", timeit(lambda: ws.moments(src, False)), 12 * px)
     report("macenko basis", timeit(lambda: ws.basis(0, n, True)), 0.001)
-    full_phases()
+    report("macenko moments_fallback (nothing flagged)", timeit(lambda: ws.moments_fallback(src)), 0.001)
     for stage in (0, 1):
         for level in (0, 1):
-            full_phases()
+            phases_until(stage, level)
             report(f"macenko hist f32 stage={stage} level={level}", timeit(lambda: ws.hist(src, False, stage, level)), 12 * px)
-    full_phases()
-    report("macenko select", timeit(lambda: ws.select(0, n, 1, 1)), 0.001)
-    full_phases()
+            phases_until(stage, level)
+            ws.hist(src, False, stage, level)
+            report(f"macenko select stage={stage} level={level}", timeit(lambda: ws.select(0, n, stage, level)), 0.001)
+    phases_until(2, 0)
+    print("status flags:", int(ws.region("status").abs().sum()))
     report("macenko apply f32 -> f32 unit", timeit(lambda: ws.apply(src, he, maxc, out, True)), 24 * px)
     for group_mb in (0, 64):
         lib.sx_macenko_set_tuning(-1, group_mb << 20)
