@@ -33,27 +33,25 @@ namespace macenko {
 constexpr int kThreads = 256;
 constexpr int kBins = 4096;      // coarse bins of the sample pass == cells of the full pass
 constexpr float kKeyMax = 16777215.0f;
-constexpr float kBeta = 0.15f;   // torch_backend.py:L542
-constexpr float kShift = 0.75f;  // moments are accumulated about this OD value
 constexpr int kSampleGroups = 4096;  // pixel groups sampled per image (float32: 16 K px, uint8: 64 K px)
 constexpr double kBracketZ = 8.0;    // half-width of the rank bracket in sample standard deviations
 
-constexpr float kLn2 = 0.693147180559945309f;
 constexpr float kLog2_240 = 7.906890595608519f;
 
 // ---- workspace layout (regions are contiguous over slots so that each can be all-reduced) ----
 struct SlotState {
     float e[6];           // E (3x2) row-major: [i][0] = middle eigenvector, [i][1] = largest
     int use_all;          // < 3 rows pass the mask: use every row (L409-410)
-    int pad0;
+    int group_px;         // pixels per sampled group (set by the sample pass)
     long long n_sel;      // rows entering the angle selection
     long long n_all;      // rows in the slot
     long long rank[2];    // wanted 0-based rank per query (nearest-rank index)
-    float lo_f[2];        // bracket [lo_f, hi_f) per query, in key units (multiples of 4096)
-    float hi_f[2];
-    float inv_w[2];       // (kBins - 2) / (hi_f - lo_f): key offset -> inner cell 1 .. kBins-2
-    int open_lo[2];       // bracket reaches the smallest key: keys < lo_f go to catch-all cell 0
-    int open_hi[2];       // bracket reaches the largest key: keys >= hi_f go to catch-all cell kBins-1
+    float proj[8];        // two affine maps of l (4 floats each) giving the stage's ranked quantities
+    float lo_v[2];        // bracket [lo_v, hi_v) per query, in the value space of the ranked quantity
+    float hi_v[2];
+    float inv_w[2];       // (kBins - 2) / (hi_v - lo_v): value offset -> inner cell 1 .. kBins-2
+    int open_lo[2];       // bracket reaches the smallest value: values < lo_v go to catch-all cell 0
+    int open_hi[2];       // bracket reaches the largest value: values >= hi_v go to cell kBins-1
     float val[2];         // selected values (angle: diamond angle p; conc: concentration)
     float pinv[6];        // (HE^T HE)^-1 HE^T, 2x3 row-major
     float c_lo[2];        // concentration key mapping: key = (C - c_lo) * c_scale
@@ -105,61 +103,62 @@ struct Ws {
 // ---- pixel loading -----------------------------------------------------------------------------
 // A thread owns kPix consecutive pixels of one image: one 128-bit load per colour plane
 // (float32: 4 px, uint8: 16 px).  Planes that are not 16-byte aligned use kPix = 1.
+//
+// Every pass works on l = log2(255 x + 1) (float32: one FFMA + one MUFU.LG2; uint8: a 256-entry
+// table built per CTA in the reference's operation order x = v / 255, t = x * 255 + 1,
+// torch_backend.py:L112, L550).  Optical density is affine in l,
+//     OD = -ln((255 x + 1) / 240) = ln2 * (log2(240) - l),
+// so the tissue mask, the moments, both projections and the reconstruction fold into FMAs on l:
+//     min_c OD_c >= 0.15        <=>  max_c l_c <= kLThr
+//     cov(OD) = ln2^2 cov(l)     (same eigenvectors)
+//     OD . v  = ln2 log2(240) sum(v) - ln2 (l . v)
 template <typename T, bool VEC>
 struct Pix {
     static constexpr int kPix = VEC ? (int)(16 / sizeof(T)) : 1;
 };
 
-// uint8: table of 256 entries (OD or log2(255x+1)), built per CTA with the accurate functions in
-// the reference's operation order: x = v / 255; t = x * 255 + 1 (torch_backend.py:L112, L550).
-template <bool WANT_OD>
-__device__ __forceinline__ void build_u8_table(float *tab) {
+constexpr float kLThr = 7.690486339f;    // log2(240) - 0.15 / ln2
+constexpr float kLShift = 6.5f;          // moments are accumulated about this value of l
+
+__device__ __forceinline__ void build_l_table(float *tab) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        float x = __fdiv_rn((float)i, 255.0f);
-        float t = __fadd_rn(__fmul_rn(x, 255.0f), 1.0f);
-        tab[i] = WANT_OD ? -logf(__fdiv_rn(t, 240.0f)) : log2f(t);
+        const float x = __fdiv_rn((float)i, 255.0f);
+        tab[i] = log2f(__fadd_rn(__fmul_rn(x, 255.0f), 1.0f));
     }
 }
-
-// float32: l = log2(255x + 1) on the SFU; OD = ln2 * (log2(240) - l).  Every op is pinned (no
-// contraction) so that all passes see bit-identical OD values for the same pixel.
 __device__ __forceinline__ float f32_l(float x) { return __log2f(__fmaf_rn(x, 255.0f, 1.0f)); }
-__device__ __forceinline__ float l_to_od(float l) { return __fmul_rn(kLn2, __fsub_rn(kLog2_240, l)); }
 
-// Loads kPix pixels; v[c][k] = OD (WANT_OD) or log2(255x+1) of channel c of pixel k.
-template <typename T, bool VEC, bool WANT_OD>
-__device__ __forceinline__ void load_pixels(const T *__restrict__ base, int64_t hw, const float *tab, float (&v)[3][Pix<T, VEC>::kPix]) {
+// Loads kPix pixels; l[c][k] = log2(255 x + 1) of channel c of pixel k.
+template <typename T, bool VEC>
+__device__ __forceinline__ void load_l(const T *__restrict__ base, int64_t hw, const float *tab, float (&l)[3][Pix<T, VEC>::kPix]) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     if constexpr (sizeof(T) == 4) {
         if constexpr (VEC) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float4 q = ld_stream(reinterpret_cast<const float4 *>(base + c * hw));
-                v[c][0] = q.x; v[c][1] = q.y; v[c][2] = q.z; v[c][3] = q.w;
+                const float4 q = ld_stream(reinterpret_cast<const float4 *>(base + c * hw));
+                l[c][0] = q.x; l[c][1] = q.y; l[c][2] = q.z; l[c][3] = q.w;
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c][0] = base[c * hw];
+            for (int c = 0; c < 3; ++c) l[c][0] = base[c * hw];
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int k = 0; k < kPix; ++k) {
-                float l = f32_l(v[c][k]);
-                v[c][k] = WANT_OD ? l_to_od(l) : l;
-            }
+            for (int k = 0; k < kPix; ++k) l[c][k] = f32_l(l[c][k]);
     } else {
         if constexpr (VEC) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                uint4 q = ld_stream(reinterpret_cast<const uint4 *>(base + c * hw));
-                unsigned w[4] = {q.x, q.y, q.z, q.w};
+                const uint4 q = ld_stream(reinterpret_cast<const uint4 *>(base + c * hw));
+                const unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int k = 0; k < kPix; ++k) v[c][k] = tab[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+                for (int k = 0; k < kPix; ++k) l[c][k] = tab[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c][0] = tab[base[c * hw]];
+            for (int c = 0; c < 3; ++c) l[c][0] = tab[base[c * hw]];
         }
     }
 }
@@ -170,49 +169,75 @@ struct PassGeom {
     int cpi;  // CTAs per image
 };
 
-// ---- keys ------------------------------------------------------------------------------------
+// ---- ranked quantities ---------------------------------------------------------------------------
 // Diamond angle: monotone in atan2(y, x) over (-pi, pi], range [-2, 2].
 __device__ __forceinline__ float diamond_angle(float y, float x) {
-    float a = __fadd_rn(fabsf(x), fabsf(y));
-    float r = a > 0.0f ? __fdividef(y, a) : 0.0f;
+    const float a = __fadd_rn(fabsf(x), fabsf(y));
+    float r = __fdividef(y, a);
+    r = a > 0.0f ? r : 0.0f;
     return x >= 0.0f ? r : (y >= 0.0f ? __fsub_rn(2.0f, r) : __fsub_rn(-2.0f, r));
 }
-// Keys are floats in [0, 2^24): monotone in the quantity being ranked.
+// value = aff[3] + aff[0] l0 + aff[1] l1 + aff[2] l2   (pinned: every pass must agree bit for bit)
+__device__ __forceinline__ float affine3(const float *aff, float l0, float l1, float l2) {
+    return __fmaf_rn(aff[2], l2, __fmaf_rn(aff[1], l1, __fmaf_rn(aff[0], l0, aff[3])));
+}
+// Sample-pass keys: floats in [0, 2^24), monotone in the ranked value.
 __device__ __forceinline__ float angle_key(float p) {  // p in [-2,2]
     return fminf(fmaxf(__fmul_rn(__fadd_rn(p, 2.0f), 4194304.0f), 0.0f), kKeyMax);
 }
 __device__ __forceinline__ float conc_key(float c, float lo, float scale) {
     return fminf(fmaxf(__fmul_rn(__fsub_rn(c, lo), scale), 0.0f), kKeyMax);
 }
-__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
-    return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+
+// The two ranked values of one pixel.  ANGLE: the diamond angle of (That1, That0) for kept rows
+// (both queries share it), NaN for masked rows so that every later comparison is false.
+// CONC: the two concentrations.
+struct RankParams {
+    float proj[8];
+    int use_all;
+    __device__ __forceinline__ explicit RankParams(const SlotState &s) : use_all(s.use_all) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) proj[i] = s.proj[i];
+    }
+};
+
+template <int STAGE>
+__device__ __forceinline__ void ranked_values(const RankParams &st, float l0, float l1, float l2, float &v0, float &v1) {
+    if constexpr (STAGE == SX_STAGE_ANGLE) {
+        const float t0 = affine3(st.proj, l0, l1, l2);      // That[:,0] (L417)
+        const float t1 = affine3(st.proj + 4, l0, l1, l2);  // That[:,1]
+        const float p = diamond_angle(t1, t0);              // monotone in atan2(t1, t0) (L418)
+        const bool keep = st.use_all || fmaxf(l0, fmaxf(l1, l2)) <= kLThr;  // L404-405
+        v0 = v1 = keep ? p : __int_as_float(0x7fc00000);
+    } else {
+        v0 = affine3(st.proj, l0, l1, l2);  // L444
+        v1 = affine3(st.proj + 4, l0, l1, l2);
+    }
 }
 
 // ---- moments (M1-M3) ---------------------------------------------------------------------------
-// Per-thread accumulation of one pixel group; float32 partial sums over the group's <= 16 pixels.
+// One pixel group into float32 partial sums s[10] (count, 3 sums, 6 products of l - kLShift over the
+// kept rows) and the running per-channel range of l over all rows.
 template <int kPix, bool MASKED>
-__device__ __forceinline__ void moments_group(const float (&od)[3][kPix], double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
-    float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ void moments_group(const float (&l)[3][kPix], float (&s)[10], float (&lo)[3], float (&hi)[3]) {
 #pragma unroll
     for (int k = 0; k < kPix; ++k) {
-        const float r = od[0][k], gg = od[1][k], b = od[2][k];
+        const float r = l[0][k], gg = l[1][k], b = l[2][k];
+        bool keep = true;
         if (MASKED) {
             lo[0] = fminf(lo[0], r); lo[1] = fminf(lo[1], gg); lo[2] = fminf(lo[2], b);
             hi[0] = fmaxf(hi[0], r); hi[1] = fmaxf(hi[1], gg); hi[2] = fmaxf(hi[2], b);
+            keep = fmaxf(r, fmaxf(gg, b)) <= kLThr;  // L404-405
         }
-        const bool keep = !MASKED || fminf(r, fminf(gg, b)) >= kBeta;  // L404-405
-        const float m = keep ? 1.0f : 0.0f;
-        const float x = (r - kShift) * m, y = (gg - kShift) * m, z = (b - kShift) * m;
-        s[0] += m;
+        const float x = keep ? r - kLShift : 0.0f, y = keep ? gg - kLShift : 0.0f, z = keep ? b - kLShift : 0.0f;
+        s[0] += keep ? 1.0f : 0.0f;
         s[1] += x; s[2] += y; s[3] += z;
         s[4] = __fmaf_rn(x, x, s[4]); s[5] = __fmaf_rn(x, y, s[5]); s[6] = __fmaf_rn(x, z, s[6]);
         s[7] = __fmaf_rn(y, y, s[7]); s[8] = __fmaf_rn(y, z, s[8]); s[9] = __fmaf_rn(z, z, s[9]);
     }
-#pragma unroll
-    for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
 }
 
-// CTA-wide sum of acc[10] into shared red[0][*] (valid for threads < 10 after the call).
+// CTA-wide sum of acc[10]; afterwards thread i < 10 holds total i in acc[0].
 __device__ __forceinline__ void block_sum10(double (&acc)[10], double (*red)[10]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -224,13 +249,35 @@ __device__ __forceinline__ void block_sum10(double (&acc)[10], double (*red)[10]
     if (threadIdx.x < 10) {
         double r = 0.0;
         for (int k = 0; k < kThreads / 32; ++k) r += red[k][threadIdx.x];
-        acc[0] = r;  // thread i < 10 now holds total i in acc[0]
+        acc[0] = r;
     }
+}
+
+// Streams the groups [first, first + stride, ...) of one image through moments_group; float32
+// partial sums are folded into the double accumulators every kFlush groups (<= 64 pixels).
+template <typename T, bool VEC, bool MASKED>
+__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    constexpr int kFlush = kPix >= 16 ? 2 : 8;
+    const int64_t groups = hw / kPix;
+    float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int pending = 0;
+    for (int64_t gi = first; gi < groups; gi += stride) {
+        float l[3][kPix];
+        load_l<T, VEC>(image + gi * kPix, hw, tab, l);
+        moments_group<kPix, MASKED>(l, s, lo, hi);
+        if (++pending == kFlush) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { acc[i] += (double)s[i]; s[i] = 0.0f; }
+            pending = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
 }
 
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
-    constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
     __shared__ double red[kThreads / 32][10];
     __shared__ float redf[kThreads / 32][6];
@@ -239,18 +286,12 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
     if constexpr (sizeof(T) == 1) {
-        build_u8_table<true>(tab);
+        build_l_table(tab);
         __syncthreads();
     }
-    const T *image = img + n * 3 * g.hw;
-    const int64_t groups = g.hw / kPix;
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
-        float od[3][kPix];
-        load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
-        moments_group<kPix, true>(od, acc, lo, hi);
-    }
+    moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads + threadIdx.x, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -264,7 +305,7 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
         const int i = threadIdx.x - 32;
         float r = -INFINITY;
         for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i]);
-        atomic_max_f32(&ws.odrange[slot * 8 + i], r);
+        atomic_max_f32(&ws.odrange[slot * 8 + i], r);  // [0..2] = -min l_c, [3..5] = max l_c
     } else if (threadIdx.x == 64 && chunk == 0) {
         atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);
     }
@@ -310,7 +351,18 @@ __device__ void eigh3(const double C[3][3], double V[3][3], double w[3]) {
     for (int i = 0; i < 3; ++i) { w[i] = ws_[i]; for (int j = 0; j < 3; ++j) V[i][j] = Vs[i][j]; }
 }
 
-// E = eigvecs[:, (1, 2)] of the unbiased covariance held (as shifted raw moments) in m[0..9].
+// Row j of a (2 x 3) linear map of OD, rewritten as an affine map of l:
+//   sum_c a[c] OD_c = ln2 log2(240) sum_c a[c] - sum_c (ln2 a[c]) l_c
+__device__ __forceinline__ void od_map_to_l(const float a[3], float *aff) {
+    const double ln2 = 0.693147180559945309, l240 = 7.906890595608519;
+    aff[0] = (float)(-ln2 * a[0]);
+    aff[1] = (float)(-ln2 * a[1]);
+    aff[2] = (float)(-ln2 * a[2]);
+    aff[3] = (float)(ln2 * l240 * ((double)a[0] + (double)a[1] + (double)a[2]));
+}
+
+// E = eigvecs[:, (1, 2)] of the unbiased covariance held (as shifted raw moments of l) in m[0..9];
+// cov(OD) = ln2^2 cov(l) has the same eigenvectors.  Also the projection maps of the ANGLE stage.
 __device__ void basis_from_moments(const double *m, SlotState &st) {
     const double n = m[0];
     st.n_sel = (long long)(n + 0.5);
@@ -323,7 +375,13 @@ __device__ void basis_from_moments(const double *m, SlotState &st) {
     }
     double V[3][3], w[3];
     eigh3(C, V, w);
-    for (int i = 0; i < 3; ++i) { st.e[i * 2] = (float)V[i][1]; st.e[i * 2 + 1] = (float)V[i][2]; }  // L415
+    float e0[3], e1[3];
+    for (int i = 0; i < 3; ++i) {
+        st.e[i * 2] = e0[i] = (float)V[i][1];      // L415: middle eigenvector
+        st.e[i * 2 + 1] = e1[i] = (float)V[i][2];  //       largest
+    }
+    od_map_to_l(e0, st.proj);
+    od_map_to_l(e1, st.proj + 4);
 }
 
 // One thread per slot.
@@ -348,28 +406,21 @@ __global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_
 // the mask and computes its basis (rare path, so it is not spread over several CTAs).
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict__ img, int64_t hw, int64_t slot0, void *ws_base, int64_t slots) {
-    constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
     __shared__ double red[kThreads / 32][10];
+    __shared__ double tot[10];
     Ws ws(ws_base, slots);
     const int64_t n = blockIdx.x;
     const int64_t slot = slot0 + n;
     if (!ws.state[slot].use_all) return;
     if constexpr (sizeof(T) == 1) {
-        build_u8_table<true>(tab);
+        build_l_table(tab);
         __syncthreads();
     }
-    const T *image = img + n * 3 * hw;
-    const int64_t groups = hw / kPix;
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float lo[3], hi[3];
-    for (int64_t gi = threadIdx.x; gi < groups; gi += kThreads) {
-        float od[3][kPix];
-        load_pixels<T, VEC, true>(image + gi * kPix, hw, tab, od);
-        moments_group<kPix, false>(od, acc, lo, hi);
-    }
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    moments_stream<T, VEC, false>(img + n * 3 * hw, hw, threadIdx.x, kThreads, tab, acc, lo, hi);
     block_sum10(acc, red);
-    __shared__ double tot[10];
     if (threadIdx.x < 10) tot[threadIdx.x] = acc[0];
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -384,24 +435,6 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
     return x;
 }
 
-// Keys of one pixel.  ANGLE: one key (both queries), valid only for kept rows.  CONC: two keys.
-template <int STAGE>
-__device__ __forceinline__ bool pixel_keys(const SlotState &st, float r, float gg, float b, float (&key)[2], float (&val)[2]) {
-    if constexpr (STAGE == SX_STAGE_ANGLE) {
-        if (!(st.use_all || fminf(r, fminf(gg, b)) >= kBeta)) return false;
-        const float t0 = dot3(r, gg, b, st.e[0], st.e[2], st.e[4]);  // That[:,0] (L417)
-        const float t1 = dot3(r, gg, b, st.e[1], st.e[3], st.e[5]);  // That[:,1]
-        val[0] = val[1] = diamond_angle(t1, t0);                     // monotone in atan2(t1, t0) (L418)
-        key[0] = key[1] = angle_key(val[0]);
-    } else {
-        val[0] = dot3(r, gg, b, st.pinv[0], st.pinv[1], st.pinv[2]);  // L444
-        val[1] = dot3(r, gg, b, st.pinv[3], st.pinv[4], st.pinv[5]);
-        key[0] = conc_key(val[0], st.c_lo[0], st.c_scale[0]);
-        key[1] = conc_key(val[1], st.c_lo[1], st.c_scale[1]);
-    }
-    return true;
-}
-
 // LEVEL 0 -- sample pass: every image contributes ~kSampleGroups pixel groups, one per stride-sized
 // window at a hashed offset (so that periodic image structure cannot alias with the sampling).
 template <typename T, bool VEC, int STAGE>
@@ -410,15 +443,20 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ 
     constexpr int kQ = (STAGE == SX_STAGE_CONC) ? 2 : 1;
     __shared__ float tab[256];
     __shared__ unsigned sh[kQ * kBins];
-    __shared__ unsigned s_cnt[kQ];
+    __shared__ unsigned s_cnt;
     Ws ws(ws_base, slots);
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
-    const SlotState st = ws.state[slot];
-    if constexpr (sizeof(T) == 1) build_u8_table<true>(tab);
+    const SlotState &gst = ws.state[slot];
+    const RankParams st(gst);
+    const float c_lo0 = gst.c_lo[0], c_lo1 = gst.c_lo[1], c_sc0 = gst.c_scale[0], c_sc1 = gst.c_scale[1];
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
     for (int i = threadIdx.x; i < kQ * kBins; i += kThreads) sh[i] = 0u;
-    if (threadIdx.x < kQ) s_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        s_cnt = 0u;
+        if (chunk == 0) ws.state[slot].group_px = kPix;
+    }
     __syncthreads();
 
     const T *image = img + n * 3 * g.hw;
@@ -429,80 +467,94 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ 
     for (int64_t i = (int64_t)chunk * kThreads + threadIdx.x; i < nsamp; i += (int64_t)g.cpi * kThreads) {
         const unsigned off = stride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + (unsigned)n * 0x85ebca6bu), (unsigned)stride) : 0u;
         const int64_t gi = i * stride + off;
-        float od[3][kPix];
-        load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
+        float l[3][kPix];
+        load_l<T, VEC>(image + gi * kPix, g.hw, tab, l);
 #pragma unroll
         for (int k = 0; k < kPix; ++k) {
-            float key[2], val[2];
-            if (!pixel_keys<STAGE>(st, od[0][k], od[1][k], od[2][k], key, val)) continue;
-            atomicAdd(&sh[__float2int_rz(key[0]) >> 12], 1u);
-            if (kQ == 2) atomicAdd(&sh[kBins + (__float2int_rz(key[1]) >> 12)], 1u);
+            float v0, v1;
+            ranked_values<STAGE>(st, l[0][k], l[1][k], l[2][k], v0, v1);
+            if (v0 != v0) continue;  // masked row
+            if (STAGE == SX_STAGE_ANGLE) {
+                atomicAdd(&sh[__float2int_rz(angle_key(v0)) >> 12], 1u);
+            } else {
+                atomicAdd(&sh[__float2int_rz(conc_key(v0, c_lo0, c_sc0)) >> 12], 1u);
+                atomicAdd(&sh[kBins + (__float2int_rz(conc_key(v1, c_lo1, c_sc1)) >> 12)], 1u);
+            }
             ++cnt;
         }
     }
     cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt[0], cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
     __syncthreads();
     unsigned *h1 = ws.hist1 + slot * 2 * kBins;
     for (int i = threadIdx.x; i < kQ * kBins; i += kThreads)
         if (sh[i]) atomicAdd(&h1[i], sh[i]);
-    if (threadIdx.x == 0 && s_cnt[0]) {
-        atomicAdd(&ws.counters[slot * 8 + 2], (unsigned long long)s_cnt[0]);
-        if (kQ == 2) atomicAdd(&ws.counters[slot * 8 + 3], (unsigned long long)s_cnt[0]);
+    if (threadIdx.x == 0 && s_cnt) {
+        atomicAdd(&ws.counters[slot * 8 + 2], (unsigned long long)s_cnt);
+        if (kQ == 2) atomicAdd(&ws.counters[slot * 8 + 3], (unsigned long long)s_cnt);
     }
 }
 
-// LEVEL 1 -- full pass: count keys below each bracket, resolve the bracket into kBins cells.
+// Rare path of the full pass: value v of query q lies in the bracket (or in an open end).
+__device__ __noinline__ void record_cell(const SlotState &st, int q, float v, unsigned *h2, float *vmin, float *vmax) {
+    int cell;
+    if (v < st.lo_v[q]) cell = 0;
+    else if (v < st.hi_v[q]) cell = 1 + min(__float2int_rz(__fmul_rn(__fsub_rn(v, st.lo_v[q]), st.inv_w[q])), kBins - 3);
+    else cell = kBins - 1;
+    const int sub = q * kBins + cell;
+    atomicAdd(&h2[sub], 1u);
+    atomic_min_f32(&vmin[sub], v);
+    atomic_max_f32(&vmax[sub], v);
+}
+
+// LEVEL 1 -- full pass: count the values below each bracket, resolve the bracket into kBins cells.
+// The bracket holds ~1-2 % of the rows, so the common path per query is two compares and a
+// predicated increment.
 template <typename T, bool VEC, int STAGE>
 __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
     __shared__ unsigned s_below[2];
+    __shared__ SlotState st;
     Ws ws(ws_base, slots);
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
-    const SlotState st = ws.state[slot];
-    if constexpr (sizeof(T) == 1) build_u8_table<true>(tab);
+    if (threadIdx.x == 0) st = ws.state[slot];
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
     if (threadIdx.x < 2) s_below[threadIdx.x] = 0u;
     __syncthreads();
     unsigned *h2 = ws.hist2 + slot * 2 * kBins;
     float *vmin = ws.vmin + slot * 2 * kBins;
     float *vmax = ws.vmax + slot * 2 * kBins;
+    // per-query bounds in registers; an open end is encoded by moving the bound to -/+ infinity
+    // for the "below" / "outside" tests and handled inside record_cell
+    const float lo0 = st.lo_v[0], hi0 = st.hi_v[0], lo1 = st.lo_v[1], hi1 = st.hi_v[1];
+    const float cl0 = st.open_lo[0] ? -INFINITY : lo0, ch0 = st.open_hi[0] ? INFINITY : hi0;
+    const float cl1 = st.open_lo[1] ? -INFINITY : lo1, ch1 = st.open_hi[1] ? INFINITY : hi1;
+    const RankParams rp(st);
 
     const T *image = img + n * 3 * g.hw;
     const int64_t groups = g.hw / kPix;
-    unsigned below[2] = {0u, 0u};
+    unsigned below0 = 0u, below1 = 0u;
     for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
-        float od[3][kPix];
-        load_pixels<T, VEC, true>(image + gi * kPix, g.hw, tab, od);
+        float l[3][kPix];
+        load_l<T, VEC>(image + gi * kPix, g.hw, tab, l);
 #pragma unroll
         for (int k = 0; k < kPix; ++k) {
-            float key[2], val[2];
-            if (!pixel_keys<STAGE>(st, od[0][k], od[1][k], od[2][k], key, val)) continue;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int cell;
-                if (key[q] < st.lo_f[q]) {
-                    if (!st.open_lo[q]) { ++below[q]; continue; }
-                    cell = 0;
-                } else if (key[q] < st.hi_f[q]) {
-                    cell = 1 + min(__float2int_rz(__fmul_rn(__fsub_rn(key[q], st.lo_f[q]), st.inv_w[q])), kBins - 3);
-                } else {
-                    if (!st.open_hi[q]) continue;
-                    cell = kBins - 1;
-                }
-                const int sub = q * kBins + cell;
-                atomicAdd(&h2[sub], 1u);
-                atomic_min_f32(&vmin[sub], val[q]);
-                atomic_max_f32(&vmax[sub], val[q]);
-            }
+            float v0, v1;
+            ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
+            below0 += v0 < cl0 ? 1u : 0u;   // NaN (masked row): every comparison is false
+            below1 += v1 < cl1 ? 1u : 0u;
+            if (v0 >= cl0 && v0 < ch0) record_cell(st, 0, v0, h2, vmin, vmax);
+            if (v1 >= cl1 && v1 < ch1) record_cell(st, 1, v1, h2, vmin, vmax);
         }
     }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const unsigned r = (unsigned)__reduce_add_sync(0xffffffffu, below[q]);
-        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_below[q], r);
+    below0 = (unsigned)__reduce_add_sync(0xffffffffu, below0);
+    below1 = (unsigned)__reduce_add_sync(0xffffffffu, below1);
+    if ((threadIdx.x & 31) == 0) {
+        if (below0) atomicAdd(&s_below[0], below0);
+        if (below1) atomicAdd(&s_below[1], below1);
     }
     __syncthreads();
     if (threadIdx.x < 2 && s_below[threadIdx.x]) atomicAdd(&ws.counters[slot * 8 + threadIdx.x], (unsigned long long)s_below[threadIdx.x]);
@@ -522,8 +574,7 @@ __device__ void block_prefix(const unsigned *__restrict__ hist, unsigned long lo
     for (int i = 0; i < kPer; ++i) { v[i] = hist[threadIdx.x * kPer + i]; s += v[i]; }
     part[threadIdx.x] = s;
     __syncthreads();
-    // Hillis-Steele scan over the 256 partial sums
-    for (int o = 1; o < kThreads; o <<= 1) {
+    for (int o = 1; o < kThreads; o <<= 1) {  // Hillis-Steele scan over the 256 partial sums
         const unsigned long long add = threadIdx.x >= o ? part[threadIdx.x - o] : 0ull;
         __syncthreads();
         part[threadIdx.x] += add;
@@ -535,7 +586,7 @@ __device__ void block_prefix(const unsigned *__restrict__ hist, unsigned long lo
     __syncthreads();
 }
 
-// Index of the bin holding 0-based rank k: first b with pre[b] > k (binary search; any thread).
+// Index of the bin holding 0-based rank k: first b with pre[b] > k.
 __device__ __forceinline__ int bin_of_rank(const unsigned long long *pre, long long k) {
     int lo = 0, hi = kBins - 1;
     while (lo < hi) {
@@ -556,7 +607,8 @@ __device__ __forceinline__ void diamond_to_unit(float p, double &c, double &s) {
     c = x / h; s = y / h;
 }
 
-// After the sample pass: wanted ranks and their brackets.
+// After the sample pass: wanted ranks and their brackets, converted from sample-key bins to the
+// value space of the full pass.
 __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
     __shared__ unsigned long long pre[kBins];
     Ws ws(ws_base, slots);
@@ -573,9 +625,10 @@ __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_
             if (k < 0) k = 0;
             st.rank[q] = k;
             const long long m = (long long)ws.counters[slot * 8 + 2 + hq];
-            // Inner cells 1 .. kBins-2 tile [lo_f, hi_f).  When the rank bracket reaches an end of
-            // the sample, the true order statistic may lie beyond the sample's extreme value: that
-            // side is left open and its keys are collected in a catch-all cell (0 or kBins-1).
+            const int group_pixels = st.group_px > 0 ? st.group_px : 16;
+            // Inner cells 1 .. kBins-2 tile [lo, hi).  When the rank bracket reaches an end of the
+            // sample, the true order statistic may lie beyond the sample's extreme value: that
+            // side is left open and its values are collected in a catch-all cell (0 or kBins-1).
             int b_lo = 0, b_hi = kBins - 1, open_lo = 1, open_hi = 1;
             if (m > 0 && n > 0) {
                 long long r_lo, r_hi;
@@ -583,19 +636,30 @@ __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_
                     r_lo = r_hi = k;
                     open_lo = open_hi = 0;
                 } else {
+                    // The pixels of one sampled group are neighbours and may be fully correlated:
+                    // the binomial deviation is taken over groups, not pixels.
                     const double ks = (double)k * (double)m / (double)n;
-                    const double sd = sqrt((double)m * (0.01 * pct) * (1.0 - 0.01 * pct));
-                    r_lo = (long long)floor(ks - kBracketZ * sd) - 2;
-                    r_hi = (long long)ceil(ks + kBracketZ * sd) + 2;
+                    const double sd = sqrt((double)group_pixels * (double)m * (0.01 * pct) * (1.0 - 0.01 * pct));
+                    r_lo = (long long)floor(ks - kBracketZ * sd) - 2 * group_pixels;
+                    r_hi = (long long)ceil(ks + kBracketZ * sd) + 2 * group_pixels;
                     open_lo = r_lo <= 0;
                     open_hi = r_hi >= m - 1;
                 }
                 b_lo = bin_of_rank(pre, r_lo < 0 ? 0 : (r_lo < m - 1 ? r_lo : m - 1));
                 b_hi = bin_of_rank(pre, r_hi < 0 ? 0 : (r_hi < m - 1 ? r_hi : m - 1));
             }
-            st.lo_f[q] = (float)(b_lo * 4096);
-            st.hi_f[q] = (float)((b_hi + 1) * 4096);
-            st.inv_w[q] = (float)((double)(kBins - 2) / ((double)(b_hi - b_lo + 1) * 4096.0));
+            // sample keys -> values: ANGLE key = (p + 2) 2^22, CONC key = (C - c_lo) c_scale
+            double lo_v, hi_v;
+            if (stage == SX_STAGE_ANGLE) {
+                lo_v = (double)b_lo * 4096.0 / 4194304.0 - 2.0;
+                hi_v = (double)(b_hi + 1) * 4096.0 / 4194304.0 - 2.0;
+            } else {
+                lo_v = (double)st.c_lo[q] + (double)b_lo * 4096.0 / (double)st.c_scale[q];
+                hi_v = (double)st.c_lo[q] + (double)(b_hi + 1) * 4096.0 / (double)st.c_scale[q];
+            }
+            st.lo_v[q] = (float)lo_v;
+            st.hi_v[q] = (float)hi_v;
+            st.inv_w[q] = (float)((double)(kBins - 2) / ((double)st.hi_v[q] - (double)st.lo_v[q]));
             st.open_lo[q] = open_lo;
             st.open_hi[q] = open_hi;
         }
@@ -603,7 +667,7 @@ __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_
     }
 }
 
-// After the full pass: the order statistics; (ANGLE) HE, pinv, concentration key range; (CONC) maxC.
+// After the full pass: the order statistics; (ANGLE) HE, pinv, concentration maps; (CONC) maxC.
 __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
     __shared__ unsigned long long pre[kBins];
     Ws ws(ws_base, slots);
@@ -615,7 +679,7 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
         if (threadIdx.x == 0) {
             const long long inside = (long long)pre[kBins - 1];
             long long k = st.rank[q] - (long long)ws.counters[slot * 8 + q];
-            if (k < 0 || k >= inside) {  // the rank fell outside the bracket (should not happen)
+            if (k < 0 || k >= inside) {  // the rank fell outside the bracket (not expected): nearest edge
                 atomicOr(&ws.status[slot * 4], 1 << q);
                 k = k < 0 ? 0 : (inside > 0 ? inside - 1 : 0);
             }
@@ -653,12 +717,15 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
                 st.pinv[i] = (float)((a11 * he[i * 2] - a01 * he[i * 2 + 1]) / det);
                 st.pinv[3 + i] = (float)((-a01 * he[i * 2] + a00 * he[i * 2 + 1]) / det);
             }
-            // Key range of each concentration row from the per-channel OD range (interval arithmetic).
+            // concentration rows as affine maps of l for the CONC stage
+            od_map_to_l(st.pinv, st.proj);
+            od_map_to_l(st.pinv + 3, st.proj + 4);
+            // Key range of each concentration row from the per-channel range of l (interval arithmetic).
             const float *rg = ws.odrange + slot * 8;
             for (int j = 0; j < 2; ++j) {
-                double lo = 0, hi = 0;
+                double lo = st.proj[j * 4 + 3], hi = lo;
                 for (int c = 0; c < 3; ++c) {
-                    const double pj = st.pinv[j * 3 + c], a = pj * (double)(-rg[c]), b = pj * (double)rg[3 + c];
+                    const double w = st.proj[j * 4 + c], a = w * (double)(-rg[c]), b = w * (double)rg[3 + c];
                     lo += fmin(a, b); hi += fmax(a, b);
                 }
                 const double pad = 1e-6 * (fabs(lo) + fabs(hi)) + 1e-12;
@@ -696,7 +763,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = slot0 + n;
-    if constexpr (sizeof(T) == 1) build_u8_table<false>(tab);
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
     if constexpr (OUT == 2 && sizeof(T) == 1)
         for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
     if (threadIdx.x < 3) {
@@ -726,7 +793,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
     const int64_t groups = g.hw / kPix;
     for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
         float l[3][kPix];
-        load_pixels<T, VEC, false>(image + gi * kPix, g.hw, tab, l);
+        load_l<T, VEC>(image + gi * kPix, g.hw, tab, l);
         float o[3][kPix];
 #pragma unroll
         for (int k = 0; k < kPix; ++k)
