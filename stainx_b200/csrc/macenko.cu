@@ -25,6 +25,8 @@
 // distinct value (the normal case: a bracket is ~1 % of the data), else it is interpolated inside
 // a cell of width <= bracket/4096.  The nearest-rank index is exact: ranks below the bracket are
 // counted, not estimated.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sx {
@@ -34,7 +36,7 @@ constexpr int kThreads = 256;
 constexpr int kBins = 4096;      // coarse bins of the sample pass == cells of the full pass
 constexpr float kKeyMax = 16777215.0f;
 constexpr int kSampleGroups = 4096;  // pixel groups sampled per image (float32: 16 K px, uint8: 64 K px)
-constexpr double kBracketZ = 8.0;    // half-width of the rank bracket in sample standard deviations
+constexpr double kBracketZ = 6.5;    // half-width of the rank bracket in sample standard deviations
 
 constexpr float kLog2_240 = 7.906890595608519f;
 
@@ -128,39 +130,77 @@ __device__ __forceinline__ void build_l_table(float *tab) {
 }
 __device__ __forceinline__ float f32_l(float x) { return __log2f(__fmaf_rn(x, 255.0f, 1.0f)); }
 
-// Loads kPix pixels; l[c][k] = log2(255 x + 1) of channel c of pixel k.
+// Raw 128-bit (or scalar) loads of one pixel group, kept in registers so that the loads of the next
+// group can be in flight while the current one is processed.
 template <typename T, bool VEC>
-__device__ __forceinline__ void load_l(const T *__restrict__ base, int64_t hw, const float *tab, float (&l)[3][Pix<T, VEC>::kPix]) {
-    constexpr int kPix = Pix<T, VEC>::kPix;
-    if constexpr (sizeof(T) == 4) {
+struct RawGroup {
+    using Vec = typename std::conditional<VEC, typename std::conditional<sizeof(T) == 4, float4, uint4>::type, T>::type;
+    Vec v[3];
+    __device__ __forceinline__ void load(const T *__restrict__ base, int64_t hw) {
         if constexpr (VEC) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float4 q = ld_stream(reinterpret_cast<const float4 *>(base + c * hw));
-                l[c][0] = q.x; l[c][1] = q.y; l[c][2] = q.z; l[c][3] = q.w;
-            }
+            for (int c = 0; c < 3; ++c) v[c] = ld_stream(reinterpret_cast<const Vec *>(base + c * hw));
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) l[c][0] = base[c * hw];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < kPix; ++k) l[c][k] = f32_l(l[c][k]);
-    } else {
-        if constexpr (VEC) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const uint4 q = ld_stream(reinterpret_cast<const uint4 *>(base + c * hw));
-                const unsigned w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int k = 0; k < kPix; ++k) l[c][k] = tab[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) l[c][0] = tab[base[c * hw]];
+            for (int c = 0; c < 3; ++c) v[c] = base[c * hw];
         }
     }
+    // l[c][k] = log2(255 x + 1) of channel c of pixel k.
+    __device__ __forceinline__ void to_l(const float *tab, float (&l)[3][Pix<T, VEC>::kPix]) const {
+        constexpr int kPix = Pix<T, VEC>::kPix;
+        if constexpr (sizeof(T) == 4) {
+            if constexpr (VEC) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { l[c][0] = f32_l(v[c].x); l[c][1] = f32_l(v[c].y); l[c][2] = f32_l(v[c].z); l[c][3] = f32_l(v[c].w); }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) l[c][0] = f32_l(v[c]);
+            }
+        } else {
+            if constexpr (VEC) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                    for (int k = 0; k < kPix; ++k) l[c][k] = tab[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) l[c][0] = tab[v[c]];
+            }
+        }
+    }
+};
+
+// Streams the pixel groups first, first + stride, ... (< groups) of one image through `body(l, gi)`
+// with one group of loads always in flight ahead of the arithmetic.  The trip count is uniform
+// over the CTA (bodies may use __syncthreads through `every`), inactive threads skip the body.
+template <typename T, bool VEC, typename Body, typename Every>
+__device__ __forceinline__ void stream_groups(const T *__restrict__ image, int64_t hw, int64_t groups, int64_t cta_first, int64_t cta_stride, const float *tab, Body body, Every every) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    RawGroup<T, VEC> cur, nxt;
+    int64_t gi = cta_first + threadIdx.x;
+    if (gi < groups) cur.load(image + gi * kPix, hw);
+    for (int64_t base = cta_first; base < groups; base += cta_stride) {
+        const int64_t gn = gi + cta_stride;
+        if (gn < groups) nxt.load(image + gn * kPix, hw);
+        if (gi < groups) {
+            float l[3][kPix];
+            cur.to_l(tab, l);
+            body(l, gi);
+        }
+        every();
+        cur = nxt;
+        gi = gn;
+    }
+}
+
+// Loads kPix pixels; l[c][k] = log2(255 x + 1) of channel c of pixel k (no prefetch; sample pass).
+template <typename T, bool VEC>
+__device__ __forceinline__ void load_l(const T *__restrict__ base, int64_t hw, const float *tab, float (&l)[3][Pix<T, VEC>::kPix]) {
+    RawGroup<T, VEC> r;
+    r.load(base, hw);
+    r.to_l(tab, l);
 }
 
 // CTA -> (image, chunk) mapping shared by all pixel passes.
@@ -253,25 +293,25 @@ __device__ __forceinline__ void block_sum10(double (&acc)[10], double (*red)[10]
     }
 }
 
-// Streams the groups [first, first + stride, ...) of one image through moments_group; float32
-// partial sums are folded into the double accumulators every kFlush groups (<= 64 pixels).
+// Streams groups of one image through moments_group; float32 partial sums are folded into the
+// double accumulators every kFlush groups (<= 64 pixels).
 template <typename T, bool VEC, bool MASKED>
-__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
+__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t cta_first, int64_t cta_stride, const float *tab, double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     constexpr int kFlush = kPix >= 16 ? 2 : 8;
-    const int64_t groups = hw / kPix;
     float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int pending = 0;
-    for (int64_t gi = first; gi < groups; gi += stride) {
-        float l[3][kPix];
-        load_l<T, VEC>(image + gi * kPix, hw, tab, l);
-        moments_group<kPix, MASKED>(l, s, lo, hi);
-        if (++pending == kFlush) {
+    stream_groups<T, VEC>(
+        image, hw, hw / kPix, cta_first, cta_stride, tab,
+        [&](const float(&l)[3][kPix], int64_t) {
+            moments_group<kPix, MASKED>(l, s, lo, hi);
+            if (++pending == kFlush) {
 #pragma unroll
-            for (int i = 0; i < 10; ++i) { acc[i] += (double)s[i]; s[i] = 0.0f; }
-            pending = 0;
-        }
-    }
+                for (int i = 0; i < 10; ++i) { acc[i] += (double)s[i]; s[i] = 0.0f; }
+                pending = 0;
+            }
+        },
+        [] {});
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
 }
@@ -291,7 +331,7 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     }
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads + threadIdx.x, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
+    moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -419,7 +459,7 @@ __global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict_
     }
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-    moments_stream<T, VEC, false>(img + n * 3 * hw, hw, threadIdx.x, kThreads, tab, acc, lo, hi);
+    moments_stream<T, VEC, false>(img + n * 3 * hw, hw, 0, kThreads, tab, acc, lo, hi);
     block_sum10(acc, red);
     if (threadIdx.x < 10) tot[threadIdx.x] = acc[0];
     __syncthreads();
@@ -437,6 +477,8 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
 
 // LEVEL 0 -- sample pass: every image contributes ~kSampleGroups pixel groups, one per stride-sized
 // window at a hashed offset (so that periodic image structure cannot alias with the sampling).
+// The offsets depend only on the window index: an image's result does not depend on where in
+// the batch it sits.
 template <typename T, bool VEC, int STAGE>
 __global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
@@ -465,7 +507,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ 
     const int64_t nsamp = groups / stride;
     unsigned cnt = 0;
     for (int64_t i = (int64_t)chunk * kThreads + threadIdx.x; i < nsamp; i += (int64_t)g.cpi * kThreads) {
-        const unsigned off = stride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + (unsigned)n * 0x85ebca6bu), (unsigned)stride) : 0u;
+        const unsigned off = stride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + 0x85ebca6bu), (unsigned)stride) : 0u;
         const int64_t gi = i * stride + off;
         float l[3][kPix];
         load_l<T, VEC>(image + gi * kPix, g.hw, tab, l);
@@ -508,13 +550,20 @@ __device__ __noinline__ void record_cell(const SlotState &st, int q, float v, un
 }
 
 // LEVEL 1 -- full pass: count the values below each bracket, resolve the bracket into kBins cells.
-// The bracket holds ~1-2 % of the rows, so the common path per query is two compares and a
-// predicated increment.
+// A bracket holds 1-3 % of the rows: rare per pixel, but not per warp (1 - 0.97^32 = 62 %), so a
+// hit is only appended to a shared-memory queue (one shared atomic + one store); the CTA drains
+// the queue with all lanes busy every kDrainEvery iterations.  The common path per query is two
+// compares and a predicated increment.
+constexpr int kQueueCap = 1536;
+constexpr int kDrainEvery = 2;
+
 template <typename T, bool VEC, int STAGE>
 __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
     __shared__ unsigned s_below[2];
+    __shared__ unsigned s_qn[2];
+    __shared__ float s_q[2][kQueueCap];
     __shared__ SlotState st;
     Ws ws(ws_base, slots);
     const int64_t n = blockIdx.x / g.cpi;
@@ -522,34 +571,53 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__
     const int64_t slot = pooled ? 0 : slot0 + n;
     if (threadIdx.x == 0) st = ws.state[slot];
     if constexpr (sizeof(T) == 1) build_l_table(tab);
-    if (threadIdx.x < 2) s_below[threadIdx.x] = 0u;
+    if (threadIdx.x < 2) { s_below[threadIdx.x] = 0u; s_qn[threadIdx.x] = 0u; }
     __syncthreads();
     unsigned *h2 = ws.hist2 + slot * 2 * kBins;
     float *vmin = ws.vmin + slot * 2 * kBins;
     float *vmax = ws.vmax + slot * 2 * kBins;
-    // per-query bounds in registers; an open end is encoded by moving the bound to -/+ infinity
-    // for the "below" / "outside" tests and handled inside record_cell
-    const float lo0 = st.lo_v[0], hi0 = st.hi_v[0], lo1 = st.lo_v[1], hi1 = st.hi_v[1];
-    const float cl0 = st.open_lo[0] ? -INFINITY : lo0, ch0 = st.open_hi[0] ? INFINITY : hi0;
-    const float cl1 = st.open_lo[1] ? -INFINITY : lo1, ch1 = st.open_hi[1] ? INFINITY : hi1;
+    // an open end is encoded by moving the bound to -/+ infinity for the below / inside tests;
+    // record_cell sorts such values into the catch-all cells
+    const float cl0 = st.open_lo[0] ? -INFINITY : st.lo_v[0], ch0 = st.open_hi[0] ? INFINITY : st.hi_v[0];
+    const float cl1 = st.open_lo[1] ? -INFINITY : st.lo_v[1], ch1 = st.open_hi[1] ? INFINITY : st.hi_v[1];
     const RankParams rp(st);
 
-    const T *image = img + n * 3 * g.hw;
-    const int64_t groups = g.hw / kPix;
-    unsigned below0 = 0u, below1 = 0u;
-    for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
-        float l[3][kPix];
-        load_l<T, VEC>(image + gi * kPix, g.hw, tab, l);
+    auto drain = [&]() {
+        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kPix; ++k) {
-            float v0, v1;
-            ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
-            below0 += v0 < cl0 ? 1u : 0u;   // NaN (masked row): every comparison is false
-            below1 += v1 < cl1 ? 1u : 0u;
-            if (v0 >= cl0 && v0 < ch0) record_cell(st, 0, v0, h2, vmin, vmax);
-            if (v1 >= cl1 && v1 < ch1) record_cell(st, 1, v1, h2, vmin, vmax);
+        for (int q = 0; q < 2; ++q) {
+            const int cnt = min((int)s_qn[q], kQueueCap);
+            for (int j = threadIdx.x; j < cnt; j += kThreads) record_cell(st, q, s_q[q][j], h2, vmin, vmax);
         }
-    }
+        __syncthreads();
+        if (threadIdx.x < 2) s_qn[threadIdx.x] = 0u;
+        __syncthreads();
+    };
+    auto hit = [&](int q, float v) {
+        const unsigned i = atomicAdd(&s_qn[q], 1u);
+        if (i < (unsigned)kQueueCap) s_q[q][i] = v;
+        else record_cell(st, q, v, h2, vmin, vmax);  // queue full (degenerate data): record directly
+    };
+
+    unsigned below0 = 0u, below1 = 0u;
+    int it = 0;
+    stream_groups<T, VEC>(
+        img + n * 3 * g.hw, g.hw, g.hw / kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab,
+        [&](const float(&l)[3][kPix], int64_t) {
+#pragma unroll
+            for (int k = 0; k < kPix; ++k) {
+                float v0, v1;
+                ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
+                below0 += v0 < cl0 ? 1u : 0u;  // NaN (masked row): every comparison is false
+                below1 += v1 < cl1 ? 1u : 0u;
+                if (v0 >= cl0 && v0 < ch0) hit(0, v0);
+                if (v1 >= cl1 && v1 < ch1) hit(1, v1);
+            }
+        },
+        [&] {
+            if (++it == kDrainEvery) { drain(); it = 0; }
+        });
+    drain();
     below0 = (unsigned)__reduce_add_sync(0xffffffffu, below0);
     below1 = (unsigned)__reduce_add_sync(0xffffffffu, below1);
     if ((threadIdx.x & 31) == 0) {
@@ -789,11 +857,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
         for (int k = 0; k < 4; ++k) A[c][k] = coef[c * 4 + k];
     const float top = (OUT == 2 && sizeof(T) == 4) ? 1.0f : 255.0f;  // clamp(.., 0, 255) (L459)
 
-    const T *image = img + n * 3 * g.hw;
-    const int64_t groups = g.hw / kPix;
-    for (int64_t gi = (int64_t)chunk * kThreads + threadIdx.x; gi < groups; gi += (int64_t)g.cpi * kThreads) {
-        float l[3][kPix];
-        load_l<T, VEC>(image + gi * kPix, g.hw, tab, l);
+    stream_groups<T, VEC>(img + n * 3 * g.hw, g.hw, g.hw / kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, [&](const float(&l)[3][kPix], int64_t gi) {
         float o[3][kPix];
 #pragma unroll
         for (int k = 0; k < kPix; ++k)
@@ -836,7 +900,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
                 }
             }
         }
-    }
+    }, [] {});
 }
 
 __global__ void init_kernel(void *ws_base, int64_t slots) {

