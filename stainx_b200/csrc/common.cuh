@@ -92,10 +92,12 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // float atomic max / min on plain float storage (works for mixed signs; NaN is ignored).
 __device__ __forceinline__ void atomic_max_f32(float *addr, float v) {
+    v += 0.0f;  // -0.0 -> +0.0: as an int, -0.0 is INT_MIN and would lose against every negative float
     if (v >= 0.0f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
     else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_min_f32(float *addr, float v) {
+    v += 0.0f;
     if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
     else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }

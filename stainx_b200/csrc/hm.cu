@@ -374,6 +374,217 @@ __global__ void __launch_bounds__(kL32Threads, 1) hist_u8_planar_lane32_kernel(c
     if (cur_c >= 0) fold(cur_c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Histogram, planar uint8, scheme P ("pairs"): the shared-memory atomic unit retires a fixed number
+// of lane-updates per clock whatever the address pattern (measured: ~6.5 per clk per SM), so the
+// way to count faster is to count MORE PER UPDATE.  Two neighbouring bytes (a, b) of a plane are
+// one 16-bit value h = a | b << 8; a single RED.ADD into a 65 536-cell table counts the pair, and
+// the 256-bin histogram is the sum of the table's two marginals:
+//     hist[v] = sum_b cell[v][b] + sum_a cell[a][v].
+// Cells are 16-bit counters packed two per word (128 KB, one CTA of 1024 threads per SM): cell h
+// lives in word h & 0x7fff, half h >> 15.  A cell overflows after 65 535 hits -- only possible when
+// one byte pair makes up a large share of a CTA's segment (flat images).  A carry changes the sum
+// over all cells, so the fold compares that sum with the number of pairs counted; on a mismatch the
+// CTA discards the segment's table and recounts the segment with 32-bit warp-private atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 1024;
+constexpr int kPairWarps = kPairThreads / 32;
+constexpr int kPairUnroll = 2;                                  // 128-bit loads per thread per tile
+constexpr int kPairTileVecs = kPairThreads * kPairUnroll;       // 32 KB of a plane per tile
+constexpr int kPairTableWords = 32768;
+constexpr int kPairSmemBytes = kPairTableWords * 4 + 256 * 4 + 64;
+
+__device__ __forceinline__ void pair_count_word(unsigned w, uint32_t table_addr) {
+    // low halfword: byte offset of its word = (h & 0x7fff) * 4, increment 1 or 1 << 16
+    const unsigned o0 = (w << 2) & 0x1fffcu;
+    const unsigned i0 = ((w >> 15) & 1u) * 0xffffu + 1u;
+    const unsigned o1 = (w >> 14) & 0x1fffcu;
+    const unsigned i1 = (w >> 31) * 0xffffu + 1u;
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(table_addr + o0), "r"(i0) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(table_addr + o1), "r"(i1) : "memory");
+}
+
+__global__ void __launch_bounds__(kPairThreads, 1) hist_u8_planar_pairs_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned int *table = reinterpret_cast<unsigned int *>(smem);              // [32768] packed 16-bit cells
+    unsigned int *hist32 = table + kPairTableWords;                            // [256] segment histogram
+    unsigned int *s_misc = hist32 + 256;                                       // [0] pairs counted, [1] sum of cells
+    const uint32_t table_addr = (uint32_t)__cvta_generic_to_shared(table);
+    const int lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < kPairTableWords; i += kPairThreads) table[i] = 0u;
+    if (threadIdx.x < 256) hist32[threadIdx.x] = 0u;
+    if (threadIdx.x < 2) s_misc[threadIdx.x] = 0u;
+    __syncthreads();
+
+    const int64_t per_channel = n_img * tiles_per_plane;
+    const int64_t items = 3 * per_channel;
+    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const int64_t first = (int64_t)blockIdx.x * per_cta;
+    const int64_t last = first + per_cta < items ? first + per_cta : items;
+
+    struct Item {
+        const uint4 *body;
+        const uint8_t *plane;
+        int64_t v0, nvec, head, tail0;
+        bool first_tile;
+    };
+    auto locate = [&](int64_t item) {
+        const int c = (int)(item / per_channel);
+        const int64_t rem = item - (int64_t)c * per_channel;
+        const int64_t n = rem / tiles_per_plane;
+        const int64_t t = rem - n * tiles_per_plane;
+        Item it;
+        it.plane = img + (n * 3 + c) * hw;
+        const PlaneSplit sp = split_plane(it.plane, hw);
+        it.body = reinterpret_cast<const uint4 *>(it.plane + sp.head);
+        it.v0 = t * kPairTileVecs;
+        it.nvec = sp.nvec;
+        it.head = sp.head;
+        it.tail0 = sp.tail0;
+        it.first_tile = t == 0;
+        return it;
+    };
+    auto issue = [&](int64_t item, uint4(&v)[kPairUnroll], unsigned &okmask) {
+        const Item it = locate(item);
+        okmask = 0;
+#pragma unroll
+        for (int u = 0; u < kPairUnroll; ++u) {
+            const int64_t vi = it.v0 + u * kPairThreads + threadIdx.x;
+            if (vi < it.nvec) {
+                v[u] = ld_stream(it.body + vi);
+                okmask |= 1u << u;
+            }
+        }
+    };
+    // ragged ends of a plane (< 32 bytes): single values, straight into the segment histogram
+    auto stragglers = [&](int64_t item) {
+        const Item it = locate(item);
+        if (!it.first_tile) return;
+        const int64_t ragged = it.head + (hw - it.tail0);
+        if ((int64_t)threadIdx.x < ragged) {
+            const int64_t idx = (int64_t)threadIdx.x < it.head ? (int64_t)threadIdx.x : it.tail0 + ((int64_t)threadIdx.x - it.head);
+            atomicAdd(&hist32[it.plane[idx]], 1u);
+        }
+    };
+
+    unsigned my_pairs = 0;  // pairs this thread has counted since the last fold
+    auto count_pairs = [&](const uint4(&v)[kPairUnroll], unsigned okmask) {
+#pragma unroll
+        for (int u = 0; u < kPairUnroll; ++u) {
+            if (okmask & (1u << u)) {
+                pair_count_word(v[u].x, table_addr);
+                pair_count_word(v[u].y, table_addr);
+                pair_count_word(v[u].z, table_addr);
+                pair_count_word(v[u].w, table_addr);
+                my_pairs += 8;
+            }
+        }
+    };
+
+    // Fold the pair table into hist32 (both marginals), re-zero it, and check the cell sum.
+    // Thread t walks words t, t + 1024, ...: a = t & 255 is fixed per thread, b & 127 = (t >> 8) + 4k
+    // is uniform over a warp.  Returns true when no cell overflowed.
+    auto fold_table = [&]() -> bool {
+        __syncthreads();
+        unsigned acc_a = 0;
+#pragma unroll 4
+        for (int k = 0; k < kPairTableWords / kPairThreads; ++k) {
+            const int i = threadIdx.x + k * kPairThreads;
+            const unsigned w = table[i];
+            table[i] = 0u;
+            const unsigned lo = w & 0xffffu, hi = w >> 16;
+            acc_a += lo + hi;
+            const unsigned slo = __reduce_add_sync(0xffffffffu, lo), shi = __reduce_add_sync(0xffffffffu, hi);
+            if (lane == 0) {
+                const int b7 = i >> 8;
+                if (slo) atomicAdd(&hist32[b7], slo);
+                if (shi) atomicAdd(&hist32[b7 + 128], shi);
+            }
+        }
+        if (acc_a) atomicAdd(&hist32[threadIdx.x & 255], acc_a);
+        const unsigned cells = __reduce_add_sync(0xffffffffu, acc_a), pairs = __reduce_add_sync(0xffffffffu, my_pairs);
+        if (lane == 0) {
+            atomicAdd(&s_misc[0], pairs);
+            atomicAdd(&s_misc[1], cells);
+        }
+        my_pairs = 0;
+        __syncthreads();
+        const bool ok = s_misc[0] == s_misc[1];
+        __syncthreads();
+        if (threadIdx.x < 2) s_misc[threadIdx.x] = 0u;
+        return ok;
+    };
+    // hist32 -> global counts of channel c, re-zero.
+    auto flush_hist = [&](int c) {
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            const unsigned v = hist32[threadIdx.x];
+            if (v) atomicAdd(&counts[c * 256 + threadIdx.x], (unsigned long long)v);
+            hist32[threadIdx.x] = 0u;
+        }
+        __syncthreads();
+    };
+    // Safe recount of items [a, b) (one channel) with warp-private 32-bit histograms held in the
+    // (already re-zeroed) table memory; hist32 keeps only the stragglers until it is rebuilt.
+    auto recount = [&](int64_t a, int64_t b) {
+        unsigned int *wh = table + (threadIdx.x >> 5) * 256;
+        for (int64_t item = a; item < b; ++item) {
+            const Item it = locate(item);
+#pragma unroll
+            for (int u = 0; u < kPairUnroll; ++u) {
+                const int64_t vi = it.v0 + u * kPairThreads + threadIdx.x;
+                if (vi < it.nvec) {
+                    const uint4 v = ld_stream(it.body + vi);
+                    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(&wh[(w[j >> 2] >> (8 * (j & 3))) & 0xffu], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            unsigned s = 0;
+            for (int wgt = 0; wgt < kPairWarps; ++wgt) s += table[wgt * 256 + threadIdx.x];
+            hist32[threadIdx.x] += s;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kPairWarps * 256; i += kPairThreads) table[i] = 0u;
+        __syncthreads();
+    };
+
+    // Walk the CTA's contiguous item range one channel segment at a time.
+    int64_t seg = first;
+    while (seg < last) {
+        const int c = (int)(seg / per_channel);
+        const int64_t chan_end = (int64_t)(c + 1) * per_channel;
+        const int64_t seg_end = chan_end < last ? chan_end : last;
+        uint4 va[kPairUnroll], vb[kPairUnroll];
+        unsigned oka = 0, okb = 0;
+        issue(seg, va, oka);
+        for (int64_t item = seg; item < seg_end; item += 2) {
+            if (item + 1 < seg_end) issue(item + 1, vb, okb);
+            count_pairs(va, oka);
+            stragglers(item);
+            if (item + 1 < seg_end) {
+                if (item + 2 < seg_end) issue(item + 2, va, oka);
+                count_pairs(vb, okb);
+                stragglers(item + 1);
+            }
+        }
+        if (!fold_table()) {  // a 16-bit cell overflowed: drop the pair counts, keep the stragglers
+            __syncthreads();
+            // hist32 currently holds marginals (garbage) + stragglers; rebuild it from scratch
+            if (threadIdx.x < 256) hist32[threadIdx.x] = 0u;
+            __syncthreads();
+            for (int64_t item = seg; item < seg_end; ++item) stragglers(item);
+            recount(seg, seg_end);
+        }
+        flush_hist(c);
+        seg = seg_end;
+    }
+}
+
 // Histogram, planar float32: quantise, then warp-private shared atomics (12 B/px of traffic per
 // 3 values, so the atomic rate is 4x lower than in the uint8 kernel).
 __global__ void __launch_bounds__(kThreads) hist_f32_planar_kernel(const float *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
@@ -512,9 +723,9 @@ __global__ void ref_hist_kernel(const unsigned long long *__restrict__ counts, f
     ref_hist[c * 256 + b] = __fdiv_rn(cf[b], denom);
 }
 
-// torch.cumsum(float32) on CPU: one double accumulator, rounded to float32 per element.  The adds
-// are inherently serial; the 32 loads + conversions of a chunk are issued together so that only
-// the DADD chain is on the critical path.
+// torch.cumsum(float32) on CPU: one double accumulator, rounded to float32 per element.
+// Serial form (one thread): the 32 loads + conversions of a chunk are issued together so that only
+// the DADD chain is on the critical path (still ~10 us for 256 elements: FP64 adds are slow here).
 __device__ __forceinline__ void serial_cumsum_256(const float *__restrict__ in, double *__restrict__ out) {
     double acc = 0.0;
     for (int chunk = 0; chunk < 8; ++chunk) {
@@ -529,8 +740,37 @@ __device__ __forceinline__ void serial_cumsum_256(const float *__restrict__ in, 
     }
 }
 
+// The same running sums by a 256-thread scan, used whenever double addition is EXACT for the data
+// and therefore independent of the order: every term is a non-negative float32 >= 2^-29 (or 0),
+// i.e. a multiple of 2^-52, and the total stays below 2, so each partial sum is a multiple of
+// 2^-52 below 2 and fits the 53-bit significand.  (Histogram fractions count / npix satisfy this up
+// to 2^29 pixels per batch.)  Anything else takes the serial loop.  out[b] = sum_{i <= b} in[i].
+__device__ __forceinline__ void cumsum_256(const float *__restrict__ in, double *__restrict__ out) {
+    __shared__ double s_warp[8];
+    const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
+    const float v = in[b];
+    const bool exact_term = v == 0.0f || (v >= 1.862645149230957e-09f && v < 2.0f);  // 2^-29
+    double x = (double)v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = __dadd_rn(x, y);
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    double base = 0.0;
+    for (int k = 0; k < warp; ++k) base = __dadd_rn(base, s_warp[k]);
+    x = __dadd_rn(x, base);
+    const bool fine = exact_term && (b != 255 || x < 2.0);
+    if (__syncthreads_and(fine)) {
+        out[b] = x;
+    } else if (b == 0) {
+        serial_cumsum_256(in, out);
+    }
+    __syncthreads();
+}
+
 // Reference CDF of channel c into rq[256] (shared): H2a, torch_backend.py:L221-223.
-// The 256 divisions run in parallel; only the double-precision running sum is serial.
 __device__ __forceinline__ void ref_cdf_to_smem(const float *__restrict__ ref_hist_c, float *h, double *dacc, float *rq) {
     __shared__ float s_denom;
     const int b = threadIdx.x;
@@ -540,8 +780,7 @@ __device__ __forceinline__ void ref_cdf_to_smem(const float *__restrict__ ref_hi
     __syncthreads();
     h[b] = __fdiv_rn(h[b], s_denom);
     __syncthreads();
-    if (b == 0) serial_cumsum_256(h, dacc);
-    __syncthreads();
+    cumsum_256(h, dacc);
     rq[b] = __double2float_rn(dacc[b]);
     __syncthreads();
 }
@@ -566,18 +805,26 @@ __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, 
     const int c = blockIdx.x, b = threadIdx.x;
     if (FROM_HIST) ref_cdf_to_smem(ref + c * 256, sq, dacc, rq);
     else rq[b] = ref[c * 256 + b];
-    if (b == 0) {
-        unsigned long long total = 0;
-        if (npix < 0) for (int i = 0; i < 256; ++i) total += counts[c * 256 + i];
-        else total = (unsigned long long)npix;
-        // L235: python float (num_pixels + 1e-8), cast to float32 for the division
-        s_npix_f = __double2float_rn(__dadd_rn((double)total, 1e-8));
+    const unsigned long long my_count = counts[c * 256 + b];
+    {
+        __shared__ unsigned long long s_part[8];
+        unsigned long long t = my_count;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((b & 31) == 0) s_part[b >> 5] = t;
+        __syncthreads();
+        if (b == 0) {
+            unsigned long long total = 0;
+            for (int k = 0; k < 8; ++k) total += s_part[k];
+            if (npix >= 0) total = (unsigned long long)npix;
+            // L235: python float (num_pixels + 1e-8), cast to float32 for the division
+            s_npix_f = __double2float_rn(__dadd_rn((double)total, 1e-8));
+        }
     }
     __syncthreads();
-    sq[b] = __fdiv_rn(__ull2float_rn(counts[c * 256 + b]), s_npix_f);  // L234-235
+    sq[b] = __fdiv_rn(__ull2float_rn(my_count), s_npix_f);  // L234-235
     __syncthreads();
-    if (b == 0) serial_cumsum_256(sq, dacc);  // L236: cumsum, double accumulator rounded per element
-    __syncthreads();
+    cumsum_256(sq, dacc);  // L236: cumsum, double accumulator rounded per element
     sq[b] = __double2float_rn(dacc[b]);
     __syncthreads();
     const float q = sq[b];
@@ -752,7 +999,7 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
 }
 
 // ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
-static int g_hist_byte_counters = 0;  // counting scheme: 0 warp atomics, 1 byte counters, 2 packed RED, 3 lane32
+static int g_hist_byte_counters = 0;  // counting scheme: 0 warp atomics, 1 byte counters, 2 packed RED, 3 lane32, 4 pairs
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 8;
 
@@ -795,7 +1042,16 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
     if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         const int64_t items = n * tiles;
-        if (g_hist_byte_counters == 3) {
+        if (g_hist_byte_counters == 4) {
+            static bool attr4_set = false;
+            if (!attr4_set) {
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+                attr4_set = true;
+            }
+            const int64_t tiles_p = max_i64(1, (hw / 16 + kPairTileVecs - 1) / kPairTileVecs);
+            const unsigned grid_p = stream_grid(3 * n * tiles_p, 1);
+            hist_u8_planar_pairs_kernel<<<grid_p, kPairThreads, kPairSmemBytes, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles_p, cnt);
+        } else if (g_hist_byte_counters == 3) {
             static bool attr3_set = false;
             if (!attr3_set) {
                 SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL32SmemBytes));

@@ -417,8 +417,10 @@ def test_macenko_full_size_float(cuda, ox):
     big = src.to(cuda).repeat(11, 1, 1, 1)[:64].contiguous()
     whole = n.transform(big)
     assert tuple(whole.shape) == (64, 3, 1024, 1024)
+    # per-image statistics: an image's result must not depend on the batch around it (up to the
+    # summation order of the moment partial sums, which follows the CTA split)
     for i in (0, 17, 63):
-        assert torch.equal(whole[i], torch.from_numpy(out[i % 6]).to(cuda))
+        assert (whole[i] - torch.from_numpy(out[i % 6]).to(cuda)).abs().max().item() <= 1e-5
 
 
 def test_macenko_sharded_fit_emulation(cuda):

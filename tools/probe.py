@@ -55,17 +55,21 @@ def probe_hm():
     lib = nv.lib()
     counts = torch.zeros((3, 256), dtype=torch.int64, device=dev)
     want = ops.hm_hist(src)
-    for mode, ctas_list in ((0, (4, 8)), (1, (3,)), (2, (2, 3)), (3, (1,))):
+    for mode, ctas_list in ((0, (4, 8)), (1, (3,)), (2, (2, 3)), (3, (1,)), (4, (1,))):
         for ctas in ctas_list:
             lib.sx_hm_set_tuning(mode, ctas, -1)
             ok = torch.equal(ops.hm_hist(src), want)
             report(f"hm hist u8 planar mode={mode} ctas/sm={ctas} ok={ok}", timeit(lambda: ops.hm_hist(src, counts=counts)), 3 * px)
     const = torch.full_like(src, 200)
     smooth = (torch.arange(src.numel(), device=dev, dtype=torch.int64) // 4096 % 256).to(torch.uint8).reshape(src.shape)
-    for mode, ctas in ((0, 8), (2, 3), (3, 1)):
+    lib.sx_hm_set_tuning(0, 8, -1)
+    want_const, want_smooth = ops.hm_hist(const), ops.hm_hist(smooth)
+    for mode, ctas in ((0, 8), (2, 3), (3, 1), (4, 1)):
         lib.sx_hm_set_tuning(mode, ctas, -1)
-        report(f"hm hist u8 CONSTANT image mode={mode}", timeit(lambda: ops.hm_hist(const, counts=counts)), 3 * px)
-        report(f"hm hist u8 SMOOTH image mode={mode}", timeit(lambda: ops.hm_hist(smooth, counts=counts)), 3 * px)
+        ok = torch.equal(ops.hm_hist(const), want_const)
+        report(f"hm hist u8 CONSTANT image mode={mode} ok={ok}", timeit(lambda: ops.hm_hist(const, counts=counts)), 3 * px)
+        ok = torch.equal(ops.hm_hist(smooth), want_smooth)
+        report(f"hm hist u8 SMOOTH image mode={mode} ok={ok}", timeit(lambda: ops.hm_hist(smooth, counts=counts)), 3 * px)
     del const, smooth
     lib.sx_hm_set_tuning(0, 8, -1)
     lut = ops.hm_build_lut(ops.hm_hist(src), px, ops.hm_ref_cdf(ref_hist))
