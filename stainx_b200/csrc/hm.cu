@@ -375,212 +375,288 @@ __global__ void __launch_bounds__(kL32Threads, 1) hist_u8_planar_lane32_kernel(c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Histogram, planar uint8, scheme P ("pairs"): the shared-memory atomic unit retires a fixed number
-// of lane-updates per clock whatever the address pattern (measured: ~6.5 per clk per SM), so the
-// way to count faster is to count MORE PER UPDATE.  Two neighbouring bytes (a, b) of a plane are
-// one 16-bit value h = a | b << 8; a single RED.ADD into a 65 536-cell table counts the pair, and
-// the 256-bin histogram is the sum of the table's two marginals:
-//     hist[v] = sum_b cell[v][b] + sum_a cell[a][v].
-// Cells are 16-bit counters packed two per word (128 KB, one CTA of 1024 threads per SM): cell h
-// lives in word h & 0x7fff, half h >> 15.  A cell overflows after 65 535 hits -- only possible when
-// one byte pair makes up a large share of a CTA's segment (flat images).  A carry changes the sum
-// over all cells, so the fold compares that sum with the number of pairs counted; on a mismatch the
-// CTA discards the segment's table and recounts the segment with 32-bit warp-private atomics.
+// Histogram, planar uint8, scheme S ("streamed"): the same warp-private ATOMS.POPC.INC counting as
+// scheme 0, arranged so that the shared-memory atomic unit never waits for HBM.  Measured on B200
+// (tools/atomsbench.cu): the unit retires ~11.8 distinct-address updates per clock per SM whatever
+// the layout (conflict-free lane-private tables: 10.5-11; 16-bit pair tables: 7.4; same address:
+// 31.5), i.e. 201 M values cannot be counted in less than ~58 us with atomics; scheme 0 reaches 7.7
+// per clock because its warps stall on their own global loads (ncu: 17 % long-scoreboard).  Here one
+// persistent CTA per SM walks a contiguous range of 16 KB tiles which one thread streams into a
+// shared-memory ring with TMA bulk copies (5 tiles = 80 KB in flight per SM; a register ring of the
+// same depth does not work: loads sharing one of the 6 scoreboard slots of a warp complete together).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPairThreads = 1024;
-constexpr int kPairWarps = kPairThreads / 32;
-constexpr int kPairUnroll = 2;                                  // 128-bit loads per thread per tile
-constexpr int kPairTileVecs = kPairThreads * kPairUnroll;       // 32 KB of a plane per tile
-constexpr int kPairTableWords = 32768;
-constexpr int kPairSmemBytes = kPairTableWords * 4 + 256 * 4 + 64;
+// Position in the channel-major tile list (channel, image, tile) of an ALIGNED planar uint8 batch
+// (16-byte aligned base, H*W a multiple of 16: every plane is a whole number of 128-bit vectors).
+// Advancing costs an add and a counter: consecutive items are consecutive tiles of a plane, then
+// the same channel of the next image.  All items of a cursor share a channel.
+struct TileCursor {
+    int64_t off;        // vector index (from the batch base) of the first vector of the current tile
+    int t;              // tile within the plane
+    int tiles;          // tiles per plane
+    int last_vecs;      // vectors in the last tile of a plane (1 .. tile size)
+    int64_t plane_gap;  // vectors from the start of a plane's last tile to the next image's plane (same channel)
+    __device__ __forceinline__ void seek(int64_t hw, int tiles_per_plane, int tile_vecs, int64_t per_channel, int64_t item) {
+        const int64_t c = item / per_channel;
+        const int64_t rem = item - c * per_channel;
+        const int64_t n = rem / tiles_per_plane;
+        const int64_t vecs = hw / 16;
+        t = (int)(rem - n * tiles_per_plane);
+        tiles = tiles_per_plane;
+        last_vecs = (int)(vecs - (int64_t)(tiles_per_plane - 1) * tile_vecs);
+        plane_gap = 3 * vecs - (int64_t)(tiles_per_plane - 1) * tile_vecs;
+        off = (n * 3 + c) * vecs + (int64_t)t * tile_vecs;
+    }
+    __device__ __forceinline__ int vecs(int tile_vecs) const { return t == tiles - 1 ? last_vecs : tile_vecs; }
+    __device__ __forceinline__ void next(int tile_vecs) {
+        if (++t == tiles) { t = 0; off += plane_gap; } else off += tile_vecs;
+    }
+    __device__ __forceinline__ void prev(int tile_vecs) {
+        if (--t < 0) { t = tiles - 1; off -= plane_gap; } else off -= tile_vecs;
+    }
+};
 
-__device__ __forceinline__ void pair_count_word(unsigned w, uint32_t table_addr) {
-    // low halfword: byte offset of its word = (h & 0x7fff) * 4, increment 1 or 1 << 16
-    const unsigned o0 = (w << 2) & 0x1fffcu;
-    const unsigned i0 = ((w >> 15) & 1u) * 0xffffu + 1u;
-    const unsigned o1 = (w >> 14) & 0x1fffcu;
-    const unsigned i1 = (w >> 31) * 0xffffu + 1u;
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(table_addr + o0), "r"(i0) : "memory");
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(table_addr + o1), "r"(i1) : "memory");
+constexpr int kStrThreads = 512;
+constexpr int kStrWarps = kStrThreads / 32;
+constexpr int kStrTileVecs = 1024;  // 16 KB of a plane per tile, two 128-bit vectors per thread
+constexpr int kStrTileBytes = kStrTileVecs * 16;
+
+// Shared-memory ring of tiles filled by TMA bulk copies.  kStages is a power of two.
+template <int kStages, int kTileVecs = kStrTileVecs, int kWarpsInCta = kStrWarps>
+struct TileRing {
+    uint4 *ring;             // [kStages][kTileVecs]
+    uint64_t *full, *empty;  // [kStages] each
+    unsigned produced, consumed;  // running tile counters (thread 0 / every thread)
+    __device__ __forceinline__ void init(unsigned char *ring_mem, uint64_t *bars) {
+        ring = reinterpret_cast<uint4 *>(ring_mem);
+        full = bars;
+        empty = bars + kStages;
+        produced = consumed = 0;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kWarpsInCta); }
+            mbar_fence_init();
+        }
+    }
+    // thread 0: start the copy of `bytes` (> 0, multiple of 16) at `src` into the next stage
+    __device__ __forceinline__ void produce(const uint4 *src, unsigned bytes) {
+        const unsigned st = produced & (kStages - 1), use = produced / kStages;
+        if (use > 0) mbar_wait(empty + st, (use - 1) & 1);  // every warp has read the previous tenant
+        mbar_arrive_expect_tx(full + st, bytes);
+        tma_load_1d(ring + (size_t)st * kTileVecs, src, bytes, full + st);
+        ++produced;
+    }
+    // every thread: wait for the next tile; returns its stage.  release() after the reads.
+    __device__ __forceinline__ const uint4 *acquire() {
+        const unsigned st = consumed & (kStages - 1), use = consumed / kStages;
+        mbar_wait(full + st, use & 1);
+        return ring + (size_t)st * kTileVecs;
+    }
+    __device__ __forceinline__ void release() {
+        const unsigned st = consumed & (kStages - 1);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + st);
+        ++consumed;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Histogram, planar uint8, scheme S ("streamed"): the same warp-private ATOMS.POPC.INC counting as
+// scheme 0, arranged so that the shared-memory atomic unit never waits for HBM and so that the
+// instruction count per value is minimal.  Measured on B200 (tools/atomsbench.cu): the unit retires
+// ~11.8 distinct-address updates per clock per SM whatever the layout (conflict-free lane-private
+// tables: 10.5-11; 16-bit pair tables: 7.4; same address: 31.5), i.e. 201 M random values cannot be
+// counted in less than ~58 us with atomics.  One persistent CTA per SM walks a contiguous range of
+// 16 KB tiles which one thread streams into a shared-memory ring with TMA bulk copies (7 tiles =
+// 112 KB in flight per SM; a register ring of the same depth does not work: loads that share one of
+// the 6 scoreboard slots of a warp complete together).  Counting one byte is SHF + LOP3 (the
+// warp's 1 KB histogram is 1 KB-aligned, so "| base" replaces the add) + ATOMS.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHistStages = 8;
+constexpr int kHistSmem = 1024 + kStrWarps * 1024 + kHistStages * kStrTileBytes + 2 * kHistStages * 8;
+
+__device__ __forceinline__ void popc_count4(unsigned w, unsigned base) {
+    const unsigned a0 = ((w << 2) & 0x3fcu) | base, a1 = ((w >> 6) & 0x3fcu) | base;
+    const unsigned a2 = ((w >> 14) & 0x3fcu) | base, a3 = ((w >> 22) & 0x3fcu) | base;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a2) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a3) : "memory");
 }
 
-__global__ void __launch_bounds__(kPairThreads, 1) hist_u8_planar_pairs_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned int *table = reinterpret_cast<unsigned int *>(smem);              // [32768] packed 16-bit cells
-    unsigned int *hist32 = table + kPairTableWords;                            // [256] segment histogram
-    unsigned int *s_misc = hist32 + 256;                                       // [0] pairs counted, [1] sum of cells
-    const uint32_t table_addr = (uint32_t)__cvta_generic_to_shared(table);
-    const int lane = threadIdx.x & 31;
-
-    for (int i = threadIdx.x; i < kPairTableWords; i += kPairThreads) table[i] = 0u;
-    if (threadIdx.x < 256) hist32[threadIdx.x] = 0u;
-    if (threadIdx.x < 2) s_misc[threadIdx.x] = 0u;
+__global__ void __launch_bounds__(kStrThreads, 1) hist_u8_planar_streamed_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *smem_hist = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB-align
+    unsigned int *whist = reinterpret_cast<unsigned int *>(smem_hist);  // [warp][256], 1 KB-aligned rows
+    unsigned char *ring_mem = smem_hist + kStrWarps * 1024;
+    TileRing<kHistStages> tr;
+    tr.init(ring_mem, reinterpret_cast<uint64_t *>(ring_mem + kHistStages * kStrTileBytes));
+    for (int i = threadIdx.x; i < kStrWarps * 256; i += kStrThreads) whist[i] = 0u;
     __syncthreads();
+    const unsigned wbase = smem_u32(whist + (threadIdx.x >> 5) * 256);
 
     const int64_t per_channel = n_img * tiles_per_plane;
     const int64_t items = 3 * per_channel;
     const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
     const int64_t first = (int64_t)blockIdx.x * per_cta;
     const int64_t last = first + per_cta < items ? first + per_cta : items;
+    const uint4 *base = reinterpret_cast<const uint4 *>(img);
 
-    struct Item {
-        const uint4 *body;
-        const uint8_t *plane;
-        int64_t v0, nvec, head, tail0;
-        bool first_tile;
-    };
-    auto locate = [&](int64_t item) {
-        const int c = (int)(item / per_channel);
-        const int64_t rem = item - (int64_t)c * per_channel;
-        const int64_t n = rem / tiles_per_plane;
-        const int64_t t = rem - n * tiles_per_plane;
-        Item it;
-        it.plane = img + (n * 3 + c) * hw;
-        const PlaneSplit sp = split_plane(it.plane, hw);
-        it.body = reinterpret_cast<const uint4 *>(it.plane + sp.head);
-        it.v0 = t * kPairTileVecs;
-        it.nvec = sp.nvec;
-        it.head = sp.head;
-        it.tail0 = sp.tail0;
-        it.first_tile = t == 0;
-        return it;
-    };
-    auto issue = [&](int64_t item, uint4(&v)[kPairUnroll], unsigned &okmask) {
-        const Item it = locate(item);
-        okmask = 0;
-#pragma unroll
-        for (int u = 0; u < kPairUnroll; ++u) {
-            const int64_t vi = it.v0 + u * kPairThreads + threadIdx.x;
-            if (vi < it.nvec) {
-                v[u] = ld_stream(it.body + vi);
-                okmask |= 1u << u;
-            }
-        }
-    };
-    // ragged ends of a plane (< 32 bytes): single values, straight into the segment histogram
-    auto stragglers = [&](int64_t item) {
-        const Item it = locate(item);
-        if (!it.first_tile) return;
-        const int64_t ragged = it.head + (hw - it.tail0);
-        if ((int64_t)threadIdx.x < ragged) {
-            const int64_t idx = (int64_t)threadIdx.x < it.head ? (int64_t)threadIdx.x : it.tail0 + ((int64_t)threadIdx.x - it.head);
-            atomicAdd(&hist32[it.plane[idx]], 1u);
-        }
-    };
-
-    unsigned my_pairs = 0;  // pairs this thread has counted since the last fold
-    auto count_pairs = [&](const uint4(&v)[kPairUnroll], unsigned okmask) {
-#pragma unroll
-        for (int u = 0; u < kPairUnroll; ++u) {
-            if (okmask & (1u << u)) {
-                pair_count_word(v[u].x, table_addr);
-                pair_count_word(v[u].y, table_addr);
-                pair_count_word(v[u].z, table_addr);
-                pair_count_word(v[u].w, table_addr);
-                my_pairs += 8;
-            }
-        }
-    };
-
-    // Fold the pair table into hist32 (both marginals), re-zero it, and check the cell sum.
-    // Thread t walks words t, t + 1024, ...: a = t & 255 is fixed per thread, b & 127 = (t >> 8) + 4k
-    // is uniform over a warp.  Returns true when no cell overflowed.
-    auto fold_table = [&]() -> bool {
-        __syncthreads();
-        unsigned acc_a = 0;
-#pragma unroll 4
-        for (int k = 0; k < kPairTableWords / kPairThreads; ++k) {
-            const int i = threadIdx.x + k * kPairThreads;
-            const unsigned w = table[i];
-            table[i] = 0u;
-            const unsigned lo = w & 0xffffu, hi = w >> 16;
-            acc_a += lo + hi;
-            const unsigned slo = __reduce_add_sync(0xffffffffu, lo), shi = __reduce_add_sync(0xffffffffu, hi);
-            if (lane == 0) {
-                const int b7 = i >> 8;
-                if (slo) atomicAdd(&hist32[b7], slo);
-                if (shi) atomicAdd(&hist32[b7 + 128], shi);
-            }
-        }
-        if (acc_a) atomicAdd(&hist32[threadIdx.x & 255], acc_a);
-        const unsigned cells = __reduce_add_sync(0xffffffffu, acc_a), pairs = __reduce_add_sync(0xffffffffu, my_pairs);
-        if (lane == 0) {
-            atomicAdd(&s_misc[0], pairs);
-            atomicAdd(&s_misc[1], cells);
-        }
-        my_pairs = 0;
-        __syncthreads();
-        const bool ok = s_misc[0] == s_misc[1];
-        __syncthreads();
-        if (threadIdx.x < 2) s_misc[threadIdx.x] = 0u;
-        return ok;
-    };
-    // hist32 -> global counts of channel c, re-zero.
-    auto flush_hist = [&](int c) {
+    // warp histograms -> global counts of channel c, re-zero
+    auto flush = [&](int c) {
         __syncthreads();
         if (threadIdx.x < 256) {
-            const unsigned v = hist32[threadIdx.x];
-            if (v) atomicAdd(&counts[c * 256 + threadIdx.x], (unsigned long long)v);
-            hist32[threadIdx.x] = 0u;
-        }
-        __syncthreads();
-    };
-    // Safe recount of items [a, b) (one channel) with warp-private 32-bit histograms held in the
-    // (already re-zeroed) table memory; hist32 keeps only the stragglers until it is rebuilt.
-    auto recount = [&](int64_t a, int64_t b) {
-        unsigned int *wh = table + (threadIdx.x >> 5) * 256;
-        for (int64_t item = a; item < b; ++item) {
-            const Item it = locate(item);
+            unsigned long long sum = 0;
 #pragma unroll
-            for (int u = 0; u < kPairUnroll; ++u) {
-                const int64_t vi = it.v0 + u * kPairThreads + threadIdx.x;
-                if (vi < it.nvec) {
-                    const uint4 v = ld_stream(it.body + vi);
-                    const unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(&wh[(w[j >> 2] >> (8 * (j & 3))) & 0xffu], 1u);
-                }
-            }
+            for (int wgt = 0; wgt < kStrWarps; ++wgt) sum += whist[wgt * 256 + threadIdx.x];
+            if (sum) atomicAdd(&counts[c * 256 + threadIdx.x], sum);
         }
         __syncthreads();
-        if (threadIdx.x < 256) {
-            unsigned s = 0;
-            for (int wgt = 0; wgt < kPairWarps; ++wgt) s += table[wgt * 256 + threadIdx.x];
-            hist32[threadIdx.x] += s;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < kPairWarps * 256; i += kPairThreads) table[i] = 0u;
+        for (int i = threadIdx.x; i < kStrWarps * 256; i += kStrThreads) whist[i] = 0u;
         __syncthreads();
     };
 
-    // Walk the CTA's contiguous item range one channel segment at a time.
     int64_t seg = first;
-    while (seg < last) {
+    while (seg < last) {  // one channel segment at a time (at most three per CTA)
         const int c = (int)(seg / per_channel);
         const int64_t chan_end = (int64_t)(c + 1) * per_channel;
         const int64_t seg_end = chan_end < last ? chan_end : last;
-        uint4 va[kPairUnroll], vb[kPairUnroll];
-        unsigned oka = 0, okb = 0;
-        issue(seg, va, oka);
-        for (int64_t item = seg; item < seg_end; item += 2) {
-            if (item + 1 < seg_end) issue(item + 1, vb, okb);
-            count_pairs(va, oka);
-            stragglers(item);
-            if (item + 1 < seg_end) {
-                if (item + 2 < seg_end) issue(item + 2, va, oka);
-                count_pairs(vb, okb);
-                stragglers(item + 1);
+        const int n_items = (int)(seg_end - seg);
+        TileCursor pc, cc;  // producer (thread 0) and consumer positions
+        pc.seek(hw, (int)tiles_per_plane, kStrTileVecs, per_channel, seg);
+        cc = pc;
+        int issued = 0;
+        for (int item = 0; item < n_items; ++item) {
+            if (threadIdx.x == 0) {  // keep kHistStages - 1 tiles in flight
+                while (issued < n_items && issued - item < kHistStages - 1) {
+                    tr.produce(base + pc.off, (unsigned)pc.vecs(kStrTileVecs) * 16u);
+                    pc.next(kStrTileVecs);
+                    ++issued;
+                }
             }
+            const int nv = cc.vecs(kStrTileVecs);
+            cc.next(kStrTileVecs);
+            const uint4 *tile = tr.acquire();
+            const bool ok0 = (int)threadIdx.x < nv, ok1 = (int)threadIdx.x + kStrThreads < nv;
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+            if (ok0) v0 = tile[threadIdx.x];
+            if (ok1) v1 = tile[threadIdx.x + kStrThreads];
+            tr.release();
+            if (ok0) { popc_count4(v0.x, wbase); popc_count4(v0.y, wbase); popc_count4(v0.z, wbase); popc_count4(v0.w, wbase); }
+            if (ok1) { popc_count4(v1.x, wbase); popc_count4(v1.y, wbase); popc_count4(v1.z, wbase); popc_count4(v1.w, wbase); }
         }
-        if (!fold_table()) {  // a 16-bit cell overflowed: drop the pair counts, keep the stragglers
-            __syncthreads();
-            // hist32 currently holds marginals (garbage) + stragglers; rebuild it from scratch
-            if (threadIdx.x < 256) hist32[threadIdx.x] = 0u;
-            __syncthreads();
-            for (int64_t item = seg; item < seg_end; ++item) stragglers(item);
-            recount(seg, seg_end);
+        flush(c);
+        seg = seg_end;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Histogram, planar uint8, scheme L ("lane-private, TMA-fed").  Random bytes make ~3.2-way bank
+// conflicts in a warp-private 256-bin table, and the shared-memory atomic unit then retires only
+// ~7.7 values per clock per SM (schemes 0 and S both land there).  With one full histogram PER
+// LANE, laid out [bin][lane] so that counter (bin, lane) sits in bank `lane`, every update is
+// conflict-free and the unit retires ~15 per clock (tools/atomsbench.cu, "lane32").  The price is
+// 32 KB of shared memory per warp, i.e. only five warps per SM -- far too few to hide HBM latency
+// with their own loads (scheme 3 tried: 95 us).  Here the five warps never touch HBM: one thread
+// streams 16 KB tiles into a 4-stage shared-memory ring with TMA bulk copies (48 KB in flight per
+// SM), the warps read their vectors from the ring and only count.  No overflow handling: 32-bit
+// counters.  Per byte: PRMT + IMAD + ATOMS.POPC.INC.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLaneWarps = 5;
+constexpr int kLaneThreads = kLaneWarps * 32;
+constexpr int kLaneTileVecs = 1024;              // 16 KB tiles: 6.4 vectors per thread
+constexpr int kLanePerThread = (kLaneTileVecs + kLaneThreads - 1) / kLaneThreads;
+constexpr int kLaneStages = 4;
+constexpr int kLaneSmem = kLaneWarps * 32768 + kLaneStages * kLaneTileVecs * 16 + 2 * kLaneStages * 8 + 256 * 4;
+
+__device__ __forceinline__ void lane_count4(unsigned w, unsigned base) {  // base = &region[0][lane]
+    const unsigned a0 = (w & 0xffu) * 128u + base;
+    const unsigned a1 = __byte_perm(w, 0, 0x4441) * 128u + base;
+    const unsigned a2 = __byte_perm(w, 0, 0x4442) * 128u + base;
+    const unsigned a3 = (w >> 24) * 128u + base;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a2) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a3) : "memory");
+}
+
+__global__ void __launch_bounds__(kLaneThreads, 1) hist_u8_planar_lane_tma_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_lane[];
+    unsigned int *regions = reinterpret_cast<unsigned int *>(smem_lane);  // [warp][bin][lane]
+    unsigned char *ring_mem = smem_lane + kLaneWarps * 32768;
+    unsigned char *tail = ring_mem + kLaneStages * kLaneTileVecs * 16;
+    unsigned int *hist32 = reinterpret_cast<unsigned int *>(tail + 2 * kLaneStages * 8);  // [bin]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileRing<kLaneStages, kLaneTileVecs, kLaneWarps> tr;
+    tr.init(ring_mem, reinterpret_cast<uint64_t *>(tail));
+    for (int i = threadIdx.x; i < kLaneWarps * 8192; i += kLaneThreads) regions[i] = 0u;
+    for (int i = threadIdx.x; i < 256; i += kLaneThreads) hist32[i] = 0u;
+    __syncthreads();
+    unsigned int *region = regions + warp * 8192;
+    const unsigned cbase = smem_u32(region) + (unsigned)lane * 4u;
+
+    const int64_t per_channel = n_img * tiles_per_plane;
+    const int64_t items = 3 * per_channel;
+    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const int64_t first = (int64_t)blockIdx.x * per_cta;
+    const int64_t last = first + per_cta < items ? first + per_cta : items;
+    const uint4 *base = reinterpret_cast<const uint4 *>(img);
+
+    // lane-private counters of every warp -> global counts of channel c, re-zero
+    auto flush = [&](int c) {
+        __syncthreads();
+        for (int bin = lane; bin < 256; bin += 32) {  // lane j: bins j, j + 32, ...; rotated walk = no conflicts
+            unsigned sum = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const int col = (k + lane) & 31;
+                sum += region[bin * 32 + col];
+                region[bin * 32 + col] = 0u;
+            }
+            if (sum) atomicAdd(&hist32[bin], sum);
         }
-        flush_hist(c);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 256; i += kLaneThreads) {
+            const unsigned v = hist32[i];
+            if (v) atomicAdd(&counts[c * 256 + i], (unsigned long long)v);
+            hist32[i] = 0u;
+        }
+        __syncthreads();
+    };
+
+    int64_t seg = first;
+    while (seg < last) {  // one channel segment at a time (at most three per CTA)
+        const int c = (int)(seg / per_channel);
+        const int64_t chan_end = (int64_t)(c + 1) * per_channel;
+        const int64_t seg_end = chan_end < last ? chan_end : last;
+        const int n_items = (int)(seg_end - seg);
+        TileCursor pc, cc;
+        pc.seek(hw, (int)tiles_per_plane, kLaneTileVecs, per_channel, seg);
+        cc = pc;
+        int issued = 0;
+        for (int item = 0; item < n_items; ++item) {
+            if (threadIdx.x == 0) {
+                while (issued < n_items && issued - item < kLaneStages - 1) {
+                    tr.produce(base + pc.off, (unsigned)pc.vecs(kLaneTileVecs) * 16u);
+                    pc.next(kLaneTileVecs);
+                    ++issued;
+                }
+            }
+            const int nv = cc.vecs(kLaneTileVecs);
+            cc.next(kLaneTileVecs);
+            const uint4 *tile = tr.acquire();
+            uint4 v[kLanePerThread];
+            bool ok[kLanePerThread];
+#pragma unroll
+            for (int u = 0; u < kLanePerThread; ++u) {
+                const int idx = (int)threadIdx.x + u * kLaneThreads;
+                ok[u] = idx < nv;
+                if (ok[u]) v[u] = tile[idx];
+            }
+            tr.release();
+#pragma unroll
+            for (int u = 0; u < kLanePerThread; ++u)
+                if (ok[u]) { lane_count4(v[u].x, cbase); lane_count4(v[u].y, cbase); lane_count4(v[u].z, cbase); lane_count4(v[u].w, cbase); }
+        }
+        flush(c);
         seg = seg_end;
     }
 }
@@ -902,6 +978,95 @@ __global__ void __launch_bounds__(kThreads) apply_u8_planar_kernel(const uint8_t
     }
 }
 
+// uint8 planar, pair LUT.  The byte-table kernel above is bound by shared-memory bank conflicts, not
+// by HBM (ncu: 16 random byte lookups per 128-bit load, ~3.2 wavefronts each, LSU data pipe at its
+// one wavefront per clock).  Here one lookup translates TWO neighbouring bytes: a 65 536-entry
+// uint16 table pair[a | b << 8] = lut[a] | lut[b] << 8 (128 KB of shared memory) halves the lookups
+// and the extract / insert arithmetic.  One persistent CTA per SM owns a contiguous range of the
+// channel-major tile list (at most three channel segments, the table is rebuilt per segment) --
+// the same range the streamed histogram kernel gave it -- and walks it BACKWARDS, so it starts in
+// the part of the batch that pass left in L2.
+constexpr int kPairLutBytes = 65536 * 2;
+
+__device__ __forceinline__ unsigned pair_lookup_word(unsigned w, uint32_t table_addr) {
+    unsigned short lo, hi;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(table_addr + ((w << 1) & 0x1fffeu)));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(table_addr + ((w >> 15) & 0x1fffeu)));
+    return (unsigned)lo | ((unsigned)hi << 16);
+}
+
+constexpr int kApplyStages = 4;
+constexpr int kPairLutSmem = kPairLutBytes + kApplyStages * kStrTileBytes + 768 + 2 * kApplyStages * 8 + 16;
+
+__global__ void __launch_bounds__(kStrThreads, 1) apply_u8_planar_pairlut_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, int64_t hw, int64_t n_img, int64_t tiles_per_plane, const float *__restrict__ lut) {
+    extern __shared__ __align__(16) unsigned char smem_apply[];
+    unsigned short *pair = reinterpret_cast<unsigned short *>(smem_apply);
+    unsigned char *ring_mem = smem_apply + kPairLutBytes;
+    unsigned char *lut8 = ring_mem + kApplyStages * kStrTileBytes;
+    const uint32_t table_addr = smem_u32(pair);
+    TileRing<kApplyStages> tr;
+    tr.init(ring_mem, reinterpret_cast<uint64_t *>(lut8 + 768));
+    for (int i = threadIdx.x; i < 768; i += kStrThreads) lut8[i] = (unsigned char)__float2int_rz(lut[i]);  // trunc, L296-298
+
+    const int64_t per_channel = n_img * tiles_per_plane;
+    const int64_t items = 3 * per_channel;
+    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const int64_t first = (int64_t)blockIdx.x * per_cta;
+    const int64_t last = first + per_cta < items ? first + per_cta : items;
+    const uint4 *base = reinterpret_cast<const uint4 *>(img);
+    uint4 *obase = reinterpret_cast<uint4 *>(out);
+
+    auto remap = [&](const uint4 &v) {
+        uint4 r;
+        r.x = pair_lookup_word(v.x, table_addr);
+        r.y = pair_lookup_word(v.y, table_addr);
+        r.z = pair_lookup_word(v.z, table_addr);
+        r.w = pair_lookup_word(v.w, table_addr);
+        return r;
+    };
+
+    int64_t seg_end = last;
+    while (seg_end > first) {  // channel segments, last to first
+        const int c = (int)((seg_end - 1) / per_channel);
+        const int64_t chan_begin = (int64_t)c * per_channel;
+        const int64_t seg = chan_begin > first ? chan_begin : first;
+        const int n_items = (int)(seg_end - seg);
+        __syncthreads();  // previous segment's lookups are done (and lut8 / the barriers are written)
+        for (int i = threadIdx.x; i < 32768; i += kStrThreads) {  // two entries per store
+            const unsigned e0 = 2 * i, e1 = 2 * i + 1;
+            const unsigned lo = (unsigned)lut8[c * 256 + (e0 & 255)] | ((unsigned)lut8[c * 256 + (e0 >> 8)] << 8);
+            const unsigned hi = (unsigned)lut8[c * 256 + (e1 & 255)] | ((unsigned)lut8[c * 256 + (e1 >> 8)] << 8);
+            reinterpret_cast<unsigned *>(pair)[i] = lo | (hi << 16);
+        }
+        __syncthreads();
+        TileCursor pc, cc;  // walk backwards: seg_end - 1, seg_end - 2, ..., seg
+        pc.seek(hw, (int)tiles_per_plane, kStrTileVecs, per_channel, seg_end - 1);
+        cc = pc;
+        int issued = 0;
+        for (int item = 0; item < n_items; ++item) {
+            if (threadIdx.x == 0) {
+                while (issued < n_items && issued - item < kApplyStages - 1) {
+                    tr.produce(base + pc.off, (unsigned)pc.vecs(kStrTileVecs) * 16u);
+                    pc.prev(kStrTileVecs);
+                    ++issued;
+                }
+            }
+            const int nv = cc.vecs(kStrTileVecs);
+            uint4 *dst = obase + cc.off;
+            cc.prev(kStrTileVecs);
+            const uint4 *tile = tr.acquire();
+            const bool ok0 = (int)threadIdx.x < nv, ok1 = (int)threadIdx.x + kStrThreads < nv;
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+            if (ok0) v0 = tile[threadIdx.x];
+            if (ok1) v1 = tile[threadIdx.x + kStrThreads];
+            tr.release();
+            if (ok0) st_stream(dst + threadIdx.x, remap(v0));
+            if (ok1) st_stream(dst + threadIdx.x + kStrThreads, remap(v1));
+        }
+        seg_end = seg;
+    }
+}
+
 // float32 planar: out = clamp(lut[trunc(clamp(255 x))] / 255, 0, 1)   (L290-296).
 __global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const float *__restrict__ img, float *__restrict__ out, int64_t hw, int64_t planes, int64_t tiles_per_plane, const float *__restrict__ lut) {
     __shared__ float lutf[3 * 256];
@@ -999,9 +1164,11 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
 }
 
 // ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
-static int g_hist_byte_counters = 0;  // counting scheme: 0 warp atomics, 1 byte counters, 2 packed RED, 3 lane32, 4 pairs
+static int g_hist_byte_counters = 0;  // counting scheme: 0 warp atomics (default: fastest on real images and within 10 % of the best on noise),
+                                      // 1 byte counters, 2 packed RED, 3 lane32, 4 streamed (TMA ring), 5 lane-private + TMA ring
 static int g_hist_ctas_per_sm = 8;
-static int g_apply_ctas_per_sm = 8;
+static int g_apply_ctas_per_sm = 16;
+static int g_apply_pair_lut = 0;       // uint8 planar remap through the 2-byte table (persistent kernel)
 
 }  // namespace hm
 }  // namespace sx
@@ -1016,6 +1183,7 @@ int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_cta
     if (hist_byte_counters >= 0) g_hist_byte_counters = hist_byte_counters;
     if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
     if (apply_ctas_per_sm > 0) g_apply_ctas_per_sm = apply_ctas_per_sm;
+    g_apply_pair_lut = apply_ctas_per_sm == 1000 ? 1 : (apply_ctas_per_sm > 0 ? 0 : g_apply_pair_lut);
     return SX_OK;
 }
 
@@ -1042,15 +1210,26 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
     if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         const int64_t items = n * tiles;
-        if (g_hist_byte_counters == 4) {
+        // scheme 4 needs whole 128-bit vectors per plane; anything else takes the general kernel
+        const bool planes_aligned = aligned16(images) && hw % 16 == 0;
+        if (g_hist_byte_counters == 5 && planes_aligned) {
+            static bool attr5_set = false;
+            if (!attr5_set) {
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem));
+                attr5_set = true;
+            }
+            const int64_t tiles_l = max_i64(1, (hw / 16 + kLaneTileVecs - 1) / kLaneTileVecs);
+            const unsigned grid_l = stream_grid(3 * n * tiles_l, 1);
+            hist_u8_planar_lane_tma_kernel<<<grid_l, kLaneThreads, kLaneSmem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles_l, cnt);
+        } else if (g_hist_byte_counters == 4 && planes_aligned) {
+            const int64_t tiles_s = max_i64(1, (hw / 16 + kStrTileVecs - 1) / kStrTileVecs);
+            const unsigned grid_s = stream_grid(3 * n * tiles_s, 1);
             static bool attr4_set = false;
             if (!attr4_set) {
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_streamed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
                 attr4_set = true;
             }
-            const int64_t tiles_p = max_i64(1, (hw / 16 + kPairTileVecs - 1) / kPairTileVecs);
-            const unsigned grid_p = stream_grid(3 * n * tiles_p, 1);
-            hist_u8_planar_pairs_kernel<<<grid_p, kPairThreads, kPairSmemBytes, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles_p, cnt);
+            hist_u8_planar_streamed_kernel<<<grid_s, kStrThreads, kHistSmem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles_s, cnt);
         } else if (g_hist_byte_counters == 3) {
             static bool attr3_set = false;
             if (!attr3_set) {
@@ -1060,7 +1239,7 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
             const int64_t tiles32 = max_i64(1, (hw / 16 + kL32TileVecs - 1) / kL32TileVecs);
             const unsigned grid32 = stream_grid(3 * n * tiles32, 1);
             hist_u8_planar_lane32_kernel<<<grid32, kL32Threads, kL32SmemBytes, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles32, cnt);
-        } else if (g_hist_byte_counters) {
+        } else if (g_hist_byte_counters == 1 || g_hist_byte_counters == 2) {
             const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * ByteCounters::kBytesPerWarp;
             static bool attr_set = false;
             if (!attr_set) {
@@ -1130,7 +1309,17 @@ int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h,
         return SX_OK;
     }
     const int64_t planes = n * 3;
-    if (dtype == SX_U8) {
+    if (dtype == SX_U8 && g_apply_pair_lut && aligned16(images) && aligned16(out) && hw % 16 == 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SX_CUDA(cudaFuncSetAttribute(apply_u8_planar_pairlut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutSmem));
+            attr_set = true;
+        }
+        const int64_t tiles_s = max_i64(1, (hw / 16 + kStrTileVecs - 1) / kStrTileVecs);
+        const unsigned grid_s = stream_grid(3 * n * tiles_s, 1);
+        apply_u8_planar_pairlut_kernel<<<grid_s, kStrThreads, kPairLutSmem, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, n, tiles_s, lut);
+        SX_LAUNCHED("apply_u8_planar_pairlut_kernel");
+    } else if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
         apply_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, planes, tiles, lut);

@@ -55,7 +55,7 @@ def probe_hm():
     lib = nv.lib()
     counts = torch.zeros((3, 256), dtype=torch.int64, device=dev)
     want = ops.hm_hist(src)
-    for mode, ctas_list in ((0, (4, 8)), (1, (3,)), (2, (2, 3)), (3, (1,)), (4, (1,))):
+    for mode, ctas_list in ((0, (4, 8)), (1, (3,)), (2, (2, 3)), (3, (1,)), (4, (1,)), (5, (1,))):
         for ctas in ctas_list:
             lib.sx_hm_set_tuning(mode, ctas, -1)
             ok = torch.equal(ops.hm_hist(src), want)
@@ -64,7 +64,7 @@ def probe_hm():
     smooth = (torch.arange(src.numel(), device=dev, dtype=torch.int64) // 4096 % 256).to(torch.uint8).reshape(src.shape)
     lib.sx_hm_set_tuning(0, 8, -1)
     want_const, want_smooth = ops.hm_hist(const), ops.hm_hist(smooth)
-    for mode, ctas in ((0, 8), (2, 3), (3, 1), (4, 1)):
+    for mode, ctas in ((0, 8), (2, 3), (3, 1), (4, 1), (5, 1)):
         lib.sx_hm_set_tuning(mode, ctas, -1)
         ok = torch.equal(ops.hm_hist(const), want_const)
         report(f"hm hist u8 CONSTANT image mode={mode} ok={ok}", timeit(lambda: ops.hm_hist(const, counts=counts)), 3 * px)
@@ -77,6 +77,17 @@ def probe_hm():
         lib.sx_hm_set_tuning(-1, -1, ctas)
         report(f"hm apply u8 planar ctas/sm={ctas}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
     lib.sx_hm_set_tuning(-1, -1, 8)
+    want_out = ops.hm_apply(src, lut)
+    lib.sx_hm_set_tuning(-1, -1, 1000)
+    ok = torch.equal(ops.hm_apply(src, lut), want_out)
+    odd = src.flatten()[3:3 + 5 * 3 * 1000 * 1001].reshape(5, 3, 1000, 1001)  # misaligned planes
+    lib.sx_hm_set_tuning(-1, -1, 8)
+    want_odd = ops.hm_apply(odd.clone(), lut)
+    lib.sx_hm_set_tuning(4, 1, 1000)
+    ok_odd = torch.equal(ops.hm_apply(odd.clone(), lut), want_odd)
+    report(f"hm apply u8 planar PAIR LUT ok={ok} odd_ok={ok_odd}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
+    report("hm transform u8 streamed hist + pair LUT", timeit(lambda: ops.hm_transform(src, ref_hist)), 9 * px)
+    lib.sx_hm_set_tuning(0, 8, 8)
     report("hm transform u8 (hist+lut+apply)", timeit(lambda: ops.hm_transform(src, ref_hist)), 9 * px)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
     report("hm transform u8 NHWC", timeit(lambda: ops.hm_transform(nhwc, ref_hist, nv.SX_NHWC)), 9 * px)
