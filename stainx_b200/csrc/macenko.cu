@@ -58,10 +58,22 @@ struct SlotState {
     float pinv[6];        // (HE^T HE)^-1 HE^T, 2x3 row-major
     float c_lo[2];        // concentration key mapping: key = (C - c_lo) * c_scale
     float c_scale[2];
+    float lrange[8];      // fused pipeline: per-channel (-min l, max l) of the slot's rows (copy of odrange)
+    int redo;             // fused pipeline: moments must be re-accumulated without the mask
+    int miss;             // fused pipeline: a wanted rank fell outside its bracket in the last resolve
 };
 
+// Team barrier of the fused pipeline: monotonically increasing arrival count and release epoch.
+struct TeamSync {
+    unsigned arrive;
+    unsigned pad0[31];
+    unsigned release;
+    unsigned pad1[31];
+};
+constexpr int kMaxTeam = 160;  // CTAs per team (<= SM count of the device)
+
 struct Layout {
-    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, total;
+    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, partials, sync, total;
     __host__ __device__ explicit Layout(int64_t slots) {
         int64_t o = 0;
         moments = o;  o += slots * 12 * 8;
@@ -74,6 +86,8 @@ struct Layout {
         fit = o;      o += slots * 8 * 4;
         status = o;   o += slots * 4 * 4;
         state = (o + 15) / 16 * 16; o = state + slots * (int64_t)sizeof(SlotState);
+        partials = (o + 15) / 16 * 16; o = partials + slots * kMaxTeam * 12 * 8;  // fused: per-CTA moment partial sums
+        sync = (o + 255) / 256 * 256; o = sync + slots * (int64_t)sizeof(TeamSync);
         total = (o + 255) / 256 * 256;
     }
 };
@@ -86,6 +100,8 @@ struct Ws {
     float *vmin, *vmax, *fit;
     int *status;                   // [slot][4]: [0] bit q set = rank of query q fell outside its bracket
     SlotState *state;
+    double *partials;              // [slot][kMaxTeam][12]
+    TeamSync *sync;                // [slot]
     __host__ __device__ Ws(void *base, int64_t slots) {
         Layout L(slots);
         char *b = static_cast<char *>(base);
@@ -99,6 +115,8 @@ struct Ws {
         fit = reinterpret_cast<float *>(b + L.fit);
         status = reinterpret_cast<int *>(b + L.status);
         state = reinterpret_cast<SlotState *>(b + L.state);
+        partials = reinterpret_cast<double *>(b + L.partials);
+        sync = reinterpret_cast<TeamSync *>(b + L.sync);
     }
 };
 
@@ -128,7 +146,7 @@ __device__ __forceinline__ void build_l_table(float *tab) {
         tab[i] = log2f(__fadd_rn(__fmul_rn(x, 255.0f), 1.0f));
     }
 }
-__device__ __forceinline__ float f32_l(float x) { return __log2f(__fmaf_rn(x, 255.0f, 1.0f)); }
+__device__ __forceinline__ float f32_l(float x) { return fast_lg2(__fmaf_rn(x, 255.0f, 1.0f)); }
 
 // Raw 128-bit (or scalar) loads of one pixel group, kept in registers so that the loads of the next
 // group can be in flight while the current one is processed.
@@ -195,6 +213,28 @@ __device__ __forceinline__ void stream_groups(const T *__restrict__ image, int64
     }
 }
 
+// The same, but the body runs on EVERY thread of the CTA in every trip (with `valid` = the thread
+// has a group; its l values are unspecified otherwise), so bodies may use full-warp collectives.
+template <typename T, bool VEC, typename Body, typename Every>
+__device__ __forceinline__ void stream_groups_uniform(const T *__restrict__ image, int64_t hw, int64_t groups, int64_t cta_first, int64_t cta_stride, const float *tab, Body body, Every every) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    RawGroup<T, VEC> cur, nxt;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { cur.v[c] = typename RawGroup<T, VEC>::Vec(); nxt.v[c] = typename RawGroup<T, VEC>::Vec(); }
+    int64_t gi = cta_first + threadIdx.x;
+    if (gi < groups) cur.load(image + gi * kPix, hw);
+    for (int64_t base = cta_first; base < groups; base += cta_stride) {
+        const int64_t gn = gi + cta_stride;
+        if (gn < groups) nxt.load(image + gn * kPix, hw);
+        float l[3][kPix];
+        cur.to_l(tab, l);
+        body(l, gi, gi < groups);
+        every();
+        cur = nxt;
+        gi = gn;
+    }
+}
+
 // Loads kPix pixels; l[c][k] = log2(255 x + 1) of channel c of pixel k (no prefetch; sample pass).
 template <typename T, bool VEC>
 __device__ __forceinline__ void load_l(const T *__restrict__ base, int64_t hw, const float *tab, float (&l)[3][Pix<T, VEC>::kPix]) {
@@ -213,9 +253,10 @@ struct PassGeom {
 // Diamond angle: monotone in atan2(y, x) over (-pi, pi], range [-2, 2].
 __device__ __forceinline__ float diamond_angle(float y, float x) {
     const float a = __fadd_rn(fabsf(x), fabsf(y));
-    float r = __fdividef(y, a);
+    float r = __fmul_rn(y, fast_rcp(a));
     r = a > 0.0f ? r : 0.0f;
-    return x >= 0.0f ? r : (y >= 0.0f ? __fsub_rn(2.0f, r) : __fsub_rn(-2.0f, r));
+    const float flipped = __fsub_rn(copysignf(2.0f, y), r);  // y >= 0: 2 - r, y < 0: -2 - r
+    return x >= 0.0f ? r : flipped;
 }
 // value = aff[3] + aff[0] l0 + aff[1] l1 + aff[2] l2   (pinned: every pass must agree bit for bit)
 __device__ __forceinline__ float affine3(const float *aff, float l0, float l1, float l2) {
@@ -265,9 +306,12 @@ __device__ __forceinline__ void moments_group(const float (&l)[3][kPix], float (
         const float r = l[0][k], gg = l[1][k], b = l[2][k];
         bool keep = true;
         if (MASKED) {
-            lo[0] = fminf(lo[0], r); lo[1] = fminf(lo[1], gg); lo[2] = fminf(lo[2], b);
-            hi[0] = fmaxf(hi[0], r); hi[1] = fmaxf(hi[1], gg); hi[2] = fmaxf(hi[2], b);
-            keep = fmaxf(r, fmaxf(gg, b)) <= kLThr;  // L404-405
+            // one range over the three channels (3 instructions per pixel instead of 6): the CONC key
+            // range only needs an enclosing interval; lo[0] / hi[0] carry it, the caller copies it
+            const float mx = fmaxf(r, fmaxf(gg, b));
+            lo[0] = fminf(lo[0], fminf(r, fminf(gg, b)));
+            hi[0] = fmaxf(hi[0], mx);
+            keep = mx <= kLThr;  // L404-405
         }
         const float x = keep ? r - kLShift : 0.0f, y = keep ? gg - kLShift : 0.0f, z = keep ? b - kLShift : 0.0f;
         s[0] += keep ? 1.0f : 0.0f;
@@ -332,6 +376,8 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
+    lo[1] = lo[2] = lo[0];
+    hi[1] = hi[2] = hi[0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -352,43 +398,66 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
 }
 
 // ---- symmetric 3x3 eigen-decomposition (M4) ----------------------------------------------------
-// Cyclic Jacobi in double.  Columns sorted by ascending eigenvalue; each column's component of
-// largest magnitude is made positive (LAPACK leaves the sign implementation-defined; the result of
-// the normaliser does not depend on it for well-posed stain planes, SURVEY.md section 7 H-a).
-__device__ void eigh3(const double C[3][3], double V[3][3], double w[3]) {
-    double A[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { A[i][j] = C[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        const double diag = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
-        if (off <= 1e-300 || off <= 1e-22 * diag) break;
-        for (int p = 0; p < 2; ++p)
-            for (int q = p + 1; q < 3; ++q) {
-                if (A[p][q] == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 3; ++k) { double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
-                for (int k = 0; k < 3; ++k) { double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
-                for (int k = 0; k < 3; ++k) { double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
-            }
+// Cyclic Jacobi in float32 on the covariance scaled to unit trace (the covariance itself comes
+// from float64 moments).  It runs on one thread between two image phases, so its latency is on the
+// critical path of the fused pipeline: no divisions or square roots beyond MUFU.RCP / MUFU.RSQ, all
+// nine + nine entries in registers.  Eigenvector accuracy ~1e-6, the same as the reference's
+// float32 LAPACK eigh.  Columns sorted by ascending eigenvalue; each column's component of largest
+// magnitude is made positive (LAPACK leaves the sign implementation-defined; the result of the
+// normaliser does not depend on it for well-posed stain planes, SURVEY.md section 7 H-a).
+__device__ __forceinline__ void jacobi_rotate(float &app, float &aqq, float &apq, float &arp, float &arq, float &v0p, float &v0q, float &v1p, float &v1q, float &v2p, float &v2q) {
+    if (apq == 0.0f) return;
+    const float d = aqq - app, b2 = 2.0f * apq;
+    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = d / b2, without forming theta
+    const float t = copysignf(1.0f, d) * b2 * fast_rcp(fabsf(d) + sqrtf(__fmaf_rn(d, d, b2 * b2)));
+    const float c = rsqrtf(__fmaf_rn(t, t, 1.0f)), sn = t * c;
+    app = __fmaf_rn(-t, apq, app);
+    aqq = __fmaf_rn(t, apq, aqq);
+    apq = 0.0f;
+    float x = arp, y = arq;
+    arp = c * x - sn * y; arq = sn * x + c * y;
+    x = v0p; y = v0q; v0p = c * x - sn * y; v0q = sn * x + c * y;
+    x = v1p; y = v1q; v1p = c * x - sn * y; v1q = sn * x + c * y;
+    x = v2p; y = v2q; v2p = c * x - sn * y; v2q = sn * x + c * y;
+}
+
+// C symmetric (only the upper triangle is read); V columns = eigenvectors, w ascending.
+__device__ void eigh3(const double C[3][3], float V[3][3], float w[3]) {
+    const double tr = fabs(C[0][0]) + fabs(C[1][1]) + fabs(C[2][2]);
+    const double sc = tr > 0.0 ? 1.0 / tr : 1.0;
+    float a00 = (float)(C[0][0] * sc), a01 = (float)(C[0][1] * sc), a02 = (float)(C[0][2] * sc);
+    float a11 = (float)(C[1][1] * sc), a12 = (float)(C[1][2] * sc), a22 = (float)(C[2][2] * sc);
+    float v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const float off = fabsf(a01) + fabsf(a02) + fabsf(a12);
+        if (off <= 1e-12f * (fabsf(a00) + fabsf(a11) + fabsf(a22))) break;
+        jacobi_rotate(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21);  // (p, q) = (0, 1), r = 2
+        jacobi_rotate(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22);  // (0, 2), r = 1
+        jacobi_rotate(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22);  // (1, 2), r = 0
     }
-    int ord[3] = {0, 1, 2};
-    for (int i = 0; i < 3; ++i) w[i] = A[i][i];
-    for (int i = 0; i < 2; ++i)
-        for (int j = 0; j < 2 - i; ++j)
-            if (w[ord[j]] > w[ord[j + 1]]) { int t = ord[j]; ord[j] = ord[j + 1]; ord[j + 1] = t; }
-    double Vs[3][3], ws_[3];
+    float ev[3] = {a00, a11, a22};
+    float vc[3][3] = {{v00, v10, v20}, {v01, v11, v21}, {v02, v12, v22}};  // vc[j] = eigenvector j
+    // sorting network on three (value, vector) pairs
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const int i = pass == 1 ? 1 : 0;
+        if (ev[i] > ev[i + 1]) {
+            const float te = ev[i]; ev[i] = ev[i + 1]; ev[i + 1] = te;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const float tv = vc[i][k]; vc[i][k] = vc[i + 1][k]; vc[i + 1][k] = tv; }
+        }
+    }
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
-        ws_[j] = w[ord[j]];
-        int big = 0;
-        for (int i = 1; i < 3; ++i)
-            if (fabs(V[i][ord[j]]) > fabs(V[big][ord[j]])) big = i;
-        const double sg = V[big][ord[j]] < 0 ? -1.0 : 1.0;
-        for (int i = 0; i < 3; ++i) Vs[i][j] = sg * V[i][ord[j]];
+        const float ax = fabsf(vc[j][0]), ay = fabsf(vc[j][1]), az = fabsf(vc[j][2]);
+        const float big = ax >= ay ? (ax >= az ? vc[j][0] : vc[j][2]) : (ay >= az ? vc[j][1] : vc[j][2]);
+        const float sg = big < 0.0f ? -1.0f : 1.0f;
+        // one normalisation removes the drift of the float32 rotations
+        const float inv = rsqrtf(vc[j][0] * vc[j][0] + vc[j][1] * vc[j][1] + vc[j][2] * vc[j][2]) * sg;
+        w[j] = (float)((double)ev[j] * tr);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) V[i][j] = vc[j][i] * inv;
     }
-    for (int i = 0; i < 3; ++i) { w[i] = ws_[i]; for (int j = 0; j < 3; ++j) V[i][j] = Vs[i][j]; }
 }
 
 // Row j of a (2 x 3) linear map of OD, rewritten as an affine map of l:
@@ -408,17 +477,18 @@ __device__ void basis_from_moments(const double *m, SlotState &st) {
     st.n_sel = (long long)(n + 0.5);
     double C[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     if (n > 1.0) {  // unbiased covariance about the mean (L393-397); n <= 1 -> zeros (L395-396)
-        const double sx = m[1], sy = m[2], sz = m[3], d = n - 1.0;
-        C[0][0] = (m[4] - sx * sx / n) / d; C[0][1] = (m[5] - sx * sy / n) / d; C[0][2] = (m[6] - sx * sz / n) / d;
-        C[1][1] = (m[7] - sy * sy / n) / d; C[1][2] = (m[8] - sy * sz / n) / d; C[2][2] = (m[9] - sz * sz / n) / d;
+        const double sx = m[1], sy = m[2], sz = m[3], rn = 1.0 / n, rd = 1.0 / (n - 1.0);
+        C[0][0] = (m[4] - sx * sx * rn) * rd; C[0][1] = (m[5] - sx * sy * rn) * rd; C[0][2] = (m[6] - sx * sz * rn) * rd;
+        C[1][1] = (m[7] - sy * sy * rn) * rd; C[1][2] = (m[8] - sy * sz * rn) * rd; C[2][2] = (m[9] - sz * sz * rn) * rd;
         C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
     }
-    double V[3][3], w[3];
+    float V[3][3], w[3];
     eigh3(C, V, w);
     float e0[3], e1[3];
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-        st.e[i * 2] = e0[i] = (float)V[i][1];      // L415: middle eigenvector
-        st.e[i * 2 + 1] = e1[i] = (float)V[i][2];  //       largest
+        st.e[i * 2] = e0[i] = V[i][1];      // L415: middle eigenvector
+        st.e[i * 2 + 1] = e1[i] = V[i][2];  //       largest
     }
     od_map_to_l(e0, st.proj);
     od_map_to_l(e1, st.proj + 4);
@@ -555,27 +625,23 @@ __device__ __noinline__ void record_cell(const SlotState &st, int q, float v, un
 // the queue with all lanes busy every kDrainEvery iterations.  The common path per query is two
 // compares and a predicated increment.
 constexpr int kQueueCap = 1536;
-constexpr int kDrainEvery = 2;
 
+// Shared scratch of the resolve pass: the hit queues.
+struct ResolveSmem {
+    unsigned below[2];
+    unsigned qn[2];
+    float q[2][kQueueCap];
+};
+
+// Streams the groups first, first + stride, ... of one image.  `st` is a shared-memory copy of the
+// slot's state, `rs` shared scratch; results go to the slot's global cells / counters.
 template <typename T, bool VEC, int STAGE>
-__global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+__device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, const SlotState &st, ResolveSmem &rs, unsigned *h2, float *vmin, float *vmax, unsigned long long *counters) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    __shared__ float tab[256];
-    __shared__ unsigned s_below[2];
-    __shared__ unsigned s_qn[2];
-    __shared__ float s_q[2][kQueueCap];
-    __shared__ SlotState st;
-    Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = pooled ? 0 : slot0 + n;
-    if (threadIdx.x == 0) st = ws.state[slot];
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
-    if (threadIdx.x < 2) { s_below[threadIdx.x] = 0u; s_qn[threadIdx.x] = 0u; }
+    // a bracket holds <= ~3 % of the rows: 256 threads x kPix x kDrainEvery x 3 % stays below the queue capacity
+    constexpr int kDrainEvery = kPix >= 16 ? 4 : (kPix >= 4 ? 12 : 32);
+    if (threadIdx.x < 2) { rs.below[threadIdx.x] = 0u; rs.qn[threadIdx.x] = 0u; }
     __syncthreads();
-    unsigned *h2 = ws.hist2 + slot * 2 * kBins;
-    float *vmin = ws.vmin + slot * 2 * kBins;
-    float *vmax = ws.vmax + slot * 2 * kBins;
     // an open end is encoded by moving the bound to -/+ infinity for the below / inside tests;
     // record_cell sorts such values into the catch-all cells
     const float cl0 = st.open_lo[0] ? -INFINITY : st.lo_v[0], ch0 = st.open_hi[0] ? INFINITY : st.hi_v[0];
@@ -586,33 +652,53 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const int cnt = min((int)s_qn[q], kQueueCap);
-            for (int j = threadIdx.x; j < cnt; j += kThreads) record_cell(st, q, s_q[q][j], h2, vmin, vmax);
+            const int cnt = min((int)rs.qn[q], kQueueCap);
+            for (int j = threadIdx.x; j < cnt; j += kThreads) record_cell(st, q, rs.q[q][j], h2, vmin, vmax);
         }
         __syncthreads();
-        if (threadIdx.x < 2) s_qn[threadIdx.x] = 0u;
+        if (threadIdx.x < 2) rs.qn[threadIdx.x] = 0u;
         __syncthreads();
     };
-    auto hit = [&](int q, float v) {
-        const unsigned i = atomicAdd(&s_qn[q], 1u);
-        if (i < (unsigned)kQueueCap) s_q[q][i] = v;
-        else record_cell(st, q, v, h2, vmin, vmax);  // queue full (degenerate data): record directly
+    // Appends this thread's flagged values to the two queues: one shared-memory atomic per queue
+    // (plain atom.shared, not atomicAdd: the compiler's warp-aggregation of atomicAdd costs ~60
+    // instructions per call site) reserves the slots, then the values are stored.
+    auto append = [&](const float(&v0)[kPix], const float(&v1)[kPix], unsigned m0, unsigned m1) {
+        unsigned i0 = 0, i1 = 0;
+        if (m0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(i0) : "r"(smem_u32(&rs.qn[0])), "r"((unsigned)__popc(m0)) : "memory");
+        if (m1) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(i1) : "r"(smem_u32(&rs.qn[1])), "r"((unsigned)__popc(m1)) : "memory");
+#pragma unroll
+        for (int k = 0; k < kPix; ++k) {  // static indices keep v0 / v1 in registers
+            if (m0 & (1u << k)) {
+                if (i0 < (unsigned)kQueueCap) rs.q[0][i0] = v0[k];
+                else record_cell(st, 0, v0[k], h2, vmin, vmax);  // queue full (degenerate data): record directly
+                ++i0;
+            }
+            if (m1 & (1u << k)) {
+                if (i1 < (unsigned)kQueueCap) rs.q[1][i1] = v1[k];
+                else record_cell(st, 1, v1[k], h2, vmin, vmax);
+                ++i1;
+            }
+        }
     };
 
     unsigned below0 = 0u, below1 = 0u;
     int it = 0;
-    stream_groups<T, VEC>(
-        img + n * 3 * g.hw, g.hw, g.hw / kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab,
-        [&](const float(&l)[3][kPix], int64_t) {
+    stream_groups_uniform<T, VEC>(
+        image, hw, hw / kPix, first, stride, tab,
+        [&](const float(&l)[3][kPix], int64_t, bool valid) {
+            // per pixel: the ranked values, two predicated counts and the two in-bracket flags
+            float v0[kPix], v1[kPix];
+            unsigned m0 = 0u, m1 = 0u;
 #pragma unroll
             for (int k = 0; k < kPix; ++k) {
-                float v0, v1;
-                ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
-                below0 += v0 < cl0 ? 1u : 0u;  // NaN (masked row): every comparison is false
-                below1 += v1 < cl1 ? 1u : 0u;
-                if (v0 >= cl0 && v0 < ch0) hit(0, v0);
-                if (v1 >= cl1 && v1 < ch1) hit(1, v1);
+                ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0[k], v1[k]);
+                if (!valid) v0[k] = v1[k] = __int_as_float(0x7fc00000);
+                below0 += v0[k] < cl0 ? 1u : 0u;  // NaN (masked row / no group): every comparison is false
+                below1 += v1[k] < cl1 ? 1u : 0u;
+                m0 |= ((v0[k] >= cl0) & (v0[k] < ch0)) ? 1u << k : 0u;
+                m1 |= ((v1[k] >= cl1) & (v1[k] < ch1)) ? 1u << k : 0u;
             }
+            if (m0 | m1) append(v0, v1, m0, m1);
         },
         [&] {
             if (++it == kDrainEvery) { drain(); it = 0; }
@@ -621,45 +707,70 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__
     below0 = (unsigned)__reduce_add_sync(0xffffffffu, below0);
     below1 = (unsigned)__reduce_add_sync(0xffffffffu, below1);
     if ((threadIdx.x & 31) == 0) {
-        if (below0) atomicAdd(&s_below[0], below0);
-        if (below1) atomicAdd(&s_below[1], below1);
+        if (below0) atomicAdd(&rs.below[0], below0);
+        if (below1) atomicAdd(&rs.below[1], below1);
     }
     __syncthreads();
-    if (threadIdx.x < 2 && s_below[threadIdx.x]) atomicAdd(&ws.counters[slot * 8 + threadIdx.x], (unsigned long long)s_below[threadIdx.x]);
+    if (threadIdx.x < 2 && rs.below[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)rs.below[threadIdx.x]);
+}
+
+template <typename T, bool VEC, int STAGE>
+__global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+    __shared__ float tab[256];
+    __shared__ ResolveSmem rs;
+    __shared__ SlotState st;
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = pooled ? 0 : slot0 + n;
+    if (threadIdx.x == 0) st = ws.state[slot];
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
+    __syncthreads();
+    resolve_pass<T, VEC, STAGE>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, st, rs, ws.hist2 + slot * 2 * kBins, ws.vmin + slot * 2 * kBins, ws.vmax + slot * 2 * kBins, ws.counters + slot * 8);
 }
 
 // ---- per-slot rank searches (one CTA per slot) --------------------------------------------------
 // Nearest-rank index (torch_backend.py:L362-365): round_half_even(0.01 * q * (n - 1)), in double.
 __device__ __forceinline__ long long rank_index(double q, long long n) { return (long long)rint(0.01 * q * (double)(n - 1)); }
 
-// Inclusive prefix sums of a kBins histogram into shared `pre` (as unsigned long long).
-__device__ void block_prefix(const unsigned *__restrict__ hist, unsigned long long *pre) {
-    __shared__ unsigned long long part[kThreads];
-    constexpr int kPer = kBins / kThreads;
-    unsigned v[kPer];
-    unsigned long long s = 0;
+// Inclusive prefix sums of TWO kBins histograms side by side (threads 0..127: h0 -> pre[0],
+// threads 128..255: h1 -> pre[1]); 32 bins per thread, warp-shuffle scan, two barriers.  Counts are
+// 32-bit: a slot holds fewer than 2^32 rows.
+__device__ void dual_prefix(const unsigned *__restrict__ h0, const unsigned *__restrict__ h1, unsigned (*pre)[kBins]) {
+    __shared__ unsigned wsum[kThreads / 32];
+    const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4 *src = reinterpret_cast<const uint4 *>((half ? h1 : h0) + t * 32);
+    unsigned v[32];
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) { v[i] = hist[threadIdx.x * kPer + i]; s += v[i]; }
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < kThreads; o <<= 1) {  // Hillis-Steele scan over the 256 partial sums
-        const unsigned long long add = threadIdx.x >= o ? part[threadIdx.x - o] : 0ull;
-        __syncthreads();
-        part[threadIdx.x] += add;
-        __syncthreads();
+    for (int i = 0; i < 8; ++i) {
+        const uint4 x = __ldcg(src + i);
+        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
     }
-    unsigned long long run = part[threadIdx.x] - s;
+    unsigned sum = 0;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i) { run += v[i]; pre[threadIdx.x * kPer + i] = run; }
+    for (int i = 0; i < 32; ++i) { sum += v[i]; v[i] = sum; }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned base = incl - sum;
+    for (int k = half * 4; k < warp; ++k) base += wsum[k];
+    uint4 *dst = reinterpret_cast<uint4 *>(&pre[half][t * 32]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(v[4 * i] + base, v[4 * i + 1] + base, v[4 * i + 2] + base, v[4 * i + 3] + base);
     __syncthreads();
 }
 
 // Index of the bin holding 0-based rank k: first b with pre[b] > k.
-__device__ __forceinline__ int bin_of_rank(const unsigned long long *pre, long long k) {
+__device__ __forceinline__ int bin_of_rank(const unsigned *pre, long long k) {
     int lo = 0, hi = kBins - 1;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (pre[mid] > (unsigned long long)k) hi = mid; else lo = mid + 1;
+        if ((long long)pre[mid] > k) hi = mid; else lo = mid + 1;
     }
     return lo;
 }
@@ -671,96 +782,128 @@ __device__ __forceinline__ void diamond_to_unit(float p, double &c, double &s) {
     if (pd > 1.0) { x = -(pd - 1.0); y = 2.0 - pd; }
     else if (pd < -1.0) { x = 1.0 + pd; y = -2.0 - pd; }
     else { x = 1.0 - fabs(pd); y = pd; }
-    const double h = sqrt(x * x + y * y);
-    c = x / h; s = y / h;
+    const double h2 = x * x + y * y;  // in [0.5, 1]
+    double r = (double)rsqrtf((float)h2);
+    r = r * (1.5 - 0.5 * h2 * r * r);  // two Newton steps: 1e-7 -> 1e-14 -> exact to double rounding
+    r = r * (1.5 - 0.5 * h2 * r * r);
+    c = x * r; s = y * r;
 }
 
 // After the sample pass: wanted ranks and their brackets, converted from sample-key bins to the
 // value space of the full pass.
+// `st` is a shared-memory copy of the slot's state (read and updated by thread 0), `pre` a shared
+// scratch array of kBins prefix sums; global accumulators are read through L2 (__ldcg).
+__device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, unsigned (*pre)[kBins]) {
+    const unsigned *h = ws.hist1 + slot * 2 * kBins;
+    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
+    dual_prefix(h, stage == SX_STAGE_ANGLE ? h : h + kBins, pre);
+    if ((threadIdx.x & 127) == 0) {  // threads 0 and 128: one query each
+        const int q = threadIdx.x >> 7;
+        const int hq = stage == SX_STAGE_ANGLE ? 0 : q;
+        const long long n = stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all;
+        const double pct = stage == SX_STAGE_ANGLE ? (q == 0 ? 1.0 : 99.0) : 99.0;  // L421-422, L447-448
+        long long k = rank_index(pct, n);
+        if (k > n - 1) k = n - 1;
+        if (k < 0) k = 0;
+        st.rank[q] = k;
+        const long long m = (long long)__ldcg(ws.counters + slot * 8 + 2 + hq);
+        const int group_pixels = st.group_px > 0 ? st.group_px : 16;
+        // Inner cells 1 .. kBins-2 tile [lo, hi).  When the rank bracket reaches an end of the
+        // sample, the true order statistic may lie beyond the sample's extreme value: that
+        // side is left open and its values are collected in a catch-all cell (0 or kBins-1).
+        int b_lo = 0, b_hi = kBins - 1, open_lo = 1, open_hi = 1;
+        if (m > 0 && n > 0) {
+            long long r_lo, r_hi;
+            if (m >= n) {  // the "sample" is the whole slot: the coarse bin of rank k is certain
+                r_lo = r_hi = k;
+            } else {
+                // The pixels of one sampled group are neighbours and may be fully correlated:
+                // the binomial deviation is taken over groups, not pixels.
+                const double ks = (double)k * (double)m / (double)n;
+                const double sd = (double)sqrtf((float)((double)group_pixels * (double)m * (0.01 * pct) * (1.0 - 0.01 * pct)));
+                r_lo = (long long)floor(ks - kBracketZ * sd) - 2 * group_pixels;
+                r_hi = (long long)ceil(ks + kBracketZ * sd) + 2 * group_pixels;
+                open_lo = r_lo <= 0;
+                open_hi = r_hi >= m - 1;
+            }
+            b_lo = bin_of_rank(pre[q], r_lo < 0 ? 0 : (r_lo < m - 1 ? r_lo : m - 1));
+            b_hi = bin_of_rank(pre[q], r_hi < 0 ? 0 : (r_hi < m - 1 ? r_hi : m - 1));
+            if (m >= n) {
+                // exact bracket: one guard bin per side, because a value on a bin edge may round
+                // differently in the sample key and in the value-space test of the full pass
+                b_lo = b_lo > 0 ? b_lo - 1 : 0;
+                b_hi = b_hi < kBins - 1 ? b_hi + 1 : kBins - 1;
+                open_lo = b_lo == 0;
+                open_hi = b_hi == kBins - 1;
+            }
+        }
+        // sample keys -> values: ANGLE key = (p + 2) 2^22, CONC key = (C - c_lo) c_scale
+        double lo_v, hi_v;
+        if (stage == SX_STAGE_ANGLE) {
+            lo_v = (double)b_lo * (4096.0 / 4194304.0) - 2.0;
+            hi_v = (double)(b_hi + 1) * (4096.0 / 4194304.0) - 2.0;
+        } else {
+            const double bin_w = 4096.0 / (double)st.c_scale[q];
+            lo_v = (double)st.c_lo[q] + (double)b_lo * bin_w;
+            hi_v = (double)st.c_lo[q] + (double)(b_hi + 1) * bin_w;
+        }
+        st.lo_v[q] = (float)lo_v;
+        st.hi_v[q] = (float)hi_v;
+        st.inv_w[q] = __fdiv_rn((float)(kBins - 2), __fsub_rn(st.hi_v[q], st.lo_v[q]));
+        st.open_lo[q] = open_lo;
+        st.open_hi[q] = open_hi;
+    }
+    __syncthreads();
+}
+
+// Cooperative copy of a slot's state between global memory (through L2) and shared memory.
+__device__ __forceinline__ void load_state(SlotState *dst_smem, const SlotState *src) {
+    const unsigned *s32 = reinterpret_cast<const unsigned *>(src);
+    unsigned *d32 = reinterpret_cast<unsigned *>(dst_smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(SlotState) / 4); i += blockDim.x) d32[i] = __ldcg(s32 + i);
+    __syncthreads();
+}
+__device__ __forceinline__ void store_state(SlotState *dst, const SlotState *src_smem) {
+    __syncthreads();
+    const unsigned *s32 = reinterpret_cast<const unsigned *>(src_smem);
+    unsigned *d32 = reinterpret_cast<unsigned *>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(SlotState) / 4); i += blockDim.x) d32[i] = s32[i];
+}
+
 __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
-    __shared__ unsigned long long pre[kBins];
+    __shared__ __align__(16) unsigned pre[2][kBins];
+    __shared__ SlotState st;
     Ws ws(ws_base, slots);
     const int64_t slot = slot0 + blockIdx.x;
-    SlotState &st = ws.state[slot];
-    for (int q = 0; q < 2; ++q) {
-        const int hq = stage == SX_STAGE_ANGLE ? 0 : q;  // ANGLE: both queries read histogram 0
-        if (q == 0 || hq != 0) block_prefix(ws.hist1 + slot * 2 * kBins + hq * kBins, pre);
-        if (threadIdx.x == 0) {
-            const long long n = stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all;
-            const double pct = stage == SX_STAGE_ANGLE ? (q == 0 ? 1.0 : 99.0) : 99.0;  // L421-422, L447-448
-            long long k = rank_index(pct, n);
-            if (k > n - 1) k = n - 1;
-            if (k < 0) k = 0;
-            st.rank[q] = k;
-            const long long m = (long long)ws.counters[slot * 8 + 2 + hq];
-            const int group_pixels = st.group_px > 0 ? st.group_px : 16;
-            // Inner cells 1 .. kBins-2 tile [lo, hi).  When the rank bracket reaches an end of the
-            // sample, the true order statistic may lie beyond the sample's extreme value: that
-            // side is left open and its values are collected in a catch-all cell (0 or kBins-1).
-            int b_lo = 0, b_hi = kBins - 1, open_lo = 1, open_hi = 1;
-            if (m > 0 && n > 0) {
-                long long r_lo, r_hi;
-                if (m >= n) {  // the "sample" is the whole slot: the coarse bin of rank k is certain
-                    r_lo = r_hi = k;
-                    open_lo = open_hi = 0;
-                } else {
-                    // The pixels of one sampled group are neighbours and may be fully correlated:
-                    // the binomial deviation is taken over groups, not pixels.
-                    const double ks = (double)k * (double)m / (double)n;
-                    const double sd = sqrt((double)group_pixels * (double)m * (0.01 * pct) * (1.0 - 0.01 * pct));
-                    r_lo = (long long)floor(ks - kBracketZ * sd) - 2 * group_pixels;
-                    r_hi = (long long)ceil(ks + kBracketZ * sd) + 2 * group_pixels;
-                    open_lo = r_lo <= 0;
-                    open_hi = r_hi >= m - 1;
-                }
-                b_lo = bin_of_rank(pre, r_lo < 0 ? 0 : (r_lo < m - 1 ? r_lo : m - 1));
-                b_hi = bin_of_rank(pre, r_hi < 0 ? 0 : (r_hi < m - 1 ? r_hi : m - 1));
-            }
-            // sample keys -> values: ANGLE key = (p + 2) 2^22, CONC key = (C - c_lo) c_scale
-            double lo_v, hi_v;
-            if (stage == SX_STAGE_ANGLE) {
-                lo_v = (double)b_lo * 4096.0 / 4194304.0 - 2.0;
-                hi_v = (double)(b_hi + 1) * 4096.0 / 4194304.0 - 2.0;
-            } else {
-                lo_v = (double)st.c_lo[q] + (double)b_lo * 4096.0 / (double)st.c_scale[q];
-                hi_v = (double)st.c_lo[q] + (double)(b_hi + 1) * 4096.0 / (double)st.c_scale[q];
-            }
-            st.lo_v[q] = (float)lo_v;
-            st.hi_v[q] = (float)hi_v;
-            st.inv_w[q] = (float)((double)(kBins - 2) / ((double)st.hi_v[q] - (double)st.lo_v[q]));
-            st.open_lo[q] = open_lo;
-            st.open_hi[q] = open_hi;
-        }
-        __syncthreads();
-    }
+    load_state(&st, ws.state + slot);
+    bracket_slot(ws, slot, stage, st, pre);
+    store_state(ws.state + slot, &st);
 }
 
 // After the full pass: the order statistics; (ANGLE) HE, pinv, concentration maps; (CONC) maxC.
-__global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
-    __shared__ unsigned long long pre[kBins];
-    Ws ws(ws_base, slots);
-    const int64_t slot = slot0 + blockIdx.x;
-    SlotState &st = ws.state[slot];
+// `rg` = per-channel (-min l, max l) of the slot (global odrange, or the state's copy); sets st.miss.
+__device__ void select_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, const float *rg, unsigned (*pre)[kBins]) {
     const int64_t base = slot * 2 * kBins;
-    for (int q = 0; q < 2; ++q) {
-        block_prefix(ws.hist2 + base + q * kBins, pre);
-        if (threadIdx.x == 0) {
-            const long long inside = (long long)pre[kBins - 1];
-            long long k = st.rank[q] - (long long)ws.counters[slot * 8 + q];
-            if (k < 0 || k >= inside) {  // the rank fell outside the bracket (not expected): nearest edge
-                atomicOr(&ws.status[slot * 4], 1 << q);
-                k = k < 0 ? 0 : (inside > 0 ? inside - 1 : 0);
-            }
-            const int cell = bin_of_rank(pre, k);
-            const long long before = cell > 0 ? (long long)pre[cell - 1] : 0;
-            const long long cnt = (long long)pre[cell] - before;
-            const float lo = ws.vmin[base + q * kBins + cell], hi = ws.vmax[base + q * kBins + cell];
-            float v = lo;
-            if (cnt > 1 && hi > lo) v = lo + (hi - lo) * (float)((double)(k - before) / (double)(cnt - 1));
-            st.val[q] = v;
+    if (threadIdx.x == 0) st.miss = 0;
+    dual_prefix(ws.hist2 + base, ws.hist2 + base + kBins, pre);
+    if ((threadIdx.x & 127) == 0) {  // threads 0 and 128: one query each
+        const int q = threadIdx.x >> 7;
+        const long long inside = (long long)pre[q][kBins - 1];
+        long long k = st.rank[q] - (long long)__ldcg(ws.counters + slot * 8 + q);
+        if (k < 0 || k >= inside) {  // the rank fell outside the bracket (not expected): nearest edge
+            atomicOr(&ws.status[slot * 4], 1 << q);
+            st.miss = 1;
+            k = k < 0 ? 0 : (inside > 0 ? inside - 1 : 0);
         }
-        __syncthreads();
+        const int cell = bin_of_rank(pre[q], k);
+        const long long before = cell > 0 ? (long long)pre[q][cell - 1] : 0;
+        const long long cnt = (long long)pre[q][cell] - before;
+        const float lo = __ldcg(ws.vmin + base + q * kBins + cell), hi = __ldcg(ws.vmax + base + q * kBins + cell);
+        float v = lo;
+        if (cnt > 1 && hi > lo) v = lo + (hi - lo) * __fdiv_rn((float)(k - before), (float)(cnt - 1));
+        st.val[q] = v;
     }
+    __syncthreads();
     float *fit = ws.fit + slot * 8;
     if (threadIdx.x == 0) {
         if (stage == SX_STAGE_ANGLE) {
@@ -780,16 +923,15 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
             // M8 (L444): least squares via the normal equations, in double.
             double a00 = 0, a01 = 0, a11 = 0;
             for (int i = 0; i < 3; ++i) { a00 += (double)he[i * 2] * he[i * 2]; a01 += (double)he[i * 2] * he[i * 2 + 1]; a11 += (double)he[i * 2 + 1] * he[i * 2 + 1]; }
-            const double det = a00 * a11 - a01 * a01;
+            const double rdet = 1.0 / (a00 * a11 - a01 * a01);
             for (int i = 0; i < 3; ++i) {
-                st.pinv[i] = (float)((a11 * he[i * 2] - a01 * he[i * 2 + 1]) / det);
-                st.pinv[3 + i] = (float)((-a01 * he[i * 2] + a00 * he[i * 2 + 1]) / det);
+                st.pinv[i] = (float)((a11 * he[i * 2] - a01 * he[i * 2 + 1]) * rdet);
+                st.pinv[3 + i] = (float)((-a01 * he[i * 2] + a00 * he[i * 2 + 1]) * rdet);
             }
             // concentration rows as affine maps of l for the CONC stage
             od_map_to_l(st.pinv, st.proj);
             od_map_to_l(st.pinv + 3, st.proj + 4);
             // Key range of each concentration row from the per-channel range of l (interval arithmetic).
-            const float *rg = ws.odrange + slot * 8;
             for (int j = 0; j < 2; ++j) {
                 double lo = st.proj[j * 4 + 3], hi = lo;
                 for (int c = 0; c < 3; ++c) {
@@ -799,13 +941,26 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
                 const double pad = 1e-6 * (fabs(lo) + fabs(hi)) + 1e-12;
                 lo -= pad; hi += pad;
                 st.c_lo[j] = (float)lo;
-                st.c_scale[j] = (float)(16777216.0 / (hi - lo));
+                st.c_scale[j] = __fdiv_rn(16777216.0f, (float)(hi - lo));
             }
         } else {
             fit[6] = st.val[0];  // maxC (L447-449)
             fit[7] = st.val[1];
         }
     }
+}
+
+__global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t slots, int64_t slot0, int stage) {
+    __shared__ __align__(16) unsigned pre[2][kBins];
+    __shared__ SlotState st;
+    __shared__ float rg[8];
+    Ws ws(ws_base, slots);
+    const int64_t slot = slot0 + blockIdx.x;
+    const int64_t base = slot * 2 * kBins;
+    if (threadIdx.x < 8) rg[threadIdx.x] = ws.odrange[slot * 8 + threadIdx.x];
+    load_state(&st, ws.state + slot);
+    select_slot(ws, slot, stage, st, rg, pre);
+    store_state(ws.state + slot, &st);
     if (stage == SX_STAGE_ANGLE) {  // re-arm the slot's histograms and counters for the CONC stage
         for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
             ws.hist1[base + i] = 0u;
@@ -817,31 +972,15 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
     }
 }
 
-// ---- apply (M10) ---------------------------------------------------------------------------------
-// OD' = he_ref . diag(maxc_ref / maxC) . pinv . OD is a 3x3 map M3 of OD.  With l = log2(255x+1):
-//   240 exp(-OD'_c) = 2^( b_c + sum_k M3[c][k] l_k ),   b_c = log2(240) (1 - sum_k M3[c][k]).
-// OUT: 0 = uint8 (truncated), 1 = float32 in [0,255], 2 = float32 / 255 (normalize_to_0_1).
-template <typename T, bool VEC, int OUT>
-__global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ img, void *__restrict__ out_, PassGeom g, int64_t slot0, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, void *ws_base, int64_t slots) {
-    constexpr int kPix = Pix<T, VEC>::kPix;
-    __shared__ float tab[256];
-    __shared__ float unit_tab[256];
-    __shared__ float coef[12];
-    Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = slot0 + n;
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
-    if constexpr (OUT == 2 && sizeof(T) == 1)
-        for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
+// coef[c][0..2] = M3 row c, coef[c][3] = bias (shared memory, written by threads 0..2).
+template <typename T, int OUT>
+__device__ __forceinline__ void apply_coefficients(float *coef, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, const float *pinv, float maxc0, float maxc1) {
     if (threadIdx.x < 3) {
         const int c = threadIdx.x;
-        const SlotState &st = ws.state[slot];
-        const float *fit = ws.fit + slot * 8;
-        const float n0 = __fdiv_rn(maxc_ref[0], fit[6]), n1 = __fdiv_rn(maxc_ref[1], fit[7]);  // L452
+        const float n0 = __fdiv_rn(maxc_ref[0], maxc0), n1 = __fdiv_rn(maxc_ref[1], maxc1);  // L452
         float sum = 0.0f;
         for (int k = 0; k < 3; ++k) {
-            const float m = he_ref[c * 2] * n0 * st.pinv[k] + he_ref[c * 2 + 1] * n1 * st.pinv[3 + k];
+            const float m = he_ref[c * 2] * n0 * pinv[k] + he_ref[c * 2 + 1] * n1 * pinv[3 + k];
             coef[c * 4 + k] = m;
             sum += m;
         }
@@ -849,7 +988,12 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
         if (OUT == 2 && sizeof(T) == 4) bias -= 7.994353436858858f;  // log2(255): fold the /255
         coef[c * 4 + 3] = bias;
     }
-    __syncthreads();
+}
+
+// Streams the groups first, first + stride, ... of one image through the reconstruction.
+template <typename T, bool VEC, int OUT>
+__device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__restrict__ out_image, int64_t hw, int64_t first, int64_t stride, const float *tab, const float *unit_tab, const float *coef) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
     float A[3][4];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -857,31 +1001,31 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
         for (int k = 0; k < 4; ++k) A[c][k] = coef[c * 4 + k];
     const float top = (OUT == 2 && sizeof(T) == 4) ? 1.0f : 255.0f;  // clamp(.., 0, 255) (L459)
 
-    stream_groups<T, VEC>(img + n * 3 * g.hw, g.hw, g.hw / kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, [&](const float(&l)[3][kPix], int64_t gi) {
+    stream_groups<T, VEC>(image, hw, hw / kPix, first, stride, tab, [&](const float(&l)[3][kPix], int64_t gi) {
         float o[3][kPix];
 #pragma unroll
         for (int k = 0; k < kPix; ++k)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float e = __fmaf_rn(A[c][2], l[2][k], __fmaf_rn(A[c][1], l[1][k], __fmaf_rn(A[c][0], l[0][k], A[c][3])));
-                o[c][k] = fminf(exp2f(e), top);
+                o[c][k] = fminf(fast_ex2(e), top);
             }
-        const int64_t off = n * 3 * g.hw + gi * kPix;
+        const int64_t off = gi * kPix;
         if constexpr (OUT == 0) {
-            uint8_t *out = static_cast<uint8_t *>(out_) + off;
+            uint8_t *out = static_cast<uint8_t *>(out_image) + off;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if constexpr (VEC) {
                     unsigned w[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int k = 0; k < kPix; ++k) w[k >> 2] |= (unsigned)__float2int_rz(o[c][k]) << (8 * (k & 3));
-                    st_stream(reinterpret_cast<uint4 *>(out + c * g.hw), make_uint4(w[0], w[1], w[2], w[3]));
+                    st_stream(reinterpret_cast<uint4 *>(out + c * hw), make_uint4(w[0], w[1], w[2], w[3]));
                 } else {
-                    out[c * g.hw] = (uint8_t)__float2int_rz(o[c][0]);
+                    out[c * hw] = (uint8_t)__float2int_rz(o[c][0]);
                 }
             }
         } else {
-            float *out = static_cast<float *>(out_) + off;
+            float *out = static_cast<float *>(out_image) + off;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 if constexpr (sizeof(T) == 1) {
@@ -894,13 +1038,35 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
                 }
                 if constexpr (VEC) {
 #pragma unroll
-                    for (int k = 0; k < kPix; k += 4) st_stream(reinterpret_cast<float4 *>(out + c * g.hw + k), make_float4(o[c][k], o[c][k + 1], o[c][k + 2], o[c][k + 3]));
+                    for (int k = 0; k < kPix; k += 4) st_stream(reinterpret_cast<float4 *>(out + c * hw + k), make_float4(o[c][k], o[c][k + 1], o[c][k + 2], o[c][k + 3]));
                 } else {
-                    out[c * g.hw] = o[c][0];
+                    out[c * hw] = o[c][0];
                 }
             }
         }
     }, [] {});
+}
+
+// ---- apply (M10) ---------------------------------------------------------------------------------
+// OD' = he_ref . diag(maxc_ref / maxC) . pinv . OD is a 3x3 map M3 of OD.  With l = log2(255x+1):
+//   240 exp(-OD'_c) = 2^( b_c + sum_k M3[c][k] l_k ),   b_c = log2(240) (1 - sum_k M3[c][k]).
+// OUT: 0 = uint8 (truncated), 1 = float32 in [0,255], 2 = float32 / 255 (normalize_to_0_1).
+template <typename T, bool VEC, int OUT>
+__global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ img, void *__restrict__ out_, PassGeom g, int64_t slot0, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, void *ws_base, int64_t slots) {
+    __shared__ float tab[256];
+    __shared__ float unit_tab[256];
+    __shared__ float coef[12];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = slot0 + n;
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
+    if constexpr (OUT == 2 && sizeof(T) == 1)
+        for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
+    apply_coefficients<T, OUT>(coef, he_ref, maxc_ref, ws.state[slot].pinv, ws.fit[slot * 8 + 6], ws.fit[slot * 8 + 7]);
+    __syncthreads();
+    constexpr int kOutBytes = OUT == 0 ? 1 : 4;
+    apply_pass<T, VEC, OUT>(img + n * 3 * g.hw, static_cast<char *>(out_) + n * 3 * g.hw * kOutBytes, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, unit_tab, coef);
 }
 
 __global__ void init_kernel(void *ws_base, int64_t slots) {
@@ -919,10 +1085,312 @@ __global__ void init_kernel(void *ws_base, int64_t slots) {
     if (i < slots) {
         SlotState z = {};
         ws.state[i] = z;
+        ws.sync[i].arrive = 0u;
+        ws.sync[i].release = 0u;
+    }
+}
+
+// ---- fused per-image pipeline ----------------------------------------------------------------
+// The phase kernels above stream the whole batch from HBM once per phase (4 full passes + the
+// output).  Every Macenko statistic is per image, and a 1024 x 1024 float32 image is 12.6 MB, so
+// the passes after the first can be served by L2 -- provided that only a few images are in
+// flight: the B200's 126 MB L2 keeps ~36 MB of data that every SM touches (tools/l2probe.cu:
+// re-read bandwidth 14-17 TB/s up to 32 MB, HBM rate from 48 MB).
+//
+// One persistent cooperative kernel; its CTAs are split into TEAMS.  A team owns one image at a
+// time and takes it through every phase, separated by team-wide barriers (an arrival counter and a
+// release epoch in global memory, ~1.3 us per barrier for 148 CTAs).  The CTA that arrives LAST at
+// a barrier runs the per-image step that follows the phase (basis / bracket / rank search) while
+// the others wait for its release, so those steps need no launch and no second barrier.  Teams are
+// interleaved over the SMs (team = CTA index / team size with one CTA of each team per SM for
+// full-size teams), so while one team waits at a barrier the SM runs the others' phases: HBM
+// reads of one image, L2 passes of a second and the output stream of a third overlap.
+//
+// Differences from the phase kernels: moment partial sums are written per CTA and added by the
+// finishing CTA in a fixed order (an image's result does not depend on the batch around it or on
+// atomic ordering); the sample histogram is updated with global reductions directly (~30 groups per
+// CTA); a rank that falls outside its bracket triggers a second attempt whose "sample" is the whole
+// image (the bracket is then exact), so the result never silently degrades.
+struct FusedArgs {
+    const void *img;
+    void *out;
+    int64_t n_img, hw;
+    const float *he_ref, *maxc_ref;
+    void *ws;
+    int64_t slots;  // = teams
+    int team_size, teams;
+    unsigned long long *timeline;  // optional (development): %globaltimer stamps of team 0 / rank 0
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Team barrier, first half.  Returns true on the CTA that arrived last: it runs the step's epilogue
+// and then calls team_release(); every other CTA calls team_wait().
+__device__ __forceinline__ bool team_arrive(TeamSync *ts, unsigned step, int team_size, int *s_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // this CTA's results (ordered before by the barrier above) become visible
+        const unsigned old = atomicAdd(&ts->arrive, 1u);
+        const int last = old + 1u == step * (unsigned)team_size;
+        if (last) __threadfence();
+        *s_flag = last;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+__device__ __forceinline__ void team_release(TeamSync *ts, unsigned step) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ts->release), "r"(step) : "memory");
+    }
+}
+__device__ __forceinline__ void team_wait(const TeamSync *ts, unsigned step) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_u32(&ts->release) < step) __nanosleep(20);
+    }
+    __syncthreads();
+}
+
+// Sum of the team's per-CTA moment partials in a fixed order: thread (j, k), j = component 0..9,
+// k = 0..15, adds CTAs k, k + 16, ... sequentially, then a butterfly over the 16 lanes.
+__device__ __forceinline__ void reduce_partials(const double *partials, int team_size, double *tot) {
+    if (threadIdx.x < 160) {
+        const int j = threadIdx.x >> 4, k = threadIdx.x & 15;
+        double acc = 0.0;
+        for (int r = k; r < team_size; r += 16) acc += __ldcg(partials + r * 12 + j);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
+        if (k == 0) tot[j] = acc;
+    }
+    __syncthreads();
+}
+
+// The phases of the fused kernel are separate (non-inlined) functions: each gets its own register
+// allocation instead of sharing one with the state that lives across the whole pipeline.
+template <typename T, bool MASKED>
+__device__ __noinline__ void fused_moments(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, double (*red)[10], float (*redf)[6], double *my_partials, float *odrange) {
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    moments_stream<T, true, MASKED>(image, hw, first, stride, tab, acc, lo, hi);
+    lo[1] = lo[2] = lo[0];
+    hi[1] = hi[2] = hi[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (MASKED) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float x = warp_max(-lo[c]), y = warp_max(hi[c]);
+            if (lane == 0) { redf[warp][c] = x; redf[warp][3 + c] = y; }
+        }
+    }
+    block_sum10(acc, red);
+    if (threadIdx.x < 10) {
+        my_partials[threadIdx.x] = acc[0];
+    } else if (MASKED && threadIdx.x >= 32 && threadIdx.x < 38) {
+        const int i = threadIdx.x - 32;
+        float r = -INFINITY;
+        for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i]);
+        if (r > -INFINITY) atomic_max_f32(&odrange[i], r);  // [0..2] = -min l_c, [3..5] = max l_c
+    }
+}
+
+// Sample pass with direct global reductions (a CTA sees ~30 groups); sstride = 1 samples every group.
+template <typename T, int STAGE>
+__device__ __noinline__ void fused_sample(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, int64_t sstride, const float *tab, const SlotState &st, unsigned *h1, unsigned long long *counters) {
+    constexpr int kPix = Pix<T, true>::kPix;
+    const int64_t nsamp = (hw / kPix) / sstride;
+    const RankParams rp(st);
+    const float c_lo0 = st.c_lo[0], c_lo1 = st.c_lo[1], c_sc0 = st.c_scale[0], c_sc1 = st.c_scale[1];
+    unsigned cnt = 0;
+    for (int64_t i = first + threadIdx.x; i < nsamp; i += stride) {
+        const unsigned off = sstride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + 0x85ebca6bu), (unsigned)sstride) : 0u;
+        const int64_t gi = i * sstride + off;
+        float l[3][kPix];
+        load_l<T, true>(image + gi * kPix, hw, tab, l);
+#pragma unroll
+        for (int k = 0; k < kPix; ++k) {
+            float v0, v1;
+            ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
+            if (v0 != v0) continue;  // masked row
+            if (STAGE == SX_STAGE_ANGLE) {
+                atomicAdd(&h1[__float2int_rz(angle_key(v0)) >> 12], 1u);
+            } else {
+                atomicAdd(&h1[__float2int_rz(conc_key(v0, c_lo0, c_sc0)) >> 12], 1u);
+                atomicAdd(&h1[kBins + (__float2int_rz(conc_key(v1, c_lo1, c_sc1)) >> 12)], 1u);
+            }
+            ++cnt;
+        }
+    }
+    cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&counters[2], (unsigned long long)cnt);
+        if (STAGE == SX_STAGE_CONC) atomicAdd(&counters[3], (unsigned long long)cnt);
+    }
+}
+
+template <typename T, int STAGE>
+__device__ __noinline__ void fused_resolve(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, const SlotState &st, ResolveSmem &rs, unsigned *h2, float *vmin, float *vmax, unsigned long long *counters) {
+    resolve_pass<T, true, STAGE>(image, hw, first, stride, tab, st, rs, h2, vmin, vmax, counters);
+}
+
+template <typename T, int OUT>
+__device__ __noinline__ void fused_apply(const T *__restrict__ image, void *__restrict__ out_image, int64_t hw, int64_t first, int64_t stride, const float *tab, const float *unit_tab, const float *coef) {
+    apply_pass<T, true, OUT>(image, out_image, hw, first, stride, tab, unit_tab, coef);
+}
+
+// Re-arm cells [i0, i1) of a slot's histograms.
+__device__ __noinline__ void rearm_cells(unsigned *h2, float *vmin, float *vmax, int i0, int i1) {
+    for (int i = i0 + threadIdx.x; i < i1; i += kThreads) { h2[i] = 0u; vmin[i] = INFINITY; vmax[i] = -INFINITY; }
+}
+
+template <typename T, int OUT>
+__global__ void __launch_bounds__(kThreads, 3) fused_kernel(FusedArgs a) {
+    constexpr bool VEC = true;
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    constexpr int kOutBytes = OUT == 0 ? 1 : 4;
+    __shared__ float tab[256];
+    __shared__ float unit_tab[256];
+    __shared__ float coef[12];
+    __shared__ SlotState st;
+    __shared__ int s_flag;
+    __shared__ double tot[12];
+    __shared__ float s_rg[8];
+    __shared__ __align__(16) unsigned char scratch[kBins * 8];  // prefix sums (epilogues) / hit queues (resolve)
+    __shared__ double red[kThreads / 32][10];
+    __shared__ float redf[kThreads / 32][6];
+    static_assert(sizeof(ResolveSmem) <= kBins * 8, "scratch too small");
+    unsigned (*pre)[kBins] = reinterpret_cast<unsigned (*)[kBins]>(scratch);
+    ResolveSmem &rs = *reinterpret_cast<ResolveSmem *>(scratch);
+
+    const int team = blockIdx.x / a.team_size, rank = blockIdx.x % a.team_size;
+    if (team >= a.teams) return;
+    Ws ws(a.ws, a.slots);
+    const int64_t slot = team;
+    TeamSync *ts = ws.sync + slot;
+    unsigned step = 0;
+    int n_stamps = 0;
+    auto stamp = [&]() {
+        if (a.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 62) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            a.timeline[1 + n_stamps++] = t;
+            a.timeline[0] = (unsigned long long)n_stamps;
+        }
+    };
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
+    if constexpr (OUT == 2 && sizeof(T) == 1)
+        for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
+    __syncthreads();
+
+    const int64_t hw = a.hw;
+    const int64_t groups = hw / kPix;
+    const int64_t first = (int64_t)rank * kThreads, stride = (int64_t)a.team_size * kThreads;
+    unsigned *h1 = ws.hist1 + slot * 2 * kBins, *h2 = ws.hist2 + slot * 2 * kBins;
+    float *vmin = ws.vmin + slot * 2 * kBins, *vmax = ws.vmax + slot * 2 * kBins;
+    unsigned long long *counters = ws.counters + slot * 8;
+    double *my_partials = ws.partials + (slot * kMaxTeam + rank) * 12;
+    // this CTA's slice of the 2 * kBins cells, for re-arming the histograms between their uses
+    const int cells = 2 * kBins;
+    const int slice0 = (int)((int64_t)cells * rank / a.team_size), slice1 = (int)((int64_t)cells * (rank + 1) / a.team_size);
+
+    // one team barrier + epilogue on the last CTA; afterwards every CTA holds the new state in `st`
+    auto team_step = [&](auto &&epilogue) {
+        ++step;
+        if (team_arrive(ts, step, a.team_size, &s_flag)) {
+            load_state(&st, ws.state + slot);
+            epilogue();
+            store_state(ws.state + slot, &st);
+            team_release(ts, step);
+            __syncthreads();
+        } else {
+            team_wait(ts, step);
+            load_state(&st, ws.state + slot);
+        }
+    };
+
+    for (int64_t n = team; n < a.n_img; n += a.teams) {
+        const T *image = static_cast<const T *>(a.img) + n * 3 * hw;
+        stamp();
+
+        // ---- moments (M1-M3), masked; unmasked second pass when fewer than 3 rows pass (L409-410)
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0) fused_moments<T, true>(image, hw, first, stride, tab, red, redf, my_partials, ws.odrange + slot * 8);
+            else fused_moments<T, false>(image, hw, first, stride, tab, red, redf, my_partials, ws.odrange + slot * 8);
+            stamp();
+            team_step([&] {
+                reduce_partials(ws.partials + slot * kMaxTeam * 12, a.team_size, tot);
+                if (pass == 0 && threadIdx.x < 6) {  // keep the range for the CONC keys, re-arm the accumulator
+                    st.lrange[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
+                    ws.odrange[slot * 8 + threadIdx.x] = -INFINITY;
+                }
+                if (threadIdx.x == 0) {
+                    st.n_all = (long long)hw;
+                    st.redo = 0;
+                    if (pass == 0 && tot[0] < 3.0) {
+                        st.use_all = 1;
+                        st.redo = 1;
+                    } else {
+                        if (pass == 0) st.use_all = 0;
+                        basis_from_moments(tot, st);
+                    }
+                }
+                __syncthreads();
+            });
+            stamp();
+            if (!st.redo) break;
+        }
+
+        // ---- the two order-statistic stages: sample -> bracket -> resolve -> rank search
+        for (int stage = 0; stage < 2; ++stage) {
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                // sample pass (attempt 1: every group, which makes the bracket exact)
+                const int64_t sstride = (attempt == 0 && groups / kSampleGroups > 1) ? groups / kSampleGroups : 1;
+                if (stage == SX_STAGE_ANGLE) fused_sample<T, SX_STAGE_ANGLE>(image, hw, first, stride, sstride, tab, st, h1, counters);
+                else fused_sample<T, SX_STAGE_CONC>(image, hw, first, stride, sstride, tab, st, h1, counters);
+                rearm_cells(h2, vmin, vmax, slice0, slice1);  // cells of the resolve pass, last read one step ago
+                stamp();
+                team_step([&] {
+                    if (threadIdx.x == 0) st.group_px = kPix;
+                    __syncthreads();
+                    bracket_slot(ws, slot, stage, st, pre);
+                    __syncthreads();
+                });
+                stamp();
+                // full pass
+                if (stage == SX_STAGE_ANGLE) fused_resolve<T, SX_STAGE_ANGLE>(image, hw, first, stride, tab, st, rs, h2, vmin, vmax, counters);
+                else fused_resolve<T, SX_STAGE_CONC>(image, hw, first, stride, tab, st, rs, h2, vmin, vmax, counters);
+                for (int i = slice0 + threadIdx.x; i < slice1; i += kThreads) h1[i] = 0u;  // re-arm the sample histogram
+                stamp();
+                team_step([&] {
+                    if (threadIdx.x < 8) s_rg[threadIdx.x] = st.lrange[threadIdx.x];
+                    __syncthreads();
+                    select_slot(ws, slot, stage, st, s_rg, pre);
+                    __syncthreads();
+                    if (threadIdx.x < 8) counters[threadIdx.x] = 0ull;
+                });
+                stamp();
+                if (!st.miss) break;
+            }
+        }
+
+        // ---- reconstruction (M10)
+        apply_coefficients<T, OUT>(coef, a.he_ref, a.maxc_ref, st.pinv, __ldcg(ws.fit + slot * 8 + 6), __ldcg(ws.fit + slot * 8 + 7));
+        __syncthreads();
+        fused_apply<T, OUT>(image, static_cast<char *>(a.out) + n * 3 * hw * kOutBytes, hw, first, stride, tab, unit_tab, coef);
+        rearm_cells(h2, vmin, vmax, slice0, slice1);
+        stamp();
+        __syncthreads();  // `st` and `coef` are rewritten by the next image
     }
 }
 
 static int g_ctas_per_sm = 4;
+static int g_fused = 0;        // per-image fused pipeline for sx_macenko_transform (0: one launch per phase)
+static int g_fused_teams = 0;  // cap on the number of teams (0: as many as fit)
+static unsigned long long *g_fused_timeline = nullptr;  // development: device buffer of 64 u64 stamps
 static int64_t g_group_bytes = 0;  // 0: one launch per phase over the whole batch; > 0: L2-sized image groups
 
 static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_override = -1) {
@@ -969,11 +1437,54 @@ static bool images_vec_ok(const void *images, const void *out, int dtype, int64_
     return in_ok && (out == nullptr || aligned16(out));
 }
 
+extern "C" int sx_macenko_begin(void *workspace, int64_t slots, sx_stream_t stream);
+
+template <typename T, int OUT>
+static int launch_fused(const void *images, int64_t n, int64_t hw, const float *he_ref, const float *maxc_ref, void *out, void *workspace, cudaStream_t stream) {
+    int per_sm = 0;
+    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<T, OUT>, kThreads, 0));
+    SX_REQUIRE(per_sm > 0, "fused kernel does not fit on an SM");
+    const int sms = sm_count();
+    const int64_t resident = (int64_t)per_sm * sms;
+    // team size from the image size only (>= 4 groups per thread and phase), so that an image's
+    // arithmetic does not depend on the batch it is in
+    const int64_t groups = hw / Pix<T, true>::kPix;
+    int64_t team_size = groups / (kThreads * 4);
+    const int64_t cap = sms < kMaxTeam ? sms : kMaxTeam;
+    if (team_size > cap) team_size = cap;
+    if (team_size < 1) team_size = 1;
+    int64_t teams = resident / team_size;
+    if (teams > n) teams = n;
+    if (g_fused_teams > 0 && teams > g_fused_teams) teams = g_fused_teams;
+    if (teams < 1) teams = 1;
+    int rc;
+    if ((rc = sx_macenko_begin(workspace, teams, stream))) return rc;
+    FusedArgs a;
+    a.img = images; a.out = out; a.n_img = n; a.hw = hw; a.he_ref = he_ref; a.maxc_ref = maxc_ref;
+    a.ws = workspace; a.slots = teams; a.team_size = (int)team_size; a.teams = (int)teams;
+    a.timeline = g_fused_timeline;
+    void *args[] = {&a};
+    SX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(fused_kernel<T, OUT>), dim3((unsigned)(teams * team_size)), dim3(kThreads), args, 0, stream));
+    SX_LAUNCHED("macenko::fused_kernel");
+    return SX_OK;
+}
+
 extern "C" {
 
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t group_bytes) {
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
     if (group_bytes >= 0) g_group_bytes = group_bytes;
+    return SX_OK;
+}
+
+int sx_macenko_set_timeline(void *device_buffer_64_u64) {
+    g_fused_timeline = static_cast<unsigned long long *>(device_buffer_64_u64);
+    return SX_OK;
+}
+
+int sx_macenko_set_fused(int enabled, int max_teams) {
+    if (enabled >= 0) g_fused = enabled;
+    if (max_teams >= 0) g_fused_teams = max_teams;
     return SX_OK;
 }
 
@@ -1125,6 +1636,16 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     if (n == 0 || h * w == 0) return SX_OK;
     SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(n), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_macenko_workspace_bytes(n));
+    if (g_fused && images_vec_ok(images, out, dtype, h * w)) {
+        SX_REQUIRE(he_ref && maxc_ref && out, "NULL argument");
+        SX_REQUIRE(out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8), "uint8 output requires uint8 input");
+        const bool unit = out_scale != 1.0f;
+        SX_REQUIRE(!unit || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
+        cudaStream_t stream = static_cast<cudaStream_t>(s);
+        if (dtype == SX_F32) return unit ? launch_fused<float, 2>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream) : launch_fused<float, 1>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream);
+        if (out_dtype == SX_U8) return launch_fused<uint8_t, 0>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream);
+        return unit ? launch_fused<uint8_t, 2>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream) : launch_fused<uint8_t, 1>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream);
+    }
     const int64_t in_bytes = (dtype == SX_F32 ? 4 : 1) * 3 * h * w;
     const int64_t out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * h * w;
     int rc;

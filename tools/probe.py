@@ -159,17 +159,23 @@ def probe_macenko():
     phases_until(2, 0)
     print("status flags:", int(ws.region("status").abs().sum()))
     report("macenko apply f32 -> f32 unit", timeit(lambda: ws.apply(src, he, maxc, out, True)), 24 * px)
-    for group_mb in (0, 64):
-        lib.sx_macenko_set_tuning(-1, group_mb << 20)
-        report(f"macenko transform f32 64x1024^2 group={group_mb}MB", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
-    for ctas in (2, 8):
-        lib.sx_macenko_set_tuning(ctas, 64 << 20)
-        report(f"macenko transform f32 ctas/sm={ctas} group=64MB", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
-    lib.sx_macenko_set_tuning(4, 64 << 20)
+    lib.sx_macenko_set_fused(0, 0)
+    want = ops.macenko_transform(src, he, maxc, unit=True)
+    report("macenko transform f32 64x1024^2 phase kernels", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
+    for teams in (0, 1, 2, 3):
+        lib.sx_macenko_set_fused(1, teams)
+        got = ops.macenko_transform(src, he, maxc, unit=True)
+        err = float((got - want).abs().max())
+        report(f"macenko transform f32 FUSED teams<={teams} maxdiff={err:.2e}", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
+    lib.sx_macenko_set_fused(1, 0)
+    del want, got
     src8 = (src * 255).to(torch.uint8)
     del src, out
-    report("macenko transform u8 -> u8", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=False), steps=5), 6 * px)
-    report("macenko transform u8 -> f32 unit", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=True), steps=5), 15 * px)
+    for fused in (0, 1):
+        lib.sx_macenko_set_fused(fused, 0)
+        report(f"macenko transform u8 -> u8 fused={fused}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=False), steps=5), 6 * px)
+        report(f"macenko transform u8 -> f32 unit fused={fused}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=True), steps=5), 15 * px)
+    lib.sx_macenko_set_fused(1, 0)
 
 
 if __name__ == "__main__":
