@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = LIB_DIR / (src + ".o")
         if force or _stale(obj, [CSRC / src, *headers]):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SX_EXTRA_NVCC_FLAGS", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))

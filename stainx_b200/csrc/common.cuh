@@ -80,6 +80,9 @@ __device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
 // an SM can keep ~100 KB of HBM reads in flight (what its share of the bandwidth needs at 1.5-2 us
 // loaded latency) from a single CTA.  Addresses and sizes must be multiples of 16 bytes.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, unsigned a, unsigned b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -560,12 +560,17 @@ __global__ void __launch_bounds__(kStrThreads, 1) hist_u8_planar_streamed_kernel
 // SM), the warps read their vectors from the ring and only count.  No overflow handling: 32-bit
 // counters.  Per byte: PRMT + IMAD + ATOMS.POPC.INC.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLaneWarps = 5;
-constexpr int kLaneThreads = kLaneWarps * 32;
-constexpr int kLaneTileVecs = 1024;              // 16 KB tiles: 6.4 vectors per thread
-constexpr int kLanePerThread = (kLaneTileVecs + kLaneThreads - 1) / kLaneThreads;
-constexpr int kLaneStages = 4;
-constexpr int kLaneSmem = kLaneWarps * 32768 + kLaneStages * kLaneTileVecs * 16 + 2 * kLaneStages * 8 + 256 * 4;
+// Geometry variants (warps, vectors per tile, ring stages): 5 x 16 KB x 4 (the first cut) and
+// 6 warps with smaller tiles, which just fit the 227 KB of an SM.
+template <int W, int TV, int ST, bool COUNT = true, bool PRODUCER = false>
+struct LaneCfg {
+    static constexpr bool kCount = COUNT;        // false: ring streaming only (feed-rate measurement)
+    static constexpr bool kProducer = PRODUCER;  // an extra warp that only issues the TMA copies
+    static_assert((ST & (ST - 1)) == 0, "ring stages must be a power of two");
+    static constexpr int kWarps = W, kCountThreads = W * 32, kThreads = (W + (PRODUCER ? 1 : 0)) * 32, kTileVecs = TV, kStages = ST;
+    static constexpr int kPerThread = (TV + W * 32 - 1) / (W * 32);
+    static constexpr int kSmem = W * 32768 + ST * TV * 16 + 2 * ST * 8 + 256 * 4;
+};
 
 __device__ __forceinline__ void lane_count4(unsigned w, unsigned base) {  // base = &region[0][lane]
     const unsigned a0 = (w & 0xffu) * 128u + base;
@@ -578,7 +583,9 @@ __device__ __forceinline__ void lane_count4(unsigned w, unsigned base) {  // bas
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a3) : "memory");
 }
 
-__global__ void __launch_bounds__(kLaneThreads, 1) hist_u8_planar_lane_tma_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_tma_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    constexpr int kLaneWarps = Cfg::kWarps, kLaneThreads = Cfg::kThreads, kCountThreads = Cfg::kCountThreads, kLaneTileVecs = Cfg::kTileVecs, kLanePerThread = Cfg::kPerThread, kLaneStages = Cfg::kStages;
     extern __shared__ __align__(16) unsigned char smem_lane[];
     unsigned int *regions = reinterpret_cast<unsigned int *>(smem_lane);  // [warp][bin][lane]
     unsigned char *ring_mem = smem_lane + kLaneWarps * 32768;
@@ -590,7 +597,8 @@ __global__ void __launch_bounds__(kLaneThreads, 1) hist_u8_planar_lane_tma_kerne
     for (int i = threadIdx.x; i < kLaneWarps * 8192; i += kLaneThreads) regions[i] = 0u;
     for (int i = threadIdx.x; i < 256; i += kLaneThreads) hist32[i] = 0u;
     __syncthreads();
-    unsigned int *region = regions + warp * 8192;
+    const bool counting = warp < kLaneWarps;  // false on the producer warp
+    unsigned int *region = regions + (counting ? warp : 0) * 8192;
     const unsigned cbase = smem_u32(region) + (unsigned)lane * 4u;
 
     const int64_t per_channel = n_img * tiles_per_plane;
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__(kLaneThreads, 1) hist_u8_planar_lane_tma_kerne
     // lane-private counters of every warp -> global counts of channel c, re-zero
     auto flush = [&](int c) {
         __syncthreads();
-        for (int bin = lane; bin < 256; bin += 32) {  // lane j: bins j, j + 32, ...; rotated walk = no conflicts
+        for (int bin = lane; counting && bin < 256; bin += 32) {  // lane j: bins j, j + 32, ...; rotated walk = no conflicts
             unsigned sum = 0;
 #pragma unroll 8
             for (int k = 0; k < 32; ++k) {
@@ -631,30 +639,45 @@ __global__ void __launch_bounds__(kLaneThreads, 1) hist_u8_planar_lane_tma_kerne
         TileCursor pc, cc;
         pc.seek(hw, (int)tiles_per_plane, kLaneTileVecs, per_channel, seg);
         cc = pc;
-        int issued = 0;
-        for (int item = 0; item < n_items; ++item) {
-            if (threadIdx.x == 0) {
-                while (issued < n_items && issued - item < kLaneStages - 1) {
+        if (Cfg::kProducer && !counting) {
+            // producer warp: keep every free stage of the ring in flight (produce() waits for the
+            // consumers to release the stage's previous tenant)
+            if (lane == 0) {
+                for (int item = 0; item < n_items; ++item) {
                     tr.produce(base + pc.off, (unsigned)pc.vecs(kLaneTileVecs) * 16u);
                     pc.next(kLaneTileVecs);
-                    ++issued;
                 }
             }
-            const int nv = cc.vecs(kLaneTileVecs);
-            cc.next(kLaneTileVecs);
-            const uint4 *tile = tr.acquire();
-            uint4 v[kLanePerThread];
-            bool ok[kLanePerThread];
+            __syncwarp();
+        } else {
+            int issued = 0;
+            for (int item = 0; item < n_items; ++item) {
+                if (!Cfg::kProducer && threadIdx.x == 0) {
+                    while (issued < n_items && issued - item < kLaneStages - 1) {
+                        tr.produce(base + pc.off, (unsigned)pc.vecs(kLaneTileVecs) * 16u);
+                        pc.next(kLaneTileVecs);
+                        ++issued;
+                    }
+                }
+                const int nv = cc.vecs(kLaneTileVecs);
+                cc.next(kLaneTileVecs);
+                const uint4 *tile = tr.acquire();
+                uint4 v[kLanePerThread];
+                bool ok[kLanePerThread];
 #pragma unroll
-            for (int u = 0; u < kLanePerThread; ++u) {
-                const int idx = (int)threadIdx.x + u * kLaneThreads;
-                ok[u] = idx < nv;
-                if (ok[u]) v[u] = tile[idx];
+                for (int u = 0; u < kLanePerThread; ++u) {
+                    const int idx = (int)threadIdx.x + u * kCountThreads;
+                    ok[u] = idx < nv;
+                    if (ok[u]) v[u] = tile[idx];
+                }
+                tr.release();
+#pragma unroll
+                for (int u = 0; u < kLanePerThread; ++u)
+                    if (ok[u]) {
+                        if constexpr (Cfg::kCount) { lane_count4(v[u].x, cbase); lane_count4(v[u].y, cbase); lane_count4(v[u].z, cbase); lane_count4(v[u].w, cbase); }
+                        else if ((v[u].x ^ v[u].y ^ v[u].z ^ v[u].w) == 0x12345678u) lane_count4(v[u].x, cbase);
+                    }
             }
-            tr.release();
-#pragma unroll
-            for (int u = 0; u < kLanePerThread; ++u)
-                if (ok[u]) { lane_count4(v[u].x, cbase); lane_count4(v[u].y, cbase); lane_count4(v[u].z, cbase); lane_count4(v[u].w, cbase); }
         }
         flush(c);
         seg = seg_end;
@@ -1164,8 +1187,10 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
 }
 
 // ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
-static int g_hist_byte_counters = 0;  // counting scheme: 0 warp atomics (default: fastest on real images and within 10 % of the best on noise),
-                                      // 1 byte counters, 2 packed RED, 3 lane32, 4 streamed (TMA ring), 5 lane-private + TMA ring
+static int g_hist_byte_counters = 5;  // counting scheme of the uint8 planar histogram: 5 lane-private counters fed by a TMA ring
+                                      // (default for 16-byte aligned planes: data-independent), 0 warp-private atomics (any alignment;
+                                      // faster on constant images, slower on noise), 1 byte counters, 2 packed RED, 3 lane32, 4 streamed,
+                                      // 6 ring feed without counting (measurement only: wrong counts)
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 16;
 static int g_apply_pair_lut = 0;       // uint8 planar remap through the 2-byte table (persistent kernel)
@@ -1175,6 +1200,25 @@ static int g_apply_pair_lut = 0;       // uint8 planar remap through the 2-byte 
 
 using namespace sx;
 using namespace sx::hm;
+
+template <typename Cfg>
+static int launch_lane_tma_cfg(const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        attr_set = true;
+    }
+    const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
+    const unsigned grid = stream_grid(3 * n * tiles, 1);
+    hist_u8_planar_lane_tma_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
+    return SX_OK;
+}
+static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
+    // measured on B200, 64 x 3 x 1024^2 noise: <5 warps, 16 KB x 4, no producer> 80 us; <4, 24 KB x 4> 69 us;
+    // <4 + producer, 24 KB x 4> 62 us (default); <4 + producer, 12 KB x 8> 67 us; <3 + producer, 32 KB x 4> 75 us
+    if (mode == 6) return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, false, true>>(images, hw, n, cnt, stream);  // feed rate only: 40 us
+    return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, true, true>>(images, hw, n, cnt, stream);
+}
 
 extern "C" {
 
@@ -1212,15 +1256,9 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
         const int64_t items = n * tiles;
         // scheme 4 needs whole 128-bit vectors per plane; anything else takes the general kernel
         const bool planes_aligned = aligned16(images) && hw % 16 == 0;
-        if (g_hist_byte_counters == 5 && planes_aligned) {
-            static bool attr5_set = false;
-            if (!attr5_set) {
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLaneSmem));
-                attr5_set = true;
-            }
-            const int64_t tiles_l = max_i64(1, (hw / 16 + kLaneTileVecs - 1) / kLaneTileVecs);
-            const unsigned grid_l = stream_grid(3 * n * tiles_l, 1);
-            hist_u8_planar_lane_tma_kernel<<<grid_l, kLaneThreads, kLaneSmem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles_l, cnt);
+        // the persistent lane-private kernel zeroes 128 KB of counters per SM: worth it from ~8 MB of pixels on
+        if (g_hist_byte_counters >= 5 && planes_aligned && n * hw * 3 >= ((int64_t)8 << 20)) {
+            if (int rc = launch_lane_tma(g_hist_byte_counters, static_cast<const uint8_t *>(images), hw, n, cnt, stream)) return rc;
         } else if (g_hist_byte_counters == 4 && planes_aligned) {
             const int64_t tiles_s = max_i64(1, (hw / 16 + kStrTileVecs - 1) / kStrTileVecs);
             const unsigned grid_s = stream_grid(3 * n * tiles_s, 1);

@@ -58,22 +58,11 @@ struct SlotState {
     float pinv[6];        // (HE^T HE)^-1 HE^T, 2x3 row-major
     float c_lo[2];        // concentration key mapping: key = (C - c_lo) * c_scale
     float c_scale[2];
-    float lrange[8];      // fused pipeline: per-channel (-min l, max l) of the slot's rows (copy of odrange)
-    int redo;             // fused pipeline: moments must be re-accumulated without the mask
-    int miss;             // fused pipeline: a wanted rank fell outside its bracket in the last resolve
+    int miss;             // a wanted rank fell outside its bracket in the last resolve (also in STATUS)
 };
-
-// Team barrier of the fused pipeline: monotonically increasing arrival count and release epoch.
-struct TeamSync {
-    unsigned arrive;
-    unsigned pad0[31];
-    unsigned release;
-    unsigned pad1[31];
-};
-constexpr int kMaxTeam = 160;  // CTAs per team (<= SM count of the device)
 
 struct Layout {
-    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, partials, sync, total;
+    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, total;
     __host__ __device__ explicit Layout(int64_t slots) {
         int64_t o = 0;
         moments = o;  o += slots * 12 * 8;
@@ -86,8 +75,6 @@ struct Layout {
         fit = o;      o += slots * 8 * 4;
         status = o;   o += slots * 4 * 4;
         state = (o + 15) / 16 * 16; o = state + slots * (int64_t)sizeof(SlotState);
-        partials = (o + 15) / 16 * 16; o = partials + slots * kMaxTeam * 12 * 8;  // fused: per-CTA moment partial sums
-        sync = (o + 255) / 256 * 256; o = sync + slots * (int64_t)sizeof(TeamSync);
         total = (o + 255) / 256 * 256;
     }
 };
@@ -98,10 +85,9 @@ struct Ws {
     float *odrange;
     unsigned *hist1, *hist2;
     float *vmin, *vmax, *fit;
-    int *status;                   // [slot][4]: [0] bit q set = rank of query q fell outside its bracket
+    int *status;                   // [slot][4]: [0] bit q set = rank of query q fell outside its bracket;
+                                   // [1..3] CTAs of the slot's image that finished moments / resolve(ANGLE) / resolve(CONC)
     SlotState *state;
-    double *partials;              // [slot][kMaxTeam][12]
-    TeamSync *sync;                // [slot]
     __host__ __device__ Ws(void *base, int64_t slots) {
         Layout L(slots);
         char *b = static_cast<char *>(base);
@@ -115,8 +101,6 @@ struct Ws {
         fit = reinterpret_cast<float *>(b + L.fit);
         status = reinterpret_cast<int *>(b + L.status);
         state = reinterpret_cast<SlotState *>(b + L.state);
-        partials = reinterpret_cast<double *>(b + L.partials);
-        sync = reinterpret_cast<TeamSync *>(b + L.sync);
     }
 };
 
@@ -228,7 +212,7 @@ __device__ __forceinline__ void stream_groups_uniform(const T *__restrict__ imag
         if (gn < groups) nxt.load(image + gn * kPix, hw);
         float l[3][kPix];
         cur.to_l(tab, l);
-        body(l, gi, gi < groups);
+        body(l, gi < groups);
         every();
         cur = nxt;
         gi = gn;
@@ -620,17 +604,20 @@ __device__ __noinline__ void record_cell(const SlotState &st, int q, float v, un
 }
 
 // LEVEL 1 -- full pass: count the values below each bracket, resolve the bracket into kBins cells.
-// A bracket holds 1-3 % of the rows: rare per pixel, but not per warp (1 - 0.97^32 = 62 %), so a
-// hit is only appended to a shared-memory queue (one shared atomic + one store); the CTA drains
-// the queue with all lanes busy every kDrainEvery iterations.  The common path per query is two
-// compares and a predicated increment.
-constexpr int kQueueCap = 1536;
+// A bracket holds 1-3 % of the rows: rare per pixel, but not per warp (1 - 0.97^32 = 62 %), so
+// hits are appended to a shared-memory queue by the WARP: a shuffle scan of the lanes' hit counts,
+// one shared atomic per warp for the slots, predicated stores of (value, query) pairs -- no
+// divergent code in the streaming loop.  The CTA drains the queue into the slot's cells with all
+// lanes busy every kDrainEvery iterations.  The common path per query and pixel is a subtraction,
+// a shifted add (rows below) and two compares.
+constexpr int kQueueCap = 2048;
 
-// Shared scratch of the resolve pass: the hit queues.
+// Shared scratch of the resolve pass: the hit queue.
 struct ResolveSmem {
     unsigned below[2];
-    unsigned qn[2];
-    float q[2][kQueueCap];
+    unsigned qn;
+    unsigned pad;
+    uint2 q[kQueueCap];  // (value bits, query)
 };
 
 // Streams the groups first, first + stride, ... of one image.  `st` is a shared-memory copy of the
@@ -638,67 +625,77 @@ struct ResolveSmem {
 template <typename T, bool VEC, int STAGE>
 __device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, const SlotState &st, ResolveSmem &rs, unsigned *h2, float *vmin, float *vmax, unsigned long long *counters) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    // a bracket holds <= ~3 % of the rows: 256 threads x kPix x kDrainEvery x 3 % stays below the queue capacity
+    // ~2.5 % of the pixel-queries hit: 256 threads x kPix x kDrainEvery x 2.5 % stays far below the queue capacity
     constexpr int kDrainEvery = kPix >= 16 ? 4 : (kPix >= 4 ? 12 : 32);
-    if (threadIdx.x < 2) { rs.below[threadIdx.x] = 0u; rs.qn[threadIdx.x] = 0u; }
+    if (threadIdx.x < 2) rs.below[threadIdx.x] = 0u;
+    if (threadIdx.x == 2) rs.qn = 0u;
     __syncthreads();
     // an open end is encoded by moving the bound to -/+ infinity for the below / inside tests;
     // record_cell sorts such values into the catch-all cells
     const float cl0 = st.open_lo[0] ? -INFINITY : st.lo_v[0], ch0 = st.open_hi[0] ? INFINITY : st.hi_v[0];
     const float cl1 = st.open_lo[1] ? -INFINITY : st.lo_v[1], ch1 = st.open_hi[1] ? INFINITY : st.hi_v[1];
     const RankParams rp(st);
+    const int lane = threadIdx.x & 31;
+    const unsigned q_addr = smem_u32(rs.q), qn_addr = smem_u32(&rs.qn);
 
     auto drain = [&]() {
         __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int cnt = min((int)rs.qn[q], kQueueCap);
-            for (int j = threadIdx.x; j < cnt; j += kThreads) record_cell(st, q, rs.q[q][j], h2, vmin, vmax);
+        const int cnt = min((int)rs.qn, kQueueCap);
+        for (int j = threadIdx.x; j < cnt; j += kThreads) {
+            const uint2 e = rs.q[j];
+            record_cell(st, (int)e.y, __uint_as_float(e.x), h2, vmin, vmax);
         }
         __syncthreads();
-        if (threadIdx.x < 2) rs.qn[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) rs.qn = 0u;
         __syncthreads();
-    };
-    // Appends this thread's flagged values to the two queues: one shared-memory atomic per queue
-    // (plain atom.shared, not atomicAdd: the compiler's warp-aggregation of atomicAdd costs ~60
-    // instructions per call site) reserves the slots, then the values are stored.
-    auto append = [&](const float(&v0)[kPix], const float(&v1)[kPix], unsigned m0, unsigned m1) {
-        unsigned i0 = 0, i1 = 0;
-        if (m0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(i0) : "r"(smem_u32(&rs.qn[0])), "r"((unsigned)__popc(m0)) : "memory");
-        if (m1) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(i1) : "r"(smem_u32(&rs.qn[1])), "r"((unsigned)__popc(m1)) : "memory");
-#pragma unroll
-        for (int k = 0; k < kPix; ++k) {  // static indices keep v0 / v1 in registers
-            if (m0 & (1u << k)) {
-                if (i0 < (unsigned)kQueueCap) rs.q[0][i0] = v0[k];
-                else record_cell(st, 0, v0[k], h2, vmin, vmax);  // queue full (degenerate data): record directly
-                ++i0;
-            }
-            if (m1 & (1u << k)) {
-                if (i1 < (unsigned)kQueueCap) rs.q[1][i1] = v1[k];
-                else record_cell(st, 1, v1[k], h2, vmin, vmax);
-                ++i1;
-            }
-        }
     };
 
     unsigned below0 = 0u, below1 = 0u;
     int it = 0;
     stream_groups_uniform<T, VEC>(
         image, hw, hw / kPix, first, stride, tab,
-        [&](const float(&l)[3][kPix], int64_t, bool valid) {
-            // per pixel: the ranked values, two predicated counts and the two in-bracket flags
+        [&](const float(&l)[3][kPix], bool valid) {
             float v0[kPix], v1[kPix];
-            unsigned m0 = 0u, m1 = 0u;
+            unsigned m0 = 0u, m1 = 0u, b0 = 0u, b1 = 0u;
 #pragma unroll
             for (int k = 0; k < kPix; ++k) {
                 ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0[k], v1[k]);
-                if (!valid) v0[k] = v1[k] = __int_as_float(0x7fc00000);
-                below0 += v0[k] < cl0 ? 1u : 0u;  // NaN (masked row / no group): every comparison is false
-                below1 += v1[k] < cl1 ? 1u : 0u;
+                // NaN (masked row): every comparison is false, NaN - x keeps a clear sign bit
+                b0 += __float_as_uint(__fsub_rn(v0[k], cl0)) >> 31;  // v < cl (cl = -inf: never)
+                b1 += __float_as_uint(__fsub_rn(v1[k], cl1)) >> 31;
                 m0 |= ((v0[k] >= cl0) & (v0[k] < ch0)) ? 1u << k : 0u;
                 m1 |= ((v1[k] >= cl1) & (v1[k] < ch1)) ? 1u << k : 0u;
             }
-            if (m0 | m1) append(v0, v1, m0, m1);
+            if (!valid) m0 = m1 = b0 = b1 = 0u;  // a thread without a group
+            below0 += b0;
+            below1 += b1;
+            if (__any_sync(0xffffffffu, (m0 | m1) != 0u)) {  // warp-uniform
+                const int c = __popc(m0) + __popc(m1);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned base = 0u;
+                if (lane == 31) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(qn_addr), "r"((unsigned)total) : "memory");
+                base = __shfl_sync(0xffffffffu, base, 31);
+                if (base + (unsigned)total <= (unsigned)kQueueCap) {  // warp-uniform
+                    unsigned addr = q_addr + (base + (unsigned)(incl - c)) * 8u;  // shared-space byte address
+#pragma unroll
+                    for (int k = 0; k < kPix; ++k) {  // static indices keep v0 / v1 in registers
+                        if (m0 & (1u << k)) { st_shared_v2(addr, __float_as_uint(v0[k]), 0u); addr += 8u; }
+                        if (m1 & (1u << k)) { st_shared_v2(addr, __float_as_uint(v1[k]), 1u); addr += 8u; }
+                    }
+                } else {  // queue full (degenerate data): record directly
+#pragma unroll
+                    for (int k = 0; k < kPix; ++k) {
+                        if (m0 & (1u << k)) record_cell(st, 0, v0[k], h2, vmin, vmax);
+                        if (m1 & (1u << k)) record_cell(st, 1, v1[k], h2, vmin, vmax);
+                    }
+                }
+            }
         },
         [&] {
             if (++it == kDrainEvery) { drain(); it = 0; }
@@ -706,12 +703,73 @@ __device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_
     drain();
     below0 = (unsigned)__reduce_add_sync(0xffffffffu, below0);
     below1 = (unsigned)__reduce_add_sync(0xffffffffu, below1);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (below0) atomicAdd(&rs.below[0], below0);
         if (below1) atomicAdd(&rs.below[1], below1);
     }
     __syncthreads();
     if (threadIdx.x < 2 && rs.below[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)rs.below[threadIdx.x]);
+}
+
+// The sample pass of one slot run by ONE CTA (epilogues of the per-image transform pipeline):
+// the same hashed groups and keys as sample_kernel, histograms in shared memory (zeroed by the
+// caller), sampled rows counted in *s_cnt.  Loads are issued four groups at a time.
+template <typename T, bool VEC, int STAGE>
+__device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw, const float *tab, const SlotState &st, unsigned (*hist)[kBins], unsigned *s_cnt) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
+    constexpr int kBatch = 4;
+    const int64_t groups = hw / kPix;
+    const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
+    const int64_t nsamp = groups / stride;
+    const RankParams rp(st);
+    const float c_lo0 = st.c_lo[0], c_lo1 = st.c_lo[1], c_sc0 = st.c_scale[0], c_sc1 = st.c_scale[1];
+    unsigned cnt = 0;
+    for (int64_t i0 = threadIdx.x; i0 < nsamp; i0 += (int64_t)kBatch * kThreads) {
+        RawGroup<T, VEC> raw[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const int64_t i = i0 + (int64_t)b * kThreads;
+            if (i < nsamp) {
+                const unsigned off = stride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + 0x85ebca6bu), (unsigned)stride) : 0u;
+                raw[b].load(image + (i * stride + off) * kPix, hw);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            if (i0 + (int64_t)b * kThreads >= nsamp) break;
+            float l[3][kPix];
+            raw[b].to_l(tab, l);
+#pragma unroll
+            for (int k = 0; k < kPix; ++k) {
+                float v0, v1;
+                ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
+                if (v0 != v0) continue;  // masked row
+                if (STAGE == SX_STAGE_ANGLE) {
+                    atomicAdd(&hist[0][__float2int_rz(angle_key(v0)) >> 12], 1u);
+                } else {
+                    atomicAdd(&hist[0][__float2int_rz(conc_key(v0, c_lo0, c_sc0)) >> 12], 1u);
+                    atomicAdd(&hist[1][__float2int_rz(conc_key(v1, c_lo1, c_sc1)) >> 12], 1u);
+                }
+                ++cnt;
+            }
+        }
+    }
+    cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_cnt, cnt);
+}
+
+// Counts this CTA as finished with phase `phase` (0 moments, 1 resolve ANGLE, 2 resolve CONC) of
+// its slot; true on the CTA that finishes last, which then sees every other CTA's results.
+__device__ __forceinline__ bool last_cta_of_slot(int *status, int64_t slot, int phase, int ctas, int *s_flag) {
+    __threadfence();  // this thread's global atomics / stores are visible before the count below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(&status[slot * 4 + 1 + phase], 1);
+        *s_flag = old == ctas - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    return *s_flag != 0;
 }
 
 template <typename T, bool VEC, int STAGE>
@@ -735,15 +793,18 @@ __device__ __forceinline__ long long rank_index(double q, long long n) { return 
 
 // Inclusive prefix sums of TWO kBins histograms side by side (threads 0..127: h0 -> pre[0],
 // threads 128..255: h1 -> pre[1]); 32 bins per thread, warp-shuffle scan, two barriers.  Counts are
-// 32-bit: a slot holds fewer than 2^32 rows.
-__device__ void dual_prefix(const unsigned *__restrict__ h0, const unsigned *__restrict__ h1, unsigned (*pre)[kBins]) {
+// 32-bit: a slot holds fewer than 2^32 rows.  SMEM: the sources are shared memory (else global,
+// read through L2).  Every source word is read before the first barrier and `pre` is written after
+// it, so the sources may alias `pre` (in-place scan).
+template <bool SMEM>
+__device__ void dual_prefix(const unsigned *h0, const unsigned *h1, unsigned (*pre)[kBins]) {
     __shared__ unsigned wsum[kThreads / 32];
     const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint4 *src = reinterpret_cast<const uint4 *>((half ? h1 : h0) + t * 32);
     unsigned v[32];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint4 x = __ldcg(src + i);
+        const uint4 x = SMEM ? src[i] : __ldcg(src + i);
         v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
     }
     unsigned sum = 0;
@@ -793,20 +854,17 @@ __device__ __forceinline__ void diamond_to_unit(float p, double &c, double &s) {
 // value space of the full pass.
 // `st` is a shared-memory copy of the slot's state (read and updated by thread 0), `pre` a shared
 // scratch array of kBins prefix sums; global accumulators are read through L2 (__ldcg).
-__device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, unsigned (*pre)[kBins]) {
-    const unsigned *h = ws.hist1 + slot * 2 * kBins;
-    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
-    dual_prefix(h, stage == SX_STAGE_ANGLE ? h : h + kBins, pre);
+// `pre[q]` = inclusive prefix sums of query q's sample histogram, m[q] = rows in that sample.
+__device__ void bracket_from_prefix(int stage, SlotState &st, unsigned (*pre)[kBins], long long m0, long long m1) {
     if ((threadIdx.x & 127) == 0) {  // threads 0 and 128: one query each
         const int q = threadIdx.x >> 7;
-        const int hq = stage == SX_STAGE_ANGLE ? 0 : q;
         const long long n = stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all;
         const double pct = stage == SX_STAGE_ANGLE ? (q == 0 ? 1.0 : 99.0) : 99.0;  // L421-422, L447-448
         long long k = rank_index(pct, n);
         if (k > n - 1) k = n - 1;
         if (k < 0) k = 0;
         st.rank[q] = k;
-        const long long m = (long long)__ldcg(ws.counters + slot * 8 + 2 + hq);
+        const long long m = q ? m1 : m0;
         const int group_pixels = st.group_px > 0 ? st.group_px : 16;
         // Inner cells 1 .. kBins-2 tile [lo, hi).  When the rank bracket reaches an end of the
         // sample, the true order statistic may lie beyond the sample's extreme value: that
@@ -856,6 +914,16 @@ __device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &s
     __syncthreads();
 }
 
+// The same from the global sample histograms of the phase-level API.
+__device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, unsigned (*pre)[kBins]) {
+    const unsigned *h = ws.hist1 + slot * 2 * kBins;
+    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
+    dual_prefix<false>(h, stage == SX_STAGE_ANGLE ? h : h + kBins, pre);
+    const long long m0 = (long long)__ldcg(ws.counters + slot * 8 + 2);
+    const long long m1 = stage == SX_STAGE_ANGLE ? m0 : (long long)__ldcg(ws.counters + slot * 8 + 3);
+    bracket_from_prefix(stage, st, pre, m0, m1);
+}
+
 // Cooperative copy of a slot's state between global memory (through L2) and shared memory.
 __device__ __forceinline__ void load_state(SlotState *dst_smem, const SlotState *src) {
     const unsigned *s32 = reinterpret_cast<const unsigned *>(src);
@@ -885,7 +953,7 @@ __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_
 __device__ void select_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, const float *rg, unsigned (*pre)[kBins]) {
     const int64_t base = slot * 2 * kBins;
     if (threadIdx.x == 0) st.miss = 0;
-    dual_prefix(ws.hist2 + base, ws.hist2 + base + kBins, pre);
+    dual_prefix<false>(ws.hist2 + base, ws.hist2 + base + kBins, pre);
     if ((threadIdx.x & 127) == 0) {  // threads 0 and 128: one query each
         const int q = threadIdx.x >> 7;
         const long long inside = (long long)pre[q][kBins - 1];
@@ -1069,6 +1137,168 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
     apply_pass<T, VEC, OUT>(img + n * 3 * g.hw, static_cast<char *>(out_) + n * 3 * g.hw * kOutBytes, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, unit_tab, coef);
 }
 
+// ---- per-image transform pipeline ------------------------------------------------------------
+// sx_macenko_transform runs FOUR launches over the batch (moments, resolve ANGLE, resolve CONC,
+// apply).  Everything between two passes of an image -- eigen-decomposition, the sample pass and
+// its bracket, the rank search, HE / pinv -- is done by the CTA that finishes the image's pass LAST
+// (a counter per slot and phase), while the CTAs of other images are still streaming: no
+// one-CTA-per-slot launches, no extra launch latencies.  The arithmetic is the phase-level API's
+// (same functions, same sample groups), so both paths give the same statistics.
+#ifdef SX_MK_TIMING
+#define SX_STAMP(ptr, i)                                             \
+    do {                                                              \
+        if (threadIdx.x == 0) {                                       \
+            unsigned long long _t;                                    \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));  \
+            (ptr)[i] = _t;                                            \
+        }                                                             \
+    } while (0)
+#else
+#define SX_STAMP(ptr, i) do {} while (0)
+#endif
+
+struct EpiSmem {
+    SlotState st;
+    unsigned s_cnt;
+    int s_flag;
+    float rg[8];
+    double tot[12];
+};
+
+// Shared scratch large enough for the resolve queues and for two kBins histograms / prefix arrays.
+constexpr int kScratchBytes = 2 * kBins * 4 > (int)sizeof(ResolveSmem) ? 2 * kBins * 4 : (int)sizeof(ResolveSmem);
+
+// Zeroes the two shared histograms, runs the sample pass of `stage` and turns it into brackets.
+template <typename T, bool VEC, int STAGE>
+__device__ __forceinline__ void sample_and_bracket(const T *__restrict__ image, int64_t hw, const float *tab, EpiSmem &ep, unsigned (*hist)[kBins]) {
+    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) hist[0][i] = 0u;
+    if (threadIdx.x == 0) {
+        ep.s_cnt = 0u;
+        ep.st.group_px = Pix<T, VEC>::kPix;
+    }
+    __syncthreads();
+    sample_slot<T, VEC, STAGE>(image, hw, tab, ep.st, hist, &ep.s_cnt);
+    __syncthreads();
+#ifdef SX_MK_TIMING
+    if (threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); ep.tot[11] = __longlong_as_double((long long)_t); }
+#endif
+    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
+    dual_prefix<true>(hist[0], STAGE == SX_STAGE_ANGLE ? hist[0] : hist[1], hist);
+    bracket_from_prefix(STAGE, ep.st, hist, (long long)ep.s_cnt, (long long)ep.s_cnt);
+}
+
+// Register budget of the pipeline kernels: the streaming loop must keep >= 3 (uint8 x 16 pixels: 2)
+// CTAs resident per SM; the once-per-image epilogue may spill.
+template <typename T, bool VEC>
+constexpr int kMinCtas = (VEC && sizeof(T) == 1) ? 2 : 3;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_moments_kernel(const T *__restrict__ img, PassGeom g, void *ws_base, int64_t slots) {
+    __shared__ float tab[256];
+    __shared__ double red[kThreads / 32][10];
+    __shared__ float redf[kThreads / 32][6];
+    __shared__ EpiSmem ep;
+    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = n;
+    const T *image = img + n * 3 * g.hw;
+    if constexpr (sizeof(T) == 1) {
+        build_l_table(tab);
+        __syncthreads();
+    }
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    moments_stream<T, VEC, true>(image, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const float a = warp_max(-lo[0]), b = warp_max(hi[0]);
+        if (lane == 0) { redf[warp][0] = a; redf[warp][1] = b; }
+    }
+    block_sum10(acc, red);
+    if (threadIdx.x < 10) {
+        if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
+        const int i = threadIdx.x - 32;  // [0..2] = -min l (one range for the three channels), [3..5] = max l
+        float r = -INFINITY;
+        for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i / 3]);
+        atomic_max_f32(&ws.odrange[slot * 8 + i], r);
+    }
+    if (!last_cta_of_slot(ws.status, slot, 0, g.cpi, &ep.s_flag)) return;
+
+    // ---- the image's moments are complete: basis (M3-M4), fallback (L409-410), ANGLE brackets
+    SX_STAMP(ws.counters + slot * 8, 4);
+    if (threadIdx.x < 10) ep.tot[threadIdx.x] = __ldcg(ws.moments + slot * 12 + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        SlotState z = {};
+        ep.st = z;
+        ep.st.n_all = (long long)g.hw;
+        ep.st.use_all = ep.tot[0] < 3.0;
+        if (!ep.st.use_all) basis_from_moments(ep.tot, ep.st);
+    }
+    __syncthreads();
+    if (ep.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
+        double acc2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float lo2[3] = {0, 0, 0}, hi2[3] = {0, 0, 0};
+        moments_stream<T, VEC, false>(image, g.hw, 0, kThreads, tab, acc2, lo2, hi2);
+        __syncthreads();
+        block_sum10(acc2, red);
+        if (threadIdx.x < 10) ep.tot[threadIdx.x] = acc2[0];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = ep.tot[i];
+            basis_from_moments(ep.tot, ep.st);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ws.moments[slot * 12 + 10] = (double)g.hw;
+    SX_STAMP(ws.counters + slot * 8, 5);
+    sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, g.hw, tab, ep, reinterpret_cast<unsigned (*)[kBins]>(scratch));
+    SX_STAMP(ws.counters + slot * 8, 6);
+    store_state(ws.state + slot, &ep.st);
+    SX_STAMP(ws.counters + slot * 8, 7);
+#ifdef SX_MK_TIMING
+    if (threadIdx.x == 0) ws.moments[slot * 12 + 11] = ep.tot[11];
+#endif
+}
+
+template <typename T, bool VEC, int STAGE>
+__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_resolve_kernel(const T *__restrict__ img, PassGeom g, void *ws_base, int64_t slots) {
+    __shared__ float tab[256];
+    __shared__ EpiSmem ep;
+    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = n;
+    const T *image = img + n * 3 * g.hw;
+    const int64_t base = slot * 2 * kBins;
+    if constexpr (sizeof(T) == 1) build_l_table(tab);
+    load_state(&ep.st, ws.state + slot);
+    resolve_pass<T, VEC, STAGE>(image, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, ep.st, *reinterpret_cast<ResolveSmem *>(scratch), ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
+    if (!last_cta_of_slot(ws.status, slot, 1 + STAGE, g.cpi, &ep.s_flag)) return;
+
+    // ---- the image's cells are complete: rank search; ANGLE: HE, pinv (M7-M8), CONC brackets
+    unsigned (*pre)[kBins] = reinterpret_cast<unsigned (*)[kBins]>(scratch);
+    if (threadIdx.x < 8) ep.rg[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
+    __syncthreads();
+    select_slot(ws, slot, STAGE, ep.st, ep.rg, pre);
+    __syncthreads();
+    if constexpr (STAGE == SX_STAGE_ANGLE) {
+        // re-arm the slot's cells and counters for the CONC stage
+        for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+            ws.hist2[base + i] = 0u;
+            ws.vmin[base + i] = INFINITY;
+            ws.vmax[base + i] = -INFINITY;
+        }
+        if (threadIdx.x < 4) ws.counters[slot * 8 + threadIdx.x] = 0ull;
+        sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, g.hw, tab, ep, pre);
+    }
+    store_state(ws.state + slot, &ep.st);
+}
+
 __global__ void init_kernel(void *ws_base, int64_t slots) {
     Ws ws(ws_base, slots);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1085,313 +1315,11 @@ __global__ void init_kernel(void *ws_base, int64_t slots) {
     if (i < slots) {
         SlotState z = {};
         ws.state[i] = z;
-        ws.sync[i].arrive = 0u;
-        ws.sync[i].release = 0u;
-    }
-}
-
-// ---- fused per-image pipeline ----------------------------------------------------------------
-// The phase kernels above stream the whole batch from HBM once per phase (4 full passes + the
-// output).  Every Macenko statistic is per image, and a 1024 x 1024 float32 image is 12.6 MB, so
-// the passes after the first can be served by L2 -- provided that only a few images are in
-// flight: the B200's 126 MB L2 keeps ~36 MB of data that every SM touches (tools/l2probe.cu:
-// re-read bandwidth 14-17 TB/s up to 32 MB, HBM rate from 48 MB).
-//
-// One persistent cooperative kernel; its CTAs are split into TEAMS.  A team owns one image at a
-// time and takes it through every phase, separated by team-wide barriers (an arrival counter and a
-// release epoch in global memory, ~1.3 us per barrier for 148 CTAs).  The CTA that arrives LAST at
-// a barrier runs the per-image step that follows the phase (basis / bracket / rank search) while
-// the others wait for its release, so those steps need no launch and no second barrier.  Teams are
-// interleaved over the SMs (team = CTA index / team size with one CTA of each team per SM for
-// full-size teams), so while one team waits at a barrier the SM runs the others' phases: HBM
-// reads of one image, L2 passes of a second and the output stream of a third overlap.
-//
-// Differences from the phase kernels: moment partial sums are written per CTA and added by the
-// finishing CTA in a fixed order (an image's result does not depend on the batch around it or on
-// atomic ordering); the sample histogram is updated with global reductions directly (~30 groups per
-// CTA); a rank that falls outside its bracket triggers a second attempt whose "sample" is the whole
-// image (the bracket is then exact), so the result never silently degrades.
-struct FusedArgs {
-    const void *img;
-    void *out;
-    int64_t n_img, hw;
-    const float *he_ref, *maxc_ref;
-    void *ws;
-    int64_t slots;  // = teams
-    int team_size, teams;
-    unsigned long long *timeline;  // optional (development): %globaltimer stamps of team 0 / rank 0
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Team barrier, first half.  Returns true on the CTA that arrived last: it runs the step's epilogue
-// and then calls team_release(); every other CTA calls team_wait().
-__device__ __forceinline__ bool team_arrive(TeamSync *ts, unsigned step, int team_size, int *s_flag) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();  // this CTA's results (ordered before by the barrier above) become visible
-        const unsigned old = atomicAdd(&ts->arrive, 1u);
-        const int last = old + 1u == step * (unsigned)team_size;
-        if (last) __threadfence();
-        *s_flag = last;
-    }
-    __syncthreads();
-    return *s_flag != 0;
-}
-__device__ __forceinline__ void team_release(TeamSync *ts, unsigned step) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ts->release), "r"(step) : "memory");
-    }
-}
-__device__ __forceinline__ void team_wait(const TeamSync *ts, unsigned step) {
-    if (threadIdx.x == 0) {
-        while (ld_acquire_u32(&ts->release) < step) __nanosleep(20);
-    }
-    __syncthreads();
-}
-
-// Sum of the team's per-CTA moment partials in a fixed order: thread (j, k), j = component 0..9,
-// k = 0..15, adds CTAs k, k + 16, ... sequentially, then a butterfly over the 16 lanes.
-__device__ __forceinline__ void reduce_partials(const double *partials, int team_size, double *tot) {
-    if (threadIdx.x < 160) {
-        const int j = threadIdx.x >> 4, k = threadIdx.x & 15;
-        double acc = 0.0;
-        for (int r = k; r < team_size; r += 16) acc += __ldcg(partials + r * 12 + j);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
-        if (k == 0) tot[j] = acc;
-    }
-    __syncthreads();
-}
-
-// The phases of the fused kernel are separate (non-inlined) functions: each gets its own register
-// allocation instead of sharing one with the state that lives across the whole pipeline.
-template <typename T, bool MASKED>
-__device__ __noinline__ void fused_moments(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, double (*red)[10], float (*redf)[6], double *my_partials, float *odrange) {
-    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    moments_stream<T, true, MASKED>(image, hw, first, stride, tab, acc, lo, hi);
-    lo[1] = lo[2] = lo[0];
-    hi[1] = hi[2] = hi[0];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (MASKED) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float x = warp_max(-lo[c]), y = warp_max(hi[c]);
-            if (lane == 0) { redf[warp][c] = x; redf[warp][3 + c] = y; }
-        }
-    }
-    block_sum10(acc, red);
-    if (threadIdx.x < 10) {
-        my_partials[threadIdx.x] = acc[0];
-    } else if (MASKED && threadIdx.x >= 32 && threadIdx.x < 38) {
-        const int i = threadIdx.x - 32;
-        float r = -INFINITY;
-        for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i]);
-        if (r > -INFINITY) atomic_max_f32(&odrange[i], r);  // [0..2] = -min l_c, [3..5] = max l_c
-    }
-}
-
-// Sample pass with direct global reductions (a CTA sees ~30 groups); sstride = 1 samples every group.
-template <typename T, int STAGE>
-__device__ __noinline__ void fused_sample(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, int64_t sstride, const float *tab, const SlotState &st, unsigned *h1, unsigned long long *counters) {
-    constexpr int kPix = Pix<T, true>::kPix;
-    const int64_t nsamp = (hw / kPix) / sstride;
-    const RankParams rp(st);
-    const float c_lo0 = st.c_lo[0], c_lo1 = st.c_lo[1], c_sc0 = st.c_scale[0], c_sc1 = st.c_scale[1];
-    unsigned cnt = 0;
-    for (int64_t i = first + threadIdx.x; i < nsamp; i += stride) {
-        const unsigned off = sstride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + 0x85ebca6bu), (unsigned)sstride) : 0u;
-        const int64_t gi = i * sstride + off;
-        float l[3][kPix];
-        load_l<T, true>(image + gi * kPix, hw, tab, l);
-#pragma unroll
-        for (int k = 0; k < kPix; ++k) {
-            float v0, v1;
-            ranked_values<STAGE>(rp, l[0][k], l[1][k], l[2][k], v0, v1);
-            if (v0 != v0) continue;  // masked row
-            if (STAGE == SX_STAGE_ANGLE) {
-                atomicAdd(&h1[__float2int_rz(angle_key(v0)) >> 12], 1u);
-            } else {
-                atomicAdd(&h1[__float2int_rz(conc_key(v0, c_lo0, c_sc0)) >> 12], 1u);
-                atomicAdd(&h1[kBins + (__float2int_rz(conc_key(v1, c_lo1, c_sc1)) >> 12)], 1u);
-            }
-            ++cnt;
-        }
-    }
-    cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) {
-        atomicAdd(&counters[2], (unsigned long long)cnt);
-        if (STAGE == SX_STAGE_CONC) atomicAdd(&counters[3], (unsigned long long)cnt);
-    }
-}
-
-template <typename T, int STAGE>
-__device__ __noinline__ void fused_resolve(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, const SlotState &st, ResolveSmem &rs, unsigned *h2, float *vmin, float *vmax, unsigned long long *counters) {
-    resolve_pass<T, true, STAGE>(image, hw, first, stride, tab, st, rs, h2, vmin, vmax, counters);
-}
-
-template <typename T, int OUT>
-__device__ __noinline__ void fused_apply(const T *__restrict__ image, void *__restrict__ out_image, int64_t hw, int64_t first, int64_t stride, const float *tab, const float *unit_tab, const float *coef) {
-    apply_pass<T, true, OUT>(image, out_image, hw, first, stride, tab, unit_tab, coef);
-}
-
-// Re-arm cells [i0, i1) of a slot's histograms.
-__device__ __noinline__ void rearm_cells(unsigned *h2, float *vmin, float *vmax, int i0, int i1) {
-    for (int i = i0 + threadIdx.x; i < i1; i += kThreads) { h2[i] = 0u; vmin[i] = INFINITY; vmax[i] = -INFINITY; }
-}
-
-template <typename T, int OUT>
-__global__ void __launch_bounds__(kThreads, 3) fused_kernel(FusedArgs a) {
-    constexpr bool VEC = true;
-    constexpr int kPix = Pix<T, VEC>::kPix;
-    constexpr int kOutBytes = OUT == 0 ? 1 : 4;
-    __shared__ float tab[256];
-    __shared__ float unit_tab[256];
-    __shared__ float coef[12];
-    __shared__ SlotState st;
-    __shared__ int s_flag;
-    __shared__ double tot[12];
-    __shared__ float s_rg[8];
-    __shared__ __align__(16) unsigned char scratch[kBins * 8];  // prefix sums (epilogues) / hit queues (resolve)
-    __shared__ double red[kThreads / 32][10];
-    __shared__ float redf[kThreads / 32][6];
-    static_assert(sizeof(ResolveSmem) <= kBins * 8, "scratch too small");
-    unsigned (*pre)[kBins] = reinterpret_cast<unsigned (*)[kBins]>(scratch);
-    ResolveSmem &rs = *reinterpret_cast<ResolveSmem *>(scratch);
-
-    const int team = blockIdx.x / a.team_size, rank = blockIdx.x % a.team_size;
-    if (team >= a.teams) return;
-    Ws ws(a.ws, a.slots);
-    const int64_t slot = team;
-    TeamSync *ts = ws.sync + slot;
-    unsigned step = 0;
-    int n_stamps = 0;
-    auto stamp = [&]() {
-        if (a.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && n_stamps < 62) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            a.timeline[1 + n_stamps++] = t;
-            a.timeline[0] = (unsigned long long)n_stamps;
-        }
-    };
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
-    if constexpr (OUT == 2 && sizeof(T) == 1)
-        for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
-    __syncthreads();
-
-    const int64_t hw = a.hw;
-    const int64_t groups = hw / kPix;
-    const int64_t first = (int64_t)rank * kThreads, stride = (int64_t)a.team_size * kThreads;
-    unsigned *h1 = ws.hist1 + slot * 2 * kBins, *h2 = ws.hist2 + slot * 2 * kBins;
-    float *vmin = ws.vmin + slot * 2 * kBins, *vmax = ws.vmax + slot * 2 * kBins;
-    unsigned long long *counters = ws.counters + slot * 8;
-    double *my_partials = ws.partials + (slot * kMaxTeam + rank) * 12;
-    // this CTA's slice of the 2 * kBins cells, for re-arming the histograms between their uses
-    const int cells = 2 * kBins;
-    const int slice0 = (int)((int64_t)cells * rank / a.team_size), slice1 = (int)((int64_t)cells * (rank + 1) / a.team_size);
-
-    // one team barrier + epilogue on the last CTA; afterwards every CTA holds the new state in `st`
-    auto team_step = [&](auto &&epilogue) {
-        ++step;
-        if (team_arrive(ts, step, a.team_size, &s_flag)) {
-            load_state(&st, ws.state + slot);
-            epilogue();
-            store_state(ws.state + slot, &st);
-            team_release(ts, step);
-            __syncthreads();
-        } else {
-            team_wait(ts, step);
-            load_state(&st, ws.state + slot);
-        }
-    };
-
-    for (int64_t n = team; n < a.n_img; n += a.teams) {
-        const T *image = static_cast<const T *>(a.img) + n * 3 * hw;
-        stamp();
-
-        // ---- moments (M1-M3), masked; unmasked second pass when fewer than 3 rows pass (L409-410)
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 0) fused_moments<T, true>(image, hw, first, stride, tab, red, redf, my_partials, ws.odrange + slot * 8);
-            else fused_moments<T, false>(image, hw, first, stride, tab, red, redf, my_partials, ws.odrange + slot * 8);
-            stamp();
-            team_step([&] {
-                reduce_partials(ws.partials + slot * kMaxTeam * 12, a.team_size, tot);
-                if (pass == 0 && threadIdx.x < 6) {  // keep the range for the CONC keys, re-arm the accumulator
-                    st.lrange[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
-                    ws.odrange[slot * 8 + threadIdx.x] = -INFINITY;
-                }
-                if (threadIdx.x == 0) {
-                    st.n_all = (long long)hw;
-                    st.redo = 0;
-                    if (pass == 0 && tot[0] < 3.0) {
-                        st.use_all = 1;
-                        st.redo = 1;
-                    } else {
-                        if (pass == 0) st.use_all = 0;
-                        basis_from_moments(tot, st);
-                    }
-                }
-                __syncthreads();
-            });
-            stamp();
-            if (!st.redo) break;
-        }
-
-        // ---- the two order-statistic stages: sample -> bracket -> resolve -> rank search
-        for (int stage = 0; stage < 2; ++stage) {
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                // sample pass (attempt 1: every group, which makes the bracket exact)
-                const int64_t sstride = (attempt == 0 && groups / kSampleGroups > 1) ? groups / kSampleGroups : 1;
-                if (stage == SX_STAGE_ANGLE) fused_sample<T, SX_STAGE_ANGLE>(image, hw, first, stride, sstride, tab, st, h1, counters);
-                else fused_sample<T, SX_STAGE_CONC>(image, hw, first, stride, sstride, tab, st, h1, counters);
-                rearm_cells(h2, vmin, vmax, slice0, slice1);  // cells of the resolve pass, last read one step ago
-                stamp();
-                team_step([&] {
-                    if (threadIdx.x == 0) st.group_px = kPix;
-                    __syncthreads();
-                    bracket_slot(ws, slot, stage, st, pre);
-                    __syncthreads();
-                });
-                stamp();
-                // full pass
-                if (stage == SX_STAGE_ANGLE) fused_resolve<T, SX_STAGE_ANGLE>(image, hw, first, stride, tab, st, rs, h2, vmin, vmax, counters);
-                else fused_resolve<T, SX_STAGE_CONC>(image, hw, first, stride, tab, st, rs, h2, vmin, vmax, counters);
-                for (int i = slice0 + threadIdx.x; i < slice1; i += kThreads) h1[i] = 0u;  // re-arm the sample histogram
-                stamp();
-                team_step([&] {
-                    if (threadIdx.x < 8) s_rg[threadIdx.x] = st.lrange[threadIdx.x];
-                    __syncthreads();
-                    select_slot(ws, slot, stage, st, s_rg, pre);
-                    __syncthreads();
-                    if (threadIdx.x < 8) counters[threadIdx.x] = 0ull;
-                });
-                stamp();
-                if (!st.miss) break;
-            }
-        }
-
-        // ---- reconstruction (M10)
-        apply_coefficients<T, OUT>(coef, a.he_ref, a.maxc_ref, st.pinv, __ldcg(ws.fit + slot * 8 + 6), __ldcg(ws.fit + slot * 8 + 7));
-        __syncthreads();
-        fused_apply<T, OUT>(image, static_cast<char *>(a.out) + n * 3 * hw * kOutBytes, hw, first, stride, tab, unit_tab, coef);
-        rearm_cells(h2, vmin, vmax, slice0, slice1);
-        stamp();
-        __syncthreads();  // `st` and `coef` are rewritten by the next image
     }
 }
 
 static int g_ctas_per_sm = 4;
-static int g_fused = 0;        // per-image fused pipeline for sx_macenko_transform (0: one launch per phase)
-static int g_fused_teams = 0;  // cap on the number of teams (0: as many as fit)
-static unsigned long long *g_fused_timeline = nullptr;  // development: device buffer of 64 u64 stamps
-static int64_t g_group_bytes = 0;  // 0: one launch per phase over the whole batch; > 0: L2-sized image groups
+static int g_phase_kernels = 0;  // development: sx_macenko_transform through the phase-level API (one launch per step)
 
 static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_override = -1) {
     PassGeom g;
@@ -1437,54 +1365,11 @@ static bool images_vec_ok(const void *images, const void *out, int dtype, int64_
     return in_ok && (out == nullptr || aligned16(out));
 }
 
-extern "C" int sx_macenko_begin(void *workspace, int64_t slots, sx_stream_t stream);
-
-template <typename T, int OUT>
-static int launch_fused(const void *images, int64_t n, int64_t hw, const float *he_ref, const float *maxc_ref, void *out, void *workspace, cudaStream_t stream) {
-    int per_sm = 0;
-    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_kernel<T, OUT>, kThreads, 0));
-    SX_REQUIRE(per_sm > 0, "fused kernel does not fit on an SM");
-    const int sms = sm_count();
-    const int64_t resident = (int64_t)per_sm * sms;
-    // team size from the image size only (>= 4 groups per thread and phase), so that an image's
-    // arithmetic does not depend on the batch it is in
-    const int64_t groups = hw / Pix<T, true>::kPix;
-    int64_t team_size = groups / (kThreads * 4);
-    const int64_t cap = sms < kMaxTeam ? sms : kMaxTeam;
-    if (team_size > cap) team_size = cap;
-    if (team_size < 1) team_size = 1;
-    int64_t teams = resident / team_size;
-    if (teams > n) teams = n;
-    if (g_fused_teams > 0 && teams > g_fused_teams) teams = g_fused_teams;
-    if (teams < 1) teams = 1;
-    int rc;
-    if ((rc = sx_macenko_begin(workspace, teams, stream))) return rc;
-    FusedArgs a;
-    a.img = images; a.out = out; a.n_img = n; a.hw = hw; a.he_ref = he_ref; a.maxc_ref = maxc_ref;
-    a.ws = workspace; a.slots = teams; a.team_size = (int)team_size; a.teams = (int)teams;
-    a.timeline = g_fused_timeline;
-    void *args[] = {&a};
-    SX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(fused_kernel<T, OUT>), dim3((unsigned)(teams * team_size)), dim3(kThreads), args, 0, stream));
-    SX_LAUNCHED("macenko::fused_kernel");
-    return SX_OK;
-}
-
 extern "C" {
 
-int sx_macenko_set_tuning(int ctas_per_sm, int64_t group_bytes) {
+int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels) {
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
-    if (group_bytes >= 0) g_group_bytes = group_bytes;
-    return SX_OK;
-}
-
-int sx_macenko_set_timeline(void *device_buffer_64_u64) {
-    g_fused_timeline = static_cast<unsigned long long *>(device_buffer_64_u64);
-    return SX_OK;
-}
-
-int sx_macenko_set_fused(int enabled, int max_teams) {
-    if (enabled >= 0) g_fused = enabled;
-    if (max_teams >= 0) g_fused_teams = max_teams;
+    if (phase_kernels >= 0) g_phase_kernels = phase_kernels != 0;
     return SX_OK;
 }
 
@@ -1636,40 +1521,37 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     if (n == 0 || h * w == 0) return SX_OK;
     SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(n), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_macenko_workspace_bytes(n));
-    if (g_fused && images_vec_ok(images, out, dtype, h * w)) {
-        SX_REQUIRE(he_ref && maxc_ref && out, "NULL argument");
-        SX_REQUIRE(out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8), "uint8 output requires uint8 input");
-        const bool unit = out_scale != 1.0f;
-        SX_REQUIRE(!unit || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
-        cudaStream_t stream = static_cast<cudaStream_t>(s);
-        if (dtype == SX_F32) return unit ? launch_fused<float, 2>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream) : launch_fused<float, 1>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream);
-        if (out_dtype == SX_U8) return launch_fused<uint8_t, 0>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream);
-        return unit ? launch_fused<uint8_t, 2>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream) : launch_fused<uint8_t, 1>(images, n, h * w, he_ref, maxc_ref, out, workspace, stream);
-    }
-    const int64_t in_bytes = (dtype == SX_F32 ? 4 : 1) * 3 * h * w;
-    const int64_t out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * h * w;
+    SX_REQUIRE(he_ref && maxc_ref && out, "NULL argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(s);
+    const int64_t hw = h * w;
     int rc;
     if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
-    // Every statistic is per image, so the batch may be walked in groups of images (group_bytes > 0)
-    // whose planes fit in L2 together; by default each phase is one launch over the whole batch.
-    int64_t group = g_group_bytes > 0 ? g_group_bytes / in_bytes : n;
-    if (group < 1) group = 1;
-    if (group > n) group = n;
-    for (int64_t i0 = 0; i0 < n; i0 += group) {
-        const int64_t cnt = (n - i0) < group ? (n - i0) : group;
-        const char *img = static_cast<const char *>(images) + i0 * in_bytes;
-        char *o = static_cast<char *>(out) + i0 * out_bytes;
-        if ((rc = sx_macenko_moments(img, dtype, cnt, h, w, 0, i0, workspace, n, s))) return rc;
-        if ((rc = sx_macenko_basis(workspace, n, i0, cnt, 1, s))) return rc;
-        if ((rc = sx_macenko_moments_fallback(img, dtype, cnt, h, w, i0, workspace, n, s))) return rc;
+    if (g_phase_kernels) {  // development: the phase-level API chained on one stream (13 launches)
+        if ((rc = sx_macenko_moments(images, dtype, n, h, w, 0, 0, workspace, n, s))) return rc;
+        if ((rc = sx_macenko_basis(workspace, n, 0, n, 1, s))) return rc;
+        if ((rc = sx_macenko_moments_fallback(images, dtype, n, h, w, 0, workspace, n, s))) return rc;
         for (int stage = 0; stage < 2; ++stage)
             for (int level = 0; level < 2; ++level) {
-                if ((rc = sx_macenko_hist(img, dtype, cnt, h, w, 0, i0, stage, level, workspace, n, s))) return rc;
-                if ((rc = sx_macenko_select(workspace, n, i0, cnt, stage, level, s))) return rc;
+                if ((rc = sx_macenko_hist(images, dtype, n, h, w, 0, 0, stage, level, workspace, n, s))) return rc;
+                if ((rc = sx_macenko_select(workspace, n, 0, n, stage, level, s))) return rc;
             }
-        if ((rc = sx_macenko_apply(img, dtype, cnt, h, w, i0, he_ref, maxc_ref, o, out_dtype, out_scale, workspace, n, s))) return rc;
+        return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
     }
-    return SX_OK;
+    // Per-image pipeline: three statistics passes whose last CTA per image runs the per-image steps,
+    // then the reconstruction.
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        const T *p = static_cast<const T *>(images);
+        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
+        const unsigned grid = (unsigned)(n * g.cpi);
+        t_moments_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(p, g, workspace, n);
+        note_launch();
+        t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, workspace, n);
+        note_launch();
+        t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, workspace, n);
+    });
+    SX_LAUNCHED("macenko::transform pipeline");
+    return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
 }
 
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t s) {

@@ -468,3 +468,29 @@ def test_macenko_sharded_fit_emulation(cuda):
         assert torch.allclose(fit[6:8], maxc_ref, rtol=1e-6, atol=0)
     assert torch.equal(wss[0].region("fit"), wss[1].region("fit"))
     assert int(wss[0].region("status").abs().sum()) == 0
+
+
+@pytest.mark.gpu
+def test_host_stream_matches_direct_transform(cuda):
+    """ingest.HostStream (pinned host in/out, three-stream pipeline) returns exactly what the
+    device-resident transform returns, batch after batch, also when staging buffers are recycled."""
+    from stainx_b200 import HistogramMatching, Macenko
+    from stainx_b200.ingest import HostStream
+
+    g = torch.Generator().manual_seed(5)
+    ref = (torch.rand(1, 3, 96, 128, generator=g) * 255).round().to(torch.uint8)
+    batches = [(torch.rand(3, 3, 96, 128, generator=g) * 255).round().to(torch.uint8).pin_memory() for _ in range(5)]
+    hm = HistogramMatching(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    pipe = HostStream(hm, depth=2)
+    outs = list(pipe.map(batches))
+    for b, o in zip(batches, outs):
+        assert torch.equal(o, hm.transform(b.to(cuda)).cpu())
+    gold = golden("macenko_he_u8")
+    mk = Macenko(device=cuda, backend="torch_cuda").fit(torch.from_numpy(gold["ref"]).to(cuda))
+    src = torch.from_numpy(gold["src"]).pin_memory()
+    pipe = HostStream(mk, depth=3)
+    tickets = [pipe.submit(src) for _ in range(4)]
+    want = mk.transform(src.to(cuda)).cpu()
+    for t in tickets:
+        assert torch.equal(t.wait(), want)
+    assert pipe.h2d_bytes == 4 * src.numel() * src.element_size()

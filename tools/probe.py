@@ -55,7 +55,7 @@ def probe_hm():
     lib = nv.lib()
     counts = torch.zeros((3, 256), dtype=torch.int64, device=dev)
     want = ops.hm_hist(src)
-    for mode, ctas_list in ((0, (4, 8)), (1, (3,)), (2, (2, 3)), (3, (1,)), (4, (1,)), (5, (1,))):
+    for mode, ctas_list in ((6, (1,)), (7, (1,)), (9, (1,)), (8, (1,))):
         for ctas in ctas_list:
             lib.sx_hm_set_tuning(mode, ctas, -1)
             ok = torch.equal(ops.hm_hist(src), want)
@@ -64,7 +64,7 @@ def probe_hm():
     smooth = (torch.arange(src.numel(), device=dev, dtype=torch.int64) // 4096 % 256).to(torch.uint8).reshape(src.shape)
     lib.sx_hm_set_tuning(0, 8, -1)
     want_const, want_smooth = ops.hm_hist(const), ops.hm_hist(smooth)
-    for mode, ctas in ((0, 8), (2, 3), (3, 1), (4, 1), (5, 1)):
+    for mode, ctas in ((0, 8), (5, 1), (6, 1)):
         lib.sx_hm_set_tuning(mode, ctas, -1)
         ok = torch.equal(ops.hm_hist(const), want_const)
         report(f"hm hist u8 CONSTANT image mode={mode} ok={ok}", timeit(lambda: ops.hm_hist(const, counts=counts)), 3 * px)
@@ -159,23 +159,25 @@ def probe_macenko():
     phases_until(2, 0)
     print("status flags:", int(ws.region("status").abs().sum()))
     report("macenko apply f32 -> f32 unit", timeit(lambda: ws.apply(src, he, maxc, out, True)), 24 * px)
-    lib.sx_macenko_set_fused(0, 0)
+    lib.sx_macenko_set_tuning(-1, 1)
     want = ops.macenko_transform(src, he, maxc, unit=True)
     report("macenko transform f32 64x1024^2 phase kernels", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
-    for teams in (0, 1, 2, 3):
-        lib.sx_macenko_set_fused(1, teams)
-        got = ops.macenko_transform(src, he, maxc, unit=True)
-        err = float((got - want).abs().max())
-        report(f"macenko transform f32 FUSED teams<={teams} maxdiff={err:.2e}", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
-    lib.sx_macenko_set_fused(1, 0)
+    lib.sx_macenko_set_tuning(-1, 0)
+    got = ops.macenko_transform(src, he, maxc, unit=True)
+    err = float((got - want).abs().max())
+    report(f"macenko transform f32 64x1024^2 pipeline maxdiff={err:.2e}", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=10), 24 * px)
+    # per-kernel times of the pipeline (events around each launch are not available through the
+    # C ABI; time prefixes of the chain instead)
     del want, got
     src8 = (src * 255).to(torch.uint8)
     del src, out
-    for fused in (0, 1):
-        lib.sx_macenko_set_fused(fused, 0)
-        report(f"macenko transform u8 -> u8 fused={fused}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=False), steps=5), 6 * px)
-        report(f"macenko transform u8 -> f32 unit fused={fused}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=True), steps=5), 15 * px)
-    lib.sx_macenko_set_fused(1, 0)
+    for phase in (1, 0):
+        lib.sx_macenko_set_tuning(-1, phase)
+        tag = "phase kernels" if phase else "pipeline"
+        report(f"macenko transform u8 -> u8 {tag}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=False), steps=5), 6 * px)
+        report(f"macenko transform u8 -> f32 unit {tag}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=True), steps=5), 15 * px)
+    big = src8.reshape(16, 3, 2048, 2048)
+    report("macenko transform u8 2048^2 x16 -> f32 unit pipeline", timeit(lambda: ops.macenko_transform(big, he, maxc, unit=True), steps=5), 15 * px)
 
 
 if __name__ == "__main__":
