@@ -180,7 +180,7 @@ struct RawGroup {
 template <typename T, bool VEC, typename Body, typename Every>
 __device__ __forceinline__ void stream_groups(const T *__restrict__ image, int64_t hw, int64_t groups, int64_t cta_first, int64_t cta_stride, const float *tab, Body body, Every every) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    RawGroup<T, VEC> cur, nxt;
+    RawGroup<T, VEC> cur, nxt;  // (two groups ahead was measured: the extra registers cost more than the latency they hide)
     int64_t gi = cta_first + threadIdx.x;
     if (gi < groups) cur.load(image + gi * kPix, hw);
     for (int64_t base = cta_first; base < groups; base += cta_stride) {
@@ -204,7 +204,7 @@ __device__ __forceinline__ void stream_groups_uniform(const T *__restrict__ imag
     constexpr int kPix = Pix<T, VEC>::kPix;
     RawGroup<T, VEC> cur, nxt;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { cur.v[c] = typename RawGroup<T, VEC>::Vec(); nxt.v[c] = typename RawGroup<T, VEC>::Vec(); }
+    for (int c = 0; c < 3; ++c) { cur.v[c] = typename RawGroup<T, VEC>::Vec(); nxt.v[c] = cur.v[c]; }
     int64_t gi = cta_first + threadIdx.x;
     if (gi < groups) cur.load(image + gi * kPix, hw);
     for (int64_t base = cta_first; base < groups; base += cta_stride) {
@@ -324,13 +324,13 @@ __device__ __forceinline__ void block_sum10(double (&acc)[10], double (*red)[10]
 // Streams groups of one image through moments_group; float32 partial sums are folded into the
 // double accumulators every kFlush groups (<= 64 pixels).
 template <typename T, bool VEC, bool MASKED>
-__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t cta_first, int64_t cta_stride, const float *tab, double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
+__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t groups_end, int64_t cta_first, int64_t cta_stride, const float *tab, double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     constexpr int kFlush = kPix >= 16 ? 2 : 8;
     float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int pending = 0;
     stream_groups<T, VEC>(
-        image, hw, hw / kPix, cta_first, cta_stride, tab,
+        image, hw, groups_end, cta_first, cta_stride, tab,
         [&](const float(&l)[3][kPix], int64_t) {
             moments_group<kPix, MASKED>(l, s, lo, hi);
             if (++pending == kFlush) {
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     }
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
+    moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, g.hw / Pix<T, VEC>::kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
     lo[1] = lo[2] = lo[0];
     hi[1] = hi[2] = hi[0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict_
     }
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-    moments_stream<T, VEC, false>(img + n * 3 * hw, hw, 0, kThreads, tab, acc, lo, hi);
+    moments_stream<T, VEC, false>(img + n * 3 * hw, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, tab, acc, lo, hi);
     block_sum10(acc, red);
     if (threadIdx.x < 10) tot[threadIdx.x] = acc[0];
     __syncthreads();
@@ -623,7 +623,7 @@ struct ResolveSmem {
 // Streams the groups first, first + stride, ... of one image.  `st` is a shared-memory copy of the
 // slot's state, `rs` shared scratch; results go to the slot's global cells / counters.
 template <typename T, bool VEC, int STAGE>
-__device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_t hw, int64_t first, int64_t stride, const float *tab, const SlotState &st, ResolveSmem &rs, unsigned *h2, float *vmin, float *vmax, unsigned long long *counters) {
+__device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_t hw, int64_t groups_end, int64_t first, int64_t stride, const float *tab, const SlotState &st, ResolveSmem &rs, unsigned *h2, float *vmin, float *vmax, unsigned long long *counters) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     // ~2.5 % of the pixel-queries hit: 256 threads x kPix x kDrainEvery x 2.5 % stays far below the queue capacity
     constexpr int kDrainEvery = kPix >= 16 ? 4 : (kPix >= 4 ? 12 : 32);
@@ -653,7 +653,7 @@ __device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_
     unsigned below0 = 0u, below1 = 0u;
     int it = 0;
     stream_groups_uniform<T, VEC>(
-        image, hw, hw / kPix, first, stride, tab,
+        image, hw, groups_end, first, stride, tab,
         [&](const float(&l)[3][kPix], bool valid) {
             float v0[kPix], v1[kPix];
             unsigned m0 = 0u, m1 = 0u, b0 = 0u, b1 = 0u;
@@ -688,11 +688,21 @@ __device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_
                         if (m0 & (1u << k)) { st_shared_v2(addr, __float_as_uint(v0[k]), 0u); addr += 8u; }
                         if (m1 & (1u << k)) { st_shared_v2(addr, __float_as_uint(v1[k]), 1u); addr += 8u; }
                     }
-                } else {  // queue full (degenerate data): record directly
+                } else {  // queue (nearly) full (degenerate data): every reserved slot below the capacity
+                          // must still be written, because the drain reads all of them; the rest is recorded directly
+                    unsigned pos = base + (unsigned)(incl - c);
 #pragma unroll
                     for (int k = 0; k < kPix; ++k) {
-                        if (m0 & (1u << k)) record_cell(st, 0, v0[k], h2, vmin, vmax);
-                        if (m1 & (1u << k)) record_cell(st, 1, v1[k], h2, vmin, vmax);
+                        if (m0 & (1u << k)) {
+                            if (pos < (unsigned)kQueueCap) st_shared_v2(q_addr + pos * 8u, __float_as_uint(v0[k]), 0u);
+                            else record_cell(st, 0, v0[k], h2, vmin, vmax);
+                            ++pos;
+                        }
+                        if (m1 & (1u << k)) {
+                            if (pos < (unsigned)kQueueCap) st_shared_v2(q_addr + pos * 8u, __float_as_uint(v1[k]), 1u);
+                            else record_cell(st, 1, v1[k], h2, vmin, vmax);
+                            ++pos;
+                        }
                     }
                 }
             }
@@ -758,14 +768,15 @@ __device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_cnt, cnt);
 }
 
-// Counts this CTA as finished with phase `phase` (0 moments, 1 resolve ANGLE, 2 resolve CONC) of
-// its slot; true on the CTA that finishes last, which then sees every other CTA's results.
-__device__ __forceinline__ bool last_cta_of_slot(int *status, int64_t slot, int phase, int ctas, int *s_flag) {
+// Reports `rows` more rows (of kThreads pixel groups) of the slot's image as finished with phase
+// `phase` (0 moments, 1 resolve ANGLE, 2 resolve CONC); true on the CTA that completes the image,
+// which then sees every other CTA's results.
+__device__ __forceinline__ bool completes_slot(int *status, int64_t slot, int phase, int rows, int rows_per_img, int *s_flag) {
     __threadfence();  // this thread's global atomics / stores are visible before the count below
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int old = atomicAdd(&status[slot * 4 + 1 + phase], 1);
-        *s_flag = old == ctas - 1;
+        const int old = atomicAdd(&status[slot * 4 + 1 + phase], rows);
+        *s_flag = old + rows == rows_per_img;
         __threadfence();
     }
     __syncthreads();
@@ -784,7 +795,7 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__
     if (threadIdx.x == 0) st = ws.state[slot];
     if constexpr (sizeof(T) == 1) build_l_table(tab);
     __syncthreads();
-    resolve_pass<T, VEC, STAGE>(img + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, st, rs, ws.hist2 + slot * 2 * kBins, ws.vmin + slot * 2 * kBins, ws.vmax + slot * 2 * kBins, ws.counters + slot * 8);
+    resolve_pass<T, VEC, STAGE>(img + n * 3 * g.hw, g.hw, g.hw / Pix<T, VEC>::kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, st, rs, ws.hist2 + slot * 2 * kBins, ws.vmin + slot * 2 * kBins, ws.vmax + slot * 2 * kBins, ws.counters + slot * 8);
 }
 
 // ---- per-slot rank searches (one CTA per slot) --------------------------------------------------
@@ -1192,111 +1203,137 @@ __device__ __forceinline__ void sample_and_bracket(const T *__restrict__ image, 
 template <typename T, bool VEC>
 constexpr int kMinCtas = (VEC && sizeof(T) == 1) ? 2 : 3;
 
+// Work decomposition of the pipeline kernels: the batch is one list of ROWS (kThreads consecutive
+// pixel groups of one image); CTA c of a grid sized to the resident capacity of the device owns the
+// contiguous rows [c R / grid, (c + 1) R / grid) -- equal work for every CTA whatever the batch and
+// image sizes, at most two images per CTA for batches larger than the grid.
+struct RowGeom {
+    int64_t n_img, hw, total_rows;
+    int rows_per_img;
+};
+
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_moments_kernel(const T *__restrict__ img, PassGeom g, void *ws_base, int64_t slots) {
+__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_moments_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
     __shared__ double red[kThreads / 32][10];
-    __shared__ float redf[kThreads / 32][6];
+    __shared__ float redf[kThreads / 32][2];
     __shared__ EpiSmem ep;
     __shared__ __align__(16) unsigned char scratch[kScratchBytes];
     Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = n;
-    const T *image = img + n * 3 * g.hw;
     if constexpr (sizeof(T) == 1) {
         build_l_table(tab);
         __syncthreads();
     }
-    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    moments_stream<T, VEC, true>(image, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        const float a = warp_max(-lo[0]), b = warp_max(hi[0]);
-        if (lane == 0) { redf[warp][0] = a; redf[warp][1] = b; }
-    }
-    block_sum10(acc, red);
-    if (threadIdx.x < 10) {
-        if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
-    } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
-        const int i = threadIdx.x - 32;  // [0..2] = -min l (one range for the three channels), [3..5] = max l
-        float r = -INFINITY;
-        for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i / 3]);
-        atomic_max_f32(&ws.odrange[slot * 8 + i], r);
-    }
-    if (!last_cta_of_slot(ws.status, slot, 0, g.cpi, &ep.s_flag)) return;
+    const int64_t groups = g.hw / kPix;
+    const int64_t r_end = (int64_t)(blockIdx.x + 1) * g.total_rows / gridDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
+        const int64_t n = r / g.rows_per_img, slot = n;
+        const int row0 = (int)(r - n * g.rows_per_img);
+        const int row1 = (int)((int64_t)row0 + (r_end - r) < (int64_t)g.rows_per_img ? (int64_t)row0 + (r_end - r) : (int64_t)g.rows_per_img);
+        r += row1 - row0;
+        const T *image = img + n * 3 * g.hw;
+        const int64_t seg_end = (int64_t)row1 * kThreads < groups ? (int64_t)row1 * kThreads : groups;
 
-    // ---- the image's moments are complete: basis (M3-M4), fallback (L409-410), ANGLE brackets
-    SX_STAMP(ws.counters + slot * 8, 4);
-    if (threadIdx.x < 10) ep.tot[threadIdx.x] = __ldcg(ws.moments + slot * 12 + threadIdx.x);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        SlotState z = {};
-        ep.st = z;
-        ep.st.n_all = (long long)g.hw;
-        ep.st.use_all = ep.tot[0] < 3.0;
-        if (!ep.st.use_all) basis_from_moments(ep.tot, ep.st);
-    }
-    __syncthreads();
-    if (ep.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
-        double acc2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        float lo2[3] = {0, 0, 0}, hi2[3] = {0, 0, 0};
-        moments_stream<T, VEC, false>(image, g.hw, 0, kThreads, tab, acc2, lo2, hi2);
-        __syncthreads();
-        block_sum10(acc2, red);
-        if (threadIdx.x < 10) ep.tot[threadIdx.x] = acc2[0];
+        double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        moments_stream<T, VEC, true>(image, g.hw, seg_end, (int64_t)row0 * kThreads, kThreads, tab, acc, lo, hi);
+        {
+            const float a = warp_max(-lo[0]), b = warp_max(hi[0]);
+            if (lane == 0) { redf[warp][0] = a; redf[warp][1] = b; }
+        }
+        block_sum10(acc, red);
+        if (threadIdx.x < 10) {
+            if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
+        } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
+            const int i = threadIdx.x - 32;  // [0..2] = -min l (one range for the three channels), [3..5] = max l
+            float v = -INFINITY;
+            for (int k = 0; k < kThreads / 32; ++k) v = fmaxf(v, redf[k][i / 3]);
+            atomic_max_f32(&ws.odrange[slot * 8 + i], v);
+        }
+        if (!completes_slot(ws.status, slot, 0, row1 - row0, g.rows_per_img, &ep.s_flag)) continue;
+
+        // ---- the image's moments are complete: basis (M3-M4), fallback (L409-410), ANGLE brackets
+        SX_STAMP(ws.counters + slot * 8, 4);
+        if (threadIdx.x < 10) ep.tot[threadIdx.x] = __ldcg(ws.moments + slot * 12 + threadIdx.x);
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = ep.tot[i];
-            basis_from_moments(ep.tot, ep.st);
+            SlotState z = {};
+            ep.st = z;
+            ep.st.n_all = (long long)g.hw;
+            ep.st.use_all = ep.tot[0] < 3.0;
+            if (!ep.st.use_all) basis_from_moments(ep.tot, ep.st);
         }
         __syncthreads();
-    }
-    if (threadIdx.x == 0) ws.moments[slot * 12 + 10] = (double)g.hw;
-    SX_STAMP(ws.counters + slot * 8, 5);
-    sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, g.hw, tab, ep, reinterpret_cast<unsigned (*)[kBins]>(scratch));
-    SX_STAMP(ws.counters + slot * 8, 6);
-    store_state(ws.state + slot, &ep.st);
-    SX_STAMP(ws.counters + slot * 8, 7);
+        if (ep.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
+            double acc2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            float lo2[3] = {0, 0, 0}, hi2[3] = {0, 0, 0};
+            moments_stream<T, VEC, false>(image, g.hw, groups, 0, kThreads, tab, acc2, lo2, hi2);
+            __syncthreads();
+            block_sum10(acc2, red);
+            if (threadIdx.x < 10) ep.tot[threadIdx.x] = acc2[0];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = ep.tot[i];
+                basis_from_moments(ep.tot, ep.st);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ws.moments[slot * 12 + 10] = (double)g.hw;
+        SX_STAMP(ws.counters + slot * 8, 5);
+        sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, g.hw, tab, ep, reinterpret_cast<unsigned (*)[kBins]>(scratch));
+        SX_STAMP(ws.counters + slot * 8, 6);
+        store_state(ws.state + slot, &ep.st);
+        SX_STAMP(ws.counters + slot * 8, 7);
 #ifdef SX_MK_TIMING
-    if (threadIdx.x == 0) ws.moments[slot * 12 + 11] = ep.tot[11];
+        if (threadIdx.x == 0) ws.moments[slot * 12 + 11] = ep.tot[11];
 #endif
+        __syncthreads();
+    }
 }
 
 template <typename T, bool VEC, int STAGE>
-__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_resolve_kernel(const T *__restrict__ img, PassGeom g, void *ws_base, int64_t slots) {
+__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_resolve_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
+    constexpr int kPix = Pix<T, VEC>::kPix;
     __shared__ float tab[256];
     __shared__ EpiSmem ep;
     __shared__ __align__(16) unsigned char scratch[kScratchBytes];
     Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = n;
-    const T *image = img + n * 3 * g.hw;
-    const int64_t base = slot * 2 * kBins;
     if constexpr (sizeof(T) == 1) build_l_table(tab);
-    load_state(&ep.st, ws.state + slot);
-    resolve_pass<T, VEC, STAGE>(image, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, ep.st, *reinterpret_cast<ResolveSmem *>(scratch), ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
-    if (!last_cta_of_slot(ws.status, slot, 1 + STAGE, g.cpi, &ep.s_flag)) return;
+    const int64_t groups = g.hw / kPix;
+    const int64_t r_end = (int64_t)(blockIdx.x + 1) * g.total_rows / gridDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
+        const int64_t n = r / g.rows_per_img, slot = n;
+        const int row0 = (int)(r - n * g.rows_per_img);
+        const int row1 = (int)((int64_t)row0 + (r_end - r) < (int64_t)g.rows_per_img ? (int64_t)row0 + (r_end - r) : (int64_t)g.rows_per_img);
+        r += row1 - row0;
+        const T *image = img + n * 3 * g.hw;
+        const int64_t seg_end = (int64_t)row1 * kThreads < groups ? (int64_t)row1 * kThreads : groups;
+        const int64_t base = slot * 2 * kBins;
+        load_state(&ep.st, ws.state + slot);
+        resolve_pass<T, VEC, STAGE>(image, g.hw, seg_end, (int64_t)row0 * kThreads, kThreads, tab, ep.st, *reinterpret_cast<ResolveSmem *>(scratch), ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
+        if (!completes_slot(ws.status, slot, 1 + STAGE, row1 - row0, g.rows_per_img, &ep.s_flag)) continue;
 
-    // ---- the image's cells are complete: rank search; ANGLE: HE, pinv (M7-M8), CONC brackets
-    unsigned (*pre)[kBins] = reinterpret_cast<unsigned (*)[kBins]>(scratch);
-    if (threadIdx.x < 8) ep.rg[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
-    __syncthreads();
-    select_slot(ws, slot, STAGE, ep.st, ep.rg, pre);
-    __syncthreads();
-    if constexpr (STAGE == SX_STAGE_ANGLE) {
-        // re-arm the slot's cells and counters for the CONC stage
-        for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
-            ws.hist2[base + i] = 0u;
-            ws.vmin[base + i] = INFINITY;
-            ws.vmax[base + i] = -INFINITY;
+        // ---- the image's cells are complete: rank search; ANGLE: HE, pinv (M7-M8), CONC brackets
+        unsigned (*pre)[kBins] = reinterpret_cast<unsigned (*)[kBins]>(scratch);
+        if (threadIdx.x < 8) ep.rg[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
+        __syncthreads();
+        select_slot(ws, slot, STAGE, ep.st, ep.rg, pre);
+        __syncthreads();
+        if constexpr (STAGE == SX_STAGE_ANGLE) {
+            // re-arm the slot's cells and counters for the CONC stage
+            for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+                ws.hist2[base + i] = 0u;
+                ws.vmin[base + i] = INFINITY;
+                ws.vmax[base + i] = -INFINITY;
+            }
+            if (threadIdx.x < 4) ws.counters[slot * 8 + threadIdx.x] = 0ull;
+            sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, g.hw, tab, ep, pre);
         }
-        if (threadIdx.x < 4) ws.counters[slot * 8 + threadIdx.x] = 0ull;
-        sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, g.hw, tab, ep, pre);
+        store_state(ws.state + slot, &ep.st);
+        __syncthreads();
     }
-    store_state(ws.state + slot, &ep.st);
 }
 
 __global__ void init_kernel(void *ws_base, int64_t slots) {
@@ -1332,6 +1369,15 @@ static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_overri
     if (want < 1) want = 1;
     g.cpi = (int)want;
     return g;
+}
+
+// Grid of a pipeline kernel: every CTA resident at once (occupancy x SMs), never more than rows.
+template <typename K>
+static unsigned pipeline_grid(K kernel, int64_t total_rows) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t resident = (int64_t)per_sm * sm_count();
+    return (unsigned)(total_rows < resident ? (total_rows > 0 ? total_rows : 1) : resident);
 }
 
 template <typename T>
@@ -1542,13 +1588,16 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         const T *p = static_cast<const T *>(images);
-        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
-        const unsigned grid = (unsigned)(n * g.cpi);
-        t_moments_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(p, g, workspace, n);
+        RowGeom g;
+        g.n_img = n;
+        g.hw = hw;
+        g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
+        g.total_rows = n * g.rows_per_img;
+        t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
         note_launch();
-        t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, workspace, n);
+        t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
         note_launch();
-        t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, workspace, n);
+        t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
     });
     SX_LAUNCHED("macenko::transform pipeline");
     return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);

@@ -494,3 +494,29 @@ def test_host_stream_matches_direct_transform(cuda):
     for t in tickets:
         assert torch.equal(t.wait(), want)
     assert pipe.h2d_bytes == 4 * src.numel() * src.element_size()
+
+
+@pytest.mark.gpu
+def test_macenko_ties_overflow_the_hit_queue(cuda, ox):
+    """Images made of a few flat colours put most pixels INSIDE the order-statistic brackets (ties),
+    so the shared hit queue of the resolve pass overflows constantly and the direct path runs; the
+    result must still match the oracle (uint8 and float32, pipeline and pooled fit)."""
+    from stainx_b200 import Macenko
+
+    g = torch.Generator().manual_seed(11)
+    tile = he_tile(256, 256, 42)
+    palette = tile[0, :, ::64, ::64].reshape(3, -1).T.contiguous()  # 16 stain-like colours
+    idx = torch.randint(0, palette.shape[0], (3, 256, 256), generator=g)
+    idx[:, :, :128] = idx[:, :1, :1]  # half of every image is one flat colour
+    flat = palette[idx].permute(0, 3, 1, 2).contiguous()  # (3, 3, 256, 256) uint8
+    ref = he_tile(256, 256, 7)
+    for src in (flat, flat.float() / 255.0):
+        n = Macenko(device=cuda, backend="torch_cuda").fit(ref.to(cuda) if src.dtype == torch.uint8 else (ref.float() / 255.0).to(cuda))
+        out = _np(n.transform(src.to(cuda)))
+        want = ox.macenko_transform(src.numpy(), _np(n._stain_matrix), _np(n._target_max_conc))
+        diff = np.abs(out.astype(np.float64) - want.astype(np.float64))
+        assert diff.max() <= (1 if src.dtype == torch.uint8 else F32_TOL * 255.0)
+    he, maxc = ox.macenko_fit(flat.numpy())
+    n = Macenko(device=cuda, backend="torch_cuda").fit(flat.to(cuda))
+    assert np.abs(_np(n._stain_matrix) - he).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / maxc - 1).max() <= 1e-3
