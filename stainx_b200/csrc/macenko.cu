@@ -124,13 +124,18 @@ struct Pix {
 constexpr float kLThr = 7.690486339f;    // log2(240) - 0.15 / ln2
 constexpr float kLShift = 6.5f;          // moments are accumulated about this value of l
 
-__device__ __forceinline__ void build_l_table(float *tab) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const float x = __fdiv_rn((float)i, 255.0f);
-        tab[i] = log2f(__fadd_rn(__fmul_rn(x, 255.0f), 1.0f));
-    }
-}
 __device__ __forceinline__ float f32_l(float x) { return fast_lg2(__fmaf_rn(x, 255.0f, 1.0f)); }
+// uint8: byte K of `w` -> l.  The reference computes x = v / 255, t = x * 255 + 1 in float32
+// (torch_backend.py:L112, L550); t == v + 1 exactly for every v in 0..255 (checked exhaustively), so
+// l = log2(v + 1).  The byte goes straight into the mantissa of 2^23 (one PRMT) and 2^23 - 1 is
+// subtracted: no integer-to-float conversion (SFU) and no table in shared memory (a 256-entry table
+// indexed by 32 random bytes costs ~3.5 bank-conflict replays per lookup, which bound the uint8
+// passes: ncu mio_throttle 8.5 warps per issue in the first version of the reconstruction).
+template <int K>
+__device__ __forceinline__ float u8_l(unsigned w) {
+    return fast_lg2(__fsub_rn(__uint_as_float(__byte_perm(w, 0x4b000000u, 0x7650 + K)), 8388607.0f));
+}
+__device__ __forceinline__ float u8_l_scalar(unsigned v) { return fast_lg2(__fsub_rn(__uint_as_float(0x4b000000u | v), 8388607.0f)); }
 
 // Raw 128-bit (or scalar) loads of one pixel group, kept in registers so that the loads of the next
 // group can be in flight while the current one is processed.
@@ -164,11 +169,16 @@ struct RawGroup {
                 for (int c = 0; c < 3; ++c) {
                     const unsigned w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
 #pragma unroll
-                    for (int k = 0; k < kPix; ++k) l[c][k] = tab[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+                    for (int k = 0; k < kPix; k += 4) {
+                        l[c][k] = u8_l<0>(w[k >> 2]);
+                        l[c][k + 1] = u8_l<1>(w[k >> 2]);
+                        l[c][k + 2] = u8_l<2>(w[k >> 2]);
+                        l[c][k + 3] = u8_l<3>(w[k >> 2]);
+                    }
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) l[c][0] = tab[v[c]];
+                for (int c = 0; c < 3; ++c) l[c][0] = u8_l_scalar(v[c]);
             }
         }
     }
@@ -353,10 +363,6 @@ __global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
-    if constexpr (sizeof(T) == 1) {
-        build_l_table(tab);
-        __syncthreads();
-    }
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, g.hw / Pix<T, VEC>::kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
@@ -507,10 +513,6 @@ __global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict_
     const int64_t n = blockIdx.x;
     const int64_t slot = slot0 + n;
     if (!ws.state[slot].use_all) return;
-    if constexpr (sizeof(T) == 1) {
-        build_l_table(tab);
-        __syncthreads();
-    }
     double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     moments_stream<T, VEC, false>(img + n * 3 * hw, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, tab, acc, lo, hi);
@@ -547,7 +549,6 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ 
     const SlotState &gst = ws.state[slot];
     const RankParams st(gst);
     const float c_lo0 = gst.c_lo[0], c_lo1 = gst.c_lo[1], c_sc0 = gst.c_scale[0], c_sc1 = gst.c_scale[1];
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
     for (int i = threadIdx.x; i < kQ * kBins; i += kThreads) sh[i] = 0u;
     if (threadIdx.x == 0) {
         s_cnt = 0u;
@@ -721,13 +722,13 @@ __device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_
     if (threadIdx.x < 2 && rs.below[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)rs.below[threadIdx.x]);
 }
 
-// The sample pass of one slot run by ONE CTA (epilogues of the per-image transform pipeline):
-// the same hashed groups and keys as sample_kernel, histograms in shared memory (zeroed by the
-// caller), sampled rows counted in *s_cnt.  Loads are issued four groups at a time.
+// The sample pass of one slot run by ONE CTA (per-image kernels of the transform pipeline): the
+// same hashed groups and keys as sample_kernel, histograms in shared memory (zeroed by the
+// caller), sampled rows counted in *s_cnt.  Loads are issued eight groups at a time.
 template <typename T, bool VEC, int STAGE>
 __device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw, const float *tab, const SlotState &st, unsigned (*hist)[kBins], unsigned *s_cnt) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    constexpr int kBatch = 4;
+    constexpr int kBatch = 8;
     const int64_t groups = hw / kPix;
     const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
     const int64_t nsamp = groups / stride;
@@ -768,21 +769,6 @@ __device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_cnt, cnt);
 }
 
-// Reports `rows` more rows (of kThreads pixel groups) of the slot's image as finished with phase
-// `phase` (0 moments, 1 resolve ANGLE, 2 resolve CONC); true on the CTA that completes the image,
-// which then sees every other CTA's results.
-__device__ __forceinline__ bool completes_slot(int *status, int64_t slot, int phase, int rows, int rows_per_img, int *s_flag) {
-    __threadfence();  // this thread's global atomics / stores are visible before the count below
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int old = atomicAdd(&status[slot * 4 + 1 + phase], rows);
-        *s_flag = old + rows == rows_per_img;
-        __threadfence();
-    }
-    __syncthreads();
-    return *s_flag != 0;
-}
-
 template <typename T, bool VEC, int STAGE>
 __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
     __shared__ float tab[256];
@@ -793,7 +779,6 @@ __global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = pooled ? 0 : slot0 + n;
     if (threadIdx.x == 0) st = ws.state[slot];
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
     __syncthreads();
     resolve_pass<T, VEC, STAGE>(img + n * 3 * g.hw, g.hw, g.hw / Pix<T, VEC>::kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, st, rs, ws.hist2 + slot * 2 * kBins, ws.vmin + slot * 2 * kBins, ws.vmax + slot * 2 * kBins, ws.counters + slot * 8);
 }
@@ -1051,6 +1036,18 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
     }
 }
 
+// Truncation of 0 <= x < 2^23 on the FMA pipe: adding 2^23 with round-toward-zero leaves trunc(x) in
+// the low mantissa bits (F2I / I2F / FRND run on the SFU, which the exponentials already load).
+__device__ __forceinline__ unsigned trunc_byte(float x) { return __float_as_uint(__fadd_rz(x, 8388608.0f)) & 0xffu; }  // x in [0, 256)
+__device__ __forceinline__ float trunc_small(float x) { return __fsub_rn(__fadd_rz(x, 8388608.0f), 8388608.0f); }
+// q / 255 correctly rounded for integer-valued 0 <= q <= 255 (checked exhaustively against the true
+// division of _template.py:L111-112): one Newton correction of q * (1 / 255).
+__device__ __forceinline__ float div255_exact(float q) {
+    const float c = 1.0f / 255.0f;
+    const float r0 = __fmul_rn(q, c);
+    return __fmaf_rn(__fmaf_rn(-255.0f, r0, q), c, r0);
+}
+
 // coef[c][0..2] = M3 row c, coef[c][3] = bias (shared memory, written by threads 0..2).
 template <typename T, int OUT>
 __device__ __forceinline__ void apply_coefficients(float *coef, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, const float *pinv, float maxc0, float maxc1) {
@@ -1097,7 +1094,7 @@ __device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__
                 if constexpr (VEC) {
                     unsigned w[4] = {0, 0, 0, 0};
 #pragma unroll
-                    for (int k = 0; k < kPix; ++k) w[k >> 2] |= (unsigned)__float2int_rz(o[c][k]) << (8 * (k & 3));
+                    for (int k = 0; k < kPix; ++k) w[k >> 2] |= trunc_byte(o[c][k]) << (8 * (k & 3));
                     st_stream(reinterpret_cast<uint4 *>(out + c * hw), make_uint4(w[0], w[1], w[2], w[3]));
                 } else {
                     out[c * hw] = (uint8_t)__float2int_rz(o[c][0]);
@@ -1111,8 +1108,8 @@ __device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__
                     // uint8 input: the reference truncates to uint8 first (L560), then casts / divides
 #pragma unroll
                     for (int k = 0; k < kPix; ++k) {
-                        const int q = __float2int_rz(o[c][k]);
-                        o[c][k] = OUT == 2 ? unit_tab[q] : (float)q;
+                        const float q = trunc_small(o[c][k]);
+                        o[c][k] = OUT == 2 ? div255_exact(q) : q;
                     }
                 }
                 if constexpr (VEC) {
@@ -1139,9 +1136,6 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
     const int64_t n = blockIdx.x / g.cpi;
     const int chunk = blockIdx.x % g.cpi;
     const int64_t slot = slot0 + n;
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
-    if constexpr (OUT == 2 && sizeof(T) == 1)
-        for (int i = threadIdx.x; i < 256; i += kThreads) unit_tab[i] = __fdiv_rn((float)i, 255.0f);  // _template.py:L111-112
     apply_coefficients<T, OUT>(coef, he_ref, maxc_ref, ws.state[slot].pinv, ws.fit[slot * 8 + 6], ws.fit[slot * 8 + 7]);
     __syncthreads();
     constexpr int kOutBytes = OUT == 0 ? 1 : 4;
@@ -1149,61 +1143,20 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
 }
 
 // ---- per-image transform pipeline ------------------------------------------------------------
-// sx_macenko_transform runs FOUR launches over the batch (moments, resolve ANGLE, resolve CONC,
-// apply).  Everything between two passes of an image -- eigen-decomposition, the sample pass and
-// its bracket, the rank search, HE / pinv -- is done by the CTA that finishes the image's pass LAST
-// (a counter per slot and phase), while the CTAs of other images are still streaming: no
-// one-CTA-per-slot launches, no extra launch latencies.  The arithmetic is the phase-level API's
-// (same functions, same sample groups), so both paths give the same statistics.
-#ifdef SX_MK_TIMING
-#define SX_STAMP(ptr, i)                                             \
-    do {                                                              \
-        if (threadIdx.x == 0) {                                       \
-            unsigned long long _t;                                    \
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));  \
-            (ptr)[i] = _t;                                            \
-        }                                                             \
-    } while (0)
-#else
-#define SX_STAMP(ptr, i) do {} while (0)
-#endif
-
-struct EpiSmem {
-    SlotState st;
-    unsigned s_cnt;
-    int s_flag;
-    float rg[8];
-    double tot[12];
-};
-
-// Shared scratch large enough for the resolve queues and for two kBins histograms / prefix arrays.
-constexpr int kScratchBytes = 2 * kBins * 4 > (int)sizeof(ResolveSmem) ? 2 * kBins * 4 : (int)sizeof(ResolveSmem);
-
-// Zeroes the two shared histograms, runs the sample pass of `stage` and turns it into brackets.
-template <typename T, bool VEC, int STAGE>
-__device__ __forceinline__ void sample_and_bracket(const T *__restrict__ image, int64_t hw, const float *tab, EpiSmem &ep, unsigned (*hist)[kBins]) {
-    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) hist[0][i] = 0u;
-    if (threadIdx.x == 0) {
-        ep.s_cnt = 0u;
-        ep.st.group_px = Pix<T, VEC>::kPix;
-    }
-    __syncthreads();
-    sample_slot<T, VEC, STAGE>(image, hw, tab, ep.st, hist, &ep.s_cnt);
-    __syncthreads();
-#ifdef SX_MK_TIMING
-    if (threadIdx.x == 0) { unsigned long long _t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t)); ep.tot[11] = __longlong_as_double((long long)_t); }
-#endif
-    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
-    dual_prefix<true>(hist[0], STAGE == SX_STAGE_ANGLE ? hist[0] : hist[1], hist);
-    bracket_from_prefix(STAGE, ep.st, hist, (long long)ep.s_cnt, (long long)ep.s_cnt);
-}
-
-// Register budget of the pipeline kernels: the streaming loop must keep >= 3 (uint8 x 16 pixels: 2)
-// CTAs resident per SM; the once-per-image epilogue may spill.
-template <typename T, bool VEC>
-constexpr int kMinCtas = (VEC && sizeof(T) == 1) ? 2 : 3;
-
-// Work decomposition of the pipeline kernels: the batch is one list of ROWS (kThreads consecutive
+// sx_macenko_transform chains EIGHT launches: three lean streaming kernels over the batch (moments,
+// resolve ANGLE, resolve CONC), the reconstruction, and between them one-CTA-per-image kernels that
+// each do ALL the per-image work due at that point:
+//   mid<0>  after moments:       basis (M3-M4), masked-row fallback (L409-410), ANGLE sample + bracket
+//   mid<1>  after resolve ANGLE: rank search, HE / pinv (M7-M8), CONC sample + bracket
+//   select  after resolve CONC:  rank search -> maxC (M9)
+// The phase-level API needs 13 launches for the same work because a sharded fit must all-reduce
+// between them.  (Folding the per-image steps into the tail of the streaming kernels -- "last CTA of
+// an image finishes it" -- was built and measured: the extra registers and shared memory slowed the
+// streaming loops by as much as the saved launches, 1004 us against 1012 us on 64 x 1024^2 float32,
+// and made uint8 slower.)  The arithmetic is the phase-level API's (same functions, same sample
+// groups), so both paths give the same statistics.
+//
+// Work decomposition of the streaming kernels: the batch is one list of ROWS (kThreads consecutive
 // pixel groups of one image); CTA c of a grid sized to the resident capacity of the device owns the
 // contiguous rows [c R / grid, (c + 1) R / grid) -- equal work for every CTA whatever the batch and
 // image sizes, at most two images per CTA for batches larger than the grid.
@@ -1212,33 +1165,35 @@ struct RowGeom {
     int rows_per_img;
 };
 
+// The segment (image, rows [row0, row1)) at row `r` of a CTA's range ending at `r_end`.
+struct RowSegment {
+    int64_t n;
+    int row0, row1;
+    __device__ __forceinline__ RowSegment(const RowGeom &g, int64_t r, int64_t r_end) {
+        n = r / g.rows_per_img;
+        row0 = (int)(r - n * g.rows_per_img);
+        const int64_t want = (int64_t)row0 + (r_end - r);
+        row1 = (int)(want < (int64_t)g.rows_per_img ? want : (int64_t)g.rows_per_img);
+    }
+};
+
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_moments_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
+__global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    __shared__ float tab[256];
     __shared__ double red[kThreads / 32][10];
     __shared__ float redf[kThreads / 32][2];
-    __shared__ EpiSmem ep;
-    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
     Ws ws(ws_base, slots);
-    if constexpr (sizeof(T) == 1) {
-        build_l_table(tab);
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t groups = g.hw / kPix;
     const int64_t r_end = (int64_t)(blockIdx.x + 1) * g.total_rows / gridDim.x;
     for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
-        const int64_t n = r / g.rows_per_img, slot = n;
-        const int row0 = (int)(r - n * g.rows_per_img);
-        const int row1 = (int)((int64_t)row0 + (r_end - r) < (int64_t)g.rows_per_img ? (int64_t)row0 + (r_end - r) : (int64_t)g.rows_per_img);
-        r += row1 - row0;
-        const T *image = img + n * 3 * g.hw;
-        const int64_t seg_end = (int64_t)row1 * kThreads < groups ? (int64_t)row1 * kThreads : groups;
-
+        const RowSegment seg(g, r, r_end);
+        r += seg.row1 - seg.row0;
+        const int64_t slot = seg.n;
+        const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
         double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        moments_stream<T, VEC, true>(image, g.hw, seg_end, (int64_t)row0 * kThreads, kThreads, tab, acc, lo, hi);
+        moments_stream<T, VEC, true>(img + seg.n * 3 * g.hw, g.hw, seg_end, (int64_t)seg.row0 * kThreads, kThreads, nullptr, acc, lo, hi);
         {
             const float a = warp_max(-lo[0]), b = warp_max(hi[0]);
             if (lane == 0) { redf[warp][0] = a; redf[warp][1] = b; }
@@ -1252,87 +1207,154 @@ __global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_moments_kernel
             for (int k = 0; k < kThreads / 32; ++k) v = fmaxf(v, redf[k][i / 3]);
             atomic_max_f32(&ws.odrange[slot * 8 + i], v);
         }
-        if (!completes_slot(ws.status, slot, 0, row1 - row0, g.rows_per_img, &ep.s_flag)) continue;
-
-        // ---- the image's moments are complete: basis (M3-M4), fallback (L409-410), ANGLE brackets
-        SX_STAMP(ws.counters + slot * 8, 4);
-        if (threadIdx.x < 10) ep.tot[threadIdx.x] = __ldcg(ws.moments + slot * 12 + threadIdx.x);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            SlotState z = {};
-            ep.st = z;
-            ep.st.n_all = (long long)g.hw;
-            ep.st.use_all = ep.tot[0] < 3.0;
-            if (!ep.st.use_all) basis_from_moments(ep.tot, ep.st);
-        }
-        __syncthreads();
-        if (ep.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
-            double acc2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            float lo2[3] = {0, 0, 0}, hi2[3] = {0, 0, 0};
-            moments_stream<T, VEC, false>(image, g.hw, groups, 0, kThreads, tab, acc2, lo2, hi2);
-            __syncthreads();
-            block_sum10(acc2, red);
-            if (threadIdx.x < 10) ep.tot[threadIdx.x] = acc2[0];
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = ep.tot[i];
-                basis_from_moments(ep.tot, ep.st);
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) ws.moments[slot * 12 + 10] = (double)g.hw;
-        SX_STAMP(ws.counters + slot * 8, 5);
-        sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, g.hw, tab, ep, reinterpret_cast<unsigned (*)[kBins]>(scratch));
-        SX_STAMP(ws.counters + slot * 8, 6);
-        store_state(ws.state + slot, &ep.st);
-        SX_STAMP(ws.counters + slot * 8, 7);
-#ifdef SX_MK_TIMING
-        if (threadIdx.x == 0) ws.moments[slot * 12 + 11] = ep.tot[11];
-#endif
-        __syncthreads();
+        __syncthreads();  // red / redf are rewritten by the next segment
     }
 }
 
 template <typename T, bool VEC, int STAGE>
-__global__ void __launch_bounds__(kThreads, (kMinCtas<T, VEC>)) t_resolve_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
+__global__ void __launch_bounds__(kThreads) t_resolve_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    __shared__ float tab[256];
-    __shared__ EpiSmem ep;
-    __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+    __shared__ SlotState st;
+    __shared__ ResolveSmem rs;
     Ws ws(ws_base, slots);
-    if constexpr (sizeof(T) == 1) build_l_table(tab);
     const int64_t groups = g.hw / kPix;
     const int64_t r_end = (int64_t)(blockIdx.x + 1) * g.total_rows / gridDim.x;
     for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
-        const int64_t n = r / g.rows_per_img, slot = n;
-        const int row0 = (int)(r - n * g.rows_per_img);
-        const int row1 = (int)((int64_t)row0 + (r_end - r) < (int64_t)g.rows_per_img ? (int64_t)row0 + (r_end - r) : (int64_t)g.rows_per_img);
-        r += row1 - row0;
-        const T *image = img + n * 3 * g.hw;
-        const int64_t seg_end = (int64_t)row1 * kThreads < groups ? (int64_t)row1 * kThreads : groups;
-        const int64_t base = slot * 2 * kBins;
-        load_state(&ep.st, ws.state + slot);
-        resolve_pass<T, VEC, STAGE>(image, g.hw, seg_end, (int64_t)row0 * kThreads, kThreads, tab, ep.st, *reinterpret_cast<ResolveSmem *>(scratch), ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
-        if (!completes_slot(ws.status, slot, 1 + STAGE, row1 - row0, g.rows_per_img, &ep.s_flag)) continue;
+        const RowSegment seg(g, r, r_end);
+        r += seg.row1 - seg.row0;
+        const int64_t slot = seg.n, base = slot * 2 * kBins;
+        const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
+        __syncthreads();  // the previous segment has finished with `st`
+        load_state(&st, ws.state + slot);
+        resolve_pass<T, VEC, STAGE>(img + seg.n * 3 * g.hw, g.hw, seg_end, (int64_t)seg.row0 * kThreads, kThreads, nullptr, st, rs, ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
+    }
+}
 
-        // ---- the image's cells are complete: rank search; ANGLE: HE, pinv (M7-M8), CONC brackets
-        unsigned (*pre)[kBins] = reinterpret_cast<unsigned (*)[kBins]>(scratch);
-        if (threadIdx.x < 8) ep.rg[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
+// Shared memory of the per-image kernels.
+struct MidSmem {
+    SlotState st;
+    unsigned s_cnt;
+    float rg[8];
+    double tot[12];
+};
+
+// Zeroes the two shared histograms, runs the sample pass of `stage` and turns it into brackets.
+template <typename T, bool VEC, int STAGE>
+__device__ __forceinline__ void sample_and_bracket(const T *__restrict__ image, int64_t hw, MidSmem &ms, unsigned (*hist)[kBins]) {
+    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) hist[0][i] = 0u;
+    if (threadIdx.x == 0) {
+        ms.s_cnt = 0u;
+        ms.st.group_px = Pix<T, VEC>::kPix;
+    }
+    __syncthreads();
+    sample_slot<T, VEC, STAGE>(image, hw, nullptr, ms.st, hist, &ms.s_cnt);
+    __syncthreads();
+    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
+    dual_prefix<true>(hist[0], STAGE == SX_STAGE_ANGLE ? hist[0] : hist[1], hist);
+    bracket_from_prefix(STAGE, ms.st, hist, (long long)ms.s_cnt, (long long)ms.s_cnt);
+}
+
+// One CTA per image.  PHASE 0: after moments.  PHASE 1: after resolve(ANGLE).
+template <typename T, bool VEC, int PHASE>
+__global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img, int64_t hw, void *ws_base, int64_t slots) {
+    __shared__ MidSmem ms;
+    __shared__ double red[kThreads / 32][10];
+    __shared__ __align__(16) unsigned hist[2][kBins];
+    Ws ws(ws_base, slots);
+    const int64_t slot = blockIdx.x;
+    const T *image = img + slot * 3 * hw;
+    if constexpr (PHASE == 0) {
+        // ---- basis (M3-M4), fallback (L409-410), ANGLE brackets
+        if (threadIdx.x < 10) ms.tot[threadIdx.x] = ws.moments[slot * 12 + threadIdx.x];
         __syncthreads();
-        select_slot(ws, slot, STAGE, ep.st, ep.rg, pre);
-        __syncthreads();
-        if constexpr (STAGE == SX_STAGE_ANGLE) {
-            // re-arm the slot's cells and counters for the CONC stage
-            for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
-                ws.hist2[base + i] = 0u;
-                ws.vmin[base + i] = INFINITY;
-                ws.vmax[base + i] = -INFINITY;
-            }
-            if (threadIdx.x < 4) ws.counters[slot * 8 + threadIdx.x] = 0ull;
-            sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, g.hw, tab, ep, pre);
+        if (threadIdx.x == 0) {
+            SlotState z = {};
+            ms.st = z;
+            ms.st.n_all = (long long)hw;
+            ms.st.use_all = ms.tot[0] < 3.0;
+            if (!ms.st.use_all) basis_from_moments(ms.tot, ms.st);
         }
-        store_state(ws.state + slot, &ep.st);
         __syncthreads();
+        if (ms.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
+            double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+            moments_stream<T, VEC, false>(image, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, nullptr, acc, lo, hi);
+            block_sum10(acc, red);
+            if (threadIdx.x < 10) ms.tot[threadIdx.x] = acc[0];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = ms.tot[i];
+                basis_from_moments(ms.tot, ms.st);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ws.moments[slot * 12 + 10] = (double)hw;
+        sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, hw, ms, hist);
+    } else {
+        // ---- rank search, HE, pinv (M7-M8), CONC brackets
+        const int64_t base = slot * 2 * kBins;
+        if (threadIdx.x < 8) ms.rg[threadIdx.x] = ws.odrange[slot * 8 + threadIdx.x];
+        load_state(&ms.st, ws.state + slot);
+        select_slot(ws, slot, SX_STAGE_ANGLE, ms.st, ms.rg, hist);
+        __syncthreads();
+        // re-arm the slot's cells and counters for the CONC stage
+        for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+            ws.hist2[base + i] = 0u;
+            ws.vmin[base + i] = INFINITY;
+            ws.vmax[base + i] = -INFINITY;
+        }
+        if (threadIdx.x < 8) ws.counters[slot * 8 + threadIdx.x] = 0ull;
+        sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, hw, ms, hist);
+    }
+    store_state(ws.state + slot, &ms.st);
+}
+
+// uint8 in, float32 out (OUT 1: [0,255], OUT 2: [0,1]): FOUR pixels per thread.  With 16 pixels per
+// thread each lane would store 64 contiguous bytes per plane, i.e. every 128-bit store of a warp
+// hits 32 different half-filled sectors (measured: 3.3 TB/s); with 4 pixels a warp's store is one
+// contiguous 512-byte run, exactly like the float32 path, and its load one 128-byte run.
+template <int OUT>
+__global__ void __launch_bounds__(kThreads) apply_u8_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, PassGeom g, int64_t slot0, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, void *ws_base, int64_t slots) {
+    __shared__ float coef[12];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = slot0 + n;
+    apply_coefficients<float, 1>(coef, he_ref, maxc_ref, ws.state[slot].pinv, ws.fit[slot * 8 + 6], ws.fit[slot * 8 + 7]);
+    __syncthreads();
+    float A[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) A[c][k] = coef[c * 4 + k];
+    const uint8_t *image = img + n * 3 * g.hw;
+    float *oimg = out + n * 3 * g.hw;
+    const int64_t groups = g.hw / 4, stride = (int64_t)g.cpi * kThreads;
+    int64_t gi = (int64_t)chunk * kThreads + threadIdx.x;
+    unsigned cur[3] = {0u, 0u, 0u}, nxt[3] = {0u, 0u, 0u};
+    auto load = [&](int64_t i, unsigned (&w)[3]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w[c]) : "l"(image + c * g.hw + i * 4));
+    };
+    if (gi < groups) load(gi, cur);
+    for (; gi < groups; gi += stride) {
+        if (gi + stride < groups) load(gi + stride, nxt);
+        float l[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { l[c][0] = u8_l<0>(cur[c]); l[c][1] = u8_l<1>(cur[c]); l[c][2] = u8_l<2>(cur[c]); l[c][3] = u8_l<3>(cur[c]); }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float e = __fmaf_rn(A[c][2], l[2][k], __fmaf_rn(A[c][1], l[1][k], __fmaf_rn(A[c][0], l[0][k], A[c][3])));
+                const float q = trunc_small(fminf(fast_ex2(e), 255.0f));  // the reference truncates to uint8 first (L560)
+                o[k] = OUT == 2 ? div255_exact(q) : q;
+            }
+            st_stream(reinterpret_cast<float4 *>(oimg + c * g.hw + gi * 4), make_float4(o[0], o[1], o[2], o[3]));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cur[c] = nxt[c];
     }
 }
 
@@ -1551,6 +1573,15 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
     const int64_t hw = h * w;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool vec = images_vec_ok(images, out, dtype, hw);
+    if (dtype == SX_U8 && out_dtype == SX_F32 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(images) & 3u) == 0 && aligned16(out)) {
+        PassGeom g = make_geom(n, hw, 4);
+        const unsigned grid = (unsigned)(n * g.cpi);
+        const uint8_t *p = static_cast<const uint8_t *>(images);
+        if (unit) apply_u8_f32_kernel<2><<<grid, kThreads, 0, stream>>>(p, static_cast<float *>(out), g, slot0, he_ref, maxc_ref, workspace, slots);
+        else apply_u8_f32_kernel<1><<<grid, kThreads, 0, stream>>>(p, static_cast<float *>(out), g, slot0, he_ref, maxc_ref, workspace, slots);
+        SX_LAUNCHED("macenko::apply_u8_f32_kernel");
+        return SX_OK;
+    }
     SX_DISPATCH_TV(dtype, vec, {
         PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
         const unsigned grid = (unsigned)(n * g.cpi);
@@ -1583,8 +1614,7 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
             }
         return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
     }
-    // Per-image pipeline: three statistics passes whose last CTA per image runs the per-image steps,
-    // then the reconstruction.
+    // Per-image pipeline (see "per-image transform pipeline" above).
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         const T *p = static_cast<const T *>(images);
@@ -1594,12 +1624,15 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
         g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
         g.total_rows = n * g.rows_per_img;
         t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-        note_launch();
+        mid_kernel<T, VEC, 0><<<(unsigned)n, kThreads, 0, stream>>>(p, hw, workspace, n);
         t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-        note_launch();
+        mid_kernel<T, VEC, 1><<<(unsigned)n, kThreads, 0, stream>>>(p, hw, workspace, n);
         t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
     });
+    note_launch(4);
     SX_LAUNCHED("macenko::transform pipeline");
+    select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, n, 0, SX_STAGE_CONC);
+    SX_LAUNCHED("macenko::select_kernel");
     return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
 }
 
