@@ -722,24 +722,25 @@ __device__ __forceinline__ void resolve_pass(const T *__restrict__ image, int64_
     if (threadIdx.x < 2 && rs.below[threadIdx.x]) atomicAdd(&counters[threadIdx.x], (unsigned long long)rs.below[threadIdx.x]);
 }
 
-// The sample pass of one slot run by ONE CTA (per-image kernels of the transform pipeline): the
-// same hashed groups and keys as sample_kernel, histograms in shared memory (zeroed by the
-// caller), sampled rows counted in *s_cnt.  Loads are issued eight groups at a time.
+// The sample pass of one slot, split over `parts` CTAs (per-image kernels of the transform
+// pipeline): the same hashed groups and keys as sample_kernel, histograms in shared memory (zeroed
+// by the caller), sampled rows counted in *s_cnt.  Loads are issued up to four groups at a time.
 template <typename T, bool VEC, int STAGE>
-__device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw, const float *tab, const SlotState &st, unsigned (*hist)[kBins], unsigned *s_cnt) {
+__device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw, const float *tab, const SlotState &st, unsigned (*hist)[kBins], unsigned *s_cnt, int part, int parts) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    constexpr int kBatch = 8;
+    constexpr int kBatch = 4;
     const int64_t groups = hw / kPix;
     const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
     const int64_t nsamp = groups / stride;
     const RankParams rp(st);
     const float c_lo0 = st.c_lo[0], c_lo1 = st.c_lo[1], c_sc0 = st.c_scale[0], c_sc1 = st.c_scale[1];
     unsigned cnt = 0;
-    for (int64_t i0 = threadIdx.x; i0 < nsamp; i0 += (int64_t)kBatch * kThreads) {
+    const int64_t step = (int64_t)parts * kThreads;  // CTA `part` of `parts` takes samples part * kThreads + t, + step, ...
+    for (int64_t i0 = (int64_t)part * kThreads + threadIdx.x; i0 < nsamp; i0 += (int64_t)kBatch * step) {
         RawGroup<T, VEC> raw[kBatch];
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            const int64_t i = i0 + (int64_t)b * kThreads;
+            const int64_t i = i0 + (int64_t)b * step;
             if (i < nsamp) {
                 const unsigned off = stride > 1 ? __umulhi(mix32((unsigned)i * 0x9e3779b9u + 0x85ebca6bu), (unsigned)stride) : 0u;
                 raw[b].load(image + (i * stride + off) * kPix, hw);
@@ -747,7 +748,7 @@ __device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw
         }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-            if (i0 + (int64_t)b * kThreads >= nsamp) break;
+            if (i0 + (int64_t)b * step >= nsamp) break;
             float l[3][kPix];
             raw[b].to_l(tab, l);
 #pragma unroll
@@ -1143,12 +1144,12 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
 }
 
 // ---- per-image transform pipeline ------------------------------------------------------------
-// sx_macenko_transform chains EIGHT launches: three lean streaming kernels over the batch (moments,
-// resolve ANGLE, resolve CONC), the reconstruction, and between them one-CTA-per-image kernels that
-// each do ALL the per-image work due at that point:
-//   mid<0>  after moments:       basis (M3-M4), masked-row fallback (L409-410), ANGLE sample + bracket
-//   mid<1>  after resolve ANGLE: rank search, HE / pinv (M7-M8), CONC sample + bracket
-//   select  after resolve CONC:  rank search -> maxC (M9)
+// sx_macenko_transform chains TEN launches: init, three lean streaming kernels over the batch
+// (moments, resolve ANGLE, resolve CONC), the reconstruction, and between them small per-image kernels:
+//   mid<ANGLE>    after moments:       basis (M3-M4), masked-row fallback (L409-410), ANGLE sample + bracket
+//   select(ANGLE) after resolve ANGLE: rank search, HE / pinv (M7-M8)
+//   mid<CONC>     then:                CONC sample + bracket
+//   select(CONC)  after resolve CONC:  rank search -> maxC (M9)
 // The phase-level API needs 13 launches for the same work because a sharded fit must all-reduce
 // between them.  (Folding the per-image steps into the tail of the streaming kernels -- "last CTA of
 // an image finishes it" -- was built and measured: the extra registers and shared memory slowed the
@@ -1234,37 +1235,28 @@ __global__ void __launch_bounds__(kThreads) t_resolve_kernel(const T *__restrict
 struct MidSmem {
     SlotState st;
     unsigned s_cnt;
-    float rg[8];
+    int s_last;
     double tot[12];
 };
 
-// Zeroes the two shared histograms, runs the sample pass of `stage` and turns it into brackets.
-template <typename T, bool VEC, int STAGE>
-__device__ __forceinline__ void sample_and_bracket(const T *__restrict__ image, int64_t hw, MidSmem &ms, unsigned (*hist)[kBins]) {
-    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) hist[0][i] = 0u;
-    if (threadIdx.x == 0) {
-        ms.s_cnt = 0u;
-        ms.st.group_px = Pix<T, VEC>::kPix;
-    }
-    __syncthreads();
-    sample_slot<T, VEC, STAGE>(image, hw, nullptr, ms.st, hist, &ms.s_cnt);
-    __syncthreads();
-    // ANGLE: both queries read histogram 0; CONC: query q reads histogram q
-    dual_prefix<true>(hist[0], STAGE == SX_STAGE_ANGLE ? hist[0] : hist[1], hist);
-    bracket_from_prefix(STAGE, ms.st, hist, (long long)ms.s_cnt, (long long)ms.s_cnt);
-}
+// Per-image step before a resolve pass, kMidParts CTAs per image: (ANGLE only: basis M3-M4 and the
+// masked-row fallback L409-410, computed redundantly by every CTA of the image -- identical inputs,
+// identical results), then each CTA samples its share of the image's sample groups into a
+// shared-memory histogram and adds it to the slot's global sample histogram; the CTA that arrives
+// last turns the histogram into the brackets of the stage and stores the slot's state.
+constexpr int kMidParts = 8;
 
-// One CTA per image.  PHASE 0: after moments.  PHASE 1: after resolve(ANGLE).
-template <typename T, bool VEC, int PHASE>
+template <typename T, bool VEC, int STAGE>
 __global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img, int64_t hw, void *ws_base, int64_t slots) {
     __shared__ MidSmem ms;
     __shared__ double red[kThreads / 32][10];
     __shared__ __align__(16) unsigned hist[2][kBins];
     Ws ws(ws_base, slots);
-    const int64_t slot = blockIdx.x;
+    const int64_t slot = blockIdx.x / kMidParts;
+    const int part = blockIdx.x % kMidParts;
     const T *image = img + slot * 3 * hw;
-    if constexpr (PHASE == 0) {
-        // ---- basis (M3-M4), fallback (L409-410), ANGLE brackets
+    const int64_t base = slot * 2 * kBins;
+    if constexpr (STAGE == SX_STAGE_ANGLE) {
         if (threadIdx.x < 10) ms.tot[threadIdx.x] = ws.moments[slot * 12 + threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1282,30 +1274,40 @@ __global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img
             block_sum10(acc, red);
             if (threadIdx.x < 10) ms.tot[threadIdx.x] = acc[0];
             __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = ms.tot[i];
-                basis_from_moments(ms.tot, ms.st);
-            }
+            if (threadIdx.x == 0) basis_from_moments(ms.tot, ms.st);
             __syncthreads();
         }
-        if (threadIdx.x == 0) ws.moments[slot * 12 + 10] = (double)hw;
-        sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, hw, ms, hist);
     } else {
-        // ---- rank search, HE, pinv (M7-M8), CONC brackets
-        const int64_t base = slot * 2 * kBins;
-        if (threadIdx.x < 8) ms.rg[threadIdx.x] = ws.odrange[slot * 8 + threadIdx.x];
         load_state(&ms.st, ws.state + slot);
-        select_slot(ws, slot, SX_STAGE_ANGLE, ms.st, ms.rg, hist);
-        __syncthreads();
-        // re-arm the slot's cells and counters for the CONC stage
-        for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
-            ws.hist2[base + i] = 0u;
-            ws.vmin[base + i] = INFINITY;
-            ws.vmax[base + i] = -INFINITY;
-        }
-        if (threadIdx.x < 8) ws.counters[slot * 8 + threadIdx.x] = 0ull;
-        sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, hw, ms, hist);
     }
+    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) hist[0][i] = 0u;
+    if (threadIdx.x == 0) {
+        ms.s_cnt = 0u;
+        ms.st.group_px = Pix<T, VEC>::kPix;
+    }
+    __syncthreads();
+    sample_slot<T, VEC, STAGE>(image, hw, nullptr, ms.st, hist, &ms.s_cnt, part, kMidParts);
+    __syncthreads();
+    constexpr int kQ = STAGE == SX_STAGE_CONC ? 2 : 1;
+    for (int i = threadIdx.x; i < kQ * kBins; i += kThreads)
+        if (hist[0][i]) atomicAdd(&ws.hist1[base + i], hist[0][i]);
+    if (threadIdx.x == 0 && ms.s_cnt) {
+        atomicAdd(&ws.counters[slot * 8 + 2], (unsigned long long)ms.s_cnt);
+        if (kQ == 2) atomicAdd(&ws.counters[slot * 8 + 3], (unsigned long long)ms.s_cnt);
+    }
+    __threadfence();  // this thread's global atomics are visible before the arrival below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ms.s_last = atomicAdd(&ws.status[slot * 4 + 1 + STAGE], 1) == kMidParts - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (!ms.s_last) return;
+    if (STAGE == SX_STAGE_ANGLE && threadIdx.x < 11) {  // the moments the basis was computed from (fallback: every row)
+        if (ms.st.use_all && threadIdx.x < 10) ws.moments[slot * 12 + threadIdx.x] = ms.tot[threadIdx.x];
+        if (threadIdx.x == 10) ws.moments[slot * 12 + 10] = (double)hw;
+    }
+    bracket_slot(ws, slot, STAGE, ms.st, hist);
     store_state(ws.state + slot, &ms.st);
 }
 
@@ -1624,12 +1626,13 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
         g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
         g.total_rows = n * g.rows_per_img;
         t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-        mid_kernel<T, VEC, 0><<<(unsigned)n, kThreads, 0, stream>>>(p, hw, workspace, n);
+        mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, workspace, n);
         t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-        mid_kernel<T, VEC, 1><<<(unsigned)n, kThreads, 0, stream>>>(p, hw, workspace, n);
+        select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, n, 0, SX_STAGE_ANGLE);
+        mid_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, workspace, n);
         t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
     });
-    note_launch(4);
+    note_launch(5);
     SX_LAUNCHED("macenko::transform pipeline");
     select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, n, 0, SX_STAGE_CONC);
     SX_LAUNCHED("macenko::select_kernel");
