@@ -25,6 +25,7 @@
 // distinct value (the normal case: a bracket is ~1 % of the data), else it is interpolated inside
 // a cell of width <= bracket/4096.  The nearest-rank index is exact: ranks below the bracket are
 // counted, not estimated.
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1162,7 +1163,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
 // contiguous rows [c R / grid, (c + 1) R / grid) -- equal work for every CTA whatever the batch and
 // image sizes, at most two images per CTA for batches larger than the grid.
 struct RowGeom {
-    int64_t n_img, hw, total_rows;
+    int64_t n_img, hw, total_rows, slot0;  // image i of this launch uses statistics slot slot0 + i
     int rows_per_img;
 };
 
@@ -1190,7 +1191,7 @@ __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict
     for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
         const RowSegment seg(g, r, r_end);
         r += seg.row1 - seg.row0;
-        const int64_t slot = seg.n;
+        const int64_t slot = g.slot0 + seg.n;
         const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
         double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -1223,7 +1224,7 @@ __global__ void __launch_bounds__(kThreads) t_resolve_kernel(const T *__restrict
     for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
         const RowSegment seg(g, r, r_end);
         r += seg.row1 - seg.row0;
-        const int64_t slot = seg.n, base = slot * 2 * kBins;
+        const int64_t slot = g.slot0 + seg.n, base = slot * 2 * kBins;
         const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
         __syncthreads();  // the previous segment has finished with `st`
         load_state(&st, ws.state + slot);
@@ -1247,14 +1248,14 @@ struct MidSmem {
 constexpr int kMidParts = 8;
 
 template <typename T, bool VEC, int STAGE>
-__global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img, int64_t hw, void *ws_base, int64_t slots) {
+__global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img, int64_t hw, int64_t slot0, void *ws_base, int64_t slots) {
     __shared__ MidSmem ms;
     __shared__ double red[kThreads / 32][10];
     __shared__ __align__(16) unsigned hist[2][kBins];
     Ws ws(ws_base, slots);
-    const int64_t slot = blockIdx.x / kMidParts;
+    const int64_t slot = slot0 + blockIdx.x / kMidParts;
     const int part = blockIdx.x % kMidParts;
-    const T *image = img + slot * 3 * hw;
+    const T *image = img + (int64_t)(blockIdx.x / kMidParts) * 3 * hw;
     const int64_t base = slot * 2 * kBins;
     if constexpr (STAGE == SX_STAGE_ANGLE) {
         if (threadIdx.x < 10) ms.tot[threadIdx.x] = ws.moments[slot * 12 + threadIdx.x];
@@ -1380,6 +1381,7 @@ __global__ void init_kernel(void *ws_base, int64_t slots) {
 }
 
 static int g_ctas_per_sm = 4;
+static int g_split = 3;          // chains (streams) a large batch is split into
 static int g_phase_kernels = 0;  // development: sx_macenko_transform through the phase-level API (one launch per step)
 
 static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_override = -1) {
@@ -1435,11 +1437,68 @@ static bool images_vec_ok(const void *images, const void *out, int dtype, int64_
     return in_ok && (out == nullptr || aligned16(out));
 }
 
+extern "C" int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, sx_stream_t stream_);
+
+// One chain of the per-image pipeline for images [0, n) -> slots [slot0, slot0 + n) on `stream`.
+static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream) {
+    const int64_t hw = h * w;
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        const T *p = static_cast<const T *>(images);
+        RowGeom g;
+        g.n_img = n;
+        g.hw = hw;
+        g.slot0 = slot0;
+        g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
+        g.total_rows = n * g.rows_per_img;
+        t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+        mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
+        t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+        select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, slots, slot0, SX_STAGE_ANGLE);
+        mid_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
+        t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+    });
+    note_launch(5);
+    SX_LAUNCHED("macenko::transform pipeline");
+    select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, slots, slot0, SX_STAGE_CONC);
+    SX_LAUNCHED("macenko::select_kernel");
+    return sx_macenko_apply(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream);
+}
+
+// Side stream of the calling thread's current device (created on first use, never destroyed: the
+// library owns no device memory, only this stream and two events per device).
+constexpr int kMaxChains = 4;
+struct SideStream {
+    cudaStream_t stream[kMaxChains - 1] = {};
+    cudaEvent_t fork = nullptr, join[kMaxChains - 1] = {};
+    std::mutex mu;
+};
+static SideStream *side_stream() {
+    static SideStream table[64];
+    static std::mutex init_mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(init_mu);
+    SideStream &s = table[dev];
+    if (s.fork == nullptr) {
+        for (int i = 0; i < kMaxChains - 1; ++i) {
+            if (cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &s;
+}
+
 extern "C" {
 
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels) {
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
-    if (phase_kernels >= 0) g_phase_kernels = phase_kernels != 0;
+    if (phase_kernels >= 0) {  // bit 0: phase-level chain; bits 4..: number of chains (0: default)
+        g_phase_kernels = (phase_kernels & 1) != 0;
+        const int chains = (int)(phase_kernels >> 4);
+        g_split = chains > 0 ? (chains < kMaxChains ? chains : kMaxChains) : 3;
+    }
     return SX_OK;
 }
 
@@ -1616,27 +1675,33 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
             }
         return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
     }
-    // Per-image pipeline (see "per-image transform pipeline" above).
-    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
-    SX_DISPATCH_TV(dtype, vec, {
-        const T *p = static_cast<const T *>(images);
-        RowGeom g;
-        g.n_img = n;
-        g.hw = hw;
-        g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
-        g.total_rows = n * g.rows_per_img;
-        t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-        mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, workspace, n);
-        t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-        select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, n, 0, SX_STAGE_ANGLE);
-        mid_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, workspace, n);
-        t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, n);
-    });
-    note_launch(5);
-    SX_LAUNCHED("macenko::transform pipeline");
-    select_kernel<<<(unsigned)n, kThreads, 0, stream>>>(workspace, n, 0, SX_STAGE_CONC);
-    SX_LAUNCHED("macenko::select_kernel");
-    return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
+    // Per-image pipeline (see "per-image transform pipeline" above).  Large batches run as up to
+    // kMaxChains part-batch chains, all but the first on side streams: the small per-image kernels of one chain
+    // (~25 us per stage of dependent global round trips on a few SMs) overlap the streaming kernels
+    // of the other.  The caller's stream forks into the side stream and joins it again, so the call
+    // keeps its stream-ordered, host-asynchronous contract (and can be captured into a CUDA graph).
+    const int64_t in_bytes = (dtype == SX_F32 ? 4 : 1) * 3 * hw, out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * hw;
+    int chains = g_split;
+    if (n * in_bytes < ((int64_t)64 << 20)) chains = 1;
+    while (chains > 1 && n / chains < 4) --chains;
+    if (chains <= 1) return run_pipeline(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, stream);
+    SideStream *side = side_stream();
+    SX_REQUIRE(side != nullptr, "could not create the side streams");
+    std::lock_guard<std::mutex> lock(side->mu);
+    SX_CUDA(cudaEventRecord(side->fork, stream));
+    rc = SX_OK;
+    for (int c = 0; c < chains; ++c) {  // chain 0 on the caller's stream, chain c > 0 on side stream c - 1
+        const int64_t i0 = n * c / chains, i1 = n * (c + 1) / chains;
+        cudaStream_t cs = c == 0 ? stream : side->stream[c - 1];
+        if (c > 0) SX_CUDA(cudaStreamWaitEvent(cs, side->fork, 0));
+        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, n, cs);
+        if (r && !rc) rc = r;
+        if (c > 0) {
+            SX_CUDA(cudaEventRecord(side->join[c - 1], cs));
+            SX_CUDA(cudaStreamWaitEvent(stream, side->join[c - 1], 0));
+        }
+    }
+    return rc;
 }
 
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t s) {

@@ -162,6 +162,9 @@ def probe_macenko():
     lib.sx_macenko_set_tuning(-1, 1)
     want = ops.macenko_transform(src, he, maxc, unit=True)
     report("macenko transform f32 64x1024^2 phase kernels", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
+    for chains in (1, 2, 3, 4):
+        lib.sx_macenko_set_tuning(-1, chains << 4)
+        report(f"macenko transform f32 64x1024^2 pipeline, {chains} chain(s)", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=10), 24 * px)
     lib.sx_macenko_set_tuning(-1, 0)
     got = ops.macenko_transform(src, he, maxc, unit=True)
     err = float((got - want).abs().max())
@@ -171,9 +174,9 @@ def probe_macenko():
     del want, got
     src8 = (src * 255).to(torch.uint8)
     del src, out
-    for phase in (1, 0):
+    for phase in (1, 16, 32, 64):
         lib.sx_macenko_set_tuning(-1, phase)
-        tag = "phase kernels" if phase else "pipeline"
+        tag = "phase kernels" if phase == 1 else f"pipeline {phase >> 4} chain(s)"
         report(f"macenko transform u8 -> u8 {tag}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=False), steps=5), 6 * px)
         report(f"macenko transform u8 -> f32 unit {tag}", timeit(lambda: ops.macenko_transform(src8, he, maxc, unit=True), steps=5), 15 * px)
     big = src8.reshape(16, 3, 2048, 2048)
