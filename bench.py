@@ -318,7 +318,7 @@ def main() -> None:
     # ---- roofline of the dominant kernel (algorithmic bytes / live CUDA-event time) ----------
     px = n_img * H * W
     kernels = {
-        "hm::hist_u8_planar_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
+        "hm::hist_u8_planar_lane_tma_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
         "hm::apply_u8_planar_kernel": {"algo_bytes": 6.0 * px, "ms": apply_ms},
     }
     for k in kernels.values():
@@ -355,22 +355,30 @@ def main() -> None:
     e2e_run(3)
     if not torch.equal(host_outs[0], step(False).cpu()):
         raise SystemExit("e2e result differs from the device-resident result")
-    barrier()
-    e0, e1 = ev(), ev()
-    e0.record()
-    e2e_run(e2e_steps)
-    pipe.synchronize()
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
-    # the same without overlap (one batch at a time), for reference
-    t0 = time.perf_counter()
-    for _ in range(3):
-        pipe.submit(host_in, host_outs[0]).wait()
-    serial_ms = (time.perf_counter() - t0) / 3 * 1e3
+
+    def e2e_time(fn, steps: int) -> float:
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        fn(steps)
+        pipe.synchronize()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def e2e_serial(steps: int) -> None:  # one batch in flight: H2D, kernels, D2H back to back
+        for _ in range(steps):
+            pipe.submit(host_in, host_outs[0]).wait()
+
+    # Whether both PCIe directions can run at once at full rate depends on the host (NUMA placement
+    # of the pinned buffers, PCIe switch): measure the pipelined and the one-batch-at-a-time mode of
+    # the same API and report the faster one, naming it.
+    overlapped_ms = e2e_time(e2e_run, e2e_steps)
+    serial_ms = e2e_time(e2e_serial, max(3, e2e_steps // 2))
+    e2e_ms = min(overlapped_ms, serial_ms)
     e2e = {"value": mp_per_gpu * world / (e2e_ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": host_in.numel(), "d2h_bytes_per_step": host_outs[0].numel(), "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "serial_ms_per_step": serial_ms,
-           "api": "stainx_b200.ingest.HostStream(HistogramMatching(backend='torch_cuda')).submit(pinned uint8 batch, pinned out): H2D + transform + D2H per step, depth-2 pipeline"}
+           "mode": "pipelined (depth 2)" if overlapped_ms <= serial_ms else "one batch in flight", "pipelined_ms_per_step": overlapped_ms, "serial_ms_per_step": serial_ms,
+           "api": "stainx_b200.ingest.HostStream(HistogramMatching(backend='torch_cuda')).submit(pinned uint8 batch, pinned out): H2D + transform + D2H per step"}
     del pipe
 
     # ---- side measurements: the other two methods (informative; N=1 only) ---------------------
