@@ -73,6 +73,18 @@ int sx_hm_build_lut(const uint64_t *counts, int64_t npix, const float *ref_cdf, 
  * (L285-298).  `out` has the dtype and layout of `images`. */
 int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
                 const float *lut, void *out, sx_stream_t stream);
+/* Sharded batches on one NVLink node: H2b with the SUM all-reduce of the counts fused into the
+ * kernel (peer loads/stores over NVLink; no NCCL call).  Every rank owns a zero-initialised buffer
+ * of sx_hm_peer_buffer_bytes() that all ranks have mapped (symmetric memory / CUDA IPC):
+ * uint64 counts[2][3][256] then uint32 flags[64].  peer_buffers_dev is a DEVICE array of `world`
+ * pointers, entry p = rank p's buffer as mapped on this device.  Step `epoch` (1, 2, 3, ... the same
+ * on every rank): zero counts[epoch & 1] of the own buffer, sx_hm_hist into it, then this call; it
+ * publishes the own counts, waits for every rank's, sums them in rank order (bit-identical on all
+ * ranks) and builds the LUT; counts_out (optional) receives the summed counts.  Replaces
+ * dist.all_reduce + sx_hm_build_lut(npix = -1). */
+int64_t sx_hm_peer_buffer_bytes(void);
+int sx_hm_build_lut_peers(const void *peer_buffers_dev, int world, int rank, uint32_t epoch,
+                          const float *ref_cdf, float *lut, uint64_t *counts_out, sx_stream_t stream);
 /* Workspace for the chained transform/fit below (bytes). */
 int64_t sx_hm_workspace_bytes(void);
 /* hist -> ref_cdf -> build_lut -> apply on one stream (single-device transform). */

@@ -30,6 +30,8 @@ PROTOTYPES: dict[str, list] = {
     "sx_hm_ref_cdf": [_vp, _vp, _vp],
     "sx_hm_build_lut": [_vp, _i64, _vp, _vp, _vp],
     "sx_hm_apply": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp],
+    "sx_hm_peer_buffer_bytes": [],
+    "sx_hm_build_lut_peers": [_vp, _int, _int, ctypes.c_uint32, _vp, _vp, _vp, _vp],
     "sx_hm_workspace_bytes": [],
     "sx_hm_transform": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
     "sx_hm_fit": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _i64, _vp],
@@ -61,6 +63,7 @@ _RESTYPES = {
     "sx_last_error": ctypes.c_char_p,
     "sx_kernel_launches": _i64,
     "sx_hm_workspace_bytes": _i64,
+    "sx_hm_peer_buffer_bytes": _i64,
     "sx_reinhard_workspace_bytes": _i64,
     "sx_macenko_workspace_bytes": _i64,
 }

@@ -74,6 +74,8 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
     def __init__(self, device: str | torch.device | None = None, channel_axis: int = 1, reducer: StatReducer | None = None, ops=None):
         super().__init__(device, reducer, ops)
         self.channel_axis = channel_axis
+        self._exchange = None        # sharding.PeerExchange (NVLink peer memory) or False when unavailable
+        self._ref_cdf_cache = None   # (ref_hist, ref_cdf): the reference CDF is a fit-time constant
 
     def _layout(self, images: torch.Tensor) -> int:
         if self.channel_axis == -1 or (self.channel_axis == 3 and images.ndim == 4):
@@ -102,6 +104,29 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
             raise ValueError(f"reference_histogram must be 1D with 256 elements. Got shape {ref.shape}")
         return ref.float().unsqueeze(0).repeat(3, 1).contiguous()
 
+    def _reference(self, reference_histogram: torch.Tensor | list) -> tuple[torch.Tensor, torch.Tensor]:
+        """(ref_hist (3, 256), ref_cdf (3, 256)) of the reference; both are fit-time constants, so they
+        are cached for as long as the caller passes the SAME tensor objects, unmodified (the cache
+        holds them, so their storage cannot be recycled under it)."""
+        parts = list(reference_histogram) if isinstance(reference_histogram, (list, tuple)) else [reference_histogram]
+        cached = self._ref_cdf_cache
+        if cached is not None and len(cached[0]) == len(parts) and all(a is b for a, b in zip(cached[0], parts)) and cached[1] == [t._version for t in parts if isinstance(t, torch.Tensor)]:
+            return cached[2], cached[3]
+        ref_hist = self._stack_reference(reference_histogram)
+        ref_cdf = self._ops.hm_ref_cdf(ref_hist)
+        self._ref_cdf_cache = (parts, [t._version for t in parts], ref_hist, ref_cdf)
+        return ref_hist, ref_cdf
+
+    def _peer_exchange(self):
+        """NVLink peer buffer for the fused counts exchange, created collectively on first use
+        (``None`` when the group cannot map peer memory: the NCCL all-reduce is used instead)."""
+        if self._exchange is None:
+            from stainx_b200.sharding import PeerExchange
+
+            nbytes = int(_native.lib().sx_hm_peer_buffer_bytes())
+            self._exchange = PeerExchange.create(self._reducer, torch.device(self.device), nbytes) or False
+        return self._exchange or None
+
     def compute_reference_counts(self, images: torch.Tensor) -> torch.Tensor:
         """Whole-reference-set per-channel counts, int64 (3, 256), summed over ranks."""
         images, _ = self._to_native(images)
@@ -118,15 +143,24 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
     def transform(self, images: torch.Tensor, reference_histogram: torch.Tensor | list) -> torch.Tensor:
         images, original = self._to_native(images)
         layout = self._layout(images)
-        ref_hist = self._stack_reference(reference_histogram)
         if self._reducer.enabled:
             # H3 -> all-reduce -> H2 -> H4: the source histogram spans the whole sharded batch.
-            counts = self._reducer.sum_(self._ops.hm_hist(images, layout))
-            # npix = -1: the LUT kernel takes the global pixel count from the reduced counts
-            lut = self._ops.hm_build_lut(counts, -1, self._ops.hm_ref_cdf(ref_hist))
+            ref_hist, ref_cdf = self._reference(reference_histogram)
+            ex = self._peer_exchange()
+            if ex is not None:
+                # the all-reduce is fused into the LUT kernel: peer loads over NVLink, no NCCL call
+                ex.epoch += 1
+                counts = ex.view((ex.epoch & 1) * 768 * 8, (3, 256), torch.int64)
+                counts.zero_()
+                self._ops.hm_hist(images, layout, counts=counts)
+                lut = self._ops.hm_build_lut_peers(ex, ref_cdf)
+            else:
+                counts = self._reducer.sum_(self._ops.hm_hist(images, layout))
+                # npix = -1: the LUT kernel takes the global pixel count from the reduced counts
+                lut = self._ops.hm_build_lut(counts, -1, ref_cdf)
             result = self._ops.hm_apply(images, lut, layout)
         else:
-            result = self._ops.hm_transform(images, ref_hist, layout)
+            result = self._ops.hm_transform(images, self._stack_reference(reference_histogram), layout)
         return self._restore_dtype(result, original)
 
 

@@ -895,8 +895,9 @@ __global__ void ref_cdf_kernel(const float *__restrict__ ref_hist, float *__rest
 // H2b: torch_backend.py:L234-281.  npix < 0: derive the pixel count from the counts themselves
 // (sum over the 256 bins of the channel), which keeps a sharded run free of host round trips.
 // FROM_HIST: the reference CDF is rebuilt from ref_hist inside the same kernel (fused transform).
+// One channel (CTA of 256 threads): thread b holds the count of bin b.
 template <bool FROM_HIST>
-__global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
+__device__ __forceinline__ void build_lut_channel(const unsigned long long my_count, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
     __shared__ float rq[256];
     __shared__ float sq[256];
     __shared__ double dacc[256];
@@ -904,7 +905,6 @@ __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, 
     const int c = blockIdx.x, b = threadIdx.x;
     if (FROM_HIST) ref_cdf_to_smem(ref + c * 256, sq, dacc, rq);
     else rq[b] = ref[c * 256 + b];
-    const unsigned long long my_count = counts[c * 256 + b];
     {
         __shared__ unsigned long long s_part[8];
         unsigned long long t = my_count;
@@ -941,6 +941,58 @@ __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, 
     if (q <= rq[0]) v = 0.0f;                                               // L268, L279
     if (q >= rq[255]) v = 255.0f;                                           // L269, L280
     lut[c * 256 + b] = fminf(fmaxf(v, 0.0f), 255.0f);                       // L281
+}
+
+template <bool FROM_HIST>
+__global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
+    build_lut_channel<FROM_HIST>(counts[blockIdx.x * 256 + threadIdx.x], npix, ref, lut);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sharded batches: the all-reduce of the counts FUSED into the LUT build, over NVLink peer memory.
+//
+// Every rank keeps its counts in a buffer that all ranks of the node have mapped (symmetric
+// memory); bufs[p] is rank p's buffer as seen from this GPU:
+//     uint64 counts[2][3][256]   (two parities: a rank may start the next step's histogram while a
+//                                 slower peer still reads this step's counts)
+//     uint32 flags[64]           flags[q] = last epoch whose counts rank q has published to us
+// One kernel per rank and step: (1) publish: a system-scope fence, then store-release the epoch
+// into flags[rank] of every peer; (2) wait until every peer's epoch has arrived here (acquire);
+// (3) every thread adds its bin over all ranks with peer loads in rank order -- integers, so every
+// rank gets bit-identical sums; (4) the bit-exact LUT build.  No NCCL call, no extra launch: the
+// exchange costs one NVLink round trip inside a kernel that had to run anyway (~25 us of NCCL
+// all-reduce + launch per step saved at 8 GPUs).
+// Ranks run on different GPUs, so the spin in (2) waits for work that is already running or queued
+// on its own device; it never waits for a kernel behind it on the same device.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPeerCountsBytes = 2 * 768 * 8;
+constexpr int kPeerMaxWorld = 64;
+
+__global__ void __launch_bounds__(256) build_lut_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, const float *__restrict__ ref_cdf, float *__restrict__ lut, unsigned long long *__restrict__ counts_out) {
+    const int c = blockIdx.x, b = threadIdx.x;
+    const int parity = (int)(epoch & 1u);
+    if (c == 0 && b < world) {  // (1) publish my counts (written by earlier kernels of this stream)
+        __threadfence_system();
+        unsigned *flag = reinterpret_cast<unsigned *>(bufs[b] + kPeerCountsBytes) + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+    if (b < world) {  // (2) wait for every rank's counts of this epoch
+        const unsigned *flag = reinterpret_cast<const unsigned *>(bufs[rank] + kPeerCountsBytes) + b;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        } while ((int)(seen - epoch) < 0);
+    }
+    __syncthreads();
+    unsigned long long total = 0;  // (3) all-reduce of bin (c, b)
+    for (int p = 0; p < world; ++p) {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(bufs[p]) + parity * 768 + c * 256 + b;
+        unsigned long long v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+        total += v;
+    }
+    if (counts_out != nullptr) counts_out[c * 256 + b] = total;
+    build_lut_channel<false>(total, -1, ref_cdf, lut);  // (4); pixel count = sum of the channel's counts
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1368,6 +1420,17 @@ int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h,
         apply_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), hw, planes, tiles, lut);
         SX_LAUNCHED("apply_f32_planar_kernel");
     }
+    return SX_OK;
+}
+
+int64_t sx_hm_peer_buffer_bytes(void) { return kPeerCountsBytes + kPeerMaxWorld * 4; }
+
+int sx_hm_build_lut_peers(const void *peer_buffers_dev, int world, int rank, uint32_t epoch, const float *ref_cdf, float *lut, uint64_t *counts_out, sx_stream_t stream) {
+    SX_REQUIRE(peer_buffers_dev && ref_cdf && lut, "NULL argument");
+    SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
+    SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
+    build_lut_peers_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, epoch, ref_cdf, lut, reinterpret_cast<unsigned long long *>(counts_out));
+    SX_LAUNCHED("build_lut_peers_kernel");
     return SX_OK;
 }
 

@@ -17,7 +17,7 @@ from stainx_b200._native import SX_F32, SX_NCHW, SX_NHWC, SX_U8, check
 
 __all__ = [
     "MacenkoWorkspace",
-    "hm_apply", "hm_build_lut", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform",
+    "hm_apply", "hm_build_lut", "hm_build_lut_peers", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform",
     "macenko_fit", "macenko_transform",
     "reinhard_apply", "reinhard_finalize", "reinhard_fit", "reinhard_stats", "reinhard_transform",
 ]
@@ -104,6 +104,18 @@ def hm_build_lut(counts: torch.Tensor, npix: int, ref_cdf: torch.Tensor) -> torc
     out = torch.empty((3, 256), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(nv.lib().sx_hm_build_lut(_ptr(counts), int(npix), _ptr(ref_cdf), _ptr(out), _stream(dev)), "sx_hm_build_lut")
+    return out
+
+
+def hm_build_lut_peers(exchange, ref_cdf: torch.Tensor, counts_out: torch.Tensor | None = None) -> torch.Tensor:
+    """LUT of a sharded batch with the all-reduce of the counts fused into the kernel (NVLink peer
+    loads; ``exchange`` is a ``sharding.PeerExchange`` whose epoch the caller has advanced and whose
+    counts[epoch & 1] hold this rank's histogram)."""
+    dev = exchange.buf.device
+    out = torch.empty((3, 256), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_hm_build_lut_peers(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, exchange.epoch & 0xFFFFFFFF, _ptr(ref_cdf),
+                                             _ptr(out), _ptr(counts_out) if counts_out is not None else None, _stream(dev)), "sx_hm_build_lut_peers")
     return out
 
 

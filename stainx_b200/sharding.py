@@ -75,6 +75,54 @@ class StatReducer:
         return tensors
 
 
+class PeerExchange:
+    """A small buffer that every rank of the group has mapped over NVLink (torch symmetric memory),
+    for exchanges fused into kernels (``sx_hm_build_lut_peers``: the all-reduce of the histogram
+    counts happens inside the LUT kernel with peer loads, no NCCL call).
+
+    ``PeerExchange.create`` returns ``None`` when symmetric memory is unavailable (gloo groups, ranks
+    on different nodes, old torch): callers then fall back to ``StatReducer``'s NCCL all-reduce.  All
+    ranks must create it and step ``epoch`` in lockstep (collective semantics)."""
+
+    def __init__(self, buf: torch.Tensor, handle, group):
+        self.buf = buf
+        self.handle = handle
+        self.group = group
+        self.rank = int(handle.rank)
+        self.world = int(handle.world_size)
+        self.ptrs_dev = int(handle.buffer_ptrs_dev)  # device array of `world` buffer pointers
+        self.epoch = 0
+
+    @classmethod
+    def create(cls, reducer: StatReducer, device: torch.device, nbytes: int) -> "PeerExchange | None":
+        if not reducer.enabled or torch.device(device).type != "cuda" or dist.get_backend(reducer.group) != "nccl":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = reducer.group if reducer.group is not None else dist.group.WORLD
+            buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=device)
+            buf.zero_()
+            handle = symm_mem.rendezvous(buf, group)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=reducer.group)  # every rank's zeros are in place before anyone signals
+            ok = torch.ones(1, dtype=torch.int32, device=device)
+        except Exception:  # noqa: BLE001 - any failure means "no peer memory": agree on it below
+            buf = handle = None
+            ok = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=reducer.group)  # all ranks or none
+        if int(ok.item()) == 0 or handle is None:
+            return None
+        return cls(buf, handle, reducer.group)
+
+    def view(self, offset: int, shape: tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        size = n * torch.empty((), dtype=dtype).element_size()
+        return self.buf[offset : offset + size].view(dtype).view(*shape)
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous image range [lo, hi) of ``rank`` when ``n`` images are split over ``world`` ranks."""
     base, extra = divmod(int(n), int(world))

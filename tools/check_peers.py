@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Sharded HistogramMatching on N GPUs of one node (run under torchrun): the fused NVLink exchange
+(sx_hm_build_lut_peers) against the NCCL all-reduce path and against the single-device result of the
+whole batch.  Exits non-zero on any mismatch.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_peers.py
+"""
+import os
+import sys
+import time
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from stainx_b200 import HistogramMatching  # noqa: E402
+from stainx_b200.sharding import shard_range  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+dist.init_process_group("nccl", device_id=dev)
+
+g = torch.Generator().manual_seed(7)
+ref = (torch.rand(1, 3, 256, 256, generator=g) ** 1.7 * 255).round().to(torch.uint8)
+n_total = 4 * world + 1  # uneven shards
+whole = (torch.rand(n_total, 3, 256, 256, generator=g) ** 0.6 * 255).round().to(torch.uint8)
+lo, hi = shard_range(n_total, rank, world)
+mine = whole[lo:hi].to(dev)
+
+hm = HistogramMatching(device=dev, backend="torch_cuda", process_group="world")
+hm.fit_broadcast(ref.to(dev), src=0)
+impl = hm._get_backend_impl()
+ex = impl._peer_exchange()
+print(f"rank {rank}: peer exchange {'ON' if ex is not None else 'unavailable (NCCL path)'}", flush=True)
+outs = [hm.transform(mine) for _ in range(5)]  # several epochs: both count parities, flag reuse
+torch.cuda.synchronize()
+
+# NCCL path of the same sharded batch
+impl._exchange = False
+want_nccl = hm.transform(mine)
+# single-device result of the whole batch
+single = HistogramMatching(device=dev, backend="torch_cuda").fit(ref.to(dev))
+want_whole = single.transform(whole.to(dev))[lo:hi]
+ok = all(torch.equal(o, want_nccl) for o in outs) and torch.equal(want_nccl, want_whole)
+
+# timing of the exchange + LUT phase
+impl._exchange = ex if ex is not None else False
+big = (torch.rand(16, 3, 1024, 1024, device=dev) * 255).to(torch.uint8)
+for label, use_peers in (("peers", True), ("nccl", False)):
+    impl._exchange = (ex if ex is not None else False) if use_peers else False
+    for _ in range(5):
+        hm.transform(big)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        hm.transform(big)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 50 * 1e6
+    if rank == 0:
+        print(f"transform 16x1024^2 per rank, exchange={label}: {dt:.1f} us per step", flush=True)
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("PEERS CHECK", "OK" if int(flag.item()) else "MISMATCH", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) else 1)
