@@ -391,39 +391,58 @@ def main() -> None:
            "api": "stainx_b200.ingest.HostStream(HistogramMatching(backend='torch_cuda')).submit(pinned uint8 batch, pinned out): H2D + transform + D2H per step"}
     del pipe
 
-    # ---- side measurements: the other two methods (informative; N=1 only) ---------------------
-    methods = {"hm_u8_64x1024": {"mp_per_s": value / world, "algo_gbs": roofline["step"]["gbs"], "frac_of_peak": roofline["step"]["frac"]}}
-    if not args.no_extras and not distributed:
+    # ---- side measurements: the other methods / BASELINE configs (aggregate MP/s over all ranks) ----
+    # Every rank runs its own shard (64 images per GPU, weak scaling); times are CUDA events, max over
+    # ranks.  Reinhard's source statistics span the sharded batch (one NCCL all-reduce of 8 doubles
+    # per step); the Macenko transform needs no exchange (per-image statistics).
+    methods = {"hm_u8_64x1024": {"mp_per_s": value, "algo_gbs_per_gpu": roofline["step"]["gbs"], "frac_of_peak": roofline["step"]["frac"]}}
+    if not args.no_extras:
         def timeit(fn, steps, warm=3):
             for _ in range(warm):
                 fn()
-            torch.cuda.synchronize()
+            barrier()
             a, b = ev(), ev()
             a.record()
             for _ in range(steps):
                 fn()
             b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / steps
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / steps
+
+        def entry(ms, bytes_per_px, mp=mp_per_gpu, **extra):
+            gbs = bytes_per_px * mp * 1e6 / (ms / 1e3) / 1e9
+            return {"mp_per_s": mp * world / (ms / 1e3), "algo_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms, **extra}
 
         del host_in, host_outs
-        g.manual_seed(43)
+        g.manual_seed(43 + rank)
         srcf = torch.rand((n_img, 3, H, W), device=dev, generator=g)
         g.manual_seed(42)
         reff = torch.rand((1, 3, H, W), device=dev, generator=g)
-        rh = Reinhard(device=dev, backend="torch_cuda").fit(reff)
-        ms = timeit(lambda: rh.transform(srcf), 5)
-        gbs = ALGO_BYTES_PER_PX["reinhard"] * px / (ms / 1e3) / 1e9
-        methods["reinhard_f32_64x1024"] = {"mp_per_s": mp_per_gpu / (ms / 1e3), "algo_gbs": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms}
-        ref10 = torch.rand((1, 3, 512, 512), device=dev, generator=g)
-        src10 = torch.rand((10, 3, 512, 512), device=dev, generator=g)
-        ms = timeit(lambda: Reinhard(device=dev, backend="torch_cuda").fit(ref10).transform(src10), 20)
-        methods["reinhard_f32_C1_fit1x512_transform10x512"] = {"mp_per_s": 10 * 512 * 512 / 1e6 / (ms / 1e3), "ms": ms, "note": "README quick-start (BASELINE configs[0]); fits in L2, launch-latency bound"}
-        mk = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True).fit(reff)
-        ms = timeit(lambda: mk.transform(srcf), 5)
-        gbs = ALGO_BYTES_PER_PX["macenko"] * px / (ms / 1e3) / 1e9
-        methods["macenko_f32_64x1024"] = {"mp_per_s": mp_per_gpu / (ms / 1e3), "algo_gbs": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms}
+        rh = Reinhard(device=dev, backend="torch_cuda", process_group=pg)
+        rh.fit_broadcast(reff, src=0) if distributed else rh.fit(reff)
+        methods["reinhard_f32_64x1024"] = entry(timeit(lambda: rh.transform(srcf), 5), ALGO_BYTES_PER_PX["reinhard"])
+        if not distributed:
+            ref10 = torch.rand((1, 3, 512, 512), device=dev, generator=g)
+            src10 = torch.rand((10, 3, 512, 512), device=dev, generator=g)
+            ms = timeit(lambda: Reinhard(device=dev, backend="torch_cuda").fit(ref10).transform(src10), 20)
+            methods["reinhard_f32_C1_fit1x512_transform10x512"] = {"mp_per_s": 10 * 512 * 512 / 1e6 / (ms / 1e3), "ms": ms, "note": "README quick-start (BASELINE configs[0]); fits in L2, launch-latency bound"}
+        mk = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True, process_group=pg)
+        mk.fit_broadcast(reff, src=0) if distributed else mk.fit(reff)
+        methods["macenko_f32_64x1024"] = entry(timeit(lambda: mk.transform(srcf), 5), ALGO_BYTES_PER_PX["macenko"], config="BASELINE configs[2]: reference-mode transform, float32 64x3x1024x1024 per GPU")
+        if distributed:  # BASELINE configs[3]: pooled fit over the sharded batch (NCCL stat all-reduces) + transform
+            mkb = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True, process_group=pg)
+            methods["macenko_f32_batch_fit_transform"] = entry(timeit(lambda: mkb.fit(srcf).transform(srcf), 3, warm=1), ALGO_BYTES_PER_PX["macenko"], config="BASELINE configs[3]: pooled fit + transform of the sharded batch")
         del srcf
+        # BASELINE configs[4]: StainNormalizerTransform("macenko") on uint8 2048x2048 tiles, 16 per GPU, float32 [0,1] out
+        from stainx_b200 import StainNormalizerTransform
+
+        g.manual_seed(43 + rank)
+        tiles = (torch.rand((16, 3, 2048, 2048), device=dev, generator=g) * 255).to(torch.uint8)
+        g.manual_seed(42)
+        ref_tile = (torch.rand((1, 3, 2048, 2048), device=dev, generator=g) * 255).to(torch.uint8)
+        snt = StainNormalizerTransform(method="macenko", mode="reference", reference=ref_tile, device=dev, backend="torch_cuda")
+        methods["macenko_transform_module_u8_16x2048"] = entry(timeit(lambda: snt(tiles), 5), 15.0, mp=16 * 2048 * 2048 / 1e6, config="BASELINE configs[4] per GPU: uint8 in, float32 [0,1] out (15 B/px)")
+        del tiles
 
     # ---- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
     cpu = None
