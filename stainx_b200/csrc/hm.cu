@@ -18,124 +18,16 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kUnroll = 4;                            // 128-bit loads in flight per thread
 constexpr int kTileVecs = kThreads * kUnroll;         // uint4 / float4 vectors per tile
-constexpr int kFlushTiles = 3;                        // 3 tiles * 4 loads * 16 B = 192 <= 255 per counter
 
 // ------------------------------------------------------------------------------------------------
-// Histogram, planar uint8.  grid = (blocks, 3 channels); a CTA only ever sees one channel.
-//
-// Counting scheme: every THREAD owns a private 256-bin histogram of 8-bit counters in shared
-// memory, so counting is a plain byte load / add / store -- no atomics and no bank conflicts:
-// the counter of (bin, lane) lives in word (bin >> 2) * 32 + lane, byte (bin & 3), i.e. lane l only
-// ever touches bank l.  Byte counters overflow after 255 hits, so each warp folds its 8 KB region
-// into the CTA's 32-bit histogram every kFlushTiles tiles (<= 192 values per thread).
+// Histogram, planar uint8, general kernel.  grid = (blocks, 3 channels); a CTA only ever sees one
+// channel.  Warp-private 256-bin tables updated with shared-memory atomics (ATOMS.POPC.INC merges
+// equal bins of a warp, so flat image regions count faster than noise).  Handles any alignment;
+// aligned large batches take the lane-private TMA-fed kernel below.  Counting schemes that were
+// built, measured and removed (201 M noise values): thread-private byte counters with plain
+// LDS/ADD/STS 120 us; lane-private packed byte counters with RED 109 us; lane-private 32-bit counters
+// fed from registers 95 us; this kernel 90 us; the same counting behind a TMA ring 91 us.
 // ------------------------------------------------------------------------------------------------
-struct ByteCounters {
-    // warp-private region: 64 rows (bin >> 2) x 32 lanes x 4 byte-counters
-    static constexpr int kBytesPerWarp = 64 * 32 * 4;
-
-    unsigned char *mine;   // &region[lane * 4]
-    unsigned int *region;  // warp region as words
-    unsigned int *hist32;  // CTA histogram (256 x u32)
-    int lane;
-
-    __device__ __forceinline__ void init(unsigned char *smem_counters, unsigned int *h32) {
-        int warp = threadIdx.x >> 5;
-        lane = threadIdx.x & 31;
-        region = reinterpret_cast<unsigned int *>(smem_counters + warp * kBytesPerWarp);
-        mine = reinterpret_cast<unsigned char *>(region) + lane * 4;
-        hist32 = h32;
-        for (int i = lane; i < 64 * 32; i += 32) region[i] = 0u;
-        __syncwarp();
-    }
-    __device__ __forceinline__ void add(unsigned b) {  // b in [0,255]
-        unsigned off = ((b & 0xfcu) << 5) | (b & 3u);
-        mine[off] = (unsigned char)(mine[off] + 1);
-    }
-    __device__ __forceinline__ void add4(unsigned w) {
-        add(w & 0xffu);
-        add((w >> 8) & 0xffu);
-        add((w >> 16) & 0xffu);
-        add(w >> 24);
-    }
-    // Fold the warp's byte counters into hist32 and clear them.  Lane j sums rows j and j + 32,
-    // walking the 32 words of a row with a lane-dependent rotation (bank = (k + lane) & 31).
-    __device__ __forceinline__ void flush() {
-        __syncwarp();
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            int q = lane + 32 * rr;
-            unsigned lo = 0, hi = 0;  // two 16-bit partial sums each
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                int col = (k + lane) & 31;
-                unsigned w = region[q * 32 + col];
-                region[q * 32 + col] = 0u;
-                lo += w & 0x00ff00ffu;
-                hi += (w >> 8) & 0x00ff00ffu;
-            }
-            if (lo & 0xffffu) atomicAdd(&hist32[4 * q + 0], lo & 0xffffu);
-            if (hi & 0xffffu) atomicAdd(&hist32[4 * q + 1], hi & 0xffffu);
-            if (lo >> 16) atomicAdd(&hist32[4 * q + 2], lo >> 16);
-            if (hi >> 16) atomicAdd(&hist32[4 * q + 3], hi >> 16);
-        }
-        __syncwarp();
-    }
-};
-
-// Counting scheme C: the same lane-private packed layout, but the update is a fire-and-forget
-// shared-memory reduction (RED.ADD of 1 << 8*(bin & 3)) instead of a byte load/add/store.  Lane l
-// only touches bank l, so the warp-wide RED is conflict-free, and nothing waits on its result.
-// A byte lane holds at most 255 hits between flushes, so a carry can never cross into its
-// neighbour.
-struct PackedRed {
-    static constexpr int kBytesPerWarp = 64 * 32 * 4;
-    unsigned int *mine;    // &region[lane]
-    unsigned int *region;
-    unsigned int *hist32;
-    int lane;
-    __device__ __forceinline__ void init(unsigned char *smem_counters, unsigned int *h32) {
-        int warp = threadIdx.x >> 5;
-        lane = threadIdx.x & 31;
-        region = reinterpret_cast<unsigned int *>(smem_counters + warp * kBytesPerWarp);
-        mine = region + lane;
-        hist32 = h32;
-        for (int i = lane; i < 64 * 32; i += 32) region[i] = 0u;
-        __syncwarp();
-    }
-    __device__ __forceinline__ void add(unsigned b) {
-        atomicAdd(mine + ((b & 0xfcu) << 3), 1u << ((b & 3u) << 3));  // word (b>>2)*32 + lane
-    }
-    __device__ __forceinline__ void add4(unsigned w) {
-        add(w & 0xffu);
-        add((w >> 8) & 0xffu);
-        add((w >> 16) & 0xffu);
-        add(w >> 24);
-    }
-    __device__ __forceinline__ void flush() {
-        __syncwarp();
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            int q = lane + 32 * rr;
-            unsigned lo = 0, hi = 0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                int col = (k + lane) & 31;
-                unsigned w = region[q * 32 + col];
-                region[q * 32 + col] = 0u;
-                lo += w & 0x00ff00ffu;
-                hi += (w >> 8) & 0x00ff00ffu;
-            }
-            if (lo & 0xffffu) atomicAdd(&hist32[4 * q + 0], lo & 0xffffu);
-            if (hi & 0xffffu) atomicAdd(&hist32[4 * q + 1], hi & 0xffffu);
-            if (lo >> 16) atomicAdd(&hist32[4 * q + 2], lo >> 16);
-            if (hi >> 16) atomicAdd(&hist32[4 * q + 3], hi >> 16);
-        }
-        __syncwarp();
-    }
-};
-
-// Alternative counting scheme (selectable for A/B measurements): warp-private 32-bit histograms
-// updated with shared-memory atomics.
 struct WarpAtomics {
     unsigned int *wh;  // warp histogram (256 x u32)
     __device__ __forceinline__ void init(unsigned int *smem_hist) {
@@ -172,24 +64,16 @@ __device__ __forceinline__ PlaneSplit split_plane(const T *p, int64_t len) {
     return s;
 }
 
-template <int MODE>  // 0: warp-private shared atomics, 1: byte counters, 2: packed lane-private RED
 __global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned int *hist32 = reinterpret_cast<unsigned int *>(smem);  // 256 words
-    unsigned char *scratch = smem + 256 * sizeof(unsigned int);
+    __shared__ unsigned int hist32[256];
+    __shared__ unsigned int whist[kWarps * 256];
     const int c = blockIdx.y;
     for (int i = threadIdx.x; i < 256; i += kThreads) hist32[i] = 0u;
-
-    constexpr bool BYTE_COUNTERS = MODE != 0;  // modes 1 and 2 need the periodic flush
-    using Packed = typename std::conditional<MODE == 2, PackedRed, ByteCounters>::type;
-    Packed bc;
     WarpAtomics wa;
-    if (BYTE_COUNTERS) bc.init(scratch, hist32);
-    else wa.init(reinterpret_cast<unsigned int *>(scratch));
+    wa.init(whist);
     __syncthreads();
 
     const int64_t items = n_img * tiles_per_plane;
-    int since_flush = 0;
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
         const int64_t n = item / tiles_per_plane;
         const int64_t t = item - n * tiles_per_plane;
@@ -206,184 +90,26 @@ __global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t 
             if (ok[u]) v[u] = ld_stream(body + vi);
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (ok[u]) {
-                if (BYTE_COUNTERS) { bc.add4(v[u].x); bc.add4(v[u].y); bc.add4(v[u].z); bc.add4(v[u].w); }
-                else { wa.add4(v[u].x); wa.add4(v[u].y); wa.add4(v[u].z); wa.add4(v[u].w); }
-            }
-        }
+        for (int u = 0; u < kUnroll; ++u)
+            if (ok[u]) { wa.add4(v[u].x); wa.add4(v[u].y); wa.add4(v[u].z); wa.add4(v[u].w); }
         if (t == 0) {  // ragged ends of the plane: < 32 bytes, one thread each
             int64_t ragged = sp.head + (hw - sp.tail0);
             if ((int64_t)threadIdx.x < ragged) {
                 int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
-                if (BYTE_COUNTERS) bc.add(plane[idx]);
-                else wa.add(plane[idx]);
+                wa.add(plane[idx]);
             }
         }
-        if (BYTE_COUNTERS && ++since_flush == kFlushTiles) {
-            bc.flush();
-            since_flush = 0;
-        }
     }
-    if (BYTE_COUNTERS) {
-        bc.flush();
-    } else {
-        __syncwarp();
-        for (int i = threadIdx.x & 31; i < 256; i += 32)
-            if (wa.wh[i]) atomicAdd(&hist32[i], wa.wh[i]);
-    }
+    __syncwarp();
+    for (int i = threadIdx.x & 31; i < 256; i += 32)
+        if (wa.wh[i]) atomicAdd(&hist32[i], wa.wh[i]);
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += kThreads)
         if (hist32[i]) atomicAdd(&counts[c * 256 + i], (unsigned long long)hist32[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Histogram, planar uint8, scheme D ("lane32"): every LANE owns a full 256-bin histogram of 32-bit
-// counters, laid out [bin][lane] inside a 32 KB warp region, so counter (bin, lane) sits in bank
-// `lane`.  Counting one byte is SHF + LOP3 + a conflict-free fire-and-forget ATOMS.ADD; there is
-// no overflow, hence no periodic flush.  7 warps x 32 KB fill the SM's shared memory, so the CTA
-// is persistent (one per SM) and walks a CONTIGUOUS range of the (channel, image, tile) list,
-// folding its histogram into the global counts whenever the channel changes (at most twice).
-// Memory-level parallelism comes from 8 independent 128-bit loads per thread.
-// ------------------------------------------------------------------------------------------------
-constexpr int kL32Warps = 7;
-constexpr int kL32Threads = kL32Warps * 32;
-constexpr int kL32Unroll = 8;
-constexpr int kL32TileVecs = kL32Threads * kL32Unroll;
-constexpr int kL32SmemBytes = kL32Warps * 256 * 32 * 4 + 256 * 4;
-
-__device__ __forceinline__ void l32_count4(unsigned w, unsigned lane_off, uint32_t region_addr) {
-    // byte offset of counter (bin, lane) = bin * 128 + lane * 4
-    unsigned o0 = ((w << 7) & 0x7f80u) | lane_off;
-    unsigned o1 = ((w >> 1) & 0x7f80u) | lane_off;
-    unsigned o2 = ((w >> 9) & 0x7f80u) | lane_off;
-    unsigned o3 = ((w >> 17) & 0x7f80u) | lane_off;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o0) : "memory");
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o1) : "memory");
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o2) : "memory");
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(region_addr + o3) : "memory");
-}
-
-__global__ void __launch_bounds__(kL32Threads, 1) hist_u8_planar_lane32_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned int *regions = reinterpret_cast<unsigned int *>(smem);                                  // [warp][bin][lane]
-    unsigned int *hist32 = reinterpret_cast<unsigned int *>(smem + kL32Warps * 256 * 32 * 4);        // [bin]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int *region = regions + warp * 256 * 32;
-    const uint32_t region_addr = (uint32_t)__cvta_generic_to_shared(region);
-    const unsigned lane_off = (unsigned)lane * 4u;
-
-    for (int i = threadIdx.x; i < kL32Warps * 256 * 32; i += kL32Threads) regions[i] = 0u;
-    for (int i = threadIdx.x; i < 256; i += kL32Threads) hist32[i] = 0u;
-    __syncthreads();
-
-    // fold the lane-private counters of every warp into the global counts of channel c, re-zero
-    auto fold = [&](int c) {
-        __syncthreads();
-        for (int bin = lane; bin < 256; bin += 32) {  // lane j: bins j, j+32, ...; rotated walk = no conflicts
-            unsigned sum = 0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const int col = (k + lane) & 31;
-                sum += region[bin * 32 + col];
-                region[bin * 32 + col] = 0u;
-            }
-            if (sum) atomicAdd(&hist32[bin], sum);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 256; i += kL32Threads) {
-            const unsigned v = hist32[i];
-            if (v) atomicAdd(&counts[c * 256 + i], (unsigned long long)v);
-            hist32[i] = 0u;
-        }
-        __syncthreads();
-    };
-
-    const int64_t per_channel = n_img * tiles_per_plane;
-    const int64_t items = 3 * per_channel;
-    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
-    const int64_t first = (int64_t)blockIdx.x * per_cta;
-    const int64_t last = first + per_cta < items ? first + per_cta : items;
-
-    // Two register buffers: the 8 loads of tile i+1 are in flight while tile i is counted.
-    uint4 va[kL32Unroll], vb[kL32Unroll];
-    unsigned oka = 0, okb = 0;
-    auto issue = [&](int64_t item, uint4(&v)[kL32Unroll], unsigned &okmask) {
-        const int c = (int)(item / per_channel);
-        const int64_t rem = item - (int64_t)c * per_channel;
-        const int64_t n = rem / tiles_per_plane;
-        const int64_t t = rem - n * tiles_per_plane;
-        const uint8_t *plane = img + (n * 3 + c) * hw;
-        const PlaneSplit sp = split_plane(plane, hw);
-        const uint4 *body = reinterpret_cast<const uint4 *>(plane + sp.head);
-        const int64_t v0 = t * kL32TileVecs;
-        okmask = 0;
-#pragma unroll
-        for (int u = 0; u < kL32Unroll; ++u) {
-            const int64_t vi = v0 + u * kL32Threads + threadIdx.x;
-            if (vi < sp.nvec) {
-                v[u] = ld_stream(body + vi);
-                okmask |= 1u << u;
-            }
-        }
-    };
-    auto count = [&](int64_t item, const uint4(&v)[kL32Unroll], unsigned okmask) {
-#pragma unroll
-        for (int u = 0; u < kL32Unroll; ++u) {
-            if (okmask & (1u << u)) {
-                l32_count4(v[u].x, lane_off, region_addr);
-                l32_count4(v[u].y, lane_off, region_addr);
-                l32_count4(v[u].z, lane_off, region_addr);
-                l32_count4(v[u].w, lane_off, region_addr);
-            }
-        }
-        const int c = (int)(item / per_channel);
-        const int64_t rem = item - (int64_t)c * per_channel;
-        const int64_t n = rem / tiles_per_plane;
-        if (rem - n * tiles_per_plane == 0) {  // ragged ends of the plane
-            const uint8_t *plane = img + (n * 3 + c) * hw;
-            const PlaneSplit sp = split_plane(plane, hw);
-            const int64_t ragged = sp.head + (hw - sp.tail0);
-            if ((int64_t)threadIdx.x < ragged) {
-                const int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
-                atomicAdd(&region[(unsigned)plane[idx] * 32 + lane], 1u);
-            }
-        }
-    };
-
-    int cur_c = -1;
-    if (first < last) issue(first, va, oka);
-    for (int64_t item = first; item < last; item += 2) {
-        if (item + 1 < last) issue(item + 1, vb, okb);
-        int c = (int)(item / per_channel);
-        if (c != cur_c) {
-            if (cur_c >= 0) fold(cur_c);
-            cur_c = c;
-        }
-        count(item, va, oka);
-        if (item + 1 < last) {
-            if (item + 2 < last) issue(item + 2, va, oka);
-            c = (int)((item + 1) / per_channel);
-            if (c != cur_c) {
-                fold(cur_c);
-                cur_c = c;
-            }
-            count(item + 1, vb, okb);
-        }
-    }
-    if (cur_c >= 0) fold(cur_c);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Histogram, planar uint8, scheme S ("streamed"): the same warp-private ATOMS.POPC.INC counting as
-// scheme 0, arranged so that the shared-memory atomic unit never waits for HBM.  Measured on B200
-// (tools/atomsbench.cu): the unit retires ~11.8 distinct-address updates per clock per SM whatever
-// the layout (conflict-free lane-private tables: 10.5-11; 16-bit pair tables: 7.4; same address:
-// 31.5), i.e. 201 M values cannot be counted in less than ~58 us with atomics; scheme 0 reaches 7.7
-// per clock because its warps stall on their own global loads (ncu: 17 % long-scoreboard).  Here one
-// persistent CTA per SM walks a contiguous range of 16 KB tiles which one thread streams into a
-// shared-memory ring with TMA bulk copies (5 tiles = 80 KB in flight per SM; a register ring of the
-// same depth does not work: loads sharing one of the 6 scoreboard slots of a warp complete together).
+// TMA-fed kernels: tile list and shared-memory ring.
 // ------------------------------------------------------------------------------------------------
 // Position in the channel-major tile list (channel, image, tile) of an ALIGNED planar uint8 batch
 // (16-byte aligned base, H*W a multiple of 16: every plane is a whole number of 128-bit vectors).
@@ -410,18 +136,11 @@ struct TileCursor {
     __device__ __forceinline__ void next(int tile_vecs) {
         if (++t == tiles) { t = 0; off += plane_gap; } else off += tile_vecs;
     }
-    __device__ __forceinline__ void prev(int tile_vecs) {
-        if (--t < 0) { t = tiles - 1; off -= plane_gap; } else off -= tile_vecs;
-    }
 };
 
-constexpr int kStrThreads = 512;
-constexpr int kStrWarps = kStrThreads / 32;
-constexpr int kStrTileVecs = 1024;  // 16 KB of a plane per tile, two 128-bit vectors per thread
-constexpr int kStrTileBytes = kStrTileVecs * 16;
 
 // Shared-memory ring of tiles filled by TMA bulk copies.  kStages is a power of two.
-template <int kStages, int kTileVecs = kStrTileVecs, int kWarpsInCta = kStrWarps>
+template <int kStages, int kTileVecs, int kWarpsInCta>
 struct TileRing {
     uint4 *ring;             // [kStages][kTileVecs]
     uint64_t *full, *empty;  // [kStages] each
@@ -457,96 +176,6 @@ struct TileRing {
         ++consumed;
     }
 };
-
-// ------------------------------------------------------------------------------------------------
-// Histogram, planar uint8, scheme S ("streamed"): the same warp-private ATOMS.POPC.INC counting as
-// scheme 0, arranged so that the shared-memory atomic unit never waits for HBM and so that the
-// instruction count per value is minimal.  Measured on B200 (tools/atomsbench.cu): the unit retires
-// ~11.8 distinct-address updates per clock per SM whatever the layout (conflict-free lane-private
-// tables: 10.5-11; 16-bit pair tables: 7.4; same address: 31.5), i.e. 201 M random values cannot be
-// counted in less than ~58 us with atomics.  One persistent CTA per SM walks a contiguous range of
-// 16 KB tiles which one thread streams into a shared-memory ring with TMA bulk copies (7 tiles =
-// 112 KB in flight per SM; a register ring of the same depth does not work: loads that share one of
-// the 6 scoreboard slots of a warp complete together).  Counting one byte is SHF + LOP3 (the
-// warp's 1 KB histogram is 1 KB-aligned, so "| base" replaces the add) + ATOMS.
-// ------------------------------------------------------------------------------------------------
-constexpr int kHistStages = 8;
-constexpr int kHistSmem = 1024 + kStrWarps * 1024 + kHistStages * kStrTileBytes + 2 * kHistStages * 8;
-
-__device__ __forceinline__ void popc_count4(unsigned w, unsigned base) {
-    const unsigned a0 = ((w << 2) & 0x3fcu) | base, a1 = ((w >> 6) & 0x3fcu) | base;
-    const unsigned a2 = ((w >> 14) & 0x3fcu) | base, a3 = ((w >> 22) & 0x3fcu) | base;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0) : "memory");
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1) : "memory");
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a2) : "memory");
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a3) : "memory");
-}
-
-__global__ void __launch_bounds__(kStrThreads, 1) hist_u8_planar_streamed_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char *smem_hist = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB-align
-    unsigned int *whist = reinterpret_cast<unsigned int *>(smem_hist);  // [warp][256], 1 KB-aligned rows
-    unsigned char *ring_mem = smem_hist + kStrWarps * 1024;
-    TileRing<kHistStages> tr;
-    tr.init(ring_mem, reinterpret_cast<uint64_t *>(ring_mem + kHistStages * kStrTileBytes));
-    for (int i = threadIdx.x; i < kStrWarps * 256; i += kStrThreads) whist[i] = 0u;
-    __syncthreads();
-    const unsigned wbase = smem_u32(whist + (threadIdx.x >> 5) * 256);
-
-    const int64_t per_channel = n_img * tiles_per_plane;
-    const int64_t items = 3 * per_channel;
-    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
-    const int64_t first = (int64_t)blockIdx.x * per_cta;
-    const int64_t last = first + per_cta < items ? first + per_cta : items;
-    const uint4 *base = reinterpret_cast<const uint4 *>(img);
-
-    // warp histograms -> global counts of channel c, re-zero
-    auto flush = [&](int c) {
-        __syncthreads();
-        if (threadIdx.x < 256) {
-            unsigned long long sum = 0;
-#pragma unroll
-            for (int wgt = 0; wgt < kStrWarps; ++wgt) sum += whist[wgt * 256 + threadIdx.x];
-            if (sum) atomicAdd(&counts[c * 256 + threadIdx.x], sum);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < kStrWarps * 256; i += kStrThreads) whist[i] = 0u;
-        __syncthreads();
-    };
-
-    int64_t seg = first;
-    while (seg < last) {  // one channel segment at a time (at most three per CTA)
-        const int c = (int)(seg / per_channel);
-        const int64_t chan_end = (int64_t)(c + 1) * per_channel;
-        const int64_t seg_end = chan_end < last ? chan_end : last;
-        const int n_items = (int)(seg_end - seg);
-        TileCursor pc, cc;  // producer (thread 0) and consumer positions
-        pc.seek(hw, (int)tiles_per_plane, kStrTileVecs, per_channel, seg);
-        cc = pc;
-        int issued = 0;
-        for (int item = 0; item < n_items; ++item) {
-            if (threadIdx.x == 0) {  // keep kHistStages - 1 tiles in flight
-                while (issued < n_items && issued - item < kHistStages - 1) {
-                    tr.produce(base + pc.off, (unsigned)pc.vecs(kStrTileVecs) * 16u);
-                    pc.next(kStrTileVecs);
-                    ++issued;
-                }
-            }
-            const int nv = cc.vecs(kStrTileVecs);
-            cc.next(kStrTileVecs);
-            const uint4 *tile = tr.acquire();
-            const bool ok0 = (int)threadIdx.x < nv, ok1 = (int)threadIdx.x + kStrThreads < nv;
-            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-            if (ok0) v0 = tile[threadIdx.x];
-            if (ok1) v1 = tile[threadIdx.x + kStrThreads];
-            tr.release();
-            if (ok0) { popc_count4(v0.x, wbase); popc_count4(v0.y, wbase); popc_count4(v0.z, wbase); popc_count4(v0.w, wbase); }
-            if (ok1) { popc_count4(v1.x, wbase); popc_count4(v1.y, wbase); popc_count4(v1.z, wbase); popc_count4(v1.w, wbase); }
-        }
-        flush(c);
-        seg = seg_end;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Histogram, planar uint8, scheme L ("lane-private, TMA-fed").  Random bytes make ~3.2-way bank
@@ -1053,95 +682,8 @@ __global__ void __launch_bounds__(kThreads) apply_u8_planar_kernel(const uint8_t
     }
 }
 
-// uint8 planar, pair LUT.  The byte-table kernel above is bound by shared-memory bank conflicts, not
-// by HBM (ncu: 16 random byte lookups per 128-bit load, ~3.2 wavefronts each, LSU data pipe at its
-// one wavefront per clock).  Here one lookup translates TWO neighbouring bytes: a 65 536-entry
-// uint16 table pair[a | b << 8] = lut[a] | lut[b] << 8 (128 KB of shared memory) halves the lookups
-// and the extract / insert arithmetic.  One persistent CTA per SM owns a contiguous range of the
-// channel-major tile list (at most three channel segments, the table is rebuilt per segment) --
-// the same range the streamed histogram kernel gave it -- and walks it BACKWARDS, so it starts in
-// the part of the batch that pass left in L2.
-constexpr int kPairLutBytes = 65536 * 2;
-
-__device__ __forceinline__ unsigned pair_lookup_word(unsigned w, uint32_t table_addr) {
-    unsigned short lo, hi;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(lo) : "r"(table_addr + ((w << 1) & 0x1fffeu)));
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hi) : "r"(table_addr + ((w >> 15) & 0x1fffeu)));
-    return (unsigned)lo | ((unsigned)hi << 16);
-}
-
-constexpr int kApplyStages = 4;
-constexpr int kPairLutSmem = kPairLutBytes + kApplyStages * kStrTileBytes + 768 + 2 * kApplyStages * 8 + 16;
-
-__global__ void __launch_bounds__(kStrThreads, 1) apply_u8_planar_pairlut_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, int64_t hw, int64_t n_img, int64_t tiles_per_plane, const float *__restrict__ lut) {
-    extern __shared__ __align__(16) unsigned char smem_apply[];
-    unsigned short *pair = reinterpret_cast<unsigned short *>(smem_apply);
-    unsigned char *ring_mem = smem_apply + kPairLutBytes;
-    unsigned char *lut8 = ring_mem + kApplyStages * kStrTileBytes;
-    const uint32_t table_addr = smem_u32(pair);
-    TileRing<kApplyStages> tr;
-    tr.init(ring_mem, reinterpret_cast<uint64_t *>(lut8 + 768));
-    for (int i = threadIdx.x; i < 768; i += kStrThreads) lut8[i] = (unsigned char)__float2int_rz(lut[i]);  // trunc, L296-298
-
-    const int64_t per_channel = n_img * tiles_per_plane;
-    const int64_t items = 3 * per_channel;
-    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
-    const int64_t first = (int64_t)blockIdx.x * per_cta;
-    const int64_t last = first + per_cta < items ? first + per_cta : items;
-    const uint4 *base = reinterpret_cast<const uint4 *>(img);
-    uint4 *obase = reinterpret_cast<uint4 *>(out);
-
-    auto remap = [&](const uint4 &v) {
-        uint4 r;
-        r.x = pair_lookup_word(v.x, table_addr);
-        r.y = pair_lookup_word(v.y, table_addr);
-        r.z = pair_lookup_word(v.z, table_addr);
-        r.w = pair_lookup_word(v.w, table_addr);
-        return r;
-    };
-
-    int64_t seg_end = last;
-    while (seg_end > first) {  // channel segments, last to first
-        const int c = (int)((seg_end - 1) / per_channel);
-        const int64_t chan_begin = (int64_t)c * per_channel;
-        const int64_t seg = chan_begin > first ? chan_begin : first;
-        const int n_items = (int)(seg_end - seg);
-        __syncthreads();  // previous segment's lookups are done (and lut8 / the barriers are written)
-        for (int i = threadIdx.x; i < 32768; i += kStrThreads) {  // two entries per store
-            const unsigned e0 = 2 * i, e1 = 2 * i + 1;
-            const unsigned lo = (unsigned)lut8[c * 256 + (e0 & 255)] | ((unsigned)lut8[c * 256 + (e0 >> 8)] << 8);
-            const unsigned hi = (unsigned)lut8[c * 256 + (e1 & 255)] | ((unsigned)lut8[c * 256 + (e1 >> 8)] << 8);
-            reinterpret_cast<unsigned *>(pair)[i] = lo | (hi << 16);
-        }
-        __syncthreads();
-        TileCursor pc, cc;  // walk backwards: seg_end - 1, seg_end - 2, ..., seg
-        pc.seek(hw, (int)tiles_per_plane, kStrTileVecs, per_channel, seg_end - 1);
-        cc = pc;
-        int issued = 0;
-        for (int item = 0; item < n_items; ++item) {
-            if (threadIdx.x == 0) {
-                while (issued < n_items && issued - item < kApplyStages - 1) {
-                    tr.produce(base + pc.off, (unsigned)pc.vecs(kStrTileVecs) * 16u);
-                    pc.prev(kStrTileVecs);
-                    ++issued;
-                }
-            }
-            const int nv = cc.vecs(kStrTileVecs);
-            uint4 *dst = obase + cc.off;
-            cc.prev(kStrTileVecs);
-            const uint4 *tile = tr.acquire();
-            const bool ok0 = (int)threadIdx.x < nv, ok1 = (int)threadIdx.x + kStrThreads < nv;
-            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-            if (ok0) v0 = tile[threadIdx.x];
-            if (ok1) v1 = tile[threadIdx.x + kStrThreads];
-            tr.release();
-            if (ok0) st_stream(dst + threadIdx.x, remap(v0));
-            if (ok1) st_stream(dst + threadIdx.x + kStrThreads, remap(v1));
-        }
-        seg_end = seg;
-    }
-}
-
+// (A 65 536-entry two-byte LUT in shared memory behind a TMA ring was built and measured for the uint8
+// planar remap: 80 us against 72 us for the kernel above; removed.)
 // float32 planar: out = clamp(lut[trunc(clamp(255 x))] / 255, 0, 1)   (L290-296).
 __global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const float *__restrict__ img, float *__restrict__ out, int64_t hw, int64_t planes, int64_t tiles_per_plane, const float *__restrict__ lut) {
     __shared__ float lutf[3 * 256];
@@ -1239,13 +781,11 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
 }
 
 // ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
-static int g_hist_byte_counters = 5;  // counting scheme of the uint8 planar histogram: 5 lane-private counters fed by a TMA ring
-                                      // (default for 16-byte aligned planes: data-independent), 0 warp-private atomics (any alignment;
-                                      // faster on constant images, slower on noise), 1 byte counters, 2 packed RED, 3 lane32, 4 streamed,
-                                      // 6 ring feed without counting (measurement only: wrong counts)
+static int g_hist_byte_counters = 5;  // uint8 planar histogram: 5 lane-private counters fed by a TMA ring (default for 16-byte aligned
+                                      // planes from 8 MB on: data-independent), 0 warp-private atomics (any alignment; faster on constant
+                                      // images, slower on noise), 6 ring feed without counting (measurement only: wrong counts)
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 16;
-static int g_apply_pair_lut = 0;       // uint8 planar remap through the 2-byte table (persistent kernel)
 
 }  // namespace hm
 }  // namespace sx
@@ -1279,7 +819,6 @@ int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_cta
     if (hist_byte_counters >= 0) g_hist_byte_counters = hist_byte_counters;
     if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
     if (apply_ctas_per_sm > 0) g_apply_ctas_per_sm = apply_ctas_per_sm;
-    g_apply_pair_lut = apply_ctas_per_sm == 1000 ? 1 : (apply_ctas_per_sm > 0 ? 0 : g_apply_pair_lut);
     return SX_OK;
 }
 
@@ -1306,46 +845,15 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
     if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         const int64_t items = n * tiles;
-        // scheme 4 needs whole 128-bit vectors per plane; anything else takes the general kernel
+        // the TMA-fed kernel needs whole 128-bit vectors per plane; anything else takes the general kernel
         const bool planes_aligned = aligned16(images) && hw % 16 == 0;
         // the persistent lane-private kernel zeroes 128 KB of counters per SM: worth it from ~8 MB of pixels on
         if (g_hist_byte_counters >= 5 && planes_aligned && n * hw * 3 >= ((int64_t)8 << 20)) {
             if (int rc = launch_lane_tma(g_hist_byte_counters, static_cast<const uint8_t *>(images), hw, n, cnt, stream)) return rc;
-        } else if (g_hist_byte_counters == 4 && planes_aligned) {
-            const int64_t tiles_s = max_i64(1, (hw / 16 + kStrTileVecs - 1) / kStrTileVecs);
-            const unsigned grid_s = stream_grid(3 * n * tiles_s, 1);
-            static bool attr4_set = false;
-            if (!attr4_set) {
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_streamed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHistSmem));
-                attr4_set = true;
-            }
-            hist_u8_planar_streamed_kernel<<<grid_s, kStrThreads, kHistSmem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles_s, cnt);
-        } else if (g_hist_byte_counters == 3) {
-            static bool attr3_set = false;
-            if (!attr3_set) {
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL32SmemBytes));
-                attr3_set = true;
-            }
-            const int64_t tiles32 = max_i64(1, (hw / 16 + kL32TileVecs - 1) / kL32TileVecs);
-            const unsigned grid32 = stream_grid(3 * n * tiles32, 1);
-            hist_u8_planar_lane32_kernel<<<grid32, kL32Threads, kL32SmemBytes, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles32, cnt);
-        } else if (g_hist_byte_counters == 1 || g_hist_byte_counters == 2) {
-            const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * ByteCounters::kBytesPerWarp;
-            static bool attr_set = false;
-            if (!attr_set) {
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
-            }
-            dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
-            grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
-            if (g_hist_byte_counters == 2) hist_u8_planar_kernel<2><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
-            else hist_u8_planar_kernel<1><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
         } else {
-            const size_t smem = 256 * sizeof(unsigned) + (size_t)kWarps * 256 * sizeof(unsigned);
             dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
             grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
-            hist_u8_planar_kernel<0><<<grid, kThreads, smem, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
+            hist_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
         }
         SX_LAUNCHED("hist_u8_planar_kernel");
     } else {
@@ -1399,17 +907,7 @@ int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h,
         return SX_OK;
     }
     const int64_t planes = n * 3;
-    if (dtype == SX_U8 && g_apply_pair_lut && aligned16(images) && aligned16(out) && hw % 16 == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            SX_CUDA(cudaFuncSetAttribute(apply_u8_planar_pairlut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairLutSmem));
-            attr_set = true;
-        }
-        const int64_t tiles_s = max_i64(1, (hw / 16 + kStrTileVecs - 1) / kStrTileVecs);
-        const unsigned grid_s = stream_grid(3 * n * tiles_s, 1);
-        apply_u8_planar_pairlut_kernel<<<grid_s, kStrThreads, kPairLutSmem, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, n, tiles_s, lut);
-        SX_LAUNCHED("apply_u8_planar_pairlut_kernel");
-    } else if (dtype == SX_U8) {
+    if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
         apply_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, planes, tiles, lut);

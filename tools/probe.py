@@ -55,39 +55,24 @@ def probe_hm():
     lib = nv.lib()
     counts = torch.zeros((3, 256), dtype=torch.int64, device=dev)
     want = ops.hm_hist(src)
-    for mode, ctas_list in ((6, (1,)), (7, (1,)), (9, (1,)), (8, (1,))):
-        for ctas in ctas_list:
-            lib.sx_hm_set_tuning(mode, ctas, -1)
-            ok = torch.equal(ops.hm_hist(src), want)
-            report(f"hm hist u8 planar mode={mode} ctas/sm={ctas} ok={ok}", timeit(lambda: ops.hm_hist(src, counts=counts)), 3 * px)
-    const = torch.full_like(src, 200)
-    smooth = (torch.arange(src.numel(), device=dev, dtype=torch.int64) // 4096 % 256).to(torch.uint8).reshape(src.shape)
-    lib.sx_hm_set_tuning(0, 8, -1)
-    want_const, want_smooth = ops.hm_hist(const), ops.hm_hist(smooth)
     for mode, ctas in ((0, 8), (5, 1), (6, 1)):
+        lib.sx_hm_set_tuning(mode, ctas, -1)
+        ok = torch.equal(ops.hm_hist(src), want)
+        report(f"hm hist u8 planar mode={mode} ctas/sm={ctas} ok={ok}", timeit(lambda: ops.hm_hist(src, counts=counts)), 3 * px)
+    const = torch.full_like(src, 200)
+    lib.sx_hm_set_tuning(0, 8, -1)
+    want_const = ops.hm_hist(const)
+    for mode, ctas in ((0, 8), (5, 1)):
         lib.sx_hm_set_tuning(mode, ctas, -1)
         ok = torch.equal(ops.hm_hist(const), want_const)
         report(f"hm hist u8 CONSTANT image mode={mode} ok={ok}", timeit(lambda: ops.hm_hist(const, counts=counts)), 3 * px)
-        ok = torch.equal(ops.hm_hist(smooth), want_smooth)
-        report(f"hm hist u8 SMOOTH image mode={mode} ok={ok}", timeit(lambda: ops.hm_hist(smooth, counts=counts)), 3 * px)
-    del const, smooth
-    lib.sx_hm_set_tuning(0, 8, -1)
+    del const
+    lib.sx_hm_set_tuning(5, 8, -1)
     lut = ops.hm_build_lut(ops.hm_hist(src), px, ops.hm_ref_cdf(ref_hist))
-    for ctas in (2, 4, 8, 16):
+    for ctas in (4, 8, 16):
         lib.sx_hm_set_tuning(-1, -1, ctas)
         report(f"hm apply u8 planar ctas/sm={ctas}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
-    lib.sx_hm_set_tuning(-1, -1, 8)
-    want_out = ops.hm_apply(src, lut)
-    lib.sx_hm_set_tuning(-1, -1, 1000)
-    ok = torch.equal(ops.hm_apply(src, lut), want_out)
-    odd = src.flatten()[3:3 + 5 * 3 * 1000 * 1001].reshape(5, 3, 1000, 1001)  # misaligned planes
-    lib.sx_hm_set_tuning(-1, -1, 8)
-    want_odd = ops.hm_apply(odd.clone(), lut)
-    lib.sx_hm_set_tuning(4, 1, 1000)
-    ok_odd = torch.equal(ops.hm_apply(odd.clone(), lut), want_odd)
-    report(f"hm apply u8 planar PAIR LUT ok={ok} odd_ok={ok_odd}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
-    report("hm transform u8 streamed hist + pair LUT", timeit(lambda: ops.hm_transform(src, ref_hist)), 9 * px)
-    lib.sx_hm_set_tuning(0, 8, 8)
+    lib.sx_hm_set_tuning(5, 8, 16)
     report("hm transform u8 (hist+lut+apply)", timeit(lambda: ops.hm_transform(src, ref_hist)), 9 * px)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
     report("hm transform u8 NHWC", timeit(lambda: ops.hm_transform(nhwc, ref_hist, nv.SX_NHWC)), 9 * px)
