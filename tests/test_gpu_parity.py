@@ -520,3 +520,46 @@ def test_macenko_ties_overflow_the_hit_queue(cuda, ox):
     n = Macenko(device=cuda, backend="torch_cuda").fit(flat.to(cuda))
     assert np.abs(_np(n._stain_matrix) - he).max() <= 1e-4
     assert np.abs(_np(n._target_max_conc) / maxc - 1).max() <= 1e-3
+
+
+def test_macenko_transform_in_cuda_graph_and_on_side_stream(cuda):
+    """The multi-chain transform forks into library-owned side streams and joins back: it must stay
+    ordered on a non-default caller stream and be capturable into a CUDA graph (replay == eager)."""
+    from stainx_b200 import ops
+
+    g = torch.Generator(device=cuda).manual_seed(9)
+    src = (torch.rand((24, 3, 1024, 1024), device=cuda, generator=g) * 255).to(torch.uint8)  # 75 MB: several chains
+    he, maxc = ops.macenko_fit(src[:1])
+    want = ops.macenko_transform(src, he, maxc, unit=False)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(s):
+        got = ops.macenko_transform(src, he, maxc, unit=False)
+        total = got.float().sum()  # ordered after the join on the same stream
+    s.synchronize()
+    assert torch.equal(got, want) and float(total) == float(want.float().sum())
+    # graph capture: static input/output/workspace buffers
+    static_out = torch.empty_like(src)
+    ws = torch.empty(int(nv_lib().sx_macenko_workspace_bytes(src.shape[0])), dtype=torch.uint8, device=cuda)
+    import ctypes
+
+    def enqueue():
+        rc = nv_lib().sx_macenko_transform(ctypes.c_void_p(src.data_ptr()), 0, 24, 1024, 1024, ctypes.c_void_p(he.data_ptr()), ctypes.c_void_p(maxc.data_ptr()), ctypes.c_void_p(static_out.data_ptr()), 0,
+                                           ctypes.c_float(1.0), ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(cuda).cuda_stream))
+        assert rc == 0
+
+    enqueue()  # warm-up outside capture (occupancy queries, function attributes)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enqueue()
+    static_out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, want)
+
+
+def nv_lib():
+    from stainx_b200 import _native
+
+    return _native.lib()
