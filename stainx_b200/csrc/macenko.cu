@@ -355,39 +355,6 @@ __device__ __forceinline__ void moments_stream(const T *__restrict__ image, int6
     for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
 }
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads) moments_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
-    __shared__ float tab[256];
-    __shared__ double red[kThreads / 32][10];
-    __shared__ float redf[kThreads / 32][6];
-    Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = pooled ? 0 : slot0 + n;
-    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    moments_stream<T, VEC, true>(img + n * 3 * g.hw, g.hw, g.hw / Pix<T, VEC>::kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, acc, lo, hi);
-    lo[1] = lo[2] = lo[0];
-    hi[1] = hi[2] = hi[0];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float a = warp_max(-lo[c]), b = warp_max(hi[c]);
-        if (lane == 0) { redf[warp][c] = a; redf[warp][3 + c] = b; }
-    }
-    block_sum10(acc, red);
-    if (threadIdx.x < 10) {
-        if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
-    } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
-        const int i = threadIdx.x - 32;
-        float r = -INFINITY;
-        for (int k = 0; k < kThreads / 32; ++k) r = fmaxf(r, redf[k][i]);
-        atomic_max_f32(&ws.odrange[slot * 8 + i], r);  // [0..2] = -min l_c, [3..5] = max l_c
-    } else if (threadIdx.x == 64 && chunk == 0) {
-        atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);
-    }
-}
-
 // ---- symmetric 3x3 eigen-decomposition (M4) ----------------------------------------------------
 // Cyclic Jacobi in float32 on the covariance scaled to unit trace (the covariance itself comes
 // from float64 moments).  It runs on one thread between two image phases, so its latency is on the
@@ -771,20 +738,6 @@ __device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_cnt, cnt);
 }
 
-template <typename T, bool VEC, int STAGE>
-__global__ void __launch_bounds__(kThreads) resolve_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
-    __shared__ float tab[256];
-    __shared__ ResolveSmem rs;
-    __shared__ SlotState st;
-    Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = pooled ? 0 : slot0 + n;
-    if (threadIdx.x == 0) st = ws.state[slot];
-    __syncthreads();
-    resolve_pass<T, VEC, STAGE>(img + n * 3 * g.hw, g.hw, g.hw / Pix<T, VEC>::kPix, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, st, rs, ws.hist2 + slot * 2 * kBins, ws.vmin + slot * 2 * kBins, ws.vmax + slot * 2 * kBins, ws.counters + slot * 8);
-}
-
 // ---- per-slot rank searches (one CTA per slot) --------------------------------------------------
 // Nearest-rank index (torch_backend.py:L362-365): round_half_even(0.01 * q * (n - 1)), in double.
 __device__ __forceinline__ long long rank_index(double q, long long n) { return (long long)rint(0.01 * q * (double)(n - 1)); }
@@ -1163,8 +1116,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
 // contiguous rows [c R / grid, (c + 1) R / grid) -- equal work for every CTA whatever the batch and
 // image sizes, at most two images per CTA for batches larger than the grid.
 struct RowGeom {
-    int64_t n_img, hw, total_rows, slot0;  // image i of this launch uses statistics slot slot0 + i
-    int rows_per_img;
+    int64_t n_img, hw, total_rows, slot0;  // image i of this launch uses statistics slot slot0 + i (pooled: every image slot0)
+    int rows_per_img, pooled;
 };
 
 // The segment (image, rows [row0, row1)) at row `r` of a CTA's range ending at `r_end`.
@@ -1191,7 +1144,7 @@ __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict
     for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
         const RowSegment seg(g, r, r_end);
         r += seg.row1 - seg.row0;
-        const int64_t slot = g.slot0 + seg.n;
+        const int64_t slot = g.pooled ? g.slot0 : g.slot0 + seg.n;
         const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
         double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -1208,6 +1161,8 @@ __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict
             float v = -INFINITY;
             for (int k = 0; k < kThreads / 32; ++k) v = fmaxf(v, redf[k][i / 3]);
             atomic_max_f32(&ws.odrange[slot * 8 + i], v);
+        } else if (threadIdx.x == 64 && seg.row0 == 0) {
+            atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);  // rows in the slot (pooled fit: all images)
         }
         __syncthreads();  // red / redf are rewritten by the next segment
     }
@@ -1224,7 +1179,7 @@ __global__ void __launch_bounds__(kThreads) t_resolve_kernel(const T *__restrict
     for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
         const RowSegment seg(g, r, r_end);
         r += seg.row1 - seg.row0;
-        const int64_t slot = g.slot0 + seg.n, base = slot * 2 * kBins;
+        const int64_t slot = g.pooled ? g.slot0 : g.slot0 + seg.n, base = slot * 2 * kBins;
         const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
         __syncthreads();  // the previous segment has finished with `st`
         load_state(&st, ws.state + slot);
@@ -1397,6 +1352,18 @@ static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_overri
     return g;
 }
 
+template <typename T, bool VEC>
+static RowGeom make_row_geom(int64_t n, int64_t hw, int64_t slot0, int pooled) {
+    RowGeom g;
+    g.n_img = n;
+    g.hw = hw;
+    g.slot0 = slot0;
+    g.pooled = pooled;
+    g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
+    g.total_rows = n * g.rows_per_img;
+    return g;
+}
+
 // Grid of a pipeline kernel: every CTA resident at once (occupancy x SMs), never more than rows.
 template <typename K>
 static unsigned pipeline_grid(K kernel, int64_t total_rows) {
@@ -1445,12 +1412,7 @@ static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         const T *p = static_cast<const T *>(images);
-        RowGeom g;
-        g.n_img = n;
-        g.hw = hw;
-        g.slot0 = slot0;
-        g.rows_per_img = (int)((hw / Pix<T, VEC>::kPix + kThreads - 1) / kThreads);
-        g.total_rows = n * g.rows_per_img;
+        const RowGeom g = make_row_geom<T, VEC>(n, hw, slot0, 0);
         t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
         mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
         t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
@@ -1551,8 +1513,8 @@ int sx_macenko_moments(const void *images, int dtype, int64_t n, int64_t h, int6
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
-        PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
-        moments_kernel<T, VEC><<<(unsigned)(n * g.cpi), kThreads, 0, stream>>>(static_cast<const T *>(images), g, pooled, slot0, workspace, slots);
+        const RowGeom g = make_row_geom<T, VEC>(n, hw, pooled ? 0 : slot0, pooled);
+        t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(static_cast<const T *>(images), g, workspace, slots);
     });
     SX_LAUNCHED("macenko::moments_kernel");
     return SX_OK;
@@ -1601,10 +1563,9 @@ int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t
             if (stage == SX_STAGE_ANGLE) sample_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
             else sample_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
         } else {
-            PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
-            const unsigned grid = (unsigned)(n * g.cpi);
-            if (stage == SX_STAGE_ANGLE) resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
-            else resolve_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+            const RowGeom g = make_row_geom<T, VEC>(n, hw, pooled ? 0 : slot0, pooled);
+            if (stage == SX_STAGE_ANGLE) t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+            else t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
         }
     });
     SX_LAUNCHED("macenko::hist kernels");
