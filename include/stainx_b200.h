@@ -110,6 +110,14 @@ int sx_reinhard_finalize(const double *sums, float *mean, float *std, sx_stream_
 int sx_reinhard_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
                       const float *src_mean, const float *src_std, const float *ref_mean,
                       const float *ref_std, void *out, sx_stream_t stream);
+/* Sharded batches on one NVLink node: finalize with the SUM all-reduce of the sums fused into the
+ * kernel (peer loads over NVLink, no NCCL call; protocol of sx_hm_build_lut_peers).  Every rank owns
+ * a zero-initialised, peer-mapped buffer of sx_reinhard_peer_buffer_bytes(): double sums[2][8] then
+ * uint32 flags[64].  Step `epoch` (1, 2, ...): zero sums[epoch & 1] of the own buffer,
+ * sx_reinhard_stats into it, then this call. */
+int64_t sx_reinhard_peer_buffer_bytes(void);
+int sx_reinhard_finalize_peers(const void *peer_buffers_dev, int world, int rank, uint32_t epoch,
+                               float *mean, float *std, sx_stream_t stream);
 int64_t sx_reinhard_workspace_bytes(void);
 /* stats -> finalize -> apply on one stream. */
 int sx_reinhard_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w,

@@ -39,6 +39,8 @@ PROTOTYPES: dict[str, list] = {
     "sx_reinhard_stats": [_vp, _int, _i64, _i64, _i64, _vp, _vp],
     "sx_reinhard_finalize": [_vp, _vp, _vp, _vp],
     "sx_reinhard_apply": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sx_reinhard_peer_buffer_bytes": [],
+    "sx_reinhard_finalize_peers": [_vp, _int, _int, ctypes.c_uint32, _vp, _vp, _vp],
     "sx_reinhard_workspace_bytes": [],
     "sx_reinhard_transform": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp],
     "sx_reinhard_fit": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
@@ -65,6 +67,7 @@ _RESTYPES = {
     "sx_hm_workspace_bytes": _i64,
     "sx_hm_peer_buffer_bytes": _i64,
     "sx_reinhard_workspace_bytes": _i64,
+    "sx_reinhard_peer_buffer_bytes": _i64,
     "sx_macenko_workspace_bytes": _i64,
 }
 

@@ -172,10 +172,28 @@ class ReinhardCUDA(TorchCUDABackendBase):
             return self._ops.reinhard_finalize(self._reducer.sum_(self._ops.reinhard_stats(images)))
         return self._ops.reinhard_fit(images)
 
+    _exchange = None  # sharding.PeerExchange (NVLink peer memory) or False when unavailable
+
+    def _peer_exchange(self):
+        if self._exchange is None:
+            from stainx_b200.sharding import PeerExchange
+
+            nbytes = int(_native.lib().sx_reinhard_peer_buffer_bytes())
+            self._exchange = PeerExchange.create(self._reducer, torch.device(self.device), nbytes) or False
+        return self._exchange or None
+
     def transform(self, images: torch.Tensor, target_mean: torch.Tensor, target_std: torch.Tensor) -> torch.Tensor:
         images, original = self._to_native(images)
         if self._reducer.enabled:
-            src_mean, src_std = self._ops.reinhard_finalize(self._reducer.sum_(self._ops.reinhard_stats(images)))
+            ex = self._peer_exchange()
+            if ex is not None:  # the all-reduce of the sums is fused into the finalize kernel (NVLink peer loads)
+                ex.epoch += 1
+                sums = ex.view((ex.epoch & 1) * 64, (8,), torch.float64)
+                sums.zero_()
+                self._ops.reinhard_stats(images, sums=sums)
+                src_mean, src_std = self._ops.reinhard_finalize_peers(ex)
+            else:
+                src_mean, src_std = self._ops.reinhard_finalize(self._reducer.sum_(self._ops.reinhard_stats(images)))
             result = self._ops.reinhard_apply(images, src_mean, src_std, target_mean, target_std)
         else:
             result = self._ops.reinhard_transform(images, target_mean, target_std)

@@ -266,6 +266,49 @@ __global__ void finalize_kernel(const double *__restrict__ sums, float *__restri
     }
 }
 
+// Sharded batches: the SUM all-reduce of the shifted sums fused into the finalize kernel, over
+// NVLink peer memory (the same protocol as hm.cu: build_lut_peers_kernel).  bufs[p] = rank p's
+// buffer as mapped here: double sums[2][8] (two parities), then uint32 flags[64].  Publish the own
+// sums of this epoch, wait for every rank's, add them in rank order (identical on every rank),
+// finalize.
+constexpr int kPeerSumsBytes = 2 * 8 * 8;
+constexpr int kPeerMaxWorld = 64;
+
+__global__ void finalize_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, float *__restrict__ mean, float *__restrict__ std) {
+    __shared__ double tot[8];
+    const int t = threadIdx.x;
+    const int parity = (int)(epoch & 1u);
+    if (t < world) {
+        __threadfence_system();
+        unsigned *flag = reinterpret_cast<unsigned *>(bufs[t] + kPeerSumsBytes) + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+        const unsigned *mine = reinterpret_cast<const unsigned *>(bufs[rank] + kPeerSumsBytes) + t;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        } while ((int)(seen - epoch) < 0);
+    }
+    __syncthreads();
+    if (t < 7) {
+        double acc = 0.0;
+        for (int p = 0; p < world; ++p) {
+            const double *src = reinterpret_cast<const double *>(bufs[p]) + parity * 8 + t;
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src) : "memory");
+            acc += v;
+        }
+        tot[t] = acc;
+    }
+    __syncthreads();
+    if (t < 3) {
+        const double n = tot[6];
+        const double m = tot[t] / n;
+        const double var = (tot[3 + t] - tot[t] * m) / (n - 1.0);
+        mean[t] = (float)(m + 128.0);
+        std[t] = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+}
+
 // ---- pass 2: transform ----------------------------------------------------------------------
 template <typename T, bool VEC, bool TAB>
 __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t n_img, int64_t hw, const float *__restrict__ src_mean, const float *__restrict__ src_std, const float *__restrict__ ref_mean, const float *__restrict__ ref_std) {
@@ -440,6 +483,17 @@ int sx_reinhard_apply(const void *images, int dtype, int64_t n, int64_t h, int64
     }
     if (rc) return rc;
     SX_LAUNCHED("reinhard::apply_kernel");
+    return SX_OK;
+}
+
+int64_t sx_reinhard_peer_buffer_bytes(void) { return kPeerSumsBytes + kPeerMaxWorld * 4; }
+
+int sx_reinhard_finalize_peers(const void *peer_buffers_dev, int world, int rank, uint32_t epoch, float *mean, float *std, sx_stream_t stream) {
+    SX_REQUIRE(peer_buffers_dev && mean && std, "NULL argument");
+    SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
+    SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
+    finalize_peers_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, epoch, mean, std);
+    SX_LAUNCHED("reinhard::finalize_peers_kernel");
     return SX_OK;
 }
 

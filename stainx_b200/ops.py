@@ -19,7 +19,7 @@ __all__ = [
     "MacenkoWorkspace",
     "hm_apply", "hm_build_lut", "hm_build_lut_peers", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform",
     "macenko_fit", "macenko_transform",
-    "reinhard_apply", "reinhard_finalize", "reinhard_fit", "reinhard_stats", "reinhard_transform",
+    "reinhard_apply", "reinhard_finalize", "reinhard_finalize_peers", "reinhard_fit", "reinhard_stats", "reinhard_transform",
 ]
 
 
@@ -170,6 +170,17 @@ def reinhard_finalize(sums: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     std = torch.empty(3, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(nv.lib().sx_reinhard_finalize(_ptr(sums), _ptr(mean), _ptr(std), _stream(dev)), "sx_reinhard_finalize")
+    return mean, std
+
+
+def reinhard_finalize_peers(exchange) -> tuple[torch.Tensor, torch.Tensor]:
+    """mean / std of a sharded batch with the all-reduce of the sums fused into the kernel (NVLink peer
+    loads; ``exchange``: a ``sharding.PeerExchange`` whose sums[epoch & 1] hold this rank's statistics)."""
+    dev = exchange.buf.device
+    mean = torch.empty(3, dtype=torch.float32, device=dev)
+    std = torch.empty(3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_reinhard_finalize_peers(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, exchange.epoch & 0xFFFFFFFF, _ptr(mean), _ptr(std), _stream(dev)), "sx_reinhard_finalize_peers")
     return mean, std
 
 

@@ -148,8 +148,36 @@ def macenko_cases():
     save("macenko_noise_u8", ref=ref, src=src, he_native=n._stain_matrix, maxc_native=n._target_max_conc, out_native=n.transform(src), **res)
 
 
+def real_he_cases():
+    """Real H&E tiles: 160x160 crops of the reference's example images (examples/data/target.png as
+    the reference slide, test_1 / test_3 as sources), normalised by all three methods of the
+    reference's torch CPU backend."""
+    from PIL import Image
+
+    data = Path("/root/reference/examples/data")
+
+    def crop(name, y, x, size=160):
+        im = np.asarray(Image.open(data / f"{name}.png").convert("RGB"))
+        return torch.from_numpy(np.ascontiguousarray(im[y:y + size, x:x + size].transpose(2, 0, 1))).unsqueeze(0)
+
+    ref = crop("target", 400, 400)
+    src = torch.cat([crop("test_1", 300, 500), crop("test_3", 600, 200)])
+    out = {}
+    n = HistogramMatching(device="cpu", backend="torch", channel_axis=1).fit(ref)
+    out["hm_ref_hist"], out["hm_out"] = torch.stack(n._ref_histograms_256), n.transform(src)
+    n = Reinhard(device="cpu", backend="torch").fit(ref)
+    out["rh_mean"], out["rh_std"], out["rh_out"] = n._reference_mean, n._reference_std, n.transform(src).contiguous()
+    n = Macenko(device="cpu", backend="torch").fit(ref)
+    out["mk_he"], out["mk_maxc"], out["mk_out"] = n._stain_matrix, n._target_max_conc, n.transform(src)
+    save("real_he_u8", ref=ref, src=src, **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "real":
+        real_he_cases()
+        sys.exit(0)
     print("reference stainx", stainx.__version__, "torch", torch.__version__, torch.backends.cpu.get_cpu_capability())
     hm_cases()
     reinhard_cases()
     macenko_cases()
+    real_he_cases()

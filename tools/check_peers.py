@@ -14,7 +14,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from stainx_b200 import HistogramMatching  # noqa: E402
+from stainx_b200 import HistogramMatching, Reinhard  # noqa: E402
 from stainx_b200.sharding import shard_range  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -45,6 +45,20 @@ want_nccl = hm.transform(mine)
 single = HistogramMatching(device=dev, backend="torch_cuda").fit(ref.to(dev))
 want_whole = single.transform(whole.to(dev))[lo:hi]
 ok = all(torch.equal(o, want_nccl) for o in outs) and torch.equal(want_nccl, want_whole)
+
+# Reinhard: fused finalize over peers against the NCCL path and the single-device whole batch
+reff, wholef = ref.float() / 255.0, whole.float() / 255.0
+rh = Reinhard(device=dev, backend="torch_cuda", process_group="world")
+rh.fit_broadcast(reff.to(dev), src=0)
+rimpl = rh._get_backend_impl()
+rex = rimpl._peer_exchange()
+r_outs = [rh.transform(wholef[lo:hi].to(dev)) for _ in range(4)]
+rimpl._exchange = False
+r_nccl = rh.transform(wholef[lo:hi].to(dev))
+r_single = Reinhard(device=dev, backend="torch_cuda").fit(reff.to(dev)).transform(wholef.to(dev))[lo:hi]
+r_ok = rex is not None and all(float((o - r_nccl).abs().max()) <= 1e-6 for o in r_outs) and float((r_nccl - r_single).abs().max()) <= 1e-5
+print(f"rank {rank}: reinhard peers {'ON' if rex is not None else 'unavailable'} max|peers-nccl|={max(float((o - r_nccl).abs().max()) for o in r_outs):.2e} max|nccl-single|={float((r_nccl - r_single).abs().max()):.2e}", flush=True)
+ok = ok and (r_ok or rex is None)
 
 # timing of the exchange + LUT phase
 impl._exchange = ex if ex is not None else False
