@@ -160,6 +160,19 @@ enum sx_macenko_region_id {
 int64_t sx_macenko_workspace_bytes(int64_t slots);
 /* Byte offset and size of a region inside the workspace. */
 int sx_macenko_region(int64_t slots, int region, int64_t *offset, int64_t *bytes);
+/* Sharded pooled fit on one NVLink node: the combine of slot 0's statistics over all ranks in ONE
+ * kernel (peer loads over NVLink) instead of 2-4 NCCL all-reduces per step.  Every rank's ONE-SLOT
+ * workspace lives at the start of a zero-initialised, peer-mapped buffer of
+ * sx_macenko_peer_buffer_bytes() (workspace, then uint32 flags[2][64]); peer_buffers_dev = device
+ * array of `world` pointers.  Call with the same increasing `epoch` (1, 2, ...) on every rank after
+ * moments (which = 0: MOMENTS sum, ODRANGE max), after hist(., 0) (1: HIST1, COUNTERS sum) and
+ * after hist(., 1) (2: HIST2, COUNTERS sum, VMIN min, VMAX max); `scratch` is private device memory
+ * of sx_macenko_peer_scratch_bytes().  On return (stream order) the own regions hold the combined
+ * values, bit-identical on every rank. */
+int64_t sx_macenko_peer_buffer_bytes(void);
+int64_t sx_macenko_peer_scratch_bytes(void);
+int sx_macenko_peer_combine(const void *peer_buffers_dev, int world, int rank, uint32_t epoch,
+                            int which, void *scratch, sx_stream_t stream);
 /* Initialise the workspace (must precede moments). */
 int sx_macenko_begin(void *workspace, int64_t slots, sx_stream_t stream);
 /* M1-M3: OD = -ln((255x+1)/240); mask min_c OD >= 0.15; accumulates count and shifted first and

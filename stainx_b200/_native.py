@@ -48,6 +48,9 @@ PROTOTYPES: dict[str, list] = {
     "sx_macenko_workspace_bytes": [_i64],
     "sx_macenko_region": [_i64, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)],
     "sx_macenko_begin": [_vp, _i64, _vp],
+    "sx_macenko_peer_buffer_bytes": [],
+    "sx_macenko_peer_scratch_bytes": [],
+    "sx_macenko_peer_combine": [_vp, _int, _int, ctypes.c_uint32, _int, _vp, _vp],
     "sx_macenko_moments": [_vp, _int, _i64, _i64, _i64, _int, _i64, _vp, _i64, _vp],
     "sx_macenko_basis": [_vp, _i64, _i64, _i64, _int, _vp],
     "sx_macenko_moments_fallback": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _i64, _vp],
@@ -69,6 +72,8 @@ _RESTYPES = {
     "sx_reinhard_workspace_bytes": _i64,
     "sx_reinhard_peer_buffer_bytes": _i64,
     "sx_macenko_workspace_bytes": _i64,
+    "sx_macenko_peer_buffer_bytes": _i64,
+    "sx_macenko_peer_scratch_bytes": _i64,
 }
 
 SX_U8, SX_F32 = 0, 1

@@ -224,27 +224,55 @@ class MacenkoCUDA(TorchCUDABackendBase):
             return self._ops.macenko_fit(images)
         return self._pooled_fit_sharded(images)
 
+    _exchange = None  # sharding.PeerExchange (NVLink peer memory) or False when unavailable
+
+    def _peer_exchange(self):
+        if self._exchange is None:
+            from stainx_b200.sharding import PeerExchange
+
+            nbytes = int(_native.lib().sx_macenko_peer_buffer_bytes())
+            self._exchange = PeerExchange.create(self._reducer, torch.device(self.device), nbytes) or False
+            if self._exchange:
+                self._scratch = torch.empty(int(_native.lib().sx_macenko_peer_scratch_bytes()), dtype=torch.uint8, device=self.device)
+        return self._exchange or None
+
     def _pooled_fit_sharded(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """Pooled fit of a sharded reference batch: every rank streams its own images into slot 0 of
+        its workspace; before each per-slot step the statistics of all ranks are combined -- in ONE
+        kernel over NVLink peer memory when the group can map it (``sx_macenko_peer_combine``), else
+        with NCCL all-reduces -- so every rank derives bit-identical HE / maxC."""
         red = self._reducer
-        ws = self._ops.MacenkoWorkspace(1, images.device)
+        ex = self._peer_exchange()
+        ws = self._ops.MacenkoWorkspace(1, images.device, buffer=ex.buf) if ex is not None else self._ops.MacenkoWorkspace(1, images.device)
+
+        def combine(which: int) -> None:
+            if ex is not None:
+                self._ops.macenko_peer_combine(ex, which, self._scratch)
+            elif which == 0:
+                red.sum_(ws.region("moments"))
+                red.max_(ws.region("odrange"))
+            elif which == 1:
+                red.sum_(ws.region("hist1"))
+                red.sum_(ws.region("counters"))
+            else:
+                red.sum_(ws.region("hist2"))
+                red.sum_(ws.region("counters"))
+                red.min_(ws.region("vmin"))
+                red.max_(ws.region("vmax"))
+
         ws.begin()
         if images.shape[0] > 0:
             ws.moments(images, pooled=True)
-        red.sum_(ws.region("moments"))
-        red.max_(ws.region("odrange"))
+        combine(0)
         ws.basis(0, 1, allow_fallback=False)
         for stage in (_native.SX_STAGE_ANGLE, _native.SX_STAGE_CONC):
             if images.shape[0] > 0:
                 ws.hist(images, True, stage, 0)   # subsample pass
-            red.sum_(ws.region("hist1"))
-            red.sum_(ws.region("counters"))
+            combine(1)
             ws.select(0, 1, stage, 0)             # ranks + brackets, identical on every rank
             if images.shape[0] > 0:
                 ws.hist(images, True, stage, 1)   # full pass
-            red.sum_(ws.region("hist2"))
-            red.sum_(ws.region("counters"))
-            red.min_(ws.region("vmin"))
-            red.max_(ws.region("vmax"))
+            combine(2)
             ws.select(0, 1, stage, 1)
         fit = ws.region("fit")[0]
         return fit[:6].reshape(3, 2).clone(), fit[6:8].clone()

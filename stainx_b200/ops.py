@@ -18,7 +18,7 @@ from stainx_b200._native import SX_F32, SX_NCHW, SX_NHWC, SX_U8, check
 __all__ = [
     "MacenkoWorkspace",
     "hm_apply", "hm_build_lut", "hm_build_lut_peers", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform",
-    "macenko_fit", "macenko_transform",
+    "macenko_fit", "macenko_peer_combine", "macenko_transform",
     "reinhard_apply", "reinhard_finalize", "reinhard_finalize_peers", "reinhard_fit", "reinhard_stats", "reinhard_transform",
 ]
 
@@ -228,11 +228,12 @@ class MacenkoWorkspace:
     """Device scratch of the Macenko phases for ``slots`` statistic slots, plus typed views of the
     regions a sharded run all-reduces (``include/stainx_b200.h``: ``sx_macenko_region``)."""
 
-    def __init__(self, slots: int, device: torch.device):
+    def __init__(self, slots: int, device: torch.device, buffer: torch.Tensor | None = None):
         self.slots = int(slots)
         self.device = torch.device(device)
         self.nbytes = int(nv.lib().sx_macenko_workspace_bytes(self.slots))
-        self.buffer = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        # `buffer`: caller-provided storage (e.g. NVLink peer-mapped memory for the sharded fit)
+        self.buffer = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) if buffer is None else buffer[: self.nbytes]
         self._views: dict[str, torch.Tensor] = {}
 
     def region(self, name: str) -> torch.Tensor:
@@ -273,6 +274,15 @@ class MacenkoWorkspace:
         n, h, w = _check_images(images)
         scale = 1.0 / 255.0 if unit else 1.0
         self._call("sx_macenko_apply", _ptr(images), _dtype_code(images), n, h, w, slot0, _ptr(he_ref), _ptr(maxc_ref), _ptr(out), _dtype_code(out), ctypes.c_float(scale), _ptr(self.buffer), self.slots)
+
+
+def macenko_peer_combine(exchange, which: int, scratch: torch.Tensor) -> None:
+    """Combine slot 0's statistics of every rank in place, in one kernel over NVLink peer memory
+    (``which``: 0 after moments, 1 after a sample pass, 2 after a resolve pass).  Advances the epoch."""
+    exchange.epoch += 1
+    dev = exchange.buf.device
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_macenko_peer_combine(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, exchange.epoch & 0xFFFFFFFF, int(which), _ptr(scratch), _stream(dev)), "sx_macenko_peer_combine")
 
 
 def _macenko_out(images: torch.Tensor, unit: bool) -> torch.Tensor:

@@ -14,7 +14,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from stainx_b200 import HistogramMatching, Reinhard  # noqa: E402
+from stainx_b200 import HistogramMatching, Macenko, Reinhard  # noqa: E402
+from tests.helpers import he_tile  # noqa: E402
 from stainx_b200.sharding import shard_range  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -59,6 +60,39 @@ r_single = Reinhard(device=dev, backend="torch_cuda").fit(reff.to(dev)).transfor
 r_ok = rex is not None and all(float((o - r_nccl).abs().max()) <= 1e-6 for o in r_outs) and float((r_nccl - r_single).abs().max()) <= 1e-5
 print(f"rank {rank}: reinhard peers {'ON' if rex is not None else 'unavailable'} max|peers-nccl|={max(float((o - r_nccl).abs().max()) for o in r_outs):.2e} max|nccl-single|={float((r_nccl - r_single).abs().max()):.2e}", flush=True)
 ok = ok and (r_ok or rex is None)
+
+# Macenko pooled fit of a sharded batch: peer combine kernel against NCCL all-reduces and the single-device fit
+tiles = torch.cat([he_tile(256, 256, 100 + i, 0.9 + 0.05 * (i % 5)) for i in range(n_total)])
+mk = Macenko(device=dev, backend="torch_cuda", process_group="world")
+mimpl = mk._get_backend_impl()
+mex = mimpl._peer_exchange()
+fits = []
+for _ in range(3):
+    mk.fit(tiles[lo:hi].to(dev))
+    fits.append((mk._stain_matrix.clone(), mk._target_max_conc.clone()))
+mimpl._exchange = False
+mk.fit(tiles[lo:hi].to(dev))
+he_nccl, mc_nccl = mk._stain_matrix.clone(), mk._target_max_conc.clone()
+single_mk = Macenko(device=dev, backend="torch_cuda").fit(tiles.to(dev))
+m_ok = all(torch.equal(h, he_nccl) and torch.equal(m, mc_nccl) for h, m in fits)
+m_ok = m_ok and float((he_nccl - single_mk._stain_matrix).abs().max()) <= 1e-6 and float((mc_nccl / single_mk._target_max_conc - 1).abs().max()) <= 1e-6
+print(f"rank {rank}: macenko peers {'ON' if mex is not None else 'unavailable'} fit==nccl: {m_ok} |he-single|={float((he_nccl - single_mk._stain_matrix).abs().max()):.2e}", flush=True)
+ok = ok and (m_ok or mex is None)
+mimpl._exchange = mex if mex is not None else False
+bigf = torch.rand(16, 3, 1024, 1024, device=dev)
+for label, use_peers in (("peers", True), ("nccl", False)):
+    mimpl._exchange = (mex if mex is not None else False) if use_peers else False
+    for _ in range(3):
+        mk.fit(bigf)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        mk.fit(bigf)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(f"macenko pooled fit 16x1024^2 f32 per rank, exchange={label}: {(time.perf_counter() - t0) / 20 * 1e6:.1f} us", flush=True)
+del bigf
 
 # timing of the exchange + LUT phase
 impl._exchange = ex if ex is not None else False
