@@ -329,7 +329,7 @@ def main() -> None:
     # ---- roofline of the dominant kernel (algorithmic bytes / live CUDA-event time) ----------
     px = n_img * H * W
     kernels = {
-        "hm::hist_u8_planar_lane_tma_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
+        "hm::hist_u8_planar_lane_pw_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
         "hm::apply_u8_planar_kernel": {"algo_bytes": 6.0 * px, "ms": apply_ms},
     }
     for k in kernels.values():

@@ -175,6 +175,16 @@ struct TileRing {
         if ((threadIdx.x & 31) == 0) mbar_arrive(empty + st);
         ++consumed;
     }
+    // the same for the tile with running index `g` (consumers that take every n-th tile)
+    __device__ __forceinline__ const uint4 *acquire_at(unsigned g) {
+        const unsigned st = g & (kStages - 1), use = g / kStages;
+        mbar_wait(full + st, use & 1);
+        return ring + (size_t)st * kTileVecs;
+    }
+    __device__ __forceinline__ void release_at(unsigned g) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + (g & (kStages - 1)));
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +318,104 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_tma_kern
                     }
             }
         }
+        flush(c);
+        seg = seg_end;
+    }
+}
+
+// The same kernel with WARP-GRANULAR tiles: tile g of the CTA's list goes to ring stage g % stages
+// and is consumed by counting warp g % warps alone (the stage's "empty" barrier expects one
+// arrival).  With CTA-wide tiles all counting warps run out of data at the same moment and the
+// shared-memory atomic unit idles until the next tile lands; here the warps drift apart, so while
+// one waits the others keep the unit busy.  A warp reads its tile straight from the ring, four
+// 128-bit vectors per lane at a time.
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    constexpr int kW = Cfg::kWarps, kThreadsAll = Cfg::kThreads, kTV = Cfg::kTileVecs, kStages = Cfg::kStages;
+    static_assert(Cfg::kProducer, "the per-warp kernel needs the producer warp");
+    extern __shared__ __align__(16) unsigned char smem_lane[];
+    unsigned int *regions = reinterpret_cast<unsigned int *>(smem_lane);  // [warp][bin][lane]
+    unsigned char *ring_mem = smem_lane + kW * 32768;
+    unsigned char *tail = ring_mem + kStages * kTV * 16;
+    unsigned int *hist32 = reinterpret_cast<unsigned int *>(tail + 2 * kStages * 8);  // [bin]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileRing<kStages, kTV, 1> tr;
+    tr.init(ring_mem, reinterpret_cast<uint64_t *>(tail));
+    for (int i = threadIdx.x; i < kW * 8192; i += kThreadsAll) regions[i] = 0u;
+    for (int i = threadIdx.x; i < 256; i += kThreadsAll) hist32[i] = 0u;
+    __syncthreads();
+    const bool counting = warp < kW;
+    unsigned int *region = regions + (counting ? warp : 0) * 8192;
+    const unsigned cbase = smem_u32(region) + (unsigned)lane * 4u;
+
+    const int64_t per_channel = n_img * tiles_per_plane;
+    const int64_t items = 3 * per_channel;
+    const int64_t per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const int64_t first = (int64_t)blockIdx.x * per_cta;
+    const int64_t last = first + per_cta < items ? first + per_cta : items;
+    const uint4 *base = reinterpret_cast<const uint4 *>(img);
+
+    auto flush = [&](int c) {  // lane-private counters of every warp -> global counts of channel c, re-zero
+        __syncthreads();
+        for (int bin = lane; counting && bin < 256; bin += 32) {
+            unsigned sum = 0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const int col = (k + lane) & 31;
+                sum += region[bin * 32 + col];
+                region[bin * 32 + col] = 0u;
+            }
+            if (sum) atomicAdd(&hist32[bin], sum);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 256; i += kThreadsAll) {
+            const unsigned v = hist32[i];
+            if (v) atomicAdd(&counts[c * 256 + i], (unsigned long long)v);
+            hist32[i] = 0u;
+        }
+        __syncthreads();
+    };
+
+    unsigned g0 = 0;  // running index of the segment's first tile
+    int64_t seg = first;
+    while (seg < last) {  // one channel segment at a time (at most three per CTA)
+        const int c = (int)(seg / per_channel);
+        const int64_t chan_end = (int64_t)(c + 1) * per_channel;
+        const int64_t seg_end = chan_end < last ? chan_end : last;
+        const int n_items = (int)(seg_end - seg);
+        TileCursor cur;
+        cur.seek(hw, (int)tiles_per_plane, kTV, per_channel, seg);
+        if (warp == kW) {  // producer warp
+            if (lane == 0) {
+                for (int item = 0; item < n_items; ++item) {
+                    tr.produce(base + cur.off, (unsigned)cur.vecs(kTV) * 16u);
+                    cur.next(kTV);
+                }
+            }
+            __syncwarp();
+        } else if (counting) {
+            for (int k = 0; k < warp; ++k) cur.next(kTV);
+            for (int item = warp; item < n_items; item += kW) {
+                const int nv = cur.vecs(kTV);
+                const uint4 *tile = tr.acquire_at(g0 + (unsigned)item);
+                for (int v0 = lane; v0 < nv; v0 += 128) {
+                    uint4 v[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ok[j] = v0 + 32 * j < nv;
+                        if (ok[j]) v[j] = tile[v0 + 32 * j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (ok[j]) { lane_count4(v[j].x, cbase); lane_count4(v[j].y, cbase); lane_count4(v[j].z, cbase); lane_count4(v[j].w, cbase); }
+                }
+                tr.release_at(g0 + (unsigned)item);
+#pragma unroll
+                for (int k = 0; k < kW; ++k) cur.next(kTV);
+            }
+        }
+        g0 += (unsigned)n_items;
         flush(c);
         seg = seg_end;
     }
@@ -524,14 +632,19 @@ __global__ void ref_cdf_kernel(const float *__restrict__ ref_hist, float *__rest
 // H2b: torch_backend.py:L234-281.  npix < 0: derive the pixel count from the counts themselves
 // (sum over the 256 bins of the channel), which keeps a sharded run free of host round trips.
 // FROM_HIST: the reference CDF is rebuilt from ref_hist inside the same kernel (fused transform).
+struct LutSmem {  // shared scratch of one channel's LUT build
+    double dacc[256];
+    float rq[256];
+    float sq[256];
+};
+
 // One channel (CTA of 256 threads): thread b holds the count of bin b.
 template <bool FROM_HIST>
-__device__ __forceinline__ void build_lut_channel(const unsigned long long my_count, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
-    __shared__ float rq[256];
-    __shared__ float sq[256];
-    __shared__ double dacc[256];
+__device__ __forceinline__ void build_lut_channel(const int c, const unsigned long long my_count, long long npix, const float *__restrict__ ref, float *__restrict__ lut, LutSmem *ls) {
+    float *rq = ls->rq, *sq = ls->sq;
+    double *dacc = ls->dacc;
     __shared__ float s_npix_f;
-    const int c = blockIdx.x, b = threadIdx.x;
+    const int b = threadIdx.x;
     if (FROM_HIST) ref_cdf_to_smem(ref + c * 256, sq, dacc, rq);
     else rq[b] = ref[c * 256 + b];
     {
@@ -574,7 +687,8 @@ __device__ __forceinline__ void build_lut_channel(const unsigned long long my_co
 
 template <bool FROM_HIST>
 __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
-    build_lut_channel<FROM_HIST>(counts[blockIdx.x * 256 + threadIdx.x], npix, ref, lut);
+    __shared__ LutSmem ls;
+    build_lut_channel<FROM_HIST>(blockIdx.x, counts[blockIdx.x * 256 + threadIdx.x], npix, ref, lut, &ls);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,7 +735,8 @@ __global__ void __launch_bounds__(256) build_lut_peers_kernel(unsigned char *con
         total += v;
     }
     if (counts_out != nullptr) counts_out[c * 256 + b] = total;
-    build_lut_channel<false>(total, -1, ref_cdf, lut);  // (4); pixel count = sum of the channel's counts
+    __shared__ LutSmem ls;
+    build_lut_channel<false>(c, total, -1, ref_cdf, lut, &ls);  // (4); pixel count = sum of the channel's counts
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -781,9 +896,10 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
 }
 
 // ---- tuning knobs (A/B measurements; defaults are the measured winners) -----------------------
-static int g_hist_byte_counters = 5;  // uint8 planar histogram: 5 lane-private counters fed by a TMA ring (default for 16-byte aligned
-                                      // planes from 8 MB on: data-independent), 0 warp-private atomics (any alignment; faster on constant
-                                      // images, slower on noise), 6 ring feed without counting (measurement only: wrong counts)
+static int g_hist_byte_counters = 5;  // uint8 planar histogram: 5 lane-private counters fed by a TMA ring, warp-granular tiles (default
+                                      // for 16-byte aligned planes from 8 MB on: data-independent), 9 the same with CTA-wide tiles,
+                                      // 0 warp-private atomics (any alignment; faster on constant images, slower on noise),
+                                      // 6 ring feed without counting (measurement only: wrong counts)
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 16;
 
@@ -805,11 +921,29 @@ static int launch_lane_tma_cfg(const uint8_t *images, int64_t hw, int64_t n, uns
     hist_u8_planar_lane_tma_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
     return SX_OK;
 }
+template <typename Cfg>
+static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_pw_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        attr_set = true;
+    }
+    const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
+    const unsigned grid = stream_grid(3 * n * tiles, 1);
+    hist_u8_planar_lane_pw_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
+    return SX_OK;
+}
 static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
-    // measured on B200, 64 x 3 x 1024^2 noise: <5 warps, 16 KB x 4, no producer> 80 us; <4, 24 KB x 4> 69 us;
-    // <4 + producer, 24 KB x 4> 62 us (default); <4 + producer, 12 KB x 8> 67 us; <3 + producer, 32 KB x 4> 75 us
+    // measured on B200, 64 x 3 x 1024^2 noise.  CTA-wide tiles: <5 warps, 16 KB x 4, no producer> 80 us; <4, 24 KB x 4> 69 us;
+    // <4 + producer, 24 KB x 4> 62 us; <4 + producer, 12 KB x 8> 67 us; <3 + producer, 32 KB x 4> 75 us.
+    // Warp-granular tiles: <4 + producer, 12 KB x 8> 59.7 us (default); <4 + producer, 6 KB x 16> 62.8 us.
+    // Floor of this design: ATOMS (2.1 clk per warp instruction) + TMA writes + LDS reads share the SM's
+    // one-wavefront-per-clock shared-memory pipe: ~110 K clk per SM = 56 us.
     if (mode == 6) return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, false, true>>(images, hw, n, cnt, stream);  // feed rate only: 40 us
-    return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, true, true>>(images, hw, n, cnt, stream);
+    if (mode == 9) return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, true, true>>(images, hw, n, cnt, stream);   // CTA-wide tiles
+    // (Building the LUT in the tail of this kernel -- last CTA, CTA padded to 256 threads -- was measured: the
+    // padded kernel is 6 us slower and the serial three-channel build costs more than the saved launch.)
+    return launch_lane_pw_cfg<LaneCfg<4, 768, 8, true, true>>(images, hw, n, cnt, stream);
 }
 
 extern "C" {
@@ -939,11 +1073,10 @@ int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_
     SX_REQUIRE(workspace && workspace_bytes >= sx_hm_workspace_bytes(), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_hm_workspace_bytes());
     SX_REQUIRE(ref_hist != nullptr, "ref_hist is NULL");
     auto *counts = static_cast<uint64_t *>(workspace);
-    auto *ref_cdf = reinterpret_cast<float *>(counts + 768);
-    auto *lut = ref_cdf + 768;
+    auto *lut = reinterpret_cast<float *>(counts + 768) + 768;
     SX_CUDA(cudaMemsetAsync(counts, 0, 768 * 8, static_cast<cudaStream_t>(stream)));
     if (int rc = sx_hm_hist(images, dtype, layout, n, h, w, counts, stream)) return rc;
-    (void)ref_cdf;
+    // H2 with the reference CDF rebuilt from ref_hist inside the same kernel
     build_lut_kernel<true><<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)(n * h * w), ref_hist, lut);
     SX_LAUNCHED("build_lut_kernel<fused>");
     return sx_hm_apply(images, dtype, layout, n, h, w, lut, out, stream);

@@ -55,7 +55,7 @@ def probe_hm():
     lib = nv.lib()
     counts = torch.zeros((3, 256), dtype=torch.int64, device=dev)
     want = ops.hm_hist(src)
-    for mode, ctas in ((0, 8), (5, 1), (6, 1)):
+    for mode, ctas in ((0, 8), (5, 1), (9, 1), (6, 1)):
         lib.sx_hm_set_tuning(mode, ctas, -1)
         ok = torch.equal(ops.hm_hist(src), want)
         report(f"hm hist u8 planar mode={mode} ctas/sm={ctas} ok={ok}", timeit(lambda: ops.hm_hist(src, counts=counts)), 3 * px)
