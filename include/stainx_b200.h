@@ -141,9 +141,12 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
  *         -> hist(ANGLE,0) -> select(ANGLE,0) -> hist(ANGLE,1) -> select(ANGLE,1)   (M5-M7)
  *         -> hist(CONC,0)  -> select(CONC,0)  -> hist(CONC,1)  -> select(CONC,1)    (M8-M9)
  *         -> apply (M10)   or   read the FIT region (M11)
- * A sharded pooled fit all-reduces the regions named by sx_macenko_region() after `moments`
- * (MOMENTS, ODRANGE) and after every `hist` (level 0: HIST1, COUNTERS; level 1: HIST2, COUNTERS,
- * VMIN, VMAX). */
+ * A sharded pooled fit combines the regions named by sx_macenko_region() over the ranks after
+ * `moments` (MOMENTS, ODRANGE) and after every `hist` (level 0: HIST1, COUNTERS; level 1: HIST2,
+ * COUNTERS, VMIN, VMAX) -- with all-reduces, or on one NVLink node with sx_macenko_peer_combine.
+ * sx_macenko_transform does not use the phase functions one by one: it chains lean streaming kernels
+ * and per-image kernels of its own (10 launches per chain, up to 4 part-batch chains on side
+ * streams that it forks from and joins into `stream`). */
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
     SX_REGION_MOMENTS = 0,  /* double  [slots][12]   reduce: SUM */
