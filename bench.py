@@ -330,7 +330,7 @@ def main() -> None:
     px = n_img * H * W
     kernels = {
         "hm::hist_u8_planar_lane_pw_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
-        "hm::apply_u8_planar_kernel": {"algo_bytes": 6.0 * px, "ms": apply_ms},
+        "hm::apply_u8_planar_vec_kernel": {"algo_bytes": 6.0 * px, "ms": apply_ms},
     }
     for k in kernels.values():
         k["gbs"] = k["algo_bytes"] / (k["ms"] / 1e3) / 1e9
