@@ -160,7 +160,9 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
                 lut = self._ops.hm_build_lut(counts, -1, ref_cdf)
             result = self._ops.hm_apply(images, lut, layout)
         else:
-            result = self._ops.hm_transform(images, self._stack_reference(reference_histogram), layout)
+            # one library call = one chain of programmatic dependent launches (zero, histogram, LUT, remap);
+            # the stacked reference is cached, so a transform enqueues no torch kernel at all
+            result = self._ops.hm_transform(images, self._reference(reference_histogram)[0], layout)
         return self._restore_dtype(result, original)
 
 

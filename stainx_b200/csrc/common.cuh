@@ -51,8 +51,37 @@ inline unsigned stream_grid(int64_t items, int per_sm) {
     return (unsigned)(g < 1 ? 1 : g);
 }
 
+// ---- programmatic dependent launch -------------------------------------------------------------
+// launch_pdl() starts `kernel` with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may
+// become resident as soon as every CTA of the kernel in front of it on the stream has executed
+// pdl_trigger() (or exited), instead of after that kernel has drained and the launch has been
+// processed (~2 us per edge on B200).  Contract inside this library: a kernel started this way
+// executes pdl_wait() before its first access to anything the kernels in front of it in the SAME
+// library call produce, and -- unless the caller of the launch knows that the first kernel of the
+// chain was started with normal stream order -- before its first global access of any kind.
+// pdl_wait() in a kernel that was launched normally is a no-op.
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- device side ----------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // 128-bit streaming loads/stores.  .nc + L1::no_allocate: every byte is used once per pass, so
 // keep it out of L1; L2 allocation stays default so that later passes over the same image can

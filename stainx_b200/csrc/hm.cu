@@ -339,14 +339,20 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kerne
     unsigned char *tail = ring_mem + kStages * kTV * 16;
     unsigned int *hist32 = reinterpret_cast<unsigned int *>(tail + 2 * kStages * 8);  // [bin]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_trigger();  // the LUT kernel behind this one may become resident; it waits for our completion
     TileRing<kStages, kTV, 1> tr;
     tr.init(ring_mem, reinterpret_cast<uint64_t *>(tail));
-    for (int i = threadIdx.x; i < kW * 8192; i += kThreadsAll) regions[i] = 0u;
-    for (int i = threadIdx.x; i < 256; i += kThreadsAll) hist32[i] = 0u;
-    __syncthreads();
+    __syncthreads();  // barriers initialised: the producer starts streaming while the counters are zeroed
     const bool counting = warp < kW;
     unsigned int *region = regions + (counting ? warp : 0) * 8192;
     const unsigned cbase = smem_u32(region) + (unsigned)lane * 4u;
+    if (counting) {  // a region is private to its warp until the first flush (which starts with a CTA barrier)
+        uint4 *r4 = reinterpret_cast<uint4 *>(region);
+        for (int i = lane; i < 2048; i += 32) r4[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (warp == 0)
+            for (int i = lane; i < 256; i += 32) hist32[i] = 0u;
+        __syncwarp();
+    }
 
     const int64_t per_channel = n_img * tiles_per_plane;
     const int64_t items = 3 * per_channel;
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kerne
             if (sum) atomicAdd(&hist32[bin], sum);
         }
         __syncthreads();
+        pdl_wait();  // `counts` is zeroed by the kernel in front of us when we run inside sx_hm_transform / sx_hm_fit
         for (int i = threadIdx.x; i < 256; i += kThreadsAll) {
             const unsigned v = hist32[i];
             if (v) atomicAdd(&counts[c * 256 + i], (unsigned long long)v);
@@ -552,7 +559,8 @@ __global__ void ref_hist_kernel(const unsigned long long *__restrict__ counts, f
     __shared__ float cf[256];
     __shared__ float denom;
     const int c = blockIdx.x, b = threadIdx.x;
-    cf[b] = __ull2float_rn(counts[c * 256 + b]);
+    pdl_wait();  // launched with launch_pdl() behind the histogram kernel
+    cf[b] = __ull2float_rn(__ldcg(counts + c * 256 + b));  // not an invariant load: see build_lut_kernel
     __syncthreads();
     if (b == 0) denom = __fadd_rn(torch_sum_256(cf), 1e-8f);
     __syncthreads();
@@ -645,8 +653,7 @@ __device__ __forceinline__ void build_lut_channel(const int c, const unsigned lo
     double *dacc = ls->dacc;
     __shared__ float s_npix_f;
     const int b = threadIdx.x;
-    if (FROM_HIST) ref_cdf_to_smem(ref + c * 256, sq, dacc, rq);
-    else rq[b] = ref[c * 256 + b];
+    if (!FROM_HIST) rq[b] = __ldcg(ref + c * 256 + b);  // FROM_HIST: the caller has filled rq (ref_cdf_to_smem)
     {
         __shared__ unsigned long long s_part[8];
         unsigned long long t = my_count;
@@ -685,10 +692,25 @@ __device__ __forceinline__ void build_lut_channel(const int c, const unsigned lo
     lut[c * 256 + b] = fminf(fmaxf(v, 0.0f), 255.0f);                       // L281
 }
 
+// Launched with launch_pdl().  FROM_HIST (only inside sx_hm_transform, whose first kernel is started in
+// normal stream order, so `ref` is visible to every kernel of the chain): the reference CDF is built
+// while the histogram kernel in front of us is still running; the counts are read after pdl_wait().
 template <bool FROM_HIST>
 __global__ void build_lut_kernel(const unsigned long long *__restrict__ counts, long long npix, const float *__restrict__ ref, float *__restrict__ lut) {
     __shared__ LutSmem ls;
-    build_lut_channel<FROM_HIST>(blockIdx.x, counts[blockIdx.x * 256 + threadIdx.x], npix, ref, lut, &ls);
+    pdl_trigger();
+    if (FROM_HIST) ref_cdf_to_smem(ref + blockIdx.x * 256, ls.sq, ls.dacc, ls.rq);
+    pdl_wait();
+    // __ldcg (a volatile, coherent load): a plain load through a const __restrict__ pointer is an
+    // invariant (ld.global.nc) load to the compiler, which may hoist it above pdl_wait()
+    build_lut_channel<FROM_HIST>(blockIdx.x, __ldcg(counts + blockIdx.x * 256 + threadIdx.x), npix, ref, lut, &ls);
+}
+
+// Zeroes the counts at the head of sx_hm_transform / sx_hm_fit (a kernel instead of a memset node so
+// that the histogram kernel behind it can be a programmatic dependent launch).
+__global__ void zero_counts_kernel(unsigned long long *__restrict__ counts) {
+    pdl_trigger();
+    counts[threadIdx.x] = 0ull;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -714,6 +736,8 @@ constexpr int kPeerMaxWorld = 64;
 __global__ void __launch_bounds__(256) build_lut_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, const float *__restrict__ ref_cdf, float *__restrict__ lut, unsigned long long *__restrict__ counts_out) {
     const int c = blockIdx.x, b = threadIdx.x;
     const int parity = (int)(epoch & 1u);
+    pdl_trigger();
+    pdl_wait();  // launched with launch_pdl(): this rank's counts come from the kernel in front of us
     if (c == 0 && b < world) {  // (1) publish my counts (written by earlier kernels of this stream)
         __threadfence_system();
         unsigned *flag = reinterpret_cast<unsigned *>(bufs[b] + kPeerCountsBytes) + rank;
@@ -813,22 +837,36 @@ __device__ __forceinline__ unsigned remap4_prmt(unsigned w, unsigned tab_addr) {
     return __byte_perm(__byte_perm(t0, t1, 0x0040), __byte_perm(t2, t3, 0x0040), 0x5410);
 }
 
-__global__ void __launch_bounds__(kThreads) apply_u8_planar_vec_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, unsigned vecs, unsigned planes, unsigned tiles_per_plane, const float *__restrict__ lut) {
+// Launched with launch_pdl().  `chain` != 0 (inside sx_hm_transform: the images were visible before the
+// first kernel of the chain started): the CTA's first tile is loaded BEFORE pdl_wait(), i.e. while the
+// LUT kernel -- and the tail of the histogram kernel -- in front of us are still running.
+__global__ void __launch_bounds__(kThreads) apply_u8_planar_vec_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, unsigned vecs, unsigned planes, unsigned tiles_per_plane, const float *__restrict__ lut, int chain) {
     __shared__ __align__(256) unsigned char lut8[3 * 256];
-    for (int i = threadIdx.x; i < 768; i += kThreads) lut8[i] = (unsigned char)__float2int_rz(lut[i]);  // trunc, L296-298
+    const unsigned items = planes * tiles_per_plane;  // < 2^31 (checked by the caller)
+    pdl_trigger();
+    if (!chain) pdl_wait();
+    uint4 v[kUnroll];
+    auto load_item = [&](unsigned it) {
+        const unsigned item = items - 1 - it;
+        const unsigned pl = item / tiles_per_plane, t = item - pl * tiles_per_plane;
+        const size_t base = (size_t)pl * vecs;
+        const unsigned v0 = t * kTileVecs + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (v0 + u * kThreads < vecs) v[u] = ld_stream(src + base + v0 + u * kThreads);
+    };
+    if (blockIdx.x < items) load_item(blockIdx.x);
+    if (chain) pdl_wait();
+    for (int i = threadIdx.x; i < 768; i += kThreads) lut8[i] = (unsigned char)__float2int_rz(__ldcg(lut + i));  // trunc, L296-298; not an invariant load (see build_lut_kernel)
     __syncthreads();
     const unsigned tab0 = smem_u32(lut8);
-    const unsigned items = planes * tiles_per_plane;  // < 2^31 (checked by the caller)
     for (unsigned it = blockIdx.x; it < items; it += gridDim.x) {
         const unsigned item = items - 1 - it;  // from the end of the batch (what a front-to-back histogram left in L2)
         const unsigned pl = item / tiles_per_plane, t = item - pl * tiles_per_plane;
         const unsigned tab = tab0 + (pl % 3u) * 256u;
         const size_t base = (size_t)pl * vecs;
         const unsigned v0 = t * kTileVecs + threadIdx.x;
-        uint4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (v0 + u * kThreads < vecs) v[u] = ld_stream(src + base + v0 + u * kThreads);
+        if (it != blockIdx.x) load_item(it);
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             if (v0 + u * kThreads < vecs) {
@@ -965,7 +1003,7 @@ static int launch_lane_tma_cfg(const uint8_t *images, int64_t hw, int64_t n, uns
     return SX_OK;
 }
 template <typename Cfg>
-static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
+static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream, bool pdl) {
     static bool attr_set = false;
     if (!attr_set) {
         SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_pw_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -973,10 +1011,11 @@ static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsi
     }
     const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
     const unsigned grid = stream_grid(3 * n * tiles, 1);
-    hist_u8_planar_lane_pw_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
+    if (pdl) SX_CUDA(launch_pdl(hist_u8_planar_lane_pw_kernel<Cfg>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, stream, images, hw, n, tiles, cnt));
+    else hist_u8_planar_lane_pw_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
     return SX_OK;
 }
-static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
+static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream, bool pdl) {
     // measured on B200, 64 x 3 x 1024^2 noise.  CTA-wide tiles: <5 warps, 16 KB x 4, no producer> 80 us; <4, 24 KB x 4> 69 us;
     // <4 + producer, 24 KB x 4> 62 us; <4 + producer, 12 KB x 8> 67 us; <3 + producer, 32 KB x 4> 75 us.
     // Warp-granular tiles: <4 + producer, 12 KB x 8> 59.7 us (default); <4 + producer, 6 KB x 16> 62.8 us.
@@ -986,7 +1025,7 @@ static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t 
     if (mode == 9) return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, true, true>>(images, hw, n, cnt, stream);   // CTA-wide tiles
     // (Building the LUT in the tail of this kernel -- last CTA, CTA padded to 256 threads -- was measured: the
     // padded kernel is 6 us slower and the serial three-channel build costs more than the saved launch.)
-    return launch_lane_pw_cfg<LaneCfg<4, 768, 8, true, true>>(images, hw, n, cnt, stream);
+    return launch_lane_pw_cfg<LaneCfg<4, 768, 8, true, true>>(images, hw, n, cnt, stream, pdl);
 }
 
 extern "C" {
@@ -999,7 +1038,9 @@ int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_cta
     return SX_OK;
 }
 
-int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, uint64_t *counts, sx_stream_t stream_) {
+// `chain`: called from sx_hm_transform / sx_hm_fit right behind zero_counts_kernel (which was started in
+// normal stream order): the persistent histogram kernel is a programmatic dependent launch.
+static int hist_impl(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, uint64_t *counts, sx_stream_t stream_, bool chain) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     SX_REQUIRE(counts != nullptr, "counts is NULL");
     SX_REQUIRE(layout == SX_NCHW || layout == SX_NHWC, "layout must be SX_NCHW or SX_NHWC, got %d", layout);
@@ -1026,7 +1067,7 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
         const bool planes_aligned = aligned16(images) && hw % 16 == 0;
         // the persistent lane-private kernel zeroes 128 KB of counters per SM: worth it from ~8 MB of pixels on
         if (g_hist_byte_counters >= 5 && planes_aligned && n * hw * 3 >= ((int64_t)8 << 20)) {
-            if (int rc = launch_lane_tma(g_hist_byte_counters, static_cast<const uint8_t *>(images), hw, n, cnt, stream)) return rc;
+            if (int rc = launch_lane_tma(g_hist_byte_counters, static_cast<const uint8_t *>(images), hw, n, cnt, stream, chain)) return rc;
         } else {
             dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
             grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
@@ -1043,9 +1084,13 @@ int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, 
     return SX_OK;
 }
 
+int sx_hm_hist(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, uint64_t *counts, sx_stream_t stream) {
+    return hist_impl(images, dtype, layout, n, h, w, counts, stream, false);
+}
+
 int sx_hm_ref_hist(const uint64_t *counts, float *ref_hist, sx_stream_t stream) {
     SX_REQUIRE(counts && ref_hist, "NULL argument");
-    ref_hist_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), ref_hist);
+    SX_CUDA(launch_pdl(ref_hist_kernel, dim3(3), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const unsigned long long *>(counts), ref_hist));
     SX_LAUNCHED("ref_hist_kernel");
     return SX_OK;
 }
@@ -1059,12 +1104,12 @@ int sx_hm_ref_cdf(const float *ref_hist, float *ref_cdf, sx_stream_t stream) {
 
 int sx_hm_build_lut(const uint64_t *counts, int64_t npix, const float *ref_cdf, float *lut, sx_stream_t stream) {
     SX_REQUIRE(counts && ref_cdf && lut, "NULL argument");
-    build_lut_kernel<false><<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)npix, ref_cdf, lut);
+    SX_CUDA(launch_pdl(build_lut_kernel<false>, dim3(3), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const unsigned long long *>(counts), (long long)npix, ref_cdf, lut));
     SX_LAUNCHED("build_lut_kernel");
     return SX_OK;
 }
 
-int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const float *lut, void *out, sx_stream_t stream_) {
+static int apply_impl(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const float *lut, void *out, sx_stream_t stream_, bool chain) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     SX_REQUIRE(layout == SX_NCHW || layout == SX_NHWC, "layout must be SX_NCHW or SX_NHWC, got %d", layout);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1087,7 +1132,7 @@ int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h,
     const int64_t tiles_v = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
     if (dtype == SX_U8 && aligned16(images) && aligned16(out) && hw % 16 == 0 && planes * tiles_v < ((int64_t)1 << 31) && hw / 16 < ((int64_t)1 << 31)) {
         unsigned grid = stream_grid(planes * tiles_v, g_apply_ctas_per_sm);
-        apply_u8_planar_vec_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut);
+        SX_CUDA(launch_pdl(apply_u8_planar_vec_kernel, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain ? 1 : 0));
         SX_LAUNCHED("apply_u8_planar_vec_kernel");
     } else if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
@@ -1103,13 +1148,17 @@ int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h,
     return SX_OK;
 }
 
+int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const float *lut, void *out, sx_stream_t stream) {
+    return apply_impl(images, dtype, layout, n, h, w, lut, out, stream, false);
+}
+
 int64_t sx_hm_peer_buffer_bytes(void) { return kPeerCountsBytes + kPeerMaxWorld * 4; }
 
 int sx_hm_build_lut_peers(const void *peer_buffers_dev, int world, int rank, uint32_t epoch, const float *ref_cdf, float *lut, uint64_t *counts_out, sx_stream_t stream) {
     SX_REQUIRE(peer_buffers_dev && ref_cdf && lut, "NULL argument");
     SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
     SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
-    build_lut_peers_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, epoch, ref_cdf, lut, reinterpret_cast<unsigned long long *>(counts_out));
+    SX_CUDA(launch_pdl(build_lut_peers_kernel, dim3(3), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, (unsigned)epoch, ref_cdf, lut, reinterpret_cast<unsigned long long *>(counts_out)));
     SX_LAUNCHED("build_lut_peers_kernel");
     return SX_OK;
 }
@@ -1122,19 +1171,24 @@ int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_
     SX_REQUIRE(ref_hist != nullptr, "ref_hist is NULL");
     auto *counts = static_cast<uint64_t *>(workspace);
     auto *lut = reinterpret_cast<float *>(counts + 768) + 768;
-    SX_CUDA(cudaMemsetAsync(counts, 0, 768 * 8, static_cast<cudaStream_t>(stream)));
-    if (int rc = sx_hm_hist(images, dtype, layout, n, h, w, counts, stream)) return rc;
+    // One chain of programmatic dependent launches: only the first kernel waits for the stream in the
+    // ordinary way; each later one is resident (prologue done, first loads in flight where they do not
+    // depend on the chain) by the time the kernel in front of it drains.
+    zero_counts_kernel<<<1, 768, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(counts));
+    SX_LAUNCHED("zero_counts_kernel");
+    if (int rc = hist_impl(images, dtype, layout, n, h, w, counts, stream, true)) return rc;
     // H2 with the reference CDF rebuilt from ref_hist inside the same kernel
-    build_lut_kernel<true><<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const unsigned long long *>(counts), (long long)(n * h * w), ref_hist, lut);
+    SX_CUDA(launch_pdl(build_lut_kernel<true>, dim3(3), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const unsigned long long *>(counts), (long long)(n * h * w), ref_hist, lut));
     SX_LAUNCHED("build_lut_kernel<fused>");
-    return sx_hm_apply(images, dtype, layout, n, h, w, lut, out, stream);
+    return apply_impl(images, dtype, layout, n, h, w, lut, out, stream, true);
 }
 
 int sx_hm_fit(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, float *ref_hist, void *workspace, int64_t workspace_bytes, sx_stream_t stream) {
     SX_REQUIRE(workspace && workspace_bytes >= sx_hm_workspace_bytes(), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_hm_workspace_bytes());
     auto *counts = static_cast<uint64_t *>(workspace);
-    SX_CUDA(cudaMemsetAsync(counts, 0, 768 * 8, static_cast<cudaStream_t>(stream)));
-    if (int rc = sx_hm_hist(images, dtype, layout, n, h, w, counts, stream)) return rc;
+    zero_counts_kernel<<<1, 768, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(counts));
+    SX_LAUNCHED("zero_counts_kernel");
+    if (int rc = hist_impl(images, dtype, layout, n, h, w, counts, stream, true)) return rc;
     return sx_hm_ref_hist(counts, ref_hist, stream);
 }
 

@@ -145,6 +145,66 @@ def test_hm_full_size_properties(cuda):
     assert (cdf(oc) - cdf(rc)).abs().max() <= bin_mass + 1e-9
 
 
+def test_hm_dependent_launch_chain_back_to_back_and_in_a_graph(cuda):
+    """sx_hm_transform is one chain of programmatic dependent launches (zero, histogram, LUT, remap; each
+    kernel resident before the one in front of it has drained).  Back-to-back transforms of different
+    batches whose scratch / output buffers are recycled by the caching allocator must stay bit-exact
+    (no kernel of step k+1 may overtake a reader of step k), on a side stream and inside a CUDA graph."""
+    from stainx_b200 import ops
+
+    g = torch.Generator(device=cuda).manual_seed(11)
+    batches = [(torch.rand((12, 3, 1024, 1024), device=cuda, generator=g).pow(p) * 255).round().to(torch.uint8) for p in (1.0, 2.0, 0.5)]
+    ref = (torch.rand((1, 3, 256, 256), device=cuda, generator=g).pow(1.5) * 255).round().to(torch.uint8)
+    ref_hist = ops.hm_fit(ref)
+    ref_cdf = ops.hm_ref_cdf(ref_hist)
+    want = []
+    for b in batches:  # phase-level calls with a device synchronisation between the phases
+        counts = ops.hm_hist(b)
+        torch.cuda.synchronize()
+        lut = ops.hm_build_lut(counts, b.numel() // 3, ref_cdf)
+        torch.cuda.synchronize()
+        want.append(ops.hm_apply(b, lut))
+        torch.cuda.synchronize()
+        for c in range(3):
+            assert torch.equal(counts[c], torch.bincount(b[:, c].reshape(-1).long(), minlength=256))
+    s = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(s):
+        sums = []
+        for i in range(30):
+            out = ops.hm_transform(batches[i % 3], ref_hist)
+            sums.append((i % 3, out.sum(dtype=torch.int64), (out != want[i % 3]).sum()))
+            del out  # the next transform's output / workspace recycle this memory
+    s.synchronize()
+    for k, total, bad in sums:
+        assert int(bad) == 0 and int(total) == int(want[k].sum(dtype=torch.int64))
+    # small batches take the general kernels behind the same chain
+    small = batches[1][:1, :, :200, :333].contiguous()
+    counts = ops.hm_hist(small)
+    assert torch.equal(ops.hm_transform(small, ref_hist), ops.hm_apply(small, ops.hm_build_lut(counts, small.numel() // 3, ref_cdf)))
+    # graph capture of the chain
+    import ctypes
+
+    src = batches[0]
+    static_out = torch.empty_like(src)
+    ws = torch.empty(int(nv_lib().sx_hm_workspace_bytes()), dtype=torch.uint8, device=cuda)
+
+    def enqueue():
+        rc = nv_lib().sx_hm_transform(ctypes.c_void_p(src.data_ptr()), 0, 0, 12, 1024, 1024, ctypes.c_void_p(ref_hist.data_ptr()), ctypes.c_void_p(static_out.data_ptr()),
+                                      ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(cuda).cuda_stream))
+        assert rc == 0
+
+    enqueue()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enqueue()
+        enqueue()
+    static_out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, want[0])
+
+
 # ======================================================================== Reinhard
 @pytest.mark.parametrize("name", ["reinhard_u8", "reinhard_f32", "reinhard_he_u8"])
 def test_reinhard_golden(cuda, name):

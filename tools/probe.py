@@ -73,7 +73,7 @@ def probe_hm():
         lib.sx_hm_set_tuning(-1, -1, ctas)
         report(f"hm apply u8 planar ctas/sm={ctas}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
     lib.sx_hm_set_tuning(5, 8, 16)
-    report("hm transform u8 (hist+lut+apply)", timeit(lambda: ops.hm_transform(src, ref_hist)), 9 * px)
+    report("hm transform u8 (hist+lut+apply)", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
     report("hm transform u8 NHWC", timeit(lambda: ops.hm_transform(nhwc, ref_hist, nv.SX_NHWC)), 9 * px)
     del nhwc
