@@ -51,6 +51,20 @@ inline unsigned stream_grid(int64_t items, int per_sm) {
     return (unsigned)(g < 1 ? 1 : g);
 }
 
+// ---- L1 / shared-memory split --------------------------------------------------------------------
+// prefer_l1(kernel, threads, dynamic smem): once per kernel and device, ask for the SMALLEST
+// shared-memory carve-out that still holds the kernel's resident CTAs, i.e. the largest L1.  A
+// streaming kernel's loads in flight live in L1 lines (also with L1::no_allocate), so its bandwidth
+// depends on the split: the uint8 LUT remap runs at 66 us with a 16 KB carve-out and at 76 us with
+// >= 132 KB.  Without a preference the driver keeps whatever split the previous kernel left when the
+// new kernel fits it -- behind the 226 KB histogram kernel that cost the remap 6 us per step.
+// SX_L1_PREF=0 in the environment disables the calls (A/B measurements).
+void prefer_l1_impl(const void *kernel, int block_threads, size_t dyn_smem);
+template <typename K>
+inline void prefer_l1(K kernel, int block_threads, size_t dyn_smem = 0) {
+    prefer_l1_impl(reinterpret_cast<const void *>(kernel), block_threads, dyn_smem);
+}
+
 // ---- programmatic dependent launch -------------------------------------------------------------
 // launch_pdl() starts `kernel` with cudaLaunchAttributeProgrammaticStreamSerialization: the grid may
 // become resident as soon as every CTA of the kernel in front of it on the stream has executed

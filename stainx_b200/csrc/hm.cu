@@ -983,6 +983,7 @@ static int g_hist_byte_counters = 5;  // uint8 planar histogram: 5 lane-private 
                                       // 6 ring feed without counting (measurement only: wrong counts)
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 16;
+static int g_chain_prefetch = 1;  // sx_hm_transform: the remap kernel loads its first tile before pdl_wait()
 
 }  // namespace hm
 }  // namespace sx
@@ -1025,6 +1026,11 @@ static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t 
     if (mode == 9) return launch_lane_tma_cfg<LaneCfg<4, 1536, 4, true, true>>(images, hw, n, cnt, stream);   // CTA-wide tiles
     // (Building the LUT in the tail of this kernel -- last CTA, CTA padded to 256 threads -- was measured: the
     // padded kernel is 6 us slower and the serial three-channel build costs more than the saved launch.)
+    // Smaller rings that leave shared memory for early-resident CTAs of the remap kernel behind this one
+    // (programmatic dependent launch) were measured: 640 / 576 / 448 / 384 vectors x 8 stages make the
+    // transform 4-8 us SLOWER -- a remap CTA that becomes resident next to this kernel pins the SM's
+    // 196-228 KB carve-out for the whole remap, whose loads in flight then do not fit the remaining L1.
+    if (mode == 8) return launch_lane_pw_cfg<LaneCfg<4, 512, 8, true, true>>(images, hw, n, cnt, stream, pdl);  // 64 KB ring (196 KB carve-out): 61.8 us
     return launch_lane_pw_cfg<LaneCfg<4, 768, 8, true, true>>(images, hw, n, cnt, stream, pdl);
 }
 
@@ -1034,7 +1040,8 @@ extern "C" {
 int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm) {
     if (hist_byte_counters >= 0) g_hist_byte_counters = hist_byte_counters;
     if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
-    if (apply_ctas_per_sm > 0) g_apply_ctas_per_sm = apply_ctas_per_sm;
+    if (apply_ctas_per_sm > 0 && apply_ctas_per_sm < 1000) g_apply_ctas_per_sm = apply_ctas_per_sm;
+    if (apply_ctas_per_sm == 1000 || apply_ctas_per_sm == 1001) g_chain_prefetch = apply_ctas_per_sm - 1000;
     return SX_OK;
 }
 
@@ -1052,9 +1059,11 @@ static int hist_impl(const void *images, int dtype, int layout, int64_t n, int64
         const int64_t total = n * hw * 3;
         if (dtype == SX_U8) {
             unsigned grid = stream_grid((total / 48 + kThreads - 1) / kThreads + 1, 8);
+            prefer_l1(hist_nhwc_kernel<uint8_t>, kThreads);
             hist_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), total, cnt);
         } else {
             unsigned grid = stream_grid((total / 12 + kThreads - 1) / kThreads + 1, 8);
+            prefer_l1(hist_nhwc_kernel<float>, kThreads);
             hist_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), total, cnt);
         }
         SX_LAUNCHED("hist_nhwc_kernel");
@@ -1071,6 +1080,7 @@ static int hist_impl(const void *images, int dtype, int layout, int64_t n, int64
         } else {
             dim3 grid(stream_grid(items, g_hist_ctas_per_sm), 3);
             grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
+            prefer_l1(hist_u8_planar_kernel, kThreads);
             hist_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), hw, n, tiles, cnt);
         }
         SX_LAUNCHED("hist_u8_planar_kernel");
@@ -1078,6 +1088,7 @@ static int hist_impl(const void *images, int dtype, int layout, int64_t n, int64
         const int64_t tiles = max_i64(1, (hw / 4 + kTileVecs - 1) / kTileVecs);
         dim3 grid(stream_grid(n * tiles, 6), 3);
         grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
+        prefer_l1(hist_f32_planar_kernel, kThreads);
         hist_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), hw, n, tiles, cnt);
         SX_LAUNCHED("hist_f32_planar_kernel");
     }
@@ -1120,9 +1131,11 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
         const int64_t total = n * hw * 3;
         if (dtype == SX_U8) {
             unsigned grid = stream_grid((total / 48 + kThreads - 1) / kThreads + 1, 8);
+            prefer_l1(apply_nhwc_kernel<uint8_t>, kThreads);
             apply_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), total, lut);
         } else {
             unsigned grid = stream_grid((total / 12 + kThreads - 1) / kThreads + 1, 8);
+            prefer_l1(apply_nhwc_kernel<float>, kThreads);
             apply_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), total, lut);
         }
         SX_LAUNCHED("apply_nhwc_kernel");
@@ -1132,16 +1145,19 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
     const int64_t tiles_v = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
     if (dtype == SX_U8 && aligned16(images) && aligned16(out) && hw % 16 == 0 && planes * tiles_v < ((int64_t)1 << 31) && hw / 16 < ((int64_t)1 << 31)) {
         unsigned grid = stream_grid(planes * tiles_v, g_apply_ctas_per_sm);
-        SX_CUDA(launch_pdl(apply_u8_planar_vec_kernel, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain ? 1 : 0));
+        prefer_l1(apply_u8_planar_vec_kernel, kThreads);
+        SX_CUDA(launch_pdl(apply_u8_planar_vec_kernel, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain && g_chain_prefetch ? 1 : 0));
         SX_LAUNCHED("apply_u8_planar_vec_kernel");
     } else if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
         unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
+        prefer_l1(apply_u8_planar_kernel, kThreads);
         apply_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, planes, tiles, lut);
         SX_LAUNCHED("apply_u8_planar_kernel");
     } else {
         const int64_t tiles = max_i64(1, (hw / 4 + kTileVecs - 1) / kTileVecs);
         unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
+        prefer_l1(apply_f32_planar_kernel, kThreads);
         apply_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), hw, planes, tiles, lut);
         SX_LAUNCHED("apply_f32_planar_kernel");
     }

@@ -2,6 +2,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -40,6 +44,34 @@ static DevCache &dev() {
         c.sms = sms > 0 ? sms : 148;
     }
     return c;
+}
+
+void prefer_l1_impl(const void *kernel, int block_threads, size_t dyn_smem) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void *>> seen;
+    static const bool enabled = [] {
+        const char *e = getenv("SX_L1_PREF");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled) return;
+    int d = 0;
+    cudaGetDevice(&d);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &k : seen)
+        if (k.first == d && k.second == kernel) return;
+    seen.emplace_back(d, kernel);
+    cudaFuncAttributes fa;
+    int ctas = 0, max_smem = 0;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, block_threads, dyn_smem) != cudaSuccess ||
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d) != cudaSuccess || max_smem <= 0) {
+        cudaGetLastError();
+        return;
+    }
+    // every resident CTA also holds 1 KB of system shared memory
+    const size_t need = (size_t)(ctas < 1 ? 1 : ctas) * (fa.sharedSizeBytes + dyn_smem + 1024);
+    int pct = (int)((need * 100 + (size_t)max_smem - 1) / (size_t)max_smem);
+    if (pct > 100) pct = 100;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
 }
 
 int sm_count() { return dev().sms; }

@@ -1468,6 +1468,7 @@ static RowGeom make_row_geom(int64_t n, int64_t hw, int64_t slot0, int pooled) {
 template <typename K>
 static unsigned pipeline_grid(K kernel, int64_t total_rows) {
     int per_sm = 0;
+    prefer_l1(kernel, kThreads);  // the pipeline kernels stream: smallest carve-out that holds the resident CTAs
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int64_t resident = (int64_t)per_sm * sm_count();
     return (unsigned)(total_rows < resident ? (total_rows > 0 ? total_rows : 1) : resident);
@@ -1711,6 +1712,8 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
         PassGeom g = make_geom(n, hw, 4);
         const unsigned grid = (unsigned)(n * g.cpi);
         const uint8_t *p = static_cast<const uint8_t *>(images);
+        prefer_l1(apply_u8_f32_kernel<2>, kThreads);
+        prefer_l1(apply_u8_f32_kernel<1>, kThreads);
         if (unit) apply_u8_f32_kernel<2><<<grid, kThreads, 0, stream>>>(p, static_cast<float *>(out), g, slot0, he_ref, maxc_ref, workspace, slots);
         else apply_u8_f32_kernel<1><<<grid, kThreads, 0, stream>>>(p, static_cast<float *>(out), g, slot0, he_ref, maxc_ref, workspace, slots);
         SX_LAUNCHED("macenko::apply_u8_f32_kernel");
@@ -1720,6 +1723,9 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
         PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix);
         const unsigned grid = (unsigned)(n * g.cpi);
         const T *p = static_cast<const T *>(images);
+        prefer_l1(apply_kernel<T, VEC, 0>, kThreads);
+        prefer_l1(apply_kernel<T, VEC, 1>, kThreads);
+        prefer_l1(apply_kernel<T, VEC, 2>, kThreads);
         if (out_dtype == SX_U8) apply_kernel<T, VEC, 0><<<grid, kThreads, 0, stream>>>(p, out, g, slot0, he_ref, maxc_ref, workspace, slots);
         else if (!unit) apply_kernel<T, VEC, 1><<<grid, kThreads, 0, stream>>>(p, out, g, slot0, he_ref, maxc_ref, workspace, slots);
         else apply_kernel<T, VEC, 2><<<grid, kThreads, 0, stream>>>(p, out, g, slot0, he_ref, maxc_ref, workspace, slots);

@@ -401,6 +401,7 @@ static int launch_stats(const T *p, int64_t n, int64_t hw, double *sums, cudaStr
     const size_t smem = TAB ? kTableBytes : 0;
     if (TAB) SX_CUDA(cudaFuncSetAttribute(stats_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
+    prefer_l1(stats_kernel<T, VEC, TAB>, kThreads, smem);
     stats_kernel<T, VEC, TAB><<<grid, kThreads, smem, stream>>>(p, n, hw, sums);
     return SX_OK;
 }
@@ -410,6 +411,7 @@ static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *sr
     const size_t smem = TAB ? kTableBytes : 0;
     if (TAB) SX_CUDA(cudaFuncSetAttribute(apply_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
+    prefer_l1(apply_kernel<T, VEC, TAB>, kThreads, smem);
     apply_kernel<T, VEC, TAB><<<grid, kThreads, smem, stream>>>(p, o, n, hw, src_mean, src_std, ref_mean, ref_std);
     return SX_OK;
 }

@@ -73,7 +73,13 @@ def probe_hm():
         lib.sx_hm_set_tuning(-1, -1, ctas)
         report(f"hm apply u8 planar ctas/sm={ctas}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
     lib.sx_hm_set_tuning(5, 8, 16)
-    report("hm transform u8 (hist+lut+apply)", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
+    for mode in (5, 8):
+        lib.sx_hm_set_tuning(mode, 8, 16)
+        for pre in (1, 0):
+            lib.sx_hm_set_tuning(-1, -1, 1000 + pre)
+            report(f"hm transform u8 (hist+lut+apply) hist mode={mode} prefetch={pre}", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
+    lib.sx_hm_set_tuning(5, 8, 16)
+    lib.sx_hm_set_tuning(-1, -1, 1001)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
     report("hm transform u8 NHWC", timeit(lambda: ops.hm_transform(nhwc, ref_hist, nv.SX_NHWC)), 9 * px)
     del nhwc
