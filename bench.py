@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--method hm|reinhard|macenko]
 
 Headline workload (N GPUs, weak scaling, 64 images per GPU): BASELINE.json configs[1] --
-HistogramMatching, uint8, 64x3x1024x1024 per GPU, reference mode.  One step = one transform of the
-batch: per-channel histogram of the (sharded) batch, [N>1: NCCL all-reduce of the 3x256 counts],
-LUT build, LUT remap.  The batch (201 MB per GPU) is larger than the 126 MB L2, so every step
+HistogramMatching, uint8, 64x3x1024x1024 per GPU, reference mode.  One step = one
+`HistogramMatching.transform(batch)`: per-channel histogram of the (sharded) batch, [N>1: all-reduce of the
+3x256 counts inside the LUT kernel over NVLink peer memory], LUT build, LUT remap.  The batch (201 MB per GPU) is larger than the 126 MB L2, so every step
 streams it from HBM; no L2 flush is needed between steps.
 
 Rank 0 prints ONE JSON line (see the keys in `main`).  `--impl reference` times the CPU oracle
@@ -27,7 +27,8 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 IMAGES_PER_GPU = 64
-EVENT_EVERY = 8  # the four cudaEventRecord calls of an instrumented step cost ~6 us of stream time
+EVENT_EVERY = 32  # an instrumented step costs ~15 us more: four cudaEventRecord calls, and the phase-level calls
+                  # cannot chain the kernels as programmatic dependent launches the way the single library call does
 H = W = 1024
 ALGO_BYTES_PER_PX = {"hm": 9.0, "reinhard": 36.0, "macenko": 24.0}
 

@@ -8,12 +8,22 @@
 // Reference semantics: src/stainx/backends/torch_backend.py:L16-101 (colour), L308-355 (Reinhard);
 // kernels replaced: csrc/reinhard.cu:L45-139 and the ATen glue (NHWC copy, mean/std, host sync) in
 // src/stainx_cuda_torch/csrc/reinhard.cu:L25-121.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sx {
 namespace reinhard {
 
 constexpr int kThreads = 256;
+#ifndef SX_RH_PREFETCH  // A/B builds: 1 = the next group's loads are issued before the current group is processed
+#define SX_RH_PREFETCH 1
+#endif
+#ifdef SX_RH_STATS_MINB  // A/B builds: resident CTAs per SM the statistics kernel is compiled for
+#define SX_RH_STATS_BOUNDS __launch_bounds__(kThreads, SX_RH_STATS_MINB)
+#else
+#define SX_RH_STATS_BOUNDS __launch_bounds__(kThreads)
+#endif
 
 // sRGB -> linear (torch_backend.py:L28-29).  pow(t, 2.4) = 2^(2.4 log2 t) on the SFU.
 __device__ __forceinline__ float srgb_to_linear(float x) {
@@ -31,10 +41,6 @@ __device__ __forceinline__ float linear_to_srgb(float v) {
 __device__ __forceinline__ float lab_f(float t) {
     float c = fast_ex2((1.0f / 3.0f) * fast_lg2(t));
     return t > 0.008856f ? c : __fmaf_rn(7.787f, t, 16.0f / 116.0f);
-}
-// inverse (L78-80).
-__device__ __forceinline__ float lab_finv(float t) {
-    return t > 0.2068966f ? t * t * t : (t - 16.0f / 116.0f) * (1.0f / 7.787f);
 }
 
 // ---- interpolated transfer-curve tables ---------------------------------------------------------
@@ -54,56 +60,88 @@ __device__ __forceinline__ float srgb_to_linear_exact(float x) {
 __device__ __forceinline__ float linear_to_srgb_exact(float v) {
     return v > 0.0031308f ? 1.055f * powf(v, 1.0f / 2.4f) - 0.055f : 12.92f * v;
 }
-// table[i] = (f(i / n), f((i + 1) / n) - f(i / n)), i = 0 .. n (the last slope is 0)
+// table[i] = (c_i, m_i), i = 0 .. n: the chord of f over [i / n, (i + 1) / n] as a function of x itself,
+// f(x) ~ c_i + m_i x  (m_i = n (f((i+1)/n) - f(i/n)), c_i = f(i/n) - m_i i/n; composed in double; the
+// last slope is 0).  A lookup is then FFMA.RZ (byte offset), LOP, LDS.64, FFMA -- no fraction to extract.
 template <typename F>
 __device__ __forceinline__ void build_curve(float2 *table, int n, F f) {
     for (int i = threadIdx.x; i <= n; i += blockDim.x) {
-        const float a = f((float)i / (float)n);
-        const float b = i < n ? f((float)(i + 1) / (float)n) : a;
-        table[i] = make_float2(a, b - a);
+        const double a = (double)f((float)i / (float)n);
+        const double b = i < n ? (double)f((float)(i + 1) / (float)n) : a;
+        const double m = (b - a) * (double)n;
+        table[i] = make_float2((float)(a - m * ((double)i / (double)n)), (float)m);
     }
 }
 // x in [0, 1]
 template <int N>
 __device__ __forceinline__ float curve(const float2 *table, float x) {
-    const float y = __fmaf_rz(x, (float)N, 8388608.0f);       // 2^23 + floor(x N)
-    const float frac = __fmaf_rn(x, (float)N, 8388608.0f - y);  // x N - floor(x N), exact difference
-    const float2 e = table[__float_as_uint(y) & 0x1fffu];
-    return __fmaf_rn(frac, e.y, e.x);
+    // 2^20 + floor(8 x N) / 8: the mantissa holds floor(x N) from bit 3 up, i.e. the BYTE offset of entry
+    // floor(x N) after one mask (no shift)
+    const float y = __fmaf_rz(x, (float)N, 1048576.0f);
+    const float2 e = *reinterpret_cast<const float2 *>(reinterpret_cast<const unsigned char *>(table) + (__float_as_uint(y) & 0xfff8u));
+    return __fmaf_rn(e.y, x, e.x);
 }
 
-// linear RGB -> (L, a, b) in the reference's 0..255 scaling (L32-53); the white point is folded
-// into the matrix rows.
-template <bool SHIFTED = false>
-__device__ __forceinline__ void linear_to_lab(float r, float g, float b, float &L, float &A, float &B) {
+// ---- pass 2 in f-space ------------------------------------------------------------------------------
+// LAB is affine in (fx, fy, fz) (L45-47: L = 295.8 fy - 40.8, a = 500 (fx - fy) + 128, b = 200 (fy - fz) + 128),
+// the Reinhard map is affine per LAB channel (L349) and LAB -> (fx, fy, fz) is affine again (L70-73),
+// so pass 2 never forms LAB: with a_c = sigma_r / (sigma_s + 1e-8), b_c = mu_r - a_c mu_s,
+//     fy' = a0 fy + cy,   fx' = a1 fx + (a0 - a1) fy + (cy + cx),   fz' = a2 fz + (a0 - a2) fy + (cy - cz)
+//     cy = (b0 - 40.8 a0) / 295.8 + 16/116,  cx = (128 a1 + b1 - 128) / 500,  cz = (128 a2 + b2 - 128) / 200
+// (five FMAs per pixel instead of twelve operations, and without the cancellation of 500 (fx - fy)).
+struct FMap {
+    float ay, cy;       // fy' = ay fy + cy
+    float ax, bx, cx;   // fx' = ax fx + bx fy + cx
+    float az, bz, cz;   // fz' = az fz + bz fy + cz
+};
+__device__ __forceinline__ FMap make_fmap(const float *src_mean, const float *src_std, const float *ref_mean, const float *ref_std) {
+    double a[3], b[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // the reference's float32 coefficients (L349), then exact composition in double
+        const float af = __fdiv_rn(__ldcg(ref_std + c), __fadd_rn(__ldcg(src_std + c), 1e-8f));
+        a[c] = (double)af;
+        b[c] = (double)__ldcg(ref_mean + c) - (double)__ldcg(src_mean + c) * a[c];
+    }
+    const double kL = 116.0 * 2.55, k0 = 16.0 * 2.55;
+    const double cy = (b[0] - k0 * a[0]) / kL + 16.0 / 116.0;
+    const double cx = (128.0 * a[1] + b[1] - 128.0) / 500.0;
+    const double cz = (128.0 * a[2] + b[2] - 128.0) / 200.0;
+    FMap m;
+    m.ay = (float)a[0]; m.cy = (float)cy;
+    m.ax = (float)a[1]; m.bx = (float)(a[0] - a[1]); m.cx = (float)(cy + cx);
+    m.az = (float)a[2]; m.bz = (float)(a[0] - a[2]); m.cz = (float)(cy - cz);
+    return m;
+}
+
+__device__ __forceinline__ float cbrt_sfu(float t) { return fast_ex2((1.0f / 3.0f) * fast_lg2(t)); }
+
+// linear RGB -> white-normalised XYZ, in place (r -> x, g -> y, b -> z).
+__device__ __forceinline__ void linear_to_xyz(float &r, float &g, float &b) {
     constexpr float wx = 1.0f / 0.95047f, wz = 1.0f / 1.08883f;
-    float x = 0.412453f * wx * r + 0.357580f * wx * g + 0.180423f * wx * b;
-    float y = 0.212671f * r + 0.715160f * g + 0.072169f * b;
-    float z = 0.019334f * wz * r + 0.119193f * wz * g + 0.950227f * wz * b;
-    float fx = lab_f(x), fy = lab_f(y), fz = lab_f(z);
-    constexpr float off = SHIFTED ? 128.0f : 0.0f;  // pass 1 accumulates lab - 128
-    L = __fmaf_rn(116.0f * 2.55f, fy, -16.0f * 2.55f - off);
-    A = __fmaf_rn(500.0f, fx - fy, 128.0f - off);
-    B = __fmaf_rn(200.0f, fy - fz, 128.0f - off);
+    const float x = 0.412453f * wx * r + 0.357580f * wx * g + 0.180423f * wx * b;
+    const float y = 0.212671f * r + 0.715160f * g + 0.072169f * b;
+    const float z = 0.019334f * wz * r + 0.119193f * wz * g + 0.950227f * wz * b;
+    r = x; g = y; b = z;
 }
-
-// (L, a, b) -> linear RGB (L70-90); the white point is folded into the matrix columns.
-__device__ __forceinline__ void lab_to_linear(float L, float A, float B, float &lr, float &lg, float &lb) {
-    float fy = __fmaf_rn(L, 1.0f / (2.55f * 116.0f), 16.0f / 116.0f);
-    float fx = __fmaf_rn(A - 128.0f, 1.0f / 500.0f, fy);
-    float fz = __fmaf_rn(B - 128.0f, -1.0f / 200.0f, fy);
-    float x = lab_finv(fx) * 0.95047f, y = lab_finv(fy), z = lab_finv(fz) * 1.08883f;
-    lr = 3.2404542f * x - 1.5371385f * y - 0.4985314f * z;
-    lg = -0.9692660f * x + 1.8760108f * y + 0.0415560f * z;
-    lb = 0.0556434f * x - 0.2040259f * y + 1.0572252f * z;
+// f(t) over a pixel chunk, in place.  Branch-free on purpose: deciding the knee of L41-42 once per
+// chunk ("every argument is above it: cube roots only") was built and measured -- on noise 2 % of the
+// pixels are below the knee, which is 8 % of the 4-pixel chunks and 93 % of the warps, so nearly every
+// warp ran both paths (float32 statistics pass 219 -> 290 us).
+template <int K>
+__device__ __forceinline__ void lab_f_group(float (&x)[K], float (&y)[K], float (&z)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { x[k] = lab_f(x[k]); y[k] = lab_f(y[k]); z[k] = lab_f(z[k]); }
 }
-// (L, a, b) -> sRGB in [0,1] (L70-96).
-__device__ __forceinline__ void lab_to_srgb(float L, float A, float B, float &r, float &g, float &b) {
-    float lr, lg, lb;
-    lab_to_linear(L, A, B, lr, lg, lb);
-    r = linear_to_srgb(lr);
-    g = linear_to_srgb(lg);
-    b = linear_to_srgb(lb);
+// (fx, fy, fz) -> linear RGB (L78-90), white point folded into the matrix columns.
+__device__ __forceinline__ void xyz_to_linear(float x, float y, float z, float &lr, float &lg, float &lb) {
+    constexpr float wx = 0.95047f, wz = 1.08883f;
+    lr = 3.2404542f * wx * x - 1.5371385f * y - 0.4985314f * wz * z;
+    lg = -0.9692660f * wx * x + 1.8760108f * y + 0.0415560f * wz * z;
+    lb = 0.0556434f * wx * x - 0.2040259f * y + 1.0572252f * wz * z;
+}
+__device__ __forceinline__ float lab_finv_general(float t) {
+    return t > 0.2068966f ? t * t * t : __fmaf_rn(t, 1.0f / 7.787f, -(16.0f / 116.0f) / 7.787f);
 }
 
 // uint8 input: sRGB -> linear is a 256-entry table (built once per CTA with the accurate powf).
@@ -113,10 +151,6 @@ __device__ __forceinline__ void build_linear_lut(float *lut) {
         lut[i] = x > 0.04045f ? powf((x + 0.055f) / 1.055f, 2.4f) : x / 12.92f;
     }
 }
-
-struct Affine {
-    float a[3], b[3];
-};
 
 // Pixel groups: a thread owns kPix consecutive pixels of one image, loaded as one 128-bit vector
 // per colour plane (float32: 4 px, uint8: 16 px).  Images whose planes are not 16-byte aligned
@@ -139,6 +173,24 @@ struct Acc {
     double n;
 };
 
+// (image, group within the image) of the grid-stride walk over all pixel groups of the batch, advanced
+// incrementally: one 64-bit division per thread instead of one per group (the division was ~25 of the
+// ~490 instructions a float32 group cost in pass 2, plus an I2F and a MUFU.RCP on the SFU).
+struct GroupCursor {
+    int64_t n, q, dn, dq, per_img;
+    __device__ __forceinline__ GroupCursor(int64_t g, int64_t stride, int64_t groups_per_img) : per_img(groups_per_img) {
+        n = g / per_img;
+        q = g - n * per_img;
+        dn = stride / per_img;
+        dq = stride - dn * per_img;
+    }
+    __device__ __forceinline__ void next() {
+        q += dq;
+        n += dn;
+        if (q >= per_img) { q -= per_img; ++n; }
+    }
+};
+
 __device__ __forceinline__ void block_reduce_and_add(double *v, int count, double *global) {
     __shared__ double red[kThreads / 32][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,55 +206,64 @@ __device__ __forceinline__ void block_reduce_and_add(double *v, int count, doubl
     }
 }
 
-// One pixel group as linear RGB: r/g/b[k] of pixel k.  uint8 goes through the 256-entry table,
-// float32 through the interpolated curve (TAB) or the SFU.  A float32 group with a value outside
-// [0, 1] (the reference does not clamp its input) takes the exact formula.
+// The raw loads of one pixel group (one 128-bit vector per colour plane, or one scalar), converted to
+// linear RGB a CHUNK of kChunk pixels at a time so that a uint8 group (16 pixels) never holds more
+// than 12 pixel values in registers.  uint8 goes through the 256-entry table, float32 through the
+// interpolated curve (TAB) or the SFU.  A float32 group with a value outside [0, 1] (the reference
+// does not clamp its input) takes the exact formula.
 template <typename T, bool VEC, bool TAB>
-__device__ __forceinline__ void load_linear(const T *__restrict__ base, int64_t hw, const float *lin_lut, const float2 *fwd, float (&r)[VEC ? Px<T>::kPix : 1], float (&g)[VEC ? Px<T>::kPix : 1], float (&b)[VEC ? Px<T>::kPix : 1]) {
-    constexpr int kPix = VEC ? Px<T>::kPix : 1;
-    if constexpr (sizeof(T) == 1) {
-        if constexpr (VEC) {
-            const uint4 vr = ld_stream(reinterpret_cast<const uint4 *>(base));
-            const uint4 vg = ld_stream(reinterpret_cast<const uint4 *>(base + hw));
-            const uint4 vb = ld_stream(reinterpret_cast<const uint4 *>(base + 2 * hw));
-            const unsigned wr[4] = {vr.x, vr.y, vr.z, vr.w}, wg[4] = {vg.x, vg.y, vg.z, vg.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+struct RawPx {
+    static constexpr int kPix = VEC ? Px<T>::kPix : 1;
+    static constexpr int kChunk = VEC ? 4 : 1;
+    static constexpr int kChunks = kPix / kChunk;
+    using Vec = typename std::conditional<VEC, typename Px<T>::Vec, T>::type;
+    Vec v[3];
+    __device__ __forceinline__ void load(const T *__restrict__ base, int64_t hw) {
 #pragma unroll
-            for (int k = 0; k < kPix; ++k) {
-                r[k] = lin_lut[(wr[k >> 2] >> (8 * (k & 3))) & 0xffu];
-                g[k] = lin_lut[(wg[k >> 2] >> (8 * (k & 3))) & 0xffu];
-                b[k] = lin_lut[(wb[k >> 2] >> (8 * (k & 3))) & 0xffu];
-            }
-        } else {
-            r[0] = lin_lut[base[0]]; g[0] = lin_lut[base[hw]]; b[0] = lin_lut[base[2 * hw]];
-        }
-    } else {
-        if constexpr (VEC) {
-            const float4 vr = ld_stream(reinterpret_cast<const float4 *>(base));
-            const float4 vg = ld_stream(reinterpret_cast<const float4 *>(base + hw));
-            const float4 vb = ld_stream(reinterpret_cast<const float4 *>(base + 2 * hw));
-            r[0] = vr.x; r[1] = vr.y; r[2] = vr.z; r[3] = vr.w;
-            g[0] = vg.x; g[1] = vg.y; g[2] = vg.z; g[3] = vg.w;
-            b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-        } else {
-            r[0] = base[0]; g[0] = base[hw]; b[0] = base[2 * hw];
-        }
-        bool in_range = TAB;
-        if constexpr (TAB) {
-            // as unsigned integers, floats in [0, 1] are <= 0x3f800000; negatives and NaN are larger
-            unsigned top = 0u;
-#pragma unroll
-            for (int k = 0; k < kPix; ++k) top = max(top, max(__float_as_uint(r[k]), max(__float_as_uint(g[k]), __float_as_uint(b[k]))));
-            in_range = top <= 0x3f800000u;
-        }
-        if (in_range) {
-#pragma unroll
-            for (int k = 0; k < kPix; ++k) { r[k] = curve<kFwdN>(fwd, r[k]); g[k] = curve<kFwdN>(fwd, g[k]); b[k] = curve<kFwdN>(fwd, b[k]); }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kPix; ++k) { r[k] = srgb_to_linear(r[k]); g[k] = srgb_to_linear(g[k]); b[k] = srgb_to_linear(b[k]); }
+        for (int c = 0; c < 3; ++c) {
+            if constexpr (VEC) v[c] = ld_stream(reinterpret_cast<const Vec *>(base + c * hw));
+            else v[c] = base[c * hw];
         }
     }
-}
+    __device__ __forceinline__ void linear(int chunk, const float *lin_lut, const float2 *fwd, float (&r)[kChunk], float (&g)[kChunk], float (&b)[kChunk]) const {
+        if constexpr (sizeof(T) == 1) {
+            if constexpr (VEC) {
+                const unsigned wr[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, wg[4] = {v[1].x, v[1].y, v[1].z, v[1].w}, wb[4] = {v[2].x, v[2].y, v[2].z, v[2].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    r[k] = lin_lut[(wr[chunk] >> (8 * k)) & 0xffu];
+                    g[k] = lin_lut[(wg[chunk] >> (8 * k)) & 0xffu];
+                    b[k] = lin_lut[(wb[chunk] >> (8 * k)) & 0xffu];
+                }
+            } else {
+                r[0] = lin_lut[v[0]]; g[0] = lin_lut[v[1]]; b[0] = lin_lut[v[2]];
+            }
+        } else {
+            if constexpr (VEC) {
+                r[0] = v[0].x; r[1] = v[0].y; r[2] = v[0].z; r[3] = v[0].w;
+                g[0] = v[1].x; g[1] = v[1].y; g[2] = v[1].z; g[3] = v[1].w;
+                b[0] = v[2].x; b[1] = v[2].y; b[2] = v[2].z; b[3] = v[2].w;
+            } else {
+                r[0] = v[0]; g[0] = v[1]; b[0] = v[2];
+            }
+            bool in_range = TAB;
+            if constexpr (TAB) {
+                // as unsigned integers, floats in [0, 1] are <= 0x3f800000; negatives and NaN are larger
+                unsigned top = 0u;
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k) top = max(top, max(__float_as_uint(r[k]), max(__float_as_uint(g[k]), __float_as_uint(b[k]))));
+                in_range = top <= 0x3f800000u;
+            }
+            if (in_range) {
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k) { r[k] = curve<kFwdN>(fwd, r[k]); g[k] = curve<kFwdN>(fwd, g[k]); b[k] = curve<kFwdN>(fwd, b[k]); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k) { r[k] = srgb_to_linear(r[k]); g[k] = srgb_to_linear(g[k]); b[k] = srgb_to_linear(b[k]); }
+            }
+        }
+    }
+};
 
 // Shared memory of both passes: [fwd curve | inv curve] (TAB only), then the uint8 table.
 template <typename T, bool TAB>
@@ -223,44 +284,63 @@ __device__ __forceinline__ void setup_tables(unsigned char *smem, const float2 *
 
 // ---- pass 1: statistics ---------------------------------------------------------------------
 template <typename T, bool VEC, bool TAB>
-__global__ void __launch_bounds__(kThreads) stats_kernel(const T *__restrict__ img, int64_t n_img, int64_t hw, double *__restrict__ sums) {
+__global__ void SX_RH_STATS_BOUNDS stats_kernel(const T *__restrict__ img, int64_t n_img, int64_t hw, double *__restrict__ sums) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float lin_lut[256];
     const float2 *fwd, *inv;
+    pdl_trigger();  // the finalize kernel behind this one may become resident (it waits for our completion)
     setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, false);
     const int64_t groups_per_img = hw / kPix;  // VEC: hw % kPix == 0
     const int64_t groups = n_img * groups_per_img;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
-        const int64_t n = g / groups_per_img;
-        const int64_t p0 = (g - n * groups_per_img) * kPix;
-        float r[kPix], gr[kPix], b[kPix];
-        load_linear<T, VEC, TAB>(img + n * 3 * hw + p0, hw, lin_lut, fwd, r, gr, b);
+    unsigned ngroups = 0u;  // groups this thread has summed (< 2^32: a thread sees groups / (grid x 256) of them)
+    const int64_t g0 = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
+    GroupCursor cur(g0, stride, groups_per_img);
+    using Raw = RawPx<T, VEC, TAB>;
+    Raw raw, ahead;  // the loads of the next group are in flight while this one is processed
+    if (SX_RH_PREFETCH && g0 < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+    for (int64_t g = g0; g < groups; g += stride) {
+        if (SX_RH_PREFETCH) raw = ahead;
+        else raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        cur.next();
+        if (SX_RH_PREFETCH && g + stride < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
         // float32 partial sums over this thread's <= 16 pixels, shifted by 128 to keep the
         // second moments small; folded into double accumulators once per group.
         float s[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < kPix; ++k) {
-            float L, A, B;
-            linear_to_lab<true>(r[k], gr[k], b[k], L, A, B);  // shifted by -128
-            s[0] += L; s[1] += A; s[2] += B;
-            s[3] = __fmaf_rn(L, L, s[3]); s[4] = __fmaf_rn(A, A, s[4]); s[5] = __fmaf_rn(B, B, s[5]);
+        for (int ch = 0; ch < Raw::kChunks; ++ch) {
+            float r[Raw::kChunk], gr[Raw::kChunk], b[Raw::kChunk];
+            raw.linear(ch, lin_lut, fwd, r, gr, b);
+#pragma unroll
+            for (int k = 0; k < Raw::kChunk; ++k) linear_to_xyz(r[k], gr[k], b[k]);
+            lab_f_group<Raw::kChunk>(r, gr, b);  // (fx, fy, fz)
+#pragma unroll
+            for (int k = 0; k < Raw::kChunk; ++k) {
+                const float L = __fmaf_rn(116.0f * 2.55f, gr[k], -16.0f * 2.55f - 128.0f);  // L45-47, shifted by -128
+                const float A = 500.0f * (r[k] - gr[k]);
+                const float B = 200.0f * (gr[k] - b[k]);
+                s[0] += L; s[1] += A; s[2] += B;
+                s[3] = __fmaf_rn(L, L, s[3]); s[4] = __fmaf_rn(A, A, s[4]); s[5] = __fmaf_rn(B, B, s[5]);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) acc[i] += (double)s[i];
-        acc[6] += (double)kPix;
+        ++ngroups;
     }
+    acc[6] = (double)ngroups * (double)kPix;
     block_reduce_and_add(acc, 7, sums);
 }
 
 // mean / unbiased std from the shifted sums (torch_backend.py:L320-321).
 __global__ void finalize_kernel(const double *__restrict__ sums, float *__restrict__ mean, float *__restrict__ std) {
     const int c = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();  // launched with launch_pdl() behind the statistics kernel
     if (c < 3) {
-        const double n = sums[6];
-        const double m = sums[c] / n;
-        const double var = (sums[3 + c] - sums[c] * m) / (n - 1.0);
+        const double n = __ldcg(sums + 6), sc = __ldcg(sums + c), sq = __ldcg(sums + 3 + c);
+        const double m = sc / n;
+        const double var = (sq - sc * m) / (n - 1.0);
         mean[c] = (float)(m + 128.0);
         std[c] = (float)sqrt(var > 0.0 ? var : 0.0);
     }
@@ -278,6 +358,8 @@ __global__ void finalize_peers_kernel(unsigned char *const *__restrict__ bufs, i
     __shared__ double tot[8];
     const int t = threadIdx.x;
     const int parity = (int)(epoch & 1u);
+    pdl_trigger();
+    pdl_wait();  // launched with launch_pdl() behind the statistics kernel
     if (t < world) {
         __threadfence_system();
         unsigned *flag = reinterpret_cast<unsigned *>(bufs[t] + kPeerSumsBytes) + rank;
@@ -309,76 +391,99 @@ __global__ void finalize_peers_kernel(unsigned char *const *__restrict__ bufs, i
     }
 }
 
+// Four values in [0, 1] -> four grey levels in one word, exactly trunc(x * 255) of torch_backend.py:L122-131
+// (the product rounded to nearest as there, then truncated) without F2I, which runs on the SFU like
+// the cube roots: adding 2^23 with round-towards-zero leaves floor(p) in the low mantissa byte, and
+// three PRMTs gather the four bytes.  The inputs are already clamped (transfer curve / L96).
+__device__ __forceinline__ unsigned pack_u8x4(const float (&x)[4]) {
+    unsigned q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = __float_as_uint(__fadd_rz(__fmul_rn(x[k], 255.0f), 8388608.0f));
+    return __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+}
+
 // ---- pass 2: transform ----------------------------------------------------------------------
 template <typename T, bool VEC, bool TAB>
-__global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t n_img, int64_t hw, const float *__restrict__ src_mean, const float *__restrict__ src_std, const float *__restrict__ ref_mean, const float *__restrict__ ref_std) {
+__global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t n_img, int64_t hw, const float *__restrict__ src_mean, const float *__restrict__ src_std, const float *__restrict__ ref_mean, const float *__restrict__ ref_std) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float lin_lut[256];
     const float2 *fwd, *inv;
     setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, true);
-    // L349: ((lab - mu_s) / (sigma_s + 1e-8)) * sigma_r + mu_r  ==  a * lab + b
-    Affine af;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        af.a[c] = __fdiv_rn(ref_std[c], __fadd_rn(src_std[c], 1e-8f));
-        af.b[c] = __fmaf_rn(-src_mean[c], af.a[c], ref_mean[c]);
-    }
+    // L349: ((lab - mu_s) / (sigma_s + 1e-8)) * sigma_r + mu_r, composed with LAB <-> (fx, fy, fz)
+    const FMap fm = make_fmap(src_mean, src_std, ref_mean, ref_std);
     const int64_t groups_per_img = hw / kPix;
     const int64_t groups = n_img * groups_per_img;
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
-        const int64_t n = g / groups_per_img;
-        const int64_t p0 = (g - n * groups_per_img) * kPix;
-        T *obase = out + n * 3 * hw + p0;
-        float r[kPix], gr[kPix], b[kPix];
-        load_linear<T, VEC, TAB>(img + n * 3 * hw + p0, hw, lin_lut, fwd, r, gr, b);
+    const int64_t g0 = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
+    GroupCursor cur(g0, stride, groups_per_img);
+    using Raw = RawPx<T, VEC, TAB>;
+    Raw raw, ahead;  // the loads of the next group are in flight while this one is processed
+    if (SX_RH_PREFETCH && g0 < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+    for (int64_t g = g0; g < groups; g += stride) {
+        T *obase = out + cur.n * 3 * hw + cur.q * kPix;
+        if (SX_RH_PREFETCH) raw = ahead;
+        else raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        cur.next();
+        if (SX_RH_PREFETCH && g + stride < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        unsigned wr[4] = {0, 0, 0, 0}, wg[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};  // uint8 output words
 #pragma unroll
-        for (int k = 0; k < kPix; ++k) {
-            float L, A, B;
-            linear_to_lab(r[k], gr[k], b[k], L, A, B);
-            L = __fmaf_rn(af.a[0], L, af.b[0]);
-            A = __fmaf_rn(af.a[1], A, af.b[1]);
-            B = __fmaf_rn(af.a[2], B, af.b[2]);
-            if constexpr (TAB) {
-                // the clamp of the output (L96) commutes with the monotone transfer curve
+        for (int ch = 0; ch < Raw::kChunks; ++ch) {
+            constexpr int K = Raw::kChunk;
+            float r[K], gr[K], b[K];
+            raw.linear(ch, lin_lut, fwd, r, gr, b);
+#pragma unroll
+            for (int k = 0; k < K; ++k) linear_to_xyz(r[k], gr[k], b[k]);
+            lab_f_group<K>(r, gr, b);  // (fx, fy, fz)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {  // the Reinhard map in f-space, then f^-1 (L78-80)
+                const float fy = gr[k];
+                r[k] = lab_finv_general(__fmaf_rn(fm.ax, r[k], __fmaf_rn(fm.bx, fy, fm.cx)));
+                b[k] = lab_finv_general(__fmaf_rn(fm.az, b[k], __fmaf_rn(fm.bz, fy, fm.cz)));
+                gr[k] = lab_finv_general(__fmaf_rn(fm.ay, fy, fm.cy));
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
                 float lr, lg, lb;
-                lab_to_linear(L, A, B, lr, lg, lb);
-                r[k] = curve<kInvN>(inv, __saturatef(lr));
-                gr[k] = curve<kInvN>(inv, __saturatef(lg));
-                b[k] = curve<kInvN>(inv, __saturatef(lb));
+                xyz_to_linear(r[k], gr[k], b[k], lr, lg, lb);
+                if constexpr (TAB) {
+                    // the clamp of the output (L96) commutes with the monotone transfer curve
+                    r[k] = curve<kInvN>(inv, __saturatef(lr));
+                    gr[k] = curve<kInvN>(inv, __saturatef(lg));
+                    b[k] = curve<kInvN>(inv, __saturatef(lb));
+                } else {
+                    r[k] = linear_to_srgb(lr);
+                    gr[k] = linear_to_srgb(lg);
+                    b[k] = linear_to_srgb(lb);
+                }
+            }
+            if constexpr (sizeof(T) == 4) {
+                if constexpr (VEC) {
+                    st_stream(reinterpret_cast<float4 *>(obase), make_float4(r[0], r[1], r[2], r[3]));
+                    st_stream(reinterpret_cast<float4 *>(obase + hw), make_float4(gr[0], gr[1], gr[2], gr[3]));
+                    st_stream(reinterpret_cast<float4 *>(obase + 2 * hw), make_float4(b[0], b[1], b[2], b[3]));
+                } else {
+                    obase[0] = r[0]; obase[hw] = gr[0]; obase[2 * hw] = b[0];
+                }
             } else {
-                lab_to_srgb(L, A, B, r[k], gr[k], b[k]);
+                // uint8 out: trunc(clamp(rgb * 255, 0, 255))  (torch_backend.py:L122-131)
+                if constexpr (VEC) {
+                    wr[ch] = pack_u8x4(r);
+                    wg[ch] = pack_u8x4(gr);
+                    wb[ch] = pack_u8x4(b);
+                } else {
+                    obase[0] = (uint8_t)quantize_u8(r[0]); obase[hw] = (uint8_t)quantize_u8(gr[0]); obase[2 * hw] = (uint8_t)quantize_u8(b[0]);
+                }
             }
         }
-        if constexpr (sizeof(T) == 4) {
-            if constexpr (VEC) {
-                st_stream(reinterpret_cast<float4 *>(obase), make_float4(r[0], r[1], r[2], r[3]));
-                st_stream(reinterpret_cast<float4 *>(obase + hw), make_float4(gr[0], gr[1], gr[2], gr[3]));
-                st_stream(reinterpret_cast<float4 *>(obase + 2 * hw), make_float4(b[0], b[1], b[2], b[3]));
-            } else {
-                obase[0] = r[0]; obase[hw] = gr[0]; obase[2 * hw] = b[0];
-            }
-        } else {
-            // uint8 out: trunc(clamp(rgb * 255, 0, 255))  (torch_backend.py:L122-131)
-            if constexpr (VEC) {
-                unsigned wr[4] = {0, 0, 0, 0}, wg[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int k = 0; k < kPix; ++k) {
-                    wr[k >> 2] |= quantize_u8(r[k]) << (8 * (k & 3));
-                    wg[k >> 2] |= quantize_u8(gr[k]) << (8 * (k & 3));
-                    wb[k >> 2] |= quantize_u8(b[k]) << (8 * (k & 3));
-                }
-                st_stream(reinterpret_cast<uint4 *>(obase), make_uint4(wr[0], wr[1], wr[2], wr[3]));
-                st_stream(reinterpret_cast<uint4 *>(obase + hw), make_uint4(wg[0], wg[1], wg[2], wg[3]));
-                st_stream(reinterpret_cast<uint4 *>(obase + 2 * hw), make_uint4(wb[0], wb[1], wb[2], wb[3]));
-            } else {
-                obase[0] = (uint8_t)quantize_u8(r[0]); obase[hw] = (uint8_t)quantize_u8(gr[0]); obase[2 * hw] = (uint8_t)quantize_u8(b[0]);
-            }
+        if constexpr (sizeof(T) == 1 && VEC) {
+            st_stream(reinterpret_cast<uint4 *>(obase), make_uint4(wr[0], wr[1], wr[2], wr[3]));
+            st_stream(reinterpret_cast<uint4 *>(obase + hw), make_uint4(wg[0], wg[1], wg[2], wg[3]));
+            st_stream(reinterpret_cast<uint4 *>(obase + 2 * hw), make_uint4(wb[0], wb[1], wb[2], wb[3]));
         }
     }
 }
 
-static int g_ctas_per_sm = 5;  // 5 x 41 KB of curve tables fill the shared memory of an SM
+static int g_ctas_per_sm = 3;  // measured (float32 64 x 1024^2 transform, loads one group ahead): 3 CTAs per SM 522 us, 4: 530, 5: 539
 static int g_tables = 1;  // interpolated transfer curves instead of SFU pows (large batches)
 
 template <typename T>
@@ -412,6 +517,10 @@ static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *sr
     if (TAB) SX_CUDA(cudaFuncSetAttribute(apply_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
     prefer_l1(apply_kernel<T, VEC, TAB>, kThreads, smem);
+    // A plain launch on purpose.  As a programmatic dependent launch this kernel was measured 80 us SLOWER
+    // (627 against 546 us per float32 transform): its CTAs are placed while the statistics kernel drains,
+    // some SMs end up with five of them and others with three, and every CTA of this grid-stride kernel
+    // carries the same share of the batch -- the slowest SM sets the time.
     apply_kernel<T, VEC, TAB><<<grid, kThreads, smem, stream>>>(p, o, n, hw, src_mean, src_std, ref_mean, ref_std);
     return SX_OK;
 }
@@ -457,7 +566,7 @@ int sx_reinhard_stats(const void *images, int dtype, int64_t n, int64_t h, int64
 
 int sx_reinhard_finalize(const double *sums, float *mean, float *std, sx_stream_t stream) {
     SX_REQUIRE(sums && mean && std, "NULL argument");
-    finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(sums, mean, std);
+    SX_CUDA(launch_pdl(finalize_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), sums, mean, std));
     SX_LAUNCHED("reinhard::finalize_kernel");
     return SX_OK;
 }
@@ -494,7 +603,7 @@ int sx_reinhard_finalize_peers(const void *peer_buffers_dev, int world, int rank
     SX_REQUIRE(peer_buffers_dev && mean && std, "NULL argument");
     SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
     SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
-    finalize_peers_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, epoch, mean, std);
+    SX_CUDA(launch_pdl(finalize_peers_kernel, dim3(1), dim3(64), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, (unsigned)epoch, mean, std));
     SX_LAUNCHED("reinhard::finalize_peers_kernel");
     return SX_OK;
 }

@@ -73,11 +73,15 @@ def probe_hm():
         lib.sx_hm_set_tuning(-1, -1, ctas)
         report(f"hm apply u8 planar ctas/sm={ctas}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
     lib.sx_hm_set_tuning(5, 8, 16)
-    for mode in (5, 8):
-        lib.sx_hm_set_tuning(mode, 8, 16)
-        for pre in (1, 0):
-            lib.sx_hm_set_tuning(-1, -1, 1000 + pre)
-            report(f"hm transform u8 (hist+lut+apply) hist mode={mode} prefetch={pre}", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
+    want_out = ops.hm_transform(src, ref_hist)
+    for ef in (0, 1):
+        for keep in (0, 32, 48, 64, 80, 100):
+            lib.sx_hm_set_tuning(-1, -1, 4000 + ef)
+            lib.sx_hm_set_tuning(-1, -1, 3000 + keep)
+            ok = torch.equal(ops.hm_transform(src, ref_hist), want_out)
+            report(f"hm transform u8 evict_first={ef} keep_mb={keep} ok={ok}", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
+    lib.sx_hm_set_tuning(-1, -1, 4000)
+    lib.sx_hm_set_tuning(-1, -1, 3000)
     lib.sx_hm_set_tuning(5, 8, 16)
     lib.sx_hm_set_tuning(-1, -1, 1001)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
@@ -98,12 +102,15 @@ def probe_reinhard():
     src = torch.rand((64, 3, 1024, 1024), device=dev, generator=g)
     mean = torch.tensor([150.0, 140.0, 130.0], device=dev)
     std = torch.tensor([40.0, 10.0, 12.0], device=dev)
-    for ctas in (2, 4, 8):
+    for ctas in (2, 3, 4):
         lib.sx_reinhard_set_tuning(ctas)
         report(f"reinhard stats f32 ctas/sm={ctas}", timeit(lambda: ops.reinhard_stats(src)), 12 * px)
         report(f"reinhard apply f32 ctas/sm={ctas}", timeit(lambda: ops.reinhard_apply(src, mean, std, mean, std)), 24 * px)
     lib.sx_reinhard_set_tuning(4)
-    report("reinhard transform f32", timeit(lambda: ops.reinhard_transform(src, mean, std)), 36 * px)
+    for ctas in (2, 3, 4):
+        lib.sx_reinhard_set_tuning(ctas)
+        report(f"reinhard transform f32 ctas/sm={ctas}", timeit(lambda: ops.reinhard_transform(src, mean, std), steps=20), 36 * px)
+    lib.sx_reinhard_set_tuning(3)
     src8 = (src * 255).to(torch.uint8)
     del src
     report("reinhard stats u8", timeit(lambda: ops.reinhard_stats(src8)), 3 * px)
