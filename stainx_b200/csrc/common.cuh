@@ -154,35 +154,6 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
-// ---- L2 eviction priorities ----------------------------------------------------------------------
-// A pass that streams more bytes than the L2 holds leaves an arbitrary tail of them resident.  With
-// explicit priorities the producer pass keeps a chosen part (evict_last) and lets the rest go
-// (evict_first), and the consumer pass reads / writes with evict_first so that its own traffic does
-// not push out what it has not read yet.
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
-                 "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ uint4 ld_stream_hint(const uint4 *p, uint64_t policy) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
-    return r;
-}
-__device__ __forceinline__ void st_stream_hint(uint4 *p, const uint4 &v, uint64_t policy) {
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
-}
-
 // Raw SFU operations.  __log2f / exp2f / __fdividef wrap the MUFU instruction in denormal handling
 // (FSETP + FMUL 2^24 + FADD -24: three extra instructions per call); the pixel passes are bound by
 // instruction issue, their arguments are never denormal (255 x + 1 >= 1, outputs clamped), and

@@ -163,14 +163,6 @@ struct TileRing {
         tma_load_1d(ring + (size_t)st * kTileVecs, src, bytes, full + st);
         ++produced;
     }
-    // the same with an L2 eviction priority for the tile's lines
-    __device__ __forceinline__ void produce(const uint4 *src, unsigned bytes, uint64_t policy) {
-        const unsigned st = produced & (kStages - 1), use = produced / kStages;
-        if (use > 0) mbar_wait(empty + st, (use - 1) & 1);
-        mbar_arrive_expect_tx(full + st, bytes);
-        tma_load_1d_hint(ring + (size_t)st * kTileVecs, src, bytes, full + st, policy);
-        ++produced;
-    }
     // every thread: wait for the next tile; returns its stage.  release() after the reads.
     __device__ __forceinline__ const uint4 *acquire() {
         const unsigned st = consumed & (kStages - 1), use = consumed / kStages;
@@ -338,7 +330,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_tma_kern
 // one waits the others keep the unit busy.  A warp reads its tile straight from the ring, four
 // 128-bit vectors per lane at a time.
 template <typename Cfg>
-__global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts, int64_t keep_items) {
+__global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
     constexpr int kW = Cfg::kWarps, kThreadsAll = Cfg::kThreads, kTV = Cfg::kTileVecs, kStages = Cfg::kStages;
     static_assert(Cfg::kProducer, "the per-warp kernel needs the producer warp");
     extern __shared__ __align__(16) unsigned char smem_lane[];
@@ -402,20 +394,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kerne
         cur.seek(hw, (int)tiles_per_plane, kTV, per_channel, seg);
         if (warp == kW) {  // producer warp
             if (lane == 0) {
-                if (keep_items < 0) {
-                    for (int item = 0; item < n_items; ++item) {
-                        tr.produce(base + cur.off, (unsigned)cur.vecs(kTV) * 16u);
-                        cur.next(kTV);
-                    }
-                } else {
-                    // the remap pass behind us re-reads the batch: the last keep_items tiles of this CTA's
-                    // range stay in L2 (evict_last), the tiles before them are the first to go
-                    const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
-                    for (int item = 0; item < n_items; ++item) {
-                        const bool keep = seg + item >= last - keep_items;
-                        tr.produce(base + cur.off, (unsigned)cur.vecs(kTV) * 16u, keep ? pol_last : pol_first);
-                        cur.next(kTV);
-                    }
+                for (int item = 0; item < n_items; ++item) {
+                    tr.produce(base + cur.off, (unsigned)cur.vecs(kTV) * 16u);
+                    cur.next(kTV);
                 }
             }
             __syncwarp();
@@ -859,11 +840,8 @@ __device__ __forceinline__ unsigned remap4_prmt(unsigned w, unsigned tab_addr) {
 // Launched with launch_pdl().  `chain` != 0 (inside sx_hm_transform: the images were visible before the
 // first kernel of the chain started): the CTA's first tile is loaded BEFORE pdl_wait(), i.e. while the
 // LUT kernel -- and the tail of the histogram kernel -- in front of us are still running.
-template <bool HINT>
 __global__ void __launch_bounds__(kThreads) apply_u8_planar_vec_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, unsigned vecs, unsigned planes, unsigned tiles_per_plane, const float *__restrict__ lut, int chain) {
     __shared__ __align__(256) unsigned char lut8[3 * 256];
-    uint64_t pol = 0;
-    if constexpr (HINT) pol = l2_policy_evict_first();
     const unsigned items = planes * tiles_per_plane;  // < 2^31 (checked by the caller)
     pdl_trigger();
     if (!chain) pdl_wait();
@@ -875,7 +853,7 @@ __global__ void __launch_bounds__(kThreads) apply_u8_planar_vec_kernel(const uin
         const unsigned v0 = t * kTileVecs + threadIdx.x;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
-            if (v0 + u * kThreads < vecs) v[u] = HINT ? ld_stream_hint(src + base + v0 + u * kThreads, pol) : ld_stream(src + base + v0 + u * kThreads);
+            if (v0 + u * kThreads < vecs) v[u] = ld_stream(src + base + v0 + u * kThreads);
     };
     if (blockIdx.x < items) load_item(blockIdx.x);
     if (chain) pdl_wait();
@@ -894,8 +872,7 @@ __global__ void __launch_bounds__(kThreads) apply_u8_planar_vec_kernel(const uin
             if (v0 + u * kThreads < vecs) {
                 uint4 o;
                 o.x = remap4_prmt(v[u].x, tab); o.y = remap4_prmt(v[u].y, tab); o.z = remap4_prmt(v[u].z, tab); o.w = remap4_prmt(v[u].w, tab);
-                if constexpr (HINT) st_stream_hint(dst + base + v0 + u * kThreads, o, pol);
-                else st_stream(dst + base + v0 + u * kThreads, o);
+                st_stream(dst + base + v0 + u * kThreads, o);
             }
         }
     }
@@ -1006,8 +983,6 @@ static int g_hist_byte_counters = 5;  // uint8 planar histogram: 5 lane-private 
                                       // 6 ring feed without counting (measurement only: wrong counts)
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 16;
-static int g_l2_keep_mb = 0;      // sx_hm_transform: megabytes of the batch the histogram pass pins in L2 for the remap (0: no eviction hints)
-static int g_apply_evict_first = 0;  // remap loads / stores with the evict_first priority
 static int g_chain_prefetch = 1;  // sx_hm_transform: the remap kernel loads its first tile before pdl_wait()
 
 }  // namespace hm
@@ -1037,15 +1012,12 @@ static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsi
     }
     const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
     const unsigned grid = stream_grid(3 * n * tiles, 1);
-    // L2 residency for the remap pass of sx_hm_transform: every CTA keeps the tail of its range, together
-    // g_l2_keep_mb megabytes of the batch
-    int64_t keep = -1;
-    if (pdl && g_l2_keep_mb > 0) {
-        const int64_t tile_bytes = (hw / 16 < Cfg::kTileVecs ? hw / 16 : Cfg::kTileVecs) * 16;
-        keep = ((int64_t)g_l2_keep_mb << 20) / (tile_bytes * grid);
-    }
-    if (pdl) SX_CUDA(launch_pdl(hist_u8_planar_lane_pw_kernel<Cfg>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, stream, images, hw, n, tiles, cnt, keep));
-    else hist_u8_planar_lane_pw_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt, (int64_t)-1);
+    // (L2 eviction priorities were measured for this chain -- the tail of every CTA's range loaded with
+    // evict_last, 32-100 MB in total, the rest and all remap traffic with evict_first: 127.1-127.4 us against
+    // 127.1 us without any hint.  The remap runs at the speed of a device copy whether or not part of its
+    // input is still in L2.)
+    if (pdl) SX_CUDA(launch_pdl(hist_u8_planar_lane_pw_kernel<Cfg>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmem, stream, images, hw, n, tiles, cnt));
+    else hist_u8_planar_lane_pw_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
     return SX_OK;
 }
 static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream, bool pdl) {
@@ -1074,8 +1046,6 @@ int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_cta
     if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
     if (apply_ctas_per_sm > 0 && apply_ctas_per_sm < 1000) g_apply_ctas_per_sm = apply_ctas_per_sm;
     if (apply_ctas_per_sm == 1000 || apply_ctas_per_sm == 1001) g_chain_prefetch = apply_ctas_per_sm - 1000;
-    if (apply_ctas_per_sm >= 3000 && apply_ctas_per_sm < 4000) g_l2_keep_mb = apply_ctas_per_sm - 3000;
-    if (apply_ctas_per_sm == 4000 || apply_ctas_per_sm == 4001) g_apply_evict_first = apply_ctas_per_sm - 4000;
     return SX_OK;
 }
 
@@ -1179,9 +1149,8 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
     const int64_t tiles_v = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);
     if (dtype == SX_U8 && aligned16(images) && aligned16(out) && hw % 16 == 0 && planes * tiles_v < ((int64_t)1 << 31) && hw / 16 < ((int64_t)1 << 31)) {
         unsigned grid = stream_grid(planes * tiles_v, g_apply_ctas_per_sm);
-        prefer_l1(apply_u8_planar_vec_kernel<false>, kThreads);
-        prefer_l1(apply_u8_planar_vec_kernel<true>, kThreads);
-        SX_CUDA(launch_pdl(g_apply_evict_first ? apply_u8_planar_vec_kernel<true> : apply_u8_planar_vec_kernel<false>, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain && g_chain_prefetch ? 1 : 0));
+        prefer_l1(apply_u8_planar_vec_kernel, kThreads);
+        SX_CUDA(launch_pdl(apply_u8_planar_vec_kernel, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain && g_chain_prefetch ? 1 : 0));
         SX_LAUNCHED("apply_u8_planar_vec_kernel");
     } else if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);

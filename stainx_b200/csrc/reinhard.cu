@@ -16,6 +16,19 @@ namespace sx {
 namespace reinhard {
 
 constexpr int kThreads = 256;
+// How many of the three colour channels evaluate a transfer curve on the SFU (lg2 + ex2) instead of the
+// interpolated table in shared memory.  ncu on the all-table pass 2 (float32): issue 57 %, SFU 28 %, top stall
+// short_scoreboard 4.5 warps per issue -- the warps wait for the 32 KB linear -> sRGB table, whose lookups by
+// 32 unrelated lanes replay ~4.5 times.  Moving that curve to the SFU: pass 2 342 -> 281 us (float32).
+#ifndef SX_RH_INV_SFU_F32
+#define SX_RH_INV_SFU_F32 3
+#endif
+#ifndef SX_RH_INV_SFU_U8  // uint8 pass 2 already spends more of the SFU per byte moved: one channel is its optimum
+#define SX_RH_INV_SFU_U8 1
+#endif
+#ifndef SX_RH_FWD_SFU     // sRGB -> linear of float32 input (both passes)
+#define SX_RH_FWD_SFU 0
+#endif
 #ifndef SX_RH_PREFETCH  // A/B builds: 1 = the next group's loads are issued before the current group is processed
 #define SX_RH_PREFETCH 1
 #endif
@@ -52,6 +65,7 @@ __device__ __forceinline__ float lab_f(float t) {
 // LDS.64.  Interpolation error: 1024 intervals for sRGB -> linear (|f''| <= 3.1): 4e-7; 4096
 // intervals for linear -> sRGB (|g''| <= 2.4e3 at the knee 0.0031): 1.8e-5 on [0, 1] outputs.
 constexpr int kFwdN = 1024, kInvN = 4096;
+constexpr int kFwdTableBytes = (kFwdN + 1) * 8;
 constexpr int kTableBytes = (kFwdN + 1 + kInvN + 1) * 8;
 
 __device__ __forceinline__ float srgb_to_linear_exact(float x) {
@@ -256,7 +270,11 @@ struct RawPx {
             }
             if (in_range) {
 #pragma unroll
-                for (int k = 0; k < kChunk; ++k) { r[k] = curve<kFwdN>(fwd, r[k]); g[k] = curve<kFwdN>(fwd, g[k]); b[k] = curve<kFwdN>(fwd, b[k]); }
+                for (int k = 0; k < kChunk; ++k) {
+                    r[k] = SX_RH_FWD_SFU >= 1 ? srgb_to_linear(r[k]) : curve<kFwdN>(fwd, r[k]);
+                    g[k] = SX_RH_FWD_SFU >= 2 ? srgb_to_linear(g[k]) : curve<kFwdN>(fwd, g[k]);
+                    b[k] = SX_RH_FWD_SFU >= 3 ? srgb_to_linear(b[k]) : curve<kFwdN>(fwd, b[k]);
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < kChunk; ++k) { r[k] = srgb_to_linear(r[k]); g[k] = srgb_to_linear(g[k]); b[k] = srgb_to_linear(b[k]); }
@@ -298,13 +316,22 @@ __global__ void SX_RH_STATS_BOUNDS stats_kernel(const T *__restrict__ img, int64
     const int64_t g0 = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
     GroupCursor cur(g0, stride, groups_per_img);
     using Raw = RawPx<T, VEC, TAB>;
-    Raw raw, ahead;  // the loads of the next group are in flight while this one is processed
-    if (SX_RH_PREFETCH && g0 < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
-    for (int64_t g = g0; g < groups; g += stride) {
-        if (SX_RH_PREFETCH) raw = ahead;
-        else raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+    Raw raw, ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH : 1];  // the loads of the next group(s) are in flight while this one is processed
+#pragma unroll
+    for (int a = 0; a < SX_RH_PREFETCH; ++a) {
+        if (g0 + a * stride < groups) ahead[a].load(img + cur.n * 3 * hw + cur.q * kPix, hw);
         cur.next();
-        if (SX_RH_PREFETCH && g + stride < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+    }
+    for (int64_t g = g0; g < groups; g += stride) {
+        if (SX_RH_PREFETCH) {
+            raw = ahead[0];
+#pragma unroll
+            for (int a = 0; a + 1 < SX_RH_PREFETCH; ++a) ahead[a] = ahead[a + 1];
+            if (g + SX_RH_PREFETCH * stride < groups) ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH - 1 : 0].load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        } else {
+            raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        }
+        cur.next();
         // float32 partial sums over this thread's <= 16 pixels, shifted by 128 to keep the
         // second moments small; folded into double accumulators once per group.
         float s[6] = {0, 0, 0, 0, 0, 0};
@@ -409,7 +436,7 @@ __global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float lin_lut[256];
     const float2 *fwd, *inv;
-    setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, true);
+    setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, (sizeof(T) == 4 ? SX_RH_INV_SFU_F32 : SX_RH_INV_SFU_U8) < 3);
     // L349: ((lab - mu_s) / (sigma_s + 1e-8)) * sigma_r + mu_r, composed with LAB <-> (fx, fy, fz)
     const FMap fm = make_fmap(src_mean, src_std, ref_mean, ref_std);
     const int64_t groups_per_img = hw / kPix;
@@ -417,14 +444,25 @@ __global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__
     const int64_t g0 = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
     GroupCursor cur(g0, stride, groups_per_img);
     using Raw = RawPx<T, VEC, TAB>;
-    Raw raw, ahead;  // the loads of the next group are in flight while this one is processed
-    if (SX_RH_PREFETCH && g0 < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+    GroupCursor pre = cur;  // position of the next load
+    Raw raw, ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH : 1];  // the loads of the next group(s) are in flight while this one is processed
+#pragma unroll
+    for (int a = 0; a < SX_RH_PREFETCH; ++a) {
+        if (g0 + a * stride < groups) ahead[a].load(img + pre.n * 3 * hw + pre.q * kPix, hw);
+        pre.next();
+    }
     for (int64_t g = g0; g < groups; g += stride) {
         T *obase = out + cur.n * 3 * hw + cur.q * kPix;
-        if (SX_RH_PREFETCH) raw = ahead;
-        else raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        if (SX_RH_PREFETCH) {
+            raw = ahead[0];
+#pragma unroll
+            for (int a = 0; a + 1 < SX_RH_PREFETCH; ++a) ahead[a] = ahead[a + 1];
+            if (g + SX_RH_PREFETCH * stride < groups) ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH - 1 : 0].load(img + pre.n * 3 * hw + pre.q * kPix, hw);
+            pre.next();
+        } else {
+            raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+        }
         cur.next();
-        if (SX_RH_PREFETCH && g + stride < groups) ahead.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
         unsigned wr[4] = {0, 0, 0, 0}, wg[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};  // uint8 output words
 #pragma unroll
         for (int ch = 0; ch < Raw::kChunks; ++ch) {
@@ -447,9 +485,10 @@ __global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__
                 xyz_to_linear(r[k], gr[k], b[k], lr, lg, lb);
                 if constexpr (TAB) {
                     // the clamp of the output (L96) commutes with the monotone transfer curve
-                    r[k] = curve<kInvN>(inv, __saturatef(lr));
-                    gr[k] = curve<kInvN>(inv, __saturatef(lg));
-                    b[k] = curve<kInvN>(inv, __saturatef(lb));
+                    constexpr int kSfu = sizeof(T) == 4 ? SX_RH_INV_SFU_F32 : SX_RH_INV_SFU_U8;
+                    r[k] = kSfu >= 1 ? linear_to_srgb(lr) : curve<kInvN>(inv, __saturatef(lr));
+                    gr[k] = kSfu >= 2 ? linear_to_srgb(lg) : curve<kInvN>(inv, __saturatef(lg));
+                    b[k] = kSfu >= 3 ? linear_to_srgb(lb) : curve<kInvN>(inv, __saturatef(lb));
                 } else {
                     r[k] = linear_to_srgb(lr);
                     gr[k] = linear_to_srgb(lg);
@@ -503,8 +542,7 @@ static bool use_tables(int64_t n, int64_t hw) { return g_tables && n * hw >= (in
 template <typename T, bool VEC, bool TAB>
 static int launch_stats(const T *p, int64_t n, int64_t hw, double *sums, cudaStream_t stream) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
-    const size_t smem = TAB ? kTableBytes : 0;
-    if (TAB) SX_CUDA(cudaFuncSetAttribute(stats_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
+    const size_t smem = TAB ? kFwdTableBytes : 0;  // pass 1 only uses the sRGB -> linear curve
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
     prefer_l1(stats_kernel<T, VEC, TAB>, kThreads, smem);
     stats_kernel<T, VEC, TAB><<<grid, kThreads, smem, stream>>>(p, n, hw, sums);
@@ -513,7 +551,7 @@ static int launch_stats(const T *p, int64_t n, int64_t hw, double *sums, cudaStr
 template <typename T, bool VEC, bool TAB>
 static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *src_mean, const float *src_std, const float *ref_mean, const float *ref_std, cudaStream_t stream) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
-    const size_t smem = TAB ? kTableBytes : 0;
+    const size_t smem = TAB ? ((sizeof(T) == 4 ? SX_RH_INV_SFU_F32 : SX_RH_INV_SFU_U8) >= 3 ? kFwdTableBytes : kTableBytes) : 0;
     if (TAB) SX_CUDA(cudaFuncSetAttribute(apply_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
     prefer_l1(apply_kernel<T, VEC, TAB>, kThreads, smem);

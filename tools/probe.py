@@ -73,17 +73,10 @@ def probe_hm():
         lib.sx_hm_set_tuning(-1, -1, ctas)
         report(f"hm apply u8 planar ctas/sm={ctas}", timeit(lambda: ops.hm_apply(src, lut)), 6 * px)
     lib.sx_hm_set_tuning(5, 8, 16)
-    want_out = ops.hm_transform(src, ref_hist)
-    for ef in (0, 1):
-        for keep in (0, 32, 48, 64, 80, 100):
-            lib.sx_hm_set_tuning(-1, -1, 4000 + ef)
-            lib.sx_hm_set_tuning(-1, -1, 3000 + keep)
-            ok = torch.equal(ops.hm_transform(src, ref_hist), want_out)
-            report(f"hm transform u8 evict_first={ef} keep_mb={keep} ok={ok}", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
-    lib.sx_hm_set_tuning(-1, -1, 4000)
-    lib.sx_hm_set_tuning(-1, -1, 3000)
+    for mode in (5, 8):
+        lib.sx_hm_set_tuning(mode, 8, 16)
+        report(f"hm transform u8 (hist+lut+apply) hist mode={mode}", timeit(lambda: ops.hm_transform(src, ref_hist), steps=200, warm=10), 9 * px)
     lib.sx_hm_set_tuning(5, 8, 16)
-    lib.sx_hm_set_tuning(-1, -1, 1001)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
     report("hm transform u8 NHWC", timeit(lambda: ops.hm_transform(nhwc, ref_hist, nv.SX_NHWC)), 9 * px)
     del nhwc
