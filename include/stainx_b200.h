@@ -85,6 +85,13 @@ int sx_hm_apply(const void *images, int dtype, int layout, int64_t n, int64_t h,
 int64_t sx_hm_peer_buffer_bytes(void);
 int sx_hm_build_lut_peers(const void *peer_buffers_dev, int world, int rank, uint32_t epoch,
                           const float *ref_cdf, float *lut, uint64_t *counts_out, sx_stream_t stream);
+/* The whole sharded transform in one call (one chain of dependent launches): zeroes counts[epoch & 1] of
+ * own_buffer (this rank's peer-mapped buffer, i.e. peer_buffers[rank]), sx_hm_hist into them,
+ * sx_hm_build_lut_peers, sx_hm_apply.  workspace: >= 3072 bytes (the LUT). */
+int sx_hm_transform_peers(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
+                          const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t epoch,
+                          const float *ref_cdf, void *out, void *workspace, int64_t workspace_bytes,
+                          sx_stream_t stream);
 /* Workspace for the chained transform/fit below (bytes). */
 int64_t sx_hm_workspace_bytes(void);
 /* hist -> ref_cdf -> build_lut -> apply on one stream (single-device transform). */

@@ -32,6 +32,7 @@ PROTOTYPES: dict[str, list] = {
     "sx_hm_apply": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp],
     "sx_hm_peer_buffer_bytes": [],
     "sx_hm_build_lut_peers": [_vp, _int, _int, ctypes.c_uint32, _vp, _vp, _vp, _vp],
+    "sx_hm_transform_peers": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _int, _int, ctypes.c_uint32, _vp, _vp, _vp, _i64, _vp],
     "sx_hm_workspace_bytes": [],
     "sx_hm_transform": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
     "sx_hm_fit": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp, _i64, _vp],

@@ -148,12 +148,9 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
             ref_hist, ref_cdf = self._reference(reference_histogram)
             ex = self._peer_exchange()
             if ex is not None:
-                # the all-reduce is fused into the LUT kernel: peer loads over NVLink, no NCCL call
-                ex.epoch += 1
-                counts = ex.view((ex.epoch & 1) * 768 * 8, (3, 256), torch.int64)
-                counts.zero_()
-                self._ops.hm_hist(images, layout, counts=counts)
-                lut = self._ops.hm_build_lut_peers(ex, ref_cdf)
+                # the all-reduce is fused into the LUT kernel (peer loads over NVLink, no NCCL call), and the
+                # whole step is one library call = one chain of programmatic dependent launches
+                return self._restore_dtype(self._ops.hm_transform_peers(images, ex, ref_cdf, layout), original)
             else:
                 counts = self._reducer.sum_(self._ops.hm_hist(images, layout))
                 # npix = -1: the LUT kernel takes the global pixel count from the reduced counts

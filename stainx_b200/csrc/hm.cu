@@ -1203,6 +1203,23 @@ int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_
     return apply_impl(images, dtype, layout, n, h, w, lut, out, stream, true);
 }
 
+// The sharded transform as ONE chain of dependent launches: zero this rank's counts of the epoch in its
+// peer-mapped buffer, histogram into them, LUT with the all-reduce over NVLink peer memory, remap.
+int sx_hm_transform_peers(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t epoch,
+                          const float *ref_cdf, void *out, void *workspace, int64_t workspace_bytes, sx_stream_t stream) {
+    SX_REQUIRE(workspace && workspace_bytes >= 768 * 4, "workspace too small (%lld < %d)", (long long)workspace_bytes, 768 * 4);
+    SX_REQUIRE(peer_buffers_dev && own_buffer && ref_cdf, "NULL argument");
+    SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
+    SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
+    auto *counts = reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(own_buffer) + (size_t)(epoch & 1u) * 768 * 8);
+    auto *lut = static_cast<float *>(workspace);
+    zero_counts_kernel<<<1, 768, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long *>(counts));
+    SX_LAUNCHED("zero_counts_kernel");
+    if (int rc = hist_impl(images, dtype, layout, n, h, w, counts, stream, true)) return rc;
+    if (int rc = sx_hm_build_lut_peers(peer_buffers_dev, world, rank, epoch, ref_cdf, lut, nullptr, stream)) return rc;
+    return apply_impl(images, dtype, layout, n, h, w, lut, out, stream, true);
+}
+
 int sx_hm_fit(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w, float *ref_hist, void *workspace, int64_t workspace_bytes, sx_stream_t stream) {
     SX_REQUIRE(workspace && workspace_bytes >= sx_hm_workspace_bytes(), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_hm_workspace_bytes());
     auto *counts = static_cast<uint64_t *>(workspace);

@@ -17,7 +17,7 @@ from stainx_b200._native import SX_F32, SX_NCHW, SX_NHWC, SX_U8, check
 
 __all__ = [
     "MacenkoWorkspace",
-    "hm_apply", "hm_build_lut", "hm_build_lut_peers", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform",
+    "hm_apply", "hm_build_lut", "hm_build_lut_peers", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform", "hm_transform_peers",
     "macenko_fit", "macenko_peer_combine", "macenko_transform",
     "reinhard_apply", "reinhard_finalize", "reinhard_finalize_peers", "reinhard_fit", "reinhard_stats", "reinhard_transform",
 ]
@@ -116,6 +116,20 @@ def hm_build_lut_peers(exchange, ref_cdf: torch.Tensor, counts_out: torch.Tensor
     with torch.cuda.device(dev):
         check(nv.lib().sx_hm_build_lut_peers(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, exchange.epoch & 0xFFFFFFFF, _ptr(ref_cdf),
                                              _ptr(out), _ptr(counts_out) if counts_out is not None else None, _stream(dev)), "sx_hm_build_lut_peers")
+    return out
+
+
+def hm_transform_peers(images: torch.Tensor, exchange, ref_cdf: torch.Tensor, layout: int = SX_NCHW) -> torch.Tensor:
+    """The sharded transform in one library call: advances the exchange's epoch, then zero / histogram /
+    LUT with the all-reduce over NVLink peer memory / remap as one chain of dependent launches."""
+    n, h, w = _check_images(images, layout)
+    dev = images.device
+    out = torch.empty_like(images)
+    ws = torch.empty(768 * 4, dtype=torch.uint8, device=dev)
+    exchange.epoch += 1
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_hm_transform_peers(_ptr(images), _dtype_code(images), layout, n, h, w, ctypes.c_void_p(exchange.ptrs_dev), _ptr(exchange.buf), exchange.world, exchange.rank,
+                                             exchange.epoch & 0xFFFFFFFF, _ptr(ref_cdf), _ptr(out), _ptr(ws), ws.numel(), _stream(dev)), "sx_hm_transform_peers")
     return out
 
 

@@ -149,7 +149,11 @@ def probe_macenko():
             report(f"macenko select stage={stage} level={level}", timeit(lambda: ws.select(0, n, stage, level)), 0.001)
     phases_until(2, 0)
     print("status flags:", int(ws.region("status").abs().sum()))
-    report("macenko apply f32 -> f32 unit", timeit(lambda: ws.apply(src, he, maxc, out, True)), 24 * px)
+    for ctas in (2, 3, 4, 6, 8):
+        lib.sx_macenko_set_tuning(ctas, -1)
+        report(f"macenko apply f32 -> f32 unit ctas/sm={ctas}", timeit(lambda: ws.apply(src, he, maxc, out, True)), 24 * px)
+        report(f"macenko transform f32 64x1024^2 ctas/sm={ctas}", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=10), 24 * px)
+    lib.sx_macenko_set_tuning(4, -1)
     lib.sx_macenko_set_tuning(-1, 1)
     want = ops.macenko_transform(src, he, maxc, unit=True)
     report("macenko transform f32 64x1024^2 phase kernels", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True), steps=5), 24 * px)
