@@ -983,7 +983,6 @@ static int g_hist_byte_counters = 5;  // uint8 planar histogram: 5 lane-private 
                                       // 6 ring feed without counting (measurement only: wrong counts)
 static int g_hist_ctas_per_sm = 8;
 static int g_apply_ctas_per_sm = 16;
-static int g_chain_prefetch = 1;  // sx_hm_transform: the remap kernel loads its first tile before pdl_wait()
 
 }  // namespace hm
 }  // namespace sx
@@ -1044,8 +1043,7 @@ extern "C" {
 int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm) {
     if (hist_byte_counters >= 0) g_hist_byte_counters = hist_byte_counters;
     if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
-    if (apply_ctas_per_sm > 0 && apply_ctas_per_sm < 1000) g_apply_ctas_per_sm = apply_ctas_per_sm;
-    if (apply_ctas_per_sm == 1000 || apply_ctas_per_sm == 1001) g_chain_prefetch = apply_ctas_per_sm - 1000;
+    if (apply_ctas_per_sm > 0) g_apply_ctas_per_sm = apply_ctas_per_sm;
     return SX_OK;
 }
 
@@ -1150,7 +1148,7 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
     if (dtype == SX_U8 && aligned16(images) && aligned16(out) && hw % 16 == 0 && planes * tiles_v < ((int64_t)1 << 31) && hw / 16 < ((int64_t)1 << 31)) {
         unsigned grid = stream_grid(planes * tiles_v, g_apply_ctas_per_sm);
         prefer_l1(apply_u8_planar_vec_kernel, kThreads);
-        SX_CUDA(launch_pdl(apply_u8_planar_vec_kernel, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain && g_chain_prefetch ? 1 : 0));
+        SX_CUDA(launch_pdl(apply_u8_planar_vec_kernel, dim3(grid), dim3(kThreads), 0, stream, static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)(hw / 16), (unsigned)planes, (unsigned)tiles_v, lut, chain ? 1 : 0));
         SX_LAUNCHED("apply_u8_planar_vec_kernel");
     } else if (dtype == SX_U8) {
         const int64_t tiles = max_i64(1, (hw / 16 + kTileVecs - 1) / kTileVecs);

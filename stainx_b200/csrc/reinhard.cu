@@ -16,27 +16,17 @@ namespace sx {
 namespace reinhard {
 
 constexpr int kThreads = 256;
-// How many of the three colour channels evaluate a transfer curve on the SFU (lg2 + ex2) instead of the
-// interpolated table in shared memory.  ncu on the all-table pass 2 (float32): issue 57 %, SFU 28 %, top stall
-// short_scoreboard 4.5 warps per issue -- the warps wait for the 32 KB linear -> sRGB table, whose lookups by
-// 32 unrelated lanes replay ~4.5 times.  Moving that curve to the SFU: pass 2 342 -> 281 us (float32).
-#ifndef SX_RH_INV_SFU_F32
-#define SX_RH_INV_SFU_F32 3
-#endif
-#ifndef SX_RH_INV_SFU_U8  // uint8 pass 2 already spends more of the SFU per byte moved: one channel is its optimum
-#define SX_RH_INV_SFU_U8 1
-#endif
-#ifndef SX_RH_FWD_SFU     // sRGB -> linear of float32 input (both passes)
-#define SX_RH_FWD_SFU 0
-#endif
-#ifndef SX_RH_PREFETCH  // A/B builds: 1 = the next group's loads are issued before the current group is processed
-#define SX_RH_PREFETCH 1
-#endif
-#ifdef SX_RH_STATS_MINB  // A/B builds: resident CTAs per SM the statistics kernel is compiled for
-#define SX_RH_STATS_BOUNDS __launch_bounds__(kThreads, SX_RH_STATS_MINB)
-#else
-#define SX_RH_STATS_BOUNDS __launch_bounds__(kThreads)
-#endif
+// How many of the three colour channels evaluate the linear -> sRGB curve of pass 2 on the SFU (lg2 + ex2)
+// instead of the interpolated table in shared memory.  ncu on the all-table pass 2 (float32): issue 57 %,
+// SFU 28 %, top stall short_scoreboard 4.5 warps per issue -- the warps wait for the 32 KB table, whose
+// lookups by 32 unrelated lanes replay ~4.5 times.  On the SFU: pass 2 342 -> 281 us (float32).  uint8
+// pass 2 already spends more of the SFU per byte moved: one channel is its optimum (226 us; none 237,
+// all 240).  sRGB -> linear stays on its 8 KB table in both passes: 1 / 2 / 3 channels on the SFU were
+// measured at 509 / 558 / 600 us per float32 transform against 460 us (pass 1 is at 64 % SFU already).
+constexpr int kInvSfuF32 = 3, kInvSfuU8 = 1;
+// Pixel groups whose loads are in flight ahead of the one being processed (measured per float32
+// transform: 0: 546 us, 1: 520 us, 2: 531 us, 3: 560 us -- registers against latency).
+constexpr int kAhead = 1;
 
 // sRGB -> linear (torch_backend.py:L28-29).  pow(t, 2.4) = 2^(2.4 log2 t) on the SFU.
 __device__ __forceinline__ float srgb_to_linear(float x) {
@@ -271,9 +261,9 @@ struct RawPx {
             if (in_range) {
 #pragma unroll
                 for (int k = 0; k < kChunk; ++k) {
-                    r[k] = SX_RH_FWD_SFU >= 1 ? srgb_to_linear(r[k]) : curve<kFwdN>(fwd, r[k]);
-                    g[k] = SX_RH_FWD_SFU >= 2 ? srgb_to_linear(g[k]) : curve<kFwdN>(fwd, g[k]);
-                    b[k] = SX_RH_FWD_SFU >= 3 ? srgb_to_linear(b[k]) : curve<kFwdN>(fwd, b[k]);
+                    r[k] = curve<kFwdN>(fwd, r[k]);
+                    g[k] = curve<kFwdN>(fwd, g[k]);
+                    b[k] = curve<kFwdN>(fwd, b[k]);
                 }
             } else {
 #pragma unroll
@@ -302,7 +292,7 @@ __device__ __forceinline__ void setup_tables(unsigned char *smem, const float2 *
 
 // ---- pass 1: statistics ---------------------------------------------------------------------
 template <typename T, bool VEC, bool TAB>
-__global__ void SX_RH_STATS_BOUNDS stats_kernel(const T *__restrict__ img, int64_t n_img, int64_t hw, double *__restrict__ sums) {
+__global__ void __launch_bounds__(kThreads) stats_kernel(const T *__restrict__ img, int64_t n_img, int64_t hw, double *__restrict__ sums) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float lin_lut[256];
@@ -316,18 +306,18 @@ __global__ void SX_RH_STATS_BOUNDS stats_kernel(const T *__restrict__ img, int64
     const int64_t g0 = (int64_t)blockIdx.x * kThreads + threadIdx.x, stride = (int64_t)gridDim.x * kThreads;
     GroupCursor cur(g0, stride, groups_per_img);
     using Raw = RawPx<T, VEC, TAB>;
-    Raw raw, ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH : 1];  // the loads of the next group(s) are in flight while this one is processed
+    Raw raw, ahead[kAhead > 0 ? kAhead : 1];  // the loads of the next group(s) are in flight while this one is processed
 #pragma unroll
-    for (int a = 0; a < SX_RH_PREFETCH; ++a) {
+    for (int a = 0; a < kAhead; ++a) {
         if (g0 + a * stride < groups) ahead[a].load(img + cur.n * 3 * hw + cur.q * kPix, hw);
         cur.next();
     }
     for (int64_t g = g0; g < groups; g += stride) {
-        if (SX_RH_PREFETCH) {
+        if (kAhead) {
             raw = ahead[0];
 #pragma unroll
-            for (int a = 0; a + 1 < SX_RH_PREFETCH; ++a) ahead[a] = ahead[a + 1];
-            if (g + SX_RH_PREFETCH * stride < groups) ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH - 1 : 0].load(img + cur.n * 3 * hw + cur.q * kPix, hw);
+            for (int a = 0; a + 1 < kAhead; ++a) ahead[a] = ahead[a + 1];
+            if (g + kAhead * stride < groups) ahead[kAhead > 0 ? kAhead - 1 : 0].load(img + cur.n * 3 * hw + cur.q * kPix, hw);
         } else {
             raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
         }
@@ -431,12 +421,12 @@ __device__ __forceinline__ unsigned pack_u8x4(const float (&x)[4]) {
 
 // ---- pass 2: transform ----------------------------------------------------------------------
 template <typename T, bool VEC, bool TAB>
-__global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t n_img, int64_t hw, const float *__restrict__ src_mean, const float *__restrict__ src_std, const float *__restrict__ ref_mean, const float *__restrict__ ref_std) {
+__global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t n_img, int64_t hw, const float *__restrict__ src_mean, const float *__restrict__ src_std, const float *__restrict__ ref_mean, const float *__restrict__ ref_std) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float lin_lut[256];
     const float2 *fwd, *inv;
-    setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, (sizeof(T) == 4 ? SX_RH_INV_SFU_F32 : SX_RH_INV_SFU_U8) < 3);
+    setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, (sizeof(T) == 4 ? kInvSfuF32 : kInvSfuU8) < 3);
     // L349: ((lab - mu_s) / (sigma_s + 1e-8)) * sigma_r + mu_r, composed with LAB <-> (fx, fy, fz)
     const FMap fm = make_fmap(src_mean, src_std, ref_mean, ref_std);
     const int64_t groups_per_img = hw / kPix;
@@ -445,19 +435,19 @@ __global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__
     GroupCursor cur(g0, stride, groups_per_img);
     using Raw = RawPx<T, VEC, TAB>;
     GroupCursor pre = cur;  // position of the next load
-    Raw raw, ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH : 1];  // the loads of the next group(s) are in flight while this one is processed
+    Raw raw, ahead[kAhead > 0 ? kAhead : 1];  // the loads of the next group(s) are in flight while this one is processed
 #pragma unroll
-    for (int a = 0; a < SX_RH_PREFETCH; ++a) {
+    for (int a = 0; a < kAhead; ++a) {
         if (g0 + a * stride < groups) ahead[a].load(img + pre.n * 3 * hw + pre.q * kPix, hw);
         pre.next();
     }
     for (int64_t g = g0; g < groups; g += stride) {
         T *obase = out + cur.n * 3 * hw + cur.q * kPix;
-        if (SX_RH_PREFETCH) {
+        if (kAhead) {
             raw = ahead[0];
 #pragma unroll
-            for (int a = 0; a + 1 < SX_RH_PREFETCH; ++a) ahead[a] = ahead[a + 1];
-            if (g + SX_RH_PREFETCH * stride < groups) ahead[SX_RH_PREFETCH > 0 ? SX_RH_PREFETCH - 1 : 0].load(img + pre.n * 3 * hw + pre.q * kPix, hw);
+            for (int a = 0; a + 1 < kAhead; ++a) ahead[a] = ahead[a + 1];
+            if (g + kAhead * stride < groups) ahead[kAhead > 0 ? kAhead - 1 : 0].load(img + pre.n * 3 * hw + pre.q * kPix, hw);
             pre.next();
         } else {
             raw.load(img + cur.n * 3 * hw + cur.q * kPix, hw);
@@ -485,7 +475,7 @@ __global__ void SX_RH_STATS_BOUNDS apply_kernel(const T *__restrict__ img, T *__
                 xyz_to_linear(r[k], gr[k], b[k], lr, lg, lb);
                 if constexpr (TAB) {
                     // the clamp of the output (L96) commutes with the monotone transfer curve
-                    constexpr int kSfu = sizeof(T) == 4 ? SX_RH_INV_SFU_F32 : SX_RH_INV_SFU_U8;
+                    constexpr int kSfu = sizeof(T) == 4 ? kInvSfuF32 : kInvSfuU8;
                     r[k] = kSfu >= 1 ? linear_to_srgb(lr) : curve<kInvN>(inv, __saturatef(lr));
                     gr[k] = kSfu >= 2 ? linear_to_srgb(lg) : curve<kInvN>(inv, __saturatef(lg));
                     b[k] = kSfu >= 3 ? linear_to_srgb(lb) : curve<kInvN>(inv, __saturatef(lb));
@@ -551,7 +541,7 @@ static int launch_stats(const T *p, int64_t n, int64_t hw, double *sums, cudaStr
 template <typename T, bool VEC, bool TAB>
 static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *src_mean, const float *src_std, const float *ref_mean, const float *ref_std, cudaStream_t stream) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
-    const size_t smem = TAB ? ((sizeof(T) == 4 ? SX_RH_INV_SFU_F32 : SX_RH_INV_SFU_U8) >= 3 ? kFwdTableBytes : kTableBytes) : 0;
+    const size_t smem = TAB ? ((sizeof(T) == 4 ? kInvSfuF32 : kInvSfuU8) >= 3 ? kFwdTableBytes : kTableBytes) : 0;
     if (TAB) SX_CUDA(cudaFuncSetAttribute(apply_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
     prefer_l1(apply_kernel<T, VEC, TAB>, kThreads, smem);

@@ -259,6 +259,58 @@ def test_reinhard_identity_property(cuda):
     assert (out - x).abs().max().item() <= 2e-3
 
 
+def test_reinhard_chain_back_to_back_and_in_a_graph(cuda, ox):
+    """sx_reinhard_transform chains statistics -> finalize (a programmatic dependent launch) -> transform:
+    back-to-back transforms of different batches with recycled scratch must each use their own statistics,
+    eagerly on a side stream and replayed from a CUDA graph."""
+    import ctypes
+
+    from stainx_b200 import ops
+
+    g = torch.Generator(device=cuda).manual_seed(21)
+    batches = [torch.rand((6, 3, 512, 512), device=cuda, generator=g).pow(p) for p in (0.6, 1.0, 1.8)]
+    mean = torch.tensor([160.0, 135.0, 120.0], device=cuda)
+    std = torch.tensor([35.0, 9.0, 14.0], device=cuda)
+    want = []
+    for b in batches:  # phase-level calls with a device synchronisation between the phases
+        sums = ops.reinhard_stats(b)
+        torch.cuda.synchronize()
+        m, s_ = ops.reinhard_finalize(sums)
+        torch.cuda.synchronize()
+        want.append(ops.reinhard_apply(b, m, s_, mean, std))
+        torch.cuda.synchronize()
+    ref = ox.reinhard_transform(_np(batches[0].cpu()), _np(mean.cpu()), _np(std.cpu()))
+    assert np.abs(_np(want[0]) - ref).max() <= F32_TOL
+    s = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(s):
+        bad = []
+        for i in range(24):
+            out = ops.reinhard_transform(batches[i % 3], mean, std)
+            bad.append((out != want[i % 3]).sum())
+            del out
+    s.synchronize()
+    assert all(int(b) == 0 for b in bad)
+    src = batches[1]
+    static_out = torch.empty_like(src)
+    ws = torch.empty(int(nv_lib().sx_reinhard_workspace_bytes()), dtype=torch.uint8, device=cuda)
+
+    def enqueue():
+        rc = nv_lib().sx_reinhard_transform(ctypes.c_void_p(src.data_ptr()), 1, 6, 512, 512, ctypes.c_void_p(mean.data_ptr()), ctypes.c_void_p(std.data_ptr()), ctypes.c_void_p(static_out.data_ptr()),
+                                            ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(cuda).cuda_stream))
+        assert rc == 0
+
+    enqueue()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enqueue()
+        enqueue()
+    static_out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, want[1])
+
+
 def test_reinhard_phase_api_shards(cuda):
     """Statistics accumulate over shards (what the multi-GPU path all-reduces)."""
     from stainx_b200 import ops
