@@ -496,7 +496,10 @@ __global__ void __launch_bounds__(kThreads) hist_nhwc_kernel(const T *__restrict
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
         if constexpr (sizeof(T) == 1) {
             const uint4 *p = reinterpret_cast<const uint4 *>(img + g * kGroup);
-            uint4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
+            // L1-allocating loads: the three 128-bit loads of a warp touch the same 48 sectors (each lane's
+            // 48 bytes start on a 16-byte boundary), so the second and third find their halves in L1
+            // (96 -> 87 us per 64 x 1024^2 batch against L1::no_allocate loads)
+            uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);
             unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int j = 0; j < 48; ++j) {
@@ -927,32 +930,85 @@ __global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const float 
     }
 }
 
+// Interleaved (NHWC) uint8 remap over whole 128-bit vectors of the flat array: a warp's load / store is one
+// contiguous 512-byte run (the general kernel below gives every thread 48 consecutive bytes, so that a
+// byte's channel is a compile-time constant -- but then each 128-bit access of a warp touches 32 half-used
+// sectors: 125 us per 64 x 1024^2 batch whatever the instruction count).  Here byte b of vector v belongs to
+// channel (v + b) % 3 (16 = 1 mod 3): the three table addresses are rotated once per vector and the
+// lookups are the PRMT-addressed ones of the planar kernel.
+__global__ void __launch_bounds__(kThreads) apply_u8_nhwc_vec_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, unsigned nvec, unsigned tiles, const float *__restrict__ lut) {
+    __shared__ __align__(256) unsigned char lut8[3 * 256];
+    for (int i = threadIdx.x; i < 768; i += kThreads) lut8[i] = (unsigned char)__float2int_rz(lut[i]);  // trunc, L296-298
+    __syncthreads();
+    const unsigned tab0 = smem_u32(lut8);
+    static_assert(kTileVecs % 3 == 1 && kThreads % 3 == 1, "the channel rotation below assumes 1024 = 256 = 1 (mod 3)");
+    for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const unsigned v0 = t * kTileVecs + threadIdx.x;
+        // channel of byte 0 of vector v0 = v0 % 3 = (t + threadIdx.x) % 3; vector v0 + u * 256 is u channels further
+        const unsigned c0 = (t + threadIdx.x) % 3u;
+        const unsigned c1 = c0 == 2u ? 0u : c0 + 1u, c2 = c0 == 0u ? 2u : c0 - 1u;
+        const unsigned tab[3] = {tab0 + c0 * 256u, tab0 + c1 * 256u, tab0 + c2 * 256u};
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (v0 + u * kThreads < nvec) v[u] = ld_stream(src + v0 + u * kThreads);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const unsigned vi = v0 + u * kThreads;
+            if (vi < nvec) {
+                const unsigned w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                unsigned r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned tt[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(tt[i]) : "r"(__byte_perm(w[k], tab[(u + 4 * k + i) % 3], 0x7650 + i)));
+                    r[k] = __byte_perm(__byte_perm(tt[0], tt[1], 0x0040), __byte_perm(tt[2], tt[3], 0x0040), 0x5410);
+                }
+                st_stream(dst + vi, make_uint4(r[0], r[1], r[2], r[3]));
+            }
+        }
+    }
+}
+
+// The < 16 bytes behind the last whole vector of an interleaved uint8 array; byte i has channel (c0 + i) % 3.
+__global__ void apply_nhwc_tail_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, int n, int c0, const float *__restrict__ lut) {
+    const int i = threadIdx.x;
+    if (i < n) out[i] = (uint8_t)__float2int_rz(lut[((c0 + i) % 3) * 256 + img[i]]);
+}
+
 // Interleaved (NHWC) remap, uint8 or float32.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t total, const float *__restrict__ lut) {
     constexpr int kPerVec = 16 / sizeof(T);
     constexpr int kGroup = 3 * kPerVec;
     __shared__ float lutf[3 * 256];
-    __shared__ unsigned char lut8[3 * 256];
+    __shared__ __align__(256) unsigned char lut8[3 * 256];  // 256-byte aligned tables: PRMT-built lookup addresses (remap4_prmt)
     for (int i = threadIdx.x; i < 768; i += kThreads) {
         lut8[i] = (unsigned char)__float2int_rz(lut[i]);
         lutf[i] = fminf(fmaxf(__fdiv_rn(lut[i], 255.0f), 0.0f), 1.0f);
     }
     __syncthreads();
+    const unsigned tab0 = smem_u32(lut8);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     const int64_t groups = vec_ok ? total / kGroup : 0;
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < groups; g += (int64_t)gridDim.x * kThreads) {
         if constexpr (sizeof(T) == 1) {
             const uint4 *p = reinterpret_cast<const uint4 *>(img + g * kGroup);
-            uint4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
+            uint4 a = __ldg(p), b = __ldg(p + 1), d = __ldg(p + 2);  // L1-allocating: see hist_nhwc_kernel
             unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
             unsigned r[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) r[k] = 0u;
+            for (int k = 0; k < 12; ++k) {
+                // byte j of the 48-byte group belongs to channel j % 3: one PRMT per byte builds the address of
+                // its entry in that channel's table, three more reassemble the word
+                unsigned t[4];
 #pragma unroll
-            for (int j = 0; j < 48; ++j) {
-                unsigned v = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                r[j >> 2] |= (unsigned)lut8[(j % 3) * 256 + v] << (8 * (j & 3));
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned tab = tab0 + (unsigned)((4 * k + i) % 3) * 256u;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t[i]) : "r"(__byte_perm(w[k], tab, 0x7650 + i)));
+                }
+                r[k] = __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
             }
             uint4 *q = reinterpret_cast<uint4 *>(out + g * kGroup);
             st_stream(q, make_uint4(r[0], r[1], r[2], r[3]));
@@ -1131,7 +1187,19 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
     SX_REQUIRE(lut && out, "NULL argument");
     if (layout == SX_NHWC) {
         const int64_t total = n * hw * 3;
-        if (dtype == SX_U8) {
+        if (dtype == SX_U8 && aligned16(images) && aligned16(out) && total / 16 < ((int64_t)1 << 31) && total >= ((int64_t)1 << 20)) {
+            // whole vectors with the coalesced kernel; the < 16 trailing bytes (total = 3 N H W is a multiple of
+            // 48 whenever H W is a multiple of 16) with the general kernel, whose channel is the byte index mod 3
+            const int64_t nvec = total / 16, tiles = (nvec + kTileVecs - 1) / kTileVecs;
+            prefer_l1(apply_u8_nhwc_vec_kernel, kThreads);
+            apply_u8_nhwc_vec_kernel<<<stream_grid(tiles, g_apply_ctas_per_sm), kThreads, 0, stream>>>(static_cast<const uint4 *>(images), static_cast<uint4 *>(out), (unsigned)nvec, (unsigned)tiles, lut);
+            const int64_t tail = total - nvec * 16;
+            if (tail > 0) {
+                SX_LAUNCHED("apply_u8_nhwc_vec_kernel");
+                // the tail starts at byte nvec * 16, whose channel is (nvec * 16) % 3 = nvec % 3: shift the LUT rows accordingly
+                apply_nhwc_tail_kernel<<<1, 32, 0, stream>>>(static_cast<const uint8_t *>(images) + nvec * 16, static_cast<uint8_t *>(out) + nvec * 16, (int)tail, (int)(nvec % 3), lut);
+            }
+        } else if (dtype == SX_U8) {
             unsigned grid = stream_grid((total / 48 + kThreads - 1) / kThreads + 1, 8);
             prefer_l1(apply_nhwc_kernel<uint8_t>, kThreads);
             apply_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), total, lut);

@@ -77,6 +77,22 @@ def test_hm_nhwc_vs_oracle(cuda, ox, dtype):
     assert np.array_equal(_np(out), want)
 
 
+@pytest.mark.parametrize("hw", [(700, 500), (701, 499), (1024, 1024)])
+def test_hm_nhwc_large_vs_planar(cuda, hw):
+    """Interleaved uint8 batches above 1 MB take the coalesced vector remap (rotating channel tables) plus a
+    tail of < 16 bytes: the result must equal the planar transform of the same pixels, bit for bit."""
+    from stainx_b200 import HistogramMatching
+
+    g = torch.Generator(device=cuda).manual_seed(31)
+    ref = (torch.rand((1, 3, 300, 300), device=cuda, generator=g).pow(1.6) * 255).round().to(torch.uint8)
+    src = (torch.rand((2, 3, *hw), device=cuda, generator=g).pow(0.7) * 255).round().to(torch.uint8)
+    planar = HistogramMatching(device=cuda, backend="torch_cuda").fit(ref)
+    nhwc = HistogramMatching(device=cuda, backend="torch_cuda", channel_axis=-1).fit(ref.permute(0, 2, 3, 1).contiguous())
+    want = planar.transform(src)
+    got = nhwc.transform(src.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(got.permute(0, 3, 1, 2), want)
+
+
 def test_hm_misaligned_view_and_noncontiguous(cuda, ox):
     """Planes that do not start on 16-byte boundaries, and a non-contiguous input."""
     from stainx_b200 import HistogramMatching

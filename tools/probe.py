@@ -79,6 +79,8 @@ def probe_hm():
     lib.sx_hm_set_tuning(5, 8, 16)
     nhwc = src.permute(0, 2, 3, 1).contiguous()
     report("hm transform u8 NHWC", timeit(lambda: ops.hm_transform(nhwc, ref_hist, nv.SX_NHWC)), 9 * px)
+    report("hm hist u8 NHWC", timeit(lambda: ops.hm_hist(nhwc, nv.SX_NHWC, counts=counts)), 3 * px)
+    report("hm apply u8 NHWC", timeit(lambda: ops.hm_apply(nhwc, lut, nv.SX_NHWC)), 6 * px)
     del nhwc
     srcf = src[:32].float() / 255
     report("hm hist f32 planar (32 img)", timeit(lambda: ops.hm_hist(srcf, counts=counts)), 12 * px / 2)
