@@ -1067,6 +1067,10 @@ static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsi
     }
     const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
     const unsigned grid = stream_grid(3 * n * tiles, 1);
+    // (Register-fed lane-private counters were measured again in this form: five counting warps, no ring, every
+    // lane keeping a batch of sixteen 128-bit loads in flight while it counts the previous batch -- 40 KB in
+    // flight per SM, 164 KB carve-out.  Correct, but 75.4 us against 59.7 us: the loads share the LSU queue with
+    // the shared-memory atomics, the TMA ring does not.)
     // (L2 eviction priorities were measured for this chain -- the tail of every CTA's range loaded with
     // evict_last, 32-100 MB in total, the rest and all remap traffic with evict_first: 127.1-127.4 us against
     // 127.1 us without any hint.  The remap runs at the speed of a device copy whether or not part of its
