@@ -94,7 +94,10 @@ int sx_hm_transform_peers(const void *images, int dtype, int layout, int64_t n, 
                           sx_stream_t stream);
 /* Workspace for the chained transform/fit below (bytes). */
 int64_t sx_hm_workspace_bytes(void);
-/* hist -> ref_cdf -> build_lut -> apply on one stream (single-device transform). */
+/* zero counts -> hist -> ref_cdf + build_lut -> apply on one stream (single-device transform), enqueued as one
+ * chain of programmatic dependent launches: only the first kernel relies on ordinary stream order, each later
+ * kernel is resident before the one in front of it has drained and waits (griddepcontrol.wait) before it reads
+ * what that kernel wrote.  To the caller the call is ordered like a plain sequence of launches. */
 int sx_hm_transform(const void *images, int dtype, int layout, int64_t n, int64_t h, int64_t w,
                     const float *ref_hist, void *out, void *workspace, int64_t workspace_bytes,
                     sx_stream_t stream);
