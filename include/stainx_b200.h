@@ -53,6 +53,15 @@ int sx_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *l2_byte
 /* Number of kernels this library has launched in the calling process (monotonic). */
 int64_t sx_kernel_launches(void);
 
+/* Peer exchanges (the *_peers functions below wait inside a kernel for the other ranks of the node).
+ * Every such wait is bounded: SX_PEER_TIMEOUT_MS in the environment at first use, default 20000.  A
+ * kernel whose wait expires records it in a per-device status record (pinned host memory, read
+ * without synchronising) and carries on with meaningless results; from then on every *_peers call on
+ * that device fails with SX_ERR_CUDA until sx_peer_status_clear().  sx_peer_status reports the record
+ * of the current device: *timed_out != 0, the rank that was waited for, and the epoch. */
+int sx_peer_status(int *timed_out, int *waited_for_rank, uint32_t *epoch);
+int sx_peer_status_clear(void);
+
 /* ---- histogram matching --------------------------------------------------------------------
  * Reference: torch_backend.py:L194-301 (oracle), csrc/histogram_matching.cu:L49-226 (CUDA). */
 
@@ -233,6 +242,16 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
 /* Whole pooled fit on one stream (slots = 1): he[3][2] row-major, maxc[2] (device pointers). */
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he,
                    float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t stream);
+
+/* ---- development hooks ----------------------------------------------------------------------
+ * Launch-geometry knobs for tools/probe.py and the ncu scripts.  NOT part of the drop-in surface:
+ * they set process-global state, are not thread-safe, and return SX_ERR_UNSUPPORTED (changing
+ * nothing) unless SX_ENABLE_TUNING=1 was in the environment before their first call.  With the
+ * hooks inert the library has no mutable global state besides per-device cached attributes, the
+ * launch counter, the side streams of sx_macenko_transform and the peer status record above. */
+int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm);
+int sx_reinhard_set_tuning(int ctas_per_sm);
+int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,15 @@ def num_threads() -> int:
     return int(lib().ox_num_threads())
 
 
+def set_num_threads(n: int | None = None) -> int:
+    """Set the OpenMP thread count explicitly (default: every host core).  torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently make a CPU baseline single-threaded."""
+    import os
+
+    lib().ox_set_num_threads(_c_int(int(n) if n else (os.cpu_count() or 1)))
+    return num_threads()
+
+
 def _prep(img: np.ndarray) -> tuple[np.ndarray, int, int, int]:
     if img.ndim != 4 or img.shape[1] != 3:
         raise ValueError(f"oracle expects NCHW with C=3, got {img.shape}")

@@ -24,6 +24,8 @@ PROTOTYPES: dict[str, list] = {
     "sx_last_error": [],
     "sx_device_info": [ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(_i64)],
     "sx_kernel_launches": [],
+    "sx_peer_status": [ctypes.POINTER(_int), ctypes.POINTER(_int), ctypes.POINTER(ctypes.c_uint32)],
+    "sx_peer_status_clear": [],
     # histogram matching
     "sx_hm_hist": [_vp, _int, _int, _i64, _i64, _i64, _vp, _vp],
     "sx_hm_ref_hist": [_vp, _vp, _vp],
@@ -129,6 +131,13 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = lib().sx_last_error()
         raise StainxNativeError(f"{what} failed (status {status}): {msg.decode() if msg else 'unknown error'}")
+
+
+def peer_status() -> tuple[bool, int, int]:
+    """(timed_out, rank waited for, epoch) of the current device's peer-exchange status record."""
+    t, r, e = _int(0), _int(0), ctypes.c_uint32(0)
+    check(lib().sx_peer_status(ctypes.byref(t), ctypes.byref(r), ctypes.byref(e)), "sx_peer_status")
+    return bool(t.value), int(r.value), int(e.value)
 
 
 def kernel_launches() -> int:

@@ -26,29 +26,30 @@ class TorchCUDABackendBase:
     """Device / availability checks shared by the three backends
     (reference: ``torch_cuda_backend.py:L17-33``)."""
 
-    def __init__(self, device: str | torch.device | None = None, reducer: StatReducer | None = None, ops=None):
-        # `ops` lets the CPU test-suite substitute the kernel layer to exercise the sharding logic;
-        # the product always uses stainx_b200.ops (the native library).
-        self._injected_ops = ops is not None
-        if ops is None:
-            if not _native.available():
-                raise ImportError("libstainx_b200 is not built. CUDA backend is not available (python -m stainx_b200.build); there is no fallback backend.")
-            from stainx_b200 import ops as native_ops
-
-            ops = native_ops
-        self._ops = ops
+    def __init__(self, device: str | torch.device | None = None, reducer: StatReducer | None = None):
+        self._ops = self._kernel_layer()
         self._reducer = reducer if reducer is not None else StatReducer()
-
         if device is None:
-            if torch.cuda.is_available():
-                self.device = torch.device("cuda")
-            elif self._injected_ops:
-                self.device = torch.device("cpu")
-            else:
+            if not torch.cuda.is_available():
                 raise RuntimeError("CUDA is not available on this system")
+            self.device = torch.device("cuda")
         else:
             self.device = torch.device(device)
-        if self.device.type != "cuda" and not self._injected_ops:
+        self._check_device()
+
+    # The two hooks below are the only seams of this class: the CPU test-suite subclasses the backends
+    # (tests/cpu_ops.py: ``cpu_backend``) to exercise the sharding control flow with gloo; the product
+    # classes always bind the native library and always require a CUDA device.
+    @staticmethod
+    def _kernel_layer():
+        if not _native.available():
+            raise ImportError("libstainx_b200 is not built. CUDA backend is not available (python -m stainx_b200.build); there is no fallback backend.")
+        from stainx_b200 import ops as native_ops
+
+        return native_ops
+
+    def _check_device(self) -> None:
+        if self.device.type != "cuda":
             raise ValueError(f"CUDA backend requires CUDA device, got {self.device.type}")
 
     def _to_native(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.dtype]:
@@ -71,8 +72,8 @@ class TorchCUDABackendBase:
 
 
 class HistogramMatchingCUDA(TorchCUDABackendBase):
-    def __init__(self, device: str | torch.device | None = None, channel_axis: int = 1, reducer: StatReducer | None = None, ops=None):
-        super().__init__(device, reducer, ops)
+    def __init__(self, device: str | torch.device | None = None, channel_axis: int = 1, reducer: StatReducer | None = None):
+        super().__init__(device, reducer)
         self.channel_axis = channel_axis
         self._exchange = None        # sharding.PeerExchange (NVLink peer memory) or False when unavailable
         self._ref_cdf_cache = None   # (ref_hist, ref_cdf): the reference CDF is a fit-time constant
@@ -81,6 +82,18 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
         if self.channel_axis == -1 or (self.channel_axis == 3 and images.ndim == 4):
             return _native.SX_NHWC
         return _native.SX_NCHW
+
+    def _require_rgb(self, images: torch.Tensor) -> None:
+        """The kernels are written for three channels ('Layout everywhere: C=3').
+        The reference's torch backend loops over any channel count (torch_backend.py:L149-179,
+        L228-286); that generality is deliberately not reproduced -- say so instead of failing deep
+        inside the kernel layer."""
+        if images.dim() != 4:
+            raise ValueError(f"HistogramMatching expects a 4-D batch (NCHW, or NHWC with channel_axis=-1), got shape {tuple(images.shape)}")
+        c = images.shape[-1] if self._layout(images) == _native.SX_NHWC else images.shape[1]
+        if c != 3:
+            raise ValueError(f"stainx_b200 HistogramMatching supports RGB images only (C=3 on channel_axis={self.channel_axis}), got C={c} with shape {tuple(images.shape)}; "
+                             "grayscale / multi-channel inputs are a documented restriction of this backend.")
 
     def _stack_reference(self, reference_histogram: torch.Tensor | list) -> torch.Tensor:
         """(3, 256) float32 reference histograms from the list / single-tensor forms the reference
@@ -130,6 +143,7 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
     def compute_reference_counts(self, images: torch.Tensor) -> torch.Tensor:
         """Whole-reference-set per-channel counts, int64 (3, 256), summed over ranks."""
         images, _ = self._to_native(images)
+        self._require_rgb(images)
         counts = self._ops.hm_hist(images, self._layout(images))
         return self._reducer.sum_(counts)
 
@@ -142,6 +156,7 @@ class HistogramMatchingCUDA(TorchCUDABackendBase):
 
     def transform(self, images: torch.Tensor, reference_histogram: torch.Tensor | list) -> torch.Tensor:
         images, original = self._to_native(images)
+        self._require_rgb(images)
         layout = self._layout(images)
         if self._reducer.enabled:
             # H3 -> all-reduce -> H2 -> H4: the source histogram spans the whole sharded batch.
@@ -186,11 +201,12 @@ class ReinhardCUDA(TorchCUDABackendBase):
         if self._reducer.enabled:
             ex = self._peer_exchange()
             if ex is not None:  # the all-reduce of the sums is fused into the finalize kernel (NVLink peer loads)
-                ex.epoch += 1
-                sums = ex.view((ex.epoch & 1) * 64, (8,), torch.float64)
+                epoch = ex.epoch + 1  # committed once every launch of the step went through (peers step in lockstep)
+                sums = ex.view((epoch & 1) * 64, (8,), torch.float64)
                 sums.zero_()
                 self._ops.reinhard_stats(images, sums=sums)
-                src_mean, src_std = self._ops.reinhard_finalize_peers(ex)
+                src_mean, src_std = self._ops.reinhard_finalize_peers(ex, epoch)
+                ex.epoch = epoch
             else:
                 src_mean, src_std = self._ops.reinhard_finalize(self._reducer.sum_(self._ops.reinhard_stats(images)))
             result = self._ops.reinhard_apply(images, src_mean, src_std, target_mean, target_std)
@@ -208,10 +224,10 @@ class MacenkoCUDA(TorchCUDABackendBase):
     both values select the same kernels.
     """
 
-    def __init__(self, device: str | torch.device | None = None, precision: str = "stable", reducer: StatReducer | None = None, ops=None):
+    def __init__(self, device: str | torch.device | None = None, precision: str = "stable", reducer: StatReducer | None = None):
         if precision not in ("stable", "fast"):
             raise ValueError(f"precision must be 'stable' or 'fast', got {precision!r}")
-        super().__init__(device, reducer, ops)
+        super().__init__(device, reducer)
         self._precision = precision
 
     def compute_reference_stain_matrix(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:

@@ -12,6 +12,14 @@ int fail(int code, const char *fmt, ...);
 void note_launch(int n = 1);
 int sm_count();
 int64_t l2_bytes();
+// Peer rendezvous (kernels that wait for other ranks over NVLink): device pointer of this device's
+// status record (NULL when it could not be mapped), the time budget of one wait, and the host-side
+// check every *_peers entry point makes first (lib.cu).
+unsigned *peer_status_device_ptr();
+unsigned long long peer_timeout_ns();
+int peer_status_check(const char *what);
+// Development hooks (sx_*_set_tuning) only act when SX_ENABLE_TUNING=1 was set before the first call.
+bool tuning_enabled();
 
 #define SX_CUDA(expr)                                                                              \
     do {                                                                                           \
@@ -152,6 +160,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// ---- bounded wait for a peer's flag ----------------------------------------------------------------
+// Spins (load-acquire, system scope) until *flag has reached `epoch`; gives up after `budget_ns` of
+// the global timer, records {1, peer, epoch, own rank} in the device's status record (host-mapped) and
+// returns false: a rank that died or skipped a step must not hang every GPU of the node.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool wait_peer_flag(const unsigned *flag, unsigned epoch, unsigned long long budget_ns, unsigned *status, int peer, int rank) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned polls = 0;
+    for (;;) {
+        unsigned seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if ((int)(seen - epoch) >= 0) return true;
+        if ((++polls & 255u) == 0u && global_timer_ns() - t0 > budget_ns) {
+            if (status != nullptr) {  // plain stores to mapped host memory (several timed-out threads may race: any one record will do)
+                volatile unsigned *st = status;
+                st[1] = (unsigned)peer;
+                st[2] = epoch;
+                st[3] = (unsigned)rank;
+                __threadfence_system();
+                st[0] = 1u;
+            }
+            return false;
+        }
+    }
 }
 
 // Raw SFU operations.  __log2f / exp2f / __fdividef wrap the MUFU instruction in denormal handling

@@ -736,7 +736,7 @@ __global__ void zero_counts_kernel(unsigned long long *__restrict__ counts) {
 constexpr int kPeerCountsBytes = 2 * 768 * 8;
 constexpr int kPeerMaxWorld = 64;
 
-__global__ void __launch_bounds__(256) build_lut_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, const float *__restrict__ ref_cdf, float *__restrict__ lut, unsigned long long *__restrict__ counts_out) {
+__global__ void __launch_bounds__(256) build_lut_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, const float *__restrict__ ref_cdf, float *__restrict__ lut, unsigned long long *__restrict__ counts_out, unsigned long long budget_ns, unsigned *status) {
     const int c = blockIdx.x, b = threadIdx.x;
     const int parity = (int)(epoch & 1u);
     pdl_trigger();
@@ -746,12 +746,9 @@ __global__ void __launch_bounds__(256) build_lut_peers_kernel(unsigned char *con
         unsigned *flag = reinterpret_cast<unsigned *>(bufs[b] + kPeerCountsBytes) + rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
     }
-    if (b < world) {  // (2) wait for every rank's counts of this epoch
+    if (b < world) {  // (2) wait for every rank's counts of this epoch (bounded: a dead rank must not hang the node)
         const unsigned *flag = reinterpret_cast<const unsigned *>(bufs[rank] + kPeerCountsBytes) + b;
-        unsigned seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        } while ((int)(seen - epoch) < 0);
+        wait_peer_flag(flag, epoch, budget_ns, status, b, rank);
     }
     __syncthreads();
     unsigned long long total = 0;  // (3) all-reduce of bin (c, b)
@@ -1099,8 +1096,10 @@ static int launch_lane_tma(int mode, const uint8_t *images, int64_t hw, int64_t 
 
 extern "C" {
 
-// Undocumented-in-header tuning hook used by bench/profiling scripts.
+// Development hook (declared in the header under "development hooks"): process-global, not
+// thread-safe, and inert unless SX_ENABLE_TUNING=1 is set in the environment.
 int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm) {
+    if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
     if (hist_byte_counters >= 0) g_hist_byte_counters = hist_byte_counters;
     if (hist_ctas_per_sm > 0) g_hist_ctas_per_sm = hist_ctas_per_sm;
     if (apply_ctas_per_sm > 0) g_apply_ctas_per_sm = apply_ctas_per_sm;
@@ -1248,7 +1247,9 @@ int sx_hm_build_lut_peers(const void *peer_buffers_dev, int world, int rank, uin
     SX_REQUIRE(peer_buffers_dev && ref_cdf && lut, "NULL argument");
     SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
     SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
-    SX_CUDA(launch_pdl(build_lut_peers_kernel, dim3(3), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, (unsigned)epoch, ref_cdf, lut, reinterpret_cast<unsigned long long *>(counts_out)));
+    if (int rc = peer_status_check("sx_hm_build_lut_peers")) return rc;
+    SX_CUDA(launch_pdl(build_lut_peers_kernel, dim3(3), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, (unsigned)epoch, ref_cdf, lut, reinterpret_cast<unsigned long long *>(counts_out),
+                       peer_timeout_ns(), peer_status_device_ptr()));
     SX_LAUNCHED("build_lut_peers_kernel");
     return SX_OK;
 }

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -74,6 +75,71 @@ void prefer_l1_impl(const void *kernel, int block_threads, size_t dyn_smem) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
 }
 
+// ---- peer rendezvous status ----------------------------------------------------------------------
+// One 16-byte record per device in pinned, device-mapped HOST memory (allocated on first use, never
+// freed; the only allocation the library makes, and it is host memory).  A peer kernel whose wait for
+// another rank exceeds the time budget writes {1, rank waited for, epoch, own rank} here and carries on
+// (its results are then meaningless); the host reads the record without synchronising: every later
+// *_peers call on that device fails with SX_ERR_CUDA until sx_peer_status_clear().
+static unsigned *g_peer_status_host = nullptr;
+static std::mutex g_peer_status_mu;
+
+static unsigned *peer_status_host() {
+    std::lock_guard<std::mutex> lock(g_peer_status_mu);
+    if (g_peer_status_host == nullptr) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, 64 * 16, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        memset(p, 0, 64 * 16);
+        g_peer_status_host = static_cast<unsigned *>(p);
+    }
+    return g_peer_status_host;
+}
+
+unsigned *peer_status_device_ptr() {
+    unsigned *h = peer_status_host();
+    if (h == nullptr) return nullptr;
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) d = 0;
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, h + d * 4, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return static_cast<unsigned *>(dp);
+}
+
+int peer_status_check(const char *what) {
+    unsigned *h = peer_status_host();
+    if (h == nullptr) return SX_OK;
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) d = 0;
+    const volatile unsigned *r = h + d * 4;
+    if (r[0] != 0u) return fail(SX_ERR_CUDA, "%s: an earlier peer exchange on this device timed out (rank %u waited for rank %u at epoch %u); results since then are invalid -- see sx_peer_status()", what, r[3], r[1], r[2]);
+    return SX_OK;
+}
+
+unsigned long long peer_timeout_ns() {
+    static const unsigned long long ns = [] {
+        const char *e = getenv("SX_PEER_TIMEOUT_MS");
+        const long long ms = e ? atoll(e) : 0;
+        return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;  // default: 20 s
+    }();
+    return ns;
+}
+
+bool tuning_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SX_ENABLE_TUNING");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 int sm_count() { return dev().sms; }
 int64_t l2_bytes() { return dev().l2; }
 
@@ -99,6 +165,27 @@ int sx_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *l2_byte
     if (cc_major) *cc_major = maj;
     if (cc_minor) *cc_minor = min;
     if (l2_bytes) *l2_bytes = l2;
+    return SX_OK;
+}
+
+int sx_peer_status(int *timed_out, int *waited_for_rank, uint32_t *epoch) {
+    unsigned *h = sx::peer_status_host();
+    int d = 0;
+    SX_CUDA(cudaGetDevice(&d));
+    if (d < 0 || d >= 64) d = 0;
+    const volatile unsigned *r = h ? h + d * 4 : nullptr;
+    if (timed_out) *timed_out = r ? (int)r[0] : 0;
+    if (waited_for_rank) *waited_for_rank = r ? (int)r[1] : 0;
+    if (epoch) *epoch = r ? r[2] : 0u;
+    return SX_OK;
+}
+
+int sx_peer_status_clear(void) {
+    unsigned *h = sx::peer_status_host();
+    int d = 0;
+    SX_CUDA(cudaGetDevice(&d));
+    if (d < 0 || d >= 64) d = 0;
+    if (h) memset(h + d * 4, 0, 16);
     return SX_OK;
 }
 

@@ -1330,17 +1330,14 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void *p) {
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void peer_rendezvous(unsigned char *const *bufs, int world, int rank, unsigned epoch, int64_t flags_off) {
+__device__ __forceinline__ void peer_rendezvous(unsigned char *const *bufs, int world, int rank, unsigned epoch, int64_t flags_off, unsigned long long budget_ns, unsigned *status) {
     __syncthreads();
     if ((int)threadIdx.x < world) {
         __threadfence_system();
         unsigned *theirs = reinterpret_cast<unsigned *>(bufs[threadIdx.x] + flags_off) + rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
         const unsigned *mine = reinterpret_cast<const unsigned *>(bufs[rank] + flags_off) + threadIdx.x;
-        unsigned seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-        } while ((int)(seen - epoch) < 0);
+        wait_peer_flag(mine, epoch, budget_ns, status, (int)threadIdx.x, rank);  // bounded: a dead rank must not hang the node
     }
     __syncthreads();
 }
@@ -1374,10 +1371,10 @@ __device__ __forceinline__ void combine_region(unsigned char *const *bufs, int w
     }
 }
 
-__global__ void __launch_bounds__(kCombineThreads) peer_combine_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, int which, unsigned char *__restrict__ scratch) {
+__global__ void __launch_bounds__(kCombineThreads) peer_combine_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, int which, unsigned char *__restrict__ scratch, unsigned long long budget_ns, unsigned *status) {
     const Layout L(1);
     const int64_t cells = 2 * kBins * 4;  // bytes of one per-slot cell array
-    peer_rendezvous(bufs, world, rank, epoch, L.total);  // (1) everybody's statistics of this step are complete
+    peer_rendezvous(bufs, world, rank, epoch, L.total, budget_ns, status);  // (1) everybody's statistics of this step are complete
     if (which == 0) {
         combine_region<kSumF64>(bufs, world, L.moments, 12 * 8, scratch, 0);
         combine_region<kMaxF32>(bufs, world, L.odrange, 8 * 4, scratch, 128);
@@ -1391,7 +1388,7 @@ __global__ void __launch_bounds__(kCombineThreads) peer_combine_kernel(unsigned 
         combine_region<kSumU64>(bufs, world, L.counters, 8 * 8, scratch, 3 * cells);
     }
     __threadfence();
-    peer_rendezvous(bufs, world, rank, epoch, L.total + kPeerMaxWorld * 4);  // (3) everybody has read everybody
+    peer_rendezvous(bufs, world, rank, epoch, L.total + kPeerMaxWorld * 4, budget_ns, status);  // (3) everybody has read everybody
     unsigned char *own = bufs[rank];
     auto put = [&](int64_t off, int64_t bytes, int64_t soff) {
         for (int64_t i = (int64_t)threadIdx.x * 16; i < bytes; i += (int64_t)kCombineThreads * 16) *reinterpret_cast<uint4 *>(own + off + i) = *reinterpret_cast<const uint4 *>(scratch + soff + i);
@@ -1550,7 +1547,9 @@ static SideStream *side_stream() {
 
 extern "C" {
 
+// Development hook: process-global, not thread-safe, inert unless SX_ENABLE_TUNING=1.
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels) {
+    if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
     if (phase_kernels >= 0) {  // bit 0: phase-level chain; bits 4..: number of chains (0: default)
         g_phase_kernels = (phase_kernels & 1) != 0;
@@ -1587,7 +1586,8 @@ int sx_macenko_peer_combine(const void *peer_buffers_dev, int world, int rank, u
     SX_REQUIRE(peer_buffers_dev && scratch, "NULL argument");
     SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
     SX_REQUIRE(epoch != 0 && which >= 0 && which <= 2, "bad epoch/which (%u, %d)", epoch, which);
-    peer_combine_kernel<<<1, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, epoch, which, static_cast<unsigned char *>(scratch));
+    if (int rc = peer_status_check("sx_macenko_peer_combine")) return rc;
+    peer_combine_kernel<<<1, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, epoch, which, static_cast<unsigned char *>(scratch), peer_timeout_ns(), peer_status_device_ptr());
     SX_LAUNCHED("macenko::peer_combine_kernel");
     return SX_OK;
 }

@@ -371,7 +371,7 @@ __global__ void finalize_kernel(const double *__restrict__ sums, float *__restri
 constexpr int kPeerSumsBytes = 2 * 8 * 8;
 constexpr int kPeerMaxWorld = 64;
 
-__global__ void finalize_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, float *__restrict__ mean, float *__restrict__ std) {
+__global__ void finalize_peers_kernel(unsigned char *const *__restrict__ bufs, int world, int rank, unsigned epoch, float *__restrict__ mean, float *__restrict__ std, unsigned long long budget_ns, unsigned *status) {
     __shared__ double tot[8];
     const int t = threadIdx.x;
     const int parity = (int)(epoch & 1u);
@@ -382,10 +382,7 @@ __global__ void finalize_peers_kernel(unsigned char *const *__restrict__ bufs, i
         unsigned *flag = reinterpret_cast<unsigned *>(bufs[t] + kPeerSumsBytes) + rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
         const unsigned *mine = reinterpret_cast<const unsigned *>(bufs[rank] + kPeerSumsBytes) + t;
-        unsigned seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-        } while ((int)(seen - epoch) < 0);
+        wait_peer_flag(mine, epoch, budget_ns, status, t, rank);  // bounded: a dead rank must not hang the node
     }
     __syncthreads();
     if (t < 7) {
@@ -561,7 +558,9 @@ static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *sr
 
 extern "C" {
 
+// Development hook: process-global, not thread-safe, inert unless SX_ENABLE_TUNING=1.
 int sx_reinhard_set_tuning(int ctas_per_sm) {
+    if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
     if (ctas_per_sm > 0 && ctas_per_sm < 100) g_ctas_per_sm = ctas_per_sm;
     if (ctas_per_sm == 100) g_tables = 0;
     if (ctas_per_sm == 101) g_tables = 1;
@@ -631,7 +630,8 @@ int sx_reinhard_finalize_peers(const void *peer_buffers_dev, int world, int rank
     SX_REQUIRE(peer_buffers_dev && mean && std, "NULL argument");
     SX_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world (%d, %d)", rank, world);
     SX_REQUIRE(epoch != 0, "epoch must start at 1 (flags are zero-initialised)");
-    SX_CUDA(launch_pdl(finalize_peers_kernel, dim3(1), dim3(64), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, (unsigned)epoch, mean, std));
+    if (int rc = peer_status_check("sx_reinhard_finalize_peers")) return rc;
+    SX_CUDA(launch_pdl(finalize_peers_kernel, dim3(1), dim3(64), 0, static_cast<cudaStream_t>(stream), static_cast<unsigned char *const *>(peer_buffers_dev), world, rank, (unsigned)epoch, mean, std, peer_timeout_ns(), peer_status_device_ptr()));
     SX_LAUNCHED("reinhard::finalize_peers_kernel");
     return SX_OK;
 }

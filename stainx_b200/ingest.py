@@ -75,6 +75,11 @@ class HostStream:
         slot = self._slots[self._next % len(self._slots)]
         self._next += 1
         with torch.cuda.device(self.device):
+            # Whatever the caller enqueued on its current stream before this submit -- above all the
+            # kernels of fit() / fit_reference(), whose fitted tensors the transform below reads -- must
+            # have finished before this batch's kernels start: the compute stream is non-blocking and
+            # shares no implicit ordering with it.
+            self._s_compute.wait_stream(torch.cuda.current_stream(self.device))
             # ---- host -> device, into a recycled staging buffer
             with torch.cuda.stream(self._s_in):
                 if slot["free"] is not None:

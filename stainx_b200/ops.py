@@ -126,10 +126,11 @@ def hm_transform_peers(images: torch.Tensor, exchange, ref_cdf: torch.Tensor, la
     dev = images.device
     out = torch.empty_like(images)
     ws = torch.empty(768 * 4, dtype=torch.uint8, device=dev)
-    exchange.epoch += 1
+    epoch = exchange.epoch + 1  # committed only when the launch went through: a rank that raises here must not run ahead of its peers
     with torch.cuda.device(dev):
         check(nv.lib().sx_hm_transform_peers(_ptr(images), _dtype_code(images), layout, n, h, w, ctypes.c_void_p(exchange.ptrs_dev), _ptr(exchange.buf), exchange.world, exchange.rank,
-                                             exchange.epoch & 0xFFFFFFFF, _ptr(ref_cdf), _ptr(out), _ptr(ws), ws.numel(), _stream(dev)), "sx_hm_transform_peers")
+                                             epoch & 0xFFFFFFFF, _ptr(ref_cdf), _ptr(out), _ptr(ws), ws.numel(), _stream(dev)), "sx_hm_transform_peers")
+    exchange.epoch = epoch
     return out
 
 
@@ -187,14 +188,16 @@ def reinhard_finalize(sums: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return mean, std
 
 
-def reinhard_finalize_peers(exchange) -> tuple[torch.Tensor, torch.Tensor]:
+def reinhard_finalize_peers(exchange, epoch: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
     """mean / std of a sharded batch with the all-reduce of the sums fused into the kernel (NVLink peer
-    loads; ``exchange``: a ``sharding.PeerExchange`` whose sums[epoch & 1] hold this rank's statistics)."""
+    loads; ``exchange``: a ``sharding.PeerExchange`` whose sums[epoch & 1] hold this rank's statistics;
+    ``epoch`` defaults to the exchange's current one)."""
     dev = exchange.buf.device
+    epoch = exchange.epoch if epoch is None else int(epoch)
     mean = torch.empty(3, dtype=torch.float32, device=dev)
     std = torch.empty(3, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(nv.lib().sx_reinhard_finalize_peers(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, exchange.epoch & 0xFFFFFFFF, _ptr(mean), _ptr(std), _stream(dev)), "sx_reinhard_finalize_peers")
+        check(nv.lib().sx_reinhard_finalize_peers(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, epoch & 0xFFFFFFFF, _ptr(mean), _ptr(std), _stream(dev)), "sx_reinhard_finalize_peers")
     return mean, std
 
 
@@ -293,10 +296,11 @@ class MacenkoWorkspace:
 def macenko_peer_combine(exchange, which: int, scratch: torch.Tensor) -> None:
     """Combine slot 0's statistics of every rank in place, in one kernel over NVLink peer memory
     (``which``: 0 after moments, 1 after a sample pass, 2 after a resolve pass).  Advances the epoch."""
-    exchange.epoch += 1
+    epoch = exchange.epoch + 1
     dev = exchange.buf.device
     with torch.cuda.device(dev):
-        check(nv.lib().sx_macenko_peer_combine(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, exchange.epoch & 0xFFFFFFFF, int(which), _ptr(scratch), _stream(dev)), "sx_macenko_peer_combine")
+        check(nv.lib().sx_macenko_peer_combine(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, epoch & 0xFFFFFFFF, int(which), _ptr(scratch), _stream(dev)), "sx_macenko_peer_combine")
+    exchange.epoch = epoch
 
 
 def _macenko_out(images: torch.Tensor, unit: bool) -> torch.Tensor:

@@ -97,22 +97,36 @@ class PeerExchange:
     def create(cls, reducer: StatReducer, device: torch.device, nbytes: int) -> "PeerExchange | None":
         if not reducer.enabled or torch.device(device).type != "cuda" or dist.get_backend(reducer.group) != "nccl":
             return None
+        group = reducer.group if reducer.group is not None else dist.group.WORLD
+
+        def agree(ok: bool) -> bool:  # all ranks or none (one small all-reduce)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=reducer.group)
+            return bool(int(flag.item()))
+
+        # Step 1 is purely local (allocation): a failure here must not leave the other ranks inside a
+        # collective, so the ranks agree on it BEFORE anyone enters the rendezvous.
+        buf = handle = None
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
-            group = reducer.group if reducer.group is not None else dist.group.WORLD
             buf = symm_mem.empty(int(nbytes), dtype=torch.uint8, device=device)
             buf.zero_()
+            local_ok = True
+        except Exception:  # noqa: BLE001 - any failure means "no peer memory on this rank"
+            local_ok = False
+        if not agree(local_ok):
+            return None
+        # Step 2 is collective: every rank enters it, and they agree on its outcome afterwards.
+        try:
             handle = symm_mem.rendezvous(buf, group)
             torch.cuda.synchronize(device)
-            dist.barrier(group=reducer.group)  # every rank's zeros are in place before anyone signals
-            ok = torch.ones(1, dtype=torch.int32, device=device)
-        except Exception:  # noqa: BLE001 - any failure means "no peer memory": agree on it below
-            buf = handle = None
-            ok = torch.zeros(1, dtype=torch.int32, device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=reducer.group)  # all ranks or none
-        if int(ok.item()) == 0 or handle is None:
+            mapped = handle is not None
+        except Exception:  # noqa: BLE001
+            mapped = False
+        if not agree(mapped):
             return None
+        dist.barrier(group=reducer.group)  # every rank's zeros are in place before anyone signals
         return cls(buf, handle, reducer.group)
 
     def view(self, offset: int, shape: tuple[int, ...], dtype: torch.dtype) -> torch.Tensor:

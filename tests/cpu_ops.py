@@ -329,3 +329,25 @@ def macenko_transform(images, he_ref, maxc_ref, unit=False):
     if unit:
         out = out.astype(np.float32) / np.float32(255.0)
     return torch.from_numpy(out)
+
+
+# ------------------------------------------------------------------ test-only backend subclasses
+def cpu_backend(cls, *args, kernel_layer=None, **kwargs):
+    """Instance of a product backend class (``HistogramMatchingCUDA`` / ``ReinhardCUDA`` /
+    ``MacenkoCUDA``) whose two seams are overridden: the kernel layer is this module (or
+    ``kernel_layer``) and CPU devices are accepted.  Lives in the tests on purpose -- the product
+    classes take no substitute ops and refuse non-CUDA devices."""
+    import sys
+
+    layer = kernel_layer if kernel_layer is not None else sys.modules[__name__]
+
+    class _CPU(cls):  # noqa: N801
+        @staticmethod
+        def _kernel_layer():
+            return layer
+
+        def _check_device(self) -> None:
+            pass
+
+    _CPU.__name__ = cls.__name__ + "OnCPU"
+    return _CPU(*args, **kwargs)

@@ -62,7 +62,11 @@ def test_backend_requires_cuda_device():
 def test_hm_reference_histogram_validation():
     from stainx_b200.backends.torch_cuda_backend import HistogramMatchingCUDA
 
-    b = HistogramMatchingCUDA("cpu", ops=object())  # injected ops: skips the device check only
+    from tests.cpu_ops import cpu_backend
+
+    b = cpu_backend(HistogramMatchingCUDA, "cpu", kernel_layer=object())  # test subclass: skips the device check only
+    with pytest.raises(ValueError, match="requires CUDA device"):
+        HistogramMatchingCUDA("cpu")  # the product class itself refuses CPU devices
     with pytest.raises(ValueError, match="cannot be empty"):
         b._stack_reference([])
     with pytest.raises(TypeError, match="must be a torch.Tensor"):

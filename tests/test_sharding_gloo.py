@@ -48,7 +48,7 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str):
             ref, src = noise_u8((2, 3, 40, 40), 1, 2.0), noise_u8((5, 3, 40, 40), 2, 0.6)
             lo, hi = shard_range(src.shape[0], rank, world)
             rlo, rhi = shard_range(ref.shape[0], rank, world)
-            b = HistogramMatchingCUDA("cpu", reducer=red, ops=cpu_ops)
+            b = cpu_ops.cpu_backend(HistogramMatchingCUDA, "cpu", reducer=red)
             counts, hists = b.compute_reference_histograms(ref[rlo:rhi])  # pooled fit over the sharded reference
             result["ref_hist"] = torch.stack(hists).numpy()
             result["out"] = b.transform(src[lo:hi], hists).numpy()
@@ -57,7 +57,7 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str):
             ref, src = noise_f32((2, 3, 32, 32), 3), noise_f32((5, 3, 32, 32), 4, 1.5)
             lo, hi = shard_range(src.shape[0], rank, world)
             rlo, rhi = shard_range(ref.shape[0], rank, world)
-            b = ReinhardCUDA("cpu", reducer=red, ops=cpu_ops)
+            b = cpu_ops.cpu_backend(ReinhardCUDA, "cpu", reducer=red)
             mean, std = b.compute_reference_mean_std(ref[rlo:rhi])
             result["mean"], result["std"] = mean.numpy(), std.numpy()
             result["out"] = b.transform(src[lo:hi], mean, std).numpy()
@@ -65,14 +65,14 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str):
         elif case == "macenko":
             ref = torch.cat([he_tile(64, 64, 42), he_tile(64, 64, 7, 1.1), he_tile(64, 64, 8, 0.9)])
             rlo, rhi = shard_range(ref.shape[0], rank, world)
-            b = MacenkoCUDA("cpu", reducer=red, ops=cpu_ops)
+            b = cpu_ops.cpu_backend(MacenkoCUDA, "cpu", reducer=red)
             he, maxc = b.compute_reference_stain_matrix(ref[rlo:rhi])
             result["he"], result["maxc"] = he.numpy(), maxc.numpy()
         elif case == "broadcast":
             from stainx_b200 import Reinhard
 
             n = Reinhard(device="cpu", process_group="world")
-            n._backend_impl = ReinhardCUDA("cpu", reducer=n._make_reducer(), ops=cpu_ops)
+            n._backend_impl = cpu_ops.cpu_backend(ReinhardCUDA, "cpu", reducer=n._make_reducer())
             ref = noise_f32((1, 3, 24, 24), 10 + rank)  # ranks hold DIFFERENT tensors: only src's counts
             n.fit_broadcast(ref if rank == 1 else None, src=1)
             result["mean"], result["std"] = n._reference_mean.numpy(), n._reference_std.numpy()
@@ -80,7 +80,7 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str):
             from stainx_b200 import StainNormalizerTransform
 
             t = StainNormalizerTransform("reinhard", mode="batch", batch_ref_index=3, process_group="world")
-            t.normalizer._backend_impl = ReinhardCUDA("cpu", reducer=t.normalizer._make_reducer(), ops=cpu_ops)
+            t.normalizer._backend_impl = cpu_ops.cpu_backend(ReinhardCUDA, "cpu", reducer=t.normalizer._make_reducer())
             t._follow_device = lambda device: None  # CPU stand-in: skip the CUDA-only device sync
             full = noise_f32((5, 3, 16, 16), 21)
             lo, hi = shard_range(5, rank, world)  # rank 0: [0,3), rank 1: [3,5) -> global index 3 lives on rank 1

@@ -9,8 +9,11 @@ achieved algorithmic GB/s, sweeping the tuning knobs exposed by the library.
 from __future__ import annotations
 
 import json
+import os
 import sys
 from pathlib import Path
+
+os.environ["SX_ENABLE_TUNING"] = "1"  # the launch-geometry hooks are inert without it
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))

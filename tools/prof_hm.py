@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Small HistogramMatching workload for ncu captures (development tool)."""
+import os
 import sys
+
+os.environ["SX_ENABLE_TUNING"] = "1"
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
