@@ -1,16 +1,28 @@
 #!/usr/bin/env python
 """Throughput bench for the stain-normalization hot path (BASELINE.json metric: megapixels/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--method hm|reinhard|macenko]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c1|c2|c3|c4|c5|reinhard]
 
-Headline workload (N GPUs, weak scaling, 64 images per GPU): BASELINE.json configs[1] --
-HistogramMatching, uint8, 64x3x1024x1024 per GPU, reference mode.  One step = one
-`HistogramMatching.transform(batch)`: per-channel histogram of the (sharded) batch, [N>1: all-reduce of the
-3x256 counts inside the LUT kernel over NVLink peer memory], LUT build, LUT remap.  The batch (201 MB per GPU) is larger than the 126 MB L2, so every step
-streams it from HBM; no L2 flush is needed between steps.
+Workloads (BASELINE.json `configs`); `--config c2` is the default and the headline:
 
-Rank 0 prints ONE JSON line (see the keys in `main`).  `--impl reference` times the CPU oracle
-port (oracle/stainx_oracle.c, OpenMP, all host threads) on a bounded sample of the same workload.
+  c1        Reinhard fit 1x3x512x512 + transform 10x3x512x512 float32 (README quick-start; N = 1 only)
+  c2        HistogramMatching uint8 64x3x1024x1024 per GPU, reference mode (bit-exact LUT path)      9 B/px
+  c3        Macenko reference-mode transform, float32 64x3x1024x1024 per GPU                        24 B/px
+  c4        Macenko pooled fit + transform of 512x3x1024x1024 float32 sharded over the N GPUs        24 B/px  (strong scaling)
+  c5        StainNormalizerTransform("macenko") uint8 2048x2048 tiles, 32 per GPU, float32 [0,1] out  15 B/px
+  reinhard  Reinhard transform float32 64x3x1024x1024 per GPU (batch-global statistics)             36 B/px
+
+One step = one pass of the method's public API over the per-GPU batch, inputs resident in HBM (`value`) or in
+pinned host memory with H2D + D2H inside the timed region (`e2e`, through stainx_b200.ingest.HostStream).
+Every batch is larger than the 126 MB L2 except c1 (said so in `config.l2`), so no flush is needed between steps.
+
+Rank 0 prints ONE JSON line.  Per-kernel times for `roofline` are taken in a SEPARATE loop after the timed
+region (phase-level calls bracketed by CUDA events, >= 16 samples after their own warm-up), never inside it.
+`parity_check` (outside the timed region): the step's result against the CPU oracle, and at N > 1 the sharded
+result against the single-device result of the gathered batch; a mismatch exits non-zero.
+
+`--impl reference` times the CPU oracle port (oracle/stainx_oracle.c, OpenMP on ALL host cores -- the thread
+count is set explicitly, torchrun's OMP_NUM_THREADS=1 is not inherited) on the same per-GPU batch.
 """
 from __future__ import annotations
 
@@ -26,27 +38,24 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
-IMAGES_PER_GPU = 64
-EVENT_EVERY = 32  # an instrumented step costs ~15 us more: four cudaEventRecord calls, and the phase-level calls
-                  # cannot chain the kernels as programmatic dependent launches the way the single library call does
-H = W = 1024
-ALGO_BYTES_PER_PX = {"hm": 9.0, "reinhard": 36.0, "macenko": 24.0}
+KERNEL_SAMPLES = 32  # per-kernel event samples of the roofline loop
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 2000 for the GPU arm, 20 for --impl reference)")
-    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default: 20 / 2)")
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: per workload)")
+    ap.add_argument("--warmup", type=int, default=None, help="warm-up steps (default: per workload, >= 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--method", default="hm", choices=["hm", "reinhard", "macenko"])
-    ap.add_argument("--no-extras", action="store_true", help="skip the per-method side measurements")
+    ap.add_argument("--config", default=None, choices=["c1", "c2", "c3", "c4", "c5", "reinhard"])
+    ap.add_argument("--method", default=None, choices=["hm", "reinhard", "macenko"], help="shorthand: hm = c2, macenko = c3, reinhard = reinhard")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements of the other workloads (c2 line only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    if args.steps is None:
-        args.steps = 2000 if args.impl == "b200" else 20
-    if args.warmup is None:
-        args.warmup = 20 if args.impl == "b200" else 2
+    if args.config is None:
+        args.config = {"hm": "c2", "macenko": "c3", "reinhard": "reinhard", None: "c2"}[args.method]
     return args
 
 
@@ -61,7 +70,7 @@ def peaks() -> tuple[float, str]:
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks: sample nvidia-smi during the timed region
+# clocks: sample NVML during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML from a background thread (every ~2 ms)
@@ -129,74 +138,163 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU legs (oracle port)
+# workload table: what both arms (GPU and CPU reference) agree on
 # ------------------------------------------------------------------------------------------------
-def cpu_hm_sample(n_img: int, seconds: float) -> dict:
-    """Time the oracle's HistogramMatching transform on `n_img` uint8 1024x1024 images, repeated
-    for about `seconds`; returns MP/s (best repetition) and what was run."""
+C4_GLOBAL_IMAGES = 512
+
+
+def images_per_gpu(config: str, world: int) -> int:
+    if config == "c1":
+        return 10
+    if config == "c4":
+        return C4_GLOBAL_IMAGES // world
+    if config == "c5":
+        return 32
+    return 64
+
+
+SPECS = {
+    # name: (method, in dtype, H, W, algorithmic B/px, scaling, description)
+    "c1": ("reinhard", "f32", 512, 512, 24.0, "weak", "Reinhard fit 1x3x512x512 + transform 10x3x512x512 float32 (BASELINE configs[0], README quick-start)"),
+    "c2": ("hm", "u8", 1024, 1024, 9.0, "weak", "HistogramMatching uint8 64x3x1024x1024 per GPU, reference mode (BASELINE configs[1])"),
+    "c3": ("macenko", "f32", 1024, 1024, 24.0, "weak", "Macenko reference-mode transform float32 64x3x1024x1024 per GPU (BASELINE configs[2])"),
+    "c4": ("macenko", "f32", 1024, 1024, 24.0, "strong", "Macenko batch-mode pooled fit + transform, 512x3x1024x1024 float32 sharded by image over the GPUs (BASELINE configs[3])"),
+    "c5": ("macenko", "u8", 2048, 2048, 15.0, "weak", "StainNormalizerTransform('macenko', mode='reference') uint8 2048x2048 tiles, 32 per GPU, float32 [0,1] out (BASELINE configs[4])"),
+    "reinhard": ("reinhard", "f32", 1024, 1024, 36.0, "weak", "Reinhard transform float32 64x3x1024x1024 per GPU (batch-global LAB statistics)"),
+}
+
+
+def config_block(config: str, world: int) -> dict:
+    """`config` of the JSON line; identical for the GPU arm and the reference arm at the same N."""
+    method, dt, h, w, bpp, scaling, desc = SPECS[config]
+    n = images_per_gpu(config, world)
+    in_mb = n * 3 * h * w * (1 if dt == "u8" else 4) / 1e6
+    return {
+        "workload": desc, "name": config, "images_per_gpu": n, "global_images": n * world, "image": f"3x{h}x{w} {'uint8' if dt == 'u8' else 'float32'}",
+        "parallelism": "single GPU" if world == 1 else f"image-sharded x{world}, one process per GPU",
+        "algorithmic_bytes_per_px": bpp,
+        "l2": (f"input per GPU ({in_mb:.0f} MB) exceeds the 126 MB L2; no flush needed" if in_mb > 130 else f"input per GPU ({in_mb:.0f} MB) fits the 126 MB L2: an L2 flush (256 MB write) runs between timed steps"),
+    }
+
+
+def make_inputs_numpy(config: str, world: int, rank: int, n_img: int | None = None):
+    """Host-side inputs of the CPU arms: same distribution and shapes as the device inputs (uniform noise,
+    BASELINE convention; exact values differ from the device RNG, which does not matter for a timing)."""
     import numpy as np
 
+    method, dt, h, w, *_ = SPECS[config]
+    n = images_per_gpu(config, world) if n_img is None else n_img
+    rng = np.random.default_rng(43 + rank)
+    rrng = np.random.default_rng(42)
+    if dt == "u8":
+        return rrng.integers(0, 256, size=(1, 3, h, w), dtype=np.uint8), rng.integers(0, 256, size=(n, 3, h, w), dtype=np.uint8)
+    return rrng.random((1, 3, h, w), dtype=np.float32), rng.random((n, 3, h, w), dtype=np.float32)
+
+
+def cpu_step_fn(config: str, ref, src):
+    """One step of the workload on the CPU oracle port (all fit-time work outside, like the GPU arm)."""
     from oracle import oracle as ox
 
-    rng = np.random.default_rng(43)
-    ref = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
-    src = rng.integers(0, 256, size=(n_img, 3, H, W), dtype=np.uint8)
-    ref_hist = ox.hm_fit(ref)
-    ox.hm_transform(src[:1], ref_hist)  # warm-up (page in, thread pool)
-    best, reps, t_end = None, 0, time.perf_counter() + seconds
-    while reps < 3 or time.perf_counter() < t_end:
-        t0 = time.perf_counter()
-        ox.hm_transform(src, ref_hist)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        reps += 1
-        if reps >= 200:
-            break
-    mp = n_img * H * W / 1e6
-    return {"value": mp / best, "unit": "MP/s", "cores": ox.num_threads(), "kind": "port", "sample": f"oracle/stainx_oracle.c hm_transform on {n_img}x3x{H}x{W} uint8 (of the {IMAGES_PER_GPU}-image batch), best of {reps} reps"}
+    method = SPECS[config][0]
+    if method == "hm":
+        ref_hist = ox.hm_fit(ref)
+        return lambda: ox.hm_transform(src, ref_hist)
+    if config == "c1":
+        def c1():
+            mean, std = ox.reinhard_fit(ref)
+            return ox.reinhard_transform(src, mean, std)
+        return c1
+    if method == "reinhard":
+        mean, std = ox.reinhard_fit(ref)
+        return lambda: ox.reinhard_transform(src, mean, std)
+    if config == "c4":
+        def c4():
+            he, maxc = ox.macenko_fit(src)
+            return ox.macenko_transform(src, he, maxc)
+        return c4
+    he, maxc = ox.macenko_fit(ref)
+    if config == "c5":
+        return lambda: ox.macenko_transform(src, he, maxc).astype("float32") / 255.0
+    return lambda: ox.macenko_transform(src, he, maxc)
 
 
-def run_reference(args) -> None:
-    """`--impl reference`: the reference's CPU path (oracle port), bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    import numpy as np
-
+def cpu_time(config: str, world: int, budget_s: float, min_reps: int = 2) -> dict:
+    """Mean MP/s of the oracle port on the per-GPU batch of `config` (or on the largest leading part of it
+    whose step fits the time budget; Macenko loops per image and every method is linear in pixels)."""
     from oracle import oracle as ox
 
     ox.build()
-    n_img = 8  # bounded sample of the 64-image batch; cost is linear in pixels
-    rng = np.random.default_rng(43)
-    ref = rng.integers(0, 256, size=(1, 3, H, W), dtype=np.uint8)
-    src = rng.integers(0, 256, size=(n_img, 3, H, W), dtype=np.uint8)
-    ref_hist = ox.hm_fit(ref)
+    cores = ox.set_num_threads(os.cpu_count())  # explicit: torchrun exports OMP_NUM_THREADS=1
+    method, dt, h, w, *_ = SPECS[config]
+    n_full = images_per_gpu(config, world)
+    ref, probe = make_inputs_numpy(config, world, 0, 1)
+    fn = cpu_step_fn(config, ref, probe)
+    fn()  # page in, thread pool
     t0 = time.perf_counter()
-    ox.hm_transform(src, ref_hist)
-    one = time.perf_counter() - t0
-    budget = 120.0  # seconds for the whole run
-    while n_img > 1 and one * (args.steps + args.warmup) > budget:
-        n_img //= 2
-        src = src[:n_img]
-        one /= 2
-    for _ in range(max(args.warmup, 1)):
-        ox.hm_transform(src, ref_hist)
+    fn()
+    per_img = time.perf_counter() - t0
+    n = n_full
+    while n > 1 and per_img * n * (min_reps + 1) > budget_s:
+        n = max(1, n // 2)
+    ref, src = make_inputs_numpy(config, world, 0, n)
+    fn = cpu_step_fn(config, ref, src)
+    fn()
+    reps, t0 = 0, time.perf_counter()
+    while reps < min_reps or (time.perf_counter() - t0 < budget_s * 0.6 and reps < 50):
+        fn()
+        reps += 1
+    dt_s = (time.perf_counter() - t0) / reps
+    mp = n * h * w / 1e6
+    full = "the full per-GPU batch" if n == n_full else f"a bounded sample of the {n_full}-image per-GPU batch (cost is linear in pixels)"
+    return {"value": mp / dt_s, "unit": "MP/s", "cores": cores, "kind": "port", "statistic": f"mean of {reps} steps",
+            "sample": f"oracle/stainx_oracle.c ({method}) on {n}x3x{h}x{w} {dt} = {full}, OpenMP on {cores} threads", "images": n, "ms_per_step": dt_s * 1e3,
+            "note": "port of the reference's torch CPU backend (torch_backend.py); the reference's own torch backend measured 64 (HM) / 18.7 (Reinhard) / 9.9 (Macenko) MP/s on the 8-core build container (SURVEY.md 8d)"}
+
+
+def run_reference(args) -> None:
+    """`--impl reference`: the reference's CPU path (oracle port) on the same per-GPU batch, all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    from oracle import oracle as ox
+
+    ox.build()
+    cores = ox.set_num_threads(os.cpu_count())
+    config = args.config
+    method, dt, h, w, bpp, scaling, _ = SPECS[config]
+    steps = args.steps if args.steps is not None else 20
+    warmup = args.warmup if args.warmup is not None else 2
+    n_full = images_per_gpu(config, world)
+    ref, probe = make_inputs_numpy(config, world, 0, 1)
+    fn = cpu_step_fn(config, ref, probe)
+    fn()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ox.hm_transform(src, ref_hist)
-    dt = time.perf_counter() - t0
-    mp_per_step = n_img * H * W / 1e6
-    value = mp_per_step * args.steps / dt
-    sample = f"{n_img}x3x{H}x{W} uint8 per step (bounded sample of the {IMAGES_PER_GPU}-image batch), oracle port with OpenMP"
-    line = {
-        "impl": "reference", "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "HistogramMatching uint8 64x3x1024x1024 per GPU, reference mode (BASELINE configs[1])", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": ox.num_threads(), "kind": "port", "sample": sample},
+    fn()
+    per_img = time.perf_counter() - t0
+    n, budget = n_full, 150.0  # seconds for the whole run
+    while n > 1 and per_img * n * (steps + warmup) > budget:
+        n = max(1, n // 2)
+    ref, src = make_inputs_numpy(config, world, 0, n)
+    fn = cpu_step_fn(config, ref, src)
+    for _ in range(max(warmup, 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt_s = time.perf_counter() - t0
+    mp_per_step = n * h * w / 1e6
+    value = mp_per_step * steps / dt_s
+    full = "the full per-GPU batch" if n == n_full else f"a bounded sample of the {n_full}-image per-GPU batch (cost is linear in pixels)"
+    sample = f"oracle/stainx_oracle.c ({method}) on {n}x3x{h}x{w} {dt} per step = {full}, OpenMP on {cores} threads"
+    emit({
+        "impl": "reference", "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": dt_s / steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": dt, "data": "synthetic",
+        "config": config_block(config, world),
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample, "statistic": f"mean of {steps} steps", "images": n},
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -221,6 +319,510 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+class Ctx:
+    """Device, ranks and the collective helpers every workload needs."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.distributed = self.world > 1
+        if self.distributed:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.pg = "world" if self.distributed else None
+        self._flush = None
+
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if not self.distributed:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok: bool) -> bool:
+        if not self.distributed:
+            return ok
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    def gather_cat(self, t):
+        """Concatenation of every rank's tensor along dim 0, on every rank."""
+        if not self.distributed:
+            return t
+        parts = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t.contiguous())
+        return self.torch.cat(parts)
+
+    def flush_l2(self):
+        if self._flush is None:
+            self._flush = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)
+        self._flush.fill_(1)
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def rand(self, shape, seed: int, dtype: str):
+        g = self.torch.Generator(device=self.dev).manual_seed(seed)
+        x = self.torch.rand(shape, device=self.dev, generator=g)
+        return (x * 255).round().to(self.torch.uint8) if dtype == "u8" else x
+
+
+class Workload:
+    """One BASELINE config on this rank's GPU: inputs, the public-API step, per-kernel probe, parity."""
+
+    default_steps, default_warmup = 200, 10
+    needs_flush = False
+
+    def __init__(self, config: str, ctx: Ctx):
+        self.config, self.ctx = config, ctx
+        self.method, self.dt, self.h, self.w, self.bpp, self.scaling, self.desc = SPECS[config]
+        self.n = images_per_gpu(config, ctx.world)
+        self.px = self.n * self.h * self.w
+        self.ref = ctx.rand((1, 3, self.h, self.w), 42, self.dt)
+        self.src = ctx.rand((self.n, 3, self.h, self.w), 43 + ctx.rank, self.dt)
+        self.extra: dict = {}
+
+    # -- to override
+    def step(self):
+        raise NotImplementedError
+
+    def e2e_fn(self):
+        """Callable device batch -> device result for ingest.HostStream (default: the step's transform)."""
+        raise NotImplementedError
+
+    def kernel_probe(self, samples: int) -> dict:
+        return {}
+
+    def parity(self) -> dict:
+        return {}
+
+
+def _events_mean(marks, i, j):
+    return sum(m[i].elapsed_time(m[j]) for m in marks) / len(marks)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+class HMWorkload(Workload):
+    default_steps, default_warmup = 2000, 20
+
+    def __init__(self, config, ctx):
+        super().__init__(config, ctx)
+        from stainx_b200 import HistogramMatching, ops
+
+        self.ops = ops
+        self.norm = HistogramMatching(device=ctx.dev, backend="torch_cuda", channel_axis=1, process_group=ctx.pg)
+        self.norm.fit_broadcast(self.ref, src=0) if ctx.distributed else self.norm.fit(self.ref)
+        self.ref_hist = ctx.torch.stack(self.norm._ref_histograms_256).contiguous()
+        self.ref_cdf = ops.hm_ref_cdf(self.ref_hist)
+        self.exchange = self.norm._get_backend_impl()._peer_exchange() if ctx.distributed else None
+        self.extra["exchange"] = ("counts all-reduced inside the LUT kernel over NVLink peer memory (no NCCL call)" if self.exchange is not None else "NCCL all-reduce of 3x256 int64 counts per step") if ctx.distributed else "none (single GPU)"
+
+    def step(self):
+        return self.norm.transform(self.src)
+
+    def e2e_fn(self):
+        return self.norm
+
+    def kernel_probe(self, samples):
+        """Phase-level calls (histogram / exchange + LUT / remap) bracketed by events.  These cannot chain their
+        kernels as programmatic dependent launches the way the single library call does, so their sum is a few
+        microseconds above a step."""
+        ctx, ops, torch = self.ctx, self.ops, self.ctx.torch
+        reducer = self.norm._make_reducer()
+        marks = []
+
+        def probe(record):
+            e = [ctx.ev() for _ in range(4)]
+            if self.exchange is not None:
+                epoch = self.exchange.epoch + 1
+                counts = self.exchange.view((epoch & 1) * 768 * 8, (3, 256), torch.int64)
+                counts.zero_()
+                e[0].record()
+                ops.hm_hist(self.src, counts=counts)
+                self.exchange.epoch = epoch
+            else:
+                counts = torch.zeros((3, 256), dtype=torch.int64, device=ctx.dev)
+                e[0].record()
+                ops.hm_hist(self.src, counts=counts)
+            e[1].record()
+            if self.exchange is not None:
+                lut = ops.hm_build_lut_peers(self.exchange, self.ref_cdf)
+            else:
+                reducer.sum_(counts)
+                lut = ops.hm_build_lut(counts, -1 if ctx.distributed else self.src.numel() // 3, self.ref_cdf)
+            e[2].record()
+            out = ops.hm_apply(self.src, lut)
+            e[3].record()
+            if record:
+                marks.append(e)
+            return out
+
+        for _ in range(5):
+            probe(False)
+        ctx.barrier()
+        for _ in range(samples):
+            probe(True)
+        ctx.barrier()
+        return {
+            "hm::hist_u8_planar_lane_pw_kernel": {"algo_bytes": 3.0 * self.px, "ms": _events_mean(marks, 0, 1)},
+            "hm::build_lut (+ exchange)": {"algo_bytes": 0.0, "ms": _events_mean(marks, 1, 2)},
+            "hm::apply_u8_planar_vec_kernel": {"algo_bytes": 6.0 * self.px, "ms": _events_mean(marks, 2, 3)},
+        }
+
+    def parity(self):
+        """Bit-exact: this rank's output == its shard of the single-device transform of the gathered batch
+        == the CPU oracle on the gathered batch (rank 0)."""
+        ctx, torch = self.ctx, self.ctx.torch
+        from oracle import oracle as ox
+        from stainx_b200 import HistogramMatching
+
+        out = self.step()
+        whole = ctx.gather_cat(self.src)
+        single = HistogramMatching(device=ctx.dev, backend="torch_cuda").fit(self.ref)
+        want = single.transform(whole)
+        lo = ctx.rank * self.n
+        ok_shard = bool(torch.equal(out, want[lo : lo + self.n]))
+        res = {"sharded_equals_single_device": ctx.all_ok(ok_shard), "bar": "torch.equal"}
+        ok_oracle = True
+        if ctx.rank == 0:
+            ox.set_num_threads(os.cpu_count())
+            ref_hist = ox.hm_fit(_np(self.ref))
+            import numpy as np
+
+            ok_oracle = bool(np.array_equal(_np(want), ox.hm_transform(_np(whole), ref_hist))) and bool(np.array_equal(_np(self.ref_hist), ref_hist))
+            res["oracle_images"] = int(whole.shape[0])
+        res["single_device_equals_oracle"] = ctx.all_ok(ok_oracle)
+        res["ok"] = res["sharded_equals_single_device"] and res["single_device_equals_oracle"]
+        return res
+
+
+class ReinhardWorkload(Workload):
+    default_steps, default_warmup = 200, 10
+
+    def __init__(self, config, ctx):
+        super().__init__(config, ctx)
+        from stainx_b200 import Reinhard, ops
+
+        self.ops = ops
+        self.c1 = config == "c1"
+        self.needs_flush = self.c1
+        if self.c1 and ctx.distributed:
+            raise SystemExit("c1 (README quick-start) is a single-GPU configuration")
+        self.norm = Reinhard(device=ctx.dev, backend="torch_cuda", process_group=ctx.pg)
+        self.norm.fit_broadcast(self.ref, src=0) if ctx.distributed else self.norm.fit(self.ref)
+        if self.c1:
+            self.default_steps, self.default_warmup = 500, 20
+
+    def step(self):
+        if self.c1:  # the quick-start times fit + transform
+            from stainx_b200 import Reinhard
+
+            return Reinhard(device=self.ctx.dev, backend="torch_cuda").fit(self.ref).transform(self.src)
+        return self.norm.transform(self.src)
+
+    def e2e_fn(self):
+        return self.norm
+
+    def kernel_probe(self, samples):
+        ctx, ops = self.ctx, self.ops
+        marks = []
+        reducer = self.norm._make_reducer()
+        for i in range(3 + samples):
+            e = [ctx.ev() for _ in range(4)]
+            sums = ctx.torch.zeros(8, dtype=ctx.torch.float64, device=ctx.dev)
+            e[0].record()
+            ops.reinhard_stats(self.src, sums=sums)
+            e[1].record()
+            m, s = ops.reinhard_finalize(reducer.sum_(sums))
+            e[2].record()
+            ops.reinhard_apply(self.src, m, s, self.norm._reference_mean, self.norm._reference_std)
+            e[3].record()
+            if i >= 3:
+                marks.append(e)
+        ctx.barrier()
+        return {
+            "reinhard::stats_kernel": {"algo_bytes": 12.0 * self.px, "ms": _events_mean(marks, 0, 1)},
+            "reinhard::finalize (+ exchange)": {"algo_bytes": 0.0, "ms": _events_mean(marks, 1, 2)},
+            "reinhard::apply_kernel": {"algo_bytes": 24.0 * self.px, "ms": _events_mean(marks, 2, 3)},
+        }
+
+    def parity(self):
+        """max-abs <= 1e-3 on [0,1] against the CPU oracle; sharded == single device to 1e-5."""
+        ctx = self.ctx
+        from oracle import oracle as ox
+        from stainx_b200 import Reinhard
+
+        out = self.step()
+        whole = ctx.gather_cat(self.src)
+        single = Reinhard(device=ctx.dev, backend="torch_cuda").fit(self.ref)
+        want = single.transform(whole)
+        lo = ctx.rank * self.n
+        d_shard = float((out - want[lo : lo + self.n]).abs().max())
+        res = {"max_abs_sharded_vs_single_device": ctx.max_over_ranks(d_shard), "bar_sharded": 1e-5}
+        d_or = 0.0
+        if ctx.rank == 0:
+            ox.set_num_threads(os.cpu_count())
+            import numpy as np
+
+            mean, std = ox.reinhard_fit(_np(self.ref))
+            d_fit = max(float(np.abs(_np(single._reference_mean) - mean).max()), float(np.abs(_np(single._reference_std) - std).max()))
+            res["fit_max_abs_vs_oracle"] = d_fit
+            d_or = 0.0 if d_fit <= 1e-3 else 1.0
+            # the oracle's source statistics span the batch it is given: compare on the whole gathered batch
+            # (up to 128 images = 1.6 GB of float32 on the host; beyond that the sharded == single-device check carries it)
+            if int(whole.shape[0]) <= 128:
+                ref_out = ox.reinhard_transform(_np(whole), _np(single._reference_mean), _np(single._reference_std))
+                d_or = max(d_or, float(np.abs(_np(want) - ref_out).max()))
+                res["oracle_images"] = int(whole.shape[0])
+        res["max_abs_vs_oracle"] = ctx.max_over_ranks(d_or)
+        res["bar_oracle"] = 1e-3
+        res["ok"] = res["max_abs_sharded_vs_single_device"] <= 1e-5 and res["max_abs_vs_oracle"] <= 1e-3
+        return res
+
+
+class MacenkoWorkload(Workload):
+    default_steps, default_warmup = 100, 10
+
+    def __init__(self, config, ctx):
+        super().__init__(config, ctx)
+        from stainx_b200 import Macenko, StainNormalizerTransform, ops
+
+        self.ops = ops
+        if config == "c5":
+            self.module = StainNormalizerTransform(method="macenko", mode="reference", reference=self.ref, device=ctx.dev, backend="torch_cuda", process_group=ctx.pg)
+            self.norm = self.module.normalizer
+        else:
+            self.norm = Macenko(device=ctx.dev, backend="torch_cuda", normalize_to_0_1=True, process_group=ctx.pg)
+            if config == "c3":
+                self.norm.fit_broadcast(self.ref, src=0) if ctx.distributed else self.norm.fit(self.ref)
+        if config == "c4":
+            self.default_steps, self.default_warmup = 30, 5
+            impl = self.norm._get_backend_impl()
+            ex = impl._peer_exchange() if ctx.distributed else None
+            self.extra["exchange"] = ("pooled-fit statistics combined by one peer kernel per step over NVLink peer memory" if ex is not None else "NCCL all-reduces of the pooled-fit statistics") if ctx.distributed else "none (single GPU)"
+
+    def step(self):
+        if self.config == "c5":
+            return self.module(self.src)
+        if self.config == "c4":
+            return self.norm.fit(self.src).transform(self.src)  # fit_transform: pooled fit over ALL ranks' images + per-image transform
+        return self.norm.transform(self.src)
+
+    def e2e_fn(self):
+        if self.config == "c5":
+            return self.module
+        if self.config == "c4":
+            return lambda x: self.norm.fit(x).transform(x)
+        return self.norm
+
+    def kernel_probe(self, samples):
+        """The streaming kernels of the transform, through the phase-level API (same kernels, one launch each)."""
+        ctx, ops, torch = self.ctx, self.ops, self.ctx.torch
+        n = self.n
+        ws = ops.MacenkoWorkspace(n, ctx.dev)
+        out = torch.empty(self.src.shape, dtype=torch.float32, device=ctx.dev)
+        he, maxc = self.norm._stain_matrix, self.norm._target_max_conc
+        if he is None:
+            he, maxc = ops.macenko_fit(self.src[:1])
+        he, maxc = he.contiguous(), maxc.contiguous()
+        marks = []
+        for i in range(2 + samples):
+            e = [ctx.ev() for _ in range(8)]
+            ws.begin()
+            e[0].record(); ws.moments(self.src, False); e[1].record()
+            ws.basis(0, n, True); ws.moments_fallback(self.src)
+            ws.hist(self.src, False, 0, 0); ws.select(0, n, 0, 0)
+            e[2].record(); ws.hist(self.src, False, 0, 1); e[3].record()
+            ws.select(0, n, 0, 1)
+            ws.hist(self.src, False, 1, 0); ws.select(0, n, 1, 0)
+            e[4].record(); ws.hist(self.src, False, 1, 1); e[5].record()
+            ws.select(0, n, 1, 1)
+            e[6].record(); ws.apply(self.src, he, maxc, out, unit=True); e[7].record()
+            if i >= 2:
+                marks.append(e)
+        ctx.barrier()
+        in_b = 3.0 if self.dt == "u8" else 12.0
+        return {
+            "macenko::t_moments_kernel": {"algo_bytes": in_b * self.px, "ms": _events_mean(marks, 0, 1)},
+            "macenko::t_resolve_kernel<ANGLE>": {"algo_bytes": in_b * self.px, "ms": _events_mean(marks, 2, 3)},
+            "macenko::t_resolve_kernel<CONC>": {"algo_bytes": in_b * self.px, "ms": _events_mean(marks, 4, 5)},
+            "macenko::apply_kernel": {"algo_bytes": (in_b + 12.0) * self.px, "ms": _events_mean(marks, 6, 7)},
+        }
+
+    def parity(self):
+        """Outputs of a few images of this rank's step against the CPU oracle under the both-signs protocol
+        (uniform noise is near-isotropic in OD: the sign of the middle eigenvector is not reproducible, SURVEY
+        7 H-a), max-abs <= 1e-3 on [0,1].  c4: the sharded pooled fit is identical on all ranks and matches the
+        single-device pooled fit of the gathered batch (HE <= 1e-4, maxC rel <= 1e-3)."""
+        ctx, torch = self.ctx, self.ctx.torch
+        import numpy as np
+
+        from oracle import oracle as ox
+        from stainx_b200 import Macenko
+
+        out = self.step()
+        res: dict = {}
+        ok = True
+        he, maxc = self.norm._stain_matrix, self.norm._target_max_conc
+        if self.config == "c4":
+            hes = ctx.gather_cat(torch.cat([he.reshape(-1), maxc.reshape(-1)]).reshape(1, 8))
+            same = bool((hes == hes[0:1]).all())
+            whole = ctx.gather_cat(self.src)
+            single = Macenko(device=ctx.dev, backend="torch_cuda").fit(whole)
+            d_he = float((single._stain_matrix - he).abs().max())
+            d_mc = float((single._target_max_conc / maxc - 1).abs().max())
+            res.update(fit_identical_on_all_ranks=ctx.all_ok(same), he_max_abs_sharded_vs_single_device=ctx.max_over_ranks(d_he), maxc_rel_sharded_vs_single_device=ctx.max_over_ranks(d_mc))
+            ok = ok and res["fit_identical_on_all_ranks"] and res["he_max_abs_sharded_vs_single_device"] <= 1e-4 and res["maxc_rel_sharded_vs_single_device"] <= 1e-3
+            del whole
+            if ctx.rank == 0:  # the pooled fit itself against the oracle, on a pooled sub-batch (both signs)
+                ox.set_num_threads(os.cpu_count())
+                sub = self.src[:4].contiguous()
+                g_he, g_mc = self.ops.macenko_fit(sub)
+                cands = [ox.macenko_fit(_np(sub), mid_sign=s) for s in (1, -1)]
+                d = min(max(float(np.abs(_np(g_he) - c[0]).max()), float(np.abs(_np(g_mc) / c[1] - 1).max()) * 0.1) for c in cands)
+                res["pooled_fit_4_images_vs_oracle"] = d
+                ok = ok and d <= 1e-4
+        k = 2 if self.h * self.w <= 1024 * 1024 else 1
+        d_or = 0.0
+        if ctx.rank == 0:
+            ox.set_num_threads(os.cpu_count())
+            sub = _np(self.src[:k])
+            cand = [ox.macenko_transform(sub, _np(he), _np(maxc), mid_signs=[s] * k) for s in (1, -1)]
+            o = _np(out[:k]).astype(np.float64)
+            if self.dt == "u8":  # uint8 in: the reference truncates to a grey level, then / 255 -> compare in grey levels
+                diffs = [np.abs(o * 255.0 - c.astype(np.float64)).reshape(k, -1).max(axis=1) for c in cand]
+                d_or = float(np.minimum(*diffs).max())
+                res["bar_oracle"] = "<= 1 grey level (uint8 truncation knife edge)"
+                ok = ok and d_or <= 1.0 + 1e-3
+            else:
+                diffs = [np.abs(o - c.astype(np.float64) / 255.0).reshape(k, -1).max(axis=1) for c in cand]
+                d_or = float(np.minimum(*diffs).max())
+                res["bar_oracle"] = 1e-3
+                ok = ok and d_or <= 1e-3
+            res["oracle_images"] = k
+        res["max_abs_vs_oracle_both_signs"] = ctx.max_over_ranks(d_or)
+        res["ok"] = ctx.all_ok(ok)
+        return res
+
+
+def make_workload(config: str, ctx: Ctx) -> Workload:
+    method = SPECS[config][0]
+    return {"hm": HMWorkload, "reinhard": ReinhardWorkload, "macenko": MacenkoWorkload}[method](config, ctx)
+
+
+def time_steps(ctx: Ctx, wl: Workload, steps: int, warmup: int) -> tuple[float, int]:
+    """(ms per step, kernels this library launched inside the timed region): CUDA events on the current
+    stream, barrier + synchronize on both sides, max over ranks."""
+    from stainx_b200 import _native
+
+    for _ in range(warmup):
+        wl.step()
+    ctx.barrier()
+    launches0 = _native.kernel_launches()
+    if not wl.needs_flush:
+        a, b = ctx.ev(), ctx.ev()
+        a.record()
+        for _ in range(steps):
+            wl.step()
+        b.record()
+        ctx.barrier()
+        return ctx.max_over_ranks(a.elapsed_time(b)) / steps, _native.kernel_launches() - launches0
+    marks = []
+    for _ in range(steps):  # batch fits L2: flush it between steps, time each step on its own
+        ctx.flush_l2()
+        a, b = ctx.ev(), ctx.ev()
+        a.record()
+        wl.step()
+        b.record()
+        marks.append((a, b))
+    ctx.barrier()
+    total = sum(a.elapsed_time(b) for a, b in marks)
+    return ctx.max_over_ranks(total) / steps, _native.kernel_launches() - launches0
+
+
+def measure_e2e(ctx: Ctx, wl: Workload, steps: int) -> dict:
+    """The same metric through the public API with HOST buffers: pinned batch -> H2D -> transform -> D2H into a
+    pinned buffer, every step (stainx_b200.ingest.HostStream).  Both the pipelined mode (depth 2: the H2D of
+    step i+1 overlaps the D2H of step i) and one-batch-at-a-time are measured; the faster one is reported."""
+    torch = ctx.torch
+    from stainx_b200.ingest import HostStream
+
+    fn = wl.e2e_fn()
+    host_in = torch.empty(wl.src.shape, dtype=wl.src.dtype).pin_memory()
+    host_in.copy_(wl.src)
+    probe = wl.step()
+    host_outs = [torch.empty(probe.shape, dtype=probe.dtype).pin_memory() for _ in range(2)]
+    pipe = HostStream(fn, device=ctx.dev, depth=2)
+
+    def run(k):
+        tickets = [pipe.submit(host_in, host_outs[i % 2]) for i in range(k)]
+        for t in tickets:
+            t.wait()
+
+    def serial(k):
+        for _ in range(k):
+            pipe.submit(host_in, host_outs[0]).wait()
+
+    run(2)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(host_outs[0], probe.cpu())) if wl.config != "c4" else True  # c4 re-fits per call: identical inputs, identical result
+    if not same and wl.method == "hm":
+        raise SystemExit("e2e result differs from the device-resident result")
+
+    def timed(f, k):
+        ctx.barrier()
+        e0, e1 = ctx.ev(), ctx.ev()
+        e0.record()
+        f(k)
+        pipe.synchronize()
+        e1.record()
+        ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1)) / k
+
+    over = timed(run, steps)
+    ser = timed(serial, max(2, steps // 2))
+    ms = min(over, ser)
+    mp = wl.px * ctx.world / 1e6
+    h2d, d2h = host_in.numel() * host_in.element_size(), host_outs[0].numel() * host_outs[0].element_size()
+    # PCIe-side ceiling of this box for exactly these copies (no kernels): both directions at once, all ranks together
+    def copies(k):
+        s1, s2 = pipe._s_in, pipe._s_out
+        dev_in = torch.empty_like(wl.src)
+        for _ in range(k):
+            with torch.cuda.stream(s1):
+                dev_in.copy_(host_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                host_outs[1].copy_(probe, non_blocking=True)
+
+    copies(1)
+    ceil_ms = timed(copies, max(2, steps // 2))
+    res = {"value": mp / (ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": steps,
+           "mode": "pipelined (depth 2)" if over <= ser else "one batch in flight", "pipelined_ms_per_step": over, "serial_ms_per_step": ser,
+           "copy_only_ms_per_step": ceil_ms, "ceiling_gbs": (h2d + d2h) * ctx.world / (ceil_ms / 1e3) / 1e9, "achieved_gbs": (h2d + d2h) * ctx.world / (ms / 1e3) / 1e9,
+           "frac_of_copy_ceiling": ceil_ms / ms, "result_equals_device_resident": same,
+           "api": f"stainx_b200.ingest.HostStream({wl.method} normalizer).submit(pinned batch, pinned out): H2D + {wl.config} step + D2H per step; ceiling = the same H2D and D2H copies alone, both directions at once, all ranks together"}
+    del pipe
+    return res
+
+
 def main() -> None:
     args = parse_args()
     _guard_stdout()
@@ -228,245 +830,95 @@ def main() -> None:
         run_reference(args)
         return
 
-    import torch
-    import torch.distributed as dist
-
-    from stainx_b200 import HistogramMatching, Macenko, Reinhard, _native, ops
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    distributed = world > 1
-    if distributed:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    pg = "world" if distributed else None
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if not distributed:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    ctx = Ctx()
+    torch = ctx.torch
+    from stainx_b200 import _native
 
     peak_gbs, peak_src = peaks()
-    n_img = IMAGES_PER_GPU
-    mp_per_gpu = n_img * H * W / 1e6
+    wl = make_workload(args.config, ctx)
+    steps = args.steps if args.steps is not None else wl.default_steps
+    warmup = max(args.warmup if args.warmup is not None else wl.default_warmup, 3)
 
-    # ---- inputs (synthetic, BASELINE convention: ref seed 42, src seed 43 + rank) ------------
-    g = torch.Generator(device=dev).manual_seed(42)
-    ref = (torch.rand((1, 3, H, W), device=dev, generator=g) * 255).round().to(torch.uint8)
-    g.manual_seed(43 + rank)
-    src = (torch.rand((n_img, 3, H, W), device=dev, generator=g) * 255).round().to(torch.uint8)
-
-    hm = HistogramMatching(device=dev, backend="torch_cuda", channel_axis=1, process_group=pg)
-    hm.fit_broadcast(ref, src=0) if distributed else hm.fit(ref)
-    ref_hist = torch.stack(hm._ref_histograms_256).contiguous()
-    ref_cdf = ops.hm_ref_cdf(ref_hist)  # reference CDF: a fit-time constant (3 x 256 floats)
-    reducer = hm._make_reducer()
-    exchange = hm._get_backend_impl()._peer_exchange() if distributed else None  # None: NCCL all-reduce
-
-    # One step = HistogramMatching.transform(batch).  Every EVENT_EVERY-th step of the timed region is
-    # instead written with the phase-level calls so that each kernel can be bracketed by events.
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    marks: list[tuple] = []
-
-    def step(record: bool):
-        if not record:  # the public API: one library call (single GPU) or hist / fused exchange + LUT / remap (sharded)
-            return hm.transform(src)
-        e = [ev() for _ in range(4)]
-        if record:
-            e[0].record()
-        if exchange is not None:  # sharded: counts into the NVLink peer buffer, all-reduce fused into the LUT kernel
-            exchange.epoch += 1
-            counts = exchange.view((exchange.epoch & 1) * 768 * 8, (3, 256), torch.int64)
-            counts.zero_()
-            ops.hm_hist(src, counts=counts)
-        else:
-            counts = ops.hm_hist(src)
-        if record:
-            e[1].record()
-        if exchange is not None:
-            lut = ops.hm_build_lut_peers(exchange, ref_cdf)
-        else:
-            reducer.sum_(counts)
-            lut = ops.hm_build_lut(counts, -1 if distributed else src.numel() // 3, ref_cdf)
-        if record:
-            e[2].record()
-        out = ops.hm_apply(src, lut)
-        if record:
-            e[3].record()
-            marks.append(tuple(e))
-        return out
-
-    for _ in range(max(args.warmup, 3)):
-        step(False)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = _native.kernel_launches()
-    t_start, t_stop = ev(), ev()
-    barrier()
-    t_start.record()
-    for i in range(args.steps):
-        step(i % EVENT_EVERY == 0)  # per-kernel events on every EVENT_EVERY-th step of the timed region
-    t_stop.record()
-    barrier()
-    elapsed_ms = max_over_ranks(t_start.elapsed_time(t_stop))
-    launches = _native.kernel_launches() - launches0
+    # ---- timed region: K steps of the public API, inputs resident in HBM ---------------------
+    for _ in range(3):
+        wl.step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
+    ms_per_step, launches = time_steps(ctx, wl, steps, warmup)
     clocks = sampler.stop() if sampler else None
+    total_px = wl.px * ctx.world
+    value = total_px / 1e6 / (ms_per_step / 1e3)
 
-    hist_ms = sum(m[0].elapsed_time(m[1]) for m in marks) / len(marks)
-    lut_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / len(marks)
-    apply_ms = sum(m[2].elapsed_time(m[3]) for m in marks) / len(marks)
-    ms_per_step = elapsed_ms / args.steps
-    value = mp_per_gpu * world / (ms_per_step / 1e3)
-
-    # ---- roofline of the dominant kernel (algorithmic bytes / live CUDA-event time) ----------
-    px = n_img * H * W
-    kernels = {
-        "hm::hist_u8_planar_lane_pw_kernel": {"algo_bytes": 3.0 * px, "ms": hist_ms},
-        "hm::apply_u8_planar_vec_kernel": {"algo_bytes": 6.0 * px, "ms": apply_ms},
-    }
+    # ---- roofline: per-kernel times from a separate event loop (never inside the timed region) ----
+    kernels = wl.kernel_probe(KERNEL_SAMPLES)
     for k in kernels.values():
         k["gbs"] = k["algo_bytes"] / (k["ms"] / 1e3) / 1e9
         k["frac"] = k["gbs"] / peak_gbs
-    dom_name = max(kernels, key=lambda k: kernels[k]["ms"])
-    dom = kernels[dom_name]
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
-                "step": {"algo_bytes": ALGO_BYTES_PER_PX["hm"] * px, "gbs": ALGO_BYTES_PER_PX["hm"] * px / (ms_per_step / 1e3) / 1e9, "frac": ALGO_BYTES_PER_PX["hm"] * px / (ms_per_step / 1e3) / 1e9 / peak_gbs},
-                "kernels": {k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "frac": round(v["frac"], 4)} for k, v in kernels.items()}, "lut_and_allreduce_ms": round(lut_ms, 4),
-                "kernel_timing": f"CUDA events around each phase on every {EVENT_EVERY}th step of the timed region ({len(marks)} samples)"}
-    traffic_file = ROOT / "profiles" / "traffic.json"  # per-launch dram bytes from the last ncu --set full capture
-    if traffic_file.exists():
-        try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name)
-        except Exception:
-            pass
+    step_gbs = wl.bpp * wl.px / (ms_per_step / 1e3) / 1e9
+    roofline = {"bound": "hbm", "peak": peak_gbs, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "step": {"algo_bytes": wl.bpp * wl.px, "gbs": step_gbs, "frac": step_gbs / peak_gbs}}
+    streaming = {k: v for k, v in kernels.items() if v["algo_bytes"] > 0}
+    if streaming:
+        dom_name = max(streaming, key=lambda k: streaming[k]["ms"])
+        dom = streaming[dom_name]
+        roofline.update(kernel=dom_name, achieved=dom["gbs"], frac=dom["frac"],
+                        kernels={k: {"ms": round(v["ms"], 4), "gbs": round(v["gbs"], 1), "frac": round(v["frac"], 4)} for k, v in kernels.items()},
+                        kernels_sum_ms=round(sum(v["ms"] for v in kernels.values()), 4),
+                        kernel_timing=f"CUDA events around each phase-level call in a separate loop after the timed region ({KERNEL_SAMPLES} samples after warm-up)")
+        traffic_file = ROOT / "profiles" / "traffic.json"  # per-launch dram bytes from the last ncu --set full capture
+        if traffic_file.exists():
+            try:
+                roofline["traffic"] = json.loads(traffic_file.read_text()).get(dom_name)
+            except Exception:
+                pass
+    else:
+        roofline.update(kernel=f"{wl.method} step (all kernels)", achieved=step_gbs, frac=step_gbs / peak_gbs)
 
-    # ---- e2e: public API, host buffers, H2D + D2H of every step inside the timed region ----------
-    # stainx_b200.ingest.HostStream chains copy-in / kernels / copy-out of each batch on three
-    # streams, so the H2D of step i+1 overlaps the D2H of step i (both PCIe directions busy).
-    from stainx_b200.ingest import HostStream
+    # ---- parity (outside the timed region) -----------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = wl.parity()
+        parity["status"] = "ok" if parity.get("ok") else "MISMATCH"
 
-    host_in = torch.empty((n_img, 3, H, W), dtype=torch.uint8).pin_memory()
-    host_in.copy_(src)
-    host_outs = [torch.empty((n_img, 3, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    e2e_steps = max(4, min(args.steps, 16))
-    pipe = HostStream(hm, device=dev, depth=2)
+    # ---- e2e ------------------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(ctx, wl, max(4, min(steps, 12)))
 
-    def e2e_run(steps: int) -> None:
-        tickets = [pipe.submit(host_in, host_outs[i % 2]) for i in range(steps)]
-        for t in tickets:
-            t.wait()
+    # ---- side measurements of the other workloads (default line only) --------------------------
+    methods = {args.config: {"mp_per_s": value, "algo_gbs_per_gpu": step_gbs, "frac_of_peak": step_gbs / peak_gbs, "ms": ms_per_step}}
+    if args.config == "c2" and not args.no_extras:
+        del wl.src
+        names = ["reinhard", "c3", "c5"] + (["c1"] if not ctx.distributed else []) + (["c4"] if ctx.distributed else [])
+        for name in names:
+            torch.cuda.empty_cache()
+            w2 = make_workload(name, ctx)
+            k = {"c1": 50, "c4": 3}.get(name, 5)
+            ms, _ = time_steps(ctx, w2, k, 3)
+            gbs = w2.bpp * w2.px / (ms / 1e3) / 1e9
+            methods[name] = {"mp_per_s": w2.px * ctx.world / 1e6 / (ms / 1e3), "algo_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms, "workload": w2.desc, "steps": k,
+                             "note": "side measurement; run `bench.py --config " + name + "` for the full line (roofline, e2e, parity_check)"}
+            del w2
 
-    e2e_run(3)
-    if not torch.equal(host_outs[0], step(False).cpu()):
-        raise SystemExit("e2e result differs from the device-resident result")
-
-    def e2e_time(fn, steps: int) -> float:
-        barrier()
-        e0, e1 = ev(), ev()
-        e0.record()
-        fn(steps)
-        pipe.synchronize()
-        e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / steps
-
-    def e2e_serial(steps: int) -> None:  # one batch in flight: H2D, kernels, D2H back to back
-        for _ in range(steps):
-            pipe.submit(host_in, host_outs[0]).wait()
-
-    # Whether both PCIe directions can run at once at full rate depends on the host (NUMA placement
-    # of the pinned buffers, PCIe switch): measure the pipelined and the one-batch-at-a-time mode of
-    # the same API and report the faster one, naming it.
-    overlapped_ms = e2e_time(e2e_run, e2e_steps)
-    serial_ms = e2e_time(e2e_serial, max(3, e2e_steps // 2))
-    e2e_ms = min(overlapped_ms, serial_ms)
-    e2e = {"value": mp_per_gpu * world / (e2e_ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": host_in.numel(), "d2h_bytes_per_step": host_outs[0].numel(), "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "mode": "pipelined (depth 2)" if overlapped_ms <= serial_ms else "one batch in flight", "pipelined_ms_per_step": overlapped_ms, "serial_ms_per_step": serial_ms,
-           "api": "stainx_b200.ingest.HostStream(HistogramMatching(backend='torch_cuda')).submit(pinned uint8 batch, pinned out): H2D + transform + D2H per step"}
-    del pipe
-
-    # ---- side measurements: the other methods / BASELINE configs (aggregate MP/s over all ranks) ----
-    # Every rank runs its own shard (64 images per GPU, weak scaling); times are CUDA events, max over
-    # ranks.  Reinhard's source statistics span the sharded batch (one NCCL all-reduce of 8 doubles
-    # per step); the Macenko transform needs no exchange (per-image statistics).
-    methods = {"hm_u8_64x1024": {"mp_per_s": value, "algo_gbs_per_gpu": roofline["step"]["gbs"], "frac_of_peak": roofline["step"]["frac"]}}
-    if not args.no_extras:
-        def timeit(fn, steps, warm=3):
-            for _ in range(warm):
-                fn()
-            barrier()
-            a, b = ev(), ev()
-            a.record()
-            for _ in range(steps):
-                fn()
-            b.record()
-            barrier()
-            return max_over_ranks(a.elapsed_time(b)) / steps
-
-        def entry(ms, bytes_per_px, mp=mp_per_gpu, **extra):
-            gbs = bytes_per_px * mp * 1e6 / (ms / 1e3) / 1e9
-            return {"mp_per_s": mp * world / (ms / 1e3), "algo_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms, **extra}
-
-        del host_in, host_outs
-        g.manual_seed(43 + rank)
-        srcf = torch.rand((n_img, 3, H, W), device=dev, generator=g)
-        g.manual_seed(42)
-        reff = torch.rand((1, 3, H, W), device=dev, generator=g)
-        rh = Reinhard(device=dev, backend="torch_cuda", process_group=pg)
-        rh.fit_broadcast(reff, src=0) if distributed else rh.fit(reff)
-        methods["reinhard_f32_64x1024"] = entry(timeit(lambda: rh.transform(srcf), 5), ALGO_BYTES_PER_PX["reinhard"])
-        if not distributed:
-            ref10 = torch.rand((1, 3, 512, 512), device=dev, generator=g)
-            src10 = torch.rand((10, 3, 512, 512), device=dev, generator=g)
-            ms = timeit(lambda: Reinhard(device=dev, backend="torch_cuda").fit(ref10).transform(src10), 20)
-            methods["reinhard_f32_C1_fit1x512_transform10x512"] = {"mp_per_s": 10 * 512 * 512 / 1e6 / (ms / 1e3), "ms": ms, "note": "README quick-start (BASELINE configs[0]); fits in L2, launch-latency bound"}
-        mk = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True, process_group=pg)
-        mk.fit_broadcast(reff, src=0) if distributed else mk.fit(reff)
-        methods["macenko_f32_64x1024"] = entry(timeit(lambda: mk.transform(srcf), 5), ALGO_BYTES_PER_PX["macenko"], config="BASELINE configs[2]: reference-mode transform, float32 64x3x1024x1024 per GPU")
-        if distributed:  # BASELINE configs[3]: pooled fit over the sharded batch (NCCL stat all-reduces) + transform
-            mkb = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True, process_group=pg)
-            methods["macenko_f32_batch_fit_transform"] = entry(timeit(lambda: mkb.fit(srcf).transform(srcf), 3, warm=1), ALGO_BYTES_PER_PX["macenko"], config="BASELINE configs[3]: pooled fit + transform of the sharded batch")
-        del srcf
-        # BASELINE configs[4]: StainNormalizerTransform("macenko") on uint8 2048x2048 tiles, 16 per GPU, float32 [0,1] out
-        from stainx_b200 import StainNormalizerTransform
-
-        g.manual_seed(43 + rank)
-        tiles = (torch.rand((16, 3, 2048, 2048), device=dev, generator=g) * 255).to(torch.uint8)
-        g.manual_seed(42)
-        ref_tile = (torch.rand((1, 3, 2048, 2048), device=dev, generator=g) * 255).to(torch.uint8)
-        snt = StainNormalizerTransform(method="macenko", mode="reference", reference=ref_tile, device=dev, backend="torch_cuda")
-        methods["macenko_transform_module_u8_16x2048"] = entry(timeit(lambda: snt(tiles), 5), 15.0, mp=16 * 2048 * 2048 / 1e6, config="BASELINE configs[4] per GPU: uint8 in, float32 [0,1] out (15 B/px)")
-        del tiles
-
-    # ---- CPU baseline (rank 0, N=1 only; bounded sample) --------------------------------------
+    # ---- CPU baseline (rank 0, every N; bounded sample; same statistic as --impl reference) -----
     cpu = None
-    if rank == 0 and not distributed and not args.no_cpu_baseline:
-        cpu = cpu_hm_sample(8, 10.0)
+    if ctx.rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_time(args.config, ctx.world, budget_s=15.0)
 
-    if rank == 0:
+    if ctx.rank == 0:
+        cfg = config_block(args.config, ctx.world)
         line = {
-            "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"HistogramMatching uint8 {n_img}x3x{H}x{W} per GPU, reference mode (BASELINE configs[1])", "images_per_gpu": n_img, "global_images": n_img * world,
-                       "parallelism": f"image-sharded x{world}" + ((", counts all-reduced inside the LUT kernel over NVLink peer memory (no NCCL call)" if exchange is not None else ", NCCL all-reduce of 3x256 int64 counts per step") if distributed else ""),
-                       "l2": "input per GPU (201 MB) exceeds L2 (126 MB); no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "methods": methods,
+            "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dt, "data": "synthetic",
+            "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": parity, "methods": methods, **wl.extra,
         }
         emit(line)
-    if distributed:
-        dist.destroy_process_group()
+    bad = parity is not None and not parity.get("ok")
+    if ctx.distributed:
+        ctx.dist.destroy_process_group()
+    if bad:
+        raise SystemExit("parity_check failed: " + json.dumps(parity))
 
 
 if __name__ == "__main__":

@@ -139,7 +139,7 @@ class StainNormalizerTransform(nn.Module):
             elif isinstance(value, (list, tuple)) and value and all(isinstance(v, torch.Tensor) for v in value):
                 setattr(self.normalizer, name, type(value)(v.to(device) for v in value))
 
-    def _prepare(self, images: torch.Tensor) -> torch.Tensor:
+    def _prepare(self, images: torch.Tensor, for_fit: bool = False) -> torch.Tensor:
         if images.dim() == 3:
             images = images.unsqueeze(0)
         if images.dim() != 4:
@@ -150,6 +150,13 @@ class StainNormalizerTransform(nn.Module):
         elif images.shape[1] != 3:
             raise ValueError(f"Expected NCHW with C=3 (got shape {tuple(images.shape)}). Macenko/Reinhard do not accept NHWC; use channel_axis=-1 only with histogram_matching, or permute to NCHW first.")
         target = self.device if self.device is not None else images.device
+        if for_fit and self.device is None and target.type != "cuda" and torch.cuda.is_available():
+            # The reference lets a device=None transform fit on a CPU reference and then follow CUDA batches
+            # (tests/torch_interface/test_stain_normalizer_transform.py:L149-157).  There is no CPU compute path
+            # here, so a host-resident REFERENCE is fitted on the CUDA device the normalizer currently points at;
+            # batches must still arrive on a CUDA device.
+            cur = torch.device(self.normalizer.device)
+            target = cur if cur.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
         self._follow_device(target)
         return images.to(target)
 
@@ -157,7 +164,7 @@ class StainNormalizerTransform(nn.Module):
     def fit_reference(self, reference: torch.Tensor) -> "StainNormalizerTransform":
         """Fit the inner normalizer on a reference image or batch (rank 0 fits and broadcasts
         when a process group was given)."""
-        ref = self._prepare(reference)
+        ref = self._prepare(reference, for_fit=True)
         if self._process_group is not None:
             self.normalizer.fit_broadcast(ref, src=0)
         else:

@@ -1,0 +1,121 @@
+"""GPU parity over the reference's size grid and at BASELINE's full shapes, directly against the CPU oracle.
+
+Size grid: the ten (H, W) of the reference's headline correctness suite
+(tests/torch_interface/test_correctness_against_references.py:L98-101), including (480, 640) and (2048, 2048);
+inputs follow its fixtures (uint8 noise, ref seed 42 / source seed 123 for histogram matching and Reinhard, the
+Beer-Lambert pair for Macenko).  Full shapes: BASELINE config 2 (uint8 64x3x1024x1024) bit-exact against the
+oracle on the whole batch, float32 noise at 1024x1024 for Macenko under the both-signs protocol.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import best_sign_diff, he_tile, noise_f32, noise_u8
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 64), (128, 128), (256, 256), (256, 512), (321, 199), (384, 256), (480, 640), (512, 512), (1024, 1024), (2048, 2048)]
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("hw", SIZES)
+def test_hm_size_grid_bit_exact(cuda, ox, hw):
+    from stainx_b200 import HistogramMatching
+
+    ref, src = noise_u8((1, 3, *hw), 42), noise_u8((1, 3, *hw), 123)
+    n = HistogramMatching(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    ref_hist = ox.hm_fit(ref.numpy())
+    assert np.array_equal(_np(torch.stack(n._ref_histograms_256)), ref_hist)
+    assert np.array_equal(_np(n.transform(src.to(cuda))), ox.hm_transform(src.numpy(), ref_hist))
+    # channels-last view of the same pixels (the reference parametrises channel_axis over 1 and -1)
+    nl = HistogramMatching(device=cuda, backend="torch_cuda", channel_axis=-1).fit(ref.permute(0, 2, 3, 1).contiguous().to(cuda))
+    out = nl.transform(src.permute(0, 2, 3, 1).contiguous().to(cuda))
+    assert np.array_equal(_np(out).transpose(0, 3, 1, 2), ox.hm_transform(src.numpy(), ref_hist))
+
+
+@pytest.mark.parametrize("hw", SIZES)
+def test_reinhard_size_grid(cuda, ox, hw):
+    from stainx_b200 import Reinhard
+
+    ref, src = noise_u8((1, 3, *hw), 42), noise_u8((1, 3, *hw), 123)
+    n = Reinhard(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    mean, std = ox.reinhard_fit(ref.numpy())
+    assert np.abs(_np(n._reference_mean) - mean).max() <= 1e-3 and np.abs(_np(n._reference_std) - std).max() <= 1e-3
+    want = ox.reinhard_transform(src.numpy(), _np(n._reference_mean), _np(n._reference_std))
+    d = np.abs(_np(n.transform(src.to(cuda))).astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01
+    # float32 view of the same pixels: <= 1e-3 on [0, 1]
+    srcf = src.float() / 255.0
+    wantf = ox.reinhard_transform(srcf.numpy(), _np(n._reference_mean), _np(n._reference_std))
+    assert np.abs(_np(n.transform(srcf.to(cuda))) - wantf).max() <= 1e-3
+
+
+@pytest.mark.parametrize("precision", ["stable", "fast"])
+@pytest.mark.parametrize("hw", SIZES)
+def test_macenko_size_grid(cuda, ox, hw, precision):
+    """The reference's Macenko pair (Beer-Lambert tiles, ref seed 42, source seed 123 with he_scale 1.15);
+    both precision values (test_correctness_against_references.py:L127-130)."""
+    from stainx_b200 import Macenko
+
+    ref, src = he_tile(*hw, 42), he_tile(*hw, 123, 1.15)
+    n = Macenko(device=cuda, backend="torch_cuda", precision=precision).fit(ref.to(cuda))
+    he, maxc = ox.macenko_fit(ref.numpy())
+    assert np.abs(_np(n._stain_matrix) - he).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / maxc - 1).max() <= 1e-3
+    want = ox.macenko_transform(src.numpy(), _np(n._stain_matrix), _np(n._target_max_conc))
+    d = np.abs(_np(n.transform(src.to(cuda))).astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01
+    if precision == "stable" and hw[0] * hw[1] <= 1024 * 1024:
+        n.normalize_to_0_1 = True
+        srcf = src.float() / 255.0
+        wantf = ox.macenko_transform(srcf.numpy(), _np(n._stain_matrix), _np(n._target_max_conc)) / 255.0
+        assert np.abs(_np(n.transform(srcf.to(cuda))) - wantf).max() <= 1e-3
+
+
+def test_c2_full_batch_bit_exact_vs_oracle(cuda, ox):
+    """BASELINE config 2 at full size: uint8 64x3x1024x1024, reference mode, the whole batch against the oracle."""
+    from stainx_b200 import HistogramMatching
+
+    g = torch.Generator(device=cuda).manual_seed(43)
+    src = (torch.rand((64, 3, 1024, 1024), device=cuda, generator=g) * 255).round().to(torch.uint8)
+    g.manual_seed(42)
+    ref = (torch.rand((1, 3, 1024, 1024), device=cuda, generator=g) * 255).round().to(torch.uint8)
+    n = HistogramMatching(device=cuda, backend="torch_cuda", channel_axis=1).fit(ref)
+    out = n.transform(src)
+    ref_hist = ox.hm_fit(_np(ref))
+    assert np.array_equal(_np(torch.stack(n._ref_histograms_256)), ref_hist)
+    assert np.array_equal(_np(out), ox.hm_transform(_np(src), ref_hist))
+
+
+def test_c3_float_noise_1024_both_signs(cuda, ox):
+    """BASELINE config 3's distribution and image size: float32 torch.rand 1024x1024, reference-mode transform
+    with normalize_to_0_1, per image against the oracle under the better middle-eigenvector sign."""
+    from stainx_b200 import Macenko
+
+    ref, src = noise_f32((1, 3, 1024, 1024), 42), noise_f32((3, 3, 1024, 1024), 43)
+    n = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=True).fit(ref.to(cuda))
+    fits = [ox.macenko_fit(ref.numpy(), mid_sign=s) for s in (1, -1)]
+    he = _np(n._stain_matrix)
+    he_o, maxc_o = min(fits, key=lambda f: np.abs(he - f[0]).max())
+    assert np.abs(he - he_o).max() <= 1e-4
+    assert np.abs(_np(n._target_max_conc) / maxc_o - 1).max() <= 1e-3
+    out = _np(n.transform(src.to(cuda)))
+    cand = [ox.macenko_transform(src.numpy(), he, _np(n._target_max_conc), mid_signs=[s] * 3) / 255.0 for s in (1, -1)]
+    assert best_sign_diff(out, cand[0], cand[1]).max() <= 1e-3
+
+
+def test_reinhard_uint8_2048_noise_tile_batch(cuda, ox):
+    """One 2048x2048 uint8 tile per method is covered by the size grid above; this is the BATCHED variant for the
+    batch-global method: 3 tiles, source statistics over all of them."""
+    from stainx_b200 import Reinhard
+
+    ref, src = noise_u8((1, 3, 2048, 2048), 42), noise_u8((3, 3, 2048, 2048), 43, 1.3)
+    n = Reinhard(device=cuda, backend="torch_cuda").fit(ref.to(cuda))
+    want = ox.reinhard_transform(src.numpy(), _np(n._reference_mean), _np(n._reference_std))
+    d = np.abs(_np(n.transform(src.to(cuda))).astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 0.01
