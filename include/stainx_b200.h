@@ -176,7 +176,9 @@ enum sx_macenko_region_id {
     SX_REGION_VMAX = 5,     /* float32 [slots][2][4096]  reduce: MAX */
     SX_REGION_FIT = 6,      /* float32 [slots][8]: HE row-major (6) + maxC (2); read-only result */
     SX_REGION_COUNTERS = 7, /* int64   [slots][8]: rows below the bracket (2), sampled rows (2), pad; reduce: SUM */
-    SX_REGION_STATUS = 8    /* int32   [slots][4]: [0] bit q set = rank q fell outside its bracket (never expected) */
+    SX_REGION_STATUS = 8,   /* int32   [slots][4]: [0] bit q set = rank q fell outside its bracket and was not recovered (never
+                             *           expected); [1] = stages of this slot that sx_macenko_transform re-ran with an exact bracket */
+    SX_REGION_PIPECTRL = 9  /* uint32  [16]: control words of the transform pipeline (tile / role dispensers, development counters) */
 };
 
 int64_t sx_macenko_workspace_bytes(int64_t slots);

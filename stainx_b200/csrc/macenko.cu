@@ -66,7 +66,7 @@ struct SlotState {
 struct PipeCtrl {
     unsigned long long next_tile;  // tile dispenser
     unsigned ticket;               // role dispenser: the first CTAs to start become the service CTAs
-    unsigned pad[13];
+    unsigned pad[61];              // development counters (debug bit 2)
 };
 // Per slot: tiles of phase k that have finished (done[k]) and "phase k may start" flags (ready[k]).
 struct PipeProgress {
@@ -1324,7 +1324,14 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { a
 // CTA-wide: returns once *flag >= want (thread 0 polls with acquire loads; the barrier publishes it).
 __device__ __forceinline__ void wait_counter(const unsigned *flag, unsigned want) {
     if (threadIdx.x == 0) {
-        while (ld_acquire_gpu(flag) < want) __nanosleep(40);
+        // exponential back-off: hundreds of CTAs polling one word every few tens of nanoseconds saturate its L2
+        // slice, and the service CTA that is to set the word queues behind the polls (measured: 35-50 us per
+        // per-image step with a 40 ns poll interval)
+        unsigned ns = 128;
+        while (ld_acquire_gpu(flag) < want) {
+            __nanosleep(ns);
+            if (ns < 2048) ns <<= 1;
+        }
     }
     __syncthreads();
 }
@@ -1366,17 +1373,27 @@ __device__ __forceinline__ void stage_cells(const Ws &ws, int64_t slot, unsigned
 
 // Sample histogram(s) of the stage in v.hist -> brackets in v.st (in-place prefix sums).
 template <typename T, bool VEC, int STAGE>
-__device__ __forceinline__ void sample_and_bracket(const T *image, int64_t hw, ServiceSmem &v, int64_t max_groups, int debug) {
+__device__ __forceinline__ void sample_and_bracket(const T *image, int64_t hw, ServiceSmem &v, int64_t max_groups, int debug, unsigned *dbg = nullptr) {
+    const long long c0 = clock64();
     for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) v.hist[0][i] = 0u;
     if (threadIdx.x == 0) {
         v.s_cnt = 0u;
         v.st.group_px = Pix<T, VEC>::kPix;
     }
     __syncthreads();
+    const long long c1 = clock64();
     sample_slot<T, VEC, STAGE>(image, hw, nullptr, v.st, v.hist, &v.s_cnt, 0, 1, max_groups);
     __syncthreads();
+    const long long c2 = clock64();
     dual_prefix<true>(v.hist[0], STAGE == SX_STAGE_ANGLE ? v.hist[0] : v.hist[1], v.hist);
+    const long long c3 = clock64();
     bracket_from_prefix(STAGE, v.st, v.hist, (long long)v.s_cnt, (long long)v.s_cnt);
+    if (dbg != nullptr && threadIdx.x == 0) {
+        atomicAdd(dbg + 0, (unsigned)((c1 - c0) >> 6));
+        atomicAdd(dbg + 1, (unsigned)((c2 - c1) >> 6));
+        atomicAdd(dbg + 2, (unsigned)((c3 - c2) >> 6));
+        atomicAdd(dbg + 3, (unsigned)((clock64() - c3) >> 6));
+    }
     if (debug & 1) {  // development: an empty bracket far away from the data, so that the rank search misses
         if (threadIdx.x < 2 && max_groups == kSampleGroups) {
             v.st.lo_v[threadIdx.x] = 3.0e30f; v.st.hi_v[threadIdx.x] = 3.1e30f; v.st.inv_w[threadIdx.x] = 0.0f;
@@ -1419,14 +1436,20 @@ __device__ __forceinline__ void select_with_recovery(const Ws &ws, int64_t slot,
 template <typename T, bool VEC>
 __device__ __noinline__ void service_loop(const PipeArgs &a, const Ws &ws, int role, ServiceSmem &v) {
     const T *img = static_cast<const T *>(a.img);
+    long long t_wait = 0, t_work = 0;  // development (debug bit 2): clocks spent waiting / working, reported in ctrl->pad
     for (int64_t i = 0; i < a.n; ++i) {
         const int64_t slot = i;
         const T *image = img + i * 3 * a.hw;
         PipeProgress *pg = ws.progress + slot;
+        const long long c0 = clock64();
         wait_counter(&pg->done[role], (unsigned)a.tpp);
+        const long long c1 = clock64();
+        t_wait += c1 - c0;
+        long long tm[6] = {c1, c1, c1, c1, c1, c1};
         if (role == 0) {
             if (threadIdx.x < 12) v.tot[threadIdx.x] = __ldcg(ws.moments + slot * 12 + threadIdx.x);
             __syncthreads();
+            tm[0] = clock64();
             if (threadIdx.x == 0) {
                 SlotState z = {};
                 v.st = z;
@@ -1435,6 +1458,7 @@ __device__ __noinline__ void service_loop(const PipeArgs &a, const Ws &ws, int r
                 if (!v.st.use_all) basis_from_moments(v.tot, v.st);
             }
             __syncthreads();
+            tm[1] = clock64();
             if (v.st.use_all) {  // fewer than 3 rows pass the mask: every row (L409-410; rare, this CTA re-reads the image)
                 double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
                 float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -1448,13 +1472,17 @@ __device__ __noinline__ void service_loop(const PipeArgs &a, const Ws &ws, int r
                 if (threadIdx.x == 0) basis_from_moments(v.tot, v.st);
                 __syncthreads();
             }
-            sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, a.hw, v, kSampleGroups, a.debug);
+            sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, a.hw, v, kSampleGroups, a.debug, (a.debug & 4) ? ws.ctrl->pad + 24 : nullptr);
+            tm[2] = clock64();
         } else if (role == 1) {
             if (threadIdx.x < 8) v.rg[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
             load_state(&v.st, ws.state + slot);
+            tm[0] = clock64();
             select_with_recovery<T, VEC, SX_STAGE_ANGLE>(ws, slot, image, a.hw, v, a.debug);
             __syncthreads();
-            sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, a.hw, v, kSampleGroups, a.debug);
+            tm[1] = clock64();
+            sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, a.hw, v, kSampleGroups, a.debug, (a.debug & 4) ? ws.ctrl->pad + 28 : nullptr);
+            tm[2] = clock64();
         } else {
             load_state(&v.st, ws.state + slot);
             select_with_recovery<T, VEC, SX_STAGE_CONC>(ws, slot, image, a.hw, v, a.debug);
@@ -1464,6 +1492,17 @@ __device__ __noinline__ void service_loop(const PipeArgs &a, const Ws &ws, int r
         __syncthreads();
         if (threadIdx.x == 0) st_release_gpu(&pg->ready[role + 1], 1u);
         __syncthreads();
+        t_work += clock64() - c1;
+        if ((a.debug & 4) && threadIdx.x == 0 && role < 2) {  // stage timers: load / basis|select / sample+bracket / publish
+            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 0], (unsigned)((tm[0] - c1) >> 6));
+            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 1], (unsigned)((tm[1] - tm[0]) >> 6));
+            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 2], (unsigned)((tm[2] - tm[1]) >> 6));
+            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 3], (unsigned)((clock64() - tm[2]) >> 6));
+        }
+    }
+    if ((a.debug & 4) && threadIdx.x == 0) {
+        ws.ctrl->pad[role * 2] = (unsigned)(t_wait >> 6);
+        ws.ctrl->pad[role * 2 + 1] = (unsigned)(t_work >> 6);
     }
 }
 
@@ -1557,11 +1596,14 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 2) pipeline_ker
     const T *img = static_cast<const T *>(a.img);
     const int64_t groups = a.hw / kPix;
     unsigned long long nxt = 0;
+    long long t_wait = 0, t_tiles = 0;
+    const long long t_begin = clock64();
     if (threadIdx.x == 0) s.tile = (long long)atomicAdd(&ws.ctrl->next_tile, 1ull);
     __syncthreads();
     for (;;) {
         const unsigned long long tile_id = (unsigned long long)s.tile;
         if (tile_id >= a.total_tiles) break;
+        ++t_tiles;
         if (threadIdx.x == 0) nxt = atomicAdd(&ws.ctrl->next_tile, 1ull);  // one ahead: the result is not consumed before the end of this tile
         const unsigned long long e = tile_id / (unsigned)a.tpp;
         const int tile = (int)(tile_id - e * (unsigned)a.tpp);
@@ -1573,7 +1615,11 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 2) pipeline_ker
         const int row0 = tile * a.tile_rows, row1 = min(row0 + a.tile_rows, a.rows_per_img);
         const int64_t g_first = (int64_t)row0 * kThreads;
         const int64_t g_end = (int64_t)row1 * kThreads < groups ? (int64_t)row1 * kThreads : groups;
-        if (k > 0) wait_counter(&pg->ready[k], 1u);
+        if (k > 0) {
+            const long long c0 = clock64();
+            wait_counter(&pg->ready[k], 1u);
+            t_wait += clock64() - c0;
+        }
         if (k == 0) tile_moments<T, VEC>(image, a.hw, g_first, g_end, ws, slot, tile, a.tpp, s);
         else if (k == 1) tile_resolve<T, VEC, SX_STAGE_ANGLE>(image, a.hw, g_first, g_end, ws, slot, s);
         else if (k == 2) tile_resolve<T, VEC, SX_STAGE_CONC>(image, a.hw, g_first, g_end, ws, slot, s);
@@ -1582,6 +1628,12 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 2) pipeline_ker
         __syncthreads();
         if (threadIdx.x == 0) s.tile = (long long)nxt;
         __syncthreads();
+    }
+    if ((a.debug & 4) && threadIdx.x == 0) {  // development: streaming CTAs' clocks waiting for ready flags / in total, tiles taken
+        atomicAdd(&ws.ctrl->pad[8], (unsigned)(t_wait >> 6));
+        atomicAdd(&ws.ctrl->pad[9], (unsigned)((clock64() - t_begin) >> 6));
+        atomicAdd(&ws.ctrl->pad[10], (unsigned)t_tiles);
+        atomicAdd(&ws.ctrl->pad[11], 1u);
     }
 }
 
@@ -1846,9 +1898,9 @@ extern "C" {
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels) {
     if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
-    if (phase_kernels >= 0) {  // bit 0: transform through the phase-level API; bit 1: force bracket misses; bits 4..13: schedule gap; bits 16..23: rows per tile
+    if (phase_kernels >= 0) {  // bit 0: transform through the phase-level API; bits 1..3: pipeline debug flags; bits 4..13: schedule gap; bits 16..23: rows per tile
         g_phase_kernels = (phase_kernels & 1) != 0;
-        g_pipe_debug = (int)((phase_kernels >> 1) & 1);
+        g_pipe_debug = (int)((phase_kernels >> 1) & 7);  // bit 0: force misses; bit 2: timing counters in ctrl->pad
         g_pipe_gap = (int)((phase_kernels >> 4) & 0x3ff);
         g_pipe_tile_rows = (int)((phase_kernels >> 16) & 0xff);
     }
@@ -1870,6 +1922,7 @@ int sx_macenko_region(int64_t slots, int region, int64_t *offset, int64_t *bytes
         case SX_REGION_FIT: *offset = L.fit; *bytes = slots * 8 * 4; break;
         case SX_REGION_COUNTERS: *offset = L.counters; *bytes = slots * 8 * 8; break;
         case SX_REGION_STATUS: *offset = L.status; *bytes = slots * 4 * 4; break;
+        case SX_REGION_PIPECTRL: *offset = L.ctrl; *bytes = (int64_t)sizeof(PipeCtrl); break;
         default: return sx::fail(SX_ERR_INVALID, "unknown region %d", region);
     }
     return SX_OK;

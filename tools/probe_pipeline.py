@@ -27,8 +27,37 @@ PEAK = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]) 
 lib = nv.lib()
 
 
-def tune(phase=0, miss=0, gap=0, rows=0):
-    assert lib.sx_macenko_set_tuning(-1, phase | (miss << 1) | (gap << 4) | (rows << 16)) == 0
+def tune(phase=0, miss=0, gap=0, rows=0, timing=0):
+    assert lib.sx_macenko_set_tuning(-1, phase | (miss << 1) | (timing << 3) | (gap << 4) | (rows << 16)) == 0
+
+
+def timing_report(src, he, maxc, label, **kw):
+    """One transform with the development counters on: where the service and streaming CTAs spend their clocks."""
+    import ctypes
+
+    n, _, h, w = src.shape
+    tune(timing=1, **kw)
+    nbytes = int(lib.sx_macenko_workspace_bytes(n))
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(src.shape, dtype=torch.float32, device=dev)
+    vp = ctypes.c_void_p
+    for _ in range(2):
+        rc = lib.sx_macenko_transform(vp(src.data_ptr()), 0 if src.dtype == torch.uint8 else 1, n, h, w, vp(he.data_ptr()), vp(maxc.data_ptr()), vp(out.data_ptr()), 1, ctypes.c_float(1.0 / 255.0),
+                                      vp(ws.data_ptr()), nbytes, vp(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+    torch.cuda.synchronize()
+    off, size = ctypes.c_int64(), ctypes.c_int64()
+    lib.sx_macenko_region(n, 9, ctypes.byref(off), ctypes.byref(size))
+    pad = ws[off.value : off.value + size.value].view(torch.int32)[3:].cpu().tolist()
+    us = lambda c: c * 64 / 1965.0  # noqa: E731
+    soff, ssize = ctypes.c_int64(), ctypes.c_int64()
+    lib.sx_macenko_region(n, 8, ctypes.byref(soff), ctypes.byref(ssize))
+    status = ws[soff.value : soff.value + ssize.value].view(torch.int32).view(n, 4).cpu()
+    print(f"[{label}] service wait/work us: " + ", ".join(f"k{r}: {us(pad[2*r]):.0f}/{us(pad[2*r+1]):.0f}" for r in range(3)) +
+          " | stage us (load, basis|select, sample+bracket, publish): " + "; ".join("k%d: " % r + "/".join(f"{us(pad[16+4*r+j]):.0f}" for j in range(4)) for r in range(2)) +
+          " | sample_and_bracket us (zero, sample, prefix, bracket): " + "; ".join("/".join(f"{us(pad[24+4*r+j]):.0f}" for j in range(4)) for r in range(2)) +
+          f" | streaming: {pad[11]} CTAs, {pad[10]} tiles, mean wait {us(pad[8])/max(pad[11],1):.0f} us of {us(pad[9])/max(pad[11],1):.0f} us | misses {int(status[:,0].ne(0).sum())}, recovered stages {int(status[:,1].sum())}", flush=True)
+    tune()
 
 
 def timeit(fn, steps=10, warm=3):
@@ -81,6 +110,8 @@ src = torch.rand((64, 3, 1024, 1024), device=dev, generator=g)
 px = 64 * 1024 * 1024
 check("64x1024^2 f32", src, he, maxc, True)
 report("macenko transform f32 64x1024^2 pipeline (default)", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True)), 24 * px)
+timing_report(src, he, maxc, "f32 64x1024^2 default")
+timing_report(src, he, maxc, "f32 64x1024^2 gap 7", gap=7)
 tune(phase=1)
 report("macenko transform f32 64x1024^2 phase chain", timeit(lambda: ops.macenko_transform(src, he, maxc, unit=True)), 24 * px)
 tune()
