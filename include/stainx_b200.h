@@ -219,7 +219,11 @@ int sx_macenko_moments_fallback(const void *images, int dtype, int64_t n, int64_
  * each least-squares concentration row over all rows (M8-M9).  level 0 histograms a 12-bit
  * prefix of a monotone key over a pseudo-random subsample (about 4096 pixel groups per image);
  * level 1 is the full pass: it counts the rows below the bracket chosen by select(.,0), resolves
- * the bracket into 4096 cells and records the exact min/max value of every cell. */
+ * the bracket into 4096 cells and records the exact min/max value of every cell.
+ * level 2 = level 0 over EVERY pixel group: select(.,0) after it yields an exact bracket (the coarse bin of
+ * the wanted rank).  It is the recovery of a missed sample bracket (STATUS region): sx_macenko_transform and
+ * sx_macenko_fit run it inside their rank-search kernels for the slots that need it; a sharded fit repeats
+ * the stage with it (stainx_b200/backends/torch_cuda_backend.py). */
 int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int pooled,
                     int64_t slot0, int stage, int level, void *workspace, int64_t slots,
                     sx_stream_t stream);

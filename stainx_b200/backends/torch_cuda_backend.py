@@ -251,14 +251,20 @@ class MacenkoCUDA(TorchCUDABackendBase):
                 self._scratch = torch.empty(int(_native.lib().sx_macenko_peer_scratch_bytes()), dtype=torch.uint8, device=self.device)
         return self._exchange or None
 
-    def _pooled_fit_sharded(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    def _pooled_fit_sharded(self, images: torch.Tensor, exact: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
         """Pooled fit of a sharded reference batch: every rank streams its own images into slot 0 of
         its workspace; before each per-slot step the statistics of all ranks are combined -- in ONE
         kernel over NVLink peer memory when the group can map it (``sx_macenko_peer_combine``), else
-        with NCCL all-reduces -- so every rank derives bit-identical HE / maxC."""
+        with NCCL all-reduces -- so every rank derives bit-identical HE / maxC.
+
+        The brackets of the rank searches come from a ~1/64 subsample (``hist`` level 0).  Should a wanted
+        rank fall outside its bracket (STATUS region, identical on every rank because it derives from the
+        combined statistics), the fit is repeated with ``exact=True``: level 2 histograms every pixel group,
+        which makes the bracket certain.  The check costs one host read per fit."""
         red = self._reducer
         ex = self._peer_exchange()
         ws = self._ops.MacenkoWorkspace(1, images.device, buffer=ex.buf) if ex is not None else self._ops.MacenkoWorkspace(1, images.device)
+        coarse = 2 if exact else 0
 
         def combine(which: int) -> None:
             if ex is not None:
@@ -282,7 +288,7 @@ class MacenkoCUDA(TorchCUDABackendBase):
         ws.basis(0, 1, allow_fallback=False)
         for stage in (_native.SX_STAGE_ANGLE, _native.SX_STAGE_CONC):
             if images.shape[0] > 0:
-                ws.hist(images, True, stage, 0)   # subsample pass
+                ws.hist(images, True, stage, coarse)  # subsample pass (exact: every pixel group)
             combine(1)
             ws.select(0, 1, stage, 0)             # ranks + brackets, identical on every rank
             if images.shape[0] > 0:
@@ -290,7 +296,13 @@ class MacenkoCUDA(TorchCUDABackendBase):
             combine(2)
             ws.select(0, 1, stage, 1)
         fit = ws.region("fit")[0]
-        return fit[:6].reshape(3, 2).clone(), fit[6:8].clone()
+        he, maxc = fit[:6].reshape(3, 2).clone(), fit[6:8].clone()
+        missed = int(ws.region("status")[0, 0].item()) & 3
+        if missed:
+            if exact:
+                raise _native.StainxNativeError("Macenko pooled fit: a rank fell outside an exact bracket (inconsistent statistics across ranks?)")
+            return self._pooled_fit_sharded(images, exact=True)
+        return he, maxc
 
     def transform(self, images: torch.Tensor, stain_matrix: torch.Tensor, target_max_conc: torch.Tensor, normalize_to_0_1: bool = False) -> torch.Tensor:
         images, original = self._to_native(images)

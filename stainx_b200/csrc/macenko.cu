@@ -62,20 +62,8 @@ struct SlotState {
     int miss;             // a wanted rank fell outside its bracket in the last resolve (also in STATUS)
 };
 
-// Control words of the persistent transform pipeline (sx_macenko_transform), per workspace.
-struct PipeCtrl {
-    unsigned long long next_tile;  // tile dispenser
-    unsigned ticket;               // role dispenser: the first CTAs to start become the service CTAs
-    unsigned pad[61];              // development counters (debug bit 2)
-};
-// Per slot: tiles of phase k that have finished (done[k]) and "phase k may start" flags (ready[k]).
-struct PipeProgress {
-    unsigned done[4];
-    unsigned ready[4];
-};
-
 struct Layout {
-    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, ctrl, progress, sched, hist3, vmin3, vmax3, total;
+    int64_t moments, odrange, hist1, hist2, vmin, vmax, fit, counters, status, state, total;
     __host__ __device__ explicit Layout(int64_t slots) {
         int64_t o = 0;
         moments = o;  o += slots * 12 * 8;
@@ -88,13 +76,6 @@ struct Layout {
         fit = o;      o += slots * 8 * 4;
         status = o;   o += slots * 4 * 4;
         state = (o + 15) / 16 * 16; o = state + slots * (int64_t)sizeof(SlotState);
-        // pipeline-only regions (behind the regions of the phase-level API, whose offsets they leave alone)
-        ctrl = (o + 63) / 64 * 64;  o = ctrl + (int64_t)sizeof(PipeCtrl);
-        progress = o; o += slots * (int64_t)sizeof(PipeProgress);
-        sched = o;    o += slots * 4 * 4;
-        hist3 = (o + 15) / 16 * 16; o = hist3 + slots * 2 * kBins * 4;  // cells of the CONC stage (the pipeline keeps both stages' cells apart: no re-arming between them)
-        vmin3 = o;    o += slots * 2 * kBins * 4;
-        vmax3 = o;    o += slots * 2 * kBins * 4;
         total = (o + 255) / 256 * 256;
     }
 };
@@ -108,10 +89,6 @@ struct Ws {
     int *status;                   // [slot][4]: [0] bit q set = rank of query q fell outside its bracket;
                                    // [1..3] CTAs of the slot's image that finished moments / resolve(ANGLE) / resolve(CONC)
     SlotState *state;
-    PipeCtrl *ctrl;
-    PipeProgress *progress;
-    unsigned *sched, *hist3;
-    float *vmin3, *vmax3;
     __host__ __device__ Ws(void *base, int64_t slots) {
         Layout L(slots);
         char *b = static_cast<char *>(base);
@@ -125,12 +102,6 @@ struct Ws {
         fit = reinterpret_cast<float *>(b + L.fit);
         status = reinterpret_cast<int *>(b + L.status);
         state = reinterpret_cast<SlotState *>(b + L.state);
-        ctrl = reinterpret_cast<PipeCtrl *>(b + L.ctrl);
-        progress = reinterpret_cast<PipeProgress *>(b + L.progress);
-        sched = reinterpret_cast<unsigned *>(b + L.sched);
-        hist3 = reinterpret_cast<unsigned *>(b + L.hist3);
-        vmin3 = reinterpret_cast<float *>(b + L.vmin3);
-        vmax3 = reinterpret_cast<float *>(b + L.vmax3);
     }
 };
 
@@ -533,7 +504,7 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
 // The offsets depend only on the window index: an image's result does not depend on where in
 // the batch it sits.
 template <typename T, bool VEC, int STAGE>
-__global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+__global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ img, PassGeom g, int pooled, int64_t slot0, void *ws_base, int64_t slots, int64_t max_groups) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     constexpr int kQ = (STAGE == SX_STAGE_CONC) ? 2 : 1;
     __shared__ float tab[256];
@@ -555,7 +526,7 @@ __global__ void __launch_bounds__(kThreads) sample_kernel(const T *__restrict__ 
 
     const T *image = img + n * 3 * g.hw;
     const int64_t groups = g.hw / kPix;
-    const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
+    const int64_t stride = groups / max_groups > 1 ? groups / max_groups : 1;  // max_groups >= groups: every group (level 2, exact)
     const int64_t nsamp = groups / stride;
     unsigned cnt = 0;
     for (int64_t i = (int64_t)chunk * kThreads + threadIdx.x; i < nsamp; i += (int64_t)g.cpi * kThreads) {
@@ -721,7 +692,7 @@ __device__ __noinline__ void sample_slot(const T *__restrict__ image, int64_t hw
     constexpr int kPix = Pix<T, VEC>::kPix;
     constexpr int kBatch = 4;
     const int64_t groups = hw / kPix;
-    const int64_t stride = groups / max_groups > 1 ? groups / max_groups : 1;  // max_groups >= groups: every group ("exact" coarse pass)
+    const int64_t stride = groups / max_groups > 1 ? groups / max_groups : 1;  // max_groups >= groups: every group (the exact coarse pass of a recovery)
     const int64_t nsamp = groups / stride;
     const RankParams rp(st);
     const float c_lo0 = st.c_lo[0], c_lo1 = st.c_lo[1], c_sc0 = st.c_scale[0], c_sc1 = st.c_scale[1];
@@ -888,6 +859,17 @@ __device__ void bracket_from_prefix(int stage, SlotState &st, unsigned (*pre)[kB
     __syncthreads();
 }
 
+// Development (SX_ENABLE_TUNING, sx_macenko_set_tuning bit 1): every SAMPLE bracket is replaced by an empty one far
+// away from the data, so that the rank search misses and the exact recovery path runs (tests of that path).
+__device__ int g_force_miss = 0;
+__device__ __forceinline__ void maybe_force_miss(SlotState &st) {
+    if (g_force_miss && threadIdx.x < 2) {
+        st.lo_v[threadIdx.x] = 3.0e30f; st.hi_v[threadIdx.x] = 3.1e30f; st.inv_w[threadIdx.x] = 0.0f;
+        st.open_lo[threadIdx.x] = st.open_hi[threadIdx.x] = 0;
+    }
+    __syncthreads();
+}
+
 // The same from the global sample histograms of the phase-level API.
 __device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, unsigned (*pre)[kBins]) {
     const unsigned *h = ws.hist1 + slot * 2 * kBins;
@@ -896,6 +878,8 @@ __device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &s
     const long long m0 = (long long)__ldcg(ws.counters + slot * 8 + 2);
     const long long m1 = stage == SX_STAGE_ANGLE ? m0 : (long long)__ldcg(ws.counters + slot * 8 + 3);
     bracket_from_prefix(stage, st, pre, m0, m1);
+    if (m0 < (stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all)) maybe_force_miss(st);  // never an exact (whole-slot) bracket
+    else __syncthreads();
 }
 
 // Cooperative copy of a slot's state between global memory (through L2) and shared memory.
@@ -924,14 +908,14 @@ __global__ void __launch_bounds__(kThreads) bracket_kernel(void *ws_base, int64_
 
 // After the full pass: the order statistics; (ANGLE) HE, pinv, concentration maps; (CONC) maxC.
 // `rg` = per-channel (-min l, max l) of the slot (global odrange, or the state's copy); sets st.miss.
-// `h2` / `vmin` / `vmax`: the slot's cells of this stage (2 x kBins each), `below`: its two rows-below counters.
-__device__ void select_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, const float *rg, unsigned (*pre)[kBins], const unsigned *h2, const float *cell_min, const float *cell_max, const unsigned long long *below) {
+__device__ void select_slot(const Ws &ws, int64_t slot, int stage, SlotState &st, const float *rg, unsigned (*pre)[kBins]) {
+    const int64_t base = slot * 2 * kBins;
     if (threadIdx.x == 0) st.miss = 0;
-    dual_prefix<false>(h2, h2 + kBins, pre);
+    dual_prefix<false>(ws.hist2 + base, ws.hist2 + base + kBins, pre);
     if ((threadIdx.x & 127) == 0) {  // threads 0 and 128: one query each
         const int q = threadIdx.x >> 7;
         const long long inside = (long long)pre[q][kBins - 1];
-        long long k = st.rank[q] - (long long)__ldcg(below + q);
+        long long k = st.rank[q] - (long long)__ldcg(ws.counters + slot * 8 + q);
         if (k < 0 || k >= inside) {  // the rank fell outside the bracket (not expected): nearest edge
             atomicOr(&ws.status[slot * 4], 1 << q);
             st.miss = 1;
@@ -940,7 +924,7 @@ __device__ void select_slot(const Ws &ws, int64_t slot, int stage, SlotState &st
         const int cell = bin_of_rank(pre[q], k);
         const long long before = cell > 0 ? (long long)pre[q][cell - 1] : 0;
         const long long cnt = (long long)pre[q][cell] - before;
-        const float lo = __ldcg(cell_min + q * kBins + cell), hi = __ldcg(cell_max + q * kBins + cell);
+        const float lo = __ldcg(ws.vmin + base + q * kBins + cell), hi = __ldcg(ws.vmax + base + q * kBins + cell);
         float v = lo;
         if (cnt > 1 && hi > lo) v = lo + (hi - lo) * __fdiv_rn((float)(k - before), (float)(cnt - 1));
         st.val[q] = v;
@@ -1001,9 +985,89 @@ __global__ void __launch_bounds__(kThreads) select_kernel(void *ws_base, int64_t
     const int64_t base = slot * 2 * kBins;
     if (threadIdx.x < 8) rg[threadIdx.x] = ws.odrange[slot * 8 + threadIdx.x];
     load_state(&st, ws.state + slot);
-    select_slot(ws, slot, stage, st, rg, pre, ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
+    select_slot(ws, slot, stage, st, rg, pre);
     store_state(ws.state + slot, &st);
     if (stage == SX_STAGE_ANGLE) {  // re-arm the slot's histograms and counters for the CONC stage
+        for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+            ws.hist1[base + i] = 0u;
+            ws.hist2[base + i] = 0u;
+            ws.vmin[base + i] = INFINITY;
+            ws.vmax[base + i] = -INFINITY;
+        }
+        if (threadIdx.x < 8) ws.counters[slot * 8 + threadIdx.x] = 0ull;
+    }
+}
+
+// ---- deterministic recovery of a missed bracket ---------------------------------------------------
+// The sample bracket holds the wanted rank with probability ~1 - 1e-10 per query for independent
+// pixels; structured images can defeat any sampling argument, so a miss must not end in a clamped
+// answer.  When select_slot reports a miss, the SAME CTA re-does the stage for its slot exactly:
+// coarse histogram over EVERY pixel group of the slot's image(s) (sample_slot with stride 1), bracket =
+// the coarse bin of the wanted rank plus one guard bin per side (bracket_from_prefix, m >= n branch),
+// cells re-armed, full resolve pass by this CTA, rank search again.  Slow (one CTA streams the slot
+// twice) and never expected to run; status[slot][3] counts the stages that took this path.
+// `pre` (2 x kBins words) serves as histogram, prefix sums and then as the hit queue of the resolve pass.
+static_assert(sizeof(ResolveSmem) <= sizeof(unsigned) * 2 * kBins, "the recovery pass keeps its hit queue in the histogram array");
+
+template <typename T, bool VEC, int STAGE>
+__device__ __noinline__ void recover_stage(const T *__restrict__ img, int64_t n_img, int64_t hw, const Ws &ws, int64_t slot, SlotState &st, const float *rg, unsigned (*pre)[kBins], unsigned *s_cnt) {
+    const int64_t base = slot * 2 * kBins;
+    if (STAGE == SX_STAGE_ANGLE && threadIdx.x == 0) {  // select(ANGLE) has replaced the projection maps by the concentration maps
+        float e0[3], e1[3];
+        for (int i = 0; i < 3; ++i) { e0[i] = st.e[i * 2]; e1[i] = st.e[i * 2 + 1]; }
+        od_map_to_l(e0, st.proj);
+        od_map_to_l(e1, st.proj + 4);
+    }
+    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) pre[0][i] = 0u;
+    if (threadIdx.x == 0) *s_cnt = 0u;
+    __syncthreads();
+    for (int64_t k = 0; k < n_img; ++k) sample_slot<T, VEC, STAGE>(img + k * 3 * hw, hw, nullptr, st, pre, s_cnt, 0, 1, (int64_t)1 << 62);
+    __syncthreads();
+    const long long m = (long long)*s_cnt;
+    dual_prefix<true>(pre[0], STAGE == SX_STAGE_ANGLE ? pre[0] : pre[1], pre);
+    bracket_from_prefix(STAGE, st, pre, m, m);  // m == n: exact bracket
+    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
+        ws.hist2[base + i] = 0u;
+        ws.vmin[base + i] = INFINITY;
+        ws.vmax[base + i] = -INFINITY;
+    }
+    if (threadIdx.x < 2) ws.counters[slot * 8 + threadIdx.x] = 0ull;
+    __threadfence();
+    __syncthreads();
+    ResolveSmem &rs = *reinterpret_cast<ResolveSmem *>(&pre[0][0]);
+    for (int64_t k = 0; k < n_img; ++k) {
+        resolve_pass<T, VEC, STAGE>(img + k * 3 * hw, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, nullptr, st, rs, ws.hist2 + base, ws.vmin + base, ws.vmax + base, ws.counters + slot * 8);
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAnd(&ws.status[slot * 4], ~3);  // the exact pass decides
+        atomicAdd(&ws.status[slot * 4 + 3], 1);
+    }
+    __syncthreads();
+    select_slot(ws, slot, STAGE, st, rg, pre);
+    __syncthreads();
+}
+
+// select_kernel with the recovery path: one CTA per slot; `pooled` != 0: the slot pools all n_img images (fit),
+// else slot slot0 + blockIdx.x belongs to image blockIdx.x (transform).
+template <typename T, bool VEC, int STAGE>
+__global__ void __launch_bounds__(kThreads) select_recover_kernel(const T *__restrict__ img, int64_t n_img, int64_t hw, int pooled, int64_t slot0, void *ws_base, int64_t slots) {
+    __shared__ __align__(16) unsigned pre[2][kBins];
+    __shared__ SlotState st;
+    __shared__ float rg[8];
+    __shared__ unsigned s_cnt;
+    Ws ws(ws_base, slots);
+    const int64_t slot = slot0 + blockIdx.x;
+    const int64_t base = slot * 2 * kBins;
+    if (threadIdx.x < 8) rg[threadIdx.x] = ws.odrange[slot * 8 + threadIdx.x];
+    load_state(&st, ws.state + slot);
+    select_slot(ws, slot, STAGE, st, rg, pre);
+    __syncthreads();
+    if (st.miss) recover_stage<T, VEC, STAGE>(pooled ? img : img + (int64_t)blockIdx.x * 3 * hw, pooled ? n_img : 1, hw, ws, slot, st, rg, pre, &s_cnt);
+    store_state(ws.state + slot, &st);
+    if (STAGE == SX_STAGE_ANGLE) {  // re-arm the slot's histograms and counters for the CONC stage
         for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) {
             ws.hist1[base + i] = 0u;
             ws.hist2[base + i] = 0u;
@@ -1046,7 +1110,7 @@ __device__ __forceinline__ void apply_coefficients(float *coef, const float *__r
 
 // Streams the groups first, first + stride, ... of one image through the reconstruction.
 template <typename T, bool VEC, int OUT>
-__device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__restrict__ out_image, int64_t hw, int64_t first, int64_t stride, const float *tab, const float *unit_tab, const float *coef, int64_t groups_end = -1) {
+__device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__restrict__ out_image, int64_t hw, int64_t first, int64_t stride, const float *tab, const float *unit_tab, const float *coef) {
     constexpr int kPix = Pix<T, VEC>::kPix;
     float A[3][4];
 #pragma unroll
@@ -1055,7 +1119,7 @@ __device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__
         for (int k = 0; k < 4; ++k) A[c][k] = coef[c * 4 + k];
     const float top = (OUT == 2 && sizeof(T) == 4) ? 1.0f : 255.0f;  // clamp(.., 0, 255) (L459)
 
-    stream_groups<T, VEC>(image, hw, groups_end >= 0 ? groups_end : hw / kPix, first, stride, tab, [&](const float(&l)[3][kPix], int64_t gi) {
+    stream_groups<T, VEC>(image, hw, hw / kPix, first, stride, tab, [&](const float(&l)[3][kPix], int64_t gi) {
         float o[3][kPix];
 #pragma unroll
         for (int k = 0; k < kPix; ++k)
@@ -1210,27 +1274,116 @@ __global__ void __launch_bounds__(kThreads) t_resolve_kernel(const T *__restrict
     }
 }
 
+// Shared memory of the per-image kernels.
+struct MidSmem {
+    SlotState st;
+    unsigned s_cnt;
+    int s_last;
+    double tot[12];
+};
+
+// Per-image step before a resolve pass, kMidParts CTAs per image: (ANGLE only: basis M3-M4 and the
+// masked-row fallback L409-410, computed redundantly by every CTA of the image -- identical inputs,
+// identical results), then each CTA samples its share of the image's sample groups into a
+// shared-memory histogram and adds it to the slot's global sample histogram; the CTA that arrives
+// last turns the histogram into the brackets of the stage and stores the slot's state.
+constexpr int kMidParts = 8;
+
+template <typename T, bool VEC, int STAGE>
+__global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img, int64_t hw, int64_t slot0, void *ws_base, int64_t slots) {
+    __shared__ MidSmem ms;
+    __shared__ double red[kThreads / 32][10];
+    __shared__ __align__(16) unsigned hist[2][kBins];
+    Ws ws(ws_base, slots);
+    const int64_t slot = slot0 + blockIdx.x / kMidParts;
+    const int part = blockIdx.x % kMidParts;
+    const T *image = img + (int64_t)(blockIdx.x / kMidParts) * 3 * hw;
+    const int64_t base = slot * 2 * kBins;
+    if constexpr (STAGE == SX_STAGE_ANGLE) {
+        if (threadIdx.x < 10) ms.tot[threadIdx.x] = ws.moments[slot * 12 + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            SlotState z = {};
+            ms.st = z;
+            ms.st.n_all = (long long)hw;
+            ms.st.use_all = ms.tot[0] < 3.0;
+            if (!ms.st.use_all) basis_from_moments(ms.tot, ms.st);
+        }
+        __syncthreads();
+        if (ms.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
+            double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+            moments_stream<T, VEC, false>(image, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, nullptr, acc, lo, hi);
+            block_sum10(acc, red);
+            if (threadIdx.x < 10) ms.tot[threadIdx.x] = acc[0];
+            __syncthreads();
+            if (threadIdx.x == 0) basis_from_moments(ms.tot, ms.st);
+            __syncthreads();
+        }
+    } else {
+        load_state(&ms.st, ws.state + slot);
+    }
+    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) hist[0][i] = 0u;
+    if (threadIdx.x == 0) {
+        ms.s_cnt = 0u;
+        ms.st.group_px = Pix<T, VEC>::kPix;
+    }
+    __syncthreads();
+    sample_slot<T, VEC, STAGE>(image, hw, nullptr, ms.st, hist, &ms.s_cnt, part, kMidParts);
+    __syncthreads();
+    constexpr int kQ = STAGE == SX_STAGE_CONC ? 2 : 1;
+    for (int i = threadIdx.x; i < kQ * kBins; i += kThreads)
+        if (hist[0][i]) atomicAdd(&ws.hist1[base + i], hist[0][i]);
+    if (threadIdx.x == 0 && ms.s_cnt) {
+        atomicAdd(&ws.counters[slot * 8 + 2], (unsigned long long)ms.s_cnt);
+        if (kQ == 2) atomicAdd(&ws.counters[slot * 8 + 3], (unsigned long long)ms.s_cnt);
+    }
+    __threadfence();  // this thread's global atomics are visible before the arrival below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ms.s_last = atomicAdd(&ws.status[slot * 4 + 1 + STAGE], 1) == kMidParts - 1;
+        __threadfence();
+    }
+    __syncthreads();
+    if (!ms.s_last) return;
+    if (STAGE == SX_STAGE_ANGLE && threadIdx.x < 11) {  // the moments the basis was computed from (fallback: every row)
+        if (ms.st.use_all && threadIdx.x < 10) ws.moments[slot * 12 + threadIdx.x] = ms.tot[threadIdx.x];
+        if (threadIdx.x == 10) ws.moments[slot * 12 + 10] = (double)hw;
+    }
+    bracket_slot(ws, slot, STAGE, ms.st, hist);
+    store_state(ws.state + slot, &ms.st);
+}
+
 // uint8 in, float32 out (OUT 1: [0,255], OUT 2: [0,1]): FOUR pixels per thread.  With 16 pixels per
 // thread each lane would store 64 contiguous bytes per plane, i.e. every 128-bit store of a warp
 // hits 32 different half-filled sectors (measured: 3.3 TB/s); with 4 pixels a warp's store is one
 // contiguous 512-byte run, exactly like the float32 path, and its load one 128-byte run.
-// Pixels [4 * g_first, 4 * g_end) of one image, groups of FOUR pixels: g_first + threadIdx.x, + stride, ...
 template <int OUT>
-__device__ __forceinline__ void apply_u8_f32_range(const uint8_t *__restrict__ image, float *__restrict__ oimg, int64_t hw, int64_t g_first, int64_t g_end, int64_t stride, const float *coef) {
+__global__ void __launch_bounds__(kThreads) apply_u8_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, PassGeom g, int64_t slot0, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, void *ws_base, int64_t slots) {
+    __shared__ float coef[12];
+    Ws ws(ws_base, slots);
+    const int64_t n = blockIdx.x / g.cpi;
+    const int chunk = blockIdx.x % g.cpi;
+    const int64_t slot = slot0 + n;
+    apply_coefficients<float, 1>(coef, he_ref, maxc_ref, ws.state[slot].pinv, ws.fit[slot * 8 + 6], ws.fit[slot * 8 + 7]);
+    __syncthreads();
     float A[3][4];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int k = 0; k < 4; ++k) A[c][k] = coef[c * 4 + k];
-    int64_t gi = g_first + threadIdx.x;
+    const uint8_t *image = img + n * 3 * g.hw;
+    float *oimg = out + n * 3 * g.hw;
+    const int64_t groups = g.hw / 4, stride = (int64_t)g.cpi * kThreads;
+    int64_t gi = (int64_t)chunk * kThreads + threadIdx.x;
     unsigned cur[3] = {0u, 0u, 0u}, nxt[3] = {0u, 0u, 0u};
     auto load = [&](int64_t i, unsigned (&w)[3]) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w[c]) : "l"(image + c * hw + i * 4));
+        for (int c = 0; c < 3; ++c) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(w[c]) : "l"(image + c * g.hw + i * 4));
     };
-    if (gi < g_end) load(gi, cur);
-    for (; gi < g_end; gi += stride) {
-        if (gi + stride < g_end) load(gi + stride, nxt);
+    if (gi < groups) load(gi, cur);
+    for (; gi < groups; gi += stride) {
+        if (gi + stride < groups) load(gi + stride, nxt);
         float l[3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { l[c][0] = u8_l<0>(cur[c]); l[c][1] = u8_l<1>(cur[c]); l[c][2] = u8_l<2>(cur[c]); l[c][3] = u8_l<3>(cur[c]); }
@@ -1243,423 +1396,10 @@ __device__ __forceinline__ void apply_u8_f32_range(const uint8_t *__restrict__ i
                 const float q = trunc_small(fminf(fast_ex2(e), 255.0f));  // the reference truncates to uint8 first (L560)
                 o[k] = OUT == 2 ? div255_exact(q) : q;
             }
-            st_stream(reinterpret_cast<float4 *>(oimg + c * hw + gi * 4), make_float4(o[0], o[1], o[2], o[3]));
+            st_stream(reinterpret_cast<float4 *>(oimg + c * g.hw + gi * 4), make_float4(o[0], o[1], o[2], o[3]));
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) cur[c] = nxt[c];
-    }
-}
-
-template <int OUT>
-__global__ void __launch_bounds__(kThreads) apply_u8_f32_kernel(const uint8_t *__restrict__ img, float *__restrict__ out, PassGeom g, int64_t slot0, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, void *ws_base, int64_t slots) {
-    __shared__ float coef[12];
-    Ws ws(ws_base, slots);
-    const int64_t n = blockIdx.x / g.cpi;
-    const int chunk = blockIdx.x % g.cpi;
-    const int64_t slot = slot0 + n;
-    apply_coefficients<float, 1>(coef, he_ref, maxc_ref, ws.state[slot].pinv, ws.fit[slot * 8 + 6], ws.fit[slot * 8 + 7]);
-    __syncthreads();
-    apply_u8_f32_range<OUT>(img + n * 3 * g.hw, out + n * 3 * g.hw, g.hw, (int64_t)chunk * kThreads, g.hw / 4, (int64_t)g.cpi * kThreads, coef);
-}
-
-// ---- persistent per-image transform pipeline ----------------------------------------------------
-// sx_macenko_transform = pipeline_init_kernel + ONE persistent kernel.
-//
-// Why: an image passes through four dependent streaming phases (M moments, R1 angle resolve, R2
-// concentration resolve, A reconstruction) with a small per-image step between them.  Run as four
-// batch-wide kernels, every phase re-reads the whole batch from HBM (4 reads + 1 write = 60 B/px against
-// 24 B/px algorithmic for float32).  Here the phases of DIFFERENT images are interleaved in one tile
-// stream so that the phases of ONE image follow each other within a few microseconds: the image (12.6 MB
-// for 1024^2 float32) is still in L2 when R1, R2 and A read it again (measured on this B200: a working
-// set re-read by all SMs stays L2-resident up to ~32 MB, profiles/r02_l2probe.md), and HBM sees one read
-// and one write per pixel.
-//
-// Tile stream: entry e of the schedule table = (image i, phase k); phase k of image i sits at slot
-// 4 i + k g (g odd: the residues k g mod 4 are distinct, so the slots tile the line without collisions),
-// i.e. dependent phases of an image are g slots apart -- g - 1 phases of OTHER images are handed out in
-// between, which is the slack that hides the per-image step and the CTAs still finishing the phase.
-// Slots whose image index falls outside the batch (pipeline fill / drain) are compacted away by
-// pipeline_init_kernel.  A phase is cut into tiles of `tile_rows` rows (row = kThreads pixel groups);
-// streaming CTAs take tiles from one global counter in schedule order (next tile fetched one ahead).
-//
-// Roles are handed out by a ticket at kernel start: the first three CTAs to RUN become the service CTAs
-// (one per dependency: after M, after R1, after R2), everybody else streams.  Service CTA k walks the
-// images in order: waits until all tiles of phase k of image i are done (done[k] counter, acquire),
-// performs the per-image step (k = 0: covariance -> eigenvectors, angle sample + bracket; k = 1: angle
-// rank search -> HE, pinv, concentration sample + brackets; k = 2: concentration rank search -> maxC)
-// and releases ready[k + 1].  A streaming CTA holding a tile of phase k > 0 waits for ready[k].
-// Deadlock freedom: tiles are handed out in schedule order and every wait is for work that was handed
-// out EARLIER to a CTA that is already running (M tiles never wait; roles and tiles are only ever taken
-// by running CTAs, so nothing depends on a CTA that is not resident).
-//
-// The slot's cell arrays are zeroed by the M tiles of the image itself (each tile a 1/tpp share), the
-// two stages use separate cell arrays (hist2/vmin/vmax and hist3/vmin3/vmax3), so there is no batch-wide
-// initialisation pass and no re-arming between the stages.
-//
-// Deterministic recovery: when a wanted rank falls outside its sample bracket (probability ~1e-10 per
-// query for independent pixels; structured images can defeat any sampling argument), the service CTA
-// re-does that stage for that image by itself with an EXACT bracket: coarse histogram over every pixel
-// group, bracket = the coarse bin of the wanted rank (+ one guard bin per side), full resolve pass.
-struct PipeArgs {
-    const void *img;
-    void *out;
-    int64_t n, hw;
-    const float *he_ref, *maxc_ref;
-    void *ws;
-    int tpp;        // tiles per phase
-    int tile_rows;  // rows per tile
-    int rows_per_img;
-    int debug;      // development (SX_ENABLE_TUNING): bit 0 forces every sample bracket to miss
-    unsigned long long total_tiles;
-};
-
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
-// CTA-wide: returns once *flag >= want (thread 0 polls with acquire loads; the barrier publishes it).
-__device__ __forceinline__ void wait_counter(const unsigned *flag, unsigned want) {
-    if (threadIdx.x == 0) {
-        // exponential back-off: hundreds of CTAs polling one word every few tens of nanoseconds saturate its L2
-        // slice, and the service CTA that is to set the word queues behind the polls (measured: 35-50 us per
-        // per-image step with a 40 ns poll interval)
-        unsigned ns = 128;
-        while (ld_acquire_gpu(flag) < want) {
-            __nanosleep(ns);
-            if (ns < 2048) ns <<= 1;
-        }
-    }
-    __syncthreads();
-}
-// CTA-wide: everything this CTA wrote (plain stores, atomics) becomes visible, then *flag += / = v.
-__device__ __forceinline__ void publish_add(unsigned *flag, unsigned v) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) red_release_gpu_add(flag, v);
-}
-
-struct StreamSmem {
-    SlotState st;
-    ResolveSmem rs;
-    double red[kThreads / 32][10];
-    float redf[kThreads / 32][2];
-    float coef[12];
-    long long tile;
-};
-struct ServiceSmem {
-    SlotState st;
-    unsigned s_cnt;
-    float rg[8];
-    double tot[12];
-    double red[kThreads / 32][10];
-    __align__(16) unsigned hist[2][kBins];  // sample histograms / prefix sums; the hit queue of a recovery pass aliases it
-};
-union PipeSmem {
-    StreamSmem s;
-    ServiceSmem v;
-};
-static_assert(sizeof(ResolveSmem) <= sizeof(unsigned) * 2 * kBins, "the recovery pass keeps its hit queue in the histogram array");
-
-template <int STAGE>
-__device__ __forceinline__ void stage_cells(const Ws &ws, int64_t slot, unsigned *&h2, float *&cmin, float *&cmax, unsigned long long *&below) {
-    const int64_t base = slot * 2 * kBins;
-    if (STAGE == SX_STAGE_ANGLE) { h2 = ws.hist2 + base; cmin = ws.vmin + base; cmax = ws.vmax + base; below = ws.counters + slot * 8; }
-    else { h2 = ws.hist3 + base; cmin = ws.vmin3 + base; cmax = ws.vmax3 + base; below = ws.counters + slot * 8 + 4; }
-}
-
-// Sample histogram(s) of the stage in v.hist -> brackets in v.st (in-place prefix sums).
-template <typename T, bool VEC, int STAGE>
-__device__ __forceinline__ void sample_and_bracket(const T *image, int64_t hw, ServiceSmem &v, int64_t max_groups, int debug, unsigned *dbg = nullptr) {
-    const long long c0 = clock64();
-    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) v.hist[0][i] = 0u;
-    if (threadIdx.x == 0) {
-        v.s_cnt = 0u;
-        v.st.group_px = Pix<T, VEC>::kPix;
-    }
-    __syncthreads();
-    const long long c1 = clock64();
-    sample_slot<T, VEC, STAGE>(image, hw, nullptr, v.st, v.hist, &v.s_cnt, 0, 1, max_groups);
-    __syncthreads();
-    const long long c2 = clock64();
-    dual_prefix<true>(v.hist[0], STAGE == SX_STAGE_ANGLE ? v.hist[0] : v.hist[1], v.hist);
-    const long long c3 = clock64();
-    bracket_from_prefix(STAGE, v.st, v.hist, (long long)v.s_cnt, (long long)v.s_cnt);
-    if (dbg != nullptr && threadIdx.x == 0) {
-        atomicAdd(dbg + 0, (unsigned)((c1 - c0) >> 6));
-        atomicAdd(dbg + 1, (unsigned)((c2 - c1) >> 6));
-        atomicAdd(dbg + 2, (unsigned)((c3 - c2) >> 6));
-        atomicAdd(dbg + 3, (unsigned)((clock64() - c3) >> 6));
-    }
-    if (debug & 1) {  // development: an empty bracket far away from the data, so that the rank search misses
-        if (threadIdx.x < 2 && max_groups == kSampleGroups) {
-            v.st.lo_v[threadIdx.x] = 3.0e30f; v.st.hi_v[threadIdx.x] = 3.1e30f; v.st.inv_w[threadIdx.x] = 0.0f;
-            v.st.open_lo[threadIdx.x] = v.st.open_hi[threadIdx.x] = 0;
-        }
-        __syncthreads();
-    }
-}
-
-// Rank search of the stage; on a miss, the exact re-run of the stage for this image by this CTA.
-template <typename T, bool VEC, int STAGE>
-__device__ __forceinline__ void select_with_recovery(const Ws &ws, int64_t slot, const T *image, int64_t hw, ServiceSmem &v, int debug) {
-    unsigned *h2; float *cmin, *cmax; unsigned long long *below;
-    stage_cells<STAGE>(ws, slot, h2, cmin, cmax, below);
-    SlotState before;
-    if (STAGE == SX_STAGE_ANGLE && threadIdx.x == 0) before = v.st;  // select(ANGLE) overwrites proj with the concentration maps
-    select_slot(ws, slot, STAGE, v.st, v.rg, v.hist, h2, cmin, cmax, below);
-    __syncthreads();
-    if (!v.st.miss) return;
-    if (STAGE == SX_STAGE_ANGLE && threadIdx.x == 0) {
-        for (int i = 0; i < 8; ++i) v.st.proj[i] = before.proj[i];
-    }
-    __syncthreads();
-    sample_and_bracket<T, VEC, STAGE>(image, hw, v, (int64_t)1 << 62, 0);  // every group: exact coarse bracket
-    for (int i = threadIdx.x; i < 2 * kBins; i += kThreads) { h2[i] = 0u; cmin[i] = INFINITY; cmax[i] = -INFINITY; }
-    if (threadIdx.x < 2) below[threadIdx.x] = 0ull;
-    __threadfence();
-    __syncthreads();
-    ResolveSmem &rs = *reinterpret_cast<ResolveSmem *>(&v.hist[0][0]);
-    resolve_pass<T, VEC, STAGE>(image, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, nullptr, v.st, rs, h2, cmin, cmax, below);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAnd(&ws.status[slot * 4], ~3);  // the exact pass below decides
-    __syncthreads();
-    select_slot(ws, slot, STAGE, v.st, v.rg, v.hist, h2, cmin, cmax, below);
-    if (threadIdx.x == 0) atomicAdd(&ws.status[slot * 4 + 1], 1);  // [1]: stages of this slot that needed the exact re-run
-    __syncthreads();
-}
-
-template <typename T, bool VEC>
-__device__ __noinline__ void service_loop(const PipeArgs &a, const Ws &ws, int role, ServiceSmem &v) {
-    const T *img = static_cast<const T *>(a.img);
-    long long t_wait = 0, t_work = 0;  // development (debug bit 2): clocks spent waiting / working, reported in ctrl->pad
-    for (int64_t i = 0; i < a.n; ++i) {
-        const int64_t slot = i;
-        const T *image = img + i * 3 * a.hw;
-        PipeProgress *pg = ws.progress + slot;
-        const long long c0 = clock64();
-        wait_counter(&pg->done[role], (unsigned)a.tpp);
-        const long long c1 = clock64();
-        t_wait += c1 - c0;
-        long long tm[6] = {c1, c1, c1, c1, c1, c1};
-        if (role == 0) {
-            if (threadIdx.x < 12) v.tot[threadIdx.x] = __ldcg(ws.moments + slot * 12 + threadIdx.x);
-            __syncthreads();
-            tm[0] = clock64();
-            if (threadIdx.x == 0) {
-                SlotState z = {};
-                v.st = z;
-                v.st.n_all = (long long)a.hw;
-                v.st.use_all = v.tot[0] < 3.0;
-                if (!v.st.use_all) basis_from_moments(v.tot, v.st);
-            }
-            __syncthreads();
-            tm[1] = clock64();
-            if (v.st.use_all) {  // fewer than 3 rows pass the mask: every row (L409-410; rare, this CTA re-reads the image)
-                double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-                moments_stream<T, VEC, false>(image, a.hw, a.hw / Pix<T, VEC>::kPix, 0, kThreads, nullptr, acc, lo, hi);
-                block_sum10(acc, v.red);
-                if (threadIdx.x < 10) {
-                    v.tot[threadIdx.x] = acc[0];
-                    ws.moments[slot * 12 + threadIdx.x] = acc[0];
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) basis_from_moments(v.tot, v.st);
-                __syncthreads();
-            }
-            sample_and_bracket<T, VEC, SX_STAGE_ANGLE>(image, a.hw, v, kSampleGroups, a.debug, (a.debug & 4) ? ws.ctrl->pad + 24 : nullptr);
-            tm[2] = clock64();
-        } else if (role == 1) {
-            if (threadIdx.x < 8) v.rg[threadIdx.x] = __ldcg(ws.odrange + slot * 8 + threadIdx.x);
-            load_state(&v.st, ws.state + slot);
-            tm[0] = clock64();
-            select_with_recovery<T, VEC, SX_STAGE_ANGLE>(ws, slot, image, a.hw, v, a.debug);
-            __syncthreads();
-            tm[1] = clock64();
-            sample_and_bracket<T, VEC, SX_STAGE_CONC>(image, a.hw, v, kSampleGroups, a.debug, (a.debug & 4) ? ws.ctrl->pad + 28 : nullptr);
-            tm[2] = clock64();
-        } else {
-            load_state(&v.st, ws.state + slot);
-            select_with_recovery<T, VEC, SX_STAGE_CONC>(ws, slot, image, a.hw, v, a.debug);
-        }
-        store_state(ws.state + slot, &v.st);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_gpu(&pg->ready[role + 1], 1u);
-        __syncthreads();
-        t_work += clock64() - c1;
-        if ((a.debug & 4) && threadIdx.x == 0 && role < 2) {  // stage timers: load / basis|select / sample+bracket / publish
-            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 0], (unsigned)((tm[0] - c1) >> 6));
-            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 1], (unsigned)((tm[1] - tm[0]) >> 6));
-            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 2], (unsigned)((tm[2] - tm[1]) >> 6));
-            atomicAdd(&ws.ctrl->pad[16 + role * 4 + 3], (unsigned)((clock64() - tm[2]) >> 6));
-        }
-    }
-    if ((a.debug & 4) && threadIdx.x == 0) {
-        ws.ctrl->pad[role * 2] = (unsigned)(t_wait >> 6);
-        ws.ctrl->pad[role * 2 + 1] = (unsigned)(t_work >> 6);
-    }
-}
-
-// The three tile bodies are separate (non-inlined) functions: each gets the kernel's whole register budget for
-// its streaming loop, and the tile loop's own state is saved around the call once per tile instead of being
-// spilled inside the loops.
-template <typename T, bool VEC>
-__device__ __noinline__ void tile_moments(const T *__restrict__ image, int64_t hw, int64_t g_first, int64_t g_end, const Ws &ws, int64_t slot, int tile, int tpp, StreamSmem &s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    moments_stream<T, VEC, true>(image, hw, g_end, g_first, kThreads, nullptr, acc, lo, hi);
-    {
-        const float x = warp_max(-lo[0]), y = warp_max(hi[0]);
-        if (lane == 0) { s.redf[warp][0] = x; s.redf[warp][1] = y; }
-    }
-    block_sum10(acc, s.red);
-    if (threadIdx.x < 10) {
-        if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
-    } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
-        const int j = threadIdx.x - 32;  // [0..2] = -min l (one range for the three channels), [3..5] = max l
-        float m = -INFINITY;
-        for (int w = 0; w < kThreads / 32; ++w) m = fmaxf(m, s.redf[w][j / 3]);
-        atomic_max_f32(&ws.odrange[slot * 8 + j], m);
-    }
-    // this tile's share of the slot's cell arrays: 6 arrays x 2 kBins words = 6 x 2048 uint4 per slot
-    constexpr int kVecs = 6 * 2 * kBins / 4;
-    const int per = (kVecs + tpp - 1) / tpp;
-    const int v0 = tile * per, v1 = min(v0 + per, kVecs);
-    const int64_t base = slot * 2 * kBins;
-    for (int j = v0 + threadIdx.x; j < v1; j += kThreads) {
-        const int which = j / (2 * kBins / 4), at = j - which * (2 * kBins / 4);
-        void *arr = which == 0 ? (void *)(ws.hist2 + base) : which == 1 ? (void *)(ws.vmin + base) : which == 2 ? (void *)(ws.vmax + base) : which == 3 ? (void *)(ws.hist3 + base) : which == 4 ? (void *)(ws.vmin3 + base) : (void *)(ws.vmax3 + base);
-        const unsigned fill = (which % 3 == 0) ? 0u : (which % 3 == 1 ? 0x7f800000u : 0xff800000u);  // 0, +inf, -inf
-        static_cast<uint4 *>(arr)[at] = make_uint4(fill, fill, fill, fill);
-    }
-}
-
-template <typename T, bool VEC, int STAGE>
-__device__ __noinline__ void tile_resolve(const T *__restrict__ image, int64_t hw, int64_t g_first, int64_t g_end, const Ws &ws, int64_t slot, StreamSmem &s) {
-    load_state(&s.st, ws.state + slot);
-    unsigned *h2; float *cmin, *cmax; unsigned long long *below;
-    stage_cells<STAGE>(ws, slot, h2, cmin, cmax, below);
-    resolve_pass<T, VEC, STAGE>(image, hw, g_end, g_first, kThreads, nullptr, s.st, s.rs, h2, cmin, cmax, below);
-}
-
-template <typename T, bool VEC, int OUT>
-__device__ __noinline__ void tile_apply(const T *__restrict__ image, void *__restrict__ out_image, int64_t hw, int64_t g_first, int64_t g_end, const Ws &ws, int64_t slot, const float *__restrict__ he_ref, const float *__restrict__ maxc_ref, StreamSmem &s) {
-    constexpr int kPix = Pix<T, VEC>::kPix;
-    if (threadIdx.x < 3) {
-        const float *pinv = ws.state[slot].pinv;  // written by a service CTA during this kernel: read through L2
-        float pv[6];
-        for (int j = 0; j < 6; ++j) pv[j] = __ldcg(pinv + j);
-        const float maxc0 = __ldcg(ws.fit + slot * 8 + 6), maxc1 = __ldcg(ws.fit + slot * 8 + 7);
-        const int c = threadIdx.x;
-        const float n0 = __fdiv_rn(maxc_ref[0], maxc0), n1 = __fdiv_rn(maxc_ref[1], maxc1);  // L452
-        float sum = 0.0f;
-        for (int j = 0; j < 3; ++j) {
-            const float m = he_ref[c * 2] * n0 * pv[j] + he_ref[c * 2 + 1] * n1 * pv[3 + j];
-            s.coef[c * 4 + j] = m;
-            sum += m;
-        }
-        float bias = kLog2_240 * (1.0f - sum);
-        if (OUT == 2 && sizeof(T) == 4) bias -= 7.994353436858858f;  // log2(255): fold the /255
-        s.coef[c * 4 + 3] = bias;
-    }
-    __syncthreads();
-    if constexpr (sizeof(T) == 1 && OUT != 0 && VEC) {
-        // uint8 -> float32: four pixels per thread (see apply_u8_f32_kernel)
-        apply_u8_f32_range<OUT>(reinterpret_cast<const uint8_t *>(image), static_cast<float *>(out_image), hw, g_first * (kPix / 4), g_end * (kPix / 4), kThreads, s.coef);
-    } else {
-        apply_pass<T, VEC, OUT>(image, out_image, hw, g_first, kThreads, nullptr, nullptr, s.coef, g_end);
-    }
-}
-
-template <typename T, bool VEC, int OUT>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 2) pipeline_kernel(const PipeArgs a) {
-    constexpr int kPix = Pix<T, VEC>::kPix;
-    __shared__ __align__(16) unsigned char smem_raw[sizeof(PipeSmem)];
-    __shared__ int s_role;
-    PipeSmem &sm = *reinterpret_cast<PipeSmem *>(smem_raw);
-    const Ws ws(a.ws, a.n);
-    if (threadIdx.x == 0) s_role = (int)atomicAdd(&ws.ctrl->ticket, 1u);
-    __syncthreads();
-    const int role = s_role;
-    if (role < 3) {
-        service_loop<T, VEC>(a, ws, role, sm.v);
-        return;
-    }
-    StreamSmem &s = sm.s;
-    const T *img = static_cast<const T *>(a.img);
-    const int64_t groups = a.hw / kPix;
-    unsigned long long nxt = 0;
-    long long t_wait = 0, t_tiles = 0;
-    const long long t_begin = clock64();
-    if (threadIdx.x == 0) s.tile = (long long)atomicAdd(&ws.ctrl->next_tile, 1ull);
-    __syncthreads();
-    for (;;) {
-        const unsigned long long tile_id = (unsigned long long)s.tile;
-        if (tile_id >= a.total_tiles) break;
-        ++t_tiles;
-        if (threadIdx.x == 0) nxt = atomicAdd(&ws.ctrl->next_tile, 1ull);  // one ahead: the result is not consumed before the end of this tile
-        const unsigned long long e = tile_id / (unsigned)a.tpp;
-        const int tile = (int)(tile_id - e * (unsigned)a.tpp);
-        const unsigned entry = __ldcg(ws.sched + e);
-        const int64_t i = entry >> 2, slot = i;
-        const int k = (int)(entry & 3u);
-        const T *image = img + i * 3 * a.hw;
-        PipeProgress *pg = ws.progress + slot;
-        const int row0 = tile * a.tile_rows, row1 = min(row0 + a.tile_rows, a.rows_per_img);
-        const int64_t g_first = (int64_t)row0 * kThreads;
-        const int64_t g_end = (int64_t)row1 * kThreads < groups ? (int64_t)row1 * kThreads : groups;
-        if (k > 0) {
-            const long long c0 = clock64();
-            wait_counter(&pg->ready[k], 1u);
-            t_wait += clock64() - c0;
-        }
-        if (k == 0) tile_moments<T, VEC>(image, a.hw, g_first, g_end, ws, slot, tile, a.tpp, s);
-        else if (k == 1) tile_resolve<T, VEC, SX_STAGE_ANGLE>(image, a.hw, g_first, g_end, ws, slot, s);
-        else if (k == 2) tile_resolve<T, VEC, SX_STAGE_CONC>(image, a.hw, g_first, g_end, ws, slot, s);
-        else tile_apply<T, VEC, OUT>(image, static_cast<char *>(a.out) + i * 3 * a.hw * (OUT == 0 ? 1 : 4), a.hw, g_first, g_end, ws, slot, a.he_ref, a.maxc_ref, s);
-        if (k < 3) publish_add(&pg->done[k], 1u);
-        __syncthreads();
-        if (threadIdx.x == 0) s.tile = (long long)nxt;
-        __syncthreads();
-    }
-    if ((a.debug & 4) && threadIdx.x == 0) {  // development: streaming CTAs' clocks waiting for ready flags / in total, tiles taken
-        atomicAdd(&ws.ctrl->pad[8], (unsigned)(t_wait >> 6));
-        atomicAdd(&ws.ctrl->pad[9], (unsigned)((clock64() - t_begin) >> 6));
-        atomicAdd(&ws.ctrl->pad[10], (unsigned)t_tiles);
-        atomicAdd(&ws.ctrl->pad[11], 1u);
-    }
-}
-
-// Zeroes the small per-slot statistics and the pipeline's control words, and builds the schedule table
-// (see "persistent per-image transform pipeline").  One thread per schedule slot / per statistic word.
-__global__ void pipeline_init_kernel(void *ws_base, int64_t n, int gap) {
-    Ws ws(ws_base, n);
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n * 12) ws.moments[t] = 0.0;
-    if (t < n * 8) { ws.odrange[t] = -INFINITY; ws.fit[t] = 0.0f; ws.counters[t] = 0ull; reinterpret_cast<unsigned *>(ws.progress)[t] = 0u; }
-    if (t < n * 4) ws.status[t] = 0;
-    if (t < (int64_t)(sizeof(PipeCtrl) / 4)) reinterpret_cast<unsigned *>(ws.ctrl)[t] = 0u;
-    const int64_t slots_total = 4 * (n - 1) + 3 * (int64_t)gap + 1;
-    if (t < slots_total) {
-        const int64_t q = t;
-        const int k = (int)((q * gap) & 3);
-        const int64_t num = q - (int64_t)k * gap;
-        if (num >= 0 && (num >> 2) < n) {
-            int64_t rank = 0;
-            for (int kk = 0; kk < 4; ++kk) {
-                int64_t c = (q - (int64_t)kk * gap + 3) >> 2;  // images i >= 0 with 4 i + kk g < q
-                c = c < 0 ? 0 : (c > n ? n : c);
-                rank += c;
-            }
-            ws.sched[rank] = (unsigned)((num >> 2) << 2) | (unsigned)k;
-        }
     }
 }
 
@@ -1781,6 +1521,7 @@ __global__ void init_kernel(void *ws_base, int64_t slots) {
 
 static int g_ctas_per_sm = 8;  // per-image kernels (sample, reconstruction): CTAs per SM the grid is sized for.  The reconstruction of
                                // 64 x 1024^2 float32 takes 259 us with 3 or 8 and 283 us with 4 (640 CTAs = 4.3 per SM: uneven last wave)
+static int g_split = 3;          // chains (streams) a large batch is split into
 static int g_phase_kernels = 0;  // development: sx_macenko_transform through the phase-level API (one launch per step)
 
 static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_override = -1) {
@@ -1849,47 +1590,51 @@ static bool images_vec_ok(const void *images, const void *out, int dtype, int64_
     return in_ok && (out == nullptr || aligned16(out));
 }
 
-// Launch of the persistent pipeline for images [0, n) -> slots [0, n) on `stream` (two launches).
-static int g_pipe_gap = 0;        // development: dependency distance in schedule slots (0: chosen from the geometry)
-static int g_pipe_tile_rows = 0;  // development: rows per tile (0: default)
-static int g_pipe_debug = 0;      // development: bit 0 forces every sample bracket to miss (exercises the exact recovery)
+extern "C" int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, sx_stream_t stream_);
 
-template <typename T, bool VEC, int OUT>
-static int launch_pipeline(const void *images, int64_t n, int64_t hw, const float *he_ref, const float *maxc_ref, void *out, void *workspace, cudaStream_t stream) {
-    auto kernel = pipeline_kernel<T, VEC, OUT>;
-    PipeArgs a;
-    a.img = images;
-    a.out = out;
-    a.n = n;
-    a.hw = hw;
-    a.he_ref = he_ref;
-    a.maxc_ref = maxc_ref;
-    a.ws = workspace;
-    a.debug = g_pipe_debug;
-    const int64_t groups = hw / Pix<T, VEC>::kPix;
-    const int64_t rows = (groups + kThreads - 1) / kThreads;
-    SX_REQUIRE(rows < ((int64_t)1 << 30), "image too large for the tile schedule");
-    a.rows_per_img = (int)rows;
-    a.tile_rows = g_pipe_tile_rows > 0 ? g_pipe_tile_rows : 2;
-    a.tpp = (int)((rows + a.tile_rows - 1) / a.tile_rows);
-    a.total_tiles = (unsigned long long)n * 4ull * (unsigned long long)a.tpp;
-    int per_sm = 0;
-    prefer_l1(kernel, kThreads);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int64_t resident = (int64_t)per_sm * sm_count();
-    int64_t grid = (int64_t)a.total_tiles + 3 < resident ? (int64_t)a.total_tiles + 3 : resident;
-    if (grid < 4) grid = 4;
-    // Dependent phases of an image are `gap` schedule slots apart: the slots the streaming CTAs span at any
-    // moment plus two slots of slack for the per-image step, made odd (see the schedule's comment).
-    int gap = g_pipe_gap > 0 ? g_pipe_gap : (int)((grid + a.tpp - 1) / a.tpp) + 2;
-    if (gap > 1023) gap = 1023;
-    gap |= 1;
-    const int64_t init_items = max_i64(max_i64(n * 12, 4 * (n - 1) + 3 * (int64_t)gap + 1), 64);
-    pipeline_init_kernel<<<(unsigned)((init_items + 255) / 256), 256, 0, stream>>>(workspace, n, gap);
-    SX_LAUNCHED("macenko::pipeline_init_kernel");
-    kernel<<<(unsigned)grid, kThreads, 0, stream>>>(a);
-    SX_LAUNCHED("macenko::pipeline_kernel");
-    return SX_OK;
+// One chain of the per-image pipeline for images [0, n) -> slots [slot0, slot0 + n) on `stream`.
+static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream) {
+    const int64_t hw = h * w;
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
+    SX_DISPATCH_TV(dtype, vec, {
+        const T *p = static_cast<const T *>(images);
+        const RowGeom g = make_row_geom<T, VEC>(n, hw, slot0, 0);
+        t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+        mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
+        t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+        select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)n, kThreads, 0, stream>>>(p, n, hw, 0, slot0, workspace, slots);
+        mid_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
+        t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+        select_recover_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)n, kThreads, 0, stream>>>(p, n, hw, 0, slot0, workspace, slots);
+    });
+    note_launch(6);
+    SX_LAUNCHED("macenko::transform pipeline");
+    return sx_macenko_apply(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream);
+}
+
+// Side stream of the calling thread's current device (created on first use, never destroyed: the
+// library owns no device memory, only this stream and two events per device).
+constexpr int kMaxChains = 4;
+struct SideStream {
+    cudaStream_t stream[kMaxChains - 1] = {};
+    cudaEvent_t fork = nullptr, join[kMaxChains - 1] = {};
+    std::mutex mu;
+};
+static SideStream *side_stream() {
+    static SideStream table[64];
+    static std::mutex init_mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(init_mu);
+    SideStream &s = table[dev];
+    if (s.fork == nullptr) {
+        for (int i = 0; i < kMaxChains - 1; ++i) {
+            if (cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &s;
 }
 
 extern "C" {
@@ -1898,11 +1643,12 @@ extern "C" {
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels) {
     if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
-    if (phase_kernels >= 0) {  // bit 0: transform through the phase-level API; bits 1..3: pipeline debug flags; bits 4..13: schedule gap; bits 16..23: rows per tile
+    if (phase_kernels >= 0) {  // bit 0: phase-level chain; bit 1: force sample-bracket misses (recovery tests); bits 4..: number of chains (0: default)
         g_phase_kernels = (phase_kernels & 1) != 0;
-        g_pipe_debug = (int)((phase_kernels >> 1) & 7);  // bit 0: force misses; bit 2: timing counters in ctrl->pad
-        g_pipe_gap = (int)((phase_kernels >> 4) & 0x3ff);
-        g_pipe_tile_rows = (int)((phase_kernels >> 16) & 0xff);
+        const int force = (int)((phase_kernels >> 1) & 1);
+        SX_CUDA(cudaMemcpyToSymbol(g_force_miss, &force, sizeof(int)));
+        const int chains = (int)(phase_kernels >> 4);
+        g_split = chains > 0 ? (chains < kMaxChains ? chains : kMaxChains) : 3;
     }
     return SX_OK;
 }
@@ -1922,7 +1668,6 @@ int sx_macenko_region(int64_t slots, int region, int64_t *offset, int64_t *bytes
         case SX_REGION_FIT: *offset = L.fit; *bytes = slots * 8 * 4; break;
         case SX_REGION_COUNTERS: *offset = L.counters; *bytes = slots * 8 * 8; break;
         case SX_REGION_STATUS: *offset = L.status; *bytes = slots * 4 * 4; break;
-        case SX_REGION_PIPECTRL: *offset = L.ctrl; *bytes = (int64_t)sizeof(PipeCtrl); break;
         default: return sx::fail(SX_ERR_INVALID, "unknown region %d", region);
     }
     return SX_OK;
@@ -2005,20 +1750,21 @@ int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     if (int rc = check_slots(n, pooled, slot0, slots)) return rc;
     SX_REQUIRE(workspace, "workspace is NULL");
-    SX_REQUIRE((stage == SX_STAGE_ANGLE || stage == SX_STAGE_CONC) && (level == 0 || level == 1), "bad stage/level (%d, %d)", stage, level);
+    SX_REQUIRE((stage == SX_STAGE_ANGLE || stage == SX_STAGE_CONC) && (level >= 0 && level <= 2), "bad stage/level (%d, %d)", stage, level);
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         const T *p = static_cast<const T *>(images);
-        if (level == 0) {
+        if (level != 1) {
             const int64_t groups = hw / Pix<T, VEC>::kPix;
-            const int64_t stride = groups / kSampleGroups > 1 ? groups / kSampleGroups : 1;
+            const int64_t max_groups = level == 0 ? (int64_t)kSampleGroups : (int64_t)1 << 62;  // level 2: every group (exact coarse histogram)
+            const int64_t stride = groups / max_groups > 1 ? groups / max_groups : 1;
             PassGeom g = make_geom(n, hw, Pix<T, VEC>::kPix, groups / stride);
             const unsigned grid = (unsigned)(n * g.cpi);
-            if (stage == SX_STAGE_ANGLE) sample_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
-            else sample_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots);
+            if (stage == SX_STAGE_ANGLE) sample_kernel<T, VEC, SX_STAGE_ANGLE><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots, max_groups);
+            else sample_kernel<T, VEC, SX_STAGE_CONC><<<grid, kThreads, 0, stream>>>(p, g, pooled, slot0, workspace, slots, max_groups);
         } else {
             const RowGeom g = make_row_geom<T, VEC>(n, hw, pooled ? 0 : slot0, pooled);
             if (stage == SX_STAGE_ANGLE) t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
@@ -2085,9 +1831,9 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     SX_REQUIRE(he_ref && maxc_ref && out, "NULL argument");
     cudaStream_t stream = static_cast<cudaStream_t>(s);
     const int64_t hw = h * w;
+    int rc;
+    if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
     if (g_phase_kernels) {  // development: the phase-level API chained on one stream (13 launches)
-        int rc;
-        if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
         if ((rc = sx_macenko_moments(images, dtype, n, h, w, 0, 0, workspace, n, s))) return rc;
         if ((rc = sx_macenko_basis(workspace, n, 0, n, 1, s))) return rc;
         if ((rc = sx_macenko_moments_fallback(images, dtype, n, h, w, 0, workspace, n, s))) return rc;
@@ -2098,22 +1844,33 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
             }
         return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
     }
-    // The persistent per-image pipeline (see "persistent per-image transform pipeline" above): two launches.
-    SX_REQUIRE(out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8), "uint8 output requires uint8 input");
-    const bool unit = out_scale != 1.0f;
-    SX_REQUIRE(!unit || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
-    const bool vec = images_vec_ok(images, out, dtype, hw);
-    const int out_mode = out_dtype == SX_U8 ? 0 : (unit ? 2 : 1);
-    SX_DISPATCH_TV(dtype, vec, {
-        if (out_mode == 0) {
-            if constexpr (sizeof(T) == 1) return launch_pipeline<T, VEC, 0>(images, n, hw, he_ref, maxc_ref, out, workspace, stream);
-        } else if (out_mode == 1) {
-            return launch_pipeline<T, VEC, 1>(images, n, hw, he_ref, maxc_ref, out, workspace, stream);
-        } else {
-            return launch_pipeline<T, VEC, 2>(images, n, hw, he_ref, maxc_ref, out, workspace, stream);
+    // Per-image pipeline (see "per-image transform pipeline" above).  Large batches run as up to
+    // kMaxChains part-batch chains, all but the first on side streams: the small per-image kernels of one chain
+    // (~25 us per stage of dependent global round trips on a few SMs) overlap the streaming kernels
+    // of the other.  The caller's stream forks into the side stream and joins it again, so the call
+    // keeps its stream-ordered, host-asynchronous contract (and can be captured into a CUDA graph).
+    const int64_t in_bytes = (dtype == SX_F32 ? 4 : 1) * 3 * hw, out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * hw;
+    int chains = g_split;
+    if (n * in_bytes < ((int64_t)64 << 20)) chains = 1;
+    while (chains > 1 && n / chains < 4) --chains;
+    if (chains <= 1) return run_pipeline(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, stream);
+    SideStream *side = side_stream();
+    SX_REQUIRE(side != nullptr, "could not create the side streams");
+    std::lock_guard<std::mutex> lock(side->mu);
+    SX_CUDA(cudaEventRecord(side->fork, stream));
+    rc = SX_OK;
+    for (int c = 0; c < chains; ++c) {  // chain 0 on the caller's stream, chain c > 0 on side stream c - 1
+        const int64_t i0 = n * c / chains, i1 = n * (c + 1) / chains;
+        cudaStream_t cs = c == 0 ? stream : side->stream[c - 1];
+        if (c > 0) SX_CUDA(cudaStreamWaitEvent(cs, side->fork, 0));
+        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, n, cs);
+        if (r && !rc) rc = r;
+        if (c > 0) {
+            SX_CUDA(cudaEventRecord(side->join[c - 1], cs));
+            SX_CUDA(cudaStreamWaitEvent(stream, side->join[c - 1], 0));
         }
-    });
-    return sx::fail(SX_ERR_INVALID, "unsupported dtype combination");
+    }
+    return rc;
 }
 
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
@@ -2125,11 +1882,20 @@ int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t 
     if ((rc = sx_macenko_begin(workspace, 1, s))) return rc;
     if ((rc = sx_macenko_moments(images, dtype, n, h, w, 1, 0, workspace, 1, s))) return rc;
     if ((rc = sx_macenko_basis(workspace, 1, 0, 1, 0, s))) return rc;  // no fallback in fit (L483-487)
-    for (int stage = 0; stage < 2; ++stage)
-        for (int level = 0; level < 2; ++level) {
-            if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, level, workspace, 1, s))) return rc;
-            if ((rc = sx_macenko_select(workspace, 1, 0, 1, stage, level, s))) return rc;
-        }
+    const int64_t hw = h * w;
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
+    for (int stage = 0; stage < 2; ++stage) {
+        if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 0, workspace, 1, s))) return rc;
+        if ((rc = sx_macenko_select(workspace, 1, 0, 1, stage, 0, s))) return rc;
+        if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 1, workspace, 1, s))) return rc;
+        // rank search; a missed bracket is re-done exactly by the same kernel (see "deterministic recovery")
+        SX_DISPATCH_TV(dtype, vec, {
+            const T *p = static_cast<const T *>(images);
+            if (stage == SX_STAGE_ANGLE) select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<1, kThreads, 0, static_cast<cudaStream_t>(s)>>>(p, n, hw, 1, 0, workspace, 1);
+            else select_recover_kernel<T, VEC, SX_STAGE_CONC><<<1, kThreads, 0, static_cast<cudaStream_t>(s)>>>(p, n, hw, 1, 0, workspace, 1);
+        });
+        SX_LAUNCHED("macenko::select_recover_kernel");
+    }
     Ws ws(workspace, 1);
     SX_CUDA(cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
     SX_CUDA(cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
