@@ -23,8 +23,8 @@
  *   - images are contiguous, C = 3.  SX_NCHW everywhere; SX_NHWC additionally for histogram
  *     matching (the reference accepts it there through a permute view,
  *     src/stainx/backends/torch_cuda_backend.py:L46-49).
- *   - uint8 images are [0,255]; float32 images are assumed [0,1] and never max-rescaled
- *     (torch_backend.py:L103-113).
+ *   - uint8 images are [0,255]; float32 / float16 / bfloat16 images are assumed [0,1] and never
+ *     max-rescaled (torch_backend.py:L103-113).
  *   - phase-level functions are split exactly where a sharded (multi-GPU) run must all-reduce
  *     statistics; the *_transform / *_fit conveniences chain the phases on one stream.
  */
@@ -40,7 +40,12 @@ extern "C" {
 #define SX_ABI_VERSION 1
 
 enum sx_status { SX_OK = 0, SX_ERR_INVALID = 1, SX_ERR_CUDA = 2, SX_ERR_UNSUPPORTED = 3 };
-enum sx_dtype { SX_U8 = 0, SX_F32 = 1 };
+/* SX_F16 / SX_BF16: float images in [0,1] stored as IEEE half / bfloat16.  The reference widens such tensors to
+ * float32, computes, and casts the result back (torch_backend.py:L103-131, src/stainx_cuda_torch/csrc/
+ * histogram_matching.cu:L63-65); here the kernels load and store the 16-bit values themselves (8 pixels per
+ * 128-bit vector, float32 arithmetic in registers, round-to-nearest-even stores): half the bytes per pixel.
+ * Outputs have the dtype of the input. */
+enum sx_dtype { SX_U8 = 0, SX_F32 = 1, SX_F16 = 2, SX_BF16 = 3 };
 enum sx_layout { SX_NCHW = 0, SX_NHWC = 1 };
 
 typedef void *sx_stream_t; /* cudaStream_t */
@@ -234,8 +239,10 @@ int sx_macenko_hist(const void *images, int dtype, int64_t n, int64_t h, int64_t
 int sx_macenko_select(void *workspace, int64_t slots, int64_t slot0, int64_t count, int stage,
                       int level, sx_stream_t stream);
 /* M10: C = pinv(HE_src).OD scaled by maxc_ref/maxC_src; OD' = he_ref.C; rgb = clamp(240 exp(-OD'),
- * 0, 255) * out_scale.  out_dtype SX_U8 (only for uint8 input, truncated; out_scale ignored) or
- * SX_F32.  out_scale = 1 keeps the reference's [0,255] float output, 1/255 folds the
+ * 0, 255) * out_scale.  out_dtype SX_U8 (only for uint8 input, truncated; out_scale ignored),
+ * SX_F32 (uint8 / float32 input), or the input's own 16-bit float type (SX_F16 / SX_BF16 input: the
+ * [0,255] value rounded to that type, then -- out_scale 1/255 -- divided by 255 and rounded again,
+ * which is what the reference's cast-back followed by `/ 255.0` gives).  out_scale = 1 keeps the reference's [0,255] float output, 1/255 folds the
  * normalize_to_0_1 division (src/stainx/normalizers/_template.py:L111-112) into the store. */
 int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0,
                      const float *he_ref, const float *maxc_ref, void *out, int out_dtype,

@@ -79,7 +79,7 @@ _RESTYPES = {
     "sx_macenko_peer_scratch_bytes": _i64,
 }
 
-SX_U8, SX_F32 = 0, 1
+SX_U8, SX_F32, SX_F16, SX_BF16 = 0, 1, 2, 3
 SX_NCHW, SX_NHWC = 0, 1
 SX_STAGE_ANGLE, SX_STAGE_CONC = 0, 1
 REGIONS = {"moments": 0, "odrange": 1, "hist1": 2, "hist2": 3, "vmin": 4, "vmax": 5, "fit": 6, "counters": 7, "status": 8}

@@ -20,6 +20,7 @@ from stainx_b200.sharding import StatReducer
 CUDA_AVAILABLE = _native.FUNCTIONS_AVAILABLE
 
 _CHANNELS_LAST = (-1, 3)
+_NATIVE_DTYPES = (torch.uint8, torch.float32, torch.float16, torch.bfloat16)
 
 
 class TorchCUDABackendBase:
@@ -53,20 +54,22 @@ class TorchCUDABackendBase:
             raise ValueError(f"CUDA backend requires CUDA device, got {self.device.type}")
 
     def _to_native(self, images: torch.Tensor) -> tuple[torch.Tensor, torch.dtype]:
-        """Move to the device and to a dtype the kernels take: uint8 stays, every other dtype is
-        read as float32 in [0, 1] (torch_backend.py:L103-113)."""
+        """Move to the device and to a dtype the kernels take: uint8, float32, float16 and bfloat16 are read
+        natively (the 16-bit types are widened inside the kernels, 8 pixels per 128-bit load -- the reference
+        widens them with a separate ``.float()`` pass, torch_backend.py:L103-113); any other dtype (float64)
+        is converted to float32 in [0, 1] first and the result is cast back (L131)."""
         if not isinstance(images, torch.Tensor):
             raise TypeError(f"images must be a torch.Tensor, got {type(images)}")
         original = images.dtype
         images = images.to(self.device)
-        if images.dtype != torch.uint8 and images.dtype != torch.float32:
+        if images.dtype not in _NATIVE_DTYPES:
             images = images.float()
         return images.contiguous(), original
 
     @staticmethod
     def _restore_dtype(result: torch.Tensor, original: torch.dtype) -> torch.Tensor:
         # torch_backend.py:L131: the result is cast back to the caller's dtype.
-        if original in (torch.uint8, torch.float32) or result.dtype == original:
+        if original in _NATIVE_DTYPES or result.dtype == original:
             return result
         return result.to(original)
 

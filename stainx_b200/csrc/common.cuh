@@ -1,5 +1,7 @@
 // common.cuh -- shared host/device helpers for libstainx_b200 (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,11 +44,12 @@ bool tuning_enabled();
     } while (0)
 
 inline int64_t max_i64(int64_t a, int64_t b) { return a > b ? a : b; }
+inline int dtype_bytes(int dtype) { return dtype == SX_U8 ? 1 : (dtype == SX_F32 ? 4 : 2); }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int check_images(const void *images, int dtype, int64_t n, int64_t h, int64_t w) {
     SX_REQUIRE(images != nullptr || n == 0 || h == 0 || w == 0, "images is NULL");
-    SX_REQUIRE(dtype == SX_U8 || dtype == SX_F32, "dtype must be SX_U8 or SX_F32, got %d", dtype);
+    SX_REQUIRE(dtype == SX_U8 || dtype == SX_F32 || dtype == SX_F16 || dtype == SX_BF16, "dtype must be SX_U8, SX_F32, SX_F16 or SX_BF16, got %d", dtype);
     SX_REQUIRE(n >= 0 && h >= 0 && w >= 0, "negative image extent (%lld, %lld, %lld)", (long long)n, (long long)h, (long long)w);
     return SX_OK;
 }
@@ -124,6 +127,35 @@ __device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
 __device__ __forceinline__ void st_stream(float4 *p, const float4 &v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ---- 16-bit float storage (SX_F16 / SX_BF16 images) ------------------------------------------------
+// A 32-bit word holds two consecutive values (low half first).  Widening is exact; narrowing rounds
+// to nearest even (what torch's `.to(dtype)` does, torch_backend.py:L131).
+template <typename T>
+struct Half2IO;
+template <>
+struct Half2IO<__half> {
+    static __device__ __forceinline__ float2 unpack(unsigned w) { return __half22float2(*reinterpret_cast<const __half2 *>(&w)); }
+    static __device__ __forceinline__ unsigned pack(float a, float b) {
+        const __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<const unsigned *>(&h);
+    }
+    static __device__ __forceinline__ float widen(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half narrow(float v) { return __float2half_rn(v); }
+};
+template <>
+struct Half2IO<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 unpack(unsigned w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+    static __device__ __forceinline__ unsigned pack(float a, float b) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<const unsigned *>(&h);
+    }
+    static __device__ __forceinline__ float widen(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 narrow(float v) { return __float2bfloat16_rn(v); }
+};
+// Round a float to the storage type and back (the value the reference holds after its cast-back).
+template <typename T>
+__device__ __forceinline__ float round_trip(float v) { return Half2IO<T>::widen(Half2IO<T>::narrow(v)); }
 
 // ---- TMA bulk copies (global -> shared) completed on an mbarrier --------------------------------
 // One thread arms the barrier with the byte count and issues cp.async.bulk; the copy engine moves

@@ -64,6 +64,39 @@ __device__ __forceinline__ PlaneSplit split_plane(const T *p, int64_t len) {
     return s;
 }
 
+// One 128-bit vector of a float-like image (float32: 4 values, float16 / bfloat16: 8), widened to float32.
+template <typename T>
+struct FloatVec {
+    static constexpr int kPer = 16 / sizeof(T);
+    float f[kPer];
+    __device__ __forceinline__ void load(const T *p) {
+        if constexpr (sizeof(T) == 4) {
+            const float4 v = ld_stream(reinterpret_cast<const float4 *>(p));
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
+            const uint4 v = ld_stream(reinterpret_cast<const uint4 *>(p));
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 x = Half2IO<T>::unpack(w[k]);
+                f[2 * k] = x.x; f[2 * k + 1] = x.y;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(T *p) const {
+        if constexpr (sizeof(T) == 4) st_stream(reinterpret_cast<float4 *>(p), make_float4(f[0], f[1], f[2], f[3]));
+        else st_stream(reinterpret_cast<uint4 *>(p), make_uint4(Half2IO<T>::pack(f[0], f[1]), Half2IO<T>::pack(f[2], f[3]), Half2IO<T>::pack(f[4], f[5]), Half2IO<T>::pack(f[6], f[7])));
+    }
+    static __device__ __forceinline__ float widen(T v) {
+        if constexpr (sizeof(T) == 4) return v;
+        else return Half2IO<T>::widen(v);
+    }
+    static __device__ __forceinline__ T narrow(float v) {
+        if constexpr (sizeof(T) == 4) return v;
+        else return Half2IO<T>::narrow(v);
+    }
+};
+
 __global__ void __launch_bounds__(kThreads) hist_u8_planar_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
     __shared__ unsigned int hist32[256];
     __shared__ unsigned int whist[kWarps * 256];
@@ -428,9 +461,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_pw_kerne
     }
 }
 
-// Histogram, planar float32: quantise, then warp-private shared atomics (12 B/px of traffic per
-// 3 values, so the atomic rate is 4x lower than in the uint8 kernel).
-__global__ void __launch_bounds__(kThreads) hist_f32_planar_kernel(const float *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+// Histogram, planar float32 / float16 / bfloat16: quantise, then warp-private shared atomics (12 or 6 B/px of
+// traffic per 3 values, so the atomic rate is 4x / 2x lower than in the uint8 kernel).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) hist_f32_planar_kernel(const T *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
+    constexpr int kPer = FloatVec<T>::kPer;
     __shared__ unsigned int hist32[256];
     __shared__ unsigned int whist[kWarps * 256];
     const int c = blockIdx.y;
@@ -442,32 +477,30 @@ __global__ void __launch_bounds__(kThreads) hist_f32_planar_kernel(const float *
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
         const int64_t n = item / tiles_per_plane;
         const int64_t t = item - n * tiles_per_plane;
-        const float *plane = img + (n * 3 + c) * hw;
+        const T *plane = img + (n * 3 + c) * hw;
         const PlaneSplit sp = split_plane(plane, hw);
-        const float4 *body = reinterpret_cast<const float4 *>(plane + sp.head);
+        const T *body = plane + sp.head;
         const int64_t v0 = t * kTileVecs;
-        float4 v[kUnroll];
+        FloatVec<T> v[kUnroll];
         bool ok[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             int64_t vi = v0 + u * kThreads + threadIdx.x;
             ok[u] = vi < sp.nvec;
-            if (ok[u]) v[u] = ld_stream(body + vi);
+            if (ok[u]) v[u].load(body + vi * kPer);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             if (ok[u]) {
-                wa.add(quantize_u8(v[u].x));
-                wa.add(quantize_u8(v[u].y));
-                wa.add(quantize_u8(v[u].z));
-                wa.add(quantize_u8(v[u].w));
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) wa.add(quantize_u8(v[u].f[k]));
             }
         }
         if (t == 0) {
             int64_t ragged = sp.head + (hw - sp.tail0);
             if ((int64_t)threadIdx.x < ragged) {
                 int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
-                wa.add(quantize_u8(plane[idx]));
+                wa.add(quantize_u8(FloatVec<T>::widen(plane[idx])));
             }
         }
     }
@@ -507,18 +540,21 @@ __global__ void __launch_bounds__(kThreads) hist_nhwc_kernel(const T *__restrict
                 atomicAdd(&wh[(j % 3) * 256 + v], 1u);
             }
         } else {
-            const float4 *p = reinterpret_cast<const float4 *>(img + g * kGroup);
-            float4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
-            float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+            FloatVec<T> a, b, d;
+            a.load(img + g * kGroup); b.load(img + g * kGroup + kPerVec); d.load(img + g * kGroup + 2 * kPerVec);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) atomicAdd(&wh[(j % 3) * 256 + quantize_u8(f[j])], 1u);
+            for (int j = 0; j < kPerVec; ++j) {  // element e of the group has channel e % 3 (kGroup is a multiple of 3)
+                atomicAdd(&wh[(j % 3) * 256 + quantize_u8(a.f[j])], 1u);
+                atomicAdd(&wh[((kPerVec + j) % 3) * 256 + quantize_u8(b.f[j])], 1u);
+                atomicAdd(&wh[((2 * kPerVec + j) % 3) * 256 + quantize_u8(d.f[j])], 1u);
+            }
         }
     }
     // scalar remainder (everything when the base pointer is not 16-byte aligned)
     for (int64_t i = groups * kGroup + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
         unsigned v;
         if constexpr (sizeof(T) == 1) v = img[i];
-        else v = quantize_u8(img[i]);
+        else v = quantize_u8(FloatVec<T>::widen(img[i]));
         atomicAdd(&wh[(int)(i % 3) * 256 + v], 1u);
     }
     __syncthreads();
@@ -880,8 +916,11 @@ __global__ void __launch_bounds__(kThreads) apply_u8_planar_vec_kernel(const uin
 
 // (A 65 536-entry two-byte LUT in shared memory behind a TMA ring was built and measured for the uint8
 // planar remap: 80 us against 72 us for the kernel above; removed.)
-// float32 planar: out = clamp(lut[trunc(clamp(255 x))] / 255, 0, 1)   (L290-296).
-__global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const float *__restrict__ img, float *__restrict__ out, int64_t hw, int64_t planes, int64_t tiles_per_plane, const float *__restrict__ lut) {
+// float32 / float16 / bfloat16 planar: out = clamp(lut[trunc(clamp(255 x))] / 255, 0, 1)   (L290-296), stored in
+// the input's dtype (round to nearest even for the 16-bit types, the reference's cast-back of L131).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const T *__restrict__ img, T *__restrict__ out, int64_t hw, int64_t planes, int64_t tiles_per_plane, const float *__restrict__ lut) {
+    constexpr int kPer = FloatVec<T>::kPer;
     __shared__ float lutf[3 * 256];
     for (int i = threadIdx.x; i < 768; i += kThreads) lutf[i] = fminf(fmaxf(__fdiv_rn(lut[i], 255.0f), 0.0f), 1.0f);
     __syncthreads();
@@ -891,37 +930,39 @@ __global__ void __launch_bounds__(kThreads) apply_f32_planar_kernel(const float 
         const int64_t pl = item / tiles_per_plane;
         const int64_t t = item - pl * tiles_per_plane;
         const float *l = lutf + (int)(pl % 3) * 256;
-        const float *src = img + pl * hw;
-        float *dst = out + pl * hw;
+        const T *src = img + pl * hw;
+        T *dst = out + pl * hw;
         const PlaneSplit sp = split_plane(src, hw);
         const bool dst_vec = ((reinterpret_cast<uintptr_t>(dst + sp.head)) & 15) == 0;
-        const float4 *body = reinterpret_cast<const float4 *>(src + sp.head);
+        const T *body = src + sp.head;
         const int64_t v0 = t * kTileVecs;
-        float4 v[kUnroll];
+        FloatVec<T> v[kUnroll];
         bool ok[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             int64_t vi = v0 + u * kThreads + threadIdx.x;
             ok[u] = vi < sp.nvec;
-            if (ok[u]) v[u] = ld_stream(body + vi);
+            if (ok[u]) v[u].load(body + vi * kPer);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             if (!ok[u]) continue;
             int64_t vi = v0 + u * kThreads + threadIdx.x;
-            float4 r = make_float4(l[quantize_u8(v[u].x)], l[quantize_u8(v[u].y)], l[quantize_u8(v[u].z)], l[quantize_u8(v[u].w)]);
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) v[u].f[k] = l[quantize_u8(v[u].f[k])];
+            T *d = dst + sp.head + vi * kPer;
             if (dst_vec) {
-                st_stream(reinterpret_cast<float4 *>(dst + sp.head) + vi, r);
+                v[u].store(d);
             } else {
-                float *d = dst + sp.head + vi * 4;
-                d[0] = r.x; d[1] = r.y; d[2] = r.z; d[3] = r.w;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) d[k] = FloatVec<T>::narrow(v[u].f[k]);
             }
         }
         if (t == 0) {
             int64_t ragged = sp.head + (hw - sp.tail0);
             if ((int64_t)threadIdx.x < ragged) {
                 int64_t idx = (int64_t)threadIdx.x < sp.head ? (int64_t)threadIdx.x : sp.tail0 + ((int64_t)threadIdx.x - sp.head);
-                dst[idx] = l[quantize_u8(src[idx])];
+                dst[idx] = FloatVec<T>::narrow(l[quantize_u8(FloatVec<T>::widen(src[idx]))]);
             }
         }
     }
@@ -1012,20 +1053,20 @@ __global__ void __launch_bounds__(kThreads) apply_nhwc_kernel(const T *__restric
             st_stream(q + 1, make_uint4(r[4], r[5], r[6], r[7]));
             st_stream(q + 2, make_uint4(r[8], r[9], r[10], r[11]));
         } else {
-            const float4 *p = reinterpret_cast<const float4 *>(img + g * kGroup);
-            float4 a = ld_stream(p), b = ld_stream(p + 1), d = ld_stream(p + 2);
-            float f[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+            FloatVec<T> a, b, d;
+            a.load(img + g * kGroup); b.load(img + g * kGroup + kPerVec); d.load(img + g * kGroup + 2 * kPerVec);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) f[j] = lutf[(j % 3) * 256 + quantize_u8(f[j])];
-            float4 *q = reinterpret_cast<float4 *>(out + g * kGroup);
-            st_stream(q, make_float4(f[0], f[1], f[2], f[3]));
-            st_stream(q + 1, make_float4(f[4], f[5], f[6], f[7]));
-            st_stream(q + 2, make_float4(f[8], f[9], f[10], f[11]));
+            for (int j = 0; j < kPerVec; ++j) {
+                a.f[j] = lutf[(j % 3) * 256 + quantize_u8(a.f[j])];
+                b.f[j] = lutf[((kPerVec + j) % 3) * 256 + quantize_u8(b.f[j])];
+                d.f[j] = lutf[((2 * kPerVec + j) % 3) * 256 + quantize_u8(d.f[j])];
+            }
+            a.store(out + g * kGroup); b.store(out + g * kGroup + kPerVec); d.store(out + g * kGroup + 2 * kPerVec);
         }
     }
     for (int64_t i = groups * kGroup + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
         if constexpr (sizeof(T) == 1) out[i] = lut8[(int)(i % 3) * 256 + img[i]];
-        else out[i] = lutf[(int)(i % 3) * 256 + quantize_u8(img[i])];
+        else out[i] = FloatVec<T>::narrow(lutf[(int)(i % 3) * 256 + quantize_u8(FloatVec<T>::widen(img[i]))]);
     }
 }
 
@@ -1124,8 +1165,16 @@ static int hist_impl(const void *images, int dtype, int layout, int64_t n, int64
             hist_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), total, cnt);
         } else {
             unsigned grid = stream_grid((total / 12 + kThreads - 1) / kThreads + 1, 8);
-            prefer_l1(hist_nhwc_kernel<float>, kThreads);
-            hist_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), total, cnt);
+            if (dtype == SX_F32) {
+                prefer_l1(hist_nhwc_kernel<float>, kThreads);
+                hist_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), total, cnt);
+            } else if (dtype == SX_F16) {
+                prefer_l1(hist_nhwc_kernel<__half>, kThreads);
+                hist_nhwc_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half *>(images), total, cnt);
+            } else {
+                prefer_l1(hist_nhwc_kernel<__nv_bfloat16>, kThreads);
+                hist_nhwc_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(images), total, cnt);
+            }
         }
         SX_LAUNCHED("hist_nhwc_kernel");
         return SX_OK;
@@ -1146,11 +1195,20 @@ static int hist_impl(const void *images, int dtype, int layout, int64_t n, int64
         }
         SX_LAUNCHED("hist_u8_planar_kernel");
     } else {
-        const int64_t tiles = max_i64(1, (hw / 4 + kTileVecs - 1) / kTileVecs);
+        const int64_t per = 16 / dtype_bytes(dtype);
+        const int64_t tiles = max_i64(1, (hw / per + kTileVecs - 1) / kTileVecs);
         dim3 grid(stream_grid(n * tiles, 6), 3);
         grid.x = (grid.x + 2) / 3 > 0 ? (grid.x + 2) / 3 : 1;
-        prefer_l1(hist_f32_planar_kernel, kThreads);
-        hist_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), hw, n, tiles, cnt);
+        if (dtype == SX_F32) {
+            prefer_l1(hist_f32_planar_kernel<float>, kThreads);
+            hist_f32_planar_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), hw, n, tiles, cnt);
+        } else if (dtype == SX_F16) {
+            prefer_l1(hist_f32_planar_kernel<__half>, kThreads);
+            hist_f32_planar_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half *>(images), hw, n, tiles, cnt);
+        } else {
+            prefer_l1(hist_f32_planar_kernel<__nv_bfloat16>, kThreads);
+            hist_f32_planar_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(images), hw, n, tiles, cnt);
+        }
         SX_LAUNCHED("hist_f32_planar_kernel");
     }
     return SX_OK;
@@ -1228,10 +1286,19 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
         apply_u8_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), hw, planes, tiles, lut);
         SX_LAUNCHED("apply_u8_planar_kernel");
     } else {
-        const int64_t tiles = max_i64(1, (hw / 4 + kTileVecs - 1) / kTileVecs);
+        const int64_t per = 16 / dtype_bytes(dtype);
+        const int64_t tiles = max_i64(1, (hw / per + kTileVecs - 1) / kTileVecs);
         unsigned grid = stream_grid(planes * tiles, g_apply_ctas_per_sm);
-        prefer_l1(apply_f32_planar_kernel, kThreads);
-        apply_f32_planar_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), hw, planes, tiles, lut);
+        if (dtype == SX_F32) {
+            prefer_l1(apply_f32_planar_kernel<float>, kThreads);
+            apply_f32_planar_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), hw, planes, tiles, lut);
+        } else if (dtype == SX_F16) {
+            prefer_l1(apply_f32_planar_kernel<__half>, kThreads);
+            apply_f32_planar_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half *>(images), static_cast<__half *>(out), hw, planes, tiles, lut);
+        } else {
+            prefer_l1(apply_f32_planar_kernel<__nv_bfloat16>, kThreads);
+            apply_f32_planar_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(images), static_cast<__nv_bfloat16 *>(out), hw, planes, tiles, lut);
+        }
         SX_LAUNCHED("apply_f32_planar_kernel");
     }
     return SX_OK;

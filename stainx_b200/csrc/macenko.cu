@@ -164,6 +164,22 @@ struct RawGroup {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) l[c][0] = f32_l(v[c]);
             }
+        } else if constexpr (sizeof(T) == 2) {  // float16 / bfloat16 storage, float32 arithmetic
+            if constexpr (VEC) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const unsigned w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = Half2IO<T>::unpack(w[k]);
+                        l[c][2 * k] = f32_l(f.x);
+                        l[c][2 * k + 1] = f32_l(f.y);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) l[c][0] = f32_l(Half2IO<T>::widen(v[c]));
+            }
         } else {
             if constexpr (VEC) {
 #pragma unroll
@@ -1142,6 +1158,22 @@ __device__ __forceinline__ void apply_pass(const T *__restrict__ image, void *__
                     out[c * hw] = (uint8_t)__float2int_rz(o[c][0]);
                 }
             }
+        } else if constexpr (sizeof(T) == 2) {
+            // 16-bit float input: the reference casts its float32 [0,255] result back to the input dtype (L131), then
+            // normalize_to_0_1 divides THAT by 255 in the same dtype (_template.py:L111-112): two roundings.
+            T *out = static_cast<T *>(out_image) + off;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if constexpr (OUT == 2) {
+#pragma unroll
+                    for (int k = 0; k < kPix; ++k) o[c][k] = __fdiv_rn(round_trip<T>(o[c][k]), 255.0f);
+                }
+                if constexpr (VEC) {
+                    st_stream(reinterpret_cast<uint4 *>(out + c * hw), make_uint4(Half2IO<T>::pack(o[c][0], o[c][1]), Half2IO<T>::pack(o[c][2], o[c][3]), Half2IO<T>::pack(o[c][4], o[c][5]), Half2IO<T>::pack(o[c][6], o[c][7])));
+                } else {
+                    out[c * hw] = Half2IO<T>::narrow(o[c][0]);
+                }
+            }
         } else {
             float *out = static_cast<float *>(out_image) + off;
 #pragma unroll
@@ -1180,7 +1212,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
     const int64_t slot = slot0 + n;
     apply_coefficients<T, OUT>(coef, he_ref, maxc_ref, ws.state[slot].pinv, ws.fit[slot * 8 + 6], ws.fit[slot * 8 + 7]);
     __syncthreads();
-    constexpr int kOutBytes = OUT == 0 ? 1 : 4;
+    constexpr int kOutBytes = OUT == 0 ? 1 : (sizeof(T) == 2 ? 2 : 4);  // 16-bit float input: output in the input's dtype
     apply_pass<T, VEC, OUT>(img + n * 3 * g.hw, static_cast<char *>(out_) + n * 3 * g.hw * kOutBytes, g.hw, (int64_t)chunk * kThreads, (int64_t)g.cpi * kThreads, tab, unit_tab, coef);
 }
 
@@ -1570,21 +1602,22 @@ static bool vec_ok(const void *a, const void *b, int64_t hw) {
 using namespace sx;
 using namespace sx::macenko;
 
+#define SX_DISPATCH_TV_ONE(TYPE, vec, ...)                                      \
+    {                                                                          \
+        using T = TYPE;                                                        \
+        if (vec) { constexpr bool VEC = true; __VA_ARGS__; }                   \
+        else { constexpr bool VEC = false; __VA_ARGS__; }                      \
+    }
 #define SX_DISPATCH_TV(dtype, vec, ...)                                        \
     do {                                                                       \
-        if ((dtype) == SX_F32) {                                               \
-            using T = float;                                                   \
-            if (vec) { constexpr bool VEC = true; __VA_ARGS__; }               \
-            else { constexpr bool VEC = false; __VA_ARGS__; }                  \
-        } else {                                                               \
-            using T = uint8_t;                                                 \
-            if (vec) { constexpr bool VEC = true; __VA_ARGS__; }               \
-            else { constexpr bool VEC = false; __VA_ARGS__; }                  \
-        }                                                                      \
+        if ((dtype) == SX_F32) SX_DISPATCH_TV_ONE(float, vec, __VA_ARGS__)     \
+        else if ((dtype) == SX_F16) SX_DISPATCH_TV_ONE(__half, vec, __VA_ARGS__) \
+        else if ((dtype) == SX_BF16) SX_DISPATCH_TV_ONE(__nv_bfloat16, vec, __VA_ARGS__) \
+        else SX_DISPATCH_TV_ONE(uint8_t, vec, __VA_ARGS__)                     \
     } while (0)
 
 static bool images_vec_ok(const void *images, const void *out, int dtype, int64_t hw) {
-    const bool in_ok = dtype == SX_F32 ? vec_ok<float>(images, nullptr, hw) : vec_ok<uint8_t>(images, nullptr, hw);
+    const bool in_ok = dtype == SX_F32 ? vec_ok<float>(images, nullptr, hw) : (dtype == SX_U8 ? vec_ok<uint8_t>(images, nullptr, hw) : vec_ok<__half>(images, nullptr, hw));
     // output plane offsets are multiples of hw elements of the output type (>= 1 byte), so an
     // aligned base and hw % kPix == 0 keep every 128-bit store aligned
     return in_ok && (out == nullptr || aligned16(out));
@@ -1792,7 +1825,8 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
     if (int rc = check_slots(n, 0, slot0, slots)) return rc;
     if (n == 0 || h * w == 0) return SX_OK;
     SX_REQUIRE(workspace && he_ref && maxc_ref && out, "NULL argument");
-    SX_REQUIRE(out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8), "uint8 output requires uint8 input");
+    const bool half_in = dtype == SX_F16 || dtype == SX_BF16;
+    SX_REQUIRE(half_in ? out_dtype == dtype : (out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8)), "output dtype %d does not go with input dtype %d (uint8 -> uint8 | float32, float32 -> float32, float16 / bfloat16 -> the same)", out_dtype, dtype);
     const bool unit = out_scale != 1.0f;
     SX_REQUIRE(!unit || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
     const int64_t hw = h * w;
@@ -1849,7 +1883,7 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     // (~25 us per stage of dependent global round trips on a few SMs) overlap the streaming kernels
     // of the other.  The caller's stream forks into the side stream and joins it again, so the call
     // keeps its stream-ordered, host-asynchronous contract (and can be captured into a CUDA graph).
-    const int64_t in_bytes = (dtype == SX_F32 ? 4 : 1) * 3 * hw, out_bytes = (out_dtype == SX_F32 ? 4 : 1) * 3 * hw;
+    const int64_t in_bytes = (int64_t)dtype_bytes(dtype) * 3 * hw, out_bytes = (int64_t)dtype_bytes(out_dtype) * 3 * hw;
     int chains = g_split;
     if (n * in_bytes < ((int64_t)64 << 20)) chains = 1;
     while (chains > 1 && n / chains < 4) --chains;

@@ -172,6 +172,17 @@ struct Px<uint8_t> {
     using Vec = uint4;
 };
 
+template <>
+struct Px<__half> {
+    static constexpr int kPix = 8;  // float16 / bfloat16 storage: 8 pixels per 128-bit vector, float32 arithmetic
+    using Vec = uint4;
+};
+template <>
+struct Px<__nv_bfloat16> {
+    static constexpr int kPix = 8;
+    using Vec = uint4;
+};
+
 struct Acc {
     double s[6];
     double n;
@@ -243,7 +254,20 @@ struct RawPx {
                 r[0] = lin_lut[v[0]]; g[0] = lin_lut[v[1]]; b[0] = lin_lut[v[2]];
             }
         } else {
-            if constexpr (VEC) {
+            if constexpr (sizeof(T) == 2) {  // two words of each plane's vector per chunk of four pixels
+                if constexpr (VEC) {
+                    const unsigned wr[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, wg[4] = {v[1].x, v[1].y, v[1].z, v[1].w}, wb[4] = {v[2].x, v[2].y, v[2].z, v[2].w};
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const float2 fr = Half2IO<T>::unpack(wr[2 * chunk + k]), fg = Half2IO<T>::unpack(wg[2 * chunk + k]), fb = Half2IO<T>::unpack(wb[2 * chunk + k]);
+                        r[2 * k] = fr.x; r[2 * k + 1] = fr.y;
+                        g[2 * k] = fg.x; g[2 * k + 1] = fg.y;
+                        b[2 * k] = fb.x; b[2 * k + 1] = fb.y;
+                    }
+                } else {
+                    r[0] = Half2IO<T>::widen(v[0]); g[0] = Half2IO<T>::widen(v[1]); b[0] = Half2IO<T>::widen(v[2]);
+                }
+            } else if constexpr (VEC) {
                 r[0] = v[0].x; r[1] = v[0].y; r[2] = v[0].z; r[3] = v[0].w;
                 g[0] = v[1].x; g[1] = v[1].y; g[2] = v[1].z; g[3] = v[1].w;
                 b[0] = v[2].x; b[1] = v[2].y; b[2] = v[2].z; b[3] = v[2].w;
@@ -281,7 +305,7 @@ __device__ __forceinline__ void setup_tables(unsigned char *smem, const float2 *
     fwd = f;
     inv = i;
     if constexpr (TAB) {
-        if (sizeof(T) == 4) build_curve(f, kFwdN, [](float x) { return srgb_to_linear_exact(x); });
+        if (sizeof(T) != 1) build_curve(f, kFwdN, [](float x) { return srgb_to_linear_exact(x); });
         // out-of-gamut values (v > 1) are clamped to 1 after the curve in the reference (L96): the
         // saturated argument must map to exactly 1 (1.055f - 0.055f is 1 - 2^-24 in float32)
         if (need_inv) build_curve(i, kInvN, [](float v) { return v >= 1.0f ? 1.0f : linear_to_srgb_exact(v); });
@@ -423,7 +447,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ float lin_lut[256];
     const float2 *fwd, *inv;
-    setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, (sizeof(T) == 4 ? kInvSfuF32 : kInvSfuU8) < 3);
+    setup_tables<T, TAB>(dyn_smem, fwd, inv, lin_lut, (sizeof(T) != 1 ? kInvSfuF32 : kInvSfuU8) < 3);
     // L349: ((lab - mu_s) / (sigma_s + 1e-8)) * sigma_r + mu_r, composed with LAB <-> (fx, fy, fz)
     const FMap fm = make_fmap(src_mean, src_std, ref_mean, ref_std);
     const int64_t groups_per_img = hw / kPix;
@@ -472,7 +496,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
                 xyz_to_linear(r[k], gr[k], b[k], lr, lg, lb);
                 if constexpr (TAB) {
                     // the clamp of the output (L96) commutes with the monotone transfer curve
-                    constexpr int kSfu = sizeof(T) == 4 ? kInvSfuF32 : kInvSfuU8;
+                    constexpr int kSfu = sizeof(T) != 1 ? kInvSfuF32 : kInvSfuU8;
                     r[k] = kSfu >= 1 ? linear_to_srgb(lr) : curve<kInvN>(inv, __saturatef(lr));
                     gr[k] = kSfu >= 2 ? linear_to_srgb(lg) : curve<kInvN>(inv, __saturatef(lg));
                     b[k] = kSfu >= 3 ? linear_to_srgb(lb) : curve<kInvN>(inv, __saturatef(lb));
@@ -490,6 +514,15 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
                 } else {
                     obase[0] = r[0]; obase[hw] = gr[0]; obase[2 * hw] = b[0];
                 }
+            } else if constexpr (sizeof(T) == 2) {
+                // float16 / bfloat16 out: the float32 result rounded to the input's dtype (torch_backend.py:L131)
+                if constexpr (VEC) {
+                    wr[2 * ch] = Half2IO<T>::pack(r[0], r[1]); wr[2 * ch + 1] = Half2IO<T>::pack(r[2], r[3]);
+                    wg[2 * ch] = Half2IO<T>::pack(gr[0], gr[1]); wg[2 * ch + 1] = Half2IO<T>::pack(gr[2], gr[3]);
+                    wb[2 * ch] = Half2IO<T>::pack(b[0], b[1]); wb[2 * ch + 1] = Half2IO<T>::pack(b[2], b[3]);
+                } else {
+                    obase[0] = Half2IO<T>::narrow(r[0]); obase[hw] = Half2IO<T>::narrow(gr[0]); obase[2 * hw] = Half2IO<T>::narrow(b[0]);
+                }
             } else {
                 // uint8 out: trunc(clamp(rgb * 255, 0, 255))  (torch_backend.py:L122-131)
                 if constexpr (VEC) {
@@ -501,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
                 }
             }
         }
-        if constexpr (sizeof(T) == 1 && VEC) {
+        if constexpr (sizeof(T) != 4 && VEC) {
             st_stream(reinterpret_cast<uint4 *>(obase), make_uint4(wr[0], wr[1], wr[2], wr[3]));
             st_stream(reinterpret_cast<uint4 *>(obase + hw), make_uint4(wg[0], wg[1], wg[2], wg[3]));
             st_stream(reinterpret_cast<uint4 *>(obase + 2 * hw), make_uint4(wb[0], wb[1], wb[2], wb[3]));
@@ -538,7 +571,7 @@ static int launch_stats(const T *p, int64_t n, int64_t hw, double *sums, cudaStr
 template <typename T, bool VEC, bool TAB>
 static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *src_mean, const float *src_std, const float *ref_mean, const float *ref_std, cudaStream_t stream) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
-    const size_t smem = TAB ? ((sizeof(T) == 4 ? kInvSfuF32 : kInvSfuU8) >= 3 ? kFwdTableBytes : kTableBytes) : 0;
+    const size_t smem = TAB ? ((sizeof(T) != 1 ? kInvSfuF32 : kInvSfuU8) >= 3 ? kFwdTableBytes : kTableBytes) : 0;
     if (TAB) SX_CUDA(cudaFuncSetAttribute(apply_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
     prefer_l1(apply_kernel<T, VEC, TAB>, kThreads, smem);
@@ -573,12 +606,22 @@ int sx_reinhard_stats(const void *images, int dtype, int64_t n, int64_t h, int64
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int64_t hw = h * w;
     if (n == 0 || hw == 0) return SX_OK;
-    const bool tab = use_tables(n, hw) && dtype == SX_F32;  // pass 1 only needs the forward curve
+    const bool tab = use_tables(n, hw) && dtype != SX_U8;  // pass 1 only needs the forward curve
     int rc = SX_OK;
     if (dtype == SX_F32) {
         const float *p = static_cast<const float *>(images);
 #define SX_CALL(T, V, B) launch_stats<T, V, B>(p, n, hw, sums, stream)
         SX_REINHARD_DISPATCH(float, can_vectorize<float>(p, nullptr, hw), tab, SX_CALL);
+#undef SX_CALL
+    } else if (dtype == SX_F16) {
+        const __half *p = static_cast<const __half *>(images);
+#define SX_CALL(T, V, B) launch_stats<T, V, B>(p, n, hw, sums, stream)
+        SX_REINHARD_DISPATCH(__half, can_vectorize<__half>(p, nullptr, hw), tab, SX_CALL);
+#undef SX_CALL
+    } else if (dtype == SX_BF16) {
+        const __nv_bfloat16 *p = static_cast<const __nv_bfloat16 *>(images);
+#define SX_CALL(T, V, B) launch_stats<T, V, B>(p, n, hw, sums, stream)
+        SX_REINHARD_DISPATCH(__nv_bfloat16, can_vectorize<__nv_bfloat16>(p, nullptr, hw), tab, SX_CALL);
 #undef SX_CALL
     } else {
         const uint8_t *p = static_cast<const uint8_t *>(images);
@@ -611,6 +654,18 @@ int sx_reinhard_apply(const void *images, int dtype, int64_t n, int64_t h, int64
         float *o = static_cast<float *>(out);
 #define SX_CALL(T, V, B) launch_apply<T, V, B>(p, o, n, hw, src_mean, src_std, ref_mean, ref_std, stream)
         SX_REINHARD_DISPATCH(float, can_vectorize<float>(p, o, hw), tab, SX_CALL);
+#undef SX_CALL
+    } else if (dtype == SX_F16) {
+        const __half *p = static_cast<const __half *>(images);
+        __half *o = static_cast<__half *>(out);
+#define SX_CALL(T, V, B) launch_apply<T, V, B>(p, o, n, hw, src_mean, src_std, ref_mean, ref_std, stream)
+        SX_REINHARD_DISPATCH(__half, can_vectorize<__half>(p, o, hw), tab, SX_CALL);
+#undef SX_CALL
+    } else if (dtype == SX_BF16) {
+        const __nv_bfloat16 *p = static_cast<const __nv_bfloat16 *>(images);
+        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
+#define SX_CALL(T, V, B) launch_apply<T, V, B>(p, o, n, hw, src_mean, src_std, ref_mean, ref_std, stream)
+        SX_REINHARD_DISPATCH(__nv_bfloat16, can_vectorize<__nv_bfloat16>(p, o, hw), tab, SX_CALL);
 #undef SX_CALL
     } else {
         const uint8_t *p = static_cast<const uint8_t *>(images);

@@ -13,7 +13,7 @@ import ctypes
 import torch
 
 from stainx_b200 import _native as nv
-from stainx_b200._native import SX_F32, SX_NCHW, SX_NHWC, SX_U8, check
+from stainx_b200._native import SX_BF16, SX_F16, SX_F32, SX_NCHW, SX_NHWC, SX_U8, check
 
 __all__ = [
     "MacenkoWorkspace",
@@ -36,7 +36,11 @@ def _dtype_code(t: torch.Tensor) -> int:
         return SX_U8
     if t.dtype == torch.float32:
         return SX_F32
-    raise TypeError(f"native kernels take uint8 or float32 images, got {t.dtype}")
+    if t.dtype == torch.float16:
+        return SX_F16
+    if t.dtype == torch.bfloat16:
+        return SX_BF16
+    raise TypeError(f"native kernels take uint8, float32, float16 or bfloat16 images, got {t.dtype}")
 
 
 def _check_images(images: torch.Tensor, layout: int = SX_NCHW) -> tuple[int, int, int]:
@@ -308,6 +312,8 @@ def _macenko_out(images: torch.Tensor, unit: bool) -> torch.Tensor:
     # normalize_to_0_1 division follows, which makes it float32 (_template.py:L111-112).
     if images.dtype == torch.uint8 and not unit:
         return torch.empty_like(images)
+    if images.dtype in (torch.float16, torch.bfloat16):
+        return torch.empty_like(images)  # 16-bit float in -> the same dtype out (the reference casts back, torch_backend.py:L131)
     return torch.empty(images.shape, dtype=torch.float32, device=images.device)
 
 
