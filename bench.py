@@ -340,6 +340,10 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
         self.pg = "world" if self.distributed else None
         self._flush = None
+        # pinned host buffers of the e2e leg should live on the GPU's own NUMA node
+        from stainx_b200.ingest import bind_host_thread_to_device
+
+        self.host_cores = bind_host_thread_to_device(self.local_rank)
 
     def barrier(self):
         if self.distributed:
@@ -822,7 +826,7 @@ def measure_e2e(ctx: Ctx, wl: Workload, steps: int) -> dict:
     res = {"value": mp / (ms / 1e3), "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": steps,
            "mode": "pipelined (depth 2)" if over <= ser else "one batch in flight", "pipelined_ms_per_step": over, "serial_ms_per_step": ser,
            "copy_only_ms_per_step": ceil_ms, "ceiling_gbs": (h2d + d2h) * ctx.world / (ceil_ms / 1e3) / 1e9, "achieved_gbs": (h2d + d2h) * ctx.world / (ms / 1e3) / 1e9,
-           "frac_of_copy_ceiling": ceil_ms / ms, "result_equals_device_resident": same,
+           "frac_of_copy_ceiling": ceil_ms / ms, "result_equals_device_resident": same, "host_cores_bound_to_gpu_numa": (len(ctx.host_cores) if ctx.host_cores else None),
            "api": f"stainx_b200.ingest.HostStream({wl.method} normalizer).submit(pinned batch, pinned out): H2D + {wl.config} step + D2H per step; ceiling = the same H2D and D2H copies alone, both directions at once, all ranks together"}
     del pipe
     return res
@@ -888,7 +892,7 @@ def main() -> None:
     # ---- e2e ------------------------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(ctx, wl, max(4, min(steps, 12)))
+        e2e = measure_e2e(ctx, wl, max(8, min(steps, 32)))  # enough batches that pipeline fill / drain (one copy each) is amortised
 
     # ---- side measurements of the other workloads (default line only) --------------------------
     methods = {args.config: {"mp_per_s": value, "algo_gbs_per_gpu": step_gbs, "frac_of_peak": step_gbs / peak_gbs, "ms": ms_per_step}}

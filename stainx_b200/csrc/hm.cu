@@ -1266,8 +1266,16 @@ static int apply_impl(const void *images, int dtype, int layout, int64_t n, int6
             apply_nhwc_kernel<uint8_t><<<grid, kThreads, 0, stream>>>(static_cast<const uint8_t *>(images), static_cast<uint8_t *>(out), total, lut);
         } else {
             unsigned grid = stream_grid((total / 12 + kThreads - 1) / kThreads + 1, 8);
-            prefer_l1(apply_nhwc_kernel<float>, kThreads);
-            apply_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), total, lut);
+            if (dtype == SX_F32) {
+                prefer_l1(apply_nhwc_kernel<float>, kThreads);
+                apply_nhwc_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<const float *>(images), static_cast<float *>(out), total, lut);
+            } else if (dtype == SX_F16) {
+                prefer_l1(apply_nhwc_kernel<__half>, kThreads);
+                apply_nhwc_kernel<__half><<<grid, kThreads, 0, stream>>>(static_cast<const __half *>(images), static_cast<__half *>(out), total, lut);
+            } else {
+                prefer_l1(apply_nhwc_kernel<__nv_bfloat16>, kThreads);
+                apply_nhwc_kernel<__nv_bfloat16><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(images), static_cast<__nv_bfloat16 *>(out), total, lut);
+            }
         }
         SX_LAUNCHED("apply_nhwc_kernel");
         return SX_OK;

@@ -23,7 +23,38 @@ from typing import Any, Callable
 
 import torch
 
-__all__ = ["HostStream", "Ticket"]
+__all__ = ["HostStream", "Ticket", "bind_host_thread_to_device"]
+
+
+def bind_host_thread_to_device(device: torch.device | int | None = None) -> list[int] | None:
+    """Restrict the calling process to the CPU cores NVML reports as local to `device`'s PCIe root (its NUMA node),
+    so that pinned host buffers allocated AFTERWARDS are first-touched on that node: a pinned buffer on the
+    far socket crosses the inter-socket link on every copy and caps host<->device bandwidth.  Call it once per
+    rank before allocating pinned memory.  Returns the core list, or None when NVML / the OS call is unavailable
+    (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+
+        idx = torch.cuda.current_device() if device is None else (device if isinstance(device, int) else (torch.device(device).index or 0))
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if idx < len(ids) and ids[idx].isdigit():
+                idx = int(ids[idx])
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < ncpu]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 - best effort: no NVML, no sched_setaffinity, restricted container
+        return None
 
 
 class Ticket:
