@@ -671,63 +671,118 @@ class MacenkoWorkload(Workload):
             "macenko::apply_kernel": {"algo_bytes": (in_b + 12.0) * self.px, "ms": _events_mean(marks, 6, 7)},
         }
 
+    def _stain_like(self, n: int, seed0: int):
+        """Beer-Lambert H&E-like tiles of this config's shape and dtype (the reference's own Macenko fixture,
+        tests/torch_interface/test_correctness_against_references.py:L41-54): a well-posed stain plane."""
+        torch = self.ctx.torch
+        import torch.nn.functional as F  # noqa: N812
+
+        he_ref = torch.tensor([[0.5626, 0.2159], [0.7201, 0.8012], [0.4062, 0.5581]])
+        scales = [1.15, 0.9, 1.05, 0.85, 1.1, 0.95, 1.0, 1.2]
+        tiles = []
+        for i in range(n):
+            g = torch.Generator().manual_seed(seed0 + i)
+            gh, gw = self.h // 8, self.w // 8
+            c_h = F.interpolate(torch.rand(1, 1, gh, gw, generator=g), size=(self.h, self.w), mode="bilinear", align_corners=False).squeeze()
+            c_e = F.interpolate(torch.rand(1, 1, gh, gw, generator=g), size=(self.h, self.w), mode="bilinear", align_corners=False).squeeze()
+            od = torch.einsum("cs,shp->chp", he_ref * scales[(seed0 + i) % 8], torch.stack([0.3 + 1.8 * c_h, 0.2 + 1.0 * c_e]))
+            tiles.append((240.0 * torch.exp(-od)).clamp(0, 255).round().to(torch.uint8))
+        t = torch.stack(tiles)
+        return t if self.dt == "u8" else t.float() / 255.0
+
     def parity(self):
-        """Outputs of a few images of this rank's step against the CPU oracle under the both-signs protocol
-        (uniform noise is near-isotropic in OD: the sign of the middle eigenvector is not reproducible, SURVEY
-        7 H-a), max-abs <= 1e-3 on [0,1].  c4: the sharded pooled fit is identical on all ranks and matches the
-        single-device pooled fit of the gathered batch (HE <= 1e-4, maxC rel <= 1e-3)."""
+        """Two inputs, both outside the timed region.
+        (1) STAIN-LIKE tiles of the config's shape and dtype through the config's own public call, against the CPU
+        oracle at the north_star bars: fitted HE <= 1e-4, maxC rel <= 1e-3, output max-abs <= 1e-3 on [0,1] (uint8 in:
+        one grey level on < 1 % of the pixels).  c4: the tiles are sharded over the ranks, the pooled fit must be
+        identical on all ranks and match the oracle's pooled fit of the gathered tiles.
+        (2) The TIMED batch (uniform noise, BASELINE's distribution): c4's sharded pooled fit against the single-device
+        pooled fit of the gathered batch (HE <= 1e-4, maxC rel <= 1e-3); outputs against the oracle per image under the
+        better middle-eigenvector sign.  Noise is the ill-posed input of SURVEY 7 H-a (isotropic OD covariance: the stain
+        plane is decided by rounding), so its bar is max-abs <= 2e-3 with <= 1e-6 of the values above 1e-3 for c3 / c5;
+        for c4 the TARGET is itself fitted on pooled noise, and the comparison is reported without gating."""
         ctx, torch = self.ctx, self.ctx.torch
         import numpy as np
 
         from oracle import oracle as ox
-        from stainx_b200 import Macenko
+        from stainx_b200 import Macenko, StainNormalizerTransform
 
-        out = self.step()
         res: dict = {}
         ok = True
-        he, maxc = self.norm._stain_matrix, self.norm._target_max_conc
+        if ctx.rank == 0:
+            ox.set_num_threads(os.cpu_count())
+        # ---- (1) stain-like tiles, strict bars -------------------------------------------------------------
+        k = 2 if self.h * self.w <= 1024 * 1024 else 1
+        ref_t = self._stain_like(1, 42)
+        tiles = self._stain_like(k, 123 + 16 * ctx.rank)
+        if self.config == "c5":
+            mod = StainNormalizerTransform(method="macenko", mode="reference", reference=ref_t.to(ctx.dev), device=ctx.dev, backend="torch_cuda", process_group=ctx.pg)
+            norm, out_t = mod.normalizer, mod(tiles.to(ctx.dev))
+            fit_on = ref_t
+        elif self.config == "c4":
+            norm = Macenko(device=ctx.dev, backend="torch_cuda", normalize_to_0_1=True, process_group=ctx.pg)
+            out_t = norm.fit(tiles.to(ctx.dev)).transform(tiles.to(ctx.dev))
+            fit_on = _np(ctx.gather_cat(tiles.to(ctx.dev)))
+            fits = ctx.gather_cat(torch.cat([norm._stain_matrix.reshape(-1), norm._target_max_conc.reshape(-1)]).reshape(1, 8))
+            res["stain_like_fit_identical_on_all_ranks"] = ctx.all_ok(bool((fits == fits[0:1]).all()))
+            ok = ok and res["stain_like_fit_identical_on_all_ranks"]
+        else:
+            norm = Macenko(device=ctx.dev, backend="torch_cuda", normalize_to_0_1=True, process_group=ctx.pg)
+            norm.fit_broadcast(ref_t.to(ctx.dev), src=0) if ctx.distributed else norm.fit(ref_t.to(ctx.dev))
+            out_t = norm.transform(tiles.to(ctx.dev))
+            fit_on = ref_t
+        he, maxc = _np(norm._stain_matrix), _np(norm._target_max_conc)
+        d_he = d_mc = d_out = frac = 0.0
+        if ctx.rank == 0:
+            o_he, o_mc = ox.macenko_fit(fit_on if isinstance(fit_on, np.ndarray) else _np(fit_on))
+            d_he, d_mc = float(np.abs(he - o_he).max()), float(np.abs(maxc / o_mc - 1).max())
+            want = ox.macenko_transform(_np(tiles), he, maxc).astype(np.float64)
+            got = _np(out_t).astype(np.float64) * 255.0
+            d = np.abs(got - want)
+            if self.dt == "u8":
+                d_out, frac = float(d.max()), float((d > 1e-3).mean())
+                ok = ok and d_out <= 1.0 + 1e-3 and frac < 0.01
+            else:
+                d_out = float(d.max()) / 255.0
+                ok = ok and d_out <= 1e-3
+            ok = ok and d_he <= 1e-4 and d_mc <= 1e-3
+        res["stain_like"] = {"images_per_rank": k, "he_max_abs_vs_oracle": d_he, "maxc_rel_vs_oracle": d_mc,
+                             ("grey_levels_max_vs_oracle" if self.dt == "u8" else "out_max_abs_vs_oracle"): d_out, "bars": "HE <= 1e-4, maxC rel <= 1e-3, " + ("<= 1 grey level on < 1 % of the pixels" if self.dt == "u8" else "output <= 1e-3 on [0,1]")}
+        if self.dt == "u8":
+            res["stain_like"]["frac_pixels_off_by_one"] = frac
+        # ---- (2) the timed noise batch ----------------------------------------------------------------------
+        out = self.step()
+        he_t, maxc_t = self.norm._stain_matrix, self.norm._target_max_conc
         if self.config == "c4":
-            hes = ctx.gather_cat(torch.cat([he.reshape(-1), maxc.reshape(-1)]).reshape(1, 8))
+            hes = ctx.gather_cat(torch.cat([he_t.reshape(-1), maxc_t.reshape(-1)]).reshape(1, 8))
             same = bool((hes == hes[0:1]).all())
             whole = ctx.gather_cat(self.src)
             single = Macenko(device=ctx.dev, backend="torch_cuda").fit(whole)
-            d_he = float((single._stain_matrix - he).abs().max())
-            d_mc = float((single._target_max_conc / maxc - 1).abs().max())
-            res.update(fit_identical_on_all_ranks=ctx.all_ok(same), he_max_abs_sharded_vs_single_device=ctx.max_over_ranks(d_he), maxc_rel_sharded_vs_single_device=ctx.max_over_ranks(d_mc))
-            ok = ok and res["fit_identical_on_all_ranks"] and res["he_max_abs_sharded_vs_single_device"] <= 1e-4 and res["maxc_rel_sharded_vs_single_device"] <= 1e-3
+            d_he = float((single._stain_matrix - he_t).abs().max())
+            d_mc = float((single._target_max_conc / maxc_t - 1).abs().max())
+            res["noise_batch"] = {"fit_identical_on_all_ranks": ctx.all_ok(same), "he_max_abs_sharded_vs_single_device": ctx.max_over_ranks(d_he), "maxc_rel_sharded_vs_single_device": ctx.max_over_ranks(d_mc),
+                                  "images_gathered": int(whole.shape[0])}
+            ok = ok and res["noise_batch"]["fit_identical_on_all_ranks"] and res["noise_batch"]["he_max_abs_sharded_vs_single_device"] <= 1e-4 and res["noise_batch"]["maxc_rel_sharded_vs_single_device"] <= 1e-3
             del whole
-            if ctx.rank == 0:  # the pooled fit itself against the oracle, on a pooled sub-batch (both signs)
-                ox.set_num_threads(os.cpu_count())
-                sub = self.src[:4].contiguous()
-                g_he, g_mc = self.ops.macenko_fit(sub)
-                cands = [ox.macenko_fit(_np(sub), mid_sign=s) for s in (1, -1)]
-                d = min(max(float(np.abs(_np(g_he) - c[0]).max()), float(np.abs(_np(g_mc) / c[1] - 1).max()) * 0.1) for c in cands)
-                res["pooled_fit_4_images_vs_oracle"] = d
-                ok = ok and d <= 1e-4
-        k = 2 if self.h * self.w <= 1024 * 1024 else 1
-        d_or = 0.0
+        else:
+            res["noise_batch"] = {}
+        kn = 2 if self.h * self.w <= 1024 * 1024 else 1
+        d_or = frac = 0.0
         if ctx.rank == 0:
-            ox.set_num_threads(os.cpu_count())
-            sub = _np(self.src[:k])
-            cand = [ox.macenko_transform(sub, _np(he), _np(maxc), mid_signs=[s] * k) for s in (1, -1)]
-            o = _np(out[:k]).astype(np.float64)
-            if self.dt == "u8":  # uint8 in: the reference truncates to a grey level, then / 255 -> compare in grey levels
-                diffs = [np.abs(o * 255.0 - c.astype(np.float64)).reshape(k, -1).max(axis=1) for c in cand]
-                d_or = float(np.minimum(*diffs).max())
-                res["bar_oracle"] = "<= 1 grey level (uint8 truncation knife edge)"
-                ok = ok and d_or <= 1.0 + 1e-3
+            sub = _np(self.src[:kn])
+            cand = [ox.macenko_transform(sub, _np(he_t), _np(maxc_t), mid_signs=[s] * kn).astype(np.float64) for s in (1, -1)]
+            o = _np(out[:kn]).astype(np.float64) * 255.0
+            per_img = [min((np.abs(o[i] - c[i]) for c in cand), key=lambda x: x.max()) for i in range(kn)]
+            if self.dt == "u8":
+                d_or, frac = float(max(d.max() for d in per_img)), float(max((d > 1e-3).mean() for d in per_img))
+                gate = d_or <= 1.0 + 1e-3
             else:
-                # per image: the better sign.  Noise is the ill-posed input (isotropic OD covariance): float32-vs-float64
-                # covariance rounding moves single pixels by ~1e-3, so the bar on noise is max-abs <= 2e-3 with at most
-                # one value in a million above 1e-3 (stain-like inputs are held to 1e-3 in tests/).
-                per_img = [min((np.abs(o[i] - c[i].astype(np.float64) / 255.0) for c in cand), key=lambda x: x.max()) for i in range(k)]
-                d_or = float(max(d.max() for d in per_img))
-                frac = float(max((d > 1e-3).mean() for d in per_img))
-                res["frac_above_1e-3"] = frac
-                res["bar_oracle"] = "max-abs <= 2e-3 and <= 1e-6 of the values above 1e-3 (uniform noise: ill-posed stain plane)"
-                ok = ok and d_or <= 2e-3 and frac <= 1e-6
-            res["oracle_images"] = k
-        res["max_abs_vs_oracle_both_signs"] = ctx.max_over_ranks(d_or)
+                d_or, frac = float(max(d.max() for d in per_img)) / 255.0, float(max((d > 1e-3 * 255.0).mean() for d in per_img))
+                gate = d_or <= 2e-3 and frac <= 1e-6
+            if self.config != "c4":
+                ok = ok and gate
+        res["noise_batch"].update({"oracle_images": kn, ("grey_levels_max_vs_oracle_both_signs" if self.dt == "u8" else "out_max_abs_vs_oracle_both_signs"): d_or, "frac_values_above_bar": frac,
+                                   "gating": self.config != "c4"})
         res["ok"] = ctx.all_ok(ok)
         return res
 
