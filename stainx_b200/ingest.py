@@ -94,6 +94,7 @@ class HostStream:
         self._s_compute = torch.cuda.Stream(self.device)
         self._s_out = torch.cuda.Stream(self.device)
         self._slots: list[dict] = [{"buf": None, "free": None} for _ in range(depth)]
+        self._inflight: list[torch.cuda.Event] = []  # completion events of the batches enqueued and not yet waited for
         self._next = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -105,6 +106,12 @@ class HostStream:
             raise ValueError("HostStream.submit expects a host tensor")
         slot = self._slots[self._next % len(self._slots)]
         self._next += 1
+        # Back-pressure: never more than depth + 1 batches enqueued.  Without it a producer that submits faster than
+        # the link drains piles up results whose memory the caching allocator cannot recycle (each is held by a
+        # pending copy-out): every further batch then costs a cudaMalloc, which synchronises the device (measured:
+        # 14.8 ms instead of 1.3 ms per 31 MB batch with 32 batches enqueued at once).
+        while len(self._inflight) > len(self._slots):
+            self._inflight.pop(0).synchronize()
         with torch.cuda.device(self.device):
             # Whatever the caller enqueued on its current stream before this submit -- above all the
             # kernels of fit() / fit_reference(), whose fitted tensors the transform below reads -- must
@@ -139,6 +146,7 @@ class HostStream:
                 out.record_stream(self._s_out)
                 done = torch.cuda.Event()
                 done.record(self._s_out)
+        self._inflight.append(done)
         self.h2d_bytes += host_in.numel() * host_in.element_size()
         self.d2h_bytes += host_out.numel() * host_out.element_size()
         return Ticket(done, host_out)
