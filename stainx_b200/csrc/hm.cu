@@ -255,6 +255,12 @@ __device__ __forceinline__ void lane_count4(unsigned w, unsigned base) {  // bas
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a3) : "memory");
 }
 
+// (Run-length merging inside the word -- a run of equal neighbouring bytes becomes ONE update carrying the run's
+// length, `red.shared.add.u32 [a], len` -- was built and measured in round 2 on 64 x 3 x 1024^2: noise 217 us, a
+// flat batch 197 us, tiled real H&E crops 232 us, against 60 us for the kernel below on all three
+// (profiles/r02_hm_hist_runlength_merge_experiment.log).  The +1 form compiles to ATOMS.POPC.INC, which the unit
+// retires at 2.1 clk per warp; an update with a register addend is ATOMS.ADD and is ~13x slower per update, so even
+// a batch that needs 4x fewer updates loses.  Merging only pays if the addend is the constant 1.)
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::kThreads, 1) hist_u8_planar_lane_tma_kernel(const uint8_t *__restrict__ img, int64_t hw, int64_t n_img, int64_t tiles_per_plane, unsigned long long *__restrict__ counts) {
     constexpr int kLaneWarps = Cfg::kWarps, kLaneThreads = Cfg::kThreads, kCountThreads = Cfg::kCountThreads, kLaneTileVecs = Cfg::kTileVecs, kLanePerThread = Cfg::kPerThread, kLaneStages = Cfg::kStages;
