@@ -18,7 +18,7 @@ src = (torch.rand((64, 3, 1024, 1024), device=dev, generator=g) * 255).round().t
 ref = (torch.rand((1, 3, 1024, 1024), device=dev, generator=g) * 255).round().to(torch.uint8)
 ref_hist = ops.hm_fit(ref)
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-nv.lib().sx_hm_set_tuning(mode, 8, 16)
+nv.lib().sx_hm_set_tuning(mode, -1, -1)
 for _ in range(3):
     out = ops.hm_transform(src, ref_hist)
 const = torch.full_like(src, 200)
