@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the secondary comparator (the reference's own CUDA extension, oracle/_ref)")
     args = ap.parse_args()
     if args.config is None:
         args.config = {"hm": "c2", "macenko": "c3", "reinhard": "reinhard", None: "c2"}[args.method]
@@ -887,6 +888,55 @@ def measure_e2e(ctx: Ctx, wl: Workload, steps: int) -> dict:
     return res
 
 
+def measure_reference_cuda(ctx: Ctx, wl: Workload, ms_ours: float) -> dict:
+    """SECONDARY comparator (N = 1): the reference's own CUDA extension (`stainx_cuda_torch`, built by
+    oracle/build_ref_cuda.py from the sources under /root/reference with the reference's flags) on the same
+    device-resident batch, called exactly as the reference's torch_cuda backend calls it
+    (src/stainx/backends/torch_cuda_backend.py:L36-131).  Reference-mode transform only: the reference fits on the
+    CPU.  Reported beside the CPU baseline; it is not the oracle and never on the product path."""
+    torch = ctx.torch
+    try:
+        from oracle import build_ref_cuda
+
+        ext = build_ref_cuda.load()
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    if ext is None:
+        return {"unavailable": "oracle/_ref/stainx_cuda_torch.so was not built (python oracle/build_ref_cuda.py in the build container)"}
+    norm = wl.norm
+    if wl.method == "hm":
+        ref_hist = torch.stack(norm._ref_histograms_256).contiguous()
+        fn = lambda: ext.histogram_matching(wl.src, ref_hist)  # noqa: E731
+    elif wl.method == "reinhard":
+        fn = lambda: ext.reinhard(wl.src, norm._reference_mean, norm._reference_std)  # noqa: E731
+    else:
+        he, maxc = norm._stain_matrix, norm._target_max_conc
+        if he is None:
+            he, maxc = wl.ops.macenko_fit(wl.src[:1])
+        fn = lambda: ext.macenko(wl.src, he, maxc) / 255.0  # noqa: E731  (normalize_to_0_1 is a separate pass in the reference, _template.py:L111-112)
+    try:
+        ref_out = fn()
+        torch.cuda.synchronize()
+        ours = wl.step() if wl.config not in ("c1", "c4") else wl.norm.transform(wl.src)
+        diff = float((ref_out.float() - ours.float()).abs().max())
+        del ref_out, ours
+        a, b = ctx.ev(), ctx.ev()
+        k = 5
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / k
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"reference extension failed on this workload: {type(exc).__name__}: {exc}"[:300]}
+    torch.cuda.empty_cache()
+    mp = wl.px / 1e6
+    return {"value": mp / (ms / 1e3), "unit": "MP/s", "ms_per_step": ms, "steps": k, "speedup_of_this_repo": ms / ms_ours, "max_abs_diff_vs_this_repo": diff,
+            "what": "rendeirolab/stainx v0.1.4 stainx_cuda_torch (its own kernels + ATen pipeline), reference-mode transform of the same device-resident batch, compiled for sm_100 with the reference's flags",
+            "note": "secondary comparator; the oracle and the CPU baseline are the reference's torch CPU backend" + ("; this config's step also fits (CPU-side in the reference): transform only here" if wl.config in ("c1", "c4") else "")}
+
+
 def main() -> None:
     args = parse_args()
     _guard_stdout()
@@ -949,6 +999,21 @@ def main() -> None:
     if not args.no_e2e:
         e2e = measure_e2e(ctx, wl, max(8, min(steps, 32)))  # enough batches that pipeline fill / drain (one copy each) is amortised
 
+    # ---- secondary comparator: the reference's own CUDA extension (N = 1) ------------------------
+    ref_cuda = None
+    if not ctx.distributed and not args.no_ref_cuda:
+        ms_transform = ms_per_step
+        if args.config in ("c1", "c4"):  # their step includes the fit: compare transform with transform
+            a, b = ctx.ev(), ctx.ev()
+            wl.norm.transform(wl.src)
+            a.record()
+            for _ in range(5):
+                wl.norm.transform(wl.src)
+            b.record()
+            torch.cuda.synchronize()
+            ms_transform = a.elapsed_time(b) / 5
+        ref_cuda = measure_reference_cuda(ctx, wl, ms_transform)
+
     # ---- side measurements of the other workloads (default line only) --------------------------
     methods = {args.config: {"mp_per_s": value, "algo_gbs_per_gpu": step_gbs, "frac_of_peak": step_gbs / peak_gbs, "ms": ms_per_step}}
     if args.config == "c2" and not args.no_extras:
@@ -975,7 +1040,7 @@ def main() -> None:
             "metric": "megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": wl.dt, "data": "synthetic",
             "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "parity_check": parity, "methods": methods, **wl.extra,
+            "parity_check": parity, "reference_cuda_extension": ref_cuda, "methods": methods, **wl.extra,
         }
         emit(line)
     bad = parity is not None and not parity.get("ok")
