@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SX_ABI_VERSION 1
+#define SX_ABI_VERSION 2 /* 2: SX_F16 / SX_BF16, sx_peer_status*, sx_macenko_hist level 2, STATUS word 3, development hooks declared */
 
 enum sx_status { SX_OK = 0, SX_ERR_INVALID = 1, SX_ERR_CUDA = 2, SX_ERR_UNSUPPORTED = 3 };
 /* SX_F16 / SX_BF16: float images in [0,1] stored as IEEE half / bfloat16.  The reference widens such tensors to

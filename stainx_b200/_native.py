@@ -79,6 +79,7 @@ _RESTYPES = {
     "sx_macenko_peer_scratch_bytes": _i64,
 }
 
+ABI_VERSION = 2  # include/stainx_b200.h: SX_ABI_VERSION
 SX_U8, SX_F32, SX_F16, SX_BF16 = 0, 1, 2, 3
 SX_NCHW, SX_NHWC = 0, 1
 SX_STAGE_ANGLE, SX_STAGE_CONC = 0, 1
@@ -94,8 +95,8 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, _int)
-    if lib.sx_abi_version() != 1:
-        raise ImportError(f"libstainx_b200 ABI {lib.sx_abi_version()} != 1; rebuild with `python -m stainx_b200.build`")
+    if lib.sx_abi_version() != ABI_VERSION:
+        raise ImportError(f"libstainx_b200 ABI {lib.sx_abi_version()} != {ABI_VERSION}; rebuild with `python -m stainx_b200.build`")
     return lib
 
 

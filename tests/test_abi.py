@@ -37,7 +37,7 @@ def test_bindings_cover_the_header():
 
     assert set(declared_functions()) <= set(_native.PROTOTYPES), set(declared_functions()) - set(_native.PROTOTYPES)
     assert _native.FUNCTIONS_AVAILABLE
-    assert _native.lib().sx_abi_version() == 1
+    assert _native.lib().sx_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_host_only_entry_points():
