@@ -57,7 +57,10 @@ r_outs = [rh.transform(wholef[lo:hi].to(dev)) for _ in range(4)]
 rimpl._exchange = False
 r_nccl = rh.transform(wholef[lo:hi].to(dev))
 r_single = Reinhard(device=dev, backend="torch_cuda").fit(reff.to(dev)).transform(wholef.to(dev))[lo:hi]
-r_ok = rex is not None and all(float((o - r_nccl).abs().max()) <= 1e-6 for o in r_outs) and float((r_nccl - r_single).abs().max()) <= 1e-5
+# peers == NCCL exactly (same kernels, same sums); vs the single-device transform of the whole batch 1e-4: a shard below
+# 2 MP takes the SFU transfer curves and the whole batch the interpolated tables (reinhard.cu: use_tables), which differ
+# by ~1.5e-5 -- both are within 1e-3 of the oracle (tests/test_gpu_parity.py)
+r_ok = rex is not None and all(float((o - r_nccl).abs().max()) <= 1e-6 for o in r_outs) and float((r_nccl - r_single).abs().max()) <= 1e-4
 print(f"rank {rank}: reinhard peers {'ON' if rex is not None else 'unavailable'} max|peers-nccl|={max(float((o - r_nccl).abs().max()) for o in r_outs):.2e} max|nccl-single|={float((r_nccl - r_single).abs().max()):.2e}", flush=True)
 ok = ok and (r_ok or rex is None)
 
@@ -93,6 +96,21 @@ for label, use_peers in (("peers", True), ("nccl", False)):
     if rank == 0:
         print(f"macenko pooled fit 16x1024^2 f32 per rank, exchange={label}: {(time.perf_counter() - t0) / 20 * 1e6:.1f} us", flush=True)
 del bigf
+
+# StainNormalizerTransform(mode="batch") on a sharded batch: the rank that owns global image `batch_ref_index` fits,
+# the parameters are broadcast; every rank's result must equal the single-device module's on the gathered batch
+from stainx_b200 import StainNormalizerTransform  # noqa: E402
+
+b_ok = True
+for method, tol in (("histogram_matching", 0.0), ("reinhard", 1e-6), ("macenko", 1e-6)):
+    gidx = n_total - 2  # lives on the last rank
+    tm = StainNormalizerTransform(method=method, mode="batch", device=dev, batch_ref_index=gidx, process_group="world")
+    got = tm(tiles[lo:hi].to(dev))
+    want = StainNormalizerTransform(method=method, mode="batch", device=dev, batch_ref_index=gidx)(tiles.to(dev))[lo:hi]
+    d = float((got.float() - want.float()).abs().max())
+    b_ok = b_ok and d <= tol
+    print(f"rank {rank}: batch-mode module {method}: max|sharded-single| = {d:.2e}", flush=True)
+ok = ok and b_ok
 
 # timing of the exchange + LUT phase
 impl._exchange = ex if ex is not None else False
