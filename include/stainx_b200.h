@@ -202,6 +202,15 @@ int64_t sx_macenko_peer_buffer_bytes(void);
 int64_t sx_macenko_peer_scratch_bytes(void);
 int sx_macenko_peer_combine(const void *peer_buffers_dev, int world, int rank, uint32_t epoch,
                             int which, void *scratch, sx_stream_t stream);
+/* The whole sharded pooled fit in one call: begin, moments, the five exchanges (epochs first_epoch .. first_epoch + 4; the
+ * caller advances its epoch counter by 5), basis, both stages' hist / select pairs.  own_buffer = this rank's peer-mapped
+ * buffer (peer_buffers[rank]); exact != 0 uses the exact coarse pass (hist level 2) instead of the sample pass; n = 0 is
+ * allowed (a rank without reference images still takes part in the exchanges); he / maxc (device, optional) receive the
+ * result, which is also in the FIT region of the workspace.  The caller should read STATUS word 0 afterwards and repeat
+ * with exact = 1 if it is non-zero (identical on every rank). */
+int sx_macenko_fit_peers(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev,
+                         void *own_buffer, int world, int rank, uint32_t first_epoch, int exact, void *scratch, float *he,
+                         float *maxc, sx_stream_t stream);
 /* Initialise the workspace (must precede moments). */
 int sx_macenko_begin(void *workspace, int64_t slots, sx_stream_t stream);
 /* M1-M3: OD = -ln((255x+1)/240); mask min_c OD >= 0.15; accumulates count and shifted first and

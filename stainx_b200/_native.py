@@ -54,6 +54,7 @@ PROTOTYPES: dict[str, list] = {
     "sx_macenko_peer_buffer_bytes": [],
     "sx_macenko_peer_scratch_bytes": [],
     "sx_macenko_peer_combine": [_vp, _int, _int, ctypes.c_uint32, _int, _vp, _vp],
+    "sx_macenko_fit_peers": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _int, _int, ctypes.c_uint32, _int, _vp, _vp, _vp, _vp],
     "sx_macenko_moments": [_vp, _int, _i64, _i64, _i64, _int, _i64, _vp, _i64, _vp],
     "sx_macenko_basis": [_vp, _i64, _i64, _i64, _int, _vp],
     "sx_macenko_moments_fallback": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _i64, _vp],

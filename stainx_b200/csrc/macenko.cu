@@ -1907,6 +1907,40 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
     return rc;
 }
 
+// The sharded pooled fit of one NVLink node as ONE library call: the phase sequence of the header's
+// "Phase order" with sx_macenko_peer_combine after moments and after every hist pass (five exchanges, epochs
+// first_epoch .. first_epoch + 4).  The same kernels as the phase-level calls; what it removes is the host time between
+// ~25 separate calls (each ~8-10 us of interpreter + ctypes), which at 16-64 images per rank is a third of the fit.
+// `own_buffer` = this rank's peer-mapped buffer (the one-slot workspace lives at its start); `exact` != 0 replaces the
+// sample passes by the exact coarse pass (level 2) -- the repeat after a missed bracket.  n may be 0 (a rank without
+// reference images still takes part in every exchange).  he / maxc may be NULL (read the FIT region instead).
+int sx_macenko_fit_peers(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t first_epoch, int exact,
+                         void *scratch, float *he, float *maxc, sx_stream_t s) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    SX_REQUIRE(peer_buffers_dev && own_buffer && scratch, "NULL argument");
+    SX_REQUIRE(first_epoch != 0 && first_epoch + 4 >= first_epoch, "bad first epoch %u", first_epoch);
+    const bool have = n > 0 && h * w > 0;
+    const int coarse = exact ? 2 : 0;
+    int rc;
+    if ((rc = sx_macenko_begin(own_buffer, 1, s))) return rc;
+    if (have && (rc = sx_macenko_moments(images, dtype, n, h, w, 1, 0, own_buffer, 1, s))) return rc;
+    uint32_t epoch = first_epoch;
+    if ((rc = sx_macenko_peer_combine(peer_buffers_dev, world, rank, epoch++, 0, scratch, s))) return rc;
+    if ((rc = sx_macenko_basis(own_buffer, 1, 0, 1, 0, s))) return rc;  // no fallback in fit (L483-487)
+    for (int stage = 0; stage < 2; ++stage) {
+        if (have && (rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, coarse, own_buffer, 1, s))) return rc;
+        if ((rc = sx_macenko_peer_combine(peer_buffers_dev, world, rank, epoch++, 1, scratch, s))) return rc;
+        if ((rc = sx_macenko_select(own_buffer, 1, 0, 1, stage, 0, s))) return rc;  // ranks + brackets, identical on every rank
+        if (have && (rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 1, own_buffer, 1, s))) return rc;
+        if ((rc = sx_macenko_peer_combine(peer_buffers_dev, world, rank, epoch++, 2, scratch, s))) return rc;
+        if ((rc = sx_macenko_select(own_buffer, 1, 0, 1, stage, 1, s))) return rc;
+    }
+    Ws ws(own_buffer, 1);
+    if (he) SX_CUDA(cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
+    if (maxc) SX_CUDA(cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
+    return SX_OK;
+}
+
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     SX_REQUIRE(n > 0 && h * w > 0, "empty reference batch");

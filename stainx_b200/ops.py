@@ -18,7 +18,7 @@ from stainx_b200._native import SX_BF16, SX_F16, SX_F32, SX_NCHW, SX_NHWC, SX_U8
 __all__ = [
     "MacenkoWorkspace",
     "hm_apply", "hm_build_lut", "hm_build_lut_peers", "hm_fit", "hm_hist", "hm_ref_cdf", "hm_ref_hist", "hm_transform", "hm_transform_peers",
-    "macenko_fit", "macenko_peer_combine", "macenko_transform",
+    "macenko_fit", "macenko_fit_peers", "macenko_peer_combine", "macenko_transform",
     "reinhard_apply", "reinhard_finalize", "reinhard_finalize_peers", "reinhard_fit", "reinhard_stats", "reinhard_transform",
 ]
 
@@ -305,6 +305,21 @@ def macenko_peer_combine(exchange, which: int, scratch: torch.Tensor) -> None:
     with torch.cuda.device(dev):
         check(nv.lib().sx_macenko_peer_combine(ctypes.c_void_p(exchange.ptrs_dev), exchange.world, exchange.rank, epoch & 0xFFFFFFFF, int(which), _ptr(scratch), _stream(dev)), "sx_macenko_peer_combine")
     exchange.epoch = epoch
+
+
+def macenko_fit_peers(images: torch.Tensor, exchange, scratch: torch.Tensor, exact: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """The sharded pooled fit of one NVLink node in one library call (five fused exchanges; advances the exchange's
+    epoch by 5).  ``images``: this rank's shard (may hold zero images).  Returns HE (3, 2), maxC (2,)."""
+    n, h, w = _check_images(images)
+    dev = exchange.buf.device
+    he = torch.empty((3, 2), dtype=torch.float32, device=dev)
+    maxc = torch.empty(2, dtype=torch.float32, device=dev)
+    first = exchange.epoch + 1
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_macenko_fit_peers(_ptr(images) if n > 0 else None, _dtype_code(images), n, h, w, ctypes.c_void_p(exchange.ptrs_dev), _ptr(exchange.buf), exchange.world, exchange.rank,
+                                            first & 0xFFFFFFFF, int(exact), _ptr(scratch), _ptr(he), _ptr(maxc), _stream(dev)), "sx_macenko_fit_peers")
+    exchange.epoch += 5
+    return he, maxc
 
 
 def _macenko_out(images: torch.Tensor, unit: bool) -> torch.Tensor:
