@@ -174,7 +174,8 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
     SX_REGION_MOMENTS = 0,  /* double  [slots][12]   reduce: SUM */
-    SX_REGION_ODRANGE = 1,  /* float32 [slots][8]    reduce: MAX  (-min_c, max_c, pad) */
+    SX_REGION_ODRANGE = 1,  /* float32 [slots][8]    reduce: MAX  (-min_c x3, max_c x3, [6] pixels per sampled group of the
+                             *                        rank's kernel variant -- the combined maximum sizes every rank's brackets) */
     SX_REGION_HIST1 = 2,    /* int32   [slots][2][4096]  sample histogram; reduce: SUM (wraps mod 2^32) */
     SX_REGION_HIST2 = 3,    /* int32   [slots][2][4096]  cells inside the bracket; reduce: SUM */
     SX_REGION_VMIN = 4,     /* float32 [slots][2][4096]  reduce: MIN */

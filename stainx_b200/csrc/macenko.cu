@@ -893,6 +893,11 @@ __device__ void bracket_slot(const Ws &ws, int64_t slot, int stage, SlotState &s
     dual_prefix<false>(h, stage == SX_STAGE_ANGLE ? h : h + kBins, pre);
     const long long m0 = (long long)__ldcg(ws.counters + slot * 8 + 2);
     const long long m1 = stage == SX_STAGE_ANGLE ? m0 : (long long)__ldcg(ws.counters + slot * 8 + 3);
+    if (threadIdx.x == 0) {  // the group size all ranks agree on (see t_moments_kernel)
+        const float gp = __ldcg(ws.odrange + slot * 8 + 6);
+        if (gp > (float)st.group_px) st.group_px = (int)gp;
+    }
+    __syncthreads();
     bracket_from_prefix(stage, st, pre, m0, m1);
     if (m0 < (stage == SX_STAGE_ANGLE ? st.n_sel : st.n_all)) maybe_force_miss(st);  // never an exact (whole-slot) bracket
     else __syncthreads();
@@ -1282,6 +1287,10 @@ __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict
             atomic_max_f32(&ws.odrange[slot * 8 + i], v);
         } else if (threadIdx.x == 64 && seg.row0 == 0) {
             atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);  // rows in the slot (pooled fit: all images)
+            // pixels per sampled group of THIS rank's kernel variant; ODRANGE is MAX-combined over the ranks of a sharded
+            // fit, so every rank sizes its sample brackets with the same (largest) group -- ranks whose shards differ in
+            // vectorisation, or hold no images at all, would otherwise define different cells for the summed histograms
+            atomic_max_f32(&ws.odrange[slot * 8 + 6], (float)kPix);
         }
         __syncthreads();  // red / redf are rewritten by the next segment
     }

@@ -598,6 +598,57 @@ def test_macenko_sharded_fit_emulation(cuda):
     assert int(wss[0].region("status").abs().sum()) == 0
 
 
+def test_macenko_sharded_fit_with_ragged_ranks(cuda):
+    """ranks of a sharded pooled fit may run different kernel variants (a shard whose planes are not
+    16-byte aligned takes the scalar kernels: 1 pixel per sampled group instead of 16) or hold no images at all.  The
+    sample brackets must still be identical on every rank -- the group size travels in the MAX-combined ODRANGE region --
+    or the summed cell histograms would mix different cell definitions."""
+    from stainx_b200 import _native as nv
+    from stainx_b200 import ops
+
+    imgs = torch.cat([he_tile(128, 160, 42), he_tile(128, 160, 7, 1.1), he_tile(128, 160, 8, 0.9)]).to(cuda)
+    he_ref, maxc_ref = ops.macenko_fit(imgs)
+    flat = torch.empty(imgs[1:].numel() + 1, dtype=torch.uint8, device=cuda)
+    misaligned = flat[1:].view(2, 3, 128, 160)  # contiguous, but every plane starts on an odd address
+    misaligned.copy_(imgs[1:])
+    assert misaligned.data_ptr() % 16 != 0 and misaligned.is_contiguous()
+    shards = [imgs[:1].contiguous(), misaligned, imgs[:0]]  # vector kernels / scalar kernels / no images
+    wss = [ops.MacenkoWorkspace(1, cuda) for _ in shards]
+
+    def reduce(name, op):
+        stack = torch.stack([w.region(name) for w in wss])
+        red = {"sum": stack.sum(0), "max": stack.max(0).values, "min": stack.min(0).values}[op]
+        for w in wss:
+            w.region(name).copy_(red.to(w.region(name).dtype))
+
+    for w, s in zip(wss, shards):
+        w.begin()
+        if s.shape[0]:
+            w.moments(s, pooled=True)
+    reduce("moments", "sum")
+    reduce("odrange", "max")
+    for w in wss:
+        w.basis(0, 1, allow_fallback=False)
+    for stage in (nv.SX_STAGE_ANGLE, nv.SX_STAGE_CONC):
+        for level in (0, 1):
+            for w, s in zip(wss, shards):
+                if s.shape[0]:
+                    w.hist(s, True, stage, level)
+            reduce("hist1" if level == 0 else "hist2", "sum")
+            reduce("counters", "sum")
+            if level == 1:
+                reduce("vmin", "min")
+                reduce("vmax", "max")
+            for w in wss:
+                w.select(0, 1, stage, level)
+    for w in wss:
+        assert torch.equal(w.region("fit"), wss[0].region("fit")), "ranks derived different fits"
+        assert int(w.region("status")[0, 0]) == 0
+    fit = wss[0].region("fit")[0]
+    assert torch.allclose(fit[:6].reshape(3, 2), he_ref, rtol=0, atol=1e-6)
+    assert torch.allclose(fit[6:8], maxc_ref, rtol=1e-5, atol=0)
+
+
 @pytest.mark.gpu
 def test_host_stream_matches_direct_transform(cuda):
     """ingest.HostStream (pinned host in/out, three-stream pipeline) returns exactly what the
