@@ -202,3 +202,23 @@ def test_host_stream_orders_behind_fit_without_host_sync(cuda, ox):
     ticket = pipe.submit(src)  # no host synchronisation between fit and submit
     out = ticket.wait()
     assert np.array_equal(out.numpy(), ox.hm_transform(src.numpy(), ox.hm_fit(ref.numpy())))
+
+
+def test_device_stream_pool_matches_direct_transform(cuda):
+    """ingest.DeviceStream issues independent device-resident batches round-robin on a pool of streams (their phases
+    overlap); every result must equal the plain transform of the same batch, for all three methods."""
+    from stainx_b200 import HistogramMatching, Macenko, Reinhard
+    from stainx_b200.ingest import DeviceStream
+
+    g = torch.Generator(device=cuda).manual_seed(17)
+    ref = (torch.rand((1, 3, 256, 256), device=cuda, generator=g).pow(1.5) * 255).round().to(torch.uint8)
+    batches = [(torch.rand((6, 3, 512, 512), device=cuda, generator=g).pow(p) * 255).round().to(torch.uint8) for p in (0.6, 1.0, 1.7, 0.8, 1.3)]
+    for cls in (HistogramMatching, Reinhard, Macenko):
+        n = cls(device=cuda, backend="torch_cuda").fit(ref)
+        want = [n.transform(b) for b in batches]
+        torch.cuda.synchronize()
+        pool = DeviceStream(n, streams=3)
+        for _ in range(3):  # repeated use: recycled outputs / workspaces across the streams
+            got = pool.map(batches)
+            checks = [(a != b).sum() for a, b in zip(got, want)]
+            assert all(int(c) == 0 for c in checks), cls.__name__
