@@ -1005,12 +1005,15 @@ def main() -> None:
         for ns in (2, 3):
             pool = DeviceStream(fn, device=ctx.dev, streams=ns)
             k = max(steps, 12)
-            for _ in range(2):
-                pool.map([wl.src] * 6)
+            for _ in range(8):
+                pool.submit(wl.src)  # results are dropped at once, as in the single-stream loop: their memory is recycled per stream
+            pool.join()
             ctx.barrier()
             a, b = ctx.ev(), ctx.ev()
             a.record()
-            pool.map([wl.src] * k)
+            for _ in range(k):
+                pool.submit(wl.src)
+            pool.join()
             b.record()
             ctx.barrier()
             ms = a.elapsed_time(b) / k

@@ -194,10 +194,11 @@ class DeviceStream:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._streams = [torch.cuda.Stream(self.device) for _ in range(streams)]
         self._next = 0
-        self._pending: list[tuple[torch.Tensor, torch.cuda.Event]] = []
 
     def submit(self, batch: torch.Tensor) -> tuple[torch.Tensor, torch.cuda.Event]:
-        """Enqueue one batch on the next stream of the pool; returns (result, event recorded behind it)."""
+        """Enqueue one batch on the next stream of the pool; returns (result, event recorded behind it).  The result
+        belongs to the pool stream: wait for the event (``event.wait()`` on the consuming stream, or ``join``) before
+        using it elsewhere.  Dropping the result frees its memory for the next batch on the same stream."""
         s = self._streams[self._next % len(self._streams)]
         self._next += 1
         with torch.cuda.device(self.device):
@@ -207,21 +208,21 @@ class DeviceStream:
                 batch.record_stream(s)
                 done = torch.cuda.Event()
                 done.record(s)
-        self._pending.append((out, done))
         return out, done
 
-    def collect(self) -> list[torch.Tensor]:
-        """Results of everything submitted since the last collect, in order; the caller's current stream waits for them."""
+    def join(self) -> None:
+        """The caller's current stream waits for everything submitted so far."""
         cur = torch.cuda.current_stream(self.device)
-        outs = []
-        for out, done in self._pending:
-            cur.wait_event(done)
-            out.record_stream(cur)
-            outs.append(out)
-        self._pending = []
-        return outs
+        for s in self._streams:
+            cur.wait_stream(s)
 
     def map(self, batches) -> list[torch.Tensor]:
+        """Results of ``batches`` in order, all alive at once (mind the memory), ready for the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        outs = []
         for b in batches:
-            self.submit(b)
-        return self.collect()
+            out, _ = self.submit(b)
+            out.record_stream(cur)
+            outs.append(out)
+        self.join()
+        return outs
