@@ -1053,6 +1053,17 @@ def main() -> None:
             gbs = w2.bpp * w2.px / (ms / 1e3) / 1e9
             methods[name] = {"mp_per_s": w2.px * ctx.world / 1e6 / (ms / 1e3), "algo_gbs_per_gpu": gbs, "frac_of_peak": gbs / peak_gbs, "ms": ms, "workload": w2.desc, "steps": k,
                              "note": "side measurement; run `bench.py --config " + name + "` for the full line (roofline, e2e, parity_check)"}
+            if name in ("reinhard", "c3"):
+                # the same batch as 16-bit float tensors, read and written by the kernels (SX_F16 / SX_BF16): half the algorithmic bytes
+                for dt_name, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+                    full = w2.src
+                    w2.src = full.to(dt)
+                    del full
+                    ms16, _ = time_steps(ctx, w2, k, 3)
+                    gbs16 = 0.5 * w2.bpp * w2.px / (ms16 / 1e3) / 1e9
+                    methods[f"{name}_{dt_name}"] = {"mp_per_s": w2.px * ctx.world / 1e6 / (ms16 / 1e3), "algo_gbs_per_gpu": gbs16, "frac_of_peak": gbs16 / peak_gbs, "ms": ms16,
+                                                    "workload": w2.desc.replace("float32", dt_name) + f" -- {dt_name} in, {dt_name} out ({0.5 * w2.bpp:.0f} B/px)", "steps": k, "speedup_vs_float32": ms / ms16}
+                    w2.src = w2.src.float()
             del w2
 
     # ---- CPU baseline (rank 0, every N; bounded sample; same statistic as --impl reference) -----
