@@ -225,7 +225,13 @@ def cpu_time(config: str, world: int, budget_s: float, min_reps: int = 2) -> dic
     from oracle import oracle as ox
 
     ox.build()
-    cores = ox.set_num_threads(os.cpu_count())  # explicit: torchrun exports OMP_NUM_THREADS=1
+    # The GPU arm pins each rank to its GPU's NUMA node for the pinned e2e buffers; the CPU baseline gets every core back.
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        usable = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        usable = os.cpu_count() or 1
+    cores = ox.set_num_threads(usable)  # explicit: torchrun exports OMP_NUM_THREADS=1
     method, dt, h, w, *_ = SPECS[config]
     n_full = images_per_gpu(config, world)
     ref, probe = make_inputs_numpy(config, world, 0, 1)
