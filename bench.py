@@ -347,10 +347,7 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.dev)
         self.pg = "world" if self.distributed else None
         self._flush = None
-        # pinned host buffers of the e2e leg should live on the GPU's own NUMA node
-        from stainx_b200.ingest import bind_host_thread_to_device
-
-        self.host_cores = bind_host_thread_to_device(self.local_rank)
+        self.host_cores = None  # set by measure_e2e: cores local to the GPU, used while the pinned buffers are allocated
 
     def barrier(self):
         if self.distributed:
@@ -837,11 +834,24 @@ def measure_e2e(ctx: Ctx, wl: Workload, steps: int) -> dict:
     torch = ctx.torch
     from stainx_b200.ingest import HostStream
 
+    from stainx_b200.ingest import bind_host_thread_to_device
+
     fn = wl.e2e_fn()
+    probe = wl.step()
+    # pinned buffers are first-touched on the GPU's own NUMA node: bind this process to the cores NVML reports as local to
+    # the GPU while they are allocated, then give the process its cores back (the CPU baseline needs all of them)
+    try:
+        before = os.sched_getaffinity(0)
+    except AttributeError:
+        before = None
+    ctx.host_cores = bind_host_thread_to_device(ctx.local_rank)
     host_in = torch.empty(wl.src.shape, dtype=wl.src.dtype).pin_memory()
     host_in.copy_(wl.src)
-    probe = wl.step()
     host_outs = [torch.empty(probe.shape, dtype=probe.dtype).pin_memory() for _ in range(2)]
+    for h in host_outs:
+        h.zero_()  # touch
+    if before is not None:
+        os.sched_setaffinity(0, before)
     pipe = HostStream(fn, device=ctx.dev, depth=2)
 
     def run(k):
