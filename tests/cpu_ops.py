@@ -218,7 +218,7 @@ class MacenkoWorkspace:
     def hist(self, images, pooled, stage, level, slot0=0):
         keys = self._keys(images, stage)
         cnt = self._r["counters"][0]
-        if level == 0:
+        if level in (0, 2):  # the stand-in histograms every pixel at level 0 already, so level 2 (exact coarse pass) is the same
             h = self._r["hist1"][0]
             for q in ((0,) if stage == 0 else (0, 1)):
                 h[q] += torch.from_numpy(np.bincount(keys[q][0].astype(np.int64) >> 12, minlength=BINS).astype(np.int32))

@@ -149,3 +149,65 @@ def test_reducer_is_identity_without_a_group():
     t = torch.arange(4)
     assert r.sum_(t) is t and r.max_(t) is t and r.min_(t) is t
     assert r.sum_int(7, torch.device("cpu")) == 7
+
+
+def test_sharded_fit_repeats_exactly_after_a_missed_bracket():
+    """Host logic of the deterministic recovery in the sharded pooled fit: when the STATUS region reports a missed bracket
+    after the sampled fit, the fit is repeated with the exact coarse pass (hist level 2); a miss after THAT raises."""
+    import types
+
+    from stainx_b200._native import StainxNativeError
+    from stainx_b200.backends.torch_cuda_backend import MacenkoCUDA
+    from tests import cpu_ops
+    from tests.helpers import he_tile
+
+    levels, state = [], {"miss_first": 1, "miss_always": False}
+
+    class Flaky(cpu_ops.MacenkoWorkspace):
+        def hist(self, images, pooled, stage, level, slot0=0):
+            levels.append(level)
+            return super().hist(images, pooled, stage, level, slot0)
+
+        def select(self, slot0, count, stage, level):
+            super().select(slot0, count, stage, level)
+            if stage == 1 and level == 1 and (state["miss_always"] or state["miss_first"] > 0):
+                state["miss_first"] -= 1
+                self.region("status")[0, 0] = 1  # "rank 0 fell outside its bracket"
+
+    layer = types.SimpleNamespace(**{k: getattr(cpu_ops, k) for k in dir(cpu_ops) if not k.startswith("_")})
+    layer.MacenkoWorkspace = Flaky
+    ref = torch.cat([he_tile(48, 48, 42), he_tile(48, 48, 7, 1.1)])
+    want = cpu_ops.cpu_backend(MacenkoCUDA, "cpu")._pooled_fit_sharded(ref)
+    levels.clear()
+    he, maxc = cpu_ops.cpu_backend(MacenkoCUDA, "cpu", kernel_layer=layer)._pooled_fit_sharded(ref)
+    assert levels == [0, 1, 0, 1, 2, 1, 2, 1], levels  # sampled fit, then the exact repeat
+    assert torch.allclose(he, want[0], atol=1e-6) and torch.allclose(maxc, want[1], rtol=1e-6)
+    state["miss_always"] = True
+    with pytest.raises(StainxNativeError, match="exact bracket"):
+        cpu_ops.cpu_backend(MacenkoCUDA, "cpu", kernel_layer=layer)._pooled_fit_sharded(ref)
+
+
+def test_hm_rejects_non_rgb_with_a_clear_error():
+    """the reference's torch backend loops over any channel count; this backend is RGB-only and says so."""
+    from stainx_b200.backends.torch_cuda_backend import HistogramMatchingCUDA
+    from tests.cpu_ops import cpu_backend
+
+    b = cpu_backend(HistogramMatchingCUDA, "cpu")
+    with pytest.raises(ValueError, match="RGB images only"):
+        b.compute_reference_counts(torch.zeros((1, 1, 8, 8), dtype=torch.uint8))
+    with pytest.raises(ValueError, match="RGB images only"):
+        b.transform(torch.zeros((1, 4, 8, 8), dtype=torch.uint8), [torch.ones(256) / 256] * 3)
+    with pytest.raises(ValueError, match="4-D batch"):
+        b.transform(torch.zeros((3, 8, 8), dtype=torch.uint8), [torch.ones(256) / 256] * 3)
+
+
+def test_bind_host_thread_is_best_effort():
+    """No NVML / no GPU in the build container: the helper changes nothing and says so."""
+    import os
+
+    from stainx_b200.ingest import bind_host_thread_to_device
+
+    before = os.sched_getaffinity(0)
+    assert bind_host_thread_to_device(0) is None or isinstance(bind_host_thread_to_device(0), list)
+    if bind_host_thread_to_device(0) is None:
+        assert os.sched_getaffinity(0) == before
