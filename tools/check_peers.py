@@ -107,7 +107,16 @@ for method, tol in (("histogram_matching", 0.0), ("reinhard", 1e-6), ("macenko",
     tm = StainNormalizerTransform(method=method, mode="batch", device=dev, batch_ref_index=gidx, process_group="world")
     got = tm(tiles[lo:hi].to(dev))
     want = StainNormalizerTransform(method=method, mode="batch", device=dev, batch_ref_index=gidx)(tiles.to(dev))[lo:hi]
-    d = float((got.float() - want.float()).abs().max())
+    diff = (got.float() - want.float()).abs()
+    d = float(diff.max())
+    if method == "macenko":
+        # uint8 in, k/255 out: the per-image moments are summed in a different order when the batch around an image
+        # changes (double atomics over a different CTA split), and a pixel on the truncation knife edge may move by
+        # ONE grey level -- the bar of the parity tests; anything beyond a handful of such pixels is a failure
+        frac = float((diff > 1e-6).float().mean())
+        b_ok = b_ok and d <= 1.0 / 255.0 + 1e-6 and frac < 1e-4
+        print(f"rank {rank}: batch-mode module {method}: max|sharded-single| = {d:.2e} on {frac:.1e} of the values", flush=True)
+        continue
     b_ok = b_ok and d <= tol
     print(f"rank {rank}: batch-mode module {method}: max|sharded-single| = {d:.2e}", flush=True)
 ok = ok and b_ok
