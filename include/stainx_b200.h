@@ -169,8 +169,9 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
  * `moments` (MOMENTS, ODRANGE) and after every `hist` (level 0: HIST1, COUNTERS; level 1: HIST2,
  * COUNTERS, VMIN, VMAX) -- with all-reduces, or on one NVLink node with sx_macenko_peer_combine.
  * sx_macenko_transform does not use the phase functions one by one: it chains lean streaming kernels
- * and per-image kernels of its own (10 launches per chain, up to 4 part-batch chains on side
- * streams that it forks from and joins into `stream`). */
+ * and per-image kernels of its own (eight launches per chain; batches of >= 64 MB run as up to three
+ * part-batch chains, all but the first on library-owned side streams that it forks from and joins into
+ * `stream`, so the call stays stream-ordered and graph-capturable). */
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
     SX_REGION_MOMENTS = 0,  /* double  [slots][12]   reduce: SUM */

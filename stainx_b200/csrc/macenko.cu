@@ -1222,12 +1222,12 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const T *__restrict__ i
 }
 
 // ---- per-image transform pipeline ------------------------------------------------------------
-// sx_macenko_transform chains TEN launches: init, three lean streaming kernels over the batch
+// sx_macenko_transform = init + EIGHT launches per chain: three lean streaming kernels over the chain's images
 // (moments, resolve ANGLE, resolve CONC), the reconstruction, and between them small per-image kernels:
-//   mid<ANGLE>    after moments:       basis (M3-M4), masked-row fallback (L409-410), ANGLE sample + bracket
-//   select(ANGLE) after resolve ANGLE: rank search, HE / pinv (M7-M8)
-//   mid<CONC>     then:                CONC sample + bracket
-//   select(CONC)  after resolve CONC:  rank search -> maxC (M9)
+//   mid<ANGLE>             after moments:       basis (M3-M4), masked-row fallback (L409-410), ANGLE sample + bracket
+//   select_recover<ANGLE>  after resolve ANGLE: rank search, HE / pinv (M7-M8); exact re-run of the stage on a missed bracket
+//   mid<CONC>              then:                CONC sample + bracket
+//   select_recover<CONC>   after resolve CONC:  rank search -> maxC (M9); same recovery
 // The phase-level API needs 13 launches for the same work because a sharded fit must all-reduce
 // between them.  (Folding the per-image steps into the tail of the streaming kernels -- "last CTA of
 // an image finishes it" -- was built and measured: the extra registers and shared memory slowed the
