@@ -174,7 +174,9 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
  * `stream`, so the call stays stream-ordered and graph-capturable). */
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
-    SX_REGION_MOMENTS = 0,  /* double  [slots][12]   reduce: SUM */
+    SX_REGION_MOMENTS = 0,  /* int64   [slots][12]   reduce: SUM.  Fixed-point (scale 2^22) count and shifted first / second moments
+                             *                        of log2(255 x + 1) over the kept rows, [10] = pixels in the slot (unscaled).
+                             *                        Integer sums: the combined value does not depend on the order of addition. */
     SX_REGION_ODRANGE = 1,  /* float32 [slots][8]    reduce: MAX  (-min_c x3, max_c x3, [6] pixels per sampled group of the
                              *                        rank's kernel variant -- the combined maximum sizes every rank's brackets) */
     SX_REGION_HIST1 = 2,    /* int32   [slots][2][4096]  sample histogram; reduce: SUM (wraps mod 2^32) */

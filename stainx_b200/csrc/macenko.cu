@@ -80,8 +80,19 @@ struct Layout {
     }
 };
 
+// MOMENTS region: 64-bit FIXED-POINT sums (scale 2^22), not doubles.  Integer addition is associative, so the combined
+// moments of a slot do not depend on the order in which CTAs (or ranks) add their partial sums: the same call on the same
+// input gives the same bits every time.  (Double atomics made the last bits order-dependent, and the float32
+// eigen-decomposition can turn a last-bit difference into ~1e-7 relative in the stain vectors: one grey level on a uint8
+// pixel near the truncation edge.)  A CTA's partial sum is converted once, at 2^-22 = 2.4e-7 absolute on values of 1e3-1e7
+// -- below the float32 rounding of the per-thread partial sums it is made of.  Range: |sum| < 2^63 / 2^22 = 2.2e12, i.e.
+// 5e10 pixels per slot (50 000 images of 1024 x 1024 in one pooled fit).  Word 10 = pixel count of the slot, unscaled.
+constexpr double kMomScale = 4194304.0;
+__device__ __forceinline__ long long mom_to_fx(double v) { return __double2ll_rn(v * kMomScale); }
+__device__ __forceinline__ double mom_from_fx(long long v) { return (double)v * (1.0 / kMomScale); }
+
 struct Ws {
-    double *moments;
+    long long *moments;
     unsigned long long *counters;  // [slot][8]: below[2], sample count[2], pad
     float *odrange;
     unsigned *hist1, *hist2;
@@ -92,7 +103,7 @@ struct Ws {
     __host__ __device__ Ws(void *base, int64_t slots) {
         Layout L(slots);
         char *b = static_cast<char *>(base);
-        moments = reinterpret_cast<double *>(b + L.moments);
+        moments = reinterpret_cast<long long *>(b + L.moments);
         counters = reinterpret_cast<unsigned long long *>(b + L.counters);
         odrange = reinterpret_cast<float *>(b + L.odrange);
         hist1 = reinterpret_cast<unsigned *>(b + L.hist1);
@@ -475,8 +486,9 @@ __global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_
     if (idx >= count) return;
     const int64_t slot = slot0 + idx;
     SlotState &st = ws.state[slot];
-    const double *m = ws.moments + slot * 12;
-    st.n_all = (long long)(m[10] + 0.5);
+    double m[10];
+    for (int i = 0; i < 10; ++i) m[i] = mom_from_fx(ws.moments[slot * 12 + i]);
+    st.n_all = ws.moments[slot * 12 + 10];
     st.use_all = 0;
     if (allow_fallback && m[0] < 3.0) {  // L409-410: handled by fallback_kernel
         st.use_all = 1;
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict_
     if (threadIdx.x < 10) tot[threadIdx.x] = acc[0];
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = tot[i];
+        for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = mom_to_fx(tot[i]);
         basis_from_moments(tot, ws.state[slot]);
     }
 }
@@ -1279,14 +1291,14 @@ __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict
         }
         block_sum10(acc, red);
         if (threadIdx.x < 10) {
-            if (acc[0] != 0.0) atomicAdd(&ws.moments[slot * 12 + threadIdx.x], acc[0]);
+            if (acc[0] != 0.0) atomicAdd(reinterpret_cast<unsigned long long *>(&ws.moments[slot * 12 + threadIdx.x]), (unsigned long long)mom_to_fx(acc[0]));
         } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
             const int i = threadIdx.x - 32;  // [0..2] = -min l (one range for the three channels), [3..5] = max l
             float v = -INFINITY;
             for (int k = 0; k < kThreads / 32; ++k) v = fmaxf(v, redf[k][i / 3]);
             atomic_max_f32(&ws.odrange[slot * 8 + i], v);
         } else if (threadIdx.x == 64 && seg.row0 == 0) {
-            atomicAdd(&ws.moments[slot * 12 + 10], (double)g.hw);  // rows in the slot (pooled fit: all images)
+            atomicAdd(reinterpret_cast<unsigned long long *>(&ws.moments[slot * 12 + 10]), (unsigned long long)g.hw);  // rows in the slot (pooled fit: all images)
             // pixels per sampled group of THIS rank's kernel variant; ODRANGE is MAX-combined over the ranks of a sharded
             // fit, so every rank sizes its sample brackets with the same (largest) group -- ranks whose shards differ in
             // vectorisation, or hold no images at all, would otherwise define different cells for the summed histograms
@@ -1341,7 +1353,7 @@ __global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img
     const T *image = img + (int64_t)(blockIdx.x / kMidParts) * 3 * hw;
     const int64_t base = slot * 2 * kBins;
     if constexpr (STAGE == SX_STAGE_ANGLE) {
-        if (threadIdx.x < 10) ms.tot[threadIdx.x] = ws.moments[slot * 12 + threadIdx.x];
+        if (threadIdx.x < 10) ms.tot[threadIdx.x] = mom_from_fx(ws.moments[slot * 12 + threadIdx.x]);
         __syncthreads();
         if (threadIdx.x == 0) {
             SlotState z = {};
@@ -1388,8 +1400,8 @@ __global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img
     __syncthreads();
     if (!ms.s_last) return;
     if (STAGE == SX_STAGE_ANGLE && threadIdx.x < 11) {  // the moments the basis was computed from (fallback: every row)
-        if (ms.st.use_all && threadIdx.x < 10) ws.moments[slot * 12 + threadIdx.x] = ms.tot[threadIdx.x];
-        if (threadIdx.x == 10) ws.moments[slot * 12 + 10] = (double)hw;
+        if (ms.st.use_all && threadIdx.x < 10) ws.moments[slot * 12 + threadIdx.x] = mom_to_fx(ms.tot[threadIdx.x]);
+        if (threadIdx.x == 10) ws.moments[slot * 12 + 10] = (long long)hw;
     }
     bracket_slot(ws, slot, STAGE, ms.st, hist);
     store_state(ws.state + slot, &ms.st);
@@ -1510,7 +1522,7 @@ __global__ void __launch_bounds__(kCombineThreads) peer_combine_kernel(unsigned 
     const int64_t cells = 2 * kBins * 4;  // bytes of one per-slot cell array
     peer_rendezvous(bufs, world, rank, epoch, L.total, budget_ns, status);  // (1) everybody's statistics of this step are complete
     if (which == 0) {
-        combine_region<kSumF64>(bufs, world, L.moments, 12 * 8, scratch, 0);
+        combine_region<kSumU64>(bufs, world, L.moments, 12 * 8, scratch, 0);  // fixed-point sums: integer addition, order-independent
         combine_region<kMaxF32>(bufs, world, L.odrange, 8 * 4, scratch, 128);
     } else if (which == 1) {
         combine_region<kSumU32>(bufs, world, L.hist1, cells, scratch, 0);
@@ -1551,7 +1563,7 @@ __global__ void init_kernel(void *ws_base, int64_t slots) {
         ws.vmin[i] = INFINITY;
         ws.vmax[i] = -INFINITY;
     }
-    if (i < slots * 12) ws.moments[i] = 0.0;
+    if (i < slots * 12) ws.moments[i] = 0;
     if (i < slots * 8) { ws.odrange[i] = -INFINITY; ws.fit[i] = 0.0f; ws.counters[i] = 0ull; }
     if (i < slots * 4) ws.status[i] = 0;
     if (i < slots) {

@@ -241,7 +241,7 @@ def reinhard_fit(images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
 
 
 # ----------------------------------------------------------------------------- macenko
-_REGION_DTYPES = {"moments": torch.float64, "odrange": torch.float32, "hist1": torch.int32, "hist2": torch.int32, "vmin": torch.float32, "vmax": torch.float32, "fit": torch.float32, "counters": torch.int64, "status": torch.int32}
+_REGION_DTYPES = {"moments": torch.int64, "odrange": torch.float32, "hist1": torch.int32, "hist2": torch.int32, "vmin": torch.float32, "vmax": torch.float32, "fit": torch.float32, "counters": torch.int64, "status": torch.int32}
 _REGION_SHAPES = {"moments": (12,), "odrange": (8,), "hist1": (2, 4096), "hist2": (2, 4096), "vmin": (2, 4096), "vmax": (2, 4096), "fit": (8,), "counters": (8,), "status": (4,)}
 
 

@@ -818,3 +818,23 @@ def test_macenko_missed_brackets_are_recovered_exactly(cuda, ox):
         assert best_sign_diff(_np(out), want, alt).max() <= 1
     finally:
         assert lib.sx_macenko_set_tuning(-1, 0) == 0
+
+
+def test_macenko_is_bit_reproducible_run_to_run(cuda):
+    """The per-image moments are combined as fixed-point integers, so the order in which the CTAs of the moments pass
+    finish cannot change them: repeated transforms (and fits) of the same batch return the same bits, uint8 and float32,
+    multi-chain batches included."""
+    from stainx_b200 import ops
+
+    g = torch.Generator(device=cuda).manual_seed(19)
+    src8 = (torch.rand((24, 3, 1024, 1024), device=cuda, generator=g) * 255).to(torch.uint8)  # 75 MB: three chains
+    srcf = torch.rand((8, 3, 1024, 1024), device=cuda, generator=g)
+    he, maxc = ops.macenko_fit(src8[:1].contiguous())
+    want8, wantf, want_fit = ops.macenko_transform(src8, he, maxc), ops.macenko_transform(srcf, he, maxc, unit=True), ops.macenko_fit(srcf)
+    bad = []
+    for _ in range(6):
+        bad.append((ops.macenko_transform(src8, he, maxc) != want8).sum())
+        bad.append((ops.macenko_transform(srcf, he, maxc, unit=True) != wantf).sum())
+        fit = ops.macenko_fit(srcf)
+        bad.append((fit[0] != want_fit[0]).sum() + (fit[1] != want_fit[1]).sum())
+    assert all(int(b) == 0 for b in bad)
