@@ -343,28 +343,42 @@ __device__ __forceinline__ void moments_group(const float (&l)[3][kPix], float (
     }
 }
 
-// CTA-wide sum of acc[10]; afterwards thread i < 10 holds total i in acc[0].
-__device__ __forceinline__ void block_sum10(double (&acc)[10], double (*red)[10]) {
+// CTA-wide sum of acc[10] (fixed-point integers: any order gives the same bits); afterwards thread i < 10 holds total i in acc[0].
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void block_sum10(long long (&acc)[10], long long (*red)[10]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const double r = warp_sum(acc[i]);
+        const long long r = warp_sum_ll(acc[i]);
         if (lane == 0) red[warp][i] = r;
     }
     __syncthreads();
     if (threadIdx.x < 10) {
-        double r = 0.0;
+        long long r = 0;
         for (int k = 0; k < kThreads / 32; ++k) r += red[k][threadIdx.x];
         acc[0] = r;
     }
 }
 
-// Streams groups of one image through moments_group; float32 partial sums are folded into the
-// double accumulators every kFlush groups (<= 64 pixels).
+// Rows (of kThreads pixel groups) whose float32 partial sums a thread folds into one fixed-point addition.
+template <typename T, bool VEC>
+struct MomFlush {
+    static constexpr int kRows = Pix<T, VEC>::kPix >= 16 ? 2 : 8;
+};
+
+// Streams groups of one image through moments_group.  A thread sums the float32 contributions of kRows consecutive rows
+// (<= 64 pixels, fixed order) and converts that partial sum to 64-bit fixed point ONCE; everything after is integer
+// addition.  Callers start at a row that is a multiple of kRows within the image, so the set of pixels behind every
+// float32 partial sum -- and with it every bit of the image's moments -- is the same whatever the batch around the image,
+// the grid size or the number of ranks.
 template <typename T, bool VEC, bool MASKED>
-__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t groups_end, int64_t cta_first, int64_t cta_stride, const float *tab, double (&acc)[10], float (&lo)[3], float (&hi)[3]) {
+__device__ __forceinline__ void moments_stream(const T *__restrict__ image, int64_t hw, int64_t groups_end, int64_t cta_first, int64_t cta_stride, const float *tab, long long (&acc)[10], float (&lo)[3], float (&hi)[3]) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    constexpr int kFlush = kPix >= 16 ? 2 : 8;
+    constexpr int kFlush = MomFlush<T, VEC>::kRows;
     float s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int pending = 0;
     stream_groups<T, VEC>(
@@ -373,13 +387,13 @@ __device__ __forceinline__ void moments_stream(const T *__restrict__ image, int6
             moments_group<kPix, MASKED>(l, s, lo, hi);
             if (++pending == kFlush) {
 #pragma unroll
-                for (int i = 0; i < 10; ++i) { acc[i] += (double)s[i]; s[i] = 0.0f; }
+                for (int i = 0; i < 10; ++i) { acc[i] += mom_to_fx((double)s[i]); s[i] = 0.0f; }
                 pending = 0;
             }
         },
         [] {});
 #pragma unroll
-    for (int i = 0; i < 10; ++i) acc[i] += (double)s[i];
+    for (int i = 0; i < 10; ++i) acc[i] += mom_to_fx((double)s[i]);
 }
 
 // ---- symmetric 3x3 eigen-decomposition (M4) ----------------------------------------------------
@@ -503,22 +517,22 @@ __global__ void basis_kernel(void *ws_base, int64_t slots, int64_t slot0, int64_
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads) fallback_kernel(const T *__restrict__ img, int64_t hw, int64_t slot0, void *ws_base, int64_t slots) {
     __shared__ float tab[256];
-    __shared__ double red[kThreads / 32][10];
+    __shared__ long long red[kThreads / 32][10];
     __shared__ double tot[10];
     Ws ws(ws_base, slots);
     const int64_t n = blockIdx.x;
     const int64_t slot = slot0 + n;
     if (!ws.state[slot].use_all) return;
-    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     moments_stream<T, VEC, false>(img + n * 3 * hw, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, tab, acc, lo, hi);
     block_sum10(acc, red);
-    if (threadIdx.x < 10) tot[threadIdx.x] = acc[0];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 10; ++i) ws.moments[slot * 12 + i] = mom_to_fx(tot[i]);
-        basis_from_moments(tot, ws.state[slot]);
+    if (threadIdx.x < 10) {
+        ws.moments[slot * 12 + threadIdx.x] = acc[0];
+        tot[threadIdx.x] = mom_from_fx(acc[0]);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) basis_from_moments(tot, ws.state[slot]);
 }
 
 // ---- order-statistic passes ----------------------------------------------------------------------
@@ -1271,18 +1285,26 @@ struct RowSegment {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict__ img, RowGeom g, void *ws_base, int64_t slots) {
     constexpr int kPix = Pix<T, VEC>::kPix;
-    __shared__ double red[kThreads / 32][10];
+    __shared__ long long red[kThreads / 32][10];
     __shared__ float redf[kThreads / 32][2];
     Ws ws(ws_base, slots);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t groups = g.hw / kPix;
-    const int64_t r_end = (int64_t)(blockIdx.x + 1) * g.total_rows / gridDim.x;
-    for (int64_t r = (int64_t)blockIdx.x * g.total_rows / gridDim.x; r < r_end;) {
-        const RowSegment seg(g, r, r_end);
-        r += seg.row1 - seg.row0;
+    // The batch is split over the CTAs in UNITS of MomFlush::kRows rows that never straddle an image and always start at
+    // a multiple of kRows within it (see moments_stream): a CTA owns the units [c U / grid, (c + 1) U / grid).
+    constexpr int kUnitRows = MomFlush<T, VEC>::kRows;
+    const int64_t upi = ((int64_t)g.rows_per_img + kUnitRows - 1) / kUnitRows, total_units = g.n_img * upi;
+    const int64_t u_end = (int64_t)(blockIdx.x + 1) * total_units / gridDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * total_units / gridDim.x; u < u_end;) {
+        struct { int64_t n; int row0, row1; } seg;
+        seg.n = u / upi;
+        const int64_t ul0 = u - seg.n * upi, want = ul0 + (u_end - u), ul1 = want < upi ? want : upi;
+        u += ul1 - ul0;
+        seg.row0 = (int)(ul0 * kUnitRows);
+        seg.row1 = (int)(ul1 * kUnitRows < (int64_t)g.rows_per_img ? ul1 * kUnitRows : (int64_t)g.rows_per_img);
         const int64_t slot = g.pooled ? g.slot0 : g.slot0 + seg.n;
         const int64_t seg_end = (int64_t)seg.row1 * kThreads < groups ? (int64_t)seg.row1 * kThreads : groups;
-        double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         moments_stream<T, VEC, true>(img + seg.n * 3 * g.hw, g.hw, seg_end, (int64_t)seg.row0 * kThreads, kThreads, nullptr, acc, lo, hi);
         {
@@ -1291,7 +1313,7 @@ __global__ void __launch_bounds__(kThreads) t_moments_kernel(const T *__restrict
         }
         block_sum10(acc, red);
         if (threadIdx.x < 10) {
-            if (acc[0] != 0.0) atomicAdd(reinterpret_cast<unsigned long long *>(&ws.moments[slot * 12 + threadIdx.x]), (unsigned long long)mom_to_fx(acc[0]));
+            if (acc[0] != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&ws.moments[slot * 12 + threadIdx.x]), (unsigned long long)acc[0]);
         } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
             const int i = threadIdx.x - 32;  // [0..2] = -min l (one range for the three channels), [3..5] = max l
             float v = -INFINITY;
@@ -1345,7 +1367,7 @@ constexpr int kMidParts = 8;
 template <typename T, bool VEC, int STAGE>
 __global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img, int64_t hw, int64_t slot0, void *ws_base, int64_t slots) {
     __shared__ MidSmem ms;
-    __shared__ double red[kThreads / 32][10];
+    __shared__ long long red[kThreads / 32][10];
     __shared__ __align__(16) unsigned hist[2][kBins];
     Ws ws(ws_base, slots);
     const int64_t slot = slot0 + blockIdx.x / kMidParts;
@@ -1364,11 +1386,11 @@ __global__ void __launch_bounds__(kThreads) mid_kernel(const T *__restrict__ img
         }
         __syncthreads();
         if (ms.st.use_all) {  // fewer than 3 rows pass the mask: every row (rare; this CTA re-reads the image)
-            double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
             moments_stream<T, VEC, false>(image, hw, hw / Pix<T, VEC>::kPix, 0, kThreads, nullptr, acc, lo, hi);
             block_sum10(acc, red);
-            if (threadIdx.x < 10) ms.tot[threadIdx.x] = acc[0];
+            if (threadIdx.x < 10) ms.tot[threadIdx.x] = mom_from_fx(acc[0]);
             __syncthreads();
             if (threadIdx.x == 0) basis_from_moments(ms.tot, ms.st);
             __syncthreads();

@@ -516,6 +516,27 @@ def test_macenko_per_image_independence(cuda):
         assert torch.equal(whole[i : i + 1], n.transform(src[i : i + 1].to(cuda)))
 
 
+@pytest.mark.parametrize("dtype", ["u8", "f32", "f16"])
+def test_macenko_per_image_independence_large_images(cuda, dtype):
+    """The same at sizes where an image's rows are split over many CTAs and the split depends on the batch around it
+    (1, 3 and 11 images): the moments are fixed-point sums of float32 partials over row blocks that are aligned within
+    the image, so an image's statistics -- and every bit of its output -- do not depend on the batch it travels in."""
+    from stainx_b200 import Macenko
+
+    ref = he_tile(256, 256, 42)
+    src = torch.cat([he_batch(8, 768, 1024), noise_u8((3, 3, 768, 1024), 9)])
+    if dtype != "u8":
+        ref, src = ref.float() / 255.0, src.float() / 255.0
+    if dtype == "f16":
+        ref, src = ref.half(), src.half()
+    n = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=dtype != "u8").fit(ref.to(cuda))
+    dev_src = src.to(cuda)
+    whole = n.transform(dev_src)
+    for i in (0, 5, 10):
+        assert torch.equal(whole[i : i + 1], n.transform(dev_src[i : i + 1].contiguous()))
+    assert torch.equal(whole[4:7], n.transform(dev_src[4:7].contiguous()))
+
+
 def test_macenko_self_reference_reconstructs(cuda):
     """With the image's own HE / maxC as target, the Beer-Lambert tile is reproduced (the stain
     plane projection of OD is OD itself up to 8-bit rounding)."""

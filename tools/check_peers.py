@@ -110,13 +110,10 @@ for method, tol in (("histogram_matching", 0.0), ("reinhard", 1e-6), ("macenko",
     diff = (got.float() - want.float()).abs()
     d = float(diff.max())
     if method == "macenko":
-        # uint8 in, k/255 out: the per-image moments are summed in a different order when the batch around an image
-        # changes (double atomics over a different CTA split), and a pixel on the truncation knife edge may move by
-        # ONE grey level (last-bit differences of the moments become ~1e-7 relative in the float32 eigenvectors, i.e. ~3e-5
-        # grey levels: pixels that close to an integer flip) -- the bar of the parity tests is one level on < 1 % of the
-        # pixels; here < 0.1 %
-        frac = float((diff > 1e-6).float().mean())
-        b_ok = b_ok and d <= 1.0 / 255.0 + 1e-6 and frac < 1e-3
+        # per-image statistics are fixed-point sums over row blocks aligned within the image: a tile's output does not
+        # depend on the batch (shard) it travels in -- bit for bit
+        frac = float((diff > 0).float().mean())
+        b_ok = b_ok and d == 0.0
         print(f"rank {rank}: batch-mode module {method}: max|sharded-single| = {d:.2e} on {frac:.1e} of the values", flush=True)
         continue
     b_ok = b_ok and d <= tol
