@@ -268,6 +268,25 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
 /* Whole pooled fit on one stream (slots = 1): he[3][2] row-major, maxc[2] (device pointers). */
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he,
                    float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t stream);
+/* fit_transform (src/stainx/base.py:L59-61: fit(images) then transform(images)) as one call that reads the batch
+ * for the moments ONCE instead of twice: the per-image moments of the transform go to slots 1..n, their sum -- the
+ * MOMENTS region holds fixed-point integers, so the sum of the slots is bit for bit what a pooled moments pass
+ * accumulates -- to slot 0, on which the pooled fit runs; the transform pipeline then skips its moments pass.
+ * he / maxc / out equal sx_macenko_fit followed by sx_macenko_transform on the same images exactly.
+ * workspace_bytes >= sx_macenko_workspace_bytes(n + 1). */
+int sx_macenko_fit_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc,
+                             void *out, int out_dtype, float out_scale, void *workspace, int64_t workspace_bytes,
+                             sx_stream_t stream);
+/* The same for a batch sharded over the ranks of one NVLink node (the batch-mode pooled fit of BASELINE config c4):
+ * sx_macenko_fit_peers on the sum of this rank's per-image moments, then the transform of this rank's images with the
+ * pooled fit.  workspace = private device memory of sx_macenko_workspace_bytes(n) (n = 0: may be NULL, the rank still
+ * takes part in the five exchanges); he / maxc are required.  As for sx_macenko_fit_peers the caller reads STATUS word 0
+ * of own_buffer afterwards and repeats the call with exact = 1 if it is non-zero. */
+int sx_macenko_fit_transform_peers(const void *images, int dtype, int64_t n, int64_t h, int64_t w,
+                                   const void *peer_buffers_dev, void *own_buffer, int world, int rank,
+                                   uint32_t first_epoch, int exact, void *scratch, float *he, float *maxc, void *out,
+                                   int out_dtype, float out_scale, void *workspace, int64_t workspace_bytes,
+                                   sx_stream_t stream);
 
 /* ---- development hooks ----------------------------------------------------------------------
  * Launch-geometry knobs for tools/probe.py and the ncu scripts.  NOT part of the drop-in surface:

@@ -63,6 +63,8 @@ PROTOTYPES: dict[str, list] = {
     "sx_macenko_apply": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _vp, _i64, _vp],
     "sx_macenko_transform": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _int, _f32, _vp, _i64, _vp],
     "sx_macenko_fit": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp],
+    "sx_macenko_fit_transform": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _int, ctypes.c_float, _vp, _i64, _vp],
+    "sx_macenko_fit_transform_peers": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _int, _int, ctypes.c_uint32, _int, _vp, _vp, _vp, _vp, _int, ctypes.c_float, _vp, _i64, _vp],
     # tuning hooks (bench / profiling only)
     "sx_hm_set_tuning": [_int, _int, _int],
     "sx_reinhard_set_tuning": [_int],

@@ -315,6 +315,33 @@ class MacenkoCUDA(TorchCUDABackendBase):
             return self._pooled_fit_sharded(images, exact=True)
         return he, maxc
 
+    def fit_transform(self, images: torch.Tensor, normalize_to_0_1: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """``fit(images)`` followed by ``transform(images)`` (base.py:L59-61) with the batch read ONCE for the moments:
+        the per-image moments of the transform, summed, ARE the pooled moments of the fit (fixed-point integers, so bit
+        for bit).  Returns HE, maxC and the normalised batch -- the same values as the two separate calls.  Sharded:
+        the pooled fit spans every rank's images (``sx_macenko_fit_transform_peers``, one library call per rank)."""
+        native, original = self._to_native(images)
+        if native.dim() != 4 or native.shape[1] != 3:
+            raise ValueError(f"Macenko fit expects NCHW with C=3, got shape {tuple(native.shape)}")
+        unit = bool(normalize_to_0_1)
+        ops = self._ops
+        ex = self._peer_exchange() if self._reducer.enabled else None
+        if not self._reducer.enabled and hasattr(ops, "macenko_fit_transform"):
+            he, maxc, result = ops.macenko_fit_transform(native, unit=unit)
+        elif ex is not None and hasattr(ops, "macenko_fit_transform_peers"):
+            he, maxc, result = ops.macenko_fit_transform_peers(native, ex, self._scratch, unit=unit)
+            status = ops.MacenkoWorkspace(1, native.device, buffer=ex.buf).region("status")
+            if int(status[0, 0].item()) & 3:  # a wanted rank outside its sample bracket (identical on every rank): exact repeat
+                he, maxc, result = ops.macenko_fit_transform_peers(native, ex, self._scratch, unit=unit, exact=True)
+                if int(status[0, 0].item()) & 3:
+                    raise _native.StainxNativeError("Macenko pooled fit: a rank fell outside an exact bracket (inconsistent statistics across ranks?)")
+        else:
+            he, maxc = self.compute_reference_stain_matrix(native)
+            result = ops.macenko_transform(native, he, maxc.flatten(), unit=unit)
+        if unit and original == torch.uint8:
+            return he, maxc, result
+        return he, maxc, self._restore_dtype(result, original)
+
     def transform(self, images: torch.Tensor, stain_matrix: torch.Tensor, target_max_conc: torch.Tensor, normalize_to_0_1: bool = False) -> torch.Tensor:
         images, original = self._to_native(images)
         if tuple(stain_matrix.shape) != (3, 2):

@@ -1575,6 +1575,31 @@ __global__ void __launch_bounds__(kCombineThreads) peer_combine_kernel(unsigned 
     }
 }
 
+// fit_transform: the pooled fit's moments are the SUM of the per-image moments the transform needs anyway (fixed-point
+// integers: the sum of the slots is bit for bit what a pooled moments pass over the same images accumulates), and its
+// ranges the MAX of theirs -- one read of the batch instead of two.  One CTA of 12 warps: warp w < 11 sums moment word w
+// (10 sums + the pixel count) of the slots [slot0, slot0 + count) of `src`, warp 11 takes the maximum of the 8 ODRANGE
+// words; the result goes to `dst_slot` of `dst` (same or another workspace, e.g. a peer-mapped one-slot buffer).
+constexpr int kPoolThreads = 384;
+__global__ void __launch_bounds__(kPoolThreads) pool_moments_kernel(const void *src_base, int64_t src_slots, int64_t slot0, int64_t count, void *dst_base, int64_t dst_slots, int64_t dst_slot) {
+    const Ws src(const_cast<void *>(src_base), src_slots);
+    Ws dst(dst_base, dst_slots);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < 11) {
+        long long v = 0;
+        for (int64_t i = lane; i < count; i += 32) v += src.moments[(slot0 + i) * 12 + warp];
+        v = warp_sum_ll(v);
+        if (lane == 0) dst.moments[dst_slot * 12 + warp] = v;
+    } else {
+        const int word = lane & 7;
+        float v = -INFINITY;
+        for (int64_t i = lane >> 3; i < count; i += 4) v = fmaxf(v, src.odrange[(slot0 + i) * 8 + word]);
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+        if (lane < 8) dst.odrange[dst_slot * 8 + word] = v;
+    }
+}
+
 __global__ void init_kernel(void *ws_base, int64_t slots) {
     Ws ws(ws_base, slots);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1669,13 +1694,14 @@ static bool images_vec_ok(const void *images, const void *out, int dtype, int64_
 extern "C" int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, sx_stream_t stream_);
 
 // One chain of the per-image pipeline for images [0, n) -> slots [slot0, slot0 + n) on `stream`.
-static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream) {
+// with_moments = false: the slots already hold the images' moments (sx_macenko_fit_transform).
+static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments = true) {
     const int64_t hw = h * w;
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
         const T *p = static_cast<const T *>(images);
         const RowGeom g = make_row_geom<T, VEC>(n, hw, slot0, 0);
-        t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
+        if (with_moments) t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
         mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
         t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
         select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)n, kThreads, 0, stream>>>(p, n, hw, 0, slot0, workspace, slots);
@@ -1683,7 +1709,7 @@ static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int
         t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
         select_recover_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)n, kThreads, 0, stream>>>(p, n, hw, 0, slot0, workspace, slots);
     });
-    note_launch(6);
+    note_launch(with_moments ? 6 : 5);
     SX_LAUNCHED("macenko::transform pipeline");
     return sx_macenko_apply(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream);
 }
@@ -1901,13 +1927,52 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
     return SX_OK;
 }
 
+// The per-image pipeline of images [0, n) -> slots [slot0, slot0 + n) (see "per-image transform pipeline" above).  Large
+// batches run as up to kMaxChains part-batch chains, all but the first on side streams: the small per-image kernels of one
+// chain (~25 us per stage of dependent global round trips on a few SMs) overlap the streaming kernels of the other.  The
+// caller's stream forks into the side streams and joins them again, so the call keeps its stream-ordered,
+// host-asynchronous contract (and can be captured into a CUDA graph).
+static int transform_chains(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments) {
+    const int64_t hw = h * w;
+    const int64_t in_bytes = (int64_t)dtype_bytes(dtype) * 3 * hw, out_bytes = (int64_t)dtype_bytes(out_dtype) * 3 * hw;
+    int chains = g_split;
+    if (n * in_bytes < ((int64_t)64 << 20)) chains = 1;
+    while (chains > 1 && n / chains < 4) --chains;
+    if (chains <= 1) return run_pipeline(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream, with_moments);
+    SideStream *side = side_stream();
+    SX_REQUIRE(side != nullptr, "could not create the side streams");
+    std::lock_guard<std::mutex> lock(side->mu);
+    SX_CUDA(cudaEventRecord(side->fork, stream));
+    int rc = SX_OK;
+    for (int c = 0; c < chains; ++c) {  // chain 0 on the caller's stream, chain c > 0 on side stream c - 1
+        const int64_t i0 = n * c / chains, i1 = n * (c + 1) / chains;
+        cudaStream_t cs = c == 0 ? stream : side->stream[c - 1];
+        if (c > 0) SX_CUDA(cudaStreamWaitEvent(cs, side->fork, 0));
+        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, slot0 + i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, slots, cs, with_moments);
+        if (r && !rc) rc = r;
+        if (c > 0) {
+            SX_CUDA(cudaEventRecord(side->join[c - 1], cs));
+            SX_CUDA(cudaStreamWaitEvent(stream, side->join[c - 1], 0));
+        }
+    }
+    return rc;
+}
+
+// What sx_macenko_apply accepts, checked before the first launch of a whole-call entry point.
+static int check_output(int dtype, const void *out, int out_dtype, float out_scale) {
+    SX_REQUIRE(out, "NULL output");
+    const bool half_in = dtype == SX_F16 || dtype == SX_BF16;
+    SX_REQUIRE(half_in ? out_dtype == dtype : (out_dtype == SX_F32 || (out_dtype == SX_U8 && dtype == SX_U8)), "output dtype %d does not go with input dtype %d (uint8 -> uint8 | float32, float32 -> float32, float16 / bfloat16 -> the same)", out_dtype, dtype);
+    SX_REQUIRE(out_scale == 1.0f || fabsf(out_scale - 1.0f / 255.0f) < 1e-9f, "out_scale must be 1 or 1/255");
+    return SX_OK;
+}
+
 int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     if (n == 0 || h * w == 0) return SX_OK;
     SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(n), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_macenko_workspace_bytes(n));
     SX_REQUIRE(he_ref && maxc_ref && out, "NULL argument");
     cudaStream_t stream = static_cast<cudaStream_t>(s);
-    const int64_t hw = h * w;
     int rc;
     if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
     if (g_phase_kernels) {  // development: the phase-level API chained on one stream (13 launches)
@@ -1921,33 +1986,7 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
             }
         return sx_macenko_apply(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, s);
     }
-    // Per-image pipeline (see "per-image transform pipeline" above).  Large batches run as up to
-    // kMaxChains part-batch chains, all but the first on side streams: the small per-image kernels of one chain
-    // (~25 us per stage of dependent global round trips on a few SMs) overlap the streaming kernels
-    // of the other.  The caller's stream forks into the side stream and joins it again, so the call
-    // keeps its stream-ordered, host-asynchronous contract (and can be captured into a CUDA graph).
-    const int64_t in_bytes = (int64_t)dtype_bytes(dtype) * 3 * hw, out_bytes = (int64_t)dtype_bytes(out_dtype) * 3 * hw;
-    int chains = g_split;
-    if (n * in_bytes < ((int64_t)64 << 20)) chains = 1;
-    while (chains > 1 && n / chains < 4) --chains;
-    if (chains <= 1) return run_pipeline(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, stream);
-    SideStream *side = side_stream();
-    SX_REQUIRE(side != nullptr, "could not create the side streams");
-    std::lock_guard<std::mutex> lock(side->mu);
-    SX_CUDA(cudaEventRecord(side->fork, stream));
-    rc = SX_OK;
-    for (int c = 0; c < chains; ++c) {  // chain 0 on the caller's stream, chain c > 0 on side stream c - 1
-        const int64_t i0 = n * c / chains, i1 = n * (c + 1) / chains;
-        cudaStream_t cs = c == 0 ? stream : side->stream[c - 1];
-        if (c > 0) SX_CUDA(cudaStreamWaitEvent(cs, side->fork, 0));
-        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, n, cs);
-        if (r && !rc) rc = r;
-        if (c > 0) {
-            SX_CUDA(cudaEventRecord(side->join[c - 1], cs));
-            SX_CUDA(cudaStreamWaitEvent(stream, side->join[c - 1], 0));
-        }
-    }
-    return rc;
+    return transform_chains(images, dtype, n, h, w, 0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, n, stream, true);
 }
 
 // The sharded pooled fit of one NVLink node as ONE library call: the phase sequence of the header's
@@ -1957,8 +1996,10 @@ int sx_macenko_transform(const void *images, int dtype, int64_t n, int64_t h, in
 // `own_buffer` = this rank's peer-mapped buffer (the one-slot workspace lives at its start); `exact` != 0 replaces the
 // sample passes by the exact coarse pass (level 2) -- the repeat after a missed bracket.  n may be 0 (a rank without
 // reference images still takes part in every exchange).  he / maxc may be NULL (read the FIT region instead).
-int sx_macenko_fit_peers(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t first_epoch, int exact,
-                         void *scratch, float *he, float *maxc, sx_stream_t s) {
+// `per_image` (optional): a workspace of n slots that already holds the per-image moments of `images`
+// (sx_macenko_fit_transform_peers) -- slot 0 of own_buffer then gets their sum instead of a second moments pass.
+static int fit_peers_impl(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t first_epoch, int exact,
+                          void *scratch, float *he, float *maxc, sx_stream_t s, const void *per_image) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     SX_REQUIRE(peer_buffers_dev && own_buffer && scratch, "NULL argument");
     SX_REQUIRE(first_epoch != 0 && first_epoch + 4 >= first_epoch, "bad first epoch %u", first_epoch);
@@ -1966,7 +2007,10 @@ int sx_macenko_fit_peers(const void *images, int dtype, int64_t n, int64_t h, in
     const int coarse = exact ? 2 : 0;
     int rc;
     if ((rc = sx_macenko_begin(own_buffer, 1, s))) return rc;
-    if (have && (rc = sx_macenko_moments(images, dtype, n, h, w, 1, 0, own_buffer, 1, s))) return rc;
+    if (have && per_image) {
+        pool_moments_kernel<<<1, kPoolThreads, 0, static_cast<cudaStream_t>(s)>>>(per_image, n, 0, n, own_buffer, 1, 0);
+        SX_LAUNCHED("macenko::pool_moments_kernel");
+    } else if (have && (rc = sx_macenko_moments(images, dtype, n, h, w, 1, 0, own_buffer, 1, s))) return rc;
     uint32_t epoch = first_epoch;
     if ((rc = sx_macenko_peer_combine(peer_buffers_dev, world, rank, epoch++, 0, scratch, s))) return rc;
     if ((rc = sx_macenko_basis(own_buffer, 1, 0, 1, 0, s))) return rc;  // no fallback in fit (L483-487)
@@ -1984,6 +2028,33 @@ int sx_macenko_fit_peers(const void *images, int dtype, int64_t n, int64_t h, in
     return SX_OK;
 }
 
+int sx_macenko_fit_peers(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t first_epoch, int exact,
+                         void *scratch, float *he, float *maxc, sx_stream_t s) {
+    return fit_peers_impl(images, dtype, n, h, w, peer_buffers_dev, own_buffer, world, rank, first_epoch, exact, scratch, he, maxc, s, nullptr);
+}
+
+// The pooled fit after its moments: basis, then per stage sample pass -> brackets -> full pass -> rank search, all on
+// slot 0 of `workspace`; the result is in the FIT region of slot 0.
+static int fit_stages(const void *images, int dtype, int64_t n, int64_t h, int64_t w, void *workspace, int64_t slots, sx_stream_t s) {
+    int rc;
+    if ((rc = sx_macenko_basis(workspace, slots, 0, 1, 0, s))) return rc;  // no fallback in fit (L483-487)
+    const int64_t hw = h * w;
+    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
+    for (int stage = 0; stage < 2; ++stage) {
+        if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 0, workspace, slots, s))) return rc;
+        if ((rc = sx_macenko_select(workspace, slots, 0, 1, stage, 0, s))) return rc;
+        if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 1, workspace, slots, s))) return rc;
+        // rank search; a missed bracket is re-done exactly by the same kernel (see "deterministic recovery")
+        SX_DISPATCH_TV(dtype, vec, {
+            const T *p = static_cast<const T *>(images);
+            if (stage == SX_STAGE_ANGLE) select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<1, kThreads, 0, static_cast<cudaStream_t>(s)>>>(p, n, hw, 1, 0, workspace, slots);
+            else select_recover_kernel<T, VEC, SX_STAGE_CONC><<<1, kThreads, 0, static_cast<cudaStream_t>(s)>>>(p, n, hw, 1, 0, workspace, slots);
+        });
+        SX_LAUNCHED("macenko::select_recover_kernel");
+    }
+    return SX_OK;
+}
+
 int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
     if (int rc = check_images(images, dtype, n, h, w)) return rc;
     SX_REQUIRE(n > 0 && h * w > 0, "empty reference batch");
@@ -1992,25 +2063,58 @@ int sx_macenko_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t 
     int rc;
     if ((rc = sx_macenko_begin(workspace, 1, s))) return rc;
     if ((rc = sx_macenko_moments(images, dtype, n, h, w, 1, 0, workspace, 1, s))) return rc;
-    if ((rc = sx_macenko_basis(workspace, 1, 0, 1, 0, s))) return rc;  // no fallback in fit (L483-487)
-    const int64_t hw = h * w;
-    const bool vec = images_vec_ok(images, nullptr, dtype, hw);
-    for (int stage = 0; stage < 2; ++stage) {
-        if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 0, workspace, 1, s))) return rc;
-        if ((rc = sx_macenko_select(workspace, 1, 0, 1, stage, 0, s))) return rc;
-        if ((rc = sx_macenko_hist(images, dtype, n, h, w, 1, 0, stage, 1, workspace, 1, s))) return rc;
-        // rank search; a missed bracket is re-done exactly by the same kernel (see "deterministic recovery")
-        SX_DISPATCH_TV(dtype, vec, {
-            const T *p = static_cast<const T *>(images);
-            if (stage == SX_STAGE_ANGLE) select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<1, kThreads, 0, static_cast<cudaStream_t>(s)>>>(p, n, hw, 1, 0, workspace, 1);
-            else select_recover_kernel<T, VEC, SX_STAGE_CONC><<<1, kThreads, 0, static_cast<cudaStream_t>(s)>>>(p, n, hw, 1, 0, workspace, 1);
-        });
-        SX_LAUNCHED("macenko::select_recover_kernel");
-    }
+    if ((rc = fit_stages(images, dtype, n, h, w, workspace, 1, s))) return rc;
     Ws ws(workspace, 1);
     SX_CUDA(cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
     SX_CUDA(cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(s)));
     return SX_OK;
+}
+
+// fit_transform (src/stainx/base.py:L59-61 = fit(images) then transform(images)) in one call that reads the batch for
+// the moments ONCE: the per-image moments the transform needs go to slots 1..n, their sum -- bit for bit the moments a
+// pooled pass accumulates, see pool_moments_kernel -- to slot 0; the fit runs on slot 0, the transform pipeline on
+// slots 1..n without its moments pass.  Results equal sx_macenko_fit followed by sx_macenko_transform exactly.
+int sx_macenko_fit_transform(const void *images, int dtype, int64_t n, int64_t h, int64_t w, float *he, float *maxc, void *out, int out_dtype, float out_scale, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    SX_REQUIRE(n > 0 && h * w > 0, "empty reference batch");
+    SX_REQUIRE(he && maxc, "NULL output");
+    if (int rc = check_output(dtype, out, out_dtype, out_scale)) return rc;
+    const int64_t slots = n + 1;
+    SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(slots), "workspace too small (%lld < %lld: n + 1 slots)", (long long)workspace_bytes, (long long)sx_macenko_workspace_bytes(slots));
+    cudaStream_t stream = static_cast<cudaStream_t>(s);
+    int rc;
+    if ((rc = sx_macenko_begin(workspace, slots, s))) return rc;
+    if ((rc = sx_macenko_moments(images, dtype, n, h, w, 0, 1, workspace, slots, s))) return rc;
+    pool_moments_kernel<<<1, kPoolThreads, 0, stream>>>(workspace, slots, 1, n, workspace, slots, 0);
+    SX_LAUNCHED("macenko::pool_moments_kernel");
+    if ((rc = fit_stages(images, dtype, n, h, w, workspace, slots, s))) return rc;
+    Ws ws(workspace, slots);
+    SX_CUDA(cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    SX_CUDA(cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return transform_chains(images, dtype, n, h, w, 1, ws.fit, ws.fit + 6, out, out_dtype, out_scale, workspace, slots, stream, false);
+}
+
+// The same over the ranks of one NVLink node: sx_macenko_fit_peers on the sum of this rank's per-image moments, then the
+// transform of this rank's images with the pooled fit.  `workspace`: private device memory of n slots (n = 0: may be
+// NULL); he / maxc are required here (the transform reads them).  After a non-zero STATUS word 0 of own_buffer the caller
+// repeats the call with exact = 1, as for sx_macenko_fit_peers.
+int sx_macenko_fit_transform_peers(const void *images, int dtype, int64_t n, int64_t h, int64_t w, const void *peer_buffers_dev, void *own_buffer, int world, int rank, uint32_t first_epoch, int exact,
+                                   void *scratch, float *he, float *maxc, void *out, int out_dtype, float out_scale, void *workspace, int64_t workspace_bytes, sx_stream_t s) {
+    if (int rc = check_images(images, dtype, n, h, w)) return rc;
+    SX_REQUIRE(he && maxc, "NULL output");
+    const bool have = n > 0 && h * w > 0;
+    if (have) {
+        if (int rc = check_output(dtype, out, out_dtype, out_scale)) return rc;
+        SX_REQUIRE(workspace && workspace_bytes >= sx_macenko_workspace_bytes(n), "workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)sx_macenko_workspace_bytes(n));
+    }
+    int rc;
+    if (have) {
+        if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
+        if ((rc = sx_macenko_moments(images, dtype, n, h, w, 0, 0, workspace, n, s))) return rc;
+    }
+    if ((rc = fit_peers_impl(images, dtype, n, h, w, peer_buffers_dev, own_buffer, world, rank, first_epoch, exact, scratch, he, maxc, s, have ? workspace : nullptr))) return rc;
+    if (!have) return SX_OK;
+    return transform_chains(images, dtype, n, h, w, 0, he, maxc, out, out_dtype, out_scale, workspace, n, static_cast<cudaStream_t>(s), false);
 }
 
 }  // extern "C"

@@ -53,6 +53,14 @@ class Macenko(NormalizerTemplate):
     def _get_reference_params(self) -> tuple:
         return (self._stain_matrix, self._target_max_conc)
 
+    def fit_transform(self, images: Any) -> Any:
+        """``fit(images).transform(images)`` (base.py:L59-61) through the backend's one-call path: the batch is read
+        once for the moments of both steps; fitted parameters and output are those of the two separate calls."""
+        self._stain_matrix, self._target_max_conc, out = self._get_backend_impl().fit_transform(images, normalize_to_0_1=bool(self.normalize_to_0_1))
+        self._concentration_matrix = None
+        self._is_fitted = True
+        return out
+
     def transform(self, images: Any) -> Any:
         if not self._is_fitted:
             raise ValueError("Must call fit() before transform()")

@@ -363,3 +363,44 @@ def macenko_fit(images: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     with torch.cuda.device(dev):
         check(nv.lib().sx_macenko_fit(_ptr(images), _dtype_code(images), n, h, w, _ptr(he), _ptr(maxc), _ptr(ws), nbytes, _stream(dev)), "sx_macenko_fit")
     return he, maxc
+
+
+def macenko_fit_transform(images: torch.Tensor, unit: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``fit(images)`` then ``transform(images)`` with ONE moments pass over the batch (``sx_macenko_fit_transform``).
+    Returns HE (3, 2), maxC (2,) and the normalised batch -- exactly what the two separate calls return."""
+    n, h, w = _check_images(images)
+    if n == 0 or h * w == 0:
+        raise RuntimeError("Macenko fit needs at least one reference pixel")
+    dev = images.device
+    he = torch.empty((3, 2), dtype=torch.float32, device=dev)
+    maxc = torch.empty(2, dtype=torch.float32, device=dev)
+    out = _macenko_out(images, unit)
+    nbytes = int(nv.lib().sx_macenko_workspace_bytes(n + 1))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    scale = 1.0 / 255.0 if unit else 1.0
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_macenko_fit_transform(_ptr(images), _dtype_code(images), n, h, w, _ptr(he), _ptr(maxc), _ptr(out), _dtype_code(out), ctypes.c_float(scale), _ptr(ws), nbytes, _stream(dev)),
+              "sx_macenko_fit_transform")
+    return he, maxc, out
+
+
+def macenko_fit_transform_peers(images: torch.Tensor, exchange, scratch: torch.Tensor, unit: bool = False, exact: bool = False) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The sharded ``fit_transform`` of one NVLink node in one library call: pooled fit over every rank's images (five
+    fused exchanges; advances the exchange's epoch by 5), then this rank's images transformed with it.  ``images`` may
+    hold zero images."""
+    n, h, w = _check_images(images)
+    dev = exchange.buf.device
+    he = torch.empty((3, 2), dtype=torch.float32, device=dev)
+    maxc = torch.empty(2, dtype=torch.float32, device=dev)
+    out = _macenko_out(images, unit)
+    have = n > 0 and h * w > 0
+    nbytes = int(nv.lib().sx_macenko_workspace_bytes(n)) if have else 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if have else None
+    scale = 1.0 / 255.0 if unit else 1.0
+    first = exchange.epoch + 1
+    with torch.cuda.device(dev):
+        check(nv.lib().sx_macenko_fit_transform_peers(_ptr(images) if have else None, _dtype_code(images), n, h, w, ctypes.c_void_p(exchange.ptrs_dev), _ptr(exchange.buf), exchange.world, exchange.rank,
+                                                      first & 0xFFFFFFFF, int(exact), _ptr(scratch), _ptr(he), _ptr(maxc), _ptr(out) if have else None, _dtype_code(out), ctypes.c_float(scale),
+                                                      _ptr(ws) if have else None, nbytes, _stream(dev)), "sx_macenko_fit_transform_peers")
+    exchange.epoch += 5
+    return he, maxc, out

@@ -537,6 +537,60 @@ def test_macenko_per_image_independence_large_images(cuda, dtype):
     assert torch.equal(whole[4:7], n.transform(dev_src[4:7].contiguous()))
 
 
+@pytest.mark.parametrize("dtype,n,h,w,unit", [("u8", 5, 256, 320, False), ("f32", 3, 255, 257, True), ("f16", 4, 256, 256, True), ("f32", 24, 1024, 1024, True), ("u8", 30, 1024, 1024, True)])
+def test_macenko_fit_transform_is_fit_then_transform(cuda, dtype, n, h, w, unit):
+    """sx_macenko_fit_transform reads the batch once for the moments of both steps (per-image fixed-point moments,
+    summed, ARE the pooled moments): fitted parameters and output equal fit() followed by transform() bit for bit --
+    single chain, unaligned (scalar kernels) and multi-chain batches (> 64 MB)."""
+    from stainx_b200 import Macenko
+
+    x = he_batch(min(n, 8), h, w).repeat((n + 7) // 8, 1, 1, 1)[:n]
+    if dtype != "u8":
+        x = x.float() / 255.0
+    if dtype == "f16":
+        x = x.half()
+    x = x.to(cuda)
+    one = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=unit)
+    out = one.fit_transform(x)
+    two = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=unit).fit(x)
+    assert torch.equal(one._stain_matrix, two._stain_matrix) and torch.equal(one._target_max_conc, two._target_max_conc)
+    want = two.transform(x)
+    assert out.dtype == want.dtype and torch.equal(out, want)
+
+
+def test_macenko_fit_transform_vs_oracle(cuda, ox):
+    """... and against the CPU oracle's pooled fit + per-image transform (float32, [0, 1] output)."""
+    from stainx_b200 import Macenko
+
+    x = he_batch(4, 256, 256).float() / 255.0
+    n = Macenko(device=cuda, backend="torch_cuda", normalize_to_0_1=True)
+    out = n.fit_transform(x.to(cuda))
+    he, maxc = ox.macenko_fit(x.numpy())
+    assert np.abs(n._stain_matrix.cpu().numpy() - he).max() <= 1e-4
+    assert np.abs(n._target_max_conc.cpu().numpy() / maxc - 1).max() <= 1e-3
+    want = ox.macenko_transform(x.numpy(), he, maxc) / 255.0
+    assert np.abs(out.cpu().numpy() - want).max() <= 1e-3
+
+
+def test_macenko_fit_transform_native_argument_checks(cuda):
+    """The C-ABI entry point rejects a workspace sized for n instead of n + 1 slots and an empty batch."""
+    import ctypes
+
+    from stainx_b200 import _native as nv
+
+    x = (he_batch(2, 64, 64).float() / 255.0).to(cuda)
+    he, maxc, out = torch.empty(6, device=cuda), torch.empty(2, device=cuda), torch.empty_like(x)
+    nbytes = int(nv.lib().sx_macenko_workspace_bytes(2))
+    ws = torch.empty(int(nv.lib().sx_macenko_workspace_bytes(3)), dtype=torch.uint8, device=cuda)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    rc = nv.lib().sx_macenko_fit_transform(p(x), nv.SX_F32, 2, 64, 64, p(he), p(maxc), p(out), nv.SX_F32, ctypes.c_float(1.0), p(ws), nbytes, None)
+    assert rc != 0 and b"workspace too small" in nv.lib().sx_last_error()
+    rc = nv.lib().sx_macenko_fit_transform(p(x), nv.SX_F32, 0, 64, 64, p(he), p(maxc), p(out), nv.SX_F32, ctypes.c_float(1.0), p(ws), ws.numel(), None)
+    assert rc != 0 and b"empty reference batch" in nv.lib().sx_last_error()
+    rc = nv.lib().sx_macenko_fit_transform(p(x), nv.SX_F32, 2, 64, 64, p(he), p(maxc), p(out), nv.SX_U8, ctypes.c_float(1.0), p(ws), ws.numel(), None)
+    assert rc != 0 and b"output dtype" in nv.lib().sx_last_error()
+
+
 def test_macenko_self_reference_reconstructs(cuda):
     """With the image's own HE / maxC as target, the Beer-Lambert tile is reproduced (the stain
     plane projection of OD is OD itself up to 8-bit rounding)."""

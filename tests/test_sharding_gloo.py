@@ -68,6 +68,16 @@ def _worker(rank: int, world: int, port: int, case: str, out_dir: str):
             b = cpu_ops.cpu_backend(MacenkoCUDA, "cpu", reducer=red)
             he, maxc = b.compute_reference_stain_matrix(ref[rlo:rhi])
             result["he"], result["maxc"] = he.numpy(), maxc.numpy()
+        elif case == "macenko_fit_transform":
+            from stainx_b200 import Macenko
+
+            batch = torch.cat([he_tile(48, 48, 42), he_tile(48, 48, 7, 1.1), he_tile(48, 48, 8, 0.9)])
+            lo, hi = shard_range(batch.shape[0], rank, world)
+            n = Macenko(device="cpu", normalize_to_0_1=True, process_group="world")
+            n._backend_impl = cpu_ops.cpu_backend(MacenkoCUDA, "cpu", reducer=n._make_reducer())
+            result["out"] = n.fit_transform(batch[lo:hi]).numpy()  # pooled fit over BOTH ranks' tiles, then the own tiles
+            result["he"], result["maxc"] = n._stain_matrix.numpy(), n._target_max_conc.numpy()
+            result["range"] = (lo, hi)
         elif case == "broadcast":
             from stainx_b200 import Reinhard
 
@@ -130,6 +140,22 @@ def test_macenko_pooled_fit_sharded(tmp_path, ox):
         assert np.abs(r["he"] - he).max() <= 1e-4
         assert np.abs(r["maxc"] / maxc - 1).max() <= 1e-3
     assert np.array_equal(res[0]["he"], res[1]["he"]) and np.array_equal(res[0]["maxc"], res[1]["maxc"])
+
+
+def test_macenko_fit_transform_sharded(tmp_path, ox):
+    """Normalizer.fit_transform on a sharded batch = pooled fit over every rank's tiles + transform of the own tiles
+    (the backend's one-call path; with the CPU stand-in it takes the two-step branch of the same method)."""
+    res = _run("macenko_fit_transform", tmp_path)
+    batch = torch.cat([he_tile(48, 48, 42), he_tile(48, 48, 7, 1.1), he_tile(48, 48, 8, 0.9)])
+    he, maxc = ox.macenko_fit(batch.numpy())
+    want = ox.macenko_transform(batch.numpy(), he, maxc) / 255.0
+    assert np.array_equal(res[0]["he"], res[1]["he"]) and np.array_equal(res[0]["maxc"], res[1]["maxc"])
+    for r in res:
+        assert np.abs(r["he"] - he).max() <= 1e-4 and np.abs(r["maxc"] / maxc - 1).max() <= 1e-3
+        lo, hi = r["range"]
+        assert r["out"].dtype == np.float32 and r["out"].shape[0] == hi - lo
+        assert np.abs(r["out"] - want[lo:hi]).max() <= 1.0 / 255.0 + 1e-6  # uint8 in: one grey level (truncation edge)
+        assert (np.abs(r["out"] - want[lo:hi]) > 1e-6).mean() < 0.01
 
 
 def test_reference_fit_is_broadcast_from_src(tmp_path, ox):

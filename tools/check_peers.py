@@ -95,6 +95,35 @@ for label, use_peers in (("peers", True), ("nccl", False)):
     torch.cuda.synchronize()
     if rank == 0:
         print(f"macenko pooled fit 16x1024^2 f32 per rank, exchange={label}: {(time.perf_counter() - t0) / 20 * 1e6:.1f} us", flush=True)
+
+# Macenko fit_transform of a sharded batch: ONE library call per rank (sx_macenko_fit_transform_peers: per-image moments
+# once, their sum pooled over the ranks, five fused exchanges, transform of the own tiles).  Must equal fit() then
+# transform() on the same shard bit for bit, and the rank's slice of the single-device fit_transform of the whole batch.
+ft = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True, process_group="world")
+ft._backend_impl = mimpl  # share the exchange
+mimpl._exchange = mex if mex is not None else False
+shard = tiles[lo:hi].to(dev)
+got_ft = ft.fit_transform(shard)
+two_ft = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True, process_group="world")
+two_ft._backend_impl = mimpl
+want_two = two_ft.fit(shard).transform(shard)
+single_ft = Macenko(device=dev, backend="torch_cuda", normalize_to_0_1=True)
+want_single = single_ft.fit_transform(tiles.to(dev))[lo:hi]
+d_single = float((got_ft - want_single).abs().max()) if hi > lo else 0.0
+ft_ok = torch.equal(got_ft, want_two) and torch.equal(ft._stain_matrix, two_ft._stain_matrix) and torch.equal(ft._target_max_conc, two_ft._target_max_conc) and d_single <= 1e-5
+print(f"rank {rank}: macenko fit_transform (one call) == fit + transform: {torch.equal(got_ft, want_two)}; max|sharded-single| = {d_single:.2e}", flush=True)
+ok = ok and (ft_ok or mex is None)
+for label, fn in (("fit_transform (one call, shared moments pass)", lambda: ft.fit_transform(bigf)), ("fit + transform (two calls)", lambda: two_ft.fit(bigf).transform(bigf))):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        fn()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(f"macenko 16x1024^2 f32 per rank, {label}: {(time.perf_counter() - t0) / 20 * 1e6:.1f} us", flush=True)
 del bigf
 
 # StainNormalizerTransform(mode="batch") on a sharded batch: the rank that owns global image `batch_ref_index` fits,
