@@ -1695,7 +1695,7 @@ extern "C" int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_
 
 // One chain of the per-image pipeline for images [0, n) -> slots [slot0, slot0 + n) on `stream`.
 // with_moments = false: the slots already hold the images' moments (sx_macenko_fit_transform).
-static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments = true) {
+static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments = true, cudaEvent_t before_apply = nullptr) {
     const int64_t hw = h * w;
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
     SX_DISPATCH_TV(dtype, vec, {
@@ -1711,6 +1711,7 @@ static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int
     });
     note_launch(with_moments ? 6 : 5);
     SX_LAUNCHED("macenko::transform pipeline");
+    if (before_apply) SX_CUDA(cudaStreamWaitEvent(stream, before_apply, 0));  // he_ref / maxc_ref come from another stream
     return sx_macenko_apply(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream);
 }
 
@@ -1721,6 +1722,10 @@ struct SideStream {
     cudaStream_t stream[kMaxChains - 1] = {};
     cudaEvent_t fork = nullptr, join[kMaxChains - 1] = {};
     std::mutex mu;
+    // fit_transform: the pooled fit runs beside the transform's per-image chains (they do not need it before `apply`)
+    cudaStream_t fit_stream = nullptr;
+    cudaEvent_t fit_fork = nullptr, fit_done = nullptr;
+    std::mutex fit_mu;
 };
 static SideStream *side_stream() {
     static SideStream table[64];
@@ -1734,6 +1739,11 @@ static SideStream *side_stream() {
             if (cudaStreamCreateWithFlags(&s.stream[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
             if (cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
+        int lo_prio = 0, hi_prio = 0;  // the fit is a chain of short dependent kernels: let them jump the queue of streaming CTAs
+        if (cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&s.fit_stream, cudaStreamNonBlocking, hi_prio) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.fit_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
     return &s;
@@ -1932,13 +1942,13 @@ int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_
 // chain (~25 us per stage of dependent global round trips on a few SMs) overlap the streaming kernels of the other.  The
 // caller's stream forks into the side streams and joins them again, so the call keeps its stream-ordered,
 // host-asynchronous contract (and can be captured into a CUDA graph).
-static int transform_chains(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments) {
+static int transform_chains(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments, cudaEvent_t before_apply = nullptr) {
     const int64_t hw = h * w;
     const int64_t in_bytes = (int64_t)dtype_bytes(dtype) * 3 * hw, out_bytes = (int64_t)dtype_bytes(out_dtype) * 3 * hw;
     int chains = g_split;
     if (n * in_bytes < ((int64_t)64 << 20)) chains = 1;
     while (chains > 1 && n / chains < 4) --chains;
-    if (chains <= 1) return run_pipeline(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream, with_moments);
+    if (chains <= 1) return run_pipeline(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream, with_moments, before_apply);
     SideStream *side = side_stream();
     SX_REQUIRE(side != nullptr, "could not create the side streams");
     std::lock_guard<std::mutex> lock(side->mu);
@@ -1948,7 +1958,7 @@ static int transform_chains(const void *images, int dtype, int64_t n, int64_t h,
         const int64_t i0 = n * c / chains, i1 = n * (c + 1) / chains;
         cudaStream_t cs = c == 0 ? stream : side->stream[c - 1];
         if (c > 0) SX_CUDA(cudaStreamWaitEvent(cs, side->fork, 0));
-        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, slot0 + i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, slots, cs, with_moments);
+        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, slot0 + i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, slots, cs, with_moments, before_apply);
         if (r && !rc) rc = r;
         if (c > 0) {
             SX_CUDA(cudaEventRecord(side->join[c - 1], cs));
@@ -2085,13 +2095,27 @@ int sx_macenko_fit_transform(const void *images, int dtype, int64_t n, int64_t h
     int rc;
     if ((rc = sx_macenko_begin(workspace, slots, s))) return rc;
     if ((rc = sx_macenko_moments(images, dtype, n, h, w, 0, 1, workspace, slots, s))) return rc;
-    pool_moments_kernel<<<1, kPoolThreads, 0, stream>>>(workspace, slots, 1, n, workspace, slots, 0);
-    SX_LAUNCHED("macenko::pool_moments_kernel");
-    if ((rc = fit_stages(images, dtype, n, h, w, workspace, slots, s))) return rc;
+    // The fit (slot 0) forks onto its own stream: the transform's rank searches (slots 1..n) need nothing from it, only
+    // `apply` does, and the fit's ~18 short dependent kernels leave the SMs idle that the transform's streaming fills.
+    SideStream *side = side_stream();
+    SX_REQUIRE(side != nullptr, "could not create the side streams");
+    std::lock_guard<std::mutex> lock(side->fit_mu);
+    cudaStream_t fs = side->fit_stream;
+    SX_CUDA(cudaEventRecord(side->fit_fork, stream));
+    SX_CUDA(cudaStreamWaitEvent(fs, side->fit_fork, 0));
     Ws ws(workspace, slots);
-    SX_CUDA(cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    SX_CUDA(cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    return transform_chains(images, dtype, n, h, w, 1, ws.fit, ws.fit + 6, out, out_dtype, out_scale, workspace, slots, stream, false);
+    pool_moments_kernel<<<1, kPoolThreads, 0, fs>>>(workspace, slots, 1, n, workspace, slots, 0);
+    note_launch();
+    rc = cudaGetLastError() == cudaSuccess ? SX_OK : sx::fail(SX_ERR_CUDA, "macenko::pool_moments_kernel launch failed");
+    if (!rc) rc = fit_stages(images, dtype, n, h, w, workspace, slots, fs);
+    if (!rc && (cudaMemcpyAsync(he, ws.fit, 6 * sizeof(float), cudaMemcpyDeviceToDevice, fs) != cudaSuccess || cudaMemcpyAsync(maxc, ws.fit + 6, 2 * sizeof(float), cudaMemcpyDeviceToDevice, fs) != cudaSuccess))
+        rc = sx::fail(SX_ERR_CUDA, "copy of the fitted parameters failed");
+    SX_CUDA(cudaEventRecord(side->fit_done, fs));  // recorded on every path: the caller's stream always joins the fit stream
+    if (rc) {
+        SX_CUDA(cudaStreamWaitEvent(stream, side->fit_done, 0));
+        return rc;
+    }
+    return transform_chains(images, dtype, n, h, w, 1, ws.fit, ws.fit + 6, out, out_dtype, out_scale, workspace, slots, stream, false, side->fit_done);
 }
 
 // The same over the ranks of one NVLink node: sx_macenko_fit_peers on the sum of this rank's per-image moments, then the
@@ -2112,9 +2136,22 @@ int sx_macenko_fit_transform_peers(const void *images, int dtype, int64_t n, int
         if ((rc = sx_macenko_begin(workspace, n, s))) return rc;
         if ((rc = sx_macenko_moments(images, dtype, n, h, w, 0, 0, workspace, n, s))) return rc;
     }
-    if ((rc = fit_peers_impl(images, dtype, n, h, w, peer_buffers_dev, own_buffer, world, rank, first_epoch, exact, scratch, he, maxc, s, have ? workspace : nullptr))) return rc;
-    if (!have) return SX_OK;
-    return transform_chains(images, dtype, n, h, w, 0, he, maxc, out, out_dtype, out_scale, workspace, n, static_cast<cudaStream_t>(s), false);
+    if (!have) return fit_peers_impl(images, dtype, n, h, w, peer_buffers_dev, own_buffer, world, rank, first_epoch, exact, scratch, he, maxc, s, nullptr);
+    // as in sx_macenko_fit_transform: the fit (with its five exchanges) beside the transform's rank searches
+    cudaStream_t stream = static_cast<cudaStream_t>(s);
+    SideStream *side = side_stream();
+    SX_REQUIRE(side != nullptr, "could not create the side streams");
+    std::lock_guard<std::mutex> lock(side->fit_mu);
+    cudaStream_t fs = side->fit_stream;
+    SX_CUDA(cudaEventRecord(side->fit_fork, stream));
+    SX_CUDA(cudaStreamWaitEvent(fs, side->fit_fork, 0));
+    rc = fit_peers_impl(images, dtype, n, h, w, peer_buffers_dev, own_buffer, world, rank, first_epoch, exact, scratch, he, maxc, fs, workspace);
+    SX_CUDA(cudaEventRecord(side->fit_done, fs));
+    if (rc) {
+        SX_CUDA(cudaStreamWaitEvent(stream, side->fit_done, 0));
+        return rc;
+    }
+    return transform_chains(images, dtype, n, h, w, 0, he, maxc, out, out_dtype, out_scale, workspace, n, stream, false, side->fit_done);
 }
 
 }  // extern "C"

@@ -813,6 +813,43 @@ def test_macenko_transform_in_cuda_graph_and_on_side_stream(cuda):
     assert torch.equal(static_out, want)
 
 
+def test_macenko_fit_transform_in_cuda_graph_and_on_side_stream(cuda):
+    """sx_macenko_fit_transform forks the pooled fit onto a library-owned stream beside the transform chains and joins
+    before `apply`: ordered on a non-default caller stream, capturable into a CUDA graph, replay == eager."""
+    import ctypes
+
+    from stainx_b200 import ops
+
+    src = (he_batch(8, 1024, 1024).repeat(3, 1, 1, 1).float() / 255.0).to(cuda)  # 24 x 12.6 MB: three chains + the fit stream
+    he_w, maxc_w, want = ops.macenko_fit_transform(src, unit=True)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(s):
+        he_g, maxc_g, got = ops.macenko_fit_transform(src, unit=True)
+        total = got.sum() + he_g.sum()  # ordered after both joins on the same stream
+    s.synchronize()
+    assert torch.equal(got, want) and torch.equal(he_g, he_w) and torch.equal(maxc_g, maxc_w)
+    assert float(total) == float(want.sum() + he_w.sum())
+    static_out, he, maxc = torch.empty_like(src), torch.zeros(6, device=cuda), torch.zeros(2, device=cuda)
+    ws = torch.empty(int(nv_lib().sx_macenko_workspace_bytes(src.shape[0] + 1)), dtype=torch.uint8, device=cuda)
+
+    def enqueue():
+        rc = nv_lib().sx_macenko_fit_transform(ctypes.c_void_p(src.data_ptr()), 1, 24, 1024, 1024, ctypes.c_void_p(he.data_ptr()), ctypes.c_void_p(maxc.data_ptr()), ctypes.c_void_p(static_out.data_ptr()), 1,
+                                               ctypes.c_float(1.0 / 255.0), ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(cuda).cuda_stream))
+        assert rc == 0
+
+    enqueue()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        enqueue()
+    static_out.zero_()
+    he.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, want) and torch.equal(he.reshape(3, 2), he_w) and torch.equal(maxc, maxc_w)
+
+
 def nv_lib():
     from stainx_b200 import _native
 
