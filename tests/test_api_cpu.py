@@ -211,3 +211,24 @@ def test_bind_host_thread_is_best_effort():
     assert bind_host_thread_to_device(0) is None or isinstance(bind_host_thread_to_device(0), list)
     if bind_host_thread_to_device(0) is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_macenko_fit_transform_is_fit_then_transform_on_the_cpu_stand_in():
+    """Normalizer.fit_transform goes through the backend's fit_transform (one library call on the GPU); with a kernel
+    layer that lacks the one-call entry it must fall back to fit + transform with the same result and fitted state."""
+    from stainx_b200 import Macenko
+    from stainx_b200.backends.torch_cuda_backend import MacenkoCUDA
+    from tests import cpu_ops
+    from tests.helpers import he_batch
+
+    x = he_batch(3, 40, 48)
+    one = Macenko(device="cpu", normalize_to_0_1=True)
+    one._backend_impl = cpu_ops.cpu_backend(MacenkoCUDA, "cpu")
+    out = one.fit_transform(x)
+    assert one._is_fitted and out.dtype == torch.float32 and out.shape == x.shape
+    two = Macenko(device="cpu", normalize_to_0_1=True)
+    two._backend_impl = cpu_ops.cpu_backend(MacenkoCUDA, "cpu")
+    want = two.fit(x).transform(x)
+    assert torch.equal(out, want) and torch.equal(one._stain_matrix, two._stain_matrix) and torch.equal(one._target_max_conc, two._target_max_conc)
+    with pytest.raises(ValueError, match="NCHW with C=3"):
+        one.fit_transform(x[:, :2])
