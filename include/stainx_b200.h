@@ -297,6 +297,9 @@ int sx_macenko_fit_transform_peers(const void *images, int dtype, int64_t n, int
 int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm);
 int sx_reinhard_set_tuning(int ctas_per_sm);
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels);
+/* Timeline of the transform chains: enable != 0 arms it for the next multi-chain sx_macenko_transform; enable == 0
+ * synchronises the device and writes one line per kernel ("chain kernel completion-time-us") into buf. */
+int sx_macenko_trace(int enable, char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,7 @@ PROTOTYPES: dict[str, list] = {
     "sx_hm_set_tuning": [_int, _int, _int],
     "sx_reinhard_set_tuning": [_int],
     "sx_macenko_set_tuning": [_int, _i64],
+    "sx_macenko_trace": [_int, ctypes.c_char_p, _i64],
 }
 _RESTYPES = {
     "sx_last_error": ctypes.c_char_p,

@@ -72,6 +72,11 @@ void prefer_l1_impl(const void *kernel, int block_threads, size_t dyn_smem) {
     const size_t need = (size_t)(ctas < 1 ? 1 : ctas) * (fa.sharedSizeBytes + dyn_smem + 1024);
     int pct = (int)((need * 100 + (size_t)max_smem - 1) / (size_t)max_smem);
     if (pct > 100) pct = 100;
+    static const int forced = [] {  // SX_L1_PCT=<0..100>: the same carve-out for every kernel (A/B measurements)
+        const char *e = getenv("SX_L1_PCT");
+        return e && e[0] ? atoi(e) : -1;
+    }();
+    if (forced >= 0 && forced <= 100) pct = forced;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
 }
 

@@ -25,8 +25,10 @@
 // distinct value (the normal case: a bracket is ~1 % of the data), else it is interpolated inside
 // a cell of width <= bracket/4096.  The nearest-rank index is exact: ranks below the bracket are
 // counted, not estimated.
+#include <cstdio>
 #include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "common.cuh"
 
@@ -1623,6 +1625,7 @@ static int g_ctas_per_sm = 8;  // per-image kernels (sample, reconstruction): CT
                                // 64 x 1024^2 float32 takes 259 us with 3 or 8 and 283 us with 4 (640 CTAs = 4.3 per SM: uneven last wave)
 static int g_split = 3;          // chains (streams) a large batch is split into
 static int g_phase_kernels = 0;  // development: sx_macenko_transform through the phase-level API (one launch per step)
+static int g_helper_streams = 1; // per-image kernels of a multi-chain transform on high-priority helper streams (see ChainHelper)
 
 static PassGeom make_geom(int64_t n, int64_t hw, int kpix, int64_t groups_override = -1) {
     PassGeom g;
@@ -1693,26 +1696,83 @@ static bool images_vec_ok(const void *images, const void *out, int dtype, int64_
 
 extern "C" int sx_macenko_apply(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, sx_stream_t stream_);
 
+// Development (sx_macenko_trace, inert unless SX_ENABLE_TUNING=1): completion time of every kernel of the transform
+// chains, from timing events recorded behind each launch -- the only timeline tool on a box without nsys.
+struct TraceRec { const char *what; int chain; cudaEvent_t ev; };
+static std::vector<TraceRec> g_trace;
+static cudaEvent_t g_trace_base = nullptr;
+static int g_trace_on = 0;
+static void trace_mark(const char *what, int chain, cudaStream_t s) {
+    if (!g_trace_on) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess || cudaEventRecord(e, s) != cudaSuccess) return;
+    g_trace.push_back({what, chain, e});
+}
+
+// Helper stream of one chain (library-owned, HIGH priority) and the events that tie it to the chain's stream.
+// The streaming kernels of a chain are single-wave grids sized to the resident capacity of the device: while one runs
+// there is no free CTA slot, and when it drains the hardware hands the slots to whatever is pending -- in launch order
+// among streams of equal priority.  With the per-image kernels on the chains' own streams a chain's `mid` / `select`
+// kernels therefore queue behind the streaming kernels the other chains already have pending, and the chains drift into
+// lockstep (the timeline of tools/trace_mk.py: all three `select` kernels of a stage complete within a few us of each
+// other, with nothing else to run beside them): the transform took the same 780-795 us with 2, 3 or 4 chains, against
+// 721 us for its four streaming kernels alone.  On a high-priority stream a chain's small kernels take the first slots
+// that drain, run beside another chain's streaming kernel, and that chain's next streaming kernel is ready when its turn
+// comes.  Same kernels on the same data, so no bit changes (tools/probe_helper.py: torch.equal over all settings);
+// measured on 64 x 1024^2 float32 781 -> 764 us (repeat: 785 -> 766), 32 x 2048^2 uint8 -> float32 1096 -> 1069 us
+// (1094 -> 1062); uint8 -> uint8 and fit_transform unchanged within the 1-2 % run-to-run spread.
+struct ChainHelper {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+};
+
 // One chain of the per-image pipeline for images [0, n) -> slots [slot0, slot0 + n) on `stream`.
 // with_moments = false: the slots already hold the images' moments (sx_macenko_fit_transform).
-static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments = true, cudaEvent_t before_apply = nullptr) {
+// hp != nullptr: the per-image kernels go to hp->stream, ordered against `stream` by hp->ev in both directions.
+static int run_pipeline(const void *images, int dtype, int64_t n, int64_t h, int64_t w, int64_t slot0, const float *he_ref, const float *maxc_ref, void *out, int out_dtype, float out_scale, void *workspace, int64_t slots, cudaStream_t stream, bool with_moments = true, cudaEvent_t before_apply = nullptr, const ChainHelper *hp = nullptr, int chain = 0) {
     const int64_t hw = h * w;
     const bool vec = images_vec_ok(images, nullptr, dtype, hw);
+    cudaStream_t small = hp ? hp->stream : stream;
+    cudaError_t herr = cudaSuccess;
+    int hop_no = 0;
+    // what `to` enqueues next runs after everything enqueued on `from` so far
+    auto hop = [&](cudaStream_t from, cudaStream_t to) {
+        if (!hp) return;
+        cudaEvent_t e = hp->ev[hop_no++];
+        if (herr == cudaSuccess) herr = cudaEventRecord(e, from);
+        if (herr == cudaSuccess) herr = cudaStreamWaitEvent(to, e, 0);
+    };
     SX_DISPATCH_TV(dtype, vec, {
         const T *p = static_cast<const T *>(images);
         const RowGeom g = make_row_geom<T, VEC>(n, hw, slot0, 0);
         if (with_moments) t_moments_kernel<T, VEC><<<pipeline_grid(t_moments_kernel<T, VEC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
-        mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
+        trace_mark("moments", chain, stream);
+        hop(stream, small);
+        mid_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)(n * kMidParts), kThreads, 0, small>>>(p, hw, slot0, workspace, slots);
+        trace_mark("mid_angle", chain, small);
+        hop(small, stream);
         t_resolve_kernel<T, VEC, SX_STAGE_ANGLE><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_ANGLE>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
-        select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)n, kThreads, 0, stream>>>(p, n, hw, 0, slot0, workspace, slots);
-        mid_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)(n * kMidParts), kThreads, 0, stream>>>(p, hw, slot0, workspace, slots);
+        trace_mark("resolve_angle", chain, stream);
+        hop(stream, small);
+        select_recover_kernel<T, VEC, SX_STAGE_ANGLE><<<(unsigned)n, kThreads, 0, small>>>(p, n, hw, 0, slot0, workspace, slots);
+        trace_mark("select_angle", chain, small);
+        mid_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)(n * kMidParts), kThreads, 0, small>>>(p, hw, slot0, workspace, slots);
+        trace_mark("mid_conc", chain, small);
+        hop(small, stream);
         t_resolve_kernel<T, VEC, SX_STAGE_CONC><<<pipeline_grid(t_resolve_kernel<T, VEC, SX_STAGE_CONC>, g.total_rows), kThreads, 0, stream>>>(p, g, workspace, slots);
-        select_recover_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)n, kThreads, 0, stream>>>(p, n, hw, 0, slot0, workspace, slots);
+        trace_mark("resolve_conc", chain, stream);
+        hop(stream, small);
+        select_recover_kernel<T, VEC, SX_STAGE_CONC><<<(unsigned)n, kThreads, 0, small>>>(p, n, hw, 0, slot0, workspace, slots);
+        trace_mark("select_conc", chain, small);
+        hop(small, stream);
     });
     note_launch(with_moments ? 6 : 5);
     SX_LAUNCHED("macenko::transform pipeline");
+    if (herr != cudaSuccess) return sx::fail(SX_ERR_CUDA, "macenko::transform pipeline: helper-stream event failed: %s", cudaGetErrorString(herr));
     if (before_apply) SX_CUDA(cudaStreamWaitEvent(stream, before_apply, 0));  // he_ref / maxc_ref come from another stream
-    return sx_macenko_apply(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream);
+    const int rc = sx_macenko_apply(images, dtype, n, h, w, slot0, he_ref, maxc_ref, out, out_dtype, out_scale, workspace, slots, stream);
+    trace_mark("apply", chain, stream);
+    return rc;
 }
 
 // Side stream of the calling thread's current device (created on first use, never destroyed: the
@@ -1726,6 +1786,7 @@ struct SideStream {
     cudaStream_t fit_stream = nullptr;
     cudaEvent_t fit_fork = nullptr, fit_done = nullptr;
     std::mutex fit_mu;
+    ChainHelper helper[kMaxChains];  // per chain: high-priority stream of its per-image kernels (see ChainHelper)
 };
 static SideStream *side_stream() {
     static SideStream table[64];
@@ -1742,6 +1803,11 @@ static SideStream *side_stream() {
         int lo_prio = 0, hi_prio = 0;  // the fit is a chain of short dependent kernels: let them jump the queue of streaming CTAs
         if (cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithPriority(&s.fit_stream, cudaStreamNonBlocking, hi_prio) != cudaSuccess) return nullptr;
+        for (int c = 0; c < kMaxChains; ++c) {
+            if (cudaStreamCreateWithPriority(&s.helper[c].stream, cudaStreamNonBlocking, hi_prio) != cudaSuccess) return nullptr;
+            for (cudaEvent_t &e : s.helper[c].ev)
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
         if (cudaEventCreateWithFlags(&s.fit_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&s.fit_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -1755,13 +1821,42 @@ extern "C" {
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels) {
     if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
     if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
-    if (phase_kernels >= 0) {  // bit 0: phase-level chain; bit 1: force sample-bracket misses (recovery tests); bits 4..: number of chains (0: default)
+    if (phase_kernels >= 0) {  // bit 0: phase-level chain; bit 1: force sample-bracket misses (recovery tests); bit 2: no helper streams; bits 4..: number of chains (0: default)
         g_phase_kernels = (phase_kernels & 1) != 0;
+        g_helper_streams = ((phase_kernels >> 2) & 1) == 0;
         const int force = (int)((phase_kernels >> 1) & 1);
         SX_CUDA(cudaMemcpyToSymbol(g_force_miss, &force, sizeof(int)));
         const int chains = (int)(phase_kernels >> 4);
         g_split = chains > 0 ? (chains < kMaxChains ? chains : kMaxChains) : 3;
     }
+    return SX_OK;
+}
+
+// Development hook: enable != 0 arms the trace for the next multi-chain transform; enable == 0 synchronises the device and
+// writes one line per kernel ("chain kernel completion-time-in-us", relative to the start of the call) into buf.
+int sx_macenko_trace(int enable, char *buf, int64_t cap) {
+    if (!tuning_enabled()) return sx::fail(SX_ERR_UNSUPPORTED, "tuning hooks are disabled (set SX_ENABLE_TUNING=1 before loading the library)");
+    if (enable) {
+        for (TraceRec &r : g_trace) cudaEventDestroy(r.ev);
+        g_trace.clear();
+        if (g_trace_base) cudaEventDestroy(g_trace_base);
+        g_trace_base = nullptr;
+        g_trace_on = 1;
+        return SX_OK;
+    }
+    g_trace_on = 0;
+    SX_CUDA(cudaDeviceSynchronize());
+    int64_t used = 0;
+    if (buf && cap > 0) buf[0] = 0;
+    for (TraceRec &r : g_trace) {
+        float ms = -1.0f;
+        if (g_trace_base) cudaEventElapsedTime(&ms, g_trace_base, r.ev);
+        if (buf && used < cap - 64) used += snprintf(buf + used, (size_t)(cap - used), "%d %s %.1f\n", r.chain, r.what, ms * 1e3f);
+        cudaEventDestroy(r.ev);
+    }
+    g_trace.clear();
+    if (g_trace_base) cudaEventDestroy(g_trace_base);
+    g_trace_base = nullptr;
     return SX_OK;
 }
 
@@ -1953,12 +2048,14 @@ static int transform_chains(const void *images, int dtype, int64_t n, int64_t h,
     SX_REQUIRE(side != nullptr, "could not create the side streams");
     std::lock_guard<std::mutex> lock(side->mu);
     SX_CUDA(cudaEventRecord(side->fork, stream));
+    if (g_trace_on && g_trace_base == nullptr && cudaEventCreate(&g_trace_base) == cudaSuccess) cudaEventRecord(g_trace_base, stream);
     int rc = SX_OK;
     for (int c = 0; c < chains; ++c) {  // chain 0 on the caller's stream, chain c > 0 on side stream c - 1
         const int64_t i0 = n * c / chains, i1 = n * (c + 1) / chains;
         cudaStream_t cs = c == 0 ? stream : side->stream[c - 1];
         if (c > 0) SX_CUDA(cudaStreamWaitEvent(cs, side->fork, 0));
-        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, slot0 + i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, slots, cs, with_moments, before_apply);
+        const int r = run_pipeline(static_cast<const char *>(images) + i0 * in_bytes, dtype, i1 - i0, h, w, slot0 + i0, he_ref, maxc_ref, static_cast<char *>(out) + i0 * out_bytes, out_dtype, out_scale, workspace, slots, cs, with_moments, before_apply,
+                                   g_helper_streams ? &side->helper[c] : nullptr, c);
         if (r && !rc) rc = r;
         if (c > 0) {
             SX_CUDA(cudaEventRecord(side->join[c - 1], cs));
