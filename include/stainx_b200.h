@@ -170,8 +170,9 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
  * COUNTERS, VMIN, VMAX) -- with all-reduces, or on one NVLink node with sx_macenko_peer_combine.
  * sx_macenko_transform does not use the phase functions one by one: it chains lean streaming kernels
  * and per-image kernels of its own (eight launches per chain; batches of >= 64 MB run as up to three
- * part-batch chains, all but the first on library-owned side streams that it forks from and joins into
- * `stream`, so the call stays stream-ordered and graph-capturable). */
+ * part-batch chains, all but the first on library-owned side streams, and every chain's four per-image
+ * kernels on a library-owned high-priority stream of its own; all of them are forked from and joined
+ * into `stream`, so the call stays stream-ordered and graph-capturable). */
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
     SX_REGION_MOMENTS = 0,  /* int64   [slots][12]   reduce: SUM.  Fixed-point (scale 2^22) count and shifted first / second moments
@@ -293,7 +294,7 @@ int sx_macenko_fit_transform_peers(const void *images, int dtype, int64_t n, int
  * they set process-global state, are not thread-safe, and return SX_ERR_UNSUPPORTED (changing
  * nothing) unless SX_ENABLE_TUNING=1 was in the environment before their first call.  With the
  * hooks inert the library has no mutable global state besides per-device cached attributes, the
- * launch counter, the side streams of sx_macenko_transform and the peer status record above. */
+ * launch counter, the side / helper streams of sx_macenko_transform and the peer status record above. */
 int sx_hm_set_tuning(int hist_byte_counters, int hist_ctas_per_sm, int apply_ctas_per_sm);
 int sx_reinhard_set_tuning(int ctas_per_sm);
 int sx_macenko_set_tuning(int ctas_per_sm, int64_t phase_kernels);
