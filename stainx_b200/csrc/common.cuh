@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/stainx_b200.h"
 
 namespace sx {
@@ -74,6 +76,23 @@ void prefer_l1_impl(const void *kernel, int block_threads, size_t dyn_smem);
 template <typename K>
 inline void prefer_l1(K kernel, int block_threads, size_t dyn_smem = 0) {
     prefer_l1_impl(reinterpret_cast<const void *>(kernel), block_threads, dyn_smem);
+}
+
+// ---- opt-in to more than 48 KB of dynamic shared memory ---------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: it is set once per kernel
+// instantiation and device (a process that drives two GPUs must set it on both), not on every launch (a
+// driver call of ~1 us on paths that are launch-bound for small batches).
+template <typename K>
+inline int allow_big_smem(K kernel, int bytes) {
+    static std::atomic<bool> done[64];  // one array per kernel instantiation, indexed by the current device
+    int d = 0;
+    SX_CUDA(cudaGetDevice(&d));
+    if (d < 0 || d >= 64) d = 0;
+    if (!done[d].load(std::memory_order_acquire)) {
+        SX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done[d].store(true, std::memory_order_release);
+    }
+    return SX_OK;
 }
 
 // ---- programmatic dependent launch -------------------------------------------------------------

@@ -1092,11 +1092,7 @@ using namespace sx::hm;
 
 template <typename Cfg>
 static int launch_lane_tma_cfg(const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_tma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        attr_set = true;
-    }
+    if (int rc = allow_big_smem(hist_u8_planar_lane_tma_kernel<Cfg>, Cfg::kSmem)) return rc;
     const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
     const unsigned grid = stream_grid(3 * n * tiles, 1);
     hist_u8_planar_lane_tma_kernel<Cfg><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(images, hw, n, tiles, cnt);
@@ -1104,11 +1100,7 @@ static int launch_lane_tma_cfg(const uint8_t *images, int64_t hw, int64_t n, uns
 }
 template <typename Cfg>
 static int launch_lane_pw_cfg(const uint8_t *images, int64_t hw, int64_t n, unsigned long long *cnt, cudaStream_t stream, bool pdl) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SX_CUDA(cudaFuncSetAttribute(hist_u8_planar_lane_pw_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        attr_set = true;
-    }
+    if (int rc = allow_big_smem(hist_u8_planar_lane_pw_kernel<Cfg>, Cfg::kSmem)) return rc;
     const int64_t tiles = max_i64(1, (hw / 16 + Cfg::kTileVecs - 1) / Cfg::kTileVecs);
     const unsigned grid = stream_grid(3 * n * tiles, 1);
     // (Register-fed lane-private counters were measured again in this form: five counting warps, no ring, every

@@ -572,7 +572,8 @@ template <typename T, bool VEC, bool TAB>
 static int launch_apply(const T *p, T *o, int64_t n, int64_t hw, const float *src_mean, const float *src_std, const float *ref_mean, const float *ref_std, cudaStream_t stream) {
     constexpr int kPix = VEC ? Px<T>::kPix : 1;
     const size_t smem = TAB ? ((sizeof(T) != 1 ? kInvSfuF32 : kInvSfuU8) >= 3 ? kFwdTableBytes : kTableBytes) : 0;
-    if (TAB) SX_CUDA(cudaFuncSetAttribute(apply_kernel<T, VEC, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytes));
+    if (TAB)
+        if (int rc = allow_big_smem(apply_kernel<T, VEC, TAB>, kTableBytes)) return rc;
     const unsigned grid = stream_grid((n * hw / kPix + kThreads - 1) / kThreads, g_ctas_per_sm);
     prefer_l1(apply_kernel<T, VEC, TAB>, kThreads, smem);
     // A plain launch on purpose.  As a programmatic dependent launch this kernel was measured 80 us SLOWER

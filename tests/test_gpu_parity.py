@@ -813,6 +813,33 @@ def test_macenko_transform_in_cuda_graph_and_on_side_stream(cuda):
     assert torch.equal(static_out, want)
 
 
+def test_macenko_chain_layout_does_not_change_a_bit(cuda):
+    """The multi-chain transform runs its per-image kernels on high-priority helper streams.  Chains and
+    helper streams only change WHERE the same kernels run: one chain, three chains with the small kernels on the
+    chains' own streams, and the default (three chains + helper streams) must agree bit for bit, uint8 and float32."""
+    import os
+
+    from stainx_b200 import _native as nv
+    from stainx_b200 import ops
+
+    os.environ["SX_ENABLE_TUNING"] = "1"  # read on the first call of a development hook
+    lib = nv.lib()
+    g = torch.Generator(device=cuda).manual_seed(21)
+    src = torch.cat([he_batch(4, 1024, 1024).to(cuda).repeat(3, 1, 1, 1), (torch.rand((12, 3, 1024, 1024), device=cuda, generator=g) * 255).to(torch.uint8)])  # 75 MB
+    he, maxc = ops.macenko_fit(src[:1])
+    want = ops.macenko_transform(src, he, maxc, unit=False)
+    srcf = src[:8].float() / 255.0  # 100 MB of float32: two chains of four images
+    wantf = ops.macenko_transform(srcf, he, maxc, unit=True)
+    assert lib.sx_macenko_set_tuning(-1, 0) == 0, "development hooks are not enabled"
+    try:
+        for bits in ((1 << 4), (3 << 4) | 4, (2 << 4), (4 << 4)):  # chains << 4 | 4: no helper streams
+            assert lib.sx_macenko_set_tuning(-1, bits) == 0
+            assert torch.equal(ops.macenko_transform(src, he, maxc, unit=False), want), bits
+            assert torch.equal(ops.macenko_transform(srcf, he, maxc, unit=True), wantf), bits
+    finally:
+        lib.sx_macenko_set_tuning(-1, 0)
+
+
 def test_macenko_fit_transform_in_cuda_graph_and_on_side_stream(cuda):
     """sx_macenko_fit_transform forks the pooled fit onto a library-owned stream beside the transform chains and joins
     before `apply`: ordered on a non-default caller stream, capturable into a CUDA graph, replay == eager."""
