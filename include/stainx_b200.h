@@ -172,7 +172,9 @@ int sx_reinhard_fit(const void *images, int dtype, int64_t n, int64_t h, int64_t
  * and per-image kernels of its own (eight launches per chain; batches of >= 64 MB run as up to three
  * part-batch chains, all but the first on library-owned side streams, and every chain's four per-image
  * kernels on a library-owned high-priority stream of its own; all of them are forked from and joined
- * into `stream`, so the call stays stream-ordered and graph-capturable). */
+ * into `stream`, so the call stays stream-ordered and graph-capturable; the library streams are per device,
+ * so while one thread CAPTURES such a call into a CUDA graph no other thread may enqueue a multi-chain Macenko
+ * call on the same device -- the shared streams are in capture mode until the capture ends). */
 enum sx_macenko_stage { SX_STAGE_ANGLE = 0, SX_STAGE_CONC = 1 };
 enum sx_macenko_region_id {
     SX_REGION_MOMENTS = 0,  /* int64   [slots][12]   reduce: SUM.  Fixed-point (scale 2^22) count and shifted first / second moments
