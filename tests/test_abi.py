@@ -83,3 +83,67 @@ def test_product_never_imports_the_oracle():
     pkg = ROOT / "stainx_b200"
     offenders = [str(p) for p in pkg.rglob("*") if p.suffix in {".py", ".cu", ".cuh", ".h"} and re.search(r"(from|import)\s+oracle|oracle[/.]|stainx_oracle|\box_[a-z]", p.read_text())]
     assert not offenders, offenders
+
+
+def _integration_stub_source() -> str:
+    """The ``stainx_cuda_torch/__init__.py`` replacement printed in INTEGRATION.md section 2, pointed at the in-tree library."""
+    from stainx_b200 import _native
+
+    text = (ROOT / "INTEGRATION.md").read_text()
+    m = re.search(r"```python\n(# src/stainx_cuda_torch/__init__\.py\n.*?)```", text, flags=re.S)
+    assert m, "INTEGRATION.md no longer holds the stub"
+    src = m.group(1)
+    assert 'ctypes.CDLL("libstainx_b200.so")' in src
+    return src.replace('ctypes.CDLL("libstainx_b200.so")', f'ctypes.CDLL({str(_native.LIB_PATH)!r})')
+
+
+def test_integration_stub_is_valid_and_matches_the_bindings(tmp_path):
+    """The stub a reference maintainer would add must at least import against the built library, expose
+    the reference's four names, and declare the same argument lists as this package's own bindings."""
+    import importlib.util
+
+    import torch
+
+    from stainx_b200 import _native
+
+    pkg = tmp_path / "stainx_cuda_torch"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text(_integration_stub_source())
+    spec = importlib.util.spec_from_file_location("_sx_stub_under_test", pkg / "__init__.py")
+    stub = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stub)
+    assert stub.FUNCTIONS_AVAILABLE is True
+    for name in ("histogram_matching", "reinhard", "macenko", "macenko_fast"):  # csrc/bindings.cpp:L27-35
+        assert callable(getattr(stub, name))
+    for fn in ("sx_hm_transform", "sx_reinhard_transform", "sx_macenko_transform"):
+        ours = _native.PROTOTYPES[fn]
+        theirs = getattr(stub._lib, fn).argtypes
+        assert len(theirs) == len(ours), fn
+        assert [ctypes.sizeof(a) for a in theirs] == [ctypes.sizeof(a) for a in ours], fn
+    with pytest.raises(AssertionError):  # host tensors are refused before any native call (the reference: TORCH_CHECK is_cuda)
+        stub.reinhard(torch.zeros(1, 3, 8, 8), torch.zeros(3), torch.ones(3))
+
+
+@pytest.mark.skipif(not Path("/root/reference/src/stainx/__init__.py").exists(), reason="the reference is only present in the build container")
+def test_integration_stub_turns_on_the_reference_cuda_backend(tmp_path):
+    """With the stub on the path in front of the reference's own (unbuilt) extension package, the UNMODIFIED reference
+    sees CUDA_AVAILABLE and builds its torch_cuda backend classes (a fresh interpreter: the reference caches the probe)."""
+    import subprocess
+    import sys
+
+    pkg = tmp_path / "stainx_cuda_torch"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text(_integration_stub_source())
+    code = (
+        "import sys; sys.path[:0] = [%r, '/root/reference/src']\n"
+        "import stainx_cuda_torch, stainx\n"
+        "from stainx.backends import torch_cuda_backend as b\n"
+        "assert stainx_cuda_torch.__file__.startswith(%r), stainx_cuda_torch.__file__\n"
+        "assert b.CUDA_AVAILABLE is True\n"
+        "for cls in (b.ReinhardCUDA, b.MacenkoCUDA, b.HistogramMatchingCUDA): cls('cuda')\n"
+        "n = stainx.Reinhard(device='cuda', backend='torch_cuda')\n"
+        "assert n.backend == 'torch_cuda'\n"
+        "print('stub ok')\n"
+    ) % (str(tmp_path), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "stub ok" in r.stdout, r.stderr[-2000:]
